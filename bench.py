@@ -1,0 +1,321 @@
+#!/usr/bin/env python3
+"""bench.py -- CZ-fidelity Lindblad gate evaluations per second on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W            this repo's CUDA path
+  python bench.py --impl reference --gpus N ...            the reference's CPU path (oracle port of
+                                                           the QuTiP mesolve path) on the host cores
+
+One "step" = one pass of the hot path over one batch of synthetic pulse candidates.  Workload
+(BASELINE.json configs[1], SURVEY.md section 8d "config 2"): Jandura-Pupillo bang-bang CZ, 5 piecewise-constant
+segments, two-atom 3-level Lindblad model with the medium apparatus's noise rates; per GPU
+65,536 candidates drawn inside the reference optimiser's bounds (RG/optimize_cz_gate.py:576-587),
+seed 1234 + rank.  Every rank evaluates its own shard (no data-path collective; the only
+exchange is the all-gather of per-candidate scores, timed inside the step) -> "scaling": "weak".
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "cz_lindblad_gate_evals_per_sec"
+UNIT = "evals/s"
+B_PER_GPU = 65536
+N_SEG = 5
+
+
+# ---------------------------------------------------------------------------- workload
+def medium_apparatus_scalars():
+    """Ω, V, δ1 and the ten noise rates of the reference's medium apparatus with full noise
+    (RG/optimize_cz_gate.py:196-213), as produced by the reference's own prologue and stored in
+    tests/golden/reference_cases.json (case bb5_noisy)."""
+    with open(os.path.join(ROOT, "tests", "golden", "reference_cases.json")) as f:
+        cases = json.load(f)["cases"]
+    c = next(c for c in cases if c["name"] == "bb5_noisy")
+    return c["scalars"], c["rates"]
+
+
+def collapsed(r):
+    b = r.get("branching_1", 0.5)
+    return (r["gamma_r"] * b,
+            r["gamma_r"] * (1 - b) + r["gamma_bbr"] + r["gamma_loss_antitrap"]
+            + r["gamma_loss_background"] + r["gamma_leakage"],
+            r["gamma_phi_laser"] + r["gamma_phi_thermal"] + r["gamma_phi_zeeman"],
+            r["gamma_scatter_intermediate"], r["mJ_leakage_rate"])
+
+
+def make_candidates(n, seed):
+    """Bang-bang candidates inside the reference bounds: omega_tau~U[5,40], 4 sorted switching
+    fractions~U[0.01,0.99], 5 phases~U[-pi,pi]; segment table built as evolve_bangbang_jp does
+    (RG/simulation.py:1859-1924)."""
+    sc, rates = medium_apparatus_scalars()
+    rng = np.random.default_rng(seed)
+    Om, V, d1 = sc["Omega"], sc["V"], sc["delta_1"]
+    ot = rng.uniform(5.0, 40.0, n)
+    fr = np.sort(rng.uniform(0.01, 0.99, (n, N_SEG - 1)), axis=1)
+    ph = rng.uniform(-np.pi, np.pi, (n, N_SEG))
+    bounds = np.concatenate([np.zeros((n, 1)), fr * ot[:, None], ot[:, None]], axis=1) / Om
+    segs = np.empty((n, N_SEG, 4))
+    segs[:, :, 0] = np.diff(bounds, axis=1)
+    segs[:, :, 1] = Om * np.cos(ph)
+    segs[:, :, 2] = Om * np.sin(ph)
+    segs[:, :, 3] = 0.0
+    pts = np.zeros((n, 12))
+    pts[:, 0], pts[:, 1] = V, d1
+    pts[:, 4:9] = collapsed(rates)
+    return pts, segs, dict(Omega=Om, V=V, delta_1=d1, rates=rates, omega_tau=ot)
+
+
+# ---------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                    "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                for line in o.strip().splitlines():
+                    self.rows.append([x.strip() for x in line.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------- CPU (reference) path
+def _cpu_one(args):
+    """One gate evaluation the way the reference does it: zvode/Adams at atol=1e-10, rtol=1e-8,
+    nsteps=10000, 51 tlist points per bang-bang segment, 4 inputs (RG/simulation.py:1890-1924)."""
+    from oracle import rydcz_oracle as orc
+    pt, seg = args
+    rates = orc.NoiseRates(gamma_r=2 * pt[4], gamma_bbr=pt[5] - pt[4], gamma_phi_laser=pt[6],
+                           gamma_scatter_intermediate=pt[7])
+    segs = [orc.Segment(s[0], complex(s[1], s[2]), s[3], 51) for s in seg if s[0] >= 1e-18]
+    fin = orc.propagate(3, segs, pt[0], pt[1], rates, mode="zvode", nsteps=10000)
+    fid, avg, info = orc.cz_fidelity_mixed(3, fin, "compat")
+    return avg
+
+
+def cpu_path_rate(pts, segs, n_sample, procs):
+    """Evaluate the first n_sample candidates with the oracle's zvode restatement on `procs`
+    host processes; returns evals/s."""
+    import multiprocessing as mp
+    work = [(pts[i], segs[i]) for i in range(n_sample)]
+    t0 = time.perf_counter()
+    if procs > 1:
+        with mp.get_context("fork").Pool(procs) as pool:
+            pool.map(_cpu_one, work, chunksize=1)
+    else:
+        for w in work:
+            _cpu_one(w)
+    dt = time.perf_counter() - t0
+    return n_sample / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    pts, segs, _ = make_candidates(B_PER_GPU, 1234)
+    n_sample = max(cores, 8)
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_path_rate(pts, segs, min(cores, 4), cores)
+    times = []
+    for k in range(args.steps):
+        _, dt = cpu_path_rate(pts[k * n_sample:], segs[k * n_sample:], n_sample, cores)
+        times.append(dt)
+    total = sum(times)
+    value = args.steps * n_sample / total
+    sample = (f"{n_sample} of the {B_PER_GPU} bang-bang candidates per step, oracle zvode/Adams restatement of the "
+              f"reference's mesolve path (QuTiP itself is not installable), {cores} processes")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "jp_bangbang_5seg_lindblad_3level", "candidates_per_step": n_sample,
+                   "host_cores": cores},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------- CUDA path
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from noisyquantumsimulator_b200.engine import Evaluator
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ev = Evaluator(local_rank)
+
+    pts, segs, info = make_candidates(B_PER_GPU, 1234 + rank)
+    d_pts = torch.from_numpy(pts).to(dev)
+    d_segs = torch.from_numpy(segs).to(dev)
+    d_out = torch.empty((B_PER_GPU, 16), dtype=torch.float64, device=dev)
+    gathered = torch.empty((world * B_PER_GPU,), dtype=torch.float64, device=dev) if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    h_pts = torch.from_numpy(pts).pin_memory()
+    h_segs = torch.from_numpy(segs).pin_memory()
+    h_out = torch.empty((B_PER_GPU, 16), dtype=torch.float64).pin_memory()
+
+    dfma_peak, dmma_peak = ev.fp64_peak()
+
+    def step():
+        flush.zero_()
+        ev.evaluate_device(3, True, d_pts, d_segs, None, out=d_out)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, d_out[:, 0].contiguous())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ev.launch_count()
+    kernel_ms = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+        # per-launch device time of the dominant kernel (events recorded inside the C ABI on the
+        # launching stream); reading it synchronises, which is inside the timed region on purpose
+        kernel_ms.append(ev.last_kernel_ms())
+    e1.record()
+    barrier()
+    total_ms = e0.elapsed_time(e1)
+    launches = ev.launch_count() - launches0
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = world * B_PER_GPU * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region
+    lib_host = ev.lib.rydcz_evaluate_host
+    def e2e_step():
+        rc = lib_host(ev.ctx, 3, 1, B_PER_GPU, h_pts.data_ptr(), h_segs.data_ptr(), None, N_SEG,
+                      h_out.data_ptr(), None)
+        assert rc == 0
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B_PER_GPU * args.steps / float(t.item())
+    if rank == 0:
+        sampler.stop_flag = True
+        sampler.join(timeout=2)
+
+    out_np = d_out.cpu().numpy()
+    flops_per_launch = float(out_np[:, 15].sum())
+    k_ms = float(np.mean(kernel_ms))
+    achieved = flops_per_launch / (k_ms * 1e-3) * 1e-12
+    h2d = pts.nbytes + segs.nbytes
+    d2h = B_PER_GPU * 16 * 8
+
+    if rank == 0:
+        cores = os.cpu_count() or 1
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            n_sample = max(2 * cores, 8)
+            rate, dt = cpu_path_rate(pts, segs, n_sample, cores)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"first {n_sample} of the {B_PER_GPU} candidates ({dt:.1f} s), oracle zvode/Adams "
+                             f"restatement of the reference's mesolve path, {cores} processes"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "jp_bangbang_5seg_lindblad_3level", "candidates_per_gpu": B_PER_GPU,
+                       "segments": N_SEG, "V_over_Omega": info["V"] / info["Omega"],
+                       "l2": "256 MiB flush write between timed iterations", "parallelism": f"shard{world}",
+                       "mean_fidelity": float(out_np[:, 0].mean())},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "rydcz_evaluate_host (C ABI, pinned host buffers)"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": dfma_peak, "unit": "TFLOP/s",
+                         "frac": achieved / dfma_peak, "traffic": None,
+                         "kernel": "rydcz::evaluate_kernel<3,true,false>", "kernel_ms": k_ms,
+                         "flops_per_launch": flops_per_launch,
+                         "peak_source": "DFMA microbenchmark (rydcz_fp64_peak) measured in this run; "
+                                        "MEASURED_PEAKS.json has no FP64 entry", "dmma_peak": dmma_peak},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

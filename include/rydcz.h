@@ -1,0 +1,131 @@
+/* rydcz.h -- C ABI of the B200 Rydberg-CZ gate evaluator.
+ *
+ * The reference has no FFI: its boundary for this path is the Python function
+ *   simulate_CZ_gate(...)            RG/simulation.py:2534-3676
+ * (RG = src/qpu_simulator/micro_physics/neutral_atoms/rydberg_gates).  Inside it, the part this
+ * library replaces is everything from operator assembly to the fidelity numbers:
+ *   build_full_hamiltonian / build_phase_modulated_hamiltonian   RG/hamiltonians.py:1057, 1179
+ *   build_all_noise_operators                                    RG/noise_models.py:1449
+ *   evolve_two_pulse_lp / evolve_bangbang_jp /
+ *   evolve_smooth_sinusoidal_jp / evolve_shaped_pulse            RG/simulation.py:740, 1795, 1502, 2099
+ *     (each a Python loop of QuTiP mesolve calls,                RG/simulation.py:689)
+ *   compute_CZ_fidelity                                          RG/simulation.py:225
+ * A maintainer binds these entry points with ctypes.
+ *
+ * All arrays are IEEE double unless stated, row-major, caller-owned.  One "point" is one gate
+ * evaluation (all four computational-basis inputs through the whole pulse).
+ *
+ *   points  [n_points][RYDCZ_POINT_STRIDE]   per-point constants, see enum below
+ *   segs    [n_points][max_seg][4]           piecewise-constant pulse: dt (s), Re Omega, Im Omega,
+ *                                            Delta (rad/s).  Built by the caller exactly as the
+ *                                            reference's evolve_* loops build their Hamiltonians.
+ *   n_seg   [n_points] (int32)               segments actually used by each point (ragged batches)
+ *   out     [n_points][RYDCZ_OUT_STRIDE]     results, see enum below
+ *   states  [n_points][rydcz_state_stride(dim)] optional raw reduced states (rho and coherences);
+ *                                            NULL to skip.  Layout: rydcz_state_offset().
+ *
+ * Every function returns 0 on success, non-zero on failure; rydcz_last_error() gives the text.
+ * Per-point numerical trouble never raises: it shows up as NaN in that point's row.
+ */
+#ifndef RYDCZ_H
+#define RYDCZ_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RYDCZ_POINT_STRIDE 12
+#define RYDCZ_SEG_STRIDE 4
+#define RYDCZ_OUT_STRIDE 16
+
+enum rydcz_point_slot {
+  RYDCZ_PT_V = 0,         /* blockade shift V = C6/R^6 (rad/s)           RG/simulation.py:2958-2959 */
+  RYDCZ_PT_DELTA1 = 1,    /* delta_zeeman + delta_stark on |1> (rad/s)    RG/simulation.py:3129-3159 */
+  RYDCZ_PT_OFF_A = 2,     /* extra detuning of atom A (rad/s), 0 in the reference                    */
+  RYDCZ_PT_OFF_B = 3,     /* extra detuning of atom B                                                */
+  RYDCZ_PT_G_R1 = 4,      /* Gamma(r->1) = gamma_r * branching_1          RG/noise_models.py:1237    */
+  RYDCZ_PT_G_R0 = 5,      /* Gamma(r->0): all channels ending in |0>      RG/noise_models.py:1242-1251, 1583-1592 */
+  RYDCZ_PT_G_PHI = 6,     /* dephasing rate on |r><r|                     RG/noise_models.py:1579    */
+  RYDCZ_PT_G_SC = 7,      /* scattering rate on |1><1|                    RG/noise_models.py:1589    */
+  RYDCZ_PT_G_MJ = 8,      /* r+ <-> r- mixing rate (dim = 4 only)         RG/noise_models.py:1287    */
+  RYDCZ_PT_SIG_DET = 9,   /* Monte-Carlo shots: std of per-atom Doppler detuning k_eff v_rms (rad/s) */
+  RYDCZ_PT_SIG_RELR = 10, /* Monte-Carlo shots: std of dR/R0 = sqrt(2) sigma_r / R0                  */
+  RYDCZ_PT_RESERVED = 11
+};
+
+enum rydcz_out_slot {
+  RYDCZ_OUT_AVG_F = 0,        /* avg_fidelity                           RG/simulation.py:631        */
+  RYDCZ_OUT_F00 = 1,
+  RYDCZ_OUT_F01 = 2,
+  RYDCZ_OUT_F10 = 3,
+  RYDCZ_OUT_F11 = 4,          /* F11 population x cz_phase_fidelity     RG/simulation.py:619-629    */
+  RYDCZ_OUT_F11_POP = 5,
+  RYDCZ_OUT_CZ_PHASE_FID = 6, /* cos^2(phase_error/2)                   RG/simulation.py:611        */
+  RYDCZ_OUT_CTRL_PHASE = 7,   /* phi11 - phi01 - phi10 + phi00 in [-pi, pi)   RG/simulation.py:607-608 */
+  RYDCZ_OUT_PHASE_ERR = 8,    /* min(|c - pi|, |c + pi|)                RG/simulation.py:610        */
+  RYDCZ_OUT_PHI01 = 9,
+  RYDCZ_OUT_PHI10 = 10,
+  RYDCZ_OUT_PHI11 = 11,
+  RYDCZ_OUT_LOSS = 12,        /* |11> input: P(an atom ended in |0>) -- where every loss channel lands */
+  RYDCZ_OUT_RYD = 13,         /* |11> input: P(an atom is left in a Rydberg level)                     */
+  RYDCZ_OUT_STEPS = 14,       /* sparse matvecs performed (work counter)                              */
+  RYDCZ_OUT_FLOPS = 15        /* useful FP64 flops performed by this point                            */
+};
+
+typedef struct rydcz_ctx rydcz_ctx;
+
+/* library / layout queries (no GPU needed) */
+int rydcz_version(void);
+int rydcz_point_stride(void);
+int rydcz_seg_stride(void);
+int rydcz_out_stride(void);
+int rydcz_state_stride(int dim);                        /* 51 (dim 3), 64 (dim 4), -1 otherwise */
+int rydcz_state_offset(int dim, const char* system);    /* "rho11","rho01","rho10","coh11","coh01","coh10" */
+int rydcz_system_size(int dim, const char* system);     /* real variables of that reduced system */
+int rydcz_system_nnz(int dim, const char* system);      /* FMAs per sparse matvec of that system */
+
+/* context: one per (process, GPU); owns a stream, timing events and scratch buffers */
+int rydcz_create(int device, rydcz_ctx** ctx);
+void rydcz_destroy(rydcz_ctx* ctx);
+const char* rydcz_last_error(const rydcz_ctx* ctx);     /* ctx may be NULL: last create() error */
+int rydcz_set_sort(rydcz_ctx* ctx, int enable);         /* order points by estimated work (default 1) */
+
+/* One batch of gate evaluations, inputs and outputs resident in device memory.
+ * dim: 3 (|0>,|1>,|r>) or 4 (|0>,|1>,|r+>,|r->).  noisy: 0 -> Schroedinger path with the
+ * pure-state epilogue (QuTiP's c_ops=[] branch); 1 -> Lindblad path.  stream: a cudaStream_t
+ * (as void*) to enqueue on, or NULL for the context's own stream.  Asynchronous. */
+int rydcz_evaluate_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points,
+                          const double* d_points, const double* d_segs, const int32_t* d_n_seg,
+                          int max_seg, double* d_out, double* d_states, void* stream);
+
+/* Same with host buffers: copies in, runs, copies out, and returns when the results are in
+ * h_out (and h_states).  This is the call the reference-side binding makes. */
+int rydcz_evaluate_host(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points,
+                        const double* h_points, const double* h_segs, const int32_t* h_n_seg,
+                        int max_seg, double* h_out, double* h_states);
+
+/* Monte-Carlo shot averaging (extension; the reference folds Doppler and position noise into
+ * dephasing rates, RG/trap_physics.py:1206-1288, 1064-1115).  Shot s of point i draws, from
+ * Philox4x32-10 keyed by (seed; i, s), two Doppler detunings N(0, SIG_DET^2) and one relative
+ * displacement eps ~ N(0, SIG_RELR^2) with V -> V / (1 + eps)^6, and is evaluated like any
+ * point.  d_out_mean[n_points][16] receives the shot mean of every slot (STEPS and FLOPS: the
+ * sum); d_out_shots [n_points][n_shots][16] is optional. */
+int rydcz_evaluate_shots_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, int n_shots,
+                                uint64_t seed, const double* d_points, const double* d_segs,
+                                const int32_t* d_n_seg, int max_seg, double* d_out_mean,
+                                double* d_out_shots, void* stream);
+int rydcz_evaluate_shots_host(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, int n_shots,
+                              uint64_t seed, const double* h_points, const double* h_segs,
+                              const int32_t* h_n_seg, int max_seg, double* h_out_mean,
+                              double* h_out_shots);
+
+/* measurement */
+int rydcz_last_kernel_ms(rydcz_ctx* ctx, float* ms);    /* device time of the last evaluate kernel */
+int rydcz_launch_count(const rydcz_ctx* ctx, int64_t* n); /* kernels launched through this context */
+/* register-resident FP64 FMA throughput of this GPU (the roofline denominator), TFLOP/s */
+int rydcz_fp64_peak(rydcz_ctx* ctx, double* dfma_tflops, double* dmma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RYDCZ_H */

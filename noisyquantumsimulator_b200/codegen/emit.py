@@ -1,0 +1,191 @@
+"""Print the reduced real systems of ``model.py`` as straight-line CUDA/C++.
+
+Each system becomes a struct with compile-time sizes and three inline functions:
+
+    coefs(p, c)      c[q] = distinct linear forms  sum_k m_k p[k]  found among the
+                     nonzeros of  sum_k p_k M_k  (p has one extra trailing entry, the
+                     spectral shift used by coherence systems);
+    bounds(c, ...)   Gershgorin information for the Chebyshev interval;
+    apply(c, x, y)   y += G x, fully unrolled: one FMA per structural nonzero, every
+                     index a literal so x, y, c stay in registers.
+
+Run ``python -m noisyquantumsimulator_b200.codegen.emit`` to regenerate
+``csrc/rydcz_systems_d3.inc`` / ``_d4.inc`` (committed; the build does not need Python).
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Tuple
+
+import numpy as np
+
+from . import model
+
+
+def _fmt(v: float) -> str:
+    r = repr(float(v))
+    return r if ("." in r or "e" in r or "inf" in r) else r + ".0"
+
+
+def _linear_forms(sysm: model.RealSystem, shift_matrix):
+    """Group nonzeros by their parameter-coefficient vector (up to sign)."""
+    mats = list(sysm.M) + ([shift_matrix] if shift_matrix is not None else [])
+    K = len(mats)
+    stack = np.stack(mats, axis=0)  # (K, n, n)
+    forms: Dict[Tuple, int] = {}
+    form_vecs: List[np.ndarray] = []
+    entries: List[Tuple[int, int, int, int]] = []  # (row, col, q, sign)
+    n = sysm.n
+    for i in range(n):
+        for j in range(n):
+            v = stack[:, i, j]
+            if not np.any(v != 0):
+                continue
+            first = v[np.nonzero(v)[0][0]]
+            sgn = 1 if first > 0 else -1
+            key = tuple(np.round(v * sgn, 12))
+            if key not in forms:
+                forms[key] = len(form_vecs)
+                form_vecs.append(v * sgn)
+            entries.append((i, j, forms[key], sgn))
+    return K, form_vecs, entries
+
+
+def emit_system(sysm: model.RealSystem, struct_name: str) -> str:
+    n = sysm.n
+    # the spectral shift: coherence systems are complex-linear, so multiplying the state by
+    # exp(-i c t) commutes with the generator.  In real (re, im) layout "multiply by -i c"
+    # is  re' += c*im, im' -= c*re ; we add p_shift * S with S = that matrix for c = -1,
+    # i.e. the generator actually exponentiated is G - i*cen (centre moved to zero).
+    shift = None
+    if not sysm.hermitian:
+        shift = np.zeros((n, n))
+        for k in range(0, n, 2):
+            assert sysm.var_info[k][2] == "re" and sysm.var_info[k + 1][2] == "im"
+            shift[k, k + 1] = -1.0
+            shift[k + 1, k] = +1.0
+    K, forms, entries = _linear_forms(sysm, shift)
+    pnames = list(sysm.params) + (["shift"] if shift is not None else [])
+    L: List[str] = []
+    A = L.append
+    A(f"// ---- {struct_name}: start operator '{sysm.name}', d={sysm.d}, n={n} real variables,")
+    A(f"//      {len(entries)} structural nonzeros, {len(forms)} distinct coefficients")
+    for k, (i, j, part) in enumerate(sysm.var_info):
+        A(f"//   x[{k}] = {part}( X[{i},{j}] )")
+    A(f"struct {struct_name} {{")
+    A(f"  static constexpr int N = {n};")
+    A(f"  static constexpr int NC = {len(forms)};")
+    A(f"  static constexpr int NNZ = {len(entries)};")
+    A(f"  static constexpr int NP = {len(pnames)};   // {', '.join(pnames)}")
+    A(f"  static constexpr bool HERMITIAN = {'true' if sysm.hermitian else 'false'};")
+    nz0 = np.nonzero(sysm.x0)[0]
+    assert len(nz0) == 1 and sysm.x0[nz0[0]] == 1.0
+    A(f"  static constexpr int START = {int(nz0[0])};   // x0 = e_START")
+    # coefs
+    A("  RYDCZ_HD static void coefs(const double* __restrict__ p, double* __restrict__ c) {")
+    for q, v in enumerate(forms):
+        terms = []
+        for k in np.nonzero(v)[0]:
+            coef = v[k]
+            if coef == 1.0:
+                terms.append(f"+ p[{k}]")
+            elif coef == -1.0:
+                terms.append(f"- p[{k}]")
+            else:
+                terms.append(f"{'+' if coef > 0 else '-'} {_fmt(abs(coef))} * p[{k}]")
+        expr = " ".join(terms).lstrip("+ ").strip()
+        A(f"    c[{q}] = {expr};")
+    A("  }")
+    # bounds: per-row |diag| and off-diagonal absolute row sums
+    A("  // Gershgorin: every eigenvalue lies in a disc centred at the (real, <=0) diagonal entry.")
+    A("  // rho systems: returns radius = max_i(|G_ii| + sum_{j!=i}|G_ij|), lo = hi = 0.")
+    A("  // coh systems: the pair frequency E_i = G[re_i][im_i]; returns the interval [lo, hi] that")
+    A("  // contains every E_i -/+ (other off-diagonals of the row) and damp = max |G_ii|.")
+    A("  RYDCZ_HD static void bounds(const double* __restrict__ c, double& lo, double& hi, double& damp) {")
+    rows: Dict[int, List[Tuple[int, int, int]]] = {}
+    for (i, j, q, s) in entries:
+        rows.setdefault(i, []).append((j, q, s))
+    if sysm.hermitian:
+        A("    double r = 0.0, t; damp = 0.0;")
+        for i in range(n):
+            parts = [f"fabs(c[{q}])" for (j, q, s) in rows.get(i, [])]
+            if not parts:
+                continue
+            A(f"    t = {' + '.join(parts)}; r = fmax(r, t);")
+            dq = [q for (j, q, s) in rows.get(i, []) if j == i]
+            if dq:
+                A(f"    damp = fmax(damp, fabs(c[{dq[0]}]));")
+        A("    lo = -r; hi = r;")
+    else:
+        A("    double t, e; lo = 1e300; hi = -1e300; damp = 0.0;")
+        for k in range(0, n, 2):
+            # row of re_k: entry on im_k carries +E (d re/dt = E*im)
+            E = [(q, s) for (j, q, s) in rows.get(k, []) if j == k + 1]
+            others = [f"fabs(c[{q}])" for (j, q, s) in rows.get(k, []) if j not in (k, k + 1)]
+            dq = [q for (j, q, s) in rows.get(k, []) if j == k]
+            A(f"    e = {('%sc[%d]' % ('' if E[0][1] > 0 else '-', E[0][0])) if E else '0.0'};"
+              f" t = {' + '.join(others) if others else '0.0'};")
+            A("    lo = fmin(lo, e - t); hi = fmax(hi, e + t);")
+            if dq:
+                A(f"    damp = fmax(damp, fabs(c[{dq[0]}]));")
+    A("  }")
+    # apply
+    A("  RYDCZ_HD static void apply(const double* __restrict__ c, const double* __restrict__ x, double* __restrict__ y) {")
+    for i in range(n):
+        for (j, q, s) in rows.get(i, []):
+            A(f"    y[{i}] {'+=' if s > 0 else '-='} c[{q}] * x[{j}];")
+    A("  }")
+    A("};")
+    A("")
+    return "\n".join(L)
+
+
+def emit_dim(d: int) -> str:
+    systems = model.standard_systems(d)
+    out = [f"// GENERATED by noisyquantumsimulator_b200/codegen/emit.py -- do not edit.",
+           f"// Two-atom {d}-level Rydberg model: reduced real Lindblad systems.",
+           f"// Parameters p[]: {', '.join(model.PARAMS3 if d == 3 else model.PARAMS4)} (, shift for coh systems)",
+           ""]
+    for key, sysm in systems.items():
+        out.append(emit_system(sysm, f"Sys_{key}_d{d}"))
+    # readout indices
+    N = d * d
+    out.append(f"// readout indices (d={d})")
+    for lab in ("01", "10", "11"):
+        a, b = int(lab[0]), int(lab[1])
+        idx = d * a + b
+        rho = systems["rho" + lab]
+        coh = systems["coh" + lab]
+        out.append(f"static constexpr int RHO{lab}_POP_D{d} = {rho.index_of(idx, idx, 'diag')};")
+        out.append(f"static constexpr int COH{lab}_RE_D{d} = {coh.index_of(idx, 0, 're')};")
+        out.append(f"static constexpr int COH{lab}_IM_D{d} = {coh.index_of(idx, 0, 'im')};")
+    # diagonal (population) variables of rho11 by sector, for loss / Rydberg-residual readouts
+    rho11 = systems["rho11"]
+    diag = [(k, i) for k, (i, j, part) in enumerate(rho11.var_info) if part == "diag"]
+    ryd = {2} if d == 3 else {2, 3}
+
+    def cls(i):
+        a, b = i // d, i % d
+        return (a in ryd or b in ryd, a == 0 or b == 0)
+
+    loss_terms = " + ".join(f"x[{k}]" for k, i in diag if cls(i)[1])
+    ryd_terms = " + ".join(f"x[{k}]" for k, i in diag if cls(i)[0])
+    out.append(f"// |11> input: probability that at least one atom sits in |0> / in a Rydberg level")
+    out.append(f"RYDCZ_HD double rho11_loss_d{d}(const double* __restrict__ x) {{ return {loss_terms}; }}")
+    out.append(f"RYDCZ_HD double rho11_ryd_d{d}(const double* __restrict__ x) {{ return {ryd_terms}; }}")
+    out.append("")
+    return "\n".join(out)
+
+
+def main():
+    here = os.path.dirname(os.path.abspath(__file__))
+    csrc = os.path.join(os.path.dirname(here), "csrc")
+    for d in (3, 4):
+        path = os.path.join(csrc, f"rydcz_systems_d{d}.inc")
+        with open(path, "w") as f:
+            f.write(emit_dim(d))
+        print("wrote", path)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,212 @@
+"""Linear-parametric description of the two-atom Rydberg Lindblad generator.
+
+The generator the reference integrates (H from RG/hamiltonians.py:584-989, collapse
+operators from RG/noise_models.py:1199-1620, assembled in RG/simulation.py:3178-3334)
+is *linear* in a handful of scalars p_k:
+
+    d/dt vec(X) = ( sum_k p_k L_k ) vec(X)
+
+with p = (Re Ω, Im Ω, Δ_A, Δ_B, V, δ_1, Γ_r→1, Γ_r→0, γ_φ, γ_sc[, γ_mJ]).  Lindblad terms
+that share an operator add in rate, so the reference's ~14 collapse operators
+collapse to these rates.  This module builds the constant matrices
+L_k, restricts them to the operator subspace reachable from one start operator
+(|ab><ab| for a density-matrix input, |ab><00| for the phase-carrying coherence),
+and turns the complex system into a real one.  ``emit.py`` prints the result as
+straight-line CUDA.
+
+Basis index of the two-atom space: d*a + b; vec(X) is row-major.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+PARAMS3 = ("om_re", "om_im", "det_a", "det_b", "V", "delta1", "g_r1", "g_r0", "g_phi", "g_sc")
+PARAMS4 = PARAMS3 + ("g_mj",)
+
+
+def _op(d, i, j):
+    m = np.zeros((d, d), dtype=complex)
+    m[i, j] = 1.0
+    return m
+
+
+def _hamiltonian_terms(d: int) -> Dict[str, np.ndarray]:
+    """H = sum_k p_k H_k for the coherent parameters."""
+    I = np.eye(d, dtype=complex)
+    ryd = [2] if d == 3 else [2, 3]
+    two = np.kron
+    up = _op(d, 2, 1)  # |r(+)><1|: the default sigma+ coupling reaches only r+ for d=4
+    # (Ω/2)|r><1| + (Ω*/2)|1><r| with Ω = re + i im
+    h_re = 0.5 * (up + up.conj().T)
+    h_im = 0.5 * (1j * up - 1j * up.conj().T)
+    Pr = sum(_op(d, r, r) for r in ryd)
+    P1 = _op(d, 1, 1)
+    return {
+        "om_re": two(h_re, I) + two(I, h_re),
+        "om_im": two(h_im, I) + two(I, h_im),
+        "det_a": -two(Pr, I),
+        "det_b": -two(I, Pr),
+        "V": two(Pr, Pr),
+        "delta1": two(P1, I) + two(I, P1),
+    }
+
+
+def _jump_terms(d: int) -> Dict[str, List[np.ndarray]]:
+    """Unit-rate jump operators grouped by the rate that multiplies them."""
+    I = np.eye(d, dtype=complex)
+    ryd = [2] if d == 3 else [2, 3]
+    two = np.kron
+
+    def both(a):
+        return [two(a, I), two(I, a)]
+
+    out = {
+        "g_r1": sum((both(_op(d, 1, r)) for r in ryd), []),
+        "g_r0": sum((both(_op(d, 0, r)) for r in ryd), []),
+        "g_phi": sum((both(_op(d, r, r)) for r in ryd), []),
+        "g_sc": both(_op(d, 1, 1)),
+    }
+    if d == 4:
+        out["g_mj"] = both(_op(d, 3, 2)) + both(_op(d, 2, 3))
+    return out
+
+
+def liouvillian_terms(d: int) -> Tuple[Tuple[str, ...], List[np.ndarray]]:
+    """(param names, [L_k]) with L_k of shape (d^4, d^4), row-major vec convention."""
+    names = PARAMS3 if d == 3 else PARAMS4
+    n = d * d
+    I = np.eye(n, dtype=complex)
+    H = _hamiltonian_terms(d)
+    J = _jump_terms(d)
+    terms = []
+    for nm in names:
+        if nm in H:
+            h = H[nm]
+            terms.append(-1j * (np.kron(h, I) - np.kron(I, h.T)))
+        else:
+            L = np.zeros((n * n, n * n), dtype=complex)
+            for C in J[nm]:
+                CdC = C.conj().T @ C
+                L += np.kron(C, C.conj()) - 0.5 * np.kron(CdC, I) - 0.5 * np.kron(I, CdC.T)
+            terms.append(L)
+    return names, terms
+
+
+@dataclass
+class RealSystem:
+    """x' = (sum_k p_k M_k) x, x real of length n."""
+
+    name: str
+    d: int
+    hermitian: bool
+    n: int
+    params: Tuple[str, ...]
+    M: List[np.ndarray]                 # one (n, n) real matrix per parameter
+    x0: np.ndarray                      # start vector
+    # variable bookkeeping: var index -> (row i, col j, part) with part in {"re", "im", "diag"}
+    var_info: List[Tuple[int, int, str]] = field(default_factory=list)
+
+    def generator(self, p: Sequence[float]) -> np.ndarray:
+        return sum(pk * Mk for pk, Mk in zip(p, self.M))
+
+    def to_operator(self, x: np.ndarray) -> np.ndarray:
+        """Rebuild the (d^2 x d^2) complex operator from the real state."""
+        N = self.d * self.d
+        X = np.zeros((N, N), dtype=complex)
+        for v, (i, j, part) in zip(x, self.var_info):
+            if part == "diag":
+                X[i, i] += v
+            elif part == "re":
+                X[i, j] += v
+                if self.hermitian:
+                    X[j, i] += v
+            else:
+                X[i, j] += 1j * v
+                if self.hermitian:
+                    X[j, i] -= 1j * v
+        return X
+
+    def index_of(self, i: int, j: int, part: str) -> int:
+        return self.var_info.index((i, j, part))
+
+
+def reduce_system(name: str, d: int, X0: np.ndarray, hermitian: bool) -> RealSystem:
+    """Restrict to the operator entries reachable from X0 and make the system real."""
+    names, L = liouvillian_terms(d)
+    N = d * d
+    pattern = sum(np.abs(Lk) for Lk in L) > 0
+    reach = np.abs(X0.reshape(-1)) > 0
+    while True:
+        new = reach | (pattern @ reach.astype(float) > 0)
+        if (new == reach).all():
+            break
+        reach = new
+    entries = [(idx // N, idx % N) for idx in np.nonzero(reach)[0]]
+    eset = set(entries)
+    var_info: List[Tuple[int, int, str]] = []
+    if hermitian:
+        for (i, j) in entries:
+            assert (j, i) in eset
+        for (i, j) in sorted(eset):
+            if i == j:
+                var_info.append((i, i, "diag"))
+            elif i < j:
+                var_info.append((i, j, "re"))
+                var_info.append((i, j, "im"))
+    else:
+        for (i, j) in sorted(eset):
+            var_info.append((i, j, "re"))
+            var_info.append((i, j, "im"))
+    n = len(var_info)
+    vidx = {t: k for k, t in enumerate(var_info)}
+
+    def expand(col_entry):
+        """entry (k,l) of X as a list of (var index, complex weight)."""
+        k, l = col_entry
+        if hermitian:
+            if k == l:
+                return [(vidx[(k, k, "diag")], 1.0 + 0j)]
+            if k < l:
+                return [(vidx[(k, l, "re")], 1.0 + 0j), (vidx[(k, l, "im")], 1j)]
+            return [(vidx[(l, k, "re")], 1.0 + 0j), (vidx[(l, k, "im")], -1j)]
+        return [(vidx[(k, l, "re")], 1.0 + 0j), (vidx[(k, l, "im")], 1j)]
+
+    M = []
+    for Lk in L:
+        Mk = np.zeros((n, n))
+        for row_var, (i, j, part) in enumerate(var_info):
+            row = Lk[i * N + j]
+            for col in np.nonzero(row)[0]:
+                kl = (col // N, col % N)
+                if kl not in eset:
+                    continue
+                for (cv, w) in expand(kl):
+                    c = row[col] * w
+                    Mk[row_var, cv] += c.imag if part == "im" else c.real
+        M.append(Mk)
+    x0 = np.zeros(n)
+    for k, (i, j, part) in enumerate(var_info):
+        x0[k] = X0[i, j].imag if part == "im" else X0[i, j].real
+    return RealSystem(name, d, hermitian, n, names, M, x0, var_info)
+
+
+def standard_systems(d: int) -> Dict[str, RealSystem]:
+    """The six systems one gate evaluation needs (|00> is inert: H and every collapse
+    operator annihilate it, so neither its ρ nor its coherence moves)."""
+    N = d * d
+    out = {}
+
+    def ket(a, b):
+        v = np.zeros(N, dtype=complex)
+        v[d * a + b] = 1.0
+        return v
+
+    k00 = ket(0, 0)
+    for lab in ("01", "10", "11"):
+        k = ket(int(lab[0]), int(lab[1]))
+        out["rho" + lab] = reduce_system("rho" + lab, d, np.outer(k, k.conj()), True)
+        out["coh" + lab] = reduce_system("coh" + lab, d, np.outer(k, k00.conj()), False)
+    return out

@@ -1,0 +1,515 @@
+// rydcz.cu -- sm_100a kernels and the C ABI (include/rydcz.h) of the Rydberg-CZ evaluator.
+//
+// Mapping.  One thread = one gate evaluation (or one Monte-Carlo shot of one).  The six reduced
+// Lindblad systems of a point (rydcz_core.cuh) are advanced one after the other with all state
+// in registers; the kernel reads ~0.2-10 KB per point and writes 128 B, so HBM is idle and the
+// bound is the FP64 FMA pipe.  Work per point varies with ||H|| tau by orders of magnitude, so a
+// pre-pass estimates it and points are processed heaviest-first in sorted order: the 32 threads
+// of a warp then run (almost) the same trip counts and the tail of the grid is made of cheap
+// points.
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+
+#include "../../include/rydcz.h"
+#include "rydcz_core.cuh"
+
+namespace rydcz {
+
+static_assert(PT_STRIDE == RYDCZ_POINT_STRIDE, "layout");
+static_assert(SG_STRIDE == RYDCZ_SEG_STRIDE, "layout");
+static_assert(OUT_STRIDE == RYDCZ_OUT_STRIDE, "layout");
+
+constexpr int kBlock = 128;
+
+// ---------------------------------------------------------------- Philox4x32-10
+struct Philox {
+  static constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  __host__ __device__ static inline void round(uint32_t (&c)[4], uint32_t (&k)[2]) {
+    const uint64_t p0 = (uint64_t)M0 * c[0], p1 = (uint64_t)M1 * c[2];
+    const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    const uint32_t n0 = hi1 ^ c[1] ^ k[0], n1 = lo1, n2 = hi0 ^ c[3] ^ k[1], n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+  }
+  __host__ __device__ static inline void block(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t c2,
+                                               uint32_t c3, uint32_t (&out)[4]) {
+    uint32_t c[4] = {c0, c1, c2, c3};
+    uint32_t k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      round(c, k);
+      k[0] += W0; k[1] += W1;
+    }
+    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
+  }
+};
+
+// two standard normals from one Philox block (Box-Muller on two 53-bit uniforms in (0,1))
+__device__ inline void philox_normal2(uint64_t seed, uint32_t point, uint32_t shot, uint32_t stream,
+                                      double& n0, double& n1) {
+  uint32_t r[4];
+  Philox::block(seed, point, shot, stream, 0u, r);
+  const uint64_t a = ((uint64_t)r[1] << 32) | r[0], b = ((uint64_t)r[3] << 32) | r[2];
+  const double u1 = ((double)(a >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  const double u2 = ((double)(b >> 11) + 0.5) * (1.0 / 9007199254740992.0);
+  const double rad = sqrt(-2.0 * log(u1));
+  double s, c;
+  sincospi(2.0 * u2, &s, &c);
+  n0 = rad * c; n1 = rad * s;
+}
+
+// ---------------------------------------------------------------- kernels
+template <int D>
+__global__ void work_kernel(int64_t n_points, const double* __restrict__ points,
+                            const double* __restrict__ segs, const int32_t* __restrict__ n_seg,
+                            int max_seg, float* __restrict__ keys, uint32_t* __restrict__ idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_points) return;
+  const double w = point_work<D>(points + i * PT_STRIDE, segs + i * (int64_t)max_seg * SG_STRIDE,
+                                 n_seg ? n_seg[i] : max_seg);
+  keys[i] = (float)w;   // non-negative floats order like their bit patterns
+  idx[i] = (uint32_t)i;
+}
+
+template <int D, bool NOISY, bool SHOTS>
+__global__ void __launch_bounds__(kBlock)
+evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, const uint32_t* __restrict__ order,
+                const double* __restrict__ points, const double* __restrict__ segs,
+                const int32_t* __restrict__ n_seg, int max_seg, double* __restrict__ out,
+                double* __restrict__ states) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_items) return;
+  int64_t point, item;
+  uint32_t shot = 0;
+  if (SHOTS) {
+    const int64_t slot = g / n_shots;
+    shot = (uint32_t)(g - slot * n_shots);
+    point = order ? order[slot] : slot;
+    item = point * n_shots + shot;
+  } else {
+    point = order ? order[g] : g;
+    item = point;
+  }
+  double pt[PT_STRIDE];
+#pragma unroll
+  for (int k = 0; k < PT_STRIDE; ++k) pt[k] = points[point * PT_STRIDE + k];
+  if (SHOTS) {
+    double da, db, er, unused;
+    philox_normal2(seed, (uint32_t)point, shot, 0u, da, db);
+    philox_normal2(seed, (uint32_t)point, shot, 1u, er, unused);
+    pt[PT_OFF_A] += pt[PT_SIG_DET] * da;
+    pt[PT_OFF_B] += pt[PT_SIG_DET] * db;
+    const double q = 1.0 + pt[PT_SIG_RELR] * er;
+    const double q2 = q * q;
+    pt[PT_V] = pt[PT_V] / (q2 * q2 * q2);
+  }
+  const double* sg = segs + point * (int64_t)max_seg * SG_STRIDE;
+  const int ns = n_seg ? n_seg[point] : max_seg;
+  double o[OUT_STRIDE];
+  double* st = states ? states + item * StateLayout<D>::STRIDE : nullptr;
+  if (D == 3) evaluate_point_d3<NOISY>(pt, sg, ns, o, st);
+  else evaluate_point_d4<NOISY>(pt, sg, ns, o, st);
+  double* op = out + item * OUT_STRIDE;
+#pragma unroll
+  for (int k = 0; k < OUT_STRIDE; k += 2)
+    *reinterpret_cast<double2*>(op + k) = make_double2(o[k], o[k + 1]);
+}
+
+// deterministic shot mean: one warp per point, fixed-order tree
+__global__ void shot_mean_kernel(int64_t n_points, int n_shots, const double* __restrict__ shots,
+                                 double* __restrict__ mean) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= n_points) return;
+  for (int k = 0; k < OUT_STRIDE; ++k) {
+    double acc = 0.0;
+    for (int s = lane; s < n_shots; s += 32) acc += shots[(w * n_shots + s) * OUT_STRIDE + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0)
+      mean[w * OUT_STRIDE + k] = (k == OUT_STEPS || k == OUT_FLOPS) ? acc : acc / (double)n_shots;
+  }
+}
+
+// ---------------------------------------------------------------- FP64 peak microbenchmarks
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+         x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double a, double b) {
+  // mma.sync.m8n8k4.f64: 8x8x4 = 256 FMA per warp instruction; four independent accumulators
+  double c0[2] = {0, 0}, c1[2] = {0, 0}, c2[2] = {0, 0}, c3[2] = {0, 0};
+  const double fa = a + threadIdx.x * 1e-9, fb = b;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c0[0]), "+d"(c0[1]) : "d"(fa), "d"(fb));
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c1[0]), "+d"(c1[1]) : "d"(fa), "d"(fb));
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c2[0]), "+d"(c2[1]) : "d"(fa), "d"(fb));
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c3[0]), "+d"(c3[1]) : "d"(fa), "d"(fb));
+    }
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = c0[0] + c0[1] + c1[0] + c1[1] + c2[0] + c2[1] + c3[0] + c3[1];
+}
+
+}  // namespace rydcz
+
+// ======================================================================= C ABI
+using namespace rydcz;
+
+struct rydcz_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  bool sort = true;
+  int64_t launches = 0;
+  std::string err;
+  // scratch
+  float* keys = nullptr; float* keys_sorted = nullptr;
+  uint32_t* idx = nullptr; uint32_t* idx_sorted = nullptr;
+  size_t order_cap = 0;
+  void* cub_tmp = nullptr; size_t cub_cap = 0;
+  // staging for the host entry points
+  void* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t stage_cap[6] = {0, 0, 0, 0, 0, 0};
+};
+
+static std::string g_create_error;
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+      return 1;                                                                           \
+    }                                                                                     \
+  } while (0)
+
+static int fail(rydcz_ctx* ctx, const char* msg) {
+  if (ctx) ctx->err = msg;
+  return 2;
+}
+
+static int grow(rydcz_ctx* ctx, void** p, size_t* cap, size_t bytes) {
+  if (bytes <= *cap) return 0;
+  if (*p) CK(cudaFree(*p));
+  *p = nullptr; *cap = 0;
+  CK(cudaMalloc(p, bytes));
+  *cap = bytes;
+  return 0;
+}
+
+static const char* kSysNames[6] = {"rho11", "rho01", "rho10", "coh11", "coh01", "coh10"};
+template <int D> static void sys_tables(int (&off)[6], int (&n)[6], int (&nnz)[6]);
+template <> void sys_tables<3>(int (&off)[6], int (&n)[6], int (&nnz)[6]) {
+  typedef StateLayout<3> L;
+  int o[6] = {L::RHO11, L::RHO01, L::RHO10, L::COH11, L::COH01, L::COH10};
+  int s[6] = {Sys_rho11_d3::N, Sys_rho01_d3::N, Sys_rho10_d3::N, Sys_coh11_d3::N, Sys_coh01_d3::N, Sys_coh10_d3::N};
+  int z[6] = {Sys_rho11_d3::NNZ, Sys_rho01_d3::NNZ, Sys_rho10_d3::NNZ, Sys_coh11_d3::NNZ, Sys_coh01_d3::NNZ, Sys_coh10_d3::NNZ};
+  for (int i = 0; i < 6; ++i) { off[i] = o[i]; n[i] = s[i]; nnz[i] = z[i]; }
+}
+template <> void sys_tables<4>(int (&off)[6], int (&n)[6], int (&nnz)[6]) {
+  typedef StateLayout<4> L;
+  int o[6] = {L::RHO11, L::RHO01, L::RHO10, L::COH11, L::COH01, L::COH10};
+  int s[6] = {Sys_rho11_d4::N, Sys_rho01_d4::N, Sys_rho10_d4::N, Sys_coh11_d4::N, Sys_coh01_d4::N, Sys_coh10_d4::N};
+  int z[6] = {Sys_rho11_d4::NNZ, Sys_rho01_d4::NNZ, Sys_rho10_d4::NNZ, Sys_coh11_d4::NNZ, Sys_coh01_d4::NNZ, Sys_coh10_d4::NNZ};
+  for (int i = 0; i < 6; ++i) { off[i] = o[i]; n[i] = s[i]; nnz[i] = z[i]; }
+}
+static int sys_lookup(int dim, const char* name, int what) {
+  int off[6], n[6], nnz[6];
+  if (dim == 3) sys_tables<3>(off, n, nnz);
+  else if (dim == 4) sys_tables<4>(off, n, nnz);
+  else return -1;
+  if (!name) return -1;
+  for (int i = 0; i < 6; ++i)
+    if (strcmp(name, kSysNames[i]) == 0) return what == 0 ? off[i] : (what == 1 ? n[i] : nnz[i]);
+  return -1;
+}
+
+// order points heaviest-first; returns the device permutation (or nullptr when sorting is off)
+template <int D>
+static int make_order(rydcz_ctx* ctx, int64_t n, const double* d_points, const double* d_segs,
+                      const int32_t* d_n_seg, int max_seg, cudaStream_t st, const uint32_t** order) {
+  *order = nullptr;
+  if (!ctx->sort || n < 64) return 0;
+  if ((size_t)n > ctx->order_cap) {
+    cudaFree(ctx->keys); cudaFree(ctx->keys_sorted); cudaFree(ctx->idx); cudaFree(ctx->idx_sorted);
+    ctx->keys = ctx->keys_sorted = nullptr; ctx->idx = ctx->idx_sorted = nullptr; ctx->order_cap = 0;
+    CK(cudaMalloc(&ctx->keys, n * sizeof(float)));
+    CK(cudaMalloc(&ctx->keys_sorted, n * sizeof(float)));
+    CK(cudaMalloc(&ctx->idx, n * sizeof(uint32_t)));
+    CK(cudaMalloc(&ctx->idx_sorted, n * sizeof(uint32_t)));
+    ctx->order_cap = (size_t)n;
+  }
+  work_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_points, d_segs, d_n_seg, max_seg,
+                                                              ctx->keys, ctx->idx);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  size_t need = 0;
+  CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, ctx->keys, ctx->keys_sorted, ctx->idx,
+                                               ctx->idx_sorted, (int)n, 0, 32, st));
+  if (grow(ctx, &ctx->cub_tmp, &ctx->cub_cap, need)) return 1;
+  CK(cub::DeviceRadixSort::SortPairsDescending(ctx->cub_tmp, need, ctx->keys, ctx->keys_sorted, ctx->idx,
+                                               ctx->idx_sorted, (int)n, 0, 32, st));
+  *order = ctx->idx_sorted;
+  return 0;
+}
+
+template <int D, bool NOISY, bool SHOTS>
+static int launch_eval(rydcz_ctx* ctx, int64_t n_items, int n_shots, uint64_t seed, const uint32_t* order,
+                       const double* d_points, const double* d_segs, const int32_t* d_n_seg, int max_seg,
+                       double* d_out, double* d_states, cudaStream_t st) {
+  const unsigned grid = (unsigned)((n_items + kBlock - 1) / kBlock);
+  CK(cudaEventRecord(ctx->ev0, st));
+  evaluate_kernel<D, NOISY, SHOTS><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, order, d_points,
+                                                            d_segs, d_n_seg, max_seg, d_out, d_states);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(ctx->ev1, st));
+  ctx->timed = true;
+  ctx->launches++;
+  return 0;
+}
+
+extern "C" {
+
+int rydcz_version(void) { return 100; }
+int rydcz_point_stride(void) { return PT_STRIDE; }
+int rydcz_seg_stride(void) { return SG_STRIDE; }
+int rydcz_out_stride(void) { return OUT_STRIDE; }
+int rydcz_state_stride(int dim) {
+  return dim == 3 ? StateLayout<3>::STRIDE : (dim == 4 ? StateLayout<4>::STRIDE : -1);
+}
+int rydcz_state_offset(int dim, const char* system) { return sys_lookup(dim, system, 0); }
+int rydcz_system_size(int dim, const char* system) { return sys_lookup(dim, system, 1); }
+int rydcz_system_nnz(int dim, const char* system) { return sys_lookup(dim, system, 2); }
+
+int rydcz_create(int device, rydcz_ctx** out) {
+  if (!out) return 2;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+    return 1;
+  }
+  if (device < 0 || device >= count) { g_create_error = "device index out of range"; return 2; }
+  rydcz_ctx* ctx = new rydcz_ctx();
+  ctx->device = device;
+  if ((e = cudaSetDevice(device)) != cudaSuccess ||
+      (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (e = cudaEventCreate(&ctx->ev0)) != cudaSuccess || (e = cudaEventCreate(&ctx->ev1)) != cudaSuccess) {
+    g_create_error = std::string("context setup: ") + cudaGetErrorString(e);
+    delete ctx;
+    return 1;
+  }
+  *out = ctx;
+  return 0;
+}
+
+void rydcz_destroy(rydcz_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->keys); cudaFree(ctx->keys_sorted); cudaFree(ctx->idx); cudaFree(ctx->idx_sorted);
+  cudaFree(ctx->cub_tmp);
+  for (int i = 0; i < 6; ++i) cudaFree(ctx->stage[i]);
+  cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* rydcz_last_error(const rydcz_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int rydcz_set_sort(rydcz_ctx* ctx, int enable) {
+  if (!ctx) return 2;
+  ctx->sort = enable != 0;
+  return 0;
+}
+
+static int check_args(rydcz_ctx* ctx, int dim, int64_t n, const void* a, const void* b, int max_seg,
+                      const void* out) {
+  if (!ctx) return 2;
+  if (dim != 3 && dim != 4) return fail(ctx, "dim must be 3 or 4");
+  if (n < 0 || n > 0x7fffffffLL) return fail(ctx, "n_points out of range");
+  if (max_seg < 0) return fail(ctx, "max_seg must be >= 0");
+  if (n > 0 && (!a || !out || (max_seg > 0 && !b))) return fail(ctx, "null buffer");
+  return 0;
+}
+
+int rydcz_evaluate_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, const double* d_points,
+                          const double* d_segs, const int32_t* d_n_seg, int max_seg, double* d_out,
+                          double* d_states, void* stream) {
+  if (int rc = check_args(ctx, dim, n_points, d_points, d_segs, max_seg, d_out)) return rc;
+  if (n_points == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  const uint32_t* order = nullptr;
+  int rc = dim == 3 ? make_order<3>(ctx, n_points, d_points, d_segs, d_n_seg, max_seg, st, &order)
+                    : make_order<4>(ctx, n_points, d_points, d_segs, d_n_seg, max_seg, st, &order);
+  if (rc) return rc;
+#define RYDCZ_GO(D, N)                                                                             \
+  return launch_eval<D, N, false>(ctx, n_points, 1, 0, order, d_points, d_segs, d_n_seg, max_seg,   \
+                                  d_out, d_states, st)
+  if (dim == 3) { if (noisy) RYDCZ_GO(3, true); else RYDCZ_GO(3, false); }
+  else { if (noisy) RYDCZ_GO(4, true); else RYDCZ_GO(4, false); }
+#undef RYDCZ_GO
+}
+
+int rydcz_evaluate_shots_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, int n_shots,
+                                uint64_t seed, const double* d_points, const double* d_segs,
+                                const int32_t* d_n_seg, int max_seg, double* d_out_mean,
+                                double* d_out_shots, void* stream) {
+  if (int rc = check_args(ctx, dim, n_points, d_points, d_segs, max_seg, d_out_mean)) return rc;
+  if (n_shots < 1) return fail(ctx, "n_shots must be >= 1");
+  if (n_points * (int64_t)n_shots > 0x7fffffffLL) return fail(ctx, "n_points * n_shots too large");
+  if (n_points == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  const int64_t n_items = n_points * n_shots;
+  double* shots = d_out_shots;
+  if (!shots) {
+    if (grow(ctx, &ctx->stage[5], &ctx->stage_cap[5], n_items * OUT_STRIDE * sizeof(double))) return 1;
+    shots = (double*)ctx->stage[5];
+  }
+  const uint32_t* order = nullptr;
+  int rc = dim == 3 ? make_order<3>(ctx, n_points, d_points, d_segs, d_n_seg, max_seg, st, &order)
+                    : make_order<4>(ctx, n_points, d_points, d_segs, d_n_seg, max_seg, st, &order);
+  if (rc) return rc;
+#define RYDCZ_GO(D, N)                                                                               \
+  rc = launch_eval<D, N, true>(ctx, n_items, n_shots, seed, order, d_points, d_segs, d_n_seg, max_seg, \
+                               shots, nullptr, st)
+  if (dim == 3) { if (noisy) RYDCZ_GO(3, true); else RYDCZ_GO(3, false); }
+  else { if (noisy) RYDCZ_GO(4, true); else RYDCZ_GO(4, false); }
+#undef RYDCZ_GO
+  if (rc) return rc;
+  const int64_t threads = n_points * 32;
+  shot_mean_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(n_points, n_shots, shots, d_out_mean);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+static int stage_in(rydcz_ctx* ctx, int slot, const void* h, size_t bytes) {
+  if (grow(ctx, &ctx->stage[slot], &ctx->stage_cap[slot], bytes ? bytes : 8)) return 1;
+  if (bytes) CK(cudaMemcpyAsync(ctx->stage[slot], h, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+int rydcz_evaluate_host(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, const double* h_points,
+                        const double* h_segs, const int32_t* h_n_seg, int max_seg, double* h_out,
+                        double* h_states) {
+  if (int rc = check_args(ctx, dim, n_points, h_points, h_segs, max_seg, h_out)) return rc;
+  if (n_points == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)n_points;
+  const size_t sb = (size_t)rydcz_state_stride(dim) * sizeof(double);
+  if (stage_in(ctx, 0, h_points, n * PT_STRIDE * sizeof(double))) return 1;
+  if (stage_in(ctx, 1, h_segs, n * max_seg * SG_STRIDE * sizeof(double))) return 1;
+  if (h_n_seg && stage_in(ctx, 2, h_n_seg, n * sizeof(int32_t))) return 1;
+  if (grow(ctx, &ctx->stage[3], &ctx->stage_cap[3], n * OUT_STRIDE * sizeof(double))) return 1;
+  if (h_states && grow(ctx, &ctx->stage[4], &ctx->stage_cap[4], n * sb)) return 1;
+  int rc = rydcz_evaluate_device(ctx, dim, noisy, n_points, (const double*)ctx->stage[0],
+                                 (const double*)ctx->stage[1], h_n_seg ? (const int32_t*)ctx->stage[2] : nullptr,
+                                 max_seg, (double*)ctx->stage[3], h_states ? (double*)ctx->stage[4] : nullptr,
+                                 nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h_out, ctx->stage[3], n * OUT_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (h_states) CK(cudaMemcpyAsync(h_states, ctx->stage[4], n * sb, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int rydcz_evaluate_shots_host(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, int n_shots, uint64_t seed,
+                              const double* h_points, const double* h_segs, const int32_t* h_n_seg,
+                              int max_seg, double* h_out_mean, double* h_out_shots) {
+  if (int rc = check_args(ctx, dim, n_points, h_points, h_segs, max_seg, h_out_mean)) return rc;
+  if (n_shots < 1) return fail(ctx, "n_shots must be >= 1");
+  if (n_points == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)n_points;
+  if (stage_in(ctx, 0, h_points, n * PT_STRIDE * sizeof(double))) return 1;
+  if (stage_in(ctx, 1, h_segs, n * max_seg * SG_STRIDE * sizeof(double))) return 1;
+  if (h_n_seg && stage_in(ctx, 2, h_n_seg, n * sizeof(int32_t))) return 1;
+  if (grow(ctx, &ctx->stage[3], &ctx->stage_cap[3], n * OUT_STRIDE * sizeof(double))) return 1;
+  if (grow(ctx, &ctx->stage[5], &ctx->stage_cap[5], n * n_shots * OUT_STRIDE * sizeof(double))) return 1;
+  int rc = rydcz_evaluate_shots_device(ctx, dim, noisy, n_points, n_shots, seed, (const double*)ctx->stage[0],
+                                       (const double*)ctx->stage[1],
+                                       h_n_seg ? (const int32_t*)ctx->stage[2] : nullptr, max_seg,
+                                       (double*)ctx->stage[3], (double*)ctx->stage[5], nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h_out_mean, ctx->stage[3], n * OUT_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (h_out_shots)
+    CK(cudaMemcpyAsync(h_out_shots, ctx->stage[5], n * n_shots * OUT_STRIDE * sizeof(double),
+                       cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int rydcz_last_kernel_ms(rydcz_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return 2;
+  if (!ctx->timed) return fail(ctx, "no evaluate kernel has been launched yet");
+  CK(cudaEventSynchronize(ctx->ev1));
+  CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+  return 0;
+}
+
+int rydcz_launch_count(const rydcz_ctx* ctx, int64_t* n) {
+  if (!ctx || !n) return 2;
+  *n = ctx->launches;
+  return 0;
+}
+
+int rydcz_fp64_peak(rydcz_ctx* ctx, double* dfma_tflops, double* dmma_tflops) {
+  if (!ctx) return 2;
+  CK(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, ctx->device));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  double* buf = nullptr;
+  CK(cudaMalloc(&buf, (size_t)blocks * threads * sizeof(double)));
+  float best_f = 1e30f, best_m = 1e30f, ms;
+  for (int rep = 0; rep < 6; ++rep) {
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(buf, iters, 0.999999, 1e-7);
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (rep > 0 && ms < best_f) best_f = ms;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    dmma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(buf, iters, 0.999999, 1e-7);
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (rep > 0 && ms < best_m) best_m = ms;
+    ctx->launches += 2;
+  }
+  CK(cudaGetLastError());
+  CK(cudaFree(buf));
+  ctx->timed = false;
+  const double fma_flops = 2.0 * 16 * 8 * (double)iters * blocks * threads;
+  const double mma_flops = 2.0 * 256 * 8 * 4 * (double)iters * blocks * (threads / 32);
+  if (dfma_tflops) *dfma_tflops = fma_flops / (best_f * 1e-3) * 1e-12;
+  if (dmma_tflops) *dmma_tflops = mma_flops / (best_m * 1e-3) * 1e-12;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,335 @@
+// rydcz_core.cuh -- per-evaluation arithmetic of the Rydberg-CZ hot path.
+//
+// One gate evaluation = the reference's simulate_CZ_gate steps 11-13
+// (RG/simulation.py:3364-3572): evolve |00>,|01>,|10>,|11> through S constant-H
+// segments (one QuTiP mesolve per input and segment, RG/simulation.py:689) and reduce to
+// fidelities (compute_CZ_fidelity, RG/simulation.py:225-633).
+//
+// Method.  The Lindblad generator is linear in a few scalars and closes on a small operator
+// subspace for each start operator (codegen/model.py).  Each such real system x' = G x
+// (n = 25 for rho_11, 8 for the |11><00| coherence, 5/4 for the single-atom inputs) lives
+// entirely in registers.  A constant segment is advanced exactly (to rounding) by the
+// Chebyshev expansion of exp(tau G) on the imaginary-axis interval that Gershgorin bounds,
+//
+//     exp(tau G) x = J_0(z) x + 2 sum_{k>=1} J_k(z) phi_k(G/R) x,   z = R tau,
+//     phi_0 = I, phi_1 = A, phi_{k+1} = 2 A phi_k + phi_{k-1}      (phi_k(A) = i^k T_k(A/i)),
+//
+// summed with Clenshaw's backward recurrence while Miller's backward recurrence produces the
+// (unnormalised) Bessel coefficients on the fly, so no coefficient table is stored and the
+// work is K ~ z + 10.3 z^(1/3) + 4 sparse matvecs per segment.  Cost is proportional to
+// ||H|| tau, with no step-size control, no rejected steps and no dependence on the number of
+// tlist points the reference requests.
+//
+// This header is plain C++ when RYDCZ_HD is empty, so tests/hostsim can compile the very same
+// arithmetic with g++ (a test harness; the product path is the CUDA kernel only).
+#pragma once
+#include <math.h>
+
+#ifndef RYDCZ_HD
+#ifdef __CUDACC__
+#define RYDCZ_HD __host__ __device__ __forceinline__
+#else
+#define RYDCZ_HD inline
+#endif
+#endif
+
+#ifndef RYDCZ_UNROLL
+#ifdef __CUDACC__
+#define RYDCZ_UNROLL _Pragma("unroll")
+#else
+#define RYDCZ_UNROLL
+#endif
+#endif
+
+namespace rydcz {
+
+#include "rydcz_systems_d3.inc"
+#include "rydcz_systems_d4.inc"
+
+// ---- layout of one point row (doubles) -------------------------------------------------
+// Everything the generator needs that is constant over the pulse.
+enum PointSlot {
+  PT_V = 0,        // blockade shift V (rad/s)                      RG/simulation.py:2958-2959
+  PT_DELTA1 = 1,   // delta_zeeman + delta_stark on |1> (rad/s)      RG/simulation.py:3129-3159
+  PT_OFF_A = 2,    // extra detuning seen by atom A (Doppler shot), rad/s
+  PT_OFF_B = 3,    // extra detuning seen by atom B
+  PT_G_R1 = 4,     // Gamma r->1 = gamma_r * b                       RG/noise_models.py:1237-1239
+  PT_G_R0 = 5,     // Gamma r->0 = gamma_r(1-b)+bbr+antitrap+bg+leak  RG/noise_models.py:1242-1251,1583-1592
+  PT_G_PHI = 6,    // dephasing on |r><r| (laser+thermal+zeeman)      RG/noise_models.py:1579-1580
+  PT_G_SC = 7,     // scattering on |1><1|                            RG/noise_models.py:1589
+  PT_G_MJ = 8,     // r+ <-> r- mixing (4-level only)                 RG/noise_models.py:1287-1295
+  PT_SIG_DET = 9,  // Monte-Carlo: std of the per-atom Doppler detuning k_eff*v_rms (rad/s)
+  PT_SIG_RELR = 10,// Monte-Carlo: std of dR/R0 = sqrt(2) sigma_r / R0
+  PT_RESERVED = 11,
+  PT_STRIDE = 12
+};
+// one segment row: dt (s), Re Omega, Im Omega, Delta (rad/s)
+enum SegSlot { SG_DT = 0, SG_RE = 1, SG_IM = 2, SG_DET = 3, SG_STRIDE = 4 };
+
+// per-point output row
+enum OutSlot {
+  OUT_AVG_F = 0,      // avg_fidelity                         RG/simulation.py:631
+  OUT_F00 = 1, OUT_F01 = 2, OUT_F10 = 3,
+  OUT_F11 = 4,        // F11 population * cz_phase_fidelity   RG/simulation.py:619-629
+  OUT_F11_POP = 5,
+  OUT_CZ_PHASE_FID = 6,
+  OUT_CTRL_PHASE = 7, // controlled phase in (-pi, pi]        RG/simulation.py:607-608
+  OUT_PHASE_ERR = 8,  // min(|c-pi|, |c+pi|)                  RG/simulation.py:610
+  OUT_PHI01 = 9, OUT_PHI10 = 10, OUT_PHI11 = 11,
+  OUT_LOSS = 12,      // |11> input: probability that an atom ended in |0> (all 'loss' channels land there)
+  OUT_RYD = 13,       // |11> input: probability that an atom is left in a Rydberg level
+  OUT_STEPS = 14,     // Chebyshev matvecs performed (work counter for the FLOP accounting)
+  OUT_FLOPS = 15,     // useful FP64 flops performed = sum 2*(NNZ+N)*steps over the systems
+  OUT_STRIDE = 16
+};
+
+// raw reduced states, written when the caller asks for rho (compat epilogue, rho parity)
+template <int D> struct StateLayout;
+template <> struct StateLayout<3> {
+  static constexpr int RHO11 = 0, RHO01 = 25, RHO10 = 30, COH11 = 35, COH01 = 43, COH10 = 47, STRIDE = 51;
+};
+template <> struct StateLayout<4> {
+  static constexpr int RHO11 = 0, RHO01 = 36, RHO10 = 42, COH11 = 48, COH01 = 56, COH10 = 60, STRIDE = 64;
+};
+
+RYDCZ_HD int cheb_terms(double z) {
+  // smallest even K with |J_k(z)| < ~1e-15 for all k > K (fit checked in tests/test_oracle_golden.py)
+  int K = (int)ceil(z + 10.3 * cbrt(z) + 4.0);
+  return K + (K & 1);
+}
+
+// Work estimate used to order points (same formula the evolution uses).
+RYDCZ_HD double cheb_work(double radius, double dt) {
+  double z = radius * fabs(dt);
+  if (!(z > 0.0)) return 0.0;
+  return z + 10.3 * cbrt(z) + 5.0;
+}
+
+// x <- exp(h G) x, repeated nsub times, where c[] already holds 2 G / R and z = R h.
+template <class Sys>
+RYDCZ_HD void cheb_advance(double (&x)[Sys::N], const double (&c)[Sys::NC], double z, int nsub,
+                           double& steps) {
+  constexpr int N = Sys::N;
+  const int K = cheb_terms(z);
+  const double tz = 2.0 / z;
+  for (int sub = 0; sub < nsub; ++sub) {
+    double b1[N], b2[N];
+    RYDCZ_UNROLL
+    for (int i = 0; i < N; ++i) { b1[i] = 0.0; b2[i] = 0.0; }
+    double jp = 0.0, jk = 1e-30;   // J_{k+1}, J_k up to a common factor (Miller)
+    double norm = 0.0;             // J_0 + 2 sum_{even k} J_k = 1 fixes the factor
+    double kd = (double)K;
+    for (int k = K; k >= 2; k -= 2) {
+      // k even:  b2 <- 2 J_k x + (2A) b1 + b2
+      double ak = jk + jk;
+      RYDCZ_UNROLL
+      for (int i = 0; i < N; ++i) b2[i] = fma(ak, x[i], b2[i]);
+      Sys::apply(c, b1, b2);
+      norm += ak;
+      double jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
+      // k-1 odd: b1 <- 2 J_{k-1} x + (2A) b2 + b1
+      ak = jk + jk;
+      RYDCZ_UNROLL
+      for (int i = 0; i < N; ++i) b1[i] = fma(ak, x[i], b1[i]);
+      Sys::apply(c, b2, b1);
+      jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
+    }
+    // k = 0:  S = J_0 x + A b1 + b2, with A b1 = (2A b1)/2
+    double t[N];
+    RYDCZ_UNROLL
+    for (int i = 0; i < N; ++i) t[i] = 0.0;
+    Sys::apply(c, b1, t);
+    const double inv = 1.0 / (norm + jk);
+    RYDCZ_UNROLL
+    for (int i = 0; i < N; ++i) x[i] = (fma(jk, x[i], b2[i]) + 0.5 * t[i]) * inv;
+    steps += (double)(K + 1);
+  }
+}
+
+// Advance one constant-generator segment of duration dt.  p[] is the parameter vector of the
+// system (Sys::NP entries; for coherence systems the last one is the spectral shift, set here).
+template <class Sys>
+RYDCZ_HD void evolve_segment(double (&x)[Sys::N], double (&p)[Sys::NP], double dt, double& steps) {
+  // dt < 0 happens in the reference when Delta_e < 0 makes Omega (hence tau = Omega*tau/Omega)
+  // negative: mesolve then integrates backwards, i.e. applies exp(-|dt| G).  Reproduced here.
+  if (dt == 0.0 || dt != dt) return;
+  const double sgn = dt < 0.0 ? -1.0 : 1.0;
+  const double adt = fabs(dt);
+  double c[Sys::NC];
+  double lo, hi, damp;
+  if (!Sys::HERMITIAN) p[Sys::NP - 1] = 0.0;
+  Sys::coefs(p, c);
+  Sys::bounds(c, lo, hi, damp);
+  double cen = 0.0, R;
+  if (Sys::HERMITIAN) {
+    R = hi;
+  } else {
+    cen = 0.5 * (lo + hi);
+    R = 0.5 * (hi - lo) + damp;
+    p[Sys::NP - 1] = cen;
+    Sys::coefs(p, c);
+  }
+  // strong damping pushes the spectrum off the imaginary axis; keep damp*h <= 2 per sub-step so
+  // the Chebyshev polynomials stay O(e^2) ("Chebyshev interval").
+  int nsub = 1;
+  if (damp * adt > 2.0) nsub = (int)ceil(0.5 * damp * adt);
+  const double h = adt / (double)nsub;
+  // a wider interval is always valid; never let z underflow the Miller recurrence
+  if (!(R * h >= 1e-2)) R = 1e-2 / h;
+  const double z = R * h;
+  const double s = sgn * 2.0 / R;
+  RYDCZ_UNROLL
+  for (int q = 0; q < Sys::NC; ++q) c[q] *= s;
+  cheb_advance<Sys>(x, c, z, nsub, steps);
+  if (!Sys::HERMITIAN) {
+    // undo the shift: multiply every complex component by exp(-i cen dt)
+    double sn, cs;
+    sincos(cen * dt, &sn, &cs);
+    RYDCZ_UNROLL
+    for (int i = 0; i < Sys::N; i += 2) {
+      const double re = x[i], im = x[i + 1];
+      x[i] = fma(re, cs, im * sn);
+      x[i + 1] = fma(im, cs, -re * sn);
+    }
+  }
+}
+
+// Run one system through all segments of a point.
+template <class Sys>
+RYDCZ_HD void run_system(double (&x)[Sys::N], const double* __restrict__ pt,
+                         const double* __restrict__ seg, int n_seg, bool noisy, double& steps) {
+  RYDCZ_UNROLL
+  for (int i = 0; i < Sys::N; ++i) x[i] = (i == Sys::START) ? 1.0 : 0.0;
+  double p[Sys::NP];
+  p[4] = pt[PT_V];
+  p[5] = pt[PT_DELTA1];
+  p[6] = noisy ? pt[PT_G_R1] : 0.0;
+  p[7] = noisy ? pt[PT_G_R0] : 0.0;
+  p[8] = noisy ? pt[PT_G_PHI] : 0.0;
+  p[9] = noisy ? pt[PT_G_SC] : 0.0;
+  if (Sys::NP - (Sys::HERMITIAN ? 0 : 1) > 10) p[10] = noisy ? pt[PT_G_MJ] : 0.0;
+  const double offa = pt[PT_OFF_A], offb = pt[PT_OFF_B];
+  for (int s = 0; s < n_seg; ++s) {
+    const double* sg = seg + (long long)s * SG_STRIDE;
+    p[0] = sg[SG_RE];
+    p[1] = sg[SG_IM];
+    p[2] = sg[SG_DET] + offa;
+    p[3] = sg[SG_DET] + offb;
+    evolve_segment<Sys>(x, p, sg[SG_DT], steps);
+  }
+}
+
+RYDCZ_HD double wrap_pi(double x) {
+  // Python: (x + pi) % (2 pi) - pi, with % taking the sign of the divisor  (RG/simulation.py:608)
+  const double twopi = 6.283185307179586476925286766559;
+  const double pi = 3.141592653589793238462643383279;
+  double y = x + pi;
+  y = y - twopi * floor(y / twopi);
+  return y - pi;
+}
+
+// Fidelity epilogue (compute_CZ_fidelity, RG/simulation.py:225-633).
+//   noiseless: pure-state branch -- F_ab = |<ab|psi_ab>|^2, phases from the overlaps.
+//   noisy    : populations F_ab = <ab|rho_ab|ab>; phases from the coherences <ab|E(|ab><00|)|00>
+//              (gauge-free replacement for the reference's dominant-eigenvector phases; the
+//              reference's own number is recomputed on the host from rho in 'compat' mode).
+RYDCZ_HD void cz_epilogue(bool noisy, double p01, double p10, double p11,
+                          double c01r, double c01i, double c10r, double c10i, double c11r, double c11i,
+                          double* __restrict__ out) {
+  const double pi = 3.141592653589793238462643383279;
+  double f00 = 1.0, f01, f10, f11;
+  if (noisy) { f01 = p01; f10 = p10; f11 = p11; }
+  else {
+    f01 = c01r * c01r + c01i * c01i;
+    f10 = c10r * c10r + c10i * c10i;
+    f11 = c11r * c11r + c11i * c11i;
+  }
+  const double phi01 = atan2(c01i, c01r), phi10 = atan2(c10i, c10r), phi11 = atan2(c11i, c11r);
+  const double ctrl = wrap_pi(phi11 - phi01 - phi10 + 0.0);
+  const double err = fmin(fabs(ctrl - pi), fabs(ctrl + pi));
+  const double ch = cos(0.5 * err);
+  const double czf = ch * ch;
+  out[OUT_F00] = f00; out[OUT_F01] = f01; out[OUT_F10] = f10;
+  out[OUT_F11_POP] = f11;
+  out[OUT_F11] = f11 * czf;
+  out[OUT_CZ_PHASE_FID] = czf;
+  out[OUT_CTRL_PHASE] = ctrl;
+  out[OUT_PHASE_ERR] = err;
+  out[OUT_PHI01] = phi01; out[OUT_PHI10] = phi10; out[OUT_PHI11] = phi11;
+  out[OUT_AVG_F] = 0.25 * (f00 + f01 + f10 + f11 * czf);
+}
+
+// One full gate evaluation.  `states` (may be null) receives the raw reduced states.
+#define RYDCZ_DEFINE_EVALUATE(D)                                                                    \
+  template <bool NOISY>                                                                             \
+  RYDCZ_HD void evaluate_point_d##D(const double* __restrict__ pt, const double* __restrict__ seg,  \
+                                    int n_seg, double* __restrict__ out,                            \
+                                    double* __restrict__ states) {                                  \
+    typedef StateLayout<D> SL;                                                                      \
+    double steps = 0.0, flops = 0.0, st;                                                            \
+    double p01 = 1.0, p10 = 1.0, p11 = 1.0, loss = 0.0, ryd = 0.0;                                  \
+    double c01r, c01i, c10r, c10i, c11r, c11i;                                                      \
+    if (NOISY) {                                                                                    \
+      double x[Sys_rho11_d##D::N]; st = 0.0;                                                        \
+      run_system<Sys_rho11_d##D>(x, pt, seg, n_seg, true, st);                                      \
+      steps += st; flops += st * 2.0 * (Sys_rho11_d##D::NNZ + Sys_rho11_d##D::N);                   \
+      p11 = x[RHO11_POP_D##D];                                                                      \
+      loss = rho11_loss_d##D(x); ryd = rho11_ryd_d##D(x);                                           \
+      if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_rho11_d##D::N; ++i) states[SL::RHO11 + i] = x[i]; } \
+    }                                                                                               \
+    {                                                                                               \
+      double x[Sys_coh11_d##D::N]; st = 0.0;                                                        \
+      run_system<Sys_coh11_d##D>(x, pt, seg, n_seg, NOISY, st);                                     \
+      steps += st; flops += st * 2.0 * (Sys_coh11_d##D::NNZ + Sys_coh11_d##D::N);                   \
+      c11r = x[COH11_RE_D##D]; c11i = x[COH11_IM_D##D];                                             \
+      if (!NOISY) ryd = 1.0 - (c11r * c11r + c11i * c11i);                                          \
+      if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh11_d##D::N; ++i) states[SL::COH11 + i] = x[i]; } \
+    }                                                                                               \
+    if (NOISY) {                                                                                    \
+      double x[Sys_rho01_d##D::N]; st = 0.0;                                                        \
+      run_system<Sys_rho01_d##D>(x, pt, seg, n_seg, true, st);                                      \
+      steps += st; flops += st * 2.0 * (Sys_rho01_d##D::NNZ + Sys_rho01_d##D::N);                   \
+      p01 = x[RHO01_POP_D##D];                                                                      \
+      if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_rho01_d##D::N; ++i) states[SL::RHO01 + i] = x[i]; } \
+      double y[Sys_rho10_d##D::N]; st = 0.0;                                                        \
+      run_system<Sys_rho10_d##D>(y, pt, seg, n_seg, true, st);                                      \
+      steps += st; flops += st * 2.0 * (Sys_rho10_d##D::NNZ + Sys_rho10_d##D::N);                   \
+      p10 = y[RHO10_POP_D##D];                                                                      \
+      if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_rho10_d##D::N; ++i) states[SL::RHO10 + i] = y[i]; } \
+    }                                                                                               \
+    {                                                                                               \
+      double x[Sys_coh01_d##D::N]; st = 0.0;                                                        \
+      run_system<Sys_coh01_d##D>(x, pt, seg, n_seg, NOISY, st);                                     \
+      steps += st; flops += st * 2.0 * (Sys_coh01_d##D::NNZ + Sys_coh01_d##D::N);                   \
+      c01r = x[COH01_RE_D##D]; c01i = x[COH01_IM_D##D];                                             \
+      if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d##D::N; ++i) states[SL::COH01 + i] = x[i]; } \
+      double y[Sys_coh10_d##D::N]; st = 0.0;                                                        \
+      run_system<Sys_coh10_d##D>(y, pt, seg, n_seg, NOISY, st);                                     \
+      steps += st; flops += st * 2.0 * (Sys_coh10_d##D::NNZ + Sys_coh10_d##D::N);                   \
+      c10r = y[COH10_RE_D##D]; c10i = y[COH10_IM_D##D];                                             \
+      if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh10_d##D::N; ++i) states[SL::COH10 + i] = y[i]; } \
+    }                                                                                               \
+    cz_epilogue(NOISY, p01, p10, p11, c01r, c01i, c10r, c10i, c11r, c11i, out);                     \
+    out[OUT_LOSS] = loss; out[OUT_RYD] = ryd; out[OUT_STEPS] = steps; out[OUT_FLOPS] = flops;       \
+  }
+
+RYDCZ_DEFINE_EVALUATE(3)
+RYDCZ_DEFINE_EVALUATE(4)
+
+// Gershgorin radius of the stiffest system (rho_11, or coh_11 when noiseless) for one segment:
+// the work estimate used to sort points so that the threads of a warp run equally long.
+template <int D>
+RYDCZ_HD double point_work(const double* __restrict__ pt, const double* __restrict__ seg, int n_seg) {
+  double w = 0.0;
+  const double V = fabs(pt[PT_V]);
+  const double damp = pt[PT_G_R1] + pt[PT_G_R0] + pt[PT_G_PHI] + pt[PT_G_SC];
+  for (int s = 0; s < n_seg; ++s) {
+    const double* sg = seg + (long long)s * SG_STRIDE;
+    const double R = V + 2.0 * (fabs(sg[SG_RE]) + fabs(sg[SG_IM])) + 2.0 * fabs(sg[SG_DET]) +
+                     fabs(pt[PT_OFF_A]) + fabs(pt[PT_OFF_B]) + 2.0 * fabs(pt[PT_DELTA1]) + 2.0 * damp;
+    w += cheb_work(R, sg[SG_DT]);
+  }
+  return w;
+}
+
+}  // namespace rydcz

@@ -1,0 +1,168 @@
+"""Batched CZ-gate evaluation on one B200 through the C ABI (include/rydcz.h).
+
+``Evaluator`` is the thin host layer between the reference-facing Python API
+(``rydberg_gates.simulation``) and the CUDA kernels.  torch is used for device memory,
+streams and (in ``sharding``) torch.distributed; the arithmetic is all in csrc/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _lib
+
+OUT = dict(avg_fidelity=0, f00=1, f01=2, f10=3, f11=4, f11_pop=5, cz_phase_fidelity=6,
+           controlled_phase=7, phase_error=8, phi01=9, phi10=10, phi11=11, loss=12, rydberg=13,
+           steps=14, flops=15)
+
+
+class RydczError(RuntimeError):
+    pass
+
+
+def _host(a, dtype):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a, a.ctypes.data
+
+
+class Evaluator:
+    """One CUDA context-bound evaluator (one per process and GPU)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        self.device = int(device)
+        ctx = C.c_void_p()
+        rc = self.lib.rydcz_create(self.device, C.byref(ctx))
+        if rc != 0:
+            msg = self.lib.rydcz_last_error(None)
+            raise RydczError(f"rydcz_create(device={device}) failed: "
+                             f"{msg.decode() if msg else rc} -- a CUDA GPU is required")
+        self.ctx = ctx
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.rydcz_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.rydcz_last_error(self.ctx)
+            raise RydczError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    # ------------------------------------------------------------------ host buffers
+    def evaluate_host(self, dim: int, noisy: bool, points, segs, n_seg=None,
+                      want_states: bool = False) -> Tuple[np.ndarray, Optional[np.ndarray]]:
+        """points [B,12], segs [B,S,4], n_seg [B] int32 (None = all S).  Returns (out [B,16],
+        states [B,stride] or None).  H2D, kernels and D2H all happen inside the C call."""
+        points, p_ptr = _host(points, np.float64)
+        segs, s_ptr = _host(segs, np.float64)
+        B = points.shape[0]
+        assert points.shape == (B, _lib.POINT_STRIDE) and segs.ndim == 3 and segs.shape[0] == B \
+            and segs.shape[2] == _lib.SEG_STRIDE, (points.shape, segs.shape)
+        n_ptr = None
+        if n_seg is not None:
+            n_seg, n_ptr = _host(n_seg, np.int32)
+            assert n_seg.shape == (B,) and (B == 0 or int(n_seg.max()) <= segs.shape[1])
+        out = np.empty((B, _lib.OUT_STRIDE))
+        states = np.empty((B, self.lib.rydcz_state_stride(dim))) if want_states else None
+        self._check(self.lib.rydcz_evaluate_host(
+            self.ctx, dim, int(bool(noisy)), B, p_ptr, s_ptr, n_ptr, segs.shape[1],
+            out.ctypes.data, states.ctypes.data if want_states else None), "rydcz_evaluate_host")
+        return out, states
+
+    def evaluate_shots_host(self, dim: int, noisy: bool, n_shots: int, seed: int, points, segs,
+                            n_seg=None, want_shots: bool = False):
+        points, p_ptr = _host(points, np.float64)
+        segs, s_ptr = _host(segs, np.float64)
+        B = points.shape[0]
+        n_ptr = None
+        if n_seg is not None:
+            n_seg, n_ptr = _host(n_seg, np.int32)
+        mean = np.empty((B, _lib.OUT_STRIDE))
+        shots = np.empty((B, n_shots, _lib.OUT_STRIDE)) if want_shots else None
+        self._check(self.lib.rydcz_evaluate_shots_host(
+            self.ctx, dim, int(bool(noisy)), B, int(n_shots), int(seed), p_ptr, s_ptr, n_ptr,
+            segs.shape[1], mean.ctypes.data, shots.ctypes.data if want_shots else None),
+            "rydcz_evaluate_shots_host")
+        return mean, shots
+
+    # ------------------------------------------------------------------ device tensors (torch)
+    def evaluate_device(self, dim: int, noisy: bool, points, segs, n_seg=None, out=None,
+                        states=None, want_states: bool = False, stream=None):
+        """Same with CUDA torch tensors already in HBM; enqueues on the current torch stream and
+        returns (out, states) tensors without synchronising."""
+        import torch
+
+        assert points.is_cuda and segs.is_cuda and points.dtype == torch.float64
+        points, segs = points.contiguous(), segs.contiguous()
+        B = points.shape[0]
+        if out is None:
+            out = torch.empty((B, _lib.OUT_STRIDE), dtype=torch.float64, device=points.device)
+        if want_states and states is None:
+            states = torch.empty((B, self.lib.rydcz_state_stride(dim)), dtype=torch.float64,
+                                 device=points.device)
+        if n_seg is not None:
+            n_seg = n_seg.contiguous()
+            assert n_seg.dtype == torch.int32
+        st = stream if stream is not None else torch.cuda.current_stream(points.device).cuda_stream
+        self._check(self.lib.rydcz_evaluate_device(
+            self.ctx, dim, int(bool(noisy)), B, points.data_ptr(), segs.data_ptr(),
+            n_seg.data_ptr() if n_seg is not None else None, segs.shape[1], out.data_ptr(),
+            states.data_ptr() if states is not None else None, st), "rydcz_evaluate_device")
+        return out, states
+
+    def evaluate_shots_device(self, dim: int, noisy: bool, n_shots: int, seed: int, points, segs,
+                              n_seg=None, mean=None, shots=None, want_shots=False, stream=None):
+        import torch
+
+        points, segs = points.contiguous(), segs.contiguous()
+        B = points.shape[0]
+        if mean is None:
+            mean = torch.empty((B, _lib.OUT_STRIDE), dtype=torch.float64, device=points.device)
+        if want_shots and shots is None:
+            shots = torch.empty((B, n_shots, _lib.OUT_STRIDE), dtype=torch.float64,
+                                device=points.device)
+        st = stream if stream is not None else torch.cuda.current_stream(points.device).cuda_stream
+        self._check(self.lib.rydcz_evaluate_shots_device(
+            self.ctx, dim, int(bool(noisy)), B, int(n_shots), int(seed), points.data_ptr(),
+            segs.data_ptr(), n_seg.data_ptr() if n_seg is not None else None, segs.shape[1],
+            mean.data_ptr(), shots.data_ptr() if shots is not None else None, st),
+            "rydcz_evaluate_shots_device")
+        return mean, shots
+
+    # ------------------------------------------------------------------ measurement
+    def set_sort(self, enable: bool):
+        self._check(self.lib.rydcz_set_sort(self.ctx, int(enable)), "rydcz_set_sort")
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self.lib.rydcz_last_kernel_ms(self.ctx, C.byref(ms)), "rydcz_last_kernel_ms")
+        return float(ms.value)
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        self._check(self.lib.rydcz_launch_count(self.ctx, C.byref(n)), "rydcz_launch_count")
+        return int(n.value)
+
+    def fp64_peak(self) -> Tuple[float, float]:
+        """(DFMA TFLOP/s, DMMA TFLOP/s) measured on this GPU by register-resident microbenchmarks."""
+        a, b = C.c_double(), C.c_double()
+        self._check(self.lib.rydcz_fp64_peak(self.ctx, C.byref(a), C.byref(b)), "rydcz_fp64_peak")
+        return float(a.value), float(b.value)
+
+
+_default = {}
+
+
+def get_evaluator(device: int = 0) -> Evaluator:
+    if device not in _default:
+        _default[device] = Evaluator(device)
+    return _default[device]

@@ -1,0 +1,122 @@
+"""Shared helpers for the parity tests: golden loading, packing into the C-ABI layout."""
+from __future__ import annotations
+
+import json
+import os
+from functools import lru_cache
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+
+PT_STRIDE, SG_STRIDE, OUT_STRIDE = 12, 4, 16
+OUT = dict(avg=0, f00=1, f01=2, f10=3, f11=4, f11_pop=5, czf=6, ctrl=7, err=8, phi01=9, phi10=10,
+           phi11=11, loss=12, ryd=13, steps=14, flops=15)
+STATE_STRIDE = {3: 51, 4: 64}
+STATE_OFFSETS = {3: dict(rho11=0, rho01=25, rho10=30, coh11=35, coh01=43, coh10=47),
+                 4: dict(rho11=0, rho01=36, rho10=42, coh11=48, coh01=56, coh10=60)}
+
+
+@lru_cache(None)
+def load(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)["cases"]
+
+
+def collapsed_rates(r):
+    """(Γ_r→1, Γ_r→0, γ_φ, γ_sc, γ_mJ) from the ten reference rates (same-operator terms add)."""
+    if r is None:
+        return (0.0,) * 5
+    b = r.get("branching_1", 0.5)
+    return (r["gamma_r"] * b,
+            r["gamma_r"] * (1 - b) + r["gamma_bbr"] + r["gamma_loss_antitrap"]
+            + r["gamma_loss_background"] + r["gamma_leakage"],
+            r["gamma_phi_laser"] + r["gamma_phi_thermal"] + r["gamma_phi_zeeman"],
+            r["gamma_scatter_intermediate"], r["mJ_leakage_rate"])
+
+
+def pack_point(V, delta1, rates5=(0, 0, 0, 0, 0), off=(0.0, 0.0), sig_det=0.0, sig_relr=0.0):
+    row = np.zeros(PT_STRIDE)
+    row[0], row[1], row[2], row[3] = V, delta1, off[0], off[1]
+    row[4:9] = rates5
+    row[9], row[10] = sig_det, sig_relr
+    return row
+
+
+def pack_case(case):
+    s = case["segments"]
+    seg = np.stack([s["dt"], s["re"], s["im"], s["delta"]], axis=1).astype(np.float64)
+    pt = pack_point(case["scalars"]["V"], case["scalars"]["delta_1"], collapsed_rates(case["rates"]))
+    return pt, seg
+
+
+def pack_batch(cases):
+    pts, segs = zip(*(pack_case(c) for c in cases))
+    S = max(len(s) for s in segs)
+    seg = np.zeros((len(cases), S, SG_STRIDE))
+    for i, s in enumerate(segs):
+        seg[i, :len(s)] = s
+    return np.stack(pts), seg, np.array([len(s) for s in segs], dtype=np.int32)
+
+
+def golden_finals(case):
+    n = case["dim"] ** 2
+    out = {}
+    for k, v in case["finals"].items():
+        a = np.array(v[0]) + 1j * np.array(v[1])
+        out[k] = a.reshape(n, n) if a.size == n * n else a.reshape(n)
+    return out
+
+
+@lru_cache(None)
+def systems(dim):
+    from noisyquantumsimulator_b200.codegen import model
+    return model.standard_systems(dim)
+
+
+def states_to_operators(dim, row):
+    """raw reduced state row -> {'rho11': (d²×d²) complex, ..., 'coh11': ...}"""
+    S = systems(dim)
+    out = {}
+    for key, off in STATE_OFFSETS[dim].items():
+        sysm = S[key]
+        out[key] = sysm.to_operator(row[off:off + sysm.n])
+    return out
+
+
+def load_hostsim():
+    """Build (if needed) and load the host harness of csrc/rydcz_core.cuh."""
+    import ctypes
+    import subprocess
+
+    d = os.path.join(HERE, "hostsim")
+    so = os.path.join(d, "libhostsim.so")
+    srcs = [os.path.join(d, "hostsim.cpp")] + [
+        os.path.join(HERE, "..", "noisyquantumsimulator_b200", "csrc", f)
+        for f in ("rydcz_core.cuh", "rydcz_systems_d3.inc", "rydcz_systems_d4.inc")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, srcs[0]])
+    lib = ctypes.CDLL(so)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.hostsim_evaluate.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, dp, dp,
+                                     ctypes.POINTER(ctypes.c_int), ctypes.c_int, dp, dp]
+    lib.hostsim_evaluate.restype = ctypes.c_int
+
+    def evaluate(dim, noisy, points, segs, n_seg, want_states=True):
+        import ctypes as C
+        points = np.ascontiguousarray(points, dtype=np.float64)
+        segs = np.ascontiguousarray(segs, dtype=np.float64)
+        n_seg = np.ascontiguousarray(n_seg, dtype=np.int32)
+        B = points.shape[0]
+        out = np.zeros((B, OUT_STRIDE))
+        st = np.zeros((B, STATE_STRIDE[dim])) if want_states else None
+        rc = lib.hostsim_evaluate(dim, int(noisy), B, points.ctypes.data_as(dp),
+                                  segs.ctypes.data_as(dp),
+                                  n_seg.ctypes.data_as(C.POINTER(C.c_int)), segs.shape[1],
+                                  out.ctypes.data_as(dp),
+                                  st.ctypes.data_as(dp) if want_states else None)
+        assert rc == 0
+        return out, st
+
+    return evaluate
