@@ -105,101 +105,26 @@ RYDCZ_HD double cheb_work(double radius, double dt) {
   return z + 10.3 * cbrt(z) + 5.0;
 }
 
-// x <- exp(h G) x, repeated nsub times, where c[] already holds 2 G / R and z = R h.
-template <class Sys>
-RYDCZ_HD void cheb_advance(double (&x)[Sys::N], const double (&c)[Sys::NC], double z, int nsub,
-                           double& steps) {
-  constexpr int N = Sys::N;
-  const int K = cheb_terms(z);
-  const double tz = 2.0 / z;
-  for (int sub = 0; sub < nsub; ++sub) {
-    double b1[N], b2[N];
-    RYDCZ_UNROLL
-    for (int i = 0; i < N; ++i) { b1[i] = 0.0; b2[i] = 0.0; }
-    double jp = 0.0, jk = 1e-30;   // J_{k+1}, J_k up to a common factor (Miller)
-    double norm = 0.0;             // J_0 + 2 sum_{even k} J_k = 1 fixes the factor
-    double kd = (double)K;
-    for (int k = K; k >= 2; k -= 2) {
-      // k even:  b2 <- 2 J_k x + (2A) b1 + b2
-      double ak = jk + jk;
-      RYDCZ_UNROLL
-      for (int i = 0; i < N; ++i) b2[i] = fma(ak, x[i], b2[i]);
-      Sys::apply(c, b1, b2);
-      norm += ak;
-      double jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
-      // k-1 odd: b1 <- 2 J_{k-1} x + (2A) b2 + b1
-      ak = jk + jk;
-      RYDCZ_UNROLL
-      for (int i = 0; i < N; ++i) b1[i] = fma(ak, x[i], b1[i]);
-      Sys::apply(c, b2, b1);
-      jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
-    }
-    // k = 0:  S = J_0 x + A b1 + b2, with A b1 = (2A b1)/2
-    double t[N];
-    RYDCZ_UNROLL
-    for (int i = 0; i < N; ++i) t[i] = 0.0;
-    Sys::apply(c, b1, t);
-    const double inv = 1.0 / (norm + jk);
-    RYDCZ_UNROLL
-    for (int i = 0; i < N; ++i) x[i] = (fma(jk, x[i], b2[i]) + 0.5 * t[i]) * inv;
-    steps += (double)(K + 1);
-  }
-}
-
-// Advance one constant-generator segment of duration dt.  p[] is the parameter vector of the
-// system (Sys::NP entries; for coherence systems the last one is the spectral shift, set here).
-template <class Sys>
-RYDCZ_HD void evolve_segment(double (&x)[Sys::N], double (&p)[Sys::NP], double dt, double& steps) {
-  // dt < 0 happens in the reference when Delta_e < 0 makes Omega (hence tau = Omega*tau/Omega)
-  // negative: mesolve then integrates backwards, i.e. applies exp(-|dt| G).  Reproduced here.
-  if (dt == 0.0 || dt != dt) return;
-  const double sgn = dt < 0.0 ? -1.0 : 1.0;
-  const double adt = fabs(dt);
-  double c[Sys::NC];
-  double lo, hi, damp;
-  if (!Sys::HERMITIAN) p[Sys::NP - 1] = 0.0;
-  Sys::coefs(p, c);
-  Sys::bounds(c, lo, hi, damp);
-  double cen = 0.0, R;
-  if (Sys::HERMITIAN) {
-    R = hi;
-  } else {
-    cen = 0.5 * (lo + hi);
-    R = 0.5 * (hi - lo) + damp;
-    p[Sys::NP - 1] = cen;
-    Sys::coefs(p, c);
-  }
-  // strong damping pushes the spectrum off the imaginary axis; keep damp*h <= 2 per sub-step so
-  // the Chebyshev polynomials stay O(e^2) ("Chebyshev interval").
-  int nsub = 1;
-  if (damp * adt > 2.0) nsub = (int)ceil(0.5 * damp * adt);
-  const double h = adt / (double)nsub;
-  // a wider interval is always valid; never let z underflow the Miller recurrence
-  if (!(R * h >= 1e-2)) R = 1e-2 / h;
-  const double z = R * h;
-  const double s = sgn * 2.0 / R;
-  RYDCZ_UNROLL
-  for (int q = 0; q < Sys::NC; ++q) c[q] *= s;
-  cheb_advance<Sys>(x, c, z, nsub, steps);
-  if (!Sys::HERMITIAN) {
-    // undo the shift: multiply every complex component by exp(-i cen dt)
-    double sn, cs;
-    sincos(cen * dt, &sn, &cs);
-    RYDCZ_UNROLL
-    for (int i = 0; i < Sys::N; i += 2) {
-      const double re = x[i], im = x[i + 1];
-      x[i] = fma(re, cs, im * sn);
-      x[i + 1] = fma(im, cs, -re * sn);
-    }
-  }
-}
-
 // Run one system through all segments of a point.
+//
+// The loop is FLAT: one iteration = two Clenshaw steps of whatever segment this lane is in.
+// Segment (and sub-step) transitions happen inside the same loop under `if (k < 2)`, so the 32
+// lanes of a warp never wait for one another at segment boundaries -- a lane whose first pulse
+// segment is long and second short costs the same as one with the opposite split.  (With one
+// loop per segment the warp pays sum_s max_lanes K_s instead of max_lanes sum_s K_s, which for
+// bang-bang candidates was ~3x.)
+//
+// Per segment:  coefs -> Gershgorin interval [cen-R, cen+R] -> z = R h, K = cheb_terms(z) ->
+// c <- (2/R) c.  dt < 0 (the reference reaches it when Delta_e < 0 makes Omega, hence tau,
+// negative; mesolve then integrates backwards) applies exp(-|dt| G).  Strong damping pushes the
+// spectrum off the imaginary axis, so a segment is cut into nsub pieces with damp*h <= 2, which
+// keeps the Chebyshev polynomials O(e^2) ("Chebyshev interval").
 template <class Sys>
 RYDCZ_HD void run_system(double (&x)[Sys::N], const double* __restrict__ pt,
                          const double* __restrict__ seg, int n_seg, bool noisy, double& steps) {
+  constexpr int N = Sys::N;
   RYDCZ_UNROLL
-  for (int i = 0; i < Sys::N; ++i) x[i] = (i == Sys::START) ? 1.0 : 0.0;
+  for (int i = 0; i < N; ++i) x[i] = (i == Sys::START) ? 1.0 : 0.0;
   double p[Sys::NP];
   p[4] = pt[PT_V];
   p[5] = pt[PT_DELTA1];
@@ -209,13 +134,106 @@ RYDCZ_HD void run_system(double (&x)[Sys::N], const double* __restrict__ pt,
   p[9] = noisy ? pt[PT_G_SC] : 0.0;
   if (Sys::NP - (Sys::HERMITIAN ? 0 : 1) > 10) p[10] = noisy ? pt[PT_G_MJ] : 0.0;
   const double offa = pt[PT_OFF_A], offb = pt[PT_OFF_B];
-  for (int s = 0; s < n_seg; ++s) {
-    const double* sg = seg + (long long)s * SG_STRIDE;
-    p[0] = sg[SG_RE];
-    p[1] = sg[SG_IM];
-    p[2] = sg[SG_DET] + offa;
-    p[3] = sg[SG_DET] + offb;
-    evolve_segment<Sys>(x, p, sg[SG_DT], steps);
+
+  double c[Sys::NC], b1[N], b2[N];
+  double jp = 0.0, jk = 0.0, norm = 0.0, kd = 0.0, tz = 0.0, rot = 0.0;
+  int k = 0;         // Clenshaw index still to process in the active sub-step
+  int K = 0;         // its starting value
+  int sub_left = 0;  // further sub-steps of the current segment
+  int s = 0;         // next segment row to load
+  bool active = false;
+  for (;;) {
+    if (k < 2) {
+      if (active) {
+        // k = 0:  exp(hG) x = (J_0 x + A b1 + b2) / (J_0 + 2 sum_even J_k),  A b1 = (2A)(b1/2)
+        RYDCZ_UNROLL
+        for (int i = 0; i < N; ++i) { b1[i] *= 0.5; b2[i] = fma(jk, x[i], b2[i]); }
+        Sys::apply(c, b1, b2);
+        const double inv = 1.0 / (norm + jk);
+        RYDCZ_UNROLL
+        for (int i = 0; i < N; ++i) x[i] = b2[i] * inv;
+        steps += (double)(K + 1);
+        if (!Sys::HERMITIAN) {
+          // undo the spectral shift: every complex component times exp(-i cen h)
+          double sn, cs;
+          sincos(rot, &sn, &cs);
+          RYDCZ_UNROLL
+          for (int i = 0; i < N; i += 2) {
+            const double re = x[i], im = x[i + 1];
+            x[i] = fma(re, cs, im * sn);
+            x[i + 1] = fma(im, cs, -re * sn);
+          }
+        }
+        active = false;
+      }
+      if (sub_left > 0) {
+        --sub_left;
+      } else {
+        double dt = 0.0;
+        bool found = false;
+        while (s < n_seg && !found) {
+          const double* sg = seg + (long long)s * SG_STRIDE;
+          dt = sg[SG_DT];
+          if (dt != 0.0 && dt == dt) {
+            p[0] = sg[SG_RE];
+            p[1] = sg[SG_IM];
+            p[2] = sg[SG_DET] + offa;
+            p[3] = sg[SG_DET] + offb;
+            found = true;
+          }
+          ++s;
+        }
+        if (!found) break;
+        const double sgn = dt < 0.0 ? -1.0 : 1.0;
+        const double adt = fabs(dt);
+        double lo, hi, damp, cen = 0.0, R;
+        if (!Sys::HERMITIAN) p[Sys::NP - 1] = 0.0;
+        Sys::coefs(p, c);
+        Sys::bounds(c, lo, hi, damp);
+        if (Sys::HERMITIAN) {
+          R = hi;
+        } else {
+          cen = 0.5 * (lo + hi);
+          R = 0.5 * (hi - lo) + damp;
+          p[Sys::NP - 1] = cen;
+          Sys::coefs(p, c);
+        }
+        int nsub = 1;
+        if (damp * adt > 2.0) nsub = (int)ceil(0.5 * damp * adt);
+        const double h = adt / (double)nsub;
+        // a wider interval is always valid; never let z underflow the Miller recurrence
+        if (!(R * h >= 1e-2)) R = 1e-2 / h;
+        const double z = R * h;
+        const double sc = sgn * 2.0 / R;
+        RYDCZ_UNROLL
+        for (int q = 0; q < Sys::NC; ++q) c[q] *= sc;
+        K = cheb_terms(z);
+        tz = 2.0 / z;
+        rot = cen * h * sgn;
+        sub_left = nsub - 1;
+      }
+      RYDCZ_UNROLL
+      for (int i = 0; i < N; ++i) { b1[i] = 0.0; b2[i] = 0.0; }
+      jp = 0.0; jk = 1e-30;   // J_{K+1}, J_K up to a common factor (Miller's backward recurrence)
+      norm = 0.0;             // J_0 + 2 sum_{even k>0} J_k = 1 fixes the factor
+      kd = (double)K;
+      k = K;
+      active = true;
+    }
+    // k even:   b2 <- 2 J_k x + (2A) b1 + b2
+    double ak = jk + jk;
+    RYDCZ_UNROLL
+    for (int i = 0; i < N; ++i) b2[i] = fma(ak, x[i], b2[i]);
+    Sys::apply(c, b1, b2);
+    norm += ak;
+    double jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
+    // k-1 odd:  b1 <- 2 J_{k-1} x + (2A) b2 + b1
+    ak = jk + jk;
+    RYDCZ_UNROLL
+    for (int i = 0; i < N; ++i) b1[i] = fma(ak, x[i], b1[i]);
+    Sys::apply(c, b2, b1);
+    jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
+    k -= 2;
   }
 }
 
