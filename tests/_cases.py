@@ -120,3 +120,50 @@ def load_hostsim():
         return out, st
 
     return evaluate
+
+
+def plan_kwargs(case):
+    """keyword arguments of rydberg_gates.prologue.build_plan for a golden case."""
+    api = case["api"]
+    e, nz = api["excitation"], api["noise"]
+    kw = {k: (tuple(v) if k.startswith("qubit") else v) for k, v in api["kwargs"].items()}
+    kw.update(api["params"])
+    kw.update(laser_1_power=e["laser_1"]["power"], laser_1_waist=e["laser_1"]["waist"],
+              laser_2_power=e["laser_2"]["power"], laser_2_waist=e["laser_2"]["waist"], Delta_e=e["Delta_e"],
+              laser_1_linewidth_hz=e["laser_1"]["linewidth_hz"], laser_2_linewidth_hz=e["laser_2"]["linewidth_hz"],
+              polarization_purity_1=e["laser_1"]["polarization_purity"],
+              polarization_purity_2=e["laser_2"]["polarization_purity"],
+              counter_propagating=e["counter_propagating"],
+              include_motional_dephasing=nz["include_motional_dephasing"],
+              include_doppler_dephasing=nz["include_doppler_dephasing"],
+              include_intensity_noise=nz["include_intensity_noise"],
+              intensity_noise_frac=nz["intensity_noise_frac"])
+    return api["protocol"], kw
+
+
+def api_inputs(case):
+    """(simulation_inputs dataclass, simulate_CZ_gate kwargs) for a golden case."""
+    from noisyquantumsimulator_b200 import rydberg_gates as rg
+    api = case["api"]
+    e = api["excitation"]
+    exc = rg.TwoPhotonExcitationConfig(laser_1=rg.LaserParameters(**e["laser_1"]),
+                                       laser_2=rg.LaserParameters(**e["laser_2"]), Delta_e=e["Delta_e"],
+                                       counter_propagating=e["counter_propagating"])
+    cls = {"lp": rg.LPSimulationInputs, "jp": rg.JPSimulationInputs, "sjp": rg.SmoothJPSimulationInputs}[api["protocol"]]
+    inputs = cls(excitation=exc, noise=rg.NoiseSourceConfig(**api["noise"]), **api["params"])
+    kw = {k: (tuple(v) if k.startswith("qubit") else v) for k, v in api["kwargs"].items()}
+    return inputs, kw
+
+
+class HostsimEvaluator:
+    """Stands in for engine.Evaluator in CPU tests of the Python API layer: same methods, arithmetic
+    from tests/hostsim (the g++ build of csrc/rydcz_core.cuh).  TEST ONLY."""
+
+    def __init__(self):
+        self._ev = load_hostsim()
+
+    def evaluate_host(self, dim, noisy, points, segs, n_seg=None, want_states=False):
+        if n_seg is None:
+            n_seg = np.full(len(points), segs.shape[1], dtype=np.int32)
+        out, st = self._ev(dim, noisy, points, segs, n_seg, want_states=True)
+        return out, (st if want_states else None)

@@ -1,0 +1,127 @@
+"""The reference-facing Python API (simulate_CZ_gate, simulate_CZ_gate_batch, the qpu_simulator
+import path) with the evaluator swapped for the host harness, so result packaging, phase modes and
+error behaviour are covered on CPU.  The same checks run against the real CUDA path in
+tests/test_gpu_api.py."""
+import math
+import sys
+import os
+
+import numpy as np
+import pytest
+
+import _cases as C
+
+REF = {c["name"]: c for c in C.load("reference_cases.json")}
+
+
+@pytest.fixture()
+def rg(monkeypatch):
+    from noisyquantumsimulator_b200 import engine
+    from noisyquantumsimulator_b200 import rydberg_gates
+    fake = C.HostsimEvaluator()
+    monkeypatch.setattr(engine, "get_evaluator", lambda device=0: fake)
+    return rydberg_gates
+
+
+def check_result_against_golden(res, case, phase_mode):
+    gold = case["result"] if case["rates"] is None else case["result_coherence"]
+    if case["rates"] is not None and phase_mode == "compat":
+        # The reference's dominant-eigenvector phases are not a function of rho alone: LAPACK picks
+        # the eigenvector's global phase, and a 1e-14 change of rho (or exact structural zeros
+        # instead of 1e-20 noise) flips it -- e.g. lp_noisy gives avg F 0.9663 from the 81x81-expm
+        # rho and 0.9057 from the same rho to 2e-14.  So 'compat' is pinned as "the reference's
+        # formula applied to the rho we return", evaluated by the oracle on this host.
+        from oracle import rydcz_oracle as orc
+        fid, avg, info = orc.cz_fidelity_mixed(case["dim"], res.results, "compat")
+        gold = dict(avg_fidelity=avg, fidelities=fid, phase_info=info)
+    assert abs(res.avg_fidelity - gold["avg_fidelity"]) < 1e-9
+    for lab in ("00", "01", "10", "11"):
+        assert abs(res.fidelities[lab] - gold["fidelities"][lab]) < 1e-9
+    for k in ("cz_phase_fidelity", "controlled_phase_deg", "phase_error_from_pi_deg"):
+        assert abs(res.phase_info[k] - gold["phase_info"][k]) < 1e-6, k
+    sc = case["scalars"]
+    assert abs(res.tau_total - sc["tau_total"]) < 1e-12 * abs(sc["tau_total"])
+    assert abs(res.V_over_Omega - sc["V_over_Omega"]) < 1e-9 * sc["V_over_Omega"]
+    assert abs(res.gate_time_us - sc["tau_total"] * 1e6) < 1e-9
+    assert res.protocol == case["protocol_name"]
+    fin = C.golden_finals(case)
+    for lab in ("00", "01", "10", "11"):
+        assert np.abs(np.asarray(res.results[lab]).reshape(fin[lab].shape) - fin[lab]).max() < 1e-10
+    for k, v in case["noise_breakdown"].items():
+        if isinstance(v, float):
+            assert abs(res.noise_breakdown[k] - v) <= 1e-10 * max(abs(v), 1e-30), k
+
+
+@pytest.mark.parametrize("name", ["lp_noisy", "bb5_noisy", "sjp_custom_noisy", "lp_noisy_cs133", "vb_bb5_default",
+                                  "vb_sjp_default", "lp_dim4_noisy", "lp_dim4_noiseless", "bb5_overshoot_switch",
+                                  "lp_include_noise_flags_off", "lp_shaped_cosine"])
+@pytest.mark.parametrize("phase_mode", ["coherence", "compat"])
+def test_simulate_cz_gate_matches_reference_run(rg, name, phase_mode):
+    case = REF[name]
+    inputs, kw = C.api_inputs(case)
+    res = rg.simulate_CZ_gate(inputs, phase_mode=phase_mode, **kw)
+    check_result_against_golden(res, case, phase_mode)
+    d = rg.simulate_CZ_gate(inputs, phase_mode=phase_mode, return_dataclass=False, **kw)
+    for key in ("avg_fidelity", "tau_total", "V_over_Omega", "Omega", "noise_breakdown", "gate_time_us", "Omega_MHz"):
+        assert key in d
+    assert d["avg_fidelity"] == res.avg_fidelity
+
+
+def test_wrong_input_type_raises_typeerror(rg):
+    with pytest.raises(TypeError, match="simulation_inputs must be"):
+        rg.simulate_CZ_gate({"omega_tau": 4.0})
+
+
+def test_reference_import_path_and_validate_bangbang_flow(rg):
+    """The flow of validate_bangbang.py:25-131 through the reference's own import path."""
+    sys.path.insert(0, os.path.join(os.path.dirname(C.HERE), "src"))
+    from qpu_simulator.micro_physics.neutral_atoms.rydberg_gates.simulation import simulate_CZ_gate
+    from qpu_simulator.micro_physics.neutral_atoms.rydberg_gates.configurations import (
+        JPSimulationInputs, SmoothJPSimulationInputs, TwoPhotonExcitationConfig, NoiseSourceConfig, LaserParameters)
+    exc = TwoPhotonExcitationConfig(laser_1=LaserParameters(power=50e-6, waist=50e-6, polarization="pi"),
+                                    laser_2=LaserParameters(power=0.3, waist=50e-6, polarization="sigma+"),
+                                    Delta_e=2 * np.pi * 1e9)
+    off = NoiseSourceConfig(False, False, False, False, False, 0.01, False, False)
+    kw = dict(species="Rb87", n_rydberg=70, spacing_factor=2.8, temperature=2e-6, include_noise=False)
+    pi = np.pi
+    runs = {
+        "vb_bb5_default": JPSimulationInputs(exc, off, 22.08, [2.214, 8.823, 13.258, 19.867], [pi / 2, 0, -pi / 2, 0, pi / 2]),
+        "vb_bb5_perturbed": JPSimulationInputs(exc, off, 22.08, [3.0, 9.0, 14.0, 20.0], [pi / 2, 0, -pi / 2, 0, pi / 2]),
+        "vb_bb5_quarter_phases": JPSimulationInputs(exc, off, 22.08, [2.214, 8.823, 13.258, 19.867], [pi / 4, 0, -pi / 4, 0, pi / 4]),
+        "vb_bb7_paper": JPSimulationInputs(exc, off, 7.0, [0.3328, 0.5859, 3.4340, 3.5530, 4.1204, 6.7431],
+                                           [pi / 2, 0, -pi / 2, -pi / 2, 0, pi / 2, 0]),
+        "vb_sjp_default": SmoothJPSimulationInputs(exc, off),
+        "vb_bb_none_defaults": JPSimulationInputs(exc, off),
+    }
+    fids = {}
+    for name, inp in runs.items():
+        r = simulate_CZ_gate(simulation_inputs=inp, verbose=False, return_dataclass=True, **kw)
+        fids[name] = r.avg_fidelity
+        assert abs(r.avg_fidelity - REF[name]["result"]["avg_fidelity"]) < 1e-9, name
+    assert len({round(fids[k], 6) for k in list(runs)[:4]}) == 4          # validate_bangbang TEST 1
+    assert abs(fids["vb_sjp_default"] - fids["vb_bb5_default"]) > 1e-6    # TEST 2
+    assert fids["vb_bb_none_defaults"] == fids["vb_bb5_default"]         # TEST 3
+
+
+def test_batch_api_matches_single_calls_and_cost(rg):
+    names = ["lp_noisy", "lp_noisy_hot50uK", "lp_noisy_spacing2", "lp_noisy_override"]
+    cases = [REF[n] for n in names]
+    kws = [C.plan_kwargs(c)[1] for c in cases]
+    keys = ("temperature", "spacing_factor", "delta_over_omega", "omega_tau")
+    base = {k: v for k, v in kws[0].items() if k not in keys}
+    arrs = {}
+    for k in keys:
+        vals = [kw.get(k) for kw in kws]
+        if all(v is None for v in vals):
+            continue
+        plan_defaults = [rg.build_plan("lp", B=1, warn=False, **kw) for kw in kws]
+        arrs[k] = np.array([v if v is not None else (pd.scalars["Delta_over_Omega"][0] if k == "delta_over_omega"
+                                                     else pd.scalars["omega_tau"][0])
+                            for v, pd in zip(vals, plan_defaults)])
+    res = rg.simulate_CZ_gate_batch("lp", B=len(cases), **base, **arrs)
+    for i, c in enumerate(cases):
+        assert abs(res.avg_fidelity[i] - c["result_coherence"]["avg_fidelity"]) < 1e-9
+        assert abs(res.gate_time_us[i] - c["scalars"]["tau_total"] * 1e6) < 1e-9
+    F, f11, czf = res.avg_fidelity, res.fidelities[:, 3], res.cz_phase_fidelity
+    want = 10 * ((1 - F) * 100) ** 2 + 5 * ((1 - f11) * 100) ** 2 + 2 * ((1 - czf) * 100) ** 2 + 0.01 * res.gate_time_us
+    assert np.allclose(res.cost(), np.where(F < 0.5, 1e6, want))
