@@ -81,6 +81,33 @@ def emit_system(sysm: model.RealSystem, struct_name: str) -> str:
     nz0 = np.nonzero(sysm.x0)[0]
     assert len(nz0) == 1 and sysm.x0[nz0[0]] == 1.0
     A(f"  static constexpr int START = {int(nz0[0])};   // x0 = e_START")
+    plist = list(sysm.params)
+
+    def pidx(*names):
+        for nm in names:
+            if nm in plist:
+                return plist.index(nm)
+        return -1
+
+    A(f"  static constexpr int IDX_OM_RE = {pidx('om_re')}, IDX_OM_IM = {pidx('om_im')}, "
+      f"IDX_DET_A = {pidx('det_a', 'det')}, IDX_DET_B = {pidx('det_b', 'det')}, IDX_V = {pidx('V')}, "
+      f"IDX_DELTA1 = {pidx('delta1')};")
+    A(f"  static constexpr int IDX_G_R1 = {pidx('g_r1')}, IDX_G_R0 = {pidx('g_r0')}, IDX_G_PHI = {pidx('g_phi')}, "
+      f"IDX_G_SC = {pidx('g_sc')}, IDX_G_MJ = {pidx('g_mj')};")
+    if getattr(sysm, "expand", None) is not None:
+        A(f"  static constexpr int FULL_N = {sysm.full_n};")
+        A("  // state of the general (unfolded) system from the exchange-folded one")
+        A("  RYDCZ_HD static void expand(const double* __restrict__ xs, double* __restrict__ xg) {")
+        E = sysm.expand
+        for r in range(E.shape[0]):
+            nz = np.nonzero(E[r])[0]
+            assert len(nz) <= 1
+            if len(nz) == 0:
+                A(f"    xg[{r}] = 0.0;")
+                continue
+            cidx = int(nz[0])
+            A(f"    xg[{r}] = {'' if E[r, cidx] > 0 else '-'}xs[{cidx}];")
+        A("  }")
     # coefs
     A("  RYDCZ_HD static void coefs(const double* __restrict__ p, double* __restrict__ c) {")
     for q, v in enumerate(forms):
@@ -148,9 +175,16 @@ def emit_dim(d: int) -> str:
            ""]
     for key, sysm in systems.items():
         out.append(emit_system(sysm, f"Sys_{key}_d{d}"))
+    folded = model.symmetric_systems(d)
+    for key, sysm in folded.items():
+        out.append(emit_system(sysm, f"Sys_{key}_d{d}"))
     # readout indices
     N = d * d
     out.append(f"// readout indices (d={d})")
+    idx11 = d * 1 + 1
+    out.append(f"static constexpr int RHO11S_POP_D{d} = {folded['rho11s'].index_of(idx11, idx11, 'diag')};")
+    out.append(f"static constexpr int COH11S_RE_D{d} = {folded['coh11s'].index_of(idx11, 0, 're')};")
+    out.append(f"static constexpr int COH11S_IM_D{d} = {folded['coh11s'].index_of(idx11, 0, 'im')};")
     for lab in ("01", "10", "11"):
         a, b = int(lab[0]), int(lab[1])
         idx = d * a + b

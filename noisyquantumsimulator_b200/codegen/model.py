@@ -210,3 +210,84 @@ def standard_systems(d: int) -> Dict[str, RealSystem]:
         out["rho" + lab] = reduce_system("rho" + lab, d, np.outer(k, k.conj()), True)
         out["coh" + lab] = reduce_system("coh" + lab, d, np.outer(k, k00.conj()), False)
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# Exchange-symmetric specialisation: identical atoms (det_a == det_b)
+# --------------------------------------------------------------------------------------------
+def sym_params(d: int) -> Tuple[str, ...]:
+    """Parameter list with the two per-atom detunings merged into one."""
+    names = PARAMS3 if d == 3 else PARAMS4
+    return tuple("det" if n == "det_a" else n for n in names if n != "det_b")
+
+
+@dataclass
+class FoldedSystem(RealSystem):
+    """A RealSystem restricted to the atom-exchange-invariant subspace.  ``expand`` (n_full x n)
+    maps its state back to the variables of the general system it was folded from."""
+
+    expand: np.ndarray = None
+    full_n: int = 0
+
+
+def fold_exchange(full: RealSystem) -> FoldedSystem:
+    """When both atoms see the same parameters the generator commutes with swapping the atoms, and
+    the start operators |11><11|, |11><00| are swap invariant, so X(t) = P X(t) P for all t.  In
+    the real variables of ``full`` the swap is a signed permutation S; the invariant subspace is
+    spanned by one representative per orbit.  Reduced generator: rows of the representatives of
+    M E, where E embeds orbit variables into the full space."""
+    d, N = full.d, full.d * full.d
+
+    def swap(i):
+        a, b = divmod(i, d)
+        return d * b + a
+
+    idx = {t: k for k, t in enumerate(full.var_info)}
+    S_perm = np.zeros(full.n, dtype=int)
+    S_sign = np.ones(full.n)
+    for k, (i, j, part) in enumerate(full.var_info):
+        i2, j2 = swap(i), swap(j)
+        sign = 1.0
+        if full.hermitian and i2 > j2:          # entry (i2, j2) is the conjugate of (j2, i2)
+            i2, j2 = j2, i2
+            sign = -1.0 if part == "im" else 1.0
+        S_perm[k], S_sign[k] = idx[(i2, j2, part)], sign
+    reps, cols = [], []
+    seen = set()
+    for k in range(full.n):
+        if k in seen:
+            continue
+        k2 = int(S_perm[k])
+        seen.update((k, k2))
+        col = np.zeros(full.n)
+        if k2 == k:
+            if S_sign[k] < 0:
+                continue                         # x = -x: identically zero on the invariant subspace
+            col[k] = 1.0
+        else:
+            col[k], col[k2] = 1.0, S_sign[k]
+        reps.append(k)
+        cols.append(col)
+    E = np.stack(cols, axis=1)                   # (n_full, n_sym)
+    names = list(full.params)
+    ia, ib = names.index("det_a"), names.index("det_b")
+    M_sym = []
+    for nm in sym_params(d):
+        Mk = full.M[ia] + full.M[ib] if nm == "det" else full.M[names.index(nm)]
+        MkE = Mk @ E
+        # invariance check: M E must lie in the range of E
+        resid = MkE - E @ MkE[reps, :]
+        assert np.abs(resid).max() < 1e-12, (full.name, nm)
+        M_sym.append(MkE[reps, :])
+    x0 = full.x0[reps]
+    assert np.allclose(E @ x0, full.x0)
+    return FoldedSystem(name=full.name + "s", d=d, hermitian=full.hermitian, n=len(reps),
+                        params=sym_params(d), M=M_sym, x0=x0,
+                        var_info=[full.var_info[k] for k in reps], expand=E, full_n=full.n)
+
+
+def symmetric_systems(d: int) -> Dict[str, FoldedSystem]:
+    """rho11 and coh11 folded by atom exchange.  (The |01> input is a single-atom problem already,
+    and by the same symmetry the |10> input equals it.)"""
+    full = standard_systems(d)
+    return {"rho11s": fold_exchange(full["rho11"]), "coh11s": fold_exchange(full["coh11"])}

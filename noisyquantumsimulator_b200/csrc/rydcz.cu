@@ -67,17 +67,23 @@ __device__ inline void philox_normal2(uint64_t seed, uint32_t point, uint32_t sh
 template <int D>
 __global__ void work_kernel(int64_t n_points, const double* __restrict__ points,
                             const double* __restrict__ segs, const int32_t* __restrict__ n_seg,
-                            int max_seg, float* __restrict__ keys, uint32_t* __restrict__ idx) {
+                            int max_seg, int shots, float* __restrict__ keys, uint32_t* __restrict__ idx) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_points) return;
-  const double w = point_work<D>(points + i * PT_STRIDE, segs + i * (int64_t)max_seg * SG_STRIDE,
-                                 n_seg ? n_seg[i] : max_seg);
+  const double* pt = points + i * PT_STRIDE;
+  double w = point_work<D>(pt, segs + i * (int64_t)max_seg * SG_STRIDE, n_seg ? n_seg[i] : max_seg);
+  // points whose atoms differ take the general kernel: keep them together (ahead of the folded
+  // ones) so warps stay homogeneous in mixed batches
+  if (!(pt[PT_OFF_A] == pt[PT_OFF_B]) || (shots && pt[PT_SIG_DET] != 0.0)) w = w * 2.0 + 1e15;
   keys[i] = (float)w;   // non-negative floats order like their bit patterns
   idx[i] = (uint32_t)i;
 }
 
-template <int D, bool NOISY, bool SHOTS>
-__global__ void __launch_bounds__(kBlock)
+// SYM = true handles the points whose two atoms see identical parameters (exchange-folded
+// systems, ~half the FMAs and half the registers); SYM = false handles the rest.  Both kernels
+// are launched over the whole batch and each thread returns at once if the point is not its kind.
+template <int D, bool NOISY, bool SHOTS, bool SYM>
+__global__ void __launch_bounds__(kBlock, SYM ? 3 : 2)
 evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, const uint32_t* __restrict__ order,
                 const double* __restrict__ points, const double* __restrict__ segs,
                 const int32_t* __restrict__ n_seg, int max_seg, double* __restrict__ out,
@@ -95,25 +101,37 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, const uint32_t* __r
     point = order ? order[g] : g;
     item = point;
   }
-  double pt[PT_STRIDE];
+  // the point row lives in shared memory, transposed ([slot][thread]: conflict-free), so it costs
+  // no registers inside the Chebyshev loop; only this thread touches its column
+  __shared__ double s_pt[PT_STRIDE * kBlock];
+  double* mine = s_pt + threadIdx.x;
+  const double* row = points + point * PT_STRIDE;
+  const bool folded = (row[PT_OFF_A] == row[PT_OFF_B]) && (!SHOTS || row[PT_SIG_DET] == 0.0);
+  if (folded != SYM) return;
 #pragma unroll
-  for (int k = 0; k < PT_STRIDE; ++k) pt[k] = points[point * PT_STRIDE + k];
+  for (int k = 0; k < PT_STRIDE; ++k) mine[k * kBlock] = row[k];
   if (SHOTS) {
     double da, db, er, unused;
     philox_normal2(seed, (uint32_t)point, shot, 0u, da, db);
     philox_normal2(seed, (uint32_t)point, shot, 1u, er, unused);
-    pt[PT_OFF_A] += pt[PT_SIG_DET] * da;
-    pt[PT_OFF_B] += pt[PT_SIG_DET] * db;
-    const double q = 1.0 + pt[PT_SIG_RELR] * er;
+    mine[PT_OFF_A * kBlock] += row[PT_SIG_DET] * da;
+    mine[PT_OFF_B * kBlock] += row[PT_SIG_DET] * db;
+    const double q = 1.0 + row[PT_SIG_RELR] * er;
     const double q2 = q * q;
-    pt[PT_V] = pt[PT_V] / (q2 * q2 * q2);
+    mine[PT_V * kBlock] = row[PT_V] / (q2 * q2 * q2);
   }
+  const PointView pt{mine, kBlock};
   const double* sg = segs + point * (int64_t)max_seg * SG_STRIDE;
   const int ns = n_seg ? n_seg[point] : max_seg;
   double o[OUT_STRIDE];
   double* st = states ? states + item * StateLayout<D>::STRIDE : nullptr;
-  if (D == 3) evaluate_point_d3<NOISY>(pt, sg, ns, o, st);
-  else evaluate_point_d4<NOISY>(pt, sg, ns, o, st);
+  if (SYM) {
+    if (D == 3) evaluate_point_sym_d3<NOISY>(pt, sg, ns, o, st);
+    else evaluate_point_sym_d4<NOISY>(pt, sg, ns, o, st);
+  } else {
+    if (D == 3) evaluate_point_d3<NOISY>(pt, sg, ns, o, st);
+    else evaluate_point_d4<NOISY>(pt, sg, ns, o, st);
+  }
   double* op = out + item * OUT_STRIDE;
 #pragma unroll
   for (int k = 0; k < OUT_STRIDE; k += 2)
@@ -248,7 +266,7 @@ static int sys_lookup(int dim, const char* name, int what) {
 // order points heaviest-first; returns the device permutation (or nullptr when sorting is off)
 template <int D>
 static int make_order(rydcz_ctx* ctx, int64_t n, const double* d_points, const double* d_segs,
-                      const int32_t* d_n_seg, int max_seg, cudaStream_t st, const uint32_t** order) {
+                      const int32_t* d_n_seg, int max_seg, int shots, cudaStream_t st, const uint32_t** order) {
   *order = nullptr;
   if (!ctx->sort || n < 64) return 0;
   if ((size_t)n > ctx->order_cap) {
@@ -260,7 +278,7 @@ static int make_order(rydcz_ctx* ctx, int64_t n, const double* d_points, const d
     CK(cudaMalloc(&ctx->idx_sorted, n * sizeof(uint32_t)));
     ctx->order_cap = (size_t)n;
   }
-  work_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_points, d_segs, d_n_seg, max_seg,
+  work_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_points, d_segs, d_n_seg, max_seg, shots,
                                                               ctx->keys, ctx->idx);
   CK(cudaGetLastError());
   ctx->launches++;
@@ -280,12 +298,15 @@ static int launch_eval(rydcz_ctx* ctx, int64_t n_items, int n_shots, uint64_t se
                        double* d_out, double* d_states, cudaStream_t st) {
   const unsigned grid = (unsigned)((n_items + kBlock - 1) / kBlock);
   CK(cudaEventRecord(ctx->ev0, st));
-  evaluate_kernel<D, NOISY, SHOTS><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, order, d_points,
-                                                            d_segs, d_n_seg, max_seg, d_out, d_states);
+  evaluate_kernel<D, NOISY, SHOTS, false><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, order, d_points,
+                                                                   d_segs, d_n_seg, max_seg, d_out, d_states);
+  CK(cudaGetLastError());
+  evaluate_kernel<D, NOISY, SHOTS, true><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, order, d_points,
+                                                                  d_segs, d_n_seg, max_seg, d_out, d_states);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev1, st));
   ctx->timed = true;
-  ctx->launches++;
+  ctx->launches += 2;
   return 0;
 }
 
@@ -363,8 +384,8 @@ int rydcz_evaluate_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, 
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
   const uint32_t* order = nullptr;
-  int rc = dim == 3 ? make_order<3>(ctx, n_points, d_points, d_segs, d_n_seg, max_seg, st, &order)
-                    : make_order<4>(ctx, n_points, d_points, d_segs, d_n_seg, max_seg, st, &order);
+  int rc = dim == 3 ? make_order<3>(ctx, n_points, d_points, d_segs, d_n_seg, max_seg, 0, st, &order)
+                    : make_order<4>(ctx, n_points, d_points, d_segs, d_n_seg, max_seg, 0, st, &order);
   if (rc) return rc;
 #define RYDCZ_GO(D, N)                                                                             \
   return launch_eval<D, N, false>(ctx, n_points, 1, 0, order, d_points, d_segs, d_n_seg, max_seg,   \
@@ -391,8 +412,8 @@ int rydcz_evaluate_shots_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_po
     shots = (double*)ctx->stage[5];
   }
   const uint32_t* order = nullptr;
-  int rc = dim == 3 ? make_order<3>(ctx, n_points, d_points, d_segs, d_n_seg, max_seg, st, &order)
-                    : make_order<4>(ctx, n_points, d_points, d_segs, d_n_seg, max_seg, st, &order);
+  int rc = dim == 3 ? make_order<3>(ctx, n_points, d_points, d_segs, d_n_seg, max_seg, 1, st, &order)
+                    : make_order<4>(ctx, n_points, d_points, d_segs, d_n_seg, max_seg, 1, st, &order);
   if (rc) return rc;
 #define RYDCZ_GO(D, N)                                                                               \
   rc = launch_eval<D, N, true>(ctx, n_items, n_shots, seed, order, d_points, d_segs, d_n_seg, max_seg, \

@@ -92,6 +92,15 @@ template <> struct StateLayout<4> {
   static constexpr int RHO11 = 0, RHO01 = 36, RHO10 = 42, COH11 = 48, COH01 = 56, COH10 = 60, STRIDE = 64;
 };
 
+// Strided read-only view of one point row: stride 1 for a plain row, blockDim for the
+// transposed shared-memory copy the kernels keep (conflict-free, and the row does not occupy
+// registers across the Chebyshev loop).
+struct PointView {
+  const double* base;
+  int stride;
+  RYDCZ_HD double operator[](int k) const { return base[(long long)k * stride]; }
+};
+
 RYDCZ_HD int cheb_terms(double z) {
   // smallest even K with |J_k(z)| < ~1e-15 for all k > K (fit checked in tests/test_oracle_golden.py)
   int K = (int)ceil(z + 10.3 * cbrt(z) + 4.0);
@@ -120,21 +129,11 @@ RYDCZ_HD double cheb_work(double radius, double dt) {
 // spectrum off the imaginary axis, so a segment is cut into nsub pieces with damp*h <= 2, which
 // keeps the Chebyshev polynomials O(e^2) ("Chebyshev interval").
 template <class Sys>
-RYDCZ_HD void run_system(double (&x)[Sys::N], const double* __restrict__ pt,
+RYDCZ_HD void run_system(double (&x)[Sys::N], const PointView pt,
                          const double* __restrict__ seg, int n_seg, bool noisy, double& steps) {
   constexpr int N = Sys::N;
   RYDCZ_UNROLL
   for (int i = 0; i < N; ++i) x[i] = (i == Sys::START) ? 1.0 : 0.0;
-  double p[Sys::NP];
-  p[4] = pt[PT_V];
-  p[5] = pt[PT_DELTA1];
-  p[6] = noisy ? pt[PT_G_R1] : 0.0;
-  p[7] = noisy ? pt[PT_G_R0] : 0.0;
-  p[8] = noisy ? pt[PT_G_PHI] : 0.0;
-  p[9] = noisy ? pt[PT_G_SC] : 0.0;
-  if (Sys::NP - (Sys::HERMITIAN ? 0 : 1) > 10) p[10] = noisy ? pt[PT_G_MJ] : 0.0;
-  const double offa = pt[PT_OFF_A], offb = pt[PT_OFF_B];
-
   double c[Sys::NC], b1[N], b2[N];
   double jp = 0.0, jk = 0.0, norm = 0.0, kd = 0.0, tz = 0.0, rot = 0.0;
   int k = 0;         // Clenshaw index still to process in the active sub-step
@@ -171,19 +170,29 @@ RYDCZ_HD void run_system(double (&x)[Sys::N], const double* __restrict__ pt,
       } else {
         double dt = 0.0;
         bool found = false;
+        double p[Sys::NP];          // rebuilt per segment so it is not live across the hot loop
+        const double offa = pt[PT_OFF_A], offb = pt[PT_OFF_B];
         while (s < n_seg && !found) {
           const double* sg = seg + (long long)s * SG_STRIDE;
           dt = sg[SG_DT];
           if (dt != 0.0 && dt == dt) {
-            p[0] = sg[SG_RE];
-            p[1] = sg[SG_IM];
-            p[2] = sg[SG_DET] + offa;
-            p[3] = sg[SG_DET] + offb;
+            p[Sys::IDX_OM_RE] = sg[SG_RE];
+            p[Sys::IDX_OM_IM] = sg[SG_IM];
+            p[Sys::IDX_DET_A] = sg[SG_DET] + offa;
+            p[Sys::IDX_DET_B] = sg[SG_DET] + offb;   // same slot as DET_A for exchange-folded systems
             found = true;
           }
           ++s;
         }
         if (!found) break;
+        p[Sys::IDX_V] = pt[PT_V];
+        p[Sys::IDX_DELTA1] = pt[PT_DELTA1];
+        p[Sys::IDX_G_R1] = noisy ? pt[PT_G_R1] : 0.0;
+        p[Sys::IDX_G_R0] = noisy ? pt[PT_G_R0] : 0.0;
+        p[Sys::IDX_G_PHI] = noisy ? pt[PT_G_PHI] : 0.0;
+        p[Sys::IDX_G_SC] = noisy ? pt[PT_G_SC] : 0.0;
+        constexpr int kMj = Sys::IDX_G_MJ >= 0 ? Sys::IDX_G_MJ : 0;
+        if (Sys::IDX_G_MJ >= 0) p[kMj] = noisy ? pt[PT_G_MJ] : 0.0;
         const double sgn = dt < 0.0 ? -1.0 : 1.0;
         const double adt = fabs(dt);
         double lo, hi, damp, cen = 0.0, R;
@@ -280,7 +289,7 @@ RYDCZ_HD void cz_epilogue(bool noisy, double p01, double p10, double p11,
 // One full gate evaluation.  `states` (may be null) receives the raw reduced states.
 #define RYDCZ_DEFINE_EVALUATE(D)                                                                    \
   template <bool NOISY>                                                                             \
-  RYDCZ_HD void evaluate_point_d##D(const double* __restrict__ pt, const double* __restrict__ seg,  \
+  RYDCZ_HD void evaluate_point_d##D(const PointView pt, const double* __restrict__ seg,            \
                                     int n_seg, double* __restrict__ out,                            \
                                     double* __restrict__ states) {                                  \
     typedef StateLayout<D> SL;                                                                      \
@@ -333,6 +342,64 @@ RYDCZ_HD void cz_epilogue(bool noisy, double p01, double p10, double p11,
 
 RYDCZ_DEFINE_EVALUATE(3)
 RYDCZ_DEFINE_EVALUATE(4)
+
+// Identical atoms (off_a == off_b): rho_11 and the |11><00| coherence are invariant under swapping
+// the atoms, so they are evolved in the folded variables (15 instead of 25, 6 instead of 8; fewer
+// than half the FMAs per step) and expanded at the end; the |10> input equals the |01> input.
+// Same outputs, same `states` layout as the general path.
+#define RYDCZ_DEFINE_EVALUATE_SYM(D)                                                                \
+  template <bool NOISY>                                                                             \
+  RYDCZ_HD void evaluate_point_sym_d##D(const PointView pt,                                         \
+                                        const double* __restrict__ seg, int n_seg,                  \
+                                        double* __restrict__ out, double* __restrict__ states) {    \
+    typedef StateLayout<D> SL;                                                                      \
+    double steps = 0.0, flops = 0.0, st;                                                            \
+    double p01 = 1.0, p11 = 1.0, loss = 0.0, ryd = 0.0;                                             \
+    double c01r, c01i, c11r, c11i;                                                                  \
+    if (NOISY) {                                                                                    \
+      double x[Sys_rho11s_d##D::N]; st = 0.0;                                                       \
+      run_system<Sys_rho11s_d##D>(x, pt, seg, n_seg, true, st);                                     \
+      steps += st; flops += st * 2.0 * (Sys_rho11s_d##D::NNZ + Sys_rho11s_d##D::N);                 \
+      p11 = x[RHO11S_POP_D##D];                                                                     \
+      double xf[Sys_rho11s_d##D::FULL_N];                                                           \
+      Sys_rho11s_d##D::expand(x, xf);                                                               \
+      loss = rho11_loss_d##D(xf); ryd = rho11_ryd_d##D(xf);                                         \
+      if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_rho11s_d##D::FULL_N; ++i) states[SL::RHO11 + i] = xf[i]; } \
+    }                                                                                               \
+    {                                                                                               \
+      double x[Sys_coh11s_d##D::N]; st = 0.0;                                                       \
+      run_system<Sys_coh11s_d##D>(x, pt, seg, n_seg, NOISY, st);                                    \
+      steps += st; flops += st * 2.0 * (Sys_coh11s_d##D::NNZ + Sys_coh11s_d##D::N);                 \
+      c11r = x[COH11S_RE_D##D]; c11i = x[COH11S_IM_D##D];                                           \
+      if (!NOISY) ryd = 1.0 - (c11r * c11r + c11i * c11i);                                          \
+      if (states) {                                                                                 \
+        double xf[Sys_coh11s_d##D::FULL_N];                                                         \
+        Sys_coh11s_d##D::expand(x, xf);                                                             \
+        RYDCZ_UNROLL for (int i = 0; i < Sys_coh11s_d##D::FULL_N; ++i) states[SL::COH11 + i] = xf[i]; \
+      }                                                                                             \
+    }                                                                                               \
+    if (NOISY) {                                                                                    \
+      double x[Sys_rho01_d##D::N]; st = 0.0;                                                        \
+      run_system<Sys_rho01_d##D>(x, pt, seg, n_seg, true, st);                                      \
+      steps += st; flops += st * 2.0 * (Sys_rho01_d##D::NNZ + Sys_rho01_d##D::N);                   \
+      p01 = x[RHO01_POP_D##D];                                                                      \
+      if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_rho01_d##D::N; ++i) {                      \
+        states[SL::RHO01 + i] = x[i]; states[SL::RHO10 + i] = x[i]; } }                             \
+    }                                                                                               \
+    {                                                                                               \
+      double x[Sys_coh01_d##D::N]; st = 0.0;                                                        \
+      run_system<Sys_coh01_d##D>(x, pt, seg, n_seg, NOISY, st);                                     \
+      steps += st; flops += st * 2.0 * (Sys_coh01_d##D::NNZ + Sys_coh01_d##D::N);                   \
+      c01r = x[COH01_RE_D##D]; c01i = x[COH01_IM_D##D];                                             \
+      if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d##D::N; ++i) {                      \
+        states[SL::COH01 + i] = x[i]; states[SL::COH10 + i] = x[i]; } }                             \
+    }                                                                                               \
+    cz_epilogue(NOISY, p01, p01, p11, c01r, c01i, c01r, c01i, c11r, c11i, out);                     \
+    out[OUT_LOSS] = loss; out[OUT_RYD] = ryd; out[OUT_STEPS] = steps; out[OUT_FLOPS] = flops;       \
+  }
+
+RYDCZ_DEFINE_EVALUATE_SYM(3)
+RYDCZ_DEFINE_EVALUATE_SYM(4)
 
 // Gershgorin radius of the stiffest system (rho_11, or coh_11 when noiseless) for one segment:
 // the work estimate used to sort points so that the threads of a warp run equally long.

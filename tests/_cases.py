@@ -102,8 +102,10 @@ def load_hostsim():
     lib.hostsim_evaluate.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, dp, dp,
                                      ctypes.POINTER(ctypes.c_int), ctypes.c_int, dp, dp]
     lib.hostsim_evaluate.restype = ctypes.c_int
+    lib.hostsim_allow_sym.argtypes = [ctypes.c_int]
 
-    def evaluate(dim, noisy, points, segs, n_seg, want_states=True):
+    def evaluate(dim, noisy, points, segs, n_seg, want_states=True, allow_sym=True):
+        lib.hostsim_allow_sym(int(allow_sym))
         import ctypes as C
         points = np.ascontiguousarray(points, dtype=np.float64)
         segs = np.ascontiguousarray(segs, dtype=np.float64)

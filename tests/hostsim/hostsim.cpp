@@ -6,21 +6,30 @@
 #define RYDCZ_UNROLL
 #include "../../noisyquantumsimulator_b200/csrc/rydcz_core.cuh"
 
+static int g_allow_sym = 1;
+extern "C" void hostsim_allow_sym(int on) { g_allow_sym = on; }
+
 extern "C" int hostsim_evaluate(int dim, int noisy, long long n_points, const double* points,
                                 const double* segs, const int* n_seg, int max_seg, double* out,
                                 double* states) {
   using namespace rydcz;
   for (long long i = 0; i < n_points; ++i) {
-    const double* pt = points + i * PT_STRIDE;
+    const PointView pt{points + i * PT_STRIDE, 1};
     const double* sg = segs + i * (long long)max_seg * SG_STRIDE;
     double* o = out + i * OUT_STRIDE;
+    // same dispatch rule as the CUDA kernels: identical atoms take the exchange-folded path
+    const bool sym = g_allow_sym && pt[PT_OFF_A] == pt[PT_OFF_B];
     if (dim == 3) {
       double* st = states ? states + i * StateLayout<3>::STRIDE : nullptr;
-      if (noisy) evaluate_point_d3<true>(pt, sg, n_seg[i], o, st);
+      if (sym) { if (noisy) evaluate_point_sym_d3<true>(pt, sg, n_seg[i], o, st);
+                 else evaluate_point_sym_d3<false>(pt, sg, n_seg[i], o, st); }
+      else if (noisy) evaluate_point_d3<true>(pt, sg, n_seg[i], o, st);
       else evaluate_point_d3<false>(pt, sg, n_seg[i], o, st);
     } else if (dim == 4) {
       double* st = states ? states + i * StateLayout<4>::STRIDE : nullptr;
-      if (noisy) evaluate_point_d4<true>(pt, sg, n_seg[i], o, st);
+      if (sym) { if (noisy) evaluate_point_sym_d4<true>(pt, sg, n_seg[i], o, st);
+                 else evaluate_point_sym_d4<false>(pt, sg, n_seg[i], o, st); }
+      else if (noisy) evaluate_point_d4<true>(pt, sg, n_seg[i], o, st);
       else evaluate_point_d4<false>(pt, sg, n_seg[i], o, st);
     } else return 1;
   }

@@ -98,3 +98,18 @@ def test_unequal_atoms_detuning_offsets(hostsim):
     for lab in ("01", "10", "11"):
         assert np.abs(ops["rho" + lab] - fin[lab]).max() < 1e-11
     assert abs(out[0, C.OUT["f01"]] - out[0, C.OUT["f10"]]) > 1e-6
+
+
+@pytest.mark.parametrize("dim", [3, 4])
+def test_exchange_folded_path_equals_general_path(hostsim, dim):
+    """Identical atoms take the exchange-folded systems (15/6 variables instead of 25/8); the
+    general systems must give the same rho, coherences and fidelities."""
+    cases = [c for c in C.load("reference_cases.json") if c["dim"] == dim and len(c["segments"]["dt"]) <= 300]
+    for noisy in (True, False):
+        sel = [c for c in cases if (c["rates"] is not None) == noisy]
+        pts, seg, ns = C.pack_batch(sel)
+        a, sa = hostsim(dim, noisy, pts, seg, ns, allow_sym=True)
+        b, sb = hostsim(dim, noisy, pts, seg, ns, allow_sym=False)
+        assert np.abs(sa - sb).max() < 1e-11
+        assert np.abs(a[:, :14] - b[:, :14]).max() < 1e-10
+        assert np.all(a[:, 15] < 0.62 * b[:, 15])          # well under two thirds of the flops
