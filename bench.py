@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "cz_lindblad_gate_evals_per_sec"
 UNIT = "evals/s"
-B_PER_GPU = 65536
+B_PER_GPU = 65536          # default candidates per GPU per step (--candidates)
 N_SEG = 5
 
 
@@ -307,7 +307,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--candidates", type=int, default=B_PER_GPU, help="bang-bang candidates per GPU per step")
     args = ap.parse_args()
+    global B_PER_GPU
+    B_PER_GPU = args.candidates
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

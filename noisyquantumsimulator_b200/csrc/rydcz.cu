@@ -103,7 +103,7 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, const uint32_t* __r
   }
   // the point row lives in shared memory, transposed ([slot][thread]: conflict-free), so it costs
   // no registers inside the Chebyshev loop; only this thread touches its column
-  __shared__ double s_pt[PT_STRIDE * kBlock];
+  __shared__ double s_pt[(PT_STRIDE + PT_SCRATCH) * kBlock];
   double* mine = s_pt + threadIdx.x;
   const double* row = points + point * PT_STRIDE;
   const bool folded = (row[PT_OFF_A] == row[PT_OFF_B]) && (!SHOTS || row[PT_SIG_DET] == 0.0);

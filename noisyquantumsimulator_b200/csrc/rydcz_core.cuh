@@ -61,7 +61,8 @@ enum PointSlot {
   PT_SIG_DET = 9,  // Monte-Carlo: std of the per-atom Doppler detuning k_eff*v_rms (rad/s)
   PT_SIG_RELR = 10,// Monte-Carlo: std of dR/R0 = sqrt(2) sigma_r / R0
   PT_RESERVED = 11,
-  PT_STRIDE = 12
+  PT_STRIDE = 12,
+  PT_SCRATCH = 6    // extra per-thread slots behind a PointView (not part of the C-ABI row)
 };
 // one segment row: dt (s), Re Omega, Im Omega, Delta (rad/s)
 enum SegSlot { SG_DT = 0, SG_RE = 1, SG_IM = 2, SG_DET = 3, SG_STRIDE = 4 };
@@ -96,14 +97,18 @@ template <> struct StateLayout<4> {
 // transposed shared-memory copy the kernels keep (conflict-free, and the row does not occupy
 // registers across the Chebyshev loop).
 struct PointView {
-  const double* base;
+  double* base;
   int stride;
   RYDCZ_HD double operator[](int k) const { return base[(long long)k * stride]; }
+  // slots PT_STRIDE .. PT_STRIDE+PT_SCRATCH-1 of the same column: per-thread scratch that must
+  // survive the Chebyshev loop without holding registers (the cached Chebyshev interval)
+  RYDCZ_HD double& scratch(int k) const { return base[(long long)(PT_STRIDE + k) * stride]; }
 };
 
 RYDCZ_HD int cheb_terms(double z) {
-  // smallest even K with |J_k(z)| < ~1e-15 for all k > K (fit checked in tests/test_oracle_golden.py)
-  int K = (int)ceil(z + 10.3 * cbrt(z) + 4.0);
+  // smallest even K with |J_k(z)| < ~1e-15 for all k > K (fit checked in tests/test_oracle_golden.py);
+  // the single-precision cube root is padded so it never undershoots
+  int K = (int)ceil(z + 10.3 * (double)(cbrtf((float)z) * 1.000001f) + 4.0);
   return K + (K & 1);
 }
 
@@ -136,6 +141,10 @@ RYDCZ_HD void run_system(double (&x)[Sys::N], const PointView pt,
   for (int i = 0; i < N; ++i) x[i] = (i == Sys::START) ? 1.0 : 0.0;
   double c[Sys::NC], b1[N], b2[N];
   double jp = 0.0, jk = 0.0, norm = 0.0, kd = 0.0, tz = 0.0, rot = 0.0;
+  // cached Chebyshev interval, kept in the point's scratch slots (shared memory on the GPU)
+  double &iv_om2 = pt.scratch(0), &iv_da = pt.scratch(1), &iv_db = pt.scratch(2), &iv_R = pt.scratch(3),
+         &iv_cen = pt.scratch(4), &iv_damp = pt.scratch(5);
+  iv_om2 = -1.0;
   int k = 0;         // Clenshaw index still to process in the active sub-step
   int K = 0;         // its starting value
   int sub_left = 0;  // further sub-steps of the current segment
@@ -195,18 +204,30 @@ RYDCZ_HD void run_system(double (&x)[Sys::N], const PointView pt,
         if (Sys::IDX_G_MJ >= 0) p[kMj] = noisy ? pt[PT_G_MJ] : 0.0;
         const double sgn = dt < 0.0 ? -1.0 : 1.0;
         const double adt = fabs(dt);
-        double lo, hi, damp, cen = 0.0, R;
-        if (!Sys::HERMITIAN) p[Sys::NP - 1] = 0.0;
-        Sys::coefs(p, c);
-        Sys::bounds(c, lo, hi, damp);
-        if (Sys::HERMITIAN) {
-          R = hi;
-        } else {
-          cen = 0.5 * (lo + hi);
-          R = 0.5 * (hi - lo) + damp;
-          p[Sys::NP - 1] = cen;
+        // Chebyshev interval.  The Gershgorin bound is taken with |Re Ω| = |Im Ω| = |Ω| (valid for
+        // any laser phase, at most ~|Ω| wider), so it depends only on (|Ω|, Δ_A, Δ_B) and the point
+        // constants: bang-bang, smooth-JP and LP segments differ only in the phase of Ω and reuse it.
+        const double om2 = p[Sys::IDX_OM_RE] * p[Sys::IDX_OM_RE] + p[Sys::IDX_OM_IM] * p[Sys::IDX_OM_IM];
+        // (|Ω|² of equal-amplitude segments differs by rounding: compare to 1e-9, far inside the
+        //  slack of the bound)
+        if (!(fabs(om2 - iv_om2) <= 1e-9 * iv_om2 && p[Sys::IDX_DET_A] == iv_da && p[Sys::IDX_DET_B] == iv_db)) {
+          const double re = p[Sys::IDX_OM_RE], im = p[Sys::IDX_OM_IM];
+          const double da = p[Sys::IDX_DET_A], db = p[Sys::IDX_DET_B];
+          const double mag = sqrt(om2);
+          p[Sys::IDX_OM_RE] = mag; p[Sys::IDX_OM_IM] = mag;
+          if (!Sys::HERMITIAN) p[Sys::NP - 1] = 0.0;
+          double lo, hi;
           Sys::coefs(p, c);
+          Sys::bounds(c, lo, hi, iv_damp);
+          if (Sys::HERMITIAN) { iv_cen = 0.0; iv_R = hi; }
+          else { iv_cen = 0.5 * (lo + hi); iv_R = 0.5 * (hi - lo) + iv_damp; }
+          p[Sys::IDX_OM_RE] = re; p[Sys::IDX_OM_IM] = im;
+          iv_om2 = om2; iv_da = da; iv_db = db;
         }
+        const double damp = iv_damp, cen = iv_cen;
+        double R = iv_R;
+        if (!Sys::HERMITIAN) p[Sys::NP - 1] = cen;
+        Sys::coefs(p, c);
         int nsub = 1;
         if (damp * adt > 2.0) nsub = (int)ceil(0.5 * damp * adt);
         const double h = adt / (double)nsub;

@@ -14,7 +14,9 @@ extern "C" int hostsim_evaluate(int dim, int noisy, long long n_points, const do
                                 double* states) {
   using namespace rydcz;
   for (long long i = 0; i < n_points; ++i) {
-    const PointView pt{points + i * PT_STRIDE, 1};
+    double row[PT_STRIDE + PT_SCRATCH];
+    for (int k = 0; k < PT_STRIDE; ++k) row[k] = points[i * PT_STRIDE + k];
+    const PointView pt{row, 1};
     const double* sg = segs + i * (long long)max_seg * SG_STRIDE;
     double* o = out + i * OUT_STRIDE;
     // same dispatch rule as the CUDA kernels: identical atoms take the exchange-folded path
