@@ -301,6 +301,7 @@ def run_ours(args, rank, world, local_rank):
 
 
 def main():
+    global B_PER_GPU
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -309,7 +310,6 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--candidates", type=int, default=B_PER_GPU, help="bang-bang candidates per GPU per step")
     args = ap.parse_args()
-    global B_PER_GPU
     B_PER_GPU = args.candidates
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
