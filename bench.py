@@ -8,7 +8,7 @@
 One "step" = one pass of the hot path over one batch of synthetic pulse candidates.  Workload
 (BASELINE.json configs[1], SURVEY.md section 8d "config 2"): Jandura-Pupillo bang-bang CZ, 5 piecewise-constant
 segments, two-atom 3-level Lindblad model with the medium apparatus's noise rates; per GPU
-65,536 candidates drawn inside the reference optimiser's bounds (RG/optimize_cz_gate.py:576-587),
+262,144 candidates (--candidates) drawn inside the reference optimiser's bounds (RG/optimize_cz_gate.py:576-587),
 seed 1234 + rank.  Every rank evaluates its own shard (no data-path collective; the only
 exchange is the all-gather of per-candidate scores, timed inside the step) -> "scaling": "weak".
 
@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "cz_lindblad_gate_evals_per_sec"
 UNIT = "evals/s"
-B_PER_GPU = 65536          # default candidates per GPU per step (--candidates)
+B_PER_GPU = 262144         # default candidates per GPU per step (--candidates); 4.6 waves of resident threads
 N_SEG = 5
 
 
