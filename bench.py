@@ -37,84 +37,93 @@ N_SEG = 5
 
 
 # ---------------------------------------------------------------------------- workload
-def medium_apparatus_scalars():
-    """Ω, V, δ1 and the ten noise rates of the reference's medium apparatus with full noise
-    (RG/optimize_cz_gate.py:196-213), as produced by the reference's own prologue and stored in
-    tests/golden/reference_cases.json (case bb5_noisy)."""
-    with open(os.path.join(ROOT, "tests", "golden", "reference_cases.json")) as f:
-        cases = json.load(f)["cases"]
-    c = next(c for c in cases if c["name"] == "bb5_noisy")
-    return c["scalars"], c["rates"]
-
-
-def collapsed(r):
-    b = r.get("branching_1", 0.5)
-    return (r["gamma_r"] * b,
-            r["gamma_r"] * (1 - b) + r["gamma_bbr"] + r["gamma_loss_antitrap"]
-            + r["gamma_loss_background"] + r["gamma_leakage"],
-            r["gamma_phi_laser"] + r["gamma_phi_thermal"] + r["gamma_phi_zeeman"],
-            r["gamma_scatter_intermediate"], r["mJ_leakage_rate"])
+MEDIUM = dict(  # the reference's 'medium' apparatus with full noise (RG/optimize_cz_gate.py:196-213, 885-891)
+    laser_1_power=50e-6, laser_1_waist=50e-6, laser_2_power=0.3, laser_2_waist=50e-6, Delta_e=2 * np.pi * 1e9,
+    laser_1_linewidth_hz=100.0, laser_2_linewidth_hz=100.0, polarization_purity_1=0.99, polarization_purity_2=0.99,
+    temperature=2e-6, spacing_factor=2.8, n_rydberg=70, species="Rb87", tweezer_power=0.020, tweezer_waist=0.8e-6,
+    B_field=1e-4, NA=0.5, include_noise=True)
 
 
 def make_candidates(n, seed):
-    """Bang-bang candidates inside the reference bounds: omega_tau~U[5,40], 4 sorted switching
-    fractions~U[0.01,0.99], 5 phases~U[-pi,pi]; segment table built as evolve_bangbang_jp does
-    (RG/simulation.py:1859-1924)."""
-    sc, rates = medium_apparatus_scalars()
+    """Bang-bang candidates inside the reference optimiser's bounds (RG/optimize_cz_gate.py:576-587):
+    omega_tau~U[5,40], 4 sorted switching fractions~U[0.01,0.99] (times = fraction*omega_tau, as
+    _build_jp_bangbang_inputs does, :501-516), 5 phases~U[-pi,pi]."""
     rng = np.random.default_rng(seed)
-    Om, V, d1 = sc["Omega"], sc["V"], sc["delta_1"]
     ot = rng.uniform(5.0, 40.0, n)
     fr = np.sort(rng.uniform(0.01, 0.99, (n, N_SEG - 1)), axis=1)
     ph = rng.uniform(-np.pi, np.pi, (n, N_SEG))
-    bounds = np.concatenate([np.zeros((n, 1)), fr * ot[:, None], ot[:, None]], axis=1) / Om
-    segs = np.empty((n, N_SEG, 4))
-    segs[:, :, 0] = np.diff(bounds, axis=1)
-    segs[:, :, 1] = Om * np.cos(ph)
-    segs[:, :, 2] = Om * np.sin(ph)
-    segs[:, :, 3] = 0.0
-    pts = np.zeros((n, 12))
-    pts[:, 0], pts[:, 1] = V, d1
-    pts[:, 4:9] = collapsed(rates)
-    return pts, segs, dict(Omega=Om, V=V, delta_1=d1, rates=rates, omega_tau=ot)
+    return dict(omega_tau=ot, switching_times=fr * ot[:, None], phases=ph)
+
+
+def host_plan(cand, idx):
+    """Evaluator inputs of a few candidates via the NumPy prologue (for the CPU path)."""
+    from noisyquantumsimulator_b200.rydberg_gates import prologue
+    sub = {k: v[idx] for k, v in cand.items()}
+    plan = prologue.build_plan("jp", B=len(idx), warn=False, **MEDIUM, **sub)
+    return plan.points, plan.segs
 
 
 # ---------------------------------------------------------------------------- clocks
 class ClockSampler(threading.Thread):
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons of one GPU every ~10 ms DURING the timed region
+    (NVML in-process; falls back to polling nvidia-smi)."""
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu = gpu_index
-        self.rows = []
+        self.sm, self.reasons, self.power = [], set(), []
+        self.sm_max = None
         self.stop_flag = False
+        self.source = "nvml"
 
-    def run(self):
+    def _nvml_loop(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+        self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1e3)
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            for k, bit in names.items():
+                if mask & bit:
+                    self.reasons.add(k)
+            time.sleep(0.01)
+
+    def _smi_loop(self):
+        self.source = "nvidia-smi"
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
             try:
-                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                    "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
-                for line in o.strip().splitlines():
-                    self.rows.append([x.strip() for x in line.split(",")])
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                    str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                r = [x.strip() for x in o.strip().splitlines()[0].split(",")]
+                self.sm.append(float(r[0])); self.sm_max = float(r[1]); self.power.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
+
+    def run(self):
+        try:
+            self._nvml_loop()
+        except Exception:
+            self._smi_loop()
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock samples"]}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "power_w_max": float(max(self.power)) if self.power else None,
+                "source": self.source}
 
 
 # ---------------------------------------------------------------------------- CPU (reference) path
@@ -151,8 +160,9 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    pts, segs, _ = make_candidates(B_PER_GPU, 1234)
     n_sample = max(cores, 8)
+    cand = make_candidates(B_PER_GPU, 1234)
+    pts, segs = host_plan(cand, np.arange(min(B_PER_GPU, n_sample * (args.steps + 1))))
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_path_rate(pts, segs, min(cores, 4), cores)
     times = []
@@ -188,21 +198,24 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     ev = Evaluator(local_rank)
 
-    pts, segs, info = make_candidates(B_PER_GPU, 1234 + rank)
-    d_pts = torch.from_numpy(pts).to(dev)
-    d_segs = torch.from_numpy(segs).to(dev)
+    from noisyquantumsimulator_b200 import rydberg_gates as rg
+    from noisyquantumsimulator_b200.rydberg_gates import device_prologue as dpro
+
+    cand = make_candidates(B_PER_GPU, 1234 + rank)
+    mk, ak = dpro.split_kwargs(dict(MEDIUM, **cand))
+    model = dpro.model_constants("jp", n_segments=N_SEG, **mk)
+    app = dpro.pack_apparatus("jp", B_PER_GPU, **ak)                 # [B, 40] apparatus rows
+    d_app = torch.from_numpy(app).to(dev)
     d_out = torch.empty((B_PER_GPU, 16), dtype=torch.float64, device=dev)
     gathered = torch.empty((world * B_PER_GPU,), dtype=torch.float64, device=dev) if world > 1 else None
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    h_pts = torch.from_numpy(pts).pin_memory()
-    h_segs = torch.from_numpy(segs).pin_memory()
-    h_out = torch.empty((B_PER_GPU, 16), dtype=torch.float64).pin_memory()
 
     dfma_peak, dmma_peak = ev.fp64_peak()
 
     def step():
+        # inputs resident in HBM: prologue kernel -> work sort -> evaluate kernels -> score all-gather
         flush.zero_()
-        ev.evaluate_device(3, True, d_pts, d_segs, None, out=d_out)
+        ev.simulate_device(model, d_app, out=d_out)
         if world > 1:
             dist.all_gather_into_tensor(gathered, d_out[:, 0].contiguous())
 
@@ -237,18 +250,18 @@ def run_ours(args, rank, world, local_rank):
     total_ms = float(t.item())
     value = world * B_PER_GPU * args.steps / (total_ms * 1e-3)
 
-    # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timed region
-    lib_host = ev.lib.rydcz_evaluate_host
+    # ---- end to end through the public API: NumPy candidate arrays in host memory ->
+    # simulate_CZ_gate_batch (packs apparatus rows into pinned staging, rydcz_simulate_host: H2D,
+    # prologue + sort + evaluate kernels, D2H) -> BatchResult arrays in host memory
     def e2e_step():
-        rc = lib_host(ev.ctx, 3, 1, B_PER_GPU, h_pts.data_ptr(), h_segs.data_ptr(), None, N_SEG,
-                      h_out.data_ptr(), None)
-        assert rc == 0
+        res = rg.simulate_CZ_gate_batch("jp", B=B_PER_GPU, device=local_rank, prologue="device", **MEDIUM, **cand)
+        return res.avg_fidelity
     for _ in range(2):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        e2e_step()
+        f_e2e = e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -263,14 +276,16 @@ def run_ours(args, rank, world, local_rank):
     flops_per_launch = float(out_np[:, 15].sum())
     k_ms = float(np.mean(kernel_ms))
     achieved = flops_per_launch / (k_ms * 1e-3) * 1e-12
-    h2d = pts.nbytes + segs.nbytes
-    d2h = B_PER_GPU * 16 * 8
+    h2d = app.nbytes
+    d2h = B_PER_GPU * (16 + 8) * 8
+    assert np.allclose(f_e2e, out_np[:, 0], rtol=0, atol=1e-12)     # both paths computed the same batch
 
     if rank == 0:
         cores = os.cpu_count() or 1
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             n_sample = max(2 * cores, 8)
+            pts, segs = host_plan(cand, np.arange(n_sample))
             rate, dt = cpu_path_rate(pts, segs, n_sample, cores)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"first {n_sample} of the {B_PER_GPU} candidates ({dt:.1f} s), oracle zvode/Adams "
@@ -280,16 +295,16 @@ def run_ours(args, rank, world, local_rank):
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "jp_bangbang_5seg_lindblad_3level", "candidates_per_gpu": B_PER_GPU,
-                       "segments": N_SEG, "V_over_Omega": info["V"] / info["Omega"],
+                       "segments": N_SEG, "apparatus": "medium (RG/optimize_cz_gate.py:196-213), full noise",
                        "l2": "256 MiB flush write between timed iterations", "parallelism": f"shard{world}",
                        "mean_fidelity": float(out_np[:, 0].mean())},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "api": "rydcz_evaluate_host (C ABI, pinned host buffers)"},
+                    "api": "rydberg_gates.simulate_CZ_gate_batch -> rydcz_simulate_host (C ABI), pinned staging"},
             "gpu_launches": launches,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": dfma_peak, "unit": "TFLOP/s",
                          "frac": achieved / dfma_peak, "traffic": None,
-                         "kernel": "rydcz::evaluate_kernel<3,true,false>", "kernel_ms": k_ms,
+                         "kernel": "rydcz::evaluate_kernel<3,true,false,true>", "kernel_ms": k_ms,
                          "flops_per_launch": flops_per_launch,
                          "peak_source": "DFMA microbenchmark (rydcz_fp64_peak) measured in this run; "
                                         "MEASURED_PEAKS.json has no FP64 entry", "dmma_peak": dmma_peak},

@@ -29,6 +29,7 @@
  */
 #ifndef RYDCZ_H
 #define RYDCZ_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -118,6 +119,34 @@ int rydcz_evaluate_shots_host(rydcz_ctx* ctx, int dim, int noisy, int64_t n_poin
                               uint64_t seed, const double* h_points, const double* h_segs,
                               const int32_t* h_n_seg, int max_seg, double* h_out_mean,
                               double* h_out_shots);
+
+/* ---- simulate: scalar prologue on the device, then evaluate ---------------------------------
+ * Replaces, for a batch, steps 1-13 of simulate_CZ_gate (RG/simulation.py:2820-3572): the per-point
+ * physics of laser_physics / trap_physics / protocols / noise_models part 1 (Rabi chain, blockade,
+ * LP table and phase jump, trap-dependent rates, coherent shifts, pulse schedule) runs in
+ * prologue_kernel from an "apparatus row" of RYDCZ_APP_STRIDE doubles per point; species- and
+ * n-level constants arrive once per call in `model` (RYDCZ_MODEL_STRIDE doubles, filled by the
+ * Python mirror: rydberg_gates/device_prologue.py).  Protocols: square LP, JP bang-bang, smooth JP.
+ * `scalars` [n][RYDCZ_SCALAR_STRIDE] (optional) returns Omega, V, tau_total, tau_single, Delta,
+ * Re xi, Im xi, Omega*tau.  n_shots > 0 -> shot means as in rydcz_evaluate_shots_*.            */
+#define RYDCZ_APP_STRIDE 40
+#define RYDCZ_MODEL_STRIDE 32
+#define RYDCZ_SCALAR_STRIDE 8
+int rydcz_app_stride(void);
+int rydcz_model_stride(void);
+int rydcz_scalar_stride(void);
+int rydcz_prologue_device(rydcz_ctx* ctx, const double* h_model, int64_t n_points, const double* d_app,
+                          double* d_points, double* d_segs, int32_t* d_n_seg, double* d_scalars,
+                          void* stream);
+int rydcz_simulate_device(rydcz_ctx* ctx, const double* h_model, int64_t n_points, const double* d_app,
+                          int n_shots, uint64_t seed, double* d_out, double* d_scalars, double* d_states,
+                          void* stream);
+int rydcz_simulate_host(rydcz_ctx* ctx, const double* h_model, int64_t n_points, const double* h_app,
+                        int n_shots, uint64_t seed, double* h_out, double* h_scalars, double* h_states);
+
+/* page-locked host buffers for the *_host entry points (plain malloc memory works too, slower) */
+int rydcz_pinned_alloc(size_t bytes, void** ptr);
+int rydcz_pinned_free(void* ptr);
 
 /* measurement */
 int rydcz_last_kernel_ms(rydcz_ctx* ctx, float* ms);    /* device time of the last evaluate kernel */

@@ -9,6 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "librydcz.so")
 
 POINT_STRIDE, SEG_STRIDE, OUT_STRIDE = 12, 4, 16
+APP_STRIDE, MODEL_STRIDE, SCALAR_STRIDE = 40, 32, 8
 SYSTEMS = ("rho11", "rho01", "rho10", "coh11", "coh01", "coh10")
 
 _dp = C.POINTER(C.c_double)
@@ -36,6 +37,14 @@ _SIGNATURES = {
                                               _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "rydcz_evaluate_shots_host": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_uint64,
                                             _vp, _vp, _vp, C.c_int, _vp, _vp]),
+    "rydcz_app_stride": (C.c_int, []),
+    "rydcz_model_stride": (C.c_int, []),
+    "rydcz_scalar_stride": (C.c_int, []),
+    "rydcz_prologue_device": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rydcz_simulate_device": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int, C.c_uint64, _vp, _vp, _vp, _vp]),
+    "rydcz_simulate_host": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int, C.c_uint64, _vp, _vp, _vp]),
+    "rydcz_pinned_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
+    "rydcz_pinned_free": (C.c_int, [_vp]),
     "rydcz_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "rydcz_launch_count": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "rydcz_fp64_peak": (C.c_int, [_vp, _dp, _dp]),

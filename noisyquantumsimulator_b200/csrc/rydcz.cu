@@ -17,6 +17,7 @@
 
 #include "../../include/rydcz.h"
 #include "rydcz_core.cuh"
+#include "rydcz_prologue.cuh"
 
 namespace rydcz {
 
@@ -138,6 +139,25 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, const uint32_t* __r
     *reinterpret_cast<double2*>(op + k) = make_double2(o[k], o[k + 1]);
 }
 
+// scalar prologue: one thread per point, apparatus row -> point row + pulse schedule
+struct ModelArg { double v[MD_STRIDE]; };
+__global__ void prologue_kernel(ModelArg md, int64_t n_points, const double* __restrict__ app,
+                                double* __restrict__ points, double* __restrict__ segs,
+                                int32_t* __restrict__ n_seg, double* __restrict__ scalars) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_points) return;
+  const int S = (int)md.v[MD_NSEG];
+  double pt[PT_STRIDE], sc[SC_STRIDE];
+  const int ns = prologue_point(md.v, app + i * APP_STRIDE, pt, segs + i * (int64_t)S * SG_STRIDE, sc);
+#pragma unroll
+  for (int k = 0; k < PT_STRIDE; ++k) points[i * PT_STRIDE + k] = pt[k];
+  n_seg[i] = ns;
+  if (scalars) {
+#pragma unroll
+    for (int k = 0; k < SC_STRIDE; ++k) scalars[i * SC_STRIDE + k] = sc[k];
+  }
+}
+
 // deterministic shot mean: one warp per point, fixed-order tree
 __global__ void shot_mean_kernel(int64_t n_points, int n_shots, const double* __restrict__ shots,
                                  double* __restrict__ mean) {
@@ -209,6 +229,9 @@ struct rydcz_ctx {
   // staging for the host entry points
   void* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t stage_cap[6] = {0, 0, 0, 0, 0, 0};
+  // evaluator inputs produced on the device by the prologue kernel
+  void* plan[3] = {nullptr, nullptr, nullptr};
+  size_t plan_cap[3] = {0, 0, 0};
 };
 
 static std::string g_create_error;
@@ -353,6 +376,7 @@ void rydcz_destroy(rydcz_ctx* ctx) {
   cudaFree(ctx->keys); cudaFree(ctx->keys_sorted); cudaFree(ctx->idx); cudaFree(ctx->idx_sorted);
   cudaFree(ctx->cub_tmp);
   for (int i = 0; i < 6; ++i) cudaFree(ctx->stage[i]);
+  for (int i = 0; i < 3; ++i) cudaFree(ctx->plan[i]);
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -481,6 +505,94 @@ int rydcz_evaluate_shots_host(rydcz_ctx* ctx, int dim, int noisy, int64_t n_poin
   if (h_out_shots)
     CK(cudaMemcpyAsync(h_out_shots, ctx->stage[5], n * n_shots * OUT_STRIDE * sizeof(double),
                        cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int rydcz_pinned_alloc(size_t bytes, void** ptr) {
+  if (!ptr) return 2;
+  *ptr = nullptr;
+  return cudaHostAlloc(ptr, bytes ? bytes : 8, cudaHostAllocDefault) == cudaSuccess ? 0 : 1;
+}
+int rydcz_pinned_free(void* ptr) { return (!ptr || cudaFreeHost(ptr) == cudaSuccess) ? 0 : 1; }
+
+int rydcz_app_stride(void) { return APP_STRIDE; }
+int rydcz_model_stride(void) { return MD_STRIDE; }
+int rydcz_scalar_stride(void) { return SC_STRIDE; }
+
+static int check_model(rydcz_ctx* ctx, const double* m) {
+  if (!ctx) return 2;
+  if (!m) return fail(ctx, "null model");
+  const int dim = (int)m[MD_DIM], proto = (int)m[MD_PROTOCOL], S = (int)m[MD_NSEG];
+  if (dim != 3 && dim != 4) return fail(ctx, "model: dim must be 3 or 4");
+  if (proto < 0 || proto > 2) return fail(ctx, "model: protocol must be 0 (lp), 1 (jp) or 2 (sjp)");
+  if (S < 1 || (proto == 0 && S != 2)) return fail(ctx, "model: bad segment count");
+  if (proto == 1 && 2 * S > APP_STRIDE - APP_PROTO) return fail(ctx, "model: too many bang-bang segments");
+  return 0;
+}
+
+int rydcz_prologue_device(rydcz_ctx* ctx, const double* h_model, int64_t n_points, const double* d_app,
+                          double* d_points, double* d_segs, int32_t* d_n_seg, double* d_scalars, void* stream) {
+  if (int rc = check_model(ctx, h_model)) return rc;
+  if (n_points < 0 || n_points > 0x7fffffffLL) return fail(ctx, "n_points out of range");
+  if (n_points == 0) return 0;
+  if (!d_app || !d_points || !d_segs || !d_n_seg) return fail(ctx, "null buffer");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  ModelArg md;
+  memcpy(md.v, h_model, sizeof(md.v));
+  prologue_kernel<<<(unsigned)((n_points + 127) / 128), 128, 0, st>>>(md, n_points, d_app, d_points, d_segs,
+                                                                       d_n_seg, d_scalars);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
+int rydcz_simulate_device(rydcz_ctx* ctx, const double* h_model, int64_t n_points, const double* d_app,
+                          int n_shots, uint64_t seed, double* d_out, double* d_scalars, double* d_states,
+                          void* stream) {
+  if (int rc = check_model(ctx, h_model)) return rc;
+  if (n_points == 0) return 0;
+  if (!d_app || !d_out) return fail(ctx, "null buffer");
+  const int dim = (int)h_model[MD_DIM], S = (int)h_model[MD_NSEG], noisy = h_model[MD_INCLUDE_NOISE] != 0;
+  const size_t n = (size_t)n_points;
+  // evaluator inputs live in context scratch (slots 0..2 are shared with the *_host entry points)
+  if (grow(ctx, &ctx->plan[0], &ctx->plan_cap[0], n * PT_STRIDE * sizeof(double))) return 1;
+  if (grow(ctx, &ctx->plan[1], &ctx->plan_cap[1], n * S * SG_STRIDE * sizeof(double))) return 1;
+  if (grow(ctx, &ctx->plan[2], &ctx->plan_cap[2], n * sizeof(int32_t))) return 1;
+  int rc = rydcz_prologue_device(ctx, h_model, n_points, d_app, (double*)ctx->plan[0], (double*)ctx->plan[1],
+                                 (int32_t*)ctx->plan[2], d_scalars, stream);
+  if (rc) return rc;
+  if (n_shots > 0)
+    return rydcz_evaluate_shots_device(ctx, dim, noisy, n_points, n_shots, seed, (const double*)ctx->plan[0],
+                                       (const double*)ctx->plan[1], (const int32_t*)ctx->plan[2], S, d_out,
+                                       nullptr, stream);
+  return rydcz_evaluate_device(ctx, dim, noisy, n_points, (const double*)ctx->plan[0], (const double*)ctx->plan[1],
+                               (const int32_t*)ctx->plan[2], S, d_out, d_states, stream);
+}
+
+int rydcz_simulate_host(rydcz_ctx* ctx, const double* h_model, int64_t n_points, const double* h_app,
+                        int n_shots, uint64_t seed, double* h_out, double* h_scalars, double* h_states) {
+  if (int rc = check_model(ctx, h_model)) return rc;
+  if (n_points == 0) return 0;
+  if (!h_app || !h_out) return fail(ctx, "null buffer");
+  CK(cudaSetDevice(ctx->device));
+  const size_t n = (size_t)n_points;
+  const int dim = (int)h_model[MD_DIM];
+  const size_t sb = (size_t)rydcz_state_stride(dim) * sizeof(double);
+  if (stage_in(ctx, 0, h_app, n * APP_STRIDE * sizeof(double))) return 1;
+  if (grow(ctx, &ctx->stage[3], &ctx->stage_cap[3], n * OUT_STRIDE * sizeof(double))) return 1;
+  if (h_scalars && grow(ctx, &ctx->stage[1], &ctx->stage_cap[1], n * SC_STRIDE * sizeof(double))) return 1;
+  if (h_states && n_shots > 0) return fail(ctx, "states are not available with shots");
+  if (h_states && grow(ctx, &ctx->stage[4], &ctx->stage_cap[4], n * sb)) return 1;
+  int rc = rydcz_simulate_device(ctx, h_model, n_points, (const double*)ctx->stage[0], n_shots, seed,
+                                 (double*)ctx->stage[3], h_scalars ? (double*)ctx->stage[1] : nullptr,
+                                 h_states ? (double*)ctx->stage[4] : nullptr, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h_out, ctx->stage[3], n * OUT_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (h_scalars)
+    CK(cudaMemcpyAsync(h_scalars, ctx->stage[1], n * SC_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (h_states) CK(cudaMemcpyAsync(h_states, ctx->stage[4], n * sb, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return 0;
 }

@@ -40,8 +40,30 @@ class Evaluator:
             raise RydczError(f"rydcz_create(device={device}) failed: "
                              f"{msg.decode() if msg else rc} -- a CUDA GPU is required")
         self.ctx = ctx
+        self._pinned = {}
+
+    def pinned(self, key: str, shape, dtype=np.float64) -> np.ndarray:
+        """A page-locked NumPy array owned by this evaluator, reused across calls (grown on demand):
+        staging for inputs and results of the *_host entry points."""
+        dtype = np.dtype(dtype)
+        need = int(np.prod(shape)) * dtype.itemsize
+        buf = self._pinned.get(key)
+        if buf is None or buf[1] < need:
+            if buf is not None:
+                self.lib.rydcz_pinned_free(buf[0])
+            p = C.c_void_p()
+            cap = max(need, 8)
+            if self.lib.rydcz_pinned_alloc(cap, C.byref(p)) != 0:
+                raise RydczError("cudaHostAlloc failed")
+            buf = (p, cap)
+            self._pinned[key] = buf
+        raw = (C.c_char * buf[1]).from_address(buf[0].value)
+        return np.frombuffer(raw, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
     def close(self):
+        for p, _ in getattr(self, "_pinned", {}).values():
+            self.lib.rydcz_pinned_free(p)
+        self._pinned = {}
         if getattr(self, "ctx", None):
             self.lib.rydcz_destroy(self.ctx)
             self.ctx = None
@@ -137,6 +159,50 @@ class Evaluator:
             mean.data_ptr(), shots.data_ptr() if shots is not None else None, st),
             "rydcz_evaluate_shots_device")
         return mean, shots
+
+    # ------------------------------------------------------------------ prologue on the device
+    def simulate_host(self, model, app, n_shots: int = 0, seed: int = 1234, want_scalars: bool = True,
+                      want_states: bool = False):
+        """model [32], app [B,40] (rydberg_gates/device_prologue.py) -> (out [B,16], scalars [B,8] or
+        None, states or None).  Prologue kernel, evaluation, copies: all inside the C call."""
+        model, m_ptr = _host(model, np.float64)
+        app, a_ptr = _host(app, np.float64)
+        B = app.shape[0]
+        assert model.shape == (_lib.MODEL_STRIDE,) and app.shape == (B, _lib.APP_STRIDE)
+        # results land in page-locked buffers owned by the evaluator (valid until the next call)
+        out = self.pinned("sim_out", (B, _lib.OUT_STRIDE))
+        sc = self.pinned("sim_sc", (B, _lib.SCALAR_STRIDE)) if want_scalars else None
+        st = self.pinned("sim_st", (B, self.lib.rydcz_state_stride(int(model[0])))) if want_states else None
+        self._check(self.lib.rydcz_simulate_host(
+            self.ctx, m_ptr, B, a_ptr, int(n_shots), int(seed), out.ctypes.data,
+            sc.ctypes.data if want_scalars else None, st.ctypes.data if want_states else None),
+            "rydcz_simulate_host")
+        return out, sc, st
+
+    def simulate_device(self, model, app, n_shots: int = 0, seed: int = 1234, out=None, scalars=None,
+                        stream=None):
+        """Same with the apparatus rows already in HBM (CUDA torch tensor); asynchronous."""
+        import torch
+
+        model, m_ptr = _host(model, np.float64)
+        app = app.contiguous()
+        B = app.shape[0]
+        if out is None:
+            out = torch.empty((B, _lib.OUT_STRIDE), dtype=torch.float64, device=app.device)
+        st = stream if stream is not None else torch.cuda.current_stream(app.device).cuda_stream
+        self._check(self.lib.rydcz_simulate_device(
+            self.ctx, m_ptr, B, app.data_ptr(), int(n_shots), int(seed), out.data_ptr(),
+            scalars.data_ptr() if scalars is not None else None, None, st), "rydcz_simulate_device")
+        return out
+
+    def prologue_device(self, model, app, points, segs, n_seg, scalars=None, stream=None):
+        import torch
+
+        model, m_ptr = _host(model, np.float64)
+        st = stream if stream is not None else torch.cuda.current_stream(app.device).cuda_stream
+        self._check(self.lib.rydcz_prologue_device(
+            self.ctx, m_ptr, app.shape[0], app.data_ptr(), points.data_ptr(), segs.data_ptr(), n_seg.data_ptr(),
+            scalars.data_ptr() if scalars is not None else None, st), "rydcz_prologue_device")
 
     # ------------------------------------------------------------------ measurement
     def set_sort(self, enable: bool):

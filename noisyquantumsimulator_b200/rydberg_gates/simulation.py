@@ -509,7 +509,7 @@ class BatchResult:
 
 def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, seed: int = 1234,
                            return_states: bool = False, return_shots: bool = False, device: int = 0,
-                           plan: GatePlan = None, **kwargs) -> BatchResult:
+                           plan: GatePlan = None, prologue: str = "auto", **kwargs) -> BatchResult:
     """Evaluate B parameter points in one launch.
 
     ``protocol`` is "lp", "jp" (bang-bang) or "sjp"; every physical keyword of ``build_plan``
@@ -517,31 +517,62 @@ def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, se
     parameters, ...) may be a scalar or an array of length B.  ``n_shots > 0`` replaces the analytic
     Doppler and position-noise dephasing rates by per-shot sampling on the device (Philox4x32-10,
     seed/point/shot keyed) and returns shot means.
+
+    ``prologue``: "device" runs the scalar prologue in ``prologue_kernel`` (square LP, bang-bang,
+    smooth JP), "host" runs the NumPy prologue (needed for shaped LP pulses and when the full
+    ``GatePlan`` with ``noise_breakdown`` is wanted), "auto" picks the device when it can.
     """
     from ..engine import get_evaluator
+    from . import device_prologue as dpro
 
-    if plan is None:
-        if B is None:
-            B = max([np.size(v) for v in kwargs.values() if isinstance(v, np.ndarray) and v.ndim == 1] or [1])
-        if n_shots > 0:
-            # shots carry Doppler and position noise explicitly: drop their analytic rates
-            kwargs = dict(kwargs, include_doppler_dephasing=False, include_motional_dephasing=False)
-        plan = build_plan(protocol, B=B, **kwargs)
-    noisy = bool(plan.include_noise)
+    shaped = protocol == "lp" and kwargs.get("pulse_shape", "square") != "square"
+    if prologue == "auto":
+        prologue = "host" if (plan is not None or shaped or return_shots) else "device"
+    if B is None and plan is None:
+        B = max([np.size(v) for v in kwargs.values() if isinstance(v, np.ndarray) and v.ndim >= 1
+                 and np.shape(v)[0] > 1] or [1])
+    if n_shots > 0:
+        # shots carry Doppler and position noise explicitly: drop their analytic rates
+        kwargs = dict(kwargs, include_doppler_dephasing=False, include_motional_dephasing=False)
     ev = get_evaluator(device)
     states = shots = None
-    if n_shots > 0:
-        out, shots = ev.evaluate_shots_host(plan.dim, noisy, n_shots, seed, plan.points, plan.segs, plan.n_seg,
-                                            want_shots=return_shots)
+    if prologue == "device":
+        if shaped:
+            raise ValueError("shaped LP pulses need prologue='host'")
+        if protocol not in PROTOCOL_NAMES:
+            raise ValueError(f"Unknown protocol: {protocol}")
+        mk, ak = dpro.split_kwargs(kwargs)
+        nseg = None
+        if protocol == "jp":
+            ph = ak.get("phases")
+            nseg = 5 if ph is None or np.size(ph) == 0 else np.shape(ph)[-1]
+        model = dpro.model_constants(protocol, n_segments=nseg, **mk)
+        # apparatus rows are written straight into a page-locked staging buffer
+        app = dpro.pack_apparatus(protocol, B, out=ev.pinned("app", (B, dpro.APP_STRIDE))
+                                  if hasattr(ev, "pinned") else None, **ak)
+        out, sc, states = ev.simulate_host(model, app, n_shots, seed, want_scalars=True,
+                                           want_states=return_states and n_shots == 0)
+        out, sc = np.array(out), np.array(sc)          # detach from the reusable staging buffers
+        states = None if states is None else np.array(states)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            voo = np.where(sc[:, 0] > 0, sc[:, 1] / sc[:, 0], np.inf)
+        tau_total, Omega = sc[:, 2], sc[:, 0]
     else:
-        out, states = ev.evaluate_host(plan.dim, noisy, plan.points, plan.segs, plan.n_seg,
-                                       want_states=return_states)
-    sc = plan.scalars
+        if plan is None:
+            plan = build_plan(protocol, B=B, **kwargs)
+        noisy = bool(plan.include_noise)
+        if n_shots > 0:
+            out, shots = ev.evaluate_shots_host(plan.dim, noisy, n_shots, seed, plan.points, plan.segs, plan.n_seg,
+                                                want_shots=return_shots)
+        else:
+            out, states = ev.evaluate_host(plan.dim, noisy, plan.points, plan.segs, plan.n_seg,
+                                           want_states=return_states)
+        tau_total, Omega, voo = plan.scalars["tau_total"], plan.scalars["Omega"], plan.scalars["V_over_Omega"]
     return BatchResult(
         avg_fidelity=out[:, 0], fidelities=out[:, 1:5], f11_population=out[:, 5], cz_phase_fidelity=out[:, 6],
         controlled_phase_rad=out[:, 7], phase_error_from_pi_rad=out[:, 8], loss_probability=out[:, 12],
-        rydberg_residual=out[:, 13], tau_total=sc["tau_total"], Omega=sc["Omega"],
-        V_over_Omega=sc["V_over_Omega"], raw=out, plan=plan, states=states, shots=shots)
+        rydberg_residual=out[:, 13], tau_total=tau_total, Omega=Omega, V_over_Omega=voo, raw=out, plan=plan,
+        states=states, shots=shots)
 
 
 def evolve_state(*args, **kwargs):

@@ -169,3 +169,32 @@ class HostsimEvaluator:
             n_seg = np.full(len(points), segs.shape[1], dtype=np.int32)
         out, st = self._ev(dim, noisy, points, segs, n_seg, want_states=True)
         return out, (st if want_states else None)
+
+
+def hostsim_prologue(model, app):
+    """Host build of the device prologue: (points, segs, n_seg, scalars)."""
+    import ctypes as Ct
+    load_hostsim()
+    lib = Ct.CDLL(os.path.join(HERE, "hostsim", "libhostsim.so"))
+    dp = Ct.POINTER(Ct.c_double)
+    lib.hostsim_prologue.argtypes = [dp, Ct.c_longlong, dp, dp, dp, Ct.POINTER(Ct.c_int), dp]
+    model = np.ascontiguousarray(model, dtype=np.float64)
+    app = np.ascontiguousarray(app, dtype=np.float64)
+    B, S = app.shape[0], int(model[2])
+    pts, segs = np.zeros((B, PT_STRIDE)), np.zeros((B, S, SG_STRIDE))
+    ns, sc = np.zeros(B, dtype=np.int32), np.zeros((B, 8))
+    rc = lib.hostsim_prologue(model.ctypes.data_as(dp), B, app.ctypes.data_as(dp), pts.ctypes.data_as(dp),
+                              segs.ctypes.data_as(dp), ns.ctypes.data_as(Ct.POINTER(Ct.c_int)),
+                              sc.ctypes.data_as(dp))
+    assert rc == 0
+    return pts, segs, ns, sc
+
+
+def _hostsim_simulate_host(self, model, app, n_shots=0, seed=1234, want_scalars=True, want_states=False):
+    assert n_shots == 0, "the host harness has no shot sampler"
+    pts, segs, ns, sc = hostsim_prologue(model, app)
+    out, st = self._ev(int(model[0]), bool(model[3]), pts, segs, ns, want_states=True)
+    return out, (sc if want_scalars else None), (st if want_states else None)
+
+
+HostsimEvaluator.simulate_host = _hostsim_simulate_host

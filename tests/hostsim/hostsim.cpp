@@ -5,6 +5,7 @@
 #define RYDCZ_HD inline
 #define RYDCZ_UNROLL
 #include "../../noisyquantumsimulator_b200/csrc/rydcz_core.cuh"
+#include "../../noisyquantumsimulator_b200/csrc/rydcz_prologue.cuh"
 
 static int g_allow_sym = 1;
 extern "C" void hostsim_allow_sym(int on) { g_allow_sym = on; }
@@ -35,5 +36,16 @@ extern "C" int hostsim_evaluate(int dim, int noisy, long long n_points, const do
       else evaluate_point_d4<false>(pt, sg, n_seg[i], o, st);
     } else return 1;
   }
+  return 0;
+}
+
+// host build of the device prologue (csrc/rydcz_prologue.cuh)
+extern "C" int hostsim_prologue(const double* model, long long n_points, const double* app, double* points,
+                                double* segs, int* n_seg, double* scalars) {
+  using namespace rydcz;
+  const int S = (int)model[MD_NSEG];
+  for (long long i = 0; i < n_points; ++i)
+    n_seg[i] = prologue_point(model, app + i * APP_STRIDE, points + i * PT_STRIDE,
+                              segs + i * (long long)S * SG_STRIDE, scalars + i * SC_STRIDE);
   return 0;
 }

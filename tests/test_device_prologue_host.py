@@ -1,0 +1,57 @@
+"""The device prologue (csrc/rydcz_prologue.cuh, compiled for the host by tests/hostsim) against
+the NumPy prologue, which is itself pinned to the reference's prologue by test_prologue_golden.py."""
+import warnings
+
+import numpy as np
+import pytest
+
+import _cases as C
+from noisyquantumsimulator_b200.rydberg_gates import device_prologue as dp
+from noisyquantumsimulator_b200.rydberg_gates import prologue
+
+CASES = [c for c in C.load("reference_cases.json") + C.load("known_answers.json")
+         if not (c["api"]["protocol"] == "lp" and c["api"]["params"].get("pulse_shape", "square") != "square")]
+
+
+def _close(a, b, tol=2e-12):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    scale = np.maximum(np.abs(b), 1e-300)
+    return np.all((a == b) | (np.abs(a - b) <= tol * scale))
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c["name"])
+def test_device_prologue_matches_numpy_prologue(case):
+    proto, kw = C.plan_kwargs(case)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        plan = prologue.build_plan(proto, B=1, warn=False, **kw)
+    mk, ak = dp.split_kwargs(kw)
+    nseg = plan.segs.shape[1]
+    model = dp.model_constants(proto, n_segments=nseg, **mk)
+    app = dp.pack_apparatus(proto, 1, **ak)
+    pts, segs, ns, sc = C.hostsim_prologue(model, app)
+    assert ns[0] == nseg
+    assert _close(pts[0], plan.points[0]), (pts[0], plan.points[0])
+    scale = np.abs(plan.segs[0]).max(0) + 1e-300
+    assert (np.abs(segs[0] - plan.segs[0]) / scale).max() < 5e-12
+    s = plan.scalars
+    want = [s["Omega"][0], s["V"][0], s["tau_total"][0], s["tau_single"][0], s["Delta"][0], s["xi"][0].real,
+            s["xi"][0].imag, s["omega_tau"][0]]
+    assert _close(sc[0], want, 1e-11)
+
+
+def test_batch_rows_with_arrays():
+    rng = np.random.default_rng(5)
+    B = 257
+    kw = dict(laser_1_power=50e-6, laser_1_waist=50e-6, laser_2_power=10 ** rng.uniform(-1.3, 0.3, B),
+              laser_2_waist=50e-6, Delta_e=2 * np.pi * 1e9, tweezer_power=0.02, tweezer_waist=0.8e-6,
+              temperature=rng.uniform(1e-6, 5e-5, B), spacing_factor=rng.uniform(2.0, 6.0, B),
+              omega_tau=rng.uniform(5, 40, B), switching_times=np.sort(rng.uniform(1, 5, (B, 4)), 1),
+              phases=rng.uniform(-3, 3, (B, 5)))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        plan = prologue.build_plan("jp", B=B, warn=False, **kw)
+    mk, ak = dp.split_kwargs(kw)
+    pts, segs, ns, sc = C.hostsim_prologue(dp.model_constants("jp", n_segments=5, **mk), dp.pack_apparatus("jp", B, **ak))
+    assert _close(pts, plan.points)
+    assert (np.abs(segs - plan.segs) / (np.abs(plan.segs).max((0, 1)) + 1e-300)).max() < 5e-12

@@ -61,3 +61,93 @@ def test_sweep_batch_with_shots_converges_to_deterministic_limit():
     assert s1024 < s64 / 2                      # ~1/4 expected
     same = rg.simulate_CZ_gate_batch("lp", B=36, temperature=20e-6, n_shots=64, seed=1, **base)
     assert np.array_equal(same.avg_fidelity, hot_a.avg_fidelity)   # counter-based: reproducible
+
+
+def test_prologue_kernel_matches_numpy_prologue():
+    """prologue_kernel on the GPU against rydberg_gates/prologue.py (itself pinned to the reference's
+    prologue by the golden fixtures): points, schedules and reported scalars for all three protocols."""
+    import torch
+    import warnings
+    from noisyquantumsimulator_b200.engine import get_evaluator
+    from noisyquantumsimulator_b200.rydberg_gates import device_prologue as dpro, prologue
+    ev = get_evaluator(0)
+    rng = np.random.default_rng(11)
+    B = 4099
+    base = dict(laser_1_power=50e-6, laser_1_waist=50e-6, laser_2_power=10 ** rng.uniform(-1.3, 0.3, B),
+                laser_2_waist=50e-6, Delta_e=2 * np.pi * 1e9, tweezer_power=rng.uniform(0.01, 0.05, B),
+                tweezer_waist=0.8e-6, temperature=rng.uniform(1e-6, 5e-5, B), spacing_factor=rng.uniform(2.0, 6.5, B),
+                B_field=rng.uniform(1e-5, 5e-4, B))
+    protos = {
+        "lp": dict(delta_over_omega=rng.uniform(0.2, 0.5, B)),                  # omega_tau from the table
+        "jp": dict(omega_tau=rng.uniform(5, 40, B), switching_times=np.sort(rng.uniform(1, 5, (B, 6)), 1),
+                   phases=rng.uniform(-3, 3, (B, 7))),
+        "sjp": dict(omega_tau=rng.uniform(5, 25, B), A=rng.uniform(0.2, 3, B), phi_offset=rng.uniform(0, 6, B)),
+    }
+    for proto, pk in protos.items():
+        for dim in (3, 4):
+            kw = dict(base, hilbert_space_dim=dim, **pk)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                plan = prologue.build_plan(proto, B=B, warn=False, **kw)
+            mk, ak = dpro.split_kwargs(kw)
+            S = plan.segs.shape[1]
+            model = dpro.model_constants(proto, n_segments=S, **mk)
+            d_app = torch.from_numpy(dpro.pack_apparatus(proto, B, **ak)).cuda()
+            d_pts = torch.empty((B, 12), dtype=torch.float64, device="cuda")
+            d_seg = torch.empty((B, S, 4), dtype=torch.float64, device="cuda")
+            d_ns = torch.empty(B, dtype=torch.int32, device="cuda")
+            d_sc = torch.empty((B, 8), dtype=torch.float64, device="cuda")
+            ev.prologue_device(model, d_app, d_pts, d_seg, d_ns, d_sc)
+            torch.cuda.synchronize()
+            pts, seg = d_pts.cpu().numpy(), d_seg.cpu().numpy()
+            ok = (pts == plan.points) | (np.abs(pts - plan.points) <= 5e-12 * np.abs(plan.points))
+            assert ok.all(), (proto, dim, np.argwhere(~ok)[:5])
+            scale = np.abs(plan.segs).max((0, 1)) + 1e-300
+            assert (np.abs(seg - plan.segs) / scale).max() < 1e-11
+            assert np.array_equal(d_ns.cpu().numpy(), plan.n_seg)
+            sc = d_sc.cpu().numpy()
+            assert np.allclose(sc[:, 0], plan.scalars["Omega"], rtol=1e-13)
+            assert np.allclose(sc[:, 2], plan.scalars["tau_total"], rtol=1e-13)
+
+
+@pytest.mark.parametrize("proto", ["lp", "jp", "sjp"])
+def test_batch_device_prologue_equals_host_prologue(proto):
+    from noisyquantumsimulator_b200 import rydberg_gates as rg
+    rng = np.random.default_rng(21)
+    B = 300
+    kw = dict(laser_1_power=50e-6, laser_1_waist=50e-6, laser_2_power=10 ** rng.uniform(-1.0, 0.3, B),
+              laser_2_waist=50e-6, Delta_e=2 * np.pi * 1e9, tweezer_power=0.02, tweezer_waist=0.8e-6,
+              temperature=rng.uniform(1e-6, 3e-5, B), spacing_factor=rng.uniform(2.5, 5.0, B), warn=False)
+    if proto == "jp":
+        kw.update(omega_tau=rng.uniform(5, 40, B), switching_times=np.sort(rng.uniform(1, 5, (B, 4)), 1),
+                  phases=rng.uniform(-3, 3, (B, 5)))
+    a = rg.simulate_CZ_gate_batch(proto, B=B, prologue="device", return_states=True, **kw)
+    b = rg.simulate_CZ_gate_batch(proto, B=B, prologue="host", return_states=True, **kw)
+    assert np.abs(a.raw[:, :14] - b.raw[:, :14]).max() < 1e-9
+    assert np.abs(a.states - b.states).max() < 1e-9
+    assert np.allclose(a.tau_total, b.tau_total, rtol=1e-13) and np.allclose(a.V_over_Omega, b.V_over_Omega, rtol=1e-13)
+    assert np.allclose(a.cost(), b.cost(), rtol=1e-7, atol=1e-9)
+
+
+def test_population_objective_and_sharded_evaluation_on_gpu():
+    """Config 4 in miniature: a DE generation as one launch; the sharded evaluator with world = 1."""
+    from noisyquantumsimulator_b200 import sharding
+    from noisyquantumsimulator_b200.engine import get_evaluator
+    from noisyquantumsimulator_b200.rydberg_gates import batched_objective as bo, prologue
+    rng = np.random.default_rng(42)                      # the reference's DE seed (RG/optimize_cz_gate.py:797)
+    for proto, nseg in (("lp", 5), ("jp", 5), ("sjp", 5)):
+        bounds, x0, _ = bo.bounds_and_x0(proto, nseg)
+        lo, hi = np.array(bounds).T
+        X = lo[:, None] + (hi - lo)[:, None] * rng.uniform(size=(len(bounds), 1024))
+        f = bo.make_vectorized_objective(proto, include_noise=True, n_segments=nseg)
+        cost = f(X)
+        assert cost.shape == (1024,) and np.all(np.isfinite(cost)) and cost.min() > 0
+        one = f(X[:, 17])
+        assert abs(one - cost[17]) <= 1e-9 * max(1.0, abs(one))
+    res = bo.optimize_cz_gate_batched("lp", bo.ApparatusConstraints(spacing_factor=5.373584), maxiter=10, popsize=12)
+    assert res.fun < 0.05
+    kw = bo.ApparatusConstraints().plan_kwargs(True)
+    plan = prologue.build_plan("jp", B=64, warn=False, omega_tau=rng.uniform(5, 40, 64), **kw)
+    ev = get_evaluator(0)
+    full = sharding.evaluate_sharded(ev, 3, True, plan.points, plan.segs, plan.n_seg, rank=0, world=1)
+    assert np.array_equal(full, ev.evaluate_host(3, True, plan.points, plan.segs, plan.n_seg)[0])

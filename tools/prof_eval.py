@@ -9,16 +9,19 @@ import torch  # noqa: E402
 
 import bench  # noqa: E402
 from noisyquantumsimulator_b200.engine import Evaluator  # noqa: E402
+from noisyquantumsimulator_b200.rydberg_gates import device_prologue as dpro  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--points", type=int, default=65536)
+ap.add_argument("--points", type=int, default=bench.B_PER_GPU)
 ap.add_argument("--iters", type=int, default=2)
 a = ap.parse_args()
-pts, segs, _ = bench.make_candidates(a.points, 1234)
+cand = bench.make_candidates(a.points, 1234)
+mk, ak = dpro.split_kwargs(dict(bench.MEDIUM, **cand))
+model = dpro.model_constants("jp", n_segments=bench.N_SEG, **mk)
+app = dpro.pack_apparatus("jp", a.points, **ak)
 ev = Evaluator(0)
-dev = torch.device("cuda:0")
-d_pts, d_segs = torch.from_numpy(pts).to(dev), torch.from_numpy(segs).to(dev)
+d_app = torch.from_numpy(app).to("cuda:0")
 for _ in range(a.iters):
-    out, _ = ev.evaluate_device(3, True, d_pts, d_segs, None)
+    out = ev.simulate_device(model, d_app)
 torch.cuda.synchronize()
 print("kernel ms", ev.last_kernel_ms(), "mean F", float(out[:, 0].mean()))
