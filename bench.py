@@ -204,7 +204,7 @@ def run_ours(args, rank, world, local_rank):
     cand = make_candidates(B_PER_GPU, 1234 + rank)
     mk, ak = dpro.split_kwargs(dict(MEDIUM, **cand))
     model = dpro.model_constants("jp", n_segments=N_SEG, **mk)
-    app = dpro.pack_apparatus("jp", B_PER_GPU, **ak)                 # [B, 40] apparatus rows
+    app = dpro.pack_apparatus("jp", B_PER_GPU, **ak)                 # [40, B] apparatus block
     d_app = torch.from_numpy(app).to(dev)
     d_out = torch.empty((B_PER_GPU, 16), dtype=torch.float64, device=dev)
     gathered = torch.empty((world * B_PER_GPU,), dtype=torch.float64, device=dev) if world > 1 else None
@@ -254,7 +254,8 @@ def run_ours(args, rank, world, local_rank):
     # simulate_CZ_gate_batch (packs apparatus rows into pinned staging, rydcz_simulate_host: H2D,
     # prologue + sort + evaluate kernels, D2H) -> BatchResult arrays in host memory
     def e2e_step():
-        res = rg.simulate_CZ_gate_batch("jp", B=B_PER_GPU, device=local_rank, prologue="device", **MEDIUM, **cand)
+        res = rg.simulate_CZ_gate_batch("jp", B=B_PER_GPU, device=local_rank, prologue="device", copy=False,
+                                        **MEDIUM, **cand)
         return res.avg_fidelity
     for _ in range(2):
         e2e_step()

@@ -124,7 +124,9 @@ int rydcz_evaluate_shots_host(rydcz_ctx* ctx, int dim, int noisy, int64_t n_poin
  * Replaces, for a batch, steps 1-13 of simulate_CZ_gate (RG/simulation.py:2820-3572): the per-point
  * physics of laser_physics / trap_physics / protocols / noise_models part 1 (Rabi chain, blockade,
  * LP table and phase jump, trap-dependent rates, coherent shifts, pulse schedule) runs in
- * prologue_kernel from an "apparatus row" of RYDCZ_APP_STRIDE doubles per point; species- and
+ * prologue_kernel from RYDCZ_APP_STRIDE apparatus slots per point, stored SLOT-MAJOR:
+ * app[RYDCZ_APP_STRIDE][n_points] (contiguous columns; NaN = "None", the reference's default;
+ * slot list: enum AppSlot in csrc/rydcz_prologue.cuh); species- and
  * n-level constants arrive once per call in `model` (RYDCZ_MODEL_STRIDE doubles, filled by the
  * Python mirror: rydberg_gates/device_prologue.py).  Protocols: square LP, JP bang-bang, smooth JP.
  * `scalars` [n][RYDCZ_SCALAR_STRIDE] (optional) returns Omega, V, tau_total, tau_single, Delta,

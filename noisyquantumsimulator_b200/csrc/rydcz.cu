@@ -148,7 +148,7 @@ __global__ void prologue_kernel(ModelArg md, int64_t n_points, const double* __r
   if (i >= n_points) return;
   const int S = (int)md.v[MD_NSEG];
   double pt[PT_STRIDE], sc[SC_STRIDE];
-  const int ns = prologue_point(md.v, app + i * APP_STRIDE, pt, segs + i * (int64_t)S * SG_STRIDE, sc);
+  const int ns = prologue_point(md.v, AppView{app + i, n_points}, pt, segs + i * (int64_t)S * SG_STRIDE, sc);
 #pragma unroll
   for (int k = 0; k < PT_STRIDE; ++k) points[i * PT_STRIDE + k] = pt[k];
   n_seg[i] = ns;

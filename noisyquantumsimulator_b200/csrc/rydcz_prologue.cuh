@@ -18,7 +18,7 @@
 
 namespace rydcz {
 
-// ---- apparatus row (doubles); NaN = "None" (use the reference's default) ----------------------
+// ---- apparatus slots (doubles); NaN = "None" (use the reference's default) --------------------
 enum AppSlot {
   APP_P1 = 0, APP_W1 = 1, APP_P2 = 2, APP_W2 = 3, APP_DELTA_E = 4,
   APP_LW1 = 5, APP_LW2 = 6,          // laser linewidths (Hz), NaN = None          RG/simulation.py:2853-2860
@@ -133,7 +133,15 @@ RYDCZ_HD double leakage_rate(double Omega, double Dleak, int shape, double tau, 
 
 // One point: apparatus row -> evaluator point row, segment rows, reported scalars.
 // `seg` must have room for MD_NSEG rows.  Returns the number of segments.
-RYDCZ_HD int prologue_point(const double* __restrict__ md, const double* __restrict__ app,
+// The apparatus block is slot-major: slot k of point i is app_base[k * n_points + i] (contiguous
+// columns: cheap to fill on the host, coalesced on the device); `app` below is &app_base[i].
+struct AppView {
+  const double* base;
+  long long stride;
+  RYDCZ_HD double operator[](int k) const { return base[(long long)k * stride]; }
+};
+
+RYDCZ_HD int prologue_point(const double* __restrict__ md, const AppView app,
                             double* __restrict__ pt, double* __restrict__ seg, double* __restrict__ sc) {
   using namespace phys;
   const int protocol = (int)md[MD_PROTOCOL], dim = (int)md[MD_DIM], S = (int)md[MD_NSEG];
@@ -155,7 +163,7 @@ RYDCZ_HD int prologue_point(const double* __restrict__ md, const double* __restr
   const double V = md[MD_C6] / pow(R, 6.0);
   const double VoO = Om > 0 ? V / Om : INFINITY;
   // protocol parameters
-  const double* pp = app + APP_PROTO;
+  const AppView pp{app.base + (long long)APP_PROTO * app.stride, app.stride};
   double o_t, d_o, tau_single, tau_total, Delta_gate;
   if (protocol == 0) {
     double td, to;

@@ -163,12 +163,12 @@ class Evaluator:
     # ------------------------------------------------------------------ prologue on the device
     def simulate_host(self, model, app, n_shots: int = 0, seed: int = 1234, want_scalars: bool = True,
                       want_states: bool = False):
-        """model [32], app [B,40] (rydberg_gates/device_prologue.py) -> (out [B,16], scalars [B,8] or
+        """model [32], app [40,B] slot-major (rydberg_gates/device_prologue.py) -> (out [B,16], scalars [B,8] or
         None, states or None).  Prologue kernel, evaluation, copies: all inside the C call."""
         model, m_ptr = _host(model, np.float64)
         app, a_ptr = _host(app, np.float64)
-        B = app.shape[0]
-        assert model.shape == (_lib.MODEL_STRIDE,) and app.shape == (B, _lib.APP_STRIDE)
+        B = app.shape[1]
+        assert model.shape == (_lib.MODEL_STRIDE,) and app.shape == (_lib.APP_STRIDE, B)
         # results land in page-locked buffers owned by the evaluator (valid until the next call)
         out = self.pinned("sim_out", (B, _lib.OUT_STRIDE))
         sc = self.pinned("sim_sc", (B, _lib.SCALAR_STRIDE)) if want_scalars else None
@@ -186,7 +186,8 @@ class Evaluator:
 
         model, m_ptr = _host(model, np.float64)
         app = app.contiguous()
-        B = app.shape[0]
+        B = app.shape[1]
+        assert app.shape[0] == _lib.APP_STRIDE
         if out is None:
             out = torch.empty((B, _lib.OUT_STRIDE), dtype=torch.float64, device=app.device)
         st = stream if stream is not None else torch.cuda.current_stream(app.device).cuda_stream
@@ -201,7 +202,7 @@ class Evaluator:
         model, m_ptr = _host(model, np.float64)
         st = stream if stream is not None else torch.cuda.current_stream(app.device).cuda_stream
         self._check(self.lib.rydcz_prologue_device(
-            self.ctx, m_ptr, app.shape[0], app.data_ptr(), points.data_ptr(), segs.data_ptr(), n_seg.data_ptr(),
+            self.ctx, m_ptr, app.shape[1], app.data_ptr(), points.data_ptr(), segs.data_ptr(), n_seg.data_ptr(),
             scalars.data_ptr() if scalars is not None else None, st), "rydcz_prologue_device")
 
     # ------------------------------------------------------------------ measurement

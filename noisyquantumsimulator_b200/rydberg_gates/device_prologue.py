@@ -76,22 +76,23 @@ def pack_apparatus(protocol: str, B: int, *, laser_1_power, laser_1_waist, laser
                    background_loss_rate_hz=None, intensity_noise_frac=0.01, delta_over_omega=None, omega_tau=None,
                    switching_times=None, phases=None, A=None, omega_mod_ratio=None, phi_offset=None,
                    out: np.ndarray = None) -> np.ndarray:
-    """[B, 40] apparatus rows; scalars broadcast, None -> NaN (= 'use the reference default')."""
-    app = out if out is not None else np.empty((B, APP_STRIDE))
+    """[40, B] apparatus block (slot-major: one contiguous column per slot); scalars broadcast,
+    None -> NaN (= 'use the reference default')."""
+    app = out if out is not None else np.empty((APP_STRIDE, B))
+    assert app.shape == (APP_STRIDE, B)
     nan = np.nan
 
-    def put(col, v):
-        app[:, col] = nan if v is None else v
+    def put(slot, v):
+        app[slot] = nan if v is None else v
 
-    for col, v in enumerate((laser_1_power, laser_1_waist, laser_2_power, laser_2_waist, Delta_e,
-                             laser_1_linewidth_hz, laser_2_linewidth_hz)):
-        put(col, v)
+    for slot, v in enumerate((laser_1_power, laser_1_waist, laser_2_power, laser_2_waist, Delta_e,
+                              laser_1_linewidth_hz, laser_2_linewidth_hz)):
+        put(slot, v)
     put(7, np.minimum(polarization_purity_1, polarization_purity_2))
-    for col, v in ((8, tweezer_power), (9, tweezer_waist), (10, tweezer_wavelength_nm), (11, temperature),
-                   (12, B_field), (13, NA), (14, spacing_factor), (15, background_loss_rate_hz),
-                   (16, intensity_noise_frac)):
-        put(col, v)
-    app[:, 17:] = nan
+    for slot, v in ((8, tweezer_power), (9, tweezer_waist), (10, tweezer_wavelength_nm), (11, temperature),
+                    (12, B_field), (13, NA), (14, spacing_factor), (15, background_loss_rate_hz),
+                    (16, intensity_noise_frac)):
+        put(slot, v)
     P = APP_PROTO
     if protocol == "lp":
         put(P, delta_over_omega)
@@ -109,8 +110,8 @@ def pack_apparatus(protocol: str, B: int, *, laser_1_power, laser_1_waist, laser
                                        f"{sw.shape[-1]} switching times")
         assert 2 * S <= APP_STRIDE - APP_PROTO, "too many bang-bang segments for the device prologue"
         put(P, omega_tau)
-        app[:, P + 1:P + S] = sw
-        app[:, P + S:P + 2 * S] = ph
+        app[P + 1:P + S] = sw.T if sw.ndim == 2 else sw[:, None]
+        app[P + S:P + 2 * S] = ph.T if ph.ndim == 2 else ph[:, None]
     return app
 
 

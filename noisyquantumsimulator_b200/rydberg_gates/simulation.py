@@ -509,7 +509,8 @@ class BatchResult:
 
 def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, seed: int = 1234,
                            return_states: bool = False, return_shots: bool = False, device: int = 0,
-                           plan: GatePlan = None, prologue: str = "auto", **kwargs) -> BatchResult:
+                           plan: GatePlan = None, prologue: str = "auto", copy: bool = True,
+                           **kwargs) -> BatchResult:
     """Evaluate B parameter points in one launch.
 
     ``protocol`` is "lp", "jp" (bang-bang) or "sjp"; every physical keyword of ``build_plan``
@@ -521,6 +522,8 @@ def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, se
     ``prologue``: "device" runs the scalar prologue in ``prologue_kernel`` (square LP, bang-bang,
     smooth JP), "host" runs the NumPy prologue (needed for shaped LP pulses and when the full
     ``GatePlan`` with ``noise_breakdown`` is wanted), "auto" picks the device when it can.
+    ``copy=False`` returns views of the evaluator's page-locked result buffers (valid until the
+    next call on that device) instead of fresh arrays.
     """
     from ..engine import get_evaluator
     from . import device_prologue as dpro
@@ -548,12 +551,13 @@ def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, se
             nseg = 5 if ph is None or np.size(ph) == 0 else np.shape(ph)[-1]
         model = dpro.model_constants(protocol, n_segments=nseg, **mk)
         # apparatus rows are written straight into a page-locked staging buffer
-        app = dpro.pack_apparatus(protocol, B, out=ev.pinned("app", (B, dpro.APP_STRIDE))
+        app = dpro.pack_apparatus(protocol, B, out=ev.pinned("app", (dpro.APP_STRIDE, B))
                                   if hasattr(ev, "pinned") else None, **ak)
         out, sc, states = ev.simulate_host(model, app, n_shots, seed, want_scalars=True,
                                            want_states=return_states and n_shots == 0)
-        out, sc = np.array(out), np.array(sc)          # detach from the reusable staging buffers
-        states = None if states is None else np.array(states)
+        if copy:                                       # detach from the reusable staging buffers
+            out, sc = np.array(out), np.array(sc)
+            states = None if states is None else np.array(states)
         with np.errstate(divide="ignore", invalid="ignore"):
             voo = np.where(sc[:, 0] > 0, sc[:, 1] / sc[:, 0], np.inf)
         tau_total, Omega = sc[:, 2], sc[:, 0]

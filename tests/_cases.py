@@ -180,7 +180,8 @@ def hostsim_prologue(model, app):
     lib.hostsim_prologue.argtypes = [dp, Ct.c_longlong, dp, dp, dp, Ct.POINTER(Ct.c_int), dp]
     model = np.ascontiguousarray(model, dtype=np.float64)
     app = np.ascontiguousarray(app, dtype=np.float64)
-    B, S = app.shape[0], int(model[2])
+    assert app.shape[0] == 40, "apparatus block is slot-major [40, B]"
+    B, S = app.shape[1], int(model[2])
     pts, segs = np.zeros((B, PT_STRIDE)), np.zeros((B, S, SG_STRIDE))
     ns, sc = np.zeros(B, dtype=np.int32), np.zeros((B, 8))
     rc = lib.hostsim_prologue(model.ctypes.data_as(dp), B, app.ctypes.data_as(dp), pts.ctypes.data_as(dp),

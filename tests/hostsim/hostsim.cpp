@@ -45,7 +45,7 @@ extern "C" int hostsim_prologue(const double* model, long long n_points, const d
   using namespace rydcz;
   const int S = (int)model[MD_NSEG];
   for (long long i = 0; i < n_points; ++i)
-    n_seg[i] = prologue_point(model, app + i * APP_STRIDE, points + i * PT_STRIDE,
+    n_seg[i] = prologue_point(model, AppView{app + i, n_points}, points + i * PT_STRIDE,
                               segs + i * (long long)S * SG_STRIDE, scalars + i * SC_STRIDE);
   return 0;
 }

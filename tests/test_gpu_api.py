@@ -92,7 +92,7 @@ def test_prologue_kernel_matches_numpy_prologue():
             mk, ak = dpro.split_kwargs(kw)
             S = plan.segs.shape[1]
             model = dpro.model_constants(proto, n_segments=S, **mk)
-            d_app = torch.from_numpy(dpro.pack_apparatus(proto, B, **ak)).cuda()
+            d_app = torch.from_numpy(dpro.pack_apparatus(proto, B, **ak)).cuda()      # [40, B] slot-major
             d_pts = torch.empty((B, 12), dtype=torch.float64, device="cuda")
             d_seg = torch.empty((B, S, 4), dtype=torch.float64, device="cuda")
             d_ns = torch.empty(B, dtype=torch.int32, device="cuda")
