@@ -304,7 +304,11 @@ def run_ours(args, rank, world, local_rank):
                     "api": "rydberg_gates.simulate_CZ_gate_batch -> rydcz_simulate_host (C ABI), pinned staging"},
             "gpu_launches": launches,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": dfma_peak, "unit": "TFLOP/s",
-                         "frac": achieved / dfma_peak, "traffic": None,
+                         "frac": achieved / dfma_peak,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this batch size, one
+                         # `ncu --set full` capture (profiles/r01_evaluate_kernel_bb5_262k.txt); scales with B
+                         "traffic": 85.58e6 * B_PER_GPU / 262144,
+                         "algorithmic_bytes": float(B_PER_GPU * (12 * 8 + N_SEG * 32 + 4 + 16 * 8)),
                          "kernel": "rydcz::evaluate_kernel<3,true,false,true>", "kernel_ms": k_ms,
                          "flops_per_launch": flops_per_launch,
                          "peak_source": "DFMA microbenchmark (rydcz_fp64_peak) measured in this run; "

@@ -158,9 +158,17 @@ def emit_system(sysm: model.RealSystem, struct_name: str) -> str:
     A("  }")
     # apply
     A("  RYDCZ_HD static void apply(const double* __restrict__ c, const double* __restrict__ x, double* __restrict__ y) {")
-    for i in range(n):
-        for (j, q, s) in rows.get(i, []):
-            A(f"    y[{i}] {'+=' if s > 0 else '-='} c[{q}] * x[{j}];")
+    order = os.environ.get("RYDCZ_EMIT_ORDER", "row")
+    stmts = [(i, j, q, s) for i in range(n) for (j, q, s) in rows.get(i, [])]
+    if order == "col":        # walk the source vector: consecutive FMAs hit different accumulators
+        stmts.sort(key=lambda t: (t[1], t[0]))
+    elif order == "rr":       # round-robin over rows: k-th nonzero of every row, then the (k+1)-th ...
+        per = {}
+        for t in stmts:
+            per.setdefault(t[0], []).append(t)
+        stmts = [per[i][k] for k in range(max(len(v) for v in per.values())) for i in sorted(per) if k < len(per[i])]
+    for (i, j, q, s) in stmts:
+        A(f"    y[{i}] {'+=' if s > 0 else '-='} c[{q}] * x[{j}];")
     A("  }")
     A("};")
     A("")
