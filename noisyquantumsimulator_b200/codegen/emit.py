@@ -79,8 +79,10 @@ def emit_system(sysm: model.RealSystem, struct_name: str) -> str:
     A(f"  static constexpr int NP = {len(pnames)};   // {', '.join(pnames)}")
     A(f"  static constexpr bool HERMITIAN = {'true' if sysm.hermitian else 'false'};")
     nz0 = np.nonzero(sysm.x0)[0]
-    assert len(nz0) == 1 and sysm.x0[nz0[0]] == 1.0
-    A(f"  static constexpr int START = {int(nz0[0])};   // x0 = e_START")
+    assert all(sysm.x0[k] == 1.0 for k in nz0)
+    A("  RYDCZ_HD static void init(double* __restrict__ x) {   // the start operator")
+    A("    " + " ".join(f"x[{k}] = {'1.0' if k in nz0 else '0.0'};" for k in range(n)))
+    A("  }")
     plist = list(sysm.params)
 
     def pidx(*names):
@@ -186,6 +188,9 @@ def emit_dim(d: int) -> str:
     folded = model.symmetric_systems(d)
     for key, sysm in folded.items():
         out.append(emit_system(sysm, f"Sys_{key}_d{d}"))
+    for key, sysm in model.combined_input_systems(d).items():
+        out.append(emit_system(sysm, f"Sys_{key}_d{d}"))
+        out.append(f"static constexpr int {key.upper()}_COH_OFFSET_D{d} = {systems['rho' + key[2:]].n};")
     # readout indices
     N = d * d
     out.append(f"// readout indices (d={d})")

@@ -62,7 +62,7 @@ enum PointSlot {
   PT_SIG_RELR = 10,// Monte-Carlo: std of dR/R0 = sqrt(2) sigma_r / R0
   PT_RESERVED = 11,
   PT_STRIDE = 12,
-  PT_SCRATCH = 6    // extra per-thread slots behind a PointView (not part of the C-ABI row)
+  PT_SCRATCH = 8    // extra per-thread slots behind a PointView (not part of the C-ABI row)
 };
 // one segment row: dt (s), Re Omega, Im Omega, Delta (rad/s)
 enum SegSlot { SG_DT = 0, SG_RE = 1, SG_IM = 2, SG_DET = 3, SG_STRIDE = 4 };
@@ -137,40 +137,34 @@ template <class Sys>
 RYDCZ_HD void run_system(double (&x)[Sys::N], const PointView pt,
                          const double* __restrict__ seg, int n_seg, bool noisy, double& steps) {
   constexpr int N = Sys::N;
-  RYDCZ_UNROLL
-  for (int i = 0; i < N; ++i) x[i] = (i == Sys::START) ? 1.0 : 0.0;
+  Sys::init(x);
   double c[Sys::NC], b1[N], b2[N];
   double jp = 0.0, jk = 0.0, norm = 0.0, kd = 0.0, tz = 0.0, rot = 0.0;
+  double &rot_total = pt.scratch(6), &rot_comp = pt.scratch(7);   // Kahan-summed shift phase
+  rot_total = 0.0; rot_comp = 0.0;
   // cached Chebyshev interval, kept in the point's scratch slots (shared memory on the GPU)
   double &iv_om2 = pt.scratch(0), &iv_da = pt.scratch(1), &iv_db = pt.scratch(2), &iv_R = pt.scratch(3),
          &iv_cen = pt.scratch(4), &iv_damp = pt.scratch(5);
   iv_om2 = -1.0;
-  int k = 0;         // Clenshaw index still to process in the active sub-step
+  int k = -2;        // (even) Clenshaw index to process next in the active sub-step; < 0: none
   int K = 0;         // its starting value
   int sub_left = 0;  // further sub-steps of the current segment
   int s = 0;         // next segment row to load
   bool active = false;
   for (;;) {
-    if (k < 2) {
+    if (k < 0) {
       if (active) {
-        // k = 0:  exp(hG) x = (J_0 x + A b1 + b2) / (J_0 + 2 sum_even J_k),  A b1 = (2A)(b1/2)
-        RYDCZ_UNROLL
-        for (int i = 0; i < N; ++i) { b1[i] *= 0.5; b2[i] = fma(jk, x[i], b2[i]); }
-        Sys::apply(c, b1, b2);
-        const double inv = 1.0 / (norm + jk);
+        // the k = 0 step below left  b2 = 2 (J_0 x + A b1 + b_2) = 2 exp(hG) x (J_0 + 2 sum_even J_k)
+        const double inv = 0.5 / norm;
         RYDCZ_UNROLL
         for (int i = 0; i < N; ++i) x[i] = b2[i] * inv;
         steps += (double)(K + 1);
         if (!Sys::HERMITIAN) {
-          // undo the spectral shift: every complex component times exp(-i cen h)
-          double sn, cs;
-          sincos(rot, &sn, &cs);
-          RYDCZ_UNROLL
-          for (int i = 0; i < N; i += 2) {
-            const double re = x[i], im = x[i + 1];
-            x[i] = fma(re, cs, im * sn);
-            x[i + 1] = fma(im, cs, -re * sn);
-          }
+          // the shift's phase factor commutes with the (complex-linear) evolution: accumulate the
+          // angle (compensated sum: ~1000 terms for shaped pulses) and rotate once after the last segment
+          const double yk = rot - rot_comp, tk = rot_total + yk;
+          rot_comp = (tk - rot_total) - yk;
+          rot_total = tk;
         }
         active = false;
       }
@@ -250,20 +244,40 @@ RYDCZ_HD void run_system(double (&x)[Sys::N], const PointView pt,
       k = K;
       active = true;
     }
+    // The last term, S = J_0 x + A b1 + b2, is folded into the uniform step: doubling b2 first makes
+    // the regular even step produce 2 S, so the sparse matvec of the k = 0 term also runs with
+    // the whole warp instead of inside the divergent transition.
+    if (k == 0) {
+      RYDCZ_UNROLL
+      for (int i = 0; i < N; ++i) b2[i] += b2[i];
+    }
     // k even:   b2 <- 2 J_k x + (2A) b1 + b2
     double ak = jk + jk;
     RYDCZ_UNROLL
     for (int i = 0; i < N; ++i) b2[i] = fma(ak, x[i], b2[i]);
     Sys::apply(c, b1, b2);
-    norm += ak;
-    double jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
-    // k-1 odd:  b1 <- 2 J_{k-1} x + (2A) b2 + b1
-    ak = jk + jk;
-    RYDCZ_UNROLL
-    for (int i = 0; i < N; ++i) b1[i] = fma(ak, x[i], b1[i]);
-    Sys::apply(c, b2, b1);
-    jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
+    norm += (k == 0) ? jk : ak;
+    if (k >= 2) {
+      double jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
+      // k-1 odd:  b1 <- 2 J_{k-1} x + (2A) b2 + b1
+      ak = jk + jk;
+      RYDCZ_UNROLL
+      for (int i = 0; i < N; ++i) b1[i] = fma(ak, x[i], b1[i]);
+      Sys::apply(c, b2, b1);
+      jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
+    }
     k -= 2;
+  }
+  if (!Sys::HERMITIAN) {
+    // undo the spectral shifts: every complex component times exp(-i sum_s cen_s h_s)
+    double sn, cs;
+    sincos(rot_total, &sn, &cs);
+    RYDCZ_UNROLL
+    for (int i = 0; i < N; i += 2) {
+      const double re = x[i], im = x[i + 1];
+      x[i] = fma(re, cs, im * sn);
+      x[i + 1] = fma(im, cs, -re * sn);
+    }
   }
 }
 
@@ -334,25 +348,33 @@ RYDCZ_HD void cz_epilogue(bool noisy, double p01, double p10, double p11,
       if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh11_d##D::N; ++i) states[SL::COH11 + i] = x[i]; } \
     }                                                                                               \
     if (NOISY) {                                                                                    \
-      double x[Sys_rho01_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_rho01_d##D>(x, pt, seg, n_seg, true, st);                                      \
-      steps += st; flops += st * 2.0 * (Sys_rho01_d##D::NNZ + Sys_rho01_d##D::N);                   \
+      /* single-atom inputs: rho_ab and its |ab><00| coherence share one Chebyshev loop */           \
+      double x[Sys_in01_d##D::N]; st = 0.0;                                                         \
+      run_system<Sys_in01_d##D>(x, pt, seg, n_seg, true, st);                                       \
+      steps += st; flops += st * 2.0 * (Sys_in01_d##D::NNZ + Sys_in01_d##D::N);                     \
       p01 = x[RHO01_POP_D##D];                                                                      \
-      if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_rho01_d##D::N; ++i) states[SL::RHO01 + i] = x[i]; } \
-      double y[Sys_rho10_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_rho10_d##D>(y, pt, seg, n_seg, true, st);                                      \
-      steps += st; flops += st * 2.0 * (Sys_rho10_d##D::NNZ + Sys_rho10_d##D::N);                   \
+      c01r = x[IN01_COH_OFFSET_D##D + COH01_RE_D##D]; c01i = x[IN01_COH_OFFSET_D##D + COH01_IM_D##D]; \
+      if (states) {                                                                                 \
+        RYDCZ_UNROLL for (int i = 0; i < Sys_rho01_d##D::N; ++i) states[SL::RHO01 + i] = x[i];      \
+        RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d##D::N; ++i) states[SL::COH01 + i] = x[IN01_COH_OFFSET_D##D + i]; \
+      }                                                                                             \
+      double y[Sys_in10_d##D::N]; st = 0.0;                                                         \
+      run_system<Sys_in10_d##D>(y, pt, seg, n_seg, true, st);                                       \
+      steps += st; flops += st * 2.0 * (Sys_in10_d##D::NNZ + Sys_in10_d##D::N);                     \
       p10 = y[RHO10_POP_D##D];                                                                      \
-      if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_rho10_d##D::N; ++i) states[SL::RHO10 + i] = y[i]; } \
-    }                                                                                               \
-    {                                                                                               \
+      c10r = y[IN10_COH_OFFSET_D##D + COH10_RE_D##D]; c10i = y[IN10_COH_OFFSET_D##D + COH10_IM_D##D]; \
+      if (states) {                                                                                 \
+        RYDCZ_UNROLL for (int i = 0; i < Sys_rho10_d##D::N; ++i) states[SL::RHO10 + i] = y[i];      \
+        RYDCZ_UNROLL for (int i = 0; i < Sys_coh10_d##D::N; ++i) states[SL::COH10 + i] = y[IN10_COH_OFFSET_D##D + i]; \
+      }                                                                                             \
+    } else {                                                                                        \
       double x[Sys_coh01_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_coh01_d##D>(x, pt, seg, n_seg, NOISY, st);                                     \
+      run_system<Sys_coh01_d##D>(x, pt, seg, n_seg, false, st);                                     \
       steps += st; flops += st * 2.0 * (Sys_coh01_d##D::NNZ + Sys_coh01_d##D::N);                   \
       c01r = x[COH01_RE_D##D]; c01i = x[COH01_IM_D##D];                                             \
       if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d##D::N; ++i) states[SL::COH01 + i] = x[i]; } \
       double y[Sys_coh10_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_coh10_d##D>(y, pt, seg, n_seg, NOISY, st);                                     \
+      run_system<Sys_coh10_d##D>(y, pt, seg, n_seg, false, st);                                     \
       steps += st; flops += st * 2.0 * (Sys_coh10_d##D::NNZ + Sys_coh10_d##D::N);                   \
       c10r = y[COH10_RE_D##D]; c10i = y[COH10_IM_D##D];                                             \
       if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh10_d##D::N; ++i) states[SL::COH10 + i] = y[i]; } \
@@ -400,16 +422,20 @@ RYDCZ_DEFINE_EVALUATE(4)
       }                                                                                             \
     }                                                                                               \
     if (NOISY) {                                                                                    \
-      double x[Sys_rho01_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_rho01_d##D>(x, pt, seg, n_seg, true, st);                                      \
-      steps += st; flops += st * 2.0 * (Sys_rho01_d##D::NNZ + Sys_rho01_d##D::N);                   \
+      double x[Sys_in01_d##D::N]; st = 0.0;                                                         \
+      run_system<Sys_in01_d##D>(x, pt, seg, n_seg, true, st);                                       \
+      steps += st; flops += st * 2.0 * (Sys_in01_d##D::NNZ + Sys_in01_d##D::N);                     \
       p01 = x[RHO01_POP_D##D];                                                                      \
-      if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_rho01_d##D::N; ++i) {                      \
-        states[SL::RHO01 + i] = x[i]; states[SL::RHO10 + i] = x[i]; } }                             \
-    }                                                                                               \
-    {                                                                                               \
+      c01r = x[IN01_COH_OFFSET_D##D + COH01_RE_D##D]; c01i = x[IN01_COH_OFFSET_D##D + COH01_IM_D##D]; \
+      if (states) {                                                                                 \
+        RYDCZ_UNROLL for (int i = 0; i < Sys_rho01_d##D::N; ++i) {                                  \
+          states[SL::RHO01 + i] = x[i]; states[SL::RHO10 + i] = x[i]; }                             \
+        RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d##D::N; ++i) {                                  \
+          states[SL::COH01 + i] = x[IN01_COH_OFFSET_D##D + i]; states[SL::COH10 + i] = x[IN01_COH_OFFSET_D##D + i]; } \
+      }                                                                                             \
+    } else {                                                                                        \
       double x[Sys_coh01_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_coh01_d##D>(x, pt, seg, n_seg, NOISY, st);                                     \
+      run_system<Sys_coh01_d##D>(x, pt, seg, n_seg, false, st);                                     \
       steps += st; flops += st * 2.0 * (Sys_coh01_d##D::NNZ + Sys_coh01_d##D::N);                   \
       c01r = x[COH01_RE_D##D]; c01i = x[COH01_IM_D##D];                                             \
       if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d##D::N; ++i) {                      \
