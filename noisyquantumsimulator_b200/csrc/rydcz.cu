@@ -83,12 +83,12 @@ __global__ void work_kernel(int64_t n_points, const double* __restrict__ points,
 // SYM = true handles the points whose two atoms see identical parameters (exchange-folded
 // systems, ~half the FMAs and half the registers); SYM = false handles the rest.  Both kernels
 // are launched over the whole batch and each thread returns at once if the point is not its kind.
-// MB = CTAs per SM the register budget is sized for.  The folded kernel is built for 3 (168
-// registers, a few spills outside the hot loop) and for 2 (212 registers, none): three CTAs per SM
-// hide FP64 latency slightly better on large batches, two leave fewer resident slots to fill, which
-// wins when the batch is only one to two waves of threads (launch_eval picks).
-template <int D, bool NOISY, bool SHOTS, bool SYM, int MB>
-__global__ void __launch_bounds__(kBlock, MB)
+// Two CTAs of 128 threads per SM for both kernels.  The folded kernel would fit three (168
+// registers with ~180 B of spills, some inside the hot loop); measured on B200 that build is no
+// faster on large batches (19.5-20.0 ms vs 20.0 ms for 262,144 bang-bang candidates) and 15 %
+// slower on a 65,536-point batch, where fewer resident slots fill the machine more evenly.
+template <int D, bool NOISY, bool SHOTS, bool SYM>
+__global__ void __launch_bounds__(kBlock, 2)
 evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, const uint32_t* __restrict__ order,
                 const double* __restrict__ points, const double* __restrict__ segs,
                 const int32_t* __restrict__ n_seg, int max_seg, double* __restrict__ out,
@@ -326,16 +326,11 @@ static int launch_eval(rydcz_ctx* ctx, int64_t n_items, int n_shots, uint64_t se
                        double* d_out, double* d_states, cudaStream_t st) {
   const unsigned grid = (unsigned)((n_items + kBlock - 1) / kBlock);
   CK(cudaEventRecord(ctx->ev0, st));
-  evaluate_kernel<D, NOISY, SHOTS, false, 2><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, order, d_points,
-                                                                      d_segs, d_n_seg, max_seg, d_out, d_states);
+  evaluate_kernel<D, NOISY, SHOTS, false><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, order, d_points,
+                                                                   d_segs, d_n_seg, max_seg, d_out, d_states);
   CK(cudaGetLastError());
-  // fewer than ~2 waves of 3-CTA/SM slots: the 2-CTA/SM build fills the machine more evenly
-  if (n_items < (int64_t)2 * ctx->sm_count * 3 * kBlock)
-    evaluate_kernel<D, NOISY, SHOTS, true, 2><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, order, d_points,
-                                                                       d_segs, d_n_seg, max_seg, d_out, d_states);
-  else
-    evaluate_kernel<D, NOISY, SHOTS, true, 3><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, order, d_points,
-                                                                       d_segs, d_n_seg, max_seg, d_out, d_states);
+  evaluate_kernel<D, NOISY, SHOTS, true><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, order, d_points,
+                                                                  d_segs, d_n_seg, max_seg, d_out, d_states);
   CK(cudaGetLastError());
   CK(cudaEventRecord(ctx->ev1, st));
   ctx->timed = true;

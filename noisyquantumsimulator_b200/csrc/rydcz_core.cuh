@@ -146,16 +146,19 @@ RYDCZ_HD void run_system(double (&x)[Sys::N], const PointView pt,
   double &iv_om2 = pt.scratch(0), &iv_da = pt.scratch(1), &iv_db = pt.scratch(2), &iv_R = pt.scratch(3),
          &iv_cen = pt.scratch(4), &iv_damp = pt.scratch(5);
   iv_om2 = -1.0;
-  int k = -2;        // (even) Clenshaw index to process next in the active sub-step; < 0: none
+  int k = 0;         // Clenshaw index still to process in the active sub-step
   int K = 0;         // its starting value
   int sub_left = 0;  // further sub-steps of the current segment
   int s = 0;         // next segment row to load
   bool active = false;
   for (;;) {
-    if (k < 0) {
+    if (k < 2) {
       if (active) {
-        // the k = 0 step below left  b2 = 2 (J_0 x + A b1 + b_2) = 2 exp(hG) x (J_0 + 2 sum_even J_k)
-        const double inv = 0.5 / norm;
+        // k = 0:  exp(hG) x = (J_0 x + A b1 + b2) / (J_0 + 2 sum_even J_k),  A b1 = (2A)(b1/2)
+        RYDCZ_UNROLL
+        for (int i = 0; i < N; ++i) { b1[i] *= 0.5; b2[i] = fma(jk, x[i], b2[i]); }
+        Sys::apply(c, b1, b2);
+        const double inv = 1.0 / (norm + jk);
         RYDCZ_UNROLL
         for (int i = 0; i < N; ++i) x[i] = b2[i] * inv;
         steps += (double)(K + 1);
@@ -244,28 +247,19 @@ RYDCZ_HD void run_system(double (&x)[Sys::N], const PointView pt,
       k = K;
       active = true;
     }
-    // The last term, S = J_0 x + A b1 + b2, is folded into the uniform step: doubling b2 first makes
-    // the regular even step produce 2 S, so the sparse matvec of the k = 0 term also runs with
-    // the whole warp instead of inside the divergent transition.
-    if (k == 0) {
-      RYDCZ_UNROLL
-      for (int i = 0; i < N; ++i) b2[i] += b2[i];
-    }
     // k even:   b2 <- 2 J_k x + (2A) b1 + b2
     double ak = jk + jk;
     RYDCZ_UNROLL
     for (int i = 0; i < N; ++i) b2[i] = fma(ak, x[i], b2[i]);
     Sys::apply(c, b1, b2);
-    norm += (k == 0) ? jk : ak;
-    if (k >= 2) {
-      double jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
-      // k-1 odd:  b1 <- 2 J_{k-1} x + (2A) b2 + b1
-      ak = jk + jk;
-      RYDCZ_UNROLL
-      for (int i = 0; i < N; ++i) b1[i] = fma(ak, x[i], b1[i]);
-      Sys::apply(c, b2, b1);
-      jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
-    }
+    norm += ak;
+    double jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
+    // k-1 odd:  b1 <- 2 J_{k-1} x + (2A) b2 + b1
+    ak = jk + jk;
+    RYDCZ_UNROLL
+    for (int i = 0; i < N; ++i) b1[i] = fma(ak, x[i], b1[i]);
+    Sys::apply(c, b2, b1);
+    jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
     k -= 2;
   }
   if (!Sys::HERMITIAN) {
