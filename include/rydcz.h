@@ -146,6 +146,20 @@ int rydcz_simulate_device(rydcz_ctx* ctx, const double* h_model, int64_t n_point
 int rydcz_simulate_host(rydcz_ctx* ctx, const double* h_model, int64_t n_points, const double* h_app,
                         int n_shots, uint64_t seed, double* h_out, double* h_scalars, double* h_states);
 
+/* Column form of rydcz_simulate_host, pipelined -- the call simulate_CZ_gate_batch makes.
+ * Slot k of point i is h_cols[k][i * col_stride[k]] when h_cols[k] != NULL, else the batch-wide
+ * constant h_const[k] (h_cols, col_stride, h_const: RYDCZ_APP_STRIDE entries; col_stride NULL = all
+ * 1; strides in doubles, so a column of a row-major [n][m] array is {ptr + k, m}).  Only varying
+ * slots cross PCIe.  The batch is cut into chunks (rydcz_set_chunk, default 65536 evaluations) and
+ * each chunk's packing, H2D copy, kernels and D2H copy run on one of three streams, so copies and
+ * host work overlap the kernels of the neighbouring chunks.  Results are identical to the
+ * unchunked call (Monte-Carlo shots are keyed by the point's index in the whole batch).  h_out /
+ * h_scalars / h_states should be page-locked for the D2H copies to overlap. */
+int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_points,
+                             const double* const* h_cols, const int64_t* col_stride, const double* h_const,
+                             int n_shots, uint64_t seed, double* h_out, double* h_scalars, double* h_states);
+int rydcz_set_chunk(rydcz_ctx* ctx, int64_t points_per_chunk);
+
 /* page-locked host buffers for the *_host entry points (plain malloc memory works too, slower) */
 int rydcz_pinned_alloc(size_t bytes, void** ptr);
 int rydcz_pinned_free(void* ptr);

@@ -43,6 +43,8 @@ _SIGNATURES = {
     "rydcz_prologue_device": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rydcz_simulate_device": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int, C.c_uint64, _vp, _vp, _vp, _vp]),
     "rydcz_simulate_host": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int, C.c_uint64, _vp, _vp, _vp]),
+    "rydcz_simulate_host_cols": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, C.c_uint64, _vp, _vp, _vp]),
+    "rydcz_set_chunk": (C.c_int, [_vp, C.c_int64]),
     "rydcz_pinned_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "rydcz_pinned_free": (C.c_int, [_vp]),
     "rydcz_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),

@@ -89,7 +89,8 @@ __global__ void work_kernel(int64_t n_points, const double* __restrict__ points,
 // slower on a 65,536-point batch, where fewer resident slots fill the machine more evenly.
 template <int D, bool NOISY, bool SHOTS, bool SYM>
 __global__ void __launch_bounds__(kBlock, 2)
-evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, const uint32_t* __restrict__ order,
+evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, int64_t point_base,
+                const uint32_t* __restrict__ order,
                 const double* __restrict__ points, const double* __restrict__ segs,
                 const int32_t* __restrict__ n_seg, int max_seg, double* __restrict__ out,
                 double* __restrict__ states) {
@@ -117,8 +118,9 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, const uint32_t* __r
   for (int k = 0; k < PT_STRIDE; ++k) mine[k * kBlock] = row[k];
   if (SHOTS) {
     double da, db, er, unused;
-    philox_normal2(seed, (uint32_t)point, shot, 0u, da, db);
-    philox_normal2(seed, (uint32_t)point, shot, 1u, er, unused);
+    // counter = (index of the point in the whole batch, shot, stream): a chunked call draws the same shots
+    philox_normal2(seed, (uint32_t)(point_base + point), shot, 0u, da, db);
+    philox_normal2(seed, (uint32_t)(point_base + point), shot, 1u, er, unused);
     mine[PT_OFF_A * kBlock] += row[PT_SIG_DET] * da;
     mine[PT_OFF_B * kBlock] += row[PT_SIG_DET] * db;
     const double q = 1.0 + row[PT_SIG_RELR] * er;
@@ -146,13 +148,13 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, const uint32_t* __r
 // scalar prologue: one thread per point, apparatus row -> point row + pulse schedule
 struct ModelArg { double v[MD_STRIDE]; };
 __global__ void prologue_kernel(ModelArg md, int64_t n_points, const double* __restrict__ app,
-                                double* __restrict__ points, double* __restrict__ segs,
+                                int64_t app_stride, double* __restrict__ points, double* __restrict__ segs,
                                 int32_t* __restrict__ n_seg, double* __restrict__ scalars) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_points) return;
   const int S = (int)md.v[MD_NSEG];
   double pt[PT_STRIDE], sc[SC_STRIDE];
-  const int ns = prologue_point(md.v, AppView{app + i, n_points}, pt, segs + i * (int64_t)S * SG_STRIDE, sc);
+  const int ns = prologue_point(md.v, AppView{app + i, app_stride}, pt, segs + i * (int64_t)S * SG_STRIDE, sc);
 #pragma unroll
   for (int k = 0; k < PT_STRIDE; ++k) points[i * PT_STRIDE + k] = pt[k];
   n_seg[i] = ns;
@@ -160,6 +162,17 @@ __global__ void prologue_kernel(ModelArg md, int64_t n_points, const double* __r
 #pragma unroll
     for (int k = 0; k < SC_STRIDE; ++k) scalars[i * SC_STRIDE + k] = sc[k];
   }
+}
+
+// apparatus slots that are the same for every point of a batch are not sent over PCIe: the host
+// passes their values once and this kernel writes them into the slot-major block
+struct ConstSlots { double v[APP_STRIDE]; uint64_t mask; };
+__global__ void fill_slots_kernel(ConstSlots cs, int64_t n_points, double* __restrict__ app, int64_t app_stride) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_points) return;
+#pragma unroll 1
+  for (int k = 0; k < APP_STRIDE; ++k)
+    if ((cs.mask >> k) & 1ull) app[(int64_t)k * app_stride + i] = cs.v[k];
 }
 
 // deterministic shot mean: one warp per point, fixed-order tree
@@ -237,6 +250,22 @@ struct rydcz_ctx {
   // evaluator inputs produced on the device by the prologue kernel
   void* plan[3] = {nullptr, nullptr, nullptr};
   size_t plan_cap[3] = {0, 0, 0};
+  // pipeline lanes of rydcz_simulate_host_cols: chunk c runs on lane c % kLanes
+  struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ring_free = nullptr;              // the H2D copies out of `ring` have completed
+    double* ring = nullptr; size_t ring_cap = 0;  // page-locked staging for the packed columns
+    void* cub_tmp = nullptr; size_t cub_cap = 0;
+  };
+  static constexpr int kLanes = 3;
+  Lane lane[kLanes];
+  int64_t chunk = 65536;                          // points per pipeline chunk
+};
+
+// scratch of one work sort (the default one belongs to the context; every lane has its own)
+struct SortScratch {
+  float* keys; float* keys_sorted; uint32_t* idx; uint32_t* idx_sorted;
+  void** tmp; size_t* tmp_cap;
 };
 
 static std::string g_create_error;
@@ -291,49 +320,62 @@ static int sys_lookup(int dim, const char* name, int what) {
   return -1;
 }
 
+static int order_reserve(rydcz_ctx* ctx, int64_t n) {
+  if ((size_t)n <= ctx->order_cap) return 0;
+  cudaFree(ctx->keys); cudaFree(ctx->keys_sorted); cudaFree(ctx->idx); cudaFree(ctx->idx_sorted);
+  ctx->keys = ctx->keys_sorted = nullptr; ctx->idx = ctx->idx_sorted = nullptr; ctx->order_cap = 0;
+  CK(cudaMalloc(&ctx->keys, n * sizeof(float)));
+  CK(cudaMalloc(&ctx->keys_sorted, n * sizeof(float)));
+  CK(cudaMalloc(&ctx->idx, n * sizeof(uint32_t)));
+  CK(cudaMalloc(&ctx->idx_sorted, n * sizeof(uint32_t)));
+  ctx->order_cap = (size_t)n;
+  return 0;
+}
+
+static SortScratch context_scratch(rydcz_ctx* ctx, int64_t offset = 0) {
+  return SortScratch{ctx->keys + offset, ctx->keys_sorted + offset, ctx->idx + offset, ctx->idx_sorted + offset,
+                     &ctx->cub_tmp, &ctx->cub_cap};
+}
+
 // order points heaviest-first; returns the device permutation (or nullptr when sorting is off)
 template <int D>
-static int make_order(rydcz_ctx* ctx, int64_t n, const double* d_points, const double* d_segs,
-                      const int32_t* d_n_seg, int max_seg, int shots, cudaStream_t st, const uint32_t** order) {
+static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const double* d_points,
+                      const double* d_segs, const int32_t* d_n_seg, int max_seg, int shots, cudaStream_t st,
+                      const uint32_t** order) {
   *order = nullptr;
   if (!ctx->sort || n < 64) return 0;
-  if ((size_t)n > ctx->order_cap) {
-    cudaFree(ctx->keys); cudaFree(ctx->keys_sorted); cudaFree(ctx->idx); cudaFree(ctx->idx_sorted);
-    ctx->keys = ctx->keys_sorted = nullptr; ctx->idx = ctx->idx_sorted = nullptr; ctx->order_cap = 0;
-    CK(cudaMalloc(&ctx->keys, n * sizeof(float)));
-    CK(cudaMalloc(&ctx->keys_sorted, n * sizeof(float)));
-    CK(cudaMalloc(&ctx->idx, n * sizeof(uint32_t)));
-    CK(cudaMalloc(&ctx->idx_sorted, n * sizeof(uint32_t)));
-    ctx->order_cap = (size_t)n;
-  }
   work_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_points, d_segs, d_n_seg, max_seg, shots,
-                                                              ctx->keys, ctx->idx);
+                                                              sc.keys, sc.idx);
   CK(cudaGetLastError());
   ctx->launches++;
   size_t need = 0;
-  CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, ctx->keys, ctx->keys_sorted, ctx->idx,
-                                               ctx->idx_sorted, (int)n, 0, 32, st));
-  if (grow(ctx, &ctx->cub_tmp, &ctx->cub_cap, need)) return 1;
-  CK(cub::DeviceRadixSort::SortPairsDescending(ctx->cub_tmp, need, ctx->keys, ctx->keys_sorted, ctx->idx,
-                                               ctx->idx_sorted, (int)n, 0, 32, st));
-  *order = ctx->idx_sorted;
+  CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, sc.keys, sc.keys_sorted, sc.idx, sc.idx_sorted,
+                                               (int)n, 0, 32, st));
+  if (grow(ctx, sc.tmp, sc.tmp_cap, need)) return 1;
+  CK(cub::DeviceRadixSort::SortPairsDescending(*sc.tmp, need, sc.keys, sc.keys_sorted, sc.idx, sc.idx_sorted,
+                                               (int)n, 0, 32, st));
+  *order = sc.idx_sorted;
   return 0;
 }
 
 template <int D, bool NOISY, bool SHOTS>
 static int launch_eval(rydcz_ctx* ctx, int64_t n_items, int n_shots, uint64_t seed, const uint32_t* order,
                        const double* d_points, const double* d_segs, const int32_t* d_n_seg, int max_seg,
-                       double* d_out, double* d_states, cudaStream_t st) {
+                       double* d_out, double* d_states, cudaStream_t st, int mark = 3,
+                       int64_t point_base = 0) {
+  // mark: bit 0 = record the start event, bit 1 = record the end event (a pipelined call marks the
+  // first chunk's start and the last chunk's end)
   const unsigned grid = (unsigned)((n_items + kBlock - 1) / kBlock);
-  CK(cudaEventRecord(ctx->ev0, st));
-  evaluate_kernel<D, NOISY, SHOTS, false><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, order, d_points,
-                                                                   d_segs, d_n_seg, max_seg, d_out, d_states);
+  if (mark & 1) CK(cudaEventRecord(ctx->ev0, st));
+  evaluate_kernel<D, NOISY, SHOTS, false><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, point_base, order,
+                                                                   d_points, d_segs, d_n_seg, max_seg, d_out,
+                                                                   d_states);
   CK(cudaGetLastError());
-  evaluate_kernel<D, NOISY, SHOTS, true><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, order, d_points,
-                                                                  d_segs, d_n_seg, max_seg, d_out, d_states);
+  evaluate_kernel<D, NOISY, SHOTS, true><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, point_base, order,
+                                                                  d_points, d_segs, d_n_seg, max_seg, d_out,
+                                                                  d_states);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(ctx->ev1, st));
-  ctx->timed = true;
+  if (mark & 2) { CK(cudaEventRecord(ctx->ev1, st)); ctx->timed = true; }
   ctx->launches += 2;
   return 0;
 }
@@ -383,6 +425,13 @@ void rydcz_destroy(rydcz_ctx* ctx) {
   cudaFree(ctx->cub_tmp);
   for (int i = 0; i < 6; ++i) cudaFree(ctx->stage[i]);
   for (int i = 0; i < 3; ++i) cudaFree(ctx->plan[i]);
+  for (int l = 0; l < rydcz_ctx::kLanes; ++l) {
+    rydcz_ctx::Lane& L = ctx->lane[l];
+    if (L.stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
+    if (L.ring_free) cudaEventDestroy(L.ring_free);
+    if (L.ring) cudaFreeHost(L.ring);
+    cudaFree(L.cub_tmp);
+  }
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -406,6 +455,21 @@ static int check_args(rydcz_ctx* ctx, int dim, int64_t n, const void* a, const v
   return 0;
 }
 
+static int evaluate_impl(rydcz_ctx* ctx, const SortScratch& sc, int dim, int noisy, int64_t n_points,
+                         const double* d_points, const double* d_segs, const int32_t* d_n_seg, int max_seg,
+                         double* d_out, double* d_states, cudaStream_t st, int mark) {
+  const uint32_t* order = nullptr;
+  int rc = dim == 3 ? make_order<3>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 0, st, &order)
+                    : make_order<4>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 0, st, &order);
+  if (rc) return rc;
+#define RYDCZ_GO(D, N)                                                                             \
+  return launch_eval<D, N, false>(ctx, n_points, 1, 0, order, d_points, d_segs, d_n_seg, max_seg,   \
+                                  d_out, d_states, st, mark)
+  if (dim == 3) { if (noisy) RYDCZ_GO(3, true); else RYDCZ_GO(3, false); }
+  else { if (noisy) RYDCZ_GO(4, true); else RYDCZ_GO(4, false); }
+#undef RYDCZ_GO
+}
+
 int rydcz_evaluate_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, const double* d_points,
                           const double* d_segs, const int32_t* d_n_seg, int max_seg, double* d_out,
                           double* d_states, void* stream) {
@@ -413,16 +477,33 @@ int rydcz_evaluate_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, 
   if (n_points == 0) return 0;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  if (order_reserve(ctx, n_points)) return 1;
+  return evaluate_impl(ctx, context_scratch(ctx), dim, noisy, n_points, d_points, d_segs, d_n_seg, max_seg,
+                       d_out, d_states, st, 3);
+}
+
+// d_shots [n_points][n_shots][16] must be given (scratch or caller's)
+static int shots_impl(rydcz_ctx* ctx, const SortScratch& sc, int dim, int noisy, int64_t n_points, int n_shots,
+                      uint64_t seed, int64_t point_base, const double* d_points, const double* d_segs,
+                      const int32_t* d_n_seg, int max_seg, double* d_out_mean, double* d_shots, cudaStream_t st,
+                      int mark) {
+  const int64_t n_items = n_points * n_shots;
   const uint32_t* order = nullptr;
-  int rc = dim == 3 ? make_order<3>(ctx, n_points, d_points, d_segs, d_n_seg, max_seg, 0, st, &order)
-                    : make_order<4>(ctx, n_points, d_points, d_segs, d_n_seg, max_seg, 0, st, &order);
+  int rc = dim == 3 ? make_order<3>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 1, st, &order)
+                    : make_order<4>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 1, st, &order);
   if (rc) return rc;
-#define RYDCZ_GO(D, N)                                                                             \
-  return launch_eval<D, N, false>(ctx, n_points, 1, 0, order, d_points, d_segs, d_n_seg, max_seg,   \
-                                  d_out, d_states, st)
+#define RYDCZ_GO(D, N)                                                                               \
+  rc = launch_eval<D, N, true>(ctx, n_items, n_shots, seed, order, d_points, d_segs, d_n_seg, max_seg, \
+                               d_shots, nullptr, st, mark, point_base)
   if (dim == 3) { if (noisy) RYDCZ_GO(3, true); else RYDCZ_GO(3, false); }
   else { if (noisy) RYDCZ_GO(4, true); else RYDCZ_GO(4, false); }
 #undef RYDCZ_GO
+  if (rc) return rc;
+  const int64_t threads = n_points * 32;
+  shot_mean_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(n_points, n_shots, d_shots, d_out_mean);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return 0;
 }
 
 int rydcz_evaluate_shots_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, int n_shots,
@@ -435,28 +516,14 @@ int rydcz_evaluate_shots_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_po
   if (n_points == 0) return 0;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  const int64_t n_items = n_points * n_shots;
   double* shots = d_out_shots;
   if (!shots) {
-    if (grow(ctx, &ctx->stage[5], &ctx->stage_cap[5], n_items * OUT_STRIDE * sizeof(double))) return 1;
+    if (grow(ctx, &ctx->stage[5], &ctx->stage_cap[5], n_points * n_shots * OUT_STRIDE * sizeof(double))) return 1;
     shots = (double*)ctx->stage[5];
   }
-  const uint32_t* order = nullptr;
-  int rc = dim == 3 ? make_order<3>(ctx, n_points, d_points, d_segs, d_n_seg, max_seg, 1, st, &order)
-                    : make_order<4>(ctx, n_points, d_points, d_segs, d_n_seg, max_seg, 1, st, &order);
-  if (rc) return rc;
-#define RYDCZ_GO(D, N)                                                                               \
-  rc = launch_eval<D, N, true>(ctx, n_items, n_shots, seed, order, d_points, d_segs, d_n_seg, max_seg, \
-                               shots, nullptr, st)
-  if (dim == 3) { if (noisy) RYDCZ_GO(3, true); else RYDCZ_GO(3, false); }
-  else { if (noisy) RYDCZ_GO(4, true); else RYDCZ_GO(4, false); }
-#undef RYDCZ_GO
-  if (rc) return rc;
-  const int64_t threads = n_points * 32;
-  shot_mean_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(n_points, n_shots, shots, d_out_mean);
-  CK(cudaGetLastError());
-  ctx->launches++;
-  return 0;
+  if (order_reserve(ctx, n_points)) return 1;
+  return shots_impl(ctx, context_scratch(ctx), dim, noisy, n_points, n_shots, seed, 0, d_points, d_segs, d_n_seg,
+                    max_seg, d_out_mean, shots, st, 3);
 }
 
 static int stage_in(rydcz_ctx* ctx, int slot, const void* h, size_t bytes) {
@@ -537,6 +604,18 @@ static int check_model(rydcz_ctx* ctx, const double* m) {
   return 0;
 }
 
+static int prologue_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_points, const double* d_app,
+                         int64_t app_stride, double* d_points, double* d_segs, int32_t* d_n_seg,
+                         double* d_scalars, cudaStream_t st) {
+  ModelArg md;
+  memcpy(md.v, h_model, sizeof(md.v));
+  prologue_kernel<<<(unsigned)((n_points + 127) / 128), 128, 0, st>>>(md, n_points, d_app, app_stride, d_points,
+                                                                       d_segs, d_n_seg, d_scalars);
+  CK(cudaGetLastError());
+  ctx->launches++;
+  return 0;
+}
+
 int rydcz_prologue_device(rydcz_ctx* ctx, const double* h_model, int64_t n_points, const double* d_app,
                           double* d_points, double* d_segs, int32_t* d_n_seg, double* d_scalars, void* stream) {
   if (int rc = check_model(ctx, h_model)) return rc;
@@ -545,13 +624,7 @@ int rydcz_prologue_device(rydcz_ctx* ctx, const double* h_model, int64_t n_point
   if (!d_app || !d_points || !d_segs || !d_n_seg) return fail(ctx, "null buffer");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  ModelArg md;
-  memcpy(md.v, h_model, sizeof(md.v));
-  prologue_kernel<<<(unsigned)((n_points + 127) / 128), 128, 0, st>>>(md, n_points, d_app, d_points, d_segs,
-                                                                       d_n_seg, d_scalars);
-  CK(cudaGetLastError());
-  ctx->launches++;
-  return 0;
+  return prologue_impl(ctx, h_model, n_points, d_app, n_points, d_points, d_segs, d_n_seg, d_scalars, st);
 }
 
 int rydcz_simulate_device(rydcz_ctx* ctx, const double* h_model, int64_t n_points, const double* d_app,
@@ -600,6 +673,125 @@ int rydcz_simulate_host(rydcz_ctx* ctx, const double* h_model, int64_t n_points,
     CK(cudaMemcpyAsync(h_scalars, ctx->stage[1], n * SC_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   if (h_states) CK(cudaMemcpyAsync(h_states, ctx->stage[4], n * sb, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int rydcz_set_chunk(rydcz_ctx* ctx, int64_t points_per_chunk) {
+  if (!ctx) return 2;
+  if (points_per_chunk < 1024) return fail(ctx, "chunk must be >= 1024 points");
+  ctx->chunk = points_per_chunk;
+  return 0;
+}
+
+// Column form of rydcz_simulate_host, pipelined.  Only the apparatus slots that vary over the batch
+// cross PCIe; the batch is cut into chunks and chunk c (pack on the host -> H2D -> prologue ->
+// work sort -> evaluate -> D2H) runs on lane c % kLanes, so the copies and the host-side packing
+// of one chunk overlap the kernels of its neighbours.
+int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_points,
+                             const double* const* h_cols, const int64_t* col_stride, const double* h_const,
+                             int n_shots, uint64_t seed, double* h_out, double* h_scalars, double* h_states) {
+  if (int rc = check_model(ctx, h_model)) return rc;
+  if (n_points < 0 || n_points > 0x7fffffffLL) return fail(ctx, "n_points out of range");
+  if (n_points == 0) return 0;
+  if (!h_cols || !h_const || !h_out) return fail(ctx, "null buffer");
+  if (n_shots < 0) return fail(ctx, "n_shots must be >= 0");
+  if (h_states && n_shots > 0) return fail(ctx, "states are not available with shots");
+  if (n_points * (int64_t)(n_shots > 0 ? n_shots : 1) > 0x7fffffffLL) return fail(ctx, "n_points * n_shots too large");
+  CK(cudaSetDevice(ctx->device));
+  const int dim = (int)h_model[MD_DIM], S = (int)h_model[MD_NSEG], noisy = h_model[MD_INCLUDE_NOISE] != 0;
+  const size_t n = (size_t)n_points;
+  const size_t sb = (size_t)rydcz_state_stride(dim) * sizeof(double);
+  // varying / constant slots
+  int var[APP_STRIDE], n_var = 0;
+  ConstSlots cs;
+  cs.mask = 0;
+  for (int k = 0; k < APP_STRIDE; ++k) {
+    cs.v[k] = h_const[k];
+    if (h_cols[k]) var[n_var++] = k; else cs.mask |= 1ull << k;
+  }
+  // chunking: a chunk must still fill the GPU (two 128-thread CTAs per SM ~ 38k threads)
+  const int64_t per_item = n_shots > 0 ? n_shots : 1;
+  int64_t chunk = ctx->chunk / per_item;
+  if (chunk < 1024) chunk = 1024;
+  if (n_points < chunk + chunk / 2) chunk = n_points;
+  const int64_t n_chunks = (n_points + chunk - 1) / chunk;
+  // device buffers for the whole batch
+  if (grow(ctx, &ctx->stage[0], &ctx->stage_cap[0], n * APP_STRIDE * sizeof(double))) return 1;
+  if (grow(ctx, &ctx->stage[3], &ctx->stage_cap[3], n * OUT_STRIDE * sizeof(double))) return 1;
+  if (h_scalars && grow(ctx, &ctx->stage[1], &ctx->stage_cap[1], n * SC_STRIDE * sizeof(double))) return 1;
+  if (h_states && grow(ctx, &ctx->stage[4], &ctx->stage_cap[4], n * sb)) return 1;
+  if (n_shots > 0 && grow(ctx, &ctx->stage[5], &ctx->stage_cap[5], n * n_shots * OUT_STRIDE * sizeof(double))) return 1;
+  if (grow(ctx, &ctx->plan[0], &ctx->plan_cap[0], n * PT_STRIDE * sizeof(double))) return 1;
+  if (grow(ctx, &ctx->plan[1], &ctx->plan_cap[1], n * S * SG_STRIDE * sizeof(double))) return 1;
+  if (grow(ctx, &ctx->plan[2], &ctx->plan_cap[2], n * sizeof(int32_t))) return 1;
+  if (order_reserve(ctx, n_points)) return 1;
+  double* d_app = (double*)ctx->stage[0];
+  double* d_out = (double*)ctx->stage[3];
+  double* d_sc = h_scalars ? (double*)ctx->stage[1] : nullptr;
+  double* d_st = h_states ? (double*)ctx->stage[4] : nullptr;
+  double* d_shots = n_shots > 0 ? (double*)ctx->stage[5] : nullptr;
+  double* d_pts = (double*)ctx->plan[0];
+  double* d_segs = (double*)ctx->plan[1];
+  int32_t* d_ns = (int32_t*)ctx->plan[2];
+  const int n_lanes = n_chunks < rydcz_ctx::kLanes ? (int)n_chunks : rydcz_ctx::kLanes;
+  for (int l = 0; l < n_lanes; ++l) {
+    rydcz_ctx::Lane& L = ctx->lane[l];
+    if (!L.stream) {
+      CK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+      CK(cudaEventCreateWithFlags(&L.ring_free, cudaEventDisableTiming));
+    }
+    const size_t need = (size_t)(n_var ? n_var : 1) * chunk * sizeof(double);
+    if (need > L.ring_cap) {
+      if (L.ring) CK(cudaFreeHost(L.ring));
+      L.ring = nullptr; L.ring_cap = 0;
+      CK(cudaHostAlloc((void**)&L.ring, need, cudaHostAllocDefault));
+      L.ring_cap = need;
+    }
+  }
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    rydcz_ctx::Lane& L = ctx->lane[c % rydcz_ctx::kLanes];
+    cudaStream_t st = L.stream;
+    const int64_t i0 = c * chunk;
+    const int64_t nc = (i0 + chunk <= n_points) ? chunk : n_points - i0;
+    if (c >= rydcz_ctx::kLanes) CK(cudaEventSynchronize(L.ring_free));   // the lane's ring is free again
+    for (int j = 0; j < n_var; ++j) {
+      const int64_t cstr = col_stride ? col_stride[var[j]] : 1;
+      const double* src = h_cols[var[j]] + i0 * cstr;
+      double* dst = L.ring + (size_t)j * chunk;
+      if (cstr == 1) memcpy(dst, src, nc * sizeof(double));
+      else for (int64_t i = 0; i < nc; ++i) dst[i] = src[i * cstr];
+      CK(cudaMemcpyAsync(d_app + (int64_t)var[j] * n_points + i0, dst, nc * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaEventRecord(L.ring_free, st));
+    if (cs.mask) {
+      fill_slots_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(cs, nc, d_app + i0, n_points);
+      CK(cudaGetLastError());
+      ctx->launches++;
+    }
+    double* c_sc = d_sc ? d_sc + i0 * SC_STRIDE : nullptr;
+    if (prologue_impl(ctx, h_model, nc, d_app + i0, n_points, d_pts + i0 * PT_STRIDE,
+                      d_segs + i0 * (int64_t)S * SG_STRIDE, d_ns + i0, c_sc, st)) return 1;
+    SortScratch sc = context_scratch(ctx, i0);
+    sc.tmp = &L.cub_tmp; sc.tmp_cap = &L.cub_cap;
+    const int mark = (c == 0 ? 1 : 0) | (c == n_chunks - 1 ? 2 : 0);
+    int rc;
+    if (n_shots > 0)
+      rc = shots_impl(ctx, sc, dim, noisy, nc, n_shots, seed, i0, d_pts + i0 * PT_STRIDE,
+                      d_segs + i0 * (int64_t)S * SG_STRIDE, d_ns + i0, S, d_out + i0 * OUT_STRIDE,
+                      d_shots + i0 * n_shots * OUT_STRIDE, st, mark);
+    else
+      rc = evaluate_impl(ctx, sc, dim, noisy, nc, d_pts + i0 * PT_STRIDE, d_segs + i0 * (int64_t)S * SG_STRIDE,
+                         d_ns + i0, S, d_out + i0 * OUT_STRIDE, d_st ? d_st + i0 * (sb / sizeof(double)) : nullptr,
+                         st, mark);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_out + i0 * OUT_STRIDE, d_out + i0 * OUT_STRIDE, nc * OUT_STRIDE * sizeof(double),
+                       cudaMemcpyDeviceToHost, st));
+    if (h_scalars)
+      CK(cudaMemcpyAsync(h_scalars + i0 * SC_STRIDE, c_sc, nc * SC_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (h_states)
+      CK(cudaMemcpyAsync((char*)h_states + i0 * sb, (char*)d_st + i0 * sb, nc * sb, cudaMemcpyDeviceToHost, st));
+  }
+  for (int l = 0; l < n_lanes; ++l) CK(cudaStreamSynchronize(ctx->lane[l].stream));
   return 0;
 }
 

@@ -179,6 +179,42 @@ class Evaluator:
             "rydcz_simulate_host")
         return out, sc, st
 
+    def simulate_host_cols(self, model, cols, B: int, n_shots: int = 0, seed: int = 1234,
+                           want_scalars: bool = True, want_states: bool = False):
+        """Column form of ``simulate_host`` (rydcz_simulate_host_cols): ``cols`` is the list of 40
+        apparatus slots from ``device_prologue.apparatus_columns`` -- floats for batch-wide constants,
+        1-D float64 arrays (any stride) for slots that vary.  Only the varying slots are copied to
+        the GPU, and the batch is pipelined in chunks over three streams.  Results land in
+        page-locked buffers owned by the evaluator (valid until the next call)."""
+        model, m_ptr = _host(model, np.float64)
+        assert model.shape == (_lib.MODEL_STRIDE,) and len(cols) == _lib.APP_STRIDE
+        ptrs = (C.c_void_p * _lib.APP_STRIDE)()
+        strides = (C.c_int64 * _lib.APP_STRIDE)()
+        consts = (C.c_double * _lib.APP_STRIDE)()
+        keep = []
+        for k, v in enumerate(cols):
+            if isinstance(v, np.ndarray):
+                if v.dtype != np.float64 or v.ndim != 1 or v.strides[0] % 8 or v.strides[0] <= 0 \
+                        or not v.flags.aligned:
+                    v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1)
+                assert v.shape == (B,)
+                keep.append(v)
+                ptrs[k], strides[k], consts[k] = v.ctypes.data, v.strides[0] // 8, np.nan
+            else:
+                ptrs[k], strides[k], consts[k] = None, 1, float(v)
+        out = self.pinned("sim_out", (B, _lib.OUT_STRIDE))
+        sc = self.pinned("sim_sc", (B, _lib.SCALAR_STRIDE)) if want_scalars else None
+        st = self.pinned("sim_st", (B, self.lib.rydcz_state_stride(int(model[0])))) if want_states else None
+        self._check(self.lib.rydcz_simulate_host_cols(
+            self.ctx, m_ptr, B, ptrs, strides, consts, int(n_shots), int(seed), out.ctypes.data,
+            sc.ctypes.data if want_scalars else None, st.ctypes.data if want_states else None),
+            "rydcz_simulate_host_cols")
+        del keep
+        return out, sc, st
+
+    def set_chunk(self, points_per_chunk: int):
+        self._check(self.lib.rydcz_set_chunk(self.ctx, int(points_per_chunk)), "rydcz_set_chunk")
+
     def simulate_device(self, model, app, n_shots: int = 0, seed: int = 1234, out=None, scalars=None,
                         stream=None):
         """Same with the apparatus rows already in HBM (CUDA torch tensor); asynchronous."""

@@ -7,7 +7,7 @@ The per-point physics then runs on the GPU (``rydcz_simulate_host`` / ``_device`
 """
 from __future__ import annotations
 
-from typing import Dict
+from typing import Dict, List
 
 import numpy as np
 
@@ -69,21 +69,27 @@ def model_constants(protocol: str, *, config: AtomicConfiguration = None, specie
     return m
 
 
-def pack_apparatus(protocol: str, B: int, *, laser_1_power, laser_1_waist, laser_2_power, laser_2_waist, Delta_e,
-                   laser_1_linewidth_hz=100.0, laser_2_linewidth_hz=100.0, polarization_purity_1=0.99,
-                   polarization_purity_2=0.99, tweezer_power=30e-3, tweezer_waist=1.0e-6,
-                   tweezer_wavelength_nm=None, temperature=2e-6, B_field=1e-4, NA=0.5, spacing_factor=2.8,
-                   background_loss_rate_hz=None, intensity_noise_frac=0.01, delta_over_omega=None, omega_tau=None,
-                   switching_times=None, phases=None, A=None, omega_mod_ratio=None, phi_offset=None,
-                   out: np.ndarray = None) -> np.ndarray:
-    """[40, B] apparatus block (slot-major: one contiguous column per slot); scalars broadcast,
-    None -> NaN (= 'use the reference default')."""
-    app = out if out is not None else np.empty((APP_STRIDE, B))
-    assert app.shape == (APP_STRIDE, B)
-    nan = np.nan
+def apparatus_columns(protocol: str, B: int, *, laser_1_power, laser_1_waist, laser_2_power, laser_2_waist, Delta_e,
+                      laser_1_linewidth_hz=100.0, laser_2_linewidth_hz=100.0, polarization_purity_1=0.99,
+                      polarization_purity_2=0.99, tweezer_power=30e-3, tweezer_waist=1.0e-6,
+                      tweezer_wavelength_nm=None, temperature=2e-6, B_field=1e-4, NA=0.5, spacing_factor=2.8,
+                      background_loss_rate_hz=None, intensity_noise_frac=0.01, delta_over_omega=None,
+                      omega_tau=None, switching_times=None, phases=None, A=None, omega_mod_ratio=None,
+                      phi_offset=None) -> List:
+    """The 40 apparatus slots as a list: a float (same for every point; None -> NaN = 'use the
+    reference default') or a 1-D float64 array view of length B (possibly strided: column k of a
+    row-major [B, m] array is passed as is).  Nothing is copied for float64 inputs."""
+    cols: List = [0.0] * APP_STRIDE
 
     def put(slot, v):
-        app[slot] = nan if v is None else v
+        if v is None:
+            cols[slot] = np.nan
+        elif np.ndim(v) == 0:
+            cols[slot] = float(v)
+        else:
+            v = np.asarray(v, dtype=np.float64)
+            assert v.shape == (B,), f"apparatus slot {slot}: expected a scalar or {B} values, got shape {v.shape}"
+            cols[slot] = v
 
     for slot, v in enumerate((laser_1_power, laser_1_waist, laser_2_power, laser_2_waist, Delta_e,
                               laser_1_linewidth_hz, laser_2_linewidth_hz)):
@@ -104,14 +110,26 @@ def pack_apparatus(protocol: str, B: int, *, laser_1_power, laser_1_waist, laser
         from .protocols import JP_DEFAULT
         sw = JP_DEFAULT.switching_times if switching_times is None or np.size(switching_times) == 0 else switching_times
         ph = JP_DEFAULT.phases if phases is None or np.size(phases) == 0 else phases
-        sw, ph = np.asarray(sw, dtype=float), np.asarray(ph, dtype=float)
+        sw, ph = np.asarray(sw, dtype=np.float64), np.asarray(ph, dtype=np.float64)
         S = ph.shape[-1]
         assert S == sw.shape[-1] + 1, (f"Need len(phases) = len(switching_times) + 1, got {S} phases and "
                                        f"{sw.shape[-1]} switching times")
         assert 2 * S <= APP_STRIDE - APP_PROTO, "too many bang-bang segments for the device prologue"
         put(P, omega_tau)
-        app[P + 1:P + S] = sw.T if sw.ndim == 2 else sw[:, None]
-        app[P + S:P + 2 * S] = ph.T if ph.ndim == 2 else ph[:, None]
+        for k in range(S - 1):
+            put(P + 1 + k, sw[:, k] if sw.ndim == 2 else sw[k])
+        for k in range(S):
+            put(P + S + k, ph[:, k] if ph.ndim == 2 else ph[k])
+    return cols
+
+
+def pack_apparatus(protocol: str, B: int, *, out: np.ndarray = None, **kwargs) -> np.ndarray:
+    """[40, B] apparatus block (slot-major: one contiguous column per slot) from the same keywords as
+    ``apparatus_columns``; scalars broadcast."""
+    app = out if out is not None else np.empty((APP_STRIDE, B))
+    assert app.shape == (APP_STRIDE, B)
+    for slot, v in enumerate(apparatus_columns(protocol, B, **kwargs)):
+        app[slot] = v
     return app
 
 

@@ -550,11 +550,11 @@ def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, se
             ph = ak.get("phases")
             nseg = 5 if ph is None or np.size(ph) == 0 else np.shape(ph)[-1]
         model = dpro.model_constants(protocol, n_segments=nseg, **mk)
-        # apparatus rows are written straight into a page-locked staging buffer
-        app = dpro.pack_apparatus(protocol, B, out=ev.pinned("app", (dpro.APP_STRIDE, B))
-                                  if hasattr(ev, "pinned") else None, **ak)
-        out, sc, states = ev.simulate_host(model, app, n_shots, seed, want_scalars=True,
-                                           want_states=return_states and n_shots == 0)
+        # apparatus slots go to the C ABI as columns (views of the caller's arrays, or one float for a
+        # slot that is the same for every point): nothing is packed or broadcast in Python
+        cols = dpro.apparatus_columns(protocol, B, **ak)
+        out, sc, states = ev.simulate_host_cols(model, cols, B, n_shots, seed, want_scalars=True,
+                                                want_states=return_states and n_shots == 0)
         if copy:                                       # detach from the reusable staging buffers
             out, sc = np.array(out), np.array(sc)
             states = None if states is None else np.array(states)

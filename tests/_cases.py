@@ -199,3 +199,13 @@ def _hostsim_simulate_host(self, model, app, n_shots=0, seed=1234, want_scalars=
 
 
 HostsimEvaluator.simulate_host = _hostsim_simulate_host
+
+
+def _hostsim_simulate_host_cols(self, model, cols, B, n_shots=0, seed=1234, want_scalars=True, want_states=False):
+    app = np.empty((40, B))
+    for k, v in enumerate(cols):
+        app[k] = v
+    return _hostsim_simulate_host(self, model, app, n_shots, seed, want_scalars, want_states)
+
+
+HostsimEvaluator.simulate_host_cols = _hostsim_simulate_host_cols
