@@ -80,7 +80,8 @@ int rydcz_version(void);
 int rydcz_point_stride(void);
 int rydcz_seg_stride(void);
 int rydcz_out_stride(void);
-int rydcz_state_stride(int dim);                        /* 51 (dim 3), 64 (dim 4), -1 otherwise */
+int rydcz_point_stride_dim(int dim);                    /* 12 (dim 3, 4), 20 (dim 5), -1 otherwise */
+int rydcz_state_stride(int dim);                        /* 51 (dim 3), 64 (dim 4), 129 (dim 5), -1 otherwise */
 int rydcz_state_offset(int dim, const char* system);    /* "rho11","rho01","rho10","coh11","coh01","coh10" */
 int rydcz_system_size(int dim, const char* system);     /* real variables of that reduced system */
 int rydcz_system_nnz(int dim, const char* system);      /* FMAs per sparse matvec of that system */

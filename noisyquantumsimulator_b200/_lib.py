@@ -21,6 +21,7 @@ _SIGNATURES = {
     "rydcz_point_stride": (C.c_int, []),
     "rydcz_seg_stride": (C.c_int, []),
     "rydcz_out_stride": (C.c_int, []),
+    "rydcz_point_stride_dim": (C.c_int, [C.c_int]),
     "rydcz_state_stride": (C.c_int, [C.c_int]),
     "rydcz_state_offset": (C.c_int, [C.c_int, C.c_char_p]),
     "rydcz_system_size": (C.c_int, [C.c_int, C.c_char_p]),

@@ -10,7 +10,7 @@ Each system becomes a struct with compile-time sizes and three inline functions:
                      index a literal so x, y, c stay in registers.
 
 Run ``python -m noisyquantumsimulator_b200.codegen.emit`` to regenerate
-``csrc/rydcz_systems_d3.inc`` / ``_d4.inc`` (committed; the build does not need Python).
+``csrc/rydcz_systems_d3.inc`` / ``_d4.inc`` / ``_d5.inc`` (committed; the build does not need Python).
 """
 from __future__ import annotations
 
@@ -20,6 +20,9 @@ from typing import Dict, List, Tuple
 import numpy as np
 
 from . import model
+
+
+BIG_SYSTEM_N = 40    # more real variables than this: coefficients and start vector live in shared memory
 
 
 def _fmt(v: float) -> str:
@@ -96,6 +99,8 @@ def emit_system(sysm: model.RealSystem, struct_name: str) -> str:
       f"IDX_DELTA1 = {pidx('delta1')};")
     A(f"  static constexpr int IDX_G_R1 = {pidx('g_r1')}, IDX_G_R0 = {pidx('g_r0')}, IDX_G_PHI = {pidx('g_phi')}, "
       f"IDX_G_SC = {pidx('g_sc')}, IDX_G_MJ = {pidx('g_mj')};")
+    A(f"  static constexpr int DIM = {sysm.d}, IDX_OM1 = {pidx('om1')}, IDX_DET_E = {pidx('det_e')}, "
+      f"IDX_G_E1 = {pidx('g_e1')}, IDX_G_E0 = {pidx('g_e0')}, IDX_G_RL = {pidx('g_rl')};")
     if getattr(sysm, "expand", None) is not None:
         A(f"  static constexpr int FULL_N = {sysm.full_n};")
         A("  // state of the general (unfolded) system from the exchange-folded one")
@@ -110,8 +115,15 @@ def emit_system(sysm: model.RealSystem, struct_name: str) -> str:
             cidx = int(nz[0])
             A(f"    xg[{r}] = {'' if E[r, cidx] > 0 else '-'}xs[{cidx}];")
         A("  }")
+    # Big systems keep their coefficients (and the segment's start vector) in per-thread shared-memory
+    # columns instead of registers: coefs/bounds take any indexable container, and apply_cm walks the
+    # nonzeros coefficient by coefficient so that each c[q] is loaded once per matvec.
+    big = n > BIG_SYSTEM_N
     # coefs
-    A("  RYDCZ_HD static void coefs(const double* __restrict__ p, double* __restrict__ c) {")
+    if big:
+        A("  template <class CV> RYDCZ_HD static void coefs(const double* __restrict__ p, CV c) {")
+    else:
+        A("  RYDCZ_HD static void coefs(const double* __restrict__ p, double* __restrict__ c) {")
     for q, v in enumerate(forms):
         terms = []
         for k in np.nonzero(v)[0]:
@@ -130,7 +142,10 @@ def emit_system(sysm: model.RealSystem, struct_name: str) -> str:
     A("  // rho systems: returns radius = max_i(|G_ii| + sum_{j!=i}|G_ij|), lo = hi = 0.")
     A("  // coh systems: the pair frequency E_i = G[re_i][im_i]; returns the interval [lo, hi] that")
     A("  // contains every E_i -/+ (other off-diagonals of the row) and damp = max |G_ii|.")
-    A("  RYDCZ_HD static void bounds(const double* __restrict__ c, double& lo, double& hi, double& damp) {")
+    if big:
+        A("  template <class CV> RYDCZ_HD static void bounds(const CV c, double& lo, double& hi, double& damp) {")
+    else:
+        A("  RYDCZ_HD static void bounds(const double* __restrict__ c, double& lo, double& hi, double& damp) {")
     rows: Dict[int, List[Tuple[int, int, int]]] = {}
     for (i, j, q, s) in entries:
         rows.setdefault(i, []).append((j, q, s))
@@ -172,6 +187,18 @@ def emit_system(sysm: model.RealSystem, struct_name: str) -> str:
     for (i, j, q, s) in stmts:
         A(f"    y[{i}] {'+=' if s > 0 else '-='} c[{q}] * x[{j}];")
     A("  }")
+    if big:
+        A("  // coefficient-major: c lives in a shared-memory column, each c[q] is read once")
+        A("  template <class CV> RYDCZ_HD static void apply_cm(const CV c, const double* __restrict__ x, double* __restrict__ y) {")
+        A("    double cq;")
+        by_q: Dict[int, List[Tuple[int, int, int]]] = {}
+        for (i, j, q, s) in stmts:
+            by_q.setdefault(q, []).append((i, j, s))
+        for q in sorted(by_q):
+            A(f"    cq = coef_load(c, {q});")
+            for (i, j, s) in by_q[q]:
+                A(f"    y[{i}] {'+=' if s > 0 else '-='} cq * x[{j}];")
+        A("  }")
     A("};")
     A("")
     return "\n".join(L)
@@ -181,7 +208,7 @@ def emit_dim(d: int) -> str:
     systems = model.standard_systems(d)
     out = [f"// GENERATED by noisyquantumsimulator_b200/codegen/emit.py -- do not edit.",
            f"// Two-atom {d}-level Rydberg model: reduced real Lindblad systems.",
-           f"// Parameters p[]: {', '.join(model.PARAMS3 if d == 3 else model.PARAMS4)} (, shift for coh systems)",
+           f"// Parameters p[]: {', '.join(model.params_of(d))} (, shift for coh systems)",
            ""]
     for key, sysm in systems.items():
         out.append(emit_system(sysm, f"Sys_{key}_d{d}"))
@@ -209,17 +236,28 @@ def emit_dim(d: int) -> str:
     # diagonal (population) variables of rho11 by sector, for loss / Rydberg-residual readouts
     rho11 = systems["rho11"]
     diag = [(k, i) for k, (i, j, part) in enumerate(rho11.var_info) if part == "diag"]
-    ryd = {2} if d == 3 else {2, 3}
+    ryd = {3: {2}, 4: {2, 3}, 5: {model.LEVEL_R5}}[d]
 
     def cls(i):
         a, b = i // d, i % d
         return (a in ryd or b in ryd, a == 0 or b == 0)
 
-    loss_terms = " + ".join(f"x[{k}]" for k, i in diag if cls(i)[1])
     ryd_terms = " + ".join(f"x[{k}]" for k, i in diag if cls(i)[0])
-    out.append(f"// |11> input: probability that at least one atom sits in |0> / in a Rydberg level")
-    out.append(f"RYDCZ_HD double rho11_loss_d{d}(const double* __restrict__ x) {{ return {loss_terms}; }}")
+    if d == 5:
+        # only the block in which no atom has been lost is evolved: loss = 1 - its trace
+        out.append("// |11> input: probability that at least one atom has left {1, e, r} (to |0> or |l>) / sits in |r>")
+        out.append(f"RYDCZ_HD double rho11_loss_d{d}(const double* __restrict__ x) {{ return 1.0 - ("
+                   + " + ".join(f"x[{k}]" for k, i in diag) + "); }")
+    else:
+        loss_terms = " + ".join(f"x[{k}]" for k, i in diag if cls(i)[1])
+        out.append(f"// |11> input: probability that at least one atom sits in |0> / in a Rydberg level")
+        out.append(f"RYDCZ_HD double rho11_loss_d{d}(const double* __restrict__ x) {{ return {loss_terms}; }}")
     out.append(f"RYDCZ_HD double rho11_ryd_d{d}(const double* __restrict__ x) {{ return {ryd_terms}; }}")
+    if d == 5:
+        coh11 = systems["coh11"]
+        terms = [f"x[{k}] * x[{k}]" for k, (i, j, part) in enumerate(coh11.var_info) if cls(i)[0]]
+        out.append("// noiseless |11> input (x = the ket, coh11 layout): probability that an atom sits in |r>")
+        out.append(f"RYDCZ_HD double coh11_ryd_d{d}(const double* __restrict__ x) {{ return {' + '.join(terms)}; }}")
     out.append("")
     return "\n".join(out)
 
@@ -227,7 +265,7 @@ def emit_dim(d: int) -> str:
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
     csrc = os.path.join(os.path.dirname(here), "csrc")
-    for d in (3, 4):
+    for d in (3, 4, 5):
         path = os.path.join(csrc, f"rydcz_systems_d{d}.inc")
         with open(path, "w") as f:
             f.write(emit_dim(d))

@@ -18,6 +18,7 @@ Basis index of the two-atom space: d*a + b; vec(X) is row-major.
 """
 from __future__ import annotations
 
+import functools
 from dataclasses import dataclass, field
 from typing import Dict, List, Sequence, Tuple
 
@@ -25,6 +26,17 @@ import numpy as np
 
 PARAMS3 = ("om_re", "om_im", "det_a", "det_b", "V", "delta1", "g_r1", "g_r0", "g_phi", "g_sc")
 PARAMS4 = PARAMS3 + ("g_mj",)
+# d = 5: the intermediate state of the two-photon excitation is kept (levels 0, 1, e, r, l; DESIGN.md
+# section 2.6).  om1 = first-leg Rabi frequency (real), om_re/om_im = second leg (carries the pulse phase),
+# det_e = intermediate detuning, det_a/det_b = two-photon detuning per atom, g_e1/g_e0 = decay of |e>
+# to |1> / |0>, g_rl = loss channels of |r> that leave the computational manifold (-> |l>).
+PARAMS5 = ("om_re", "om_im", "det_a", "det_b", "V", "delta1", "g_r1", "g_r0", "g_phi", "om1", "det_e", "g_e1",
+           "g_e0", "g_rl")
+LEVEL_E, LEVEL_R5, LEVEL_L = 2, 3, 4
+
+
+def params_of(d: int) -> Tuple[str, ...]:
+    return {3: PARAMS3, 4: PARAMS4, 5: PARAMS5}[d]
 
 
 def _op(d, i, j):
@@ -36,6 +48,8 @@ def _op(d, i, j):
 def _hamiltonian_terms(d: int) -> Dict[str, np.ndarray]:
     """H = sum_k p_k H_k for the coherent parameters."""
     I = np.eye(d, dtype=complex)
+    if d == 5:
+        return _hamiltonian_terms_5()
     ryd = [2] if d == 3 else [2, 3]
     two = np.kron
     up = _op(d, 2, 1)  # |r(+)><1|: the default sigma+ coupling reaches only r+ for d=4
@@ -54,9 +68,42 @@ def _hamiltonian_terms(d: int) -> Dict[str, np.ndarray]:
     }
 
 
+def _hamiltonian_terms_5() -> Dict[str, np.ndarray]:
+    """Ladder 1 -(om1)- e -(om2)- r per atom:
+    H = sum_atoms [ om1/2 (|e><1| + h.c.) + (om2/2 |r><e| + h.c.) - det_e |e><e| - det |r><r| + delta1 |1><1| ]
+        + V |rr><rr|.  Eliminating |e> for |det_e| >> om1, |om2| gives the 3-level model with
+    Omega = om1 om2 / (2 det_e) (the reference's effective Rabi frequency, RG/laser_physics.py:265-359)
+    plus light shifts om1^2/(4 det_e) on |1> and |om2|^2/(4 det_e) on |r>."""
+    d = 5
+    I = np.eye(d, dtype=complex)
+    two = np.kron
+    e, r = LEVEL_E, LEVEL_R5
+    up1 = _op(d, e, 1)
+    up2 = _op(d, r, e)
+    h1 = 0.5 * (up1 + up1.conj().T)
+    h_re = 0.5 * (up2 + up2.conj().T)
+    h_im = 0.5 * (1j * up2 - 1j * up2.conj().T)
+    Pe, Pr, P1 = _op(d, e, e), _op(d, r, r), _op(d, 1, 1)
+    return {
+        "om1": two(h1, I) + two(I, h1),
+        "om_re": two(h_re, I) + two(I, h_re),
+        "om_im": two(h_im, I) + two(I, h_im),
+        "det_e": -(two(Pe, I) + two(I, Pe)),
+        "det_a": -two(Pr, I),
+        "det_b": -two(I, Pr),
+        "V": two(Pr, Pr),
+        "delta1": two(P1, I) + two(I, P1),
+    }
+
+
 def _jump_terms(d: int) -> Dict[str, List[np.ndarray]]:
     """Unit-rate jump operators grouped by the rate that multiplies them."""
     I = np.eye(d, dtype=complex)
+    if d == 5:
+        e, r, l = LEVEL_E, LEVEL_R5, LEVEL_L
+        both5 = lambda a: [np.kron(a, I), np.kron(I, a)]
+        return {"g_r1": both5(_op(d, 1, r)), "g_r0": both5(_op(d, 0, r)), "g_rl": both5(_op(d, l, r)),
+                "g_phi": both5(_op(d, r, r)), "g_e1": both5(_op(d, 1, e)), "g_e0": both5(_op(d, 0, e))}
     ryd = [2] if d == 3 else [2, 3]
     two = np.kron
 
@@ -74,9 +121,10 @@ def _jump_terms(d: int) -> Dict[str, List[np.ndarray]]:
     return out
 
 
+@functools.lru_cache(maxsize=None)
 def liouvillian_terms(d: int) -> Tuple[Tuple[str, ...], List[np.ndarray]]:
     """(param names, [L_k]) with L_k of shape (d^4, d^4), row-major vec convention."""
-    names = PARAMS3 if d == 3 else PARAMS4
+    names = params_of(d)
     n = d * d
     I = np.eye(n, dtype=complex)
     H = _hamiltonian_terms(d)
@@ -133,8 +181,12 @@ class RealSystem:
         return self.var_info.index((i, j, part))
 
 
-def reduce_system(name: str, d: int, X0: np.ndarray, hermitian: bool) -> RealSystem:
-    """Restrict to the operator entries reachable from X0 and make the system real."""
+def reduce_system(name: str, d: int, X0: np.ndarray, hermitian: bool, readout=None) -> RealSystem:
+    """Restrict to the operator entries reachable from X0 and make the system real.
+
+    ``readout`` (a list of operator entries (i, j)) additionally drops every entry that cannot
+    influence any readout entry: sink sectors (an atom lost to |0> or |l>) are fed by the active
+    block and never feed back, so the remaining system is still closed and exact."""
     names, L = liouvillian_terms(d)
     N = d * d
     pattern = sum(np.abs(Lk) for Lk in L) > 0
@@ -144,6 +196,18 @@ def reduce_system(name: str, d: int, X0: np.ndarray, hermitian: bool) -> RealSys
         if (new == reach).all():
             break
         reach = new
+    if readout is not None:
+        need = np.zeros(N * N, dtype=bool)
+        for (i, j) in readout:
+            need[i * N + j] = True
+            if hermitian:
+                need[j * N + i] = True
+        while True:
+            new = need | (pattern.T @ need.astype(float) > 0)
+            if (new == need).all():
+                break
+            need = new
+        reach = reach & need
     entries = [(idx // N, idx % N) for idx in np.nonzero(reach)[0]]
     eset = set(entries)
     var_info: List[Tuple[int, int, str]] = []
@@ -206,9 +270,18 @@ def standard_systems(d: int) -> Dict[str, RealSystem]:
 
     k00 = ket(0, 0)
     for lab in ("01", "10", "11"):
-        k = ket(int(lab[0]), int(lab[1]))
-        out["rho" + lab] = reduce_system("rho" + lab, d, np.outer(k, k.conj()), True)
-        out["coh" + lab] = reduce_system("coh" + lab, d, np.outer(k, k00.conj()), False)
+        a, b = int(lab[0]), int(lab[1])
+        k = ket(a, b)
+        ro_rho = ro_coh = None
+        if d == 5:
+            # keep the block in which no atom has been lost: populations of every state an atom that
+            # started in |1> can still coherently occupy (1, e, r); an atom that started in |0> stays there
+            act = lambda s: (1, LEVEL_E, LEVEL_R5) if s == 1 else (0,)
+            states = [d * x + y for x in act(a) for y in act(b)]
+            ro_rho = [(i, i) for i in states]
+            ro_coh = [(i, 0) for i in states]
+        out["rho" + lab] = reduce_system("rho" + lab, d, np.outer(k, k.conj()), True, ro_rho)
+        out["coh" + lab] = reduce_system("coh" + lab, d, np.outer(k, k00.conj()), False, ro_coh)
     return out
 
 
@@ -217,8 +290,7 @@ def standard_systems(d: int) -> Dict[str, RealSystem]:
 # --------------------------------------------------------------------------------------------
 def sym_params(d: int) -> Tuple[str, ...]:
     """Parameter list with the two per-atom detunings merged into one."""
-    names = PARAMS3 if d == 3 else PARAMS4
-    return tuple("det" if n == "det_a" else n for n in names if n != "det_b")
+    return tuple("det" if n == "det_a" else n for n in params_of(d) if n != "det_b")
 
 
 @dataclass

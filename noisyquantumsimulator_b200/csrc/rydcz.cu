@@ -71,7 +71,7 @@ __global__ void work_kernel(int64_t n_points, const double* __restrict__ points,
                             int max_seg, int shots, float* __restrict__ keys, uint32_t* __restrict__ idx) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_points) return;
-  const double* pt = points + i * PT_STRIDE;
+  const double* pt = points + i * PointStride<D>::value;
   double w = point_work<D>(pt, segs + i * (int64_t)max_seg * SG_STRIDE, n_seg ? n_seg[i] : max_seg);
   // points whose atoms differ take the general kernel: keep them together (ahead of the folded
   // ones) so warps stay homogeneous in mixed batches
@@ -109,7 +109,7 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, int64_t point_base,
   }
   // the point row lives in shared memory, transposed ([slot][thread]: conflict-free), so it costs
   // no registers inside the Chebyshev loop; only this thread touches its column
-  __shared__ double s_pt[(PT_STRIDE + PT_SCRATCH) * kBlock];
+  __shared__ double s_pt[(PT_MAX_STRIDE + PT_SCRATCH) * kBlock];
   double* mine = s_pt + threadIdx.x;
   const double* row = points + point * PT_STRIDE;
   const bool folded = (row[PT_OFF_A] == row[PT_OFF_B]) && (!SHOTS || row[PT_SIG_DET] == 0.0);
@@ -140,6 +140,44 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, int64_t point_base,
     else evaluate_point_d4<NOISY>(pt, sg, ns, o, st);
   }
   double* op = out + item * OUT_STRIDE;
+#pragma unroll
+  for (int k = 0; k < OUT_STRIDE; k += 2)
+    *reinterpret_cast<double2*>(op + k) = make_double2(o[k], o[k + 1]);
+}
+
+// dim = 5 (intermediate state kept; identical atoms).  Per thread, in dynamic shared memory
+// ([slot][thread], conflict-free): the point row + scratch (26 slots), the start vector of rho_11
+// (45) and its generator coefficients (41) -- 896 B per thread, 112 KB per CTA, two CTAs per SM.
+constexpr int kSlots5 = PT_MAX_STRIDE + PT_SCRATCH + Sys_rho11s_d5::N + Sys_rho11s_d5::NC;
+constexpr size_t kSmem5 = (size_t)kSlots5 * kBlock * sizeof(double);
+template <bool NOISY>
+__global__ void __launch_bounds__(kBlock, 2)
+evaluate5_kernel(int64_t n_items, const uint32_t* __restrict__ order, const double* __restrict__ points,
+                 const double* __restrict__ segs, const int32_t* __restrict__ n_seg, int max_seg,
+                 double* __restrict__ out, double* __restrict__ states) {
+  extern __shared__ double s5[];
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_items) return;
+  const int64_t point = order ? order[g] : g;
+  double* mine = s5 + threadIdx.x;
+  const double* row = points + point * PT5_STRIDE;
+  double* op = out + point * OUT_STRIDE;
+  if (!(row[PT_OFF_A] == row[PT_OFF_B])) {
+    // the 81-variable general system is not built: atoms with different detunings are not evaluated
+#pragma unroll
+    for (int k = 0; k < OUT_STRIDE; ++k) op[k] = __longlong_as_double(0x7ff8000000000000LL);
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < PT5_USED; ++k) mine[k * kBlock] = row[k];
+  const PointView pt{mine, kBlock};
+  const Col xcol{mine + (PT_MAX_STRIDE + PT_SCRATCH) * kBlock, kBlock};
+  const Col ccol{mine + (PT_MAX_STRIDE + PT_SCRATCH + Sys_rho11s_d5::N) * kBlock, kBlock};
+  const double* sg = segs + point * (int64_t)max_seg * SG_STRIDE;
+  const int ns = n_seg ? n_seg[point] : max_seg;
+  double o[OUT_STRIDE];
+  double* st = states ? states + point * StateLayout<5>::STRIDE : nullptr;
+  evaluate_point_sym_d5<NOISY>(pt, xcol, ccol, sg, ns, o, st);
 #pragma unroll
   for (int k = 0; k < OUT_STRIDE; k += 2)
     *reinterpret_cast<double2*>(op + k) = make_double2(o[k], o[k + 1]);
@@ -237,6 +275,7 @@ struct rydcz_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   bool sort = true;
+  bool smem5_set = false;
   int64_t launches = 0;
   std::string err;
   // scratch
@@ -309,10 +348,18 @@ template <> void sys_tables<4>(int (&off)[6], int (&n)[6], int (&nnz)[6]) {
   int z[6] = {Sys_rho11_d4::NNZ, Sys_rho01_d4::NNZ, Sys_rho10_d4::NNZ, Sys_coh11_d4::NNZ, Sys_coh01_d4::NNZ, Sys_coh10_d4::NNZ};
   for (int i = 0; i < 6; ++i) { off[i] = o[i]; n[i] = s[i]; nnz[i] = z[i]; }
 }
+template <> void sys_tables<5>(int (&off)[6], int (&n)[6], int (&nnz)[6]) {
+  typedef StateLayout<5> L;
+  int o[6] = {L::RHO11, L::RHO01, L::RHO10, L::COH11, L::COH01, L::COH10};
+  int s[6] = {Sys_rho11_d5::N, Sys_rho01_d5::N, Sys_rho10_d5::N, Sys_coh11_d5::N, Sys_coh01_d5::N, Sys_coh10_d5::N};
+  int z[6] = {Sys_rho11_d5::NNZ, Sys_rho01_d5::NNZ, Sys_rho10_d5::NNZ, Sys_coh11_d5::NNZ, Sys_coh01_d5::NNZ, Sys_coh10_d5::NNZ};
+  for (int i = 0; i < 6; ++i) { off[i] = o[i]; n[i] = s[i]; nnz[i] = z[i]; }
+}
 static int sys_lookup(int dim, const char* name, int what) {
   int off[6], n[6], nnz[6];
   if (dim == 3) sys_tables<3>(off, n, nnz);
   else if (dim == 4) sys_tables<4>(off, n, nnz);
+  else if (dim == 5) sys_tables<5>(off, n, nnz);
   else return -1;
   if (!name) return -1;
   for (int i = 0; i < 6; ++i)
@@ -386,8 +433,10 @@ int rydcz_version(void) { return 100; }
 int rydcz_point_stride(void) { return PT_STRIDE; }
 int rydcz_seg_stride(void) { return SG_STRIDE; }
 int rydcz_out_stride(void) { return OUT_STRIDE; }
+int rydcz_point_stride_dim(int dim) { return dim == 5 ? PT5_STRIDE : ((dim == 3 || dim == 4) ? PT_STRIDE : -1); }
 int rydcz_state_stride(int dim) {
-  return dim == 3 ? StateLayout<3>::STRIDE : (dim == 4 ? StateLayout<4>::STRIDE : -1);
+  return dim == 3 ? StateLayout<3>::STRIDE
+                  : (dim == 4 ? StateLayout<4>::STRIDE : (dim == 5 ? StateLayout<5>::STRIDE : -1));
 }
 int rydcz_state_offset(int dim, const char* system) { return sys_lookup(dim, system, 0); }
 int rydcz_system_size(int dim, const char* system) { return sys_lookup(dim, system, 1); }
@@ -446,9 +495,10 @@ int rydcz_set_sort(rydcz_ctx* ctx, int enable) {
 }
 
 static int check_args(rydcz_ctx* ctx, int dim, int64_t n, const void* a, const void* b, int max_seg,
-                      const void* out) {
+                      const void* out, bool allow5 = false) {
   if (!ctx) return 2;
-  if (dim != 3 && dim != 4) return fail(ctx, "dim must be 3 or 4");
+  if (dim == 5 && !allow5) return fail(ctx, "dim 5 supports rydcz_evaluate_device/_host only (no shots)");
+  if (dim != 3 && dim != 4 && dim != 5) return fail(ctx, "dim must be 3, 4 or 5");
   if (n < 0 || n > 0x7fffffffLL) return fail(ctx, "n_points out of range");
   if (max_seg < 0) return fail(ctx, "max_seg must be >= 0");
   if (n > 0 && (!a || !out || (max_seg > 0 && !b))) return fail(ctx, "null buffer");
@@ -459,6 +509,24 @@ static int evaluate_impl(rydcz_ctx* ctx, const SortScratch& sc, int dim, int noi
                          const double* d_points, const double* d_segs, const int32_t* d_n_seg, int max_seg,
                          double* d_out, double* d_states, cudaStream_t st, int mark) {
   const uint32_t* order = nullptr;
+  if (dim == 5) {
+    if (make_order<5>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 0, st, &order)) return 1;
+    if (!ctx->smem5_set) {
+      CK(cudaFuncSetAttribute(evaluate5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem5));
+      CK(cudaFuncSetAttribute(evaluate5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem5));
+      ctx->smem5_set = true;
+    }
+    const unsigned grid = (unsigned)((n_points + kBlock - 1) / kBlock);
+    if (mark & 1) CK(cudaEventRecord(ctx->ev0, st));
+    if (noisy) evaluate5_kernel<true><<<grid, kBlock, kSmem5, st>>>(n_points, order, d_points, d_segs, d_n_seg,
+                                                                   max_seg, d_out, d_states);
+    else evaluate5_kernel<false><<<grid, kBlock, kSmem5, st>>>(n_points, order, d_points, d_segs, d_n_seg, max_seg,
+                                                              d_out, d_states);
+    CK(cudaGetLastError());
+    if (mark & 2) { CK(cudaEventRecord(ctx->ev1, st)); ctx->timed = true; }
+    ctx->launches++;
+    return 0;
+  }
   int rc = dim == 3 ? make_order<3>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 0, st, &order)
                     : make_order<4>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 0, st, &order);
   if (rc) return rc;
@@ -473,7 +541,7 @@ static int evaluate_impl(rydcz_ctx* ctx, const SortScratch& sc, int dim, int noi
 int rydcz_evaluate_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, const double* d_points,
                           const double* d_segs, const int32_t* d_n_seg, int max_seg, double* d_out,
                           double* d_states, void* stream) {
-  if (int rc = check_args(ctx, dim, n_points, d_points, d_segs, max_seg, d_out)) return rc;
+  if (int rc = check_args(ctx, dim, n_points, d_points, d_segs, max_seg, d_out, true)) return rc;
   if (n_points == 0) return 0;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
@@ -535,12 +603,12 @@ static int stage_in(rydcz_ctx* ctx, int slot, const void* h, size_t bytes) {
 int rydcz_evaluate_host(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, const double* h_points,
                         const double* h_segs, const int32_t* h_n_seg, int max_seg, double* h_out,
                         double* h_states) {
-  if (int rc = check_args(ctx, dim, n_points, h_points, h_segs, max_seg, h_out)) return rc;
+  if (int rc = check_args(ctx, dim, n_points, h_points, h_segs, max_seg, h_out, true)) return rc;
   if (n_points == 0) return 0;
   CK(cudaSetDevice(ctx->device));
   const size_t n = (size_t)n_points;
   const size_t sb = (size_t)rydcz_state_stride(dim) * sizeof(double);
-  if (stage_in(ctx, 0, h_points, n * PT_STRIDE * sizeof(double))) return 1;
+  if (stage_in(ctx, 0, h_points, n * rydcz_point_stride_dim(dim) * sizeof(double))) return 1;
   if (stage_in(ctx, 1, h_segs, n * max_seg * SG_STRIDE * sizeof(double))) return 1;
   if (h_n_seg && stage_in(ctx, 2, h_n_seg, n * sizeof(int32_t))) return 1;
   if (grow(ctx, &ctx->stage[3], &ctx->stage_cap[3], n * OUT_STRIDE * sizeof(double))) return 1;
@@ -597,7 +665,7 @@ static int check_model(rydcz_ctx* ctx, const double* m) {
   if (!ctx) return 2;
   if (!m) return fail(ctx, "null model");
   const int dim = (int)m[MD_DIM], proto = (int)m[MD_PROTOCOL], S = (int)m[MD_NSEG];
-  if (dim != 3 && dim != 4) return fail(ctx, "model: dim must be 3 or 4");
+  if (dim != 3 && dim != 4) return fail(ctx, "model: dim must be 3 or 4 (the device prologue does not cover dim 5)");
   if (proto < 0 || proto > 2) return fail(ctx, "model: protocol must be 0 (lp), 1 (jp) or 2 (sjp)");
   if (S < 1 || (proto == 0 && S != 2)) return fail(ctx, "model: bad segment count");
   if (proto == 1 && 2 * S > APP_STRIDE - APP_PROTO) return fail(ctx, "model: too many bang-bang segments");

@@ -43,8 +43,21 @@
 
 namespace rydcz {
 
+// a writable strided column (per-thread vector in shared memory; stride 1 on the host)
+struct Col {
+  double* base;
+  int stride;
+  RYDCZ_HD double& operator[](int k) const { return base[(long long)k * stride]; }
+};
+// One generator coefficient for the coefficient-major matvec of a big system.  The load is
+// volatile so that the compiler issues it where it is written (41 short-lived values per matvec)
+// instead of hoisting all coefficients of both Clenshaw half-steps into registers and spilling.
+RYDCZ_HD double coef_load(const Col c, int q) { return *(const volatile double*)(c.base + (long long)q * c.stride); }
+RYDCZ_HD double coef_load(const double* c, int q) { return c[q]; }
+
 #include "rydcz_systems_d3.inc"
 #include "rydcz_systems_d4.inc"
+#include "rydcz_systems_d5.inc"
 
 // ---- layout of one point row (doubles) -------------------------------------------------
 // Everything the generator needs that is constant over the pulse.
@@ -62,8 +75,19 @@ enum PointSlot {
   PT_SIG_RELR = 10,// Monte-Carlo: std of dR/R0 = sqrt(2) sigma_r / R0
   PT_RESERVED = 11,
   PT_STRIDE = 12,
+  // dim = 5 only (rows of PT5_STRIDE doubles): the intermediate state of the two-photon excitation
+  PT5_OM1 = 12,     // first-leg Rabi frequency Omega_1 (rad/s)                RG/simulation.py:2910
+  PT5_DET_E = 13,   // intermediate detuning Delta_e (rad/s)
+  PT5_G_E1 = 14,    // decay |e> -> |1>
+  PT5_G_E0 = 15,    // decay |e> -> |0>
+  PT5_G_RL = 16,    // |r> -> |l>: the loss channels that leave the atom untrapped / outside the manifold
+  PT5_LS_COMP = 17, // 1 = light shifts of both legs compensated (the reference's effective model), 0 = bare
+  PT5_USED = 18,    // slots of a dim-5 row that carry data
+  PT5_STRIDE = 20,
+  PT_MAX_STRIDE = 18, // slots of the per-thread copy of a row, any dim (the scratch slots follow)
   PT_SCRATCH = 8    // extra per-thread slots behind a PointView (not part of the C-ABI row)
 };
+template <int D> struct PointStride { static constexpr int value = D == 5 ? PT5_STRIDE : PT_STRIDE; };
 // one segment row: dt (s), Re Omega, Im Omega, Delta (rad/s)
 enum SegSlot { SG_DT = 0, SG_RE = 1, SG_IM = 2, SG_DET = 3, SG_STRIDE = 4 };
 
@@ -92,6 +116,9 @@ template <> struct StateLayout<3> {
 template <> struct StateLayout<4> {
   static constexpr int RHO11 = 0, RHO01 = 36, RHO10 = 42, COH11 = 48, COH01 = 56, COH10 = 60, STRIDE = 64;
 };
+template <> struct StateLayout<5> {   // only the block in which no atom has been lost
+  static constexpr int RHO11 = 0, RHO01 = 81, RHO10 = 90, COH11 = 99, COH01 = 117, COH10 = 123, STRIDE = 129;
+};
 
 // Strided read-only view of one point row: stride 1 for a plain row, blockDim for the
 // transposed shared-memory copy the kernels keep (conflict-free, and the row does not occupy
@@ -100,9 +127,9 @@ struct PointView {
   double* base;
   int stride;
   RYDCZ_HD double operator[](int k) const { return base[(long long)k * stride]; }
-  // slots PT_STRIDE .. PT_STRIDE+PT_SCRATCH-1 of the same column: per-thread scratch that must
-  // survive the Chebyshev loop without holding registers (the cached Chebyshev interval)
-  RYDCZ_HD double& scratch(int k) const { return base[(long long)(PT_STRIDE + k) * stride]; }
+  // slots PT_MAX_STRIDE .. PT_MAX_STRIDE+PT_SCRATCH-1 of the same column: per-thread scratch that
+  // must survive the Chebyshev loop without holding registers (the cached Chebyshev interval)
+  RYDCZ_HD double& scratch(int k) const { return base[(long long)(PT_MAX_STRIDE + k) * stride]; }
 };
 
 RYDCZ_HD int cheb_terms(double z) {
@@ -117,6 +144,66 @@ RYDCZ_HD double cheb_work(double radius, double dt) {
   double z = radius * fabs(dt);
   if (!(z > 0.0)) return 0.0;
   return z + 10.3 * cbrt(z) + 5.0;
+}
+
+// Interval-cache test for a detuning.  dim 5 adds the light-shift compensation |Omega_2|^2/4Delta_e to the
+// detuning, which differs by rounding between equal-amplitude segments: compare to 1e-9 like |Omega|^2.
+template <class Sys>
+RYDCZ_HD bool same_detuning(double a, double b) {
+  return Sys::DIM == 5 ? fabs(a - b) <= 1e-9 * fabs(b) || a == b : a == b;
+}
+
+// Advance `s` to the next segment with a non-zero duration and fill the generator's parameter
+// vector p for it; false when the schedule is exhausted.
+template <class Sys>
+RYDCZ_HD bool next_segment(double* __restrict__ p, const PointView pt, const double* __restrict__ seg, int n_seg,
+                           int& s, double& dt, bool noisy) {
+  bool found = false;
+  const double offa = pt[PT_OFF_A], offb = pt[PT_OFF_B];
+  while (s < n_seg && !found) {
+    const double* sg = seg + (long long)s * SG_STRIDE;
+    dt = sg[SG_DT];
+    if (dt != 0.0 && dt == dt) {
+      p[Sys::IDX_OM_RE] = sg[SG_RE];
+      p[Sys::IDX_OM_IM] = sg[SG_IM];
+      p[Sys::IDX_DET_A] = sg[SG_DET] + offa;
+      p[Sys::IDX_DET_B] = sg[SG_DET] + offb;   // same slot as DET_A for exchange-folded systems
+      found = true;
+    }
+    ++s;
+  }
+  if (!found) return false;
+  p[Sys::IDX_V] = pt[PT_V];
+  p[Sys::IDX_DELTA1] = pt[PT_DELTA1];
+  p[Sys::IDX_G_R1] = noisy ? pt[PT_G_R1] : 0.0;
+  p[Sys::IDX_G_R0] = noisy ? pt[PT_G_R0] : 0.0;
+  p[Sys::IDX_G_PHI] = noisy ? pt[PT_G_PHI] : 0.0;
+  constexpr int kSc = Sys::IDX_G_SC >= 0 ? Sys::IDX_G_SC : 0;
+  if (Sys::IDX_G_SC >= 0) p[kSc] = noisy ? pt[PT_G_SC] : 0.0;
+  constexpr int kMj = Sys::IDX_G_MJ >= 0 ? Sys::IDX_G_MJ : 0;
+  if (Sys::IDX_G_MJ >= 0) p[kMj] = noisy ? pt[PT_G_MJ] : 0.0;
+  if (Sys::DIM == 5) {
+    // The segment row carries the effective two-photon Rabi frequency (so every pulse schedule of
+    // the 3-level path applies unchanged); the second leg is Omega_2 = Omega_eff * 2 Delta_e / Omega_1
+    // and, with PT5_LS_COMP = 1, the light shifts of both legs are compensated.
+    constexpr int kOm1 = Sys::IDX_OM1 >= 0 ? Sys::IDX_OM1 : 0, kDe = Sys::IDX_DET_E >= 0 ? Sys::IDX_DET_E : 0,
+                  kE1 = Sys::IDX_G_E1 >= 0 ? Sys::IDX_G_E1 : 0, kE0 = Sys::IDX_G_E0 >= 0 ? Sys::IDX_G_E0 : 0,
+                  kRl = Sys::IDX_G_RL >= 0 ? Sys::IDX_G_RL : 0;
+    const double om1 = pt[PT5_OM1], dete = pt[PT5_DET_E];
+    const double k2 = 2.0 * dete / om1, ls = pt[PT5_LS_COMP] / (4.0 * dete);
+    const double re2 = p[Sys::IDX_OM_RE] * k2, im2 = p[Sys::IDX_OM_IM] * k2;
+    const double shift_r = ls * (re2 * re2 + im2 * im2);
+    p[Sys::IDX_OM_RE] = re2; p[Sys::IDX_OM_IM] = im2;
+    const double da = p[Sys::IDX_DET_A], db = p[Sys::IDX_DET_B];
+    p[Sys::IDX_DET_A] = da + shift_r;
+    if (Sys::IDX_DET_B != Sys::IDX_DET_A) p[Sys::IDX_DET_B] = db + shift_r;
+    p[Sys::IDX_DELTA1] = pt[PT_DELTA1] - ls * (om1 * om1);
+    p[kOm1] = om1; p[kDe] = dete;
+    p[kE1] = noisy ? pt[PT5_G_E1] : 0.0;
+    p[kE0] = noisy ? pt[PT5_G_E0] : 0.0;
+    p[kRl] = noisy ? pt[PT5_G_RL] : 0.0;
+  }
+  return true;
 }
 
 // Run one system through all segments of a point.
@@ -175,30 +262,8 @@ RYDCZ_HD void run_system(double (&x)[Sys::N], const PointView pt,
         --sub_left;
       } else {
         double dt = 0.0;
-        bool found = false;
         double p[Sys::NP];          // rebuilt per segment so it is not live across the hot loop
-        const double offa = pt[PT_OFF_A], offb = pt[PT_OFF_B];
-        while (s < n_seg && !found) {
-          const double* sg = seg + (long long)s * SG_STRIDE;
-          dt = sg[SG_DT];
-          if (dt != 0.0 && dt == dt) {
-            p[Sys::IDX_OM_RE] = sg[SG_RE];
-            p[Sys::IDX_OM_IM] = sg[SG_IM];
-            p[Sys::IDX_DET_A] = sg[SG_DET] + offa;
-            p[Sys::IDX_DET_B] = sg[SG_DET] + offb;   // same slot as DET_A for exchange-folded systems
-            found = true;
-          }
-          ++s;
-        }
-        if (!found) break;
-        p[Sys::IDX_V] = pt[PT_V];
-        p[Sys::IDX_DELTA1] = pt[PT_DELTA1];
-        p[Sys::IDX_G_R1] = noisy ? pt[PT_G_R1] : 0.0;
-        p[Sys::IDX_G_R0] = noisy ? pt[PT_G_R0] : 0.0;
-        p[Sys::IDX_G_PHI] = noisy ? pt[PT_G_PHI] : 0.0;
-        p[Sys::IDX_G_SC] = noisy ? pt[PT_G_SC] : 0.0;
-        constexpr int kMj = Sys::IDX_G_MJ >= 0 ? Sys::IDX_G_MJ : 0;
-        if (Sys::IDX_G_MJ >= 0) p[kMj] = noisy ? pt[PT_G_MJ] : 0.0;
+        if (!next_segment<Sys>(p, pt, seg, n_seg, s, dt, noisy)) break;
         const double sgn = dt < 0.0 ? -1.0 : 1.0;
         const double adt = fabs(dt);
         // Chebyshev interval.  The Gershgorin bound is taken with |Re Ω| = |Im Ω| = |Ω| (valid for
@@ -207,7 +272,8 @@ RYDCZ_HD void run_system(double (&x)[Sys::N], const PointView pt,
         const double om2 = p[Sys::IDX_OM_RE] * p[Sys::IDX_OM_RE] + p[Sys::IDX_OM_IM] * p[Sys::IDX_OM_IM];
         // (|Ω|² of equal-amplitude segments differs by rounding: compare to 1e-9, far inside the
         //  slack of the bound)
-        if (!(fabs(om2 - iv_om2) <= 1e-9 * iv_om2 && p[Sys::IDX_DET_A] == iv_da && p[Sys::IDX_DET_B] == iv_db)) {
+        if (!(fabs(om2 - iv_om2) <= 1e-9 * iv_om2 && same_detuning<Sys>(p[Sys::IDX_DET_A], iv_da) &&
+              same_detuning<Sys>(p[Sys::IDX_DET_B], iv_db))) {
           const double re = p[Sys::IDX_OM_RE], im = p[Sys::IDX_OM_IM];
           const double da = p[Sys::IDX_DET_A], db = p[Sys::IDX_DET_B];
           const double mag = sqrt(om2);
@@ -272,6 +338,101 @@ RYDCZ_HD void run_system(double (&x)[Sys::N], const PointView pt,
       x[i] = fma(re, cs, im * sn);
       x[i + 1] = fma(im, cs, -re * sn);
     }
+  }
+}
+
+// run_system for a system too large for registers (rho_11 of the 5-level model: 45 real variables).
+// The two Clenshaw vectors b1, b2 stay in registers; the segment's start vector x and the
+// generator's coefficients c live in per-thread shared-memory columns.  x is read once per Clenshaw
+// step (the 2 J_k x term) and every c[q] once per matvec (Sys::apply_cm walks the nonzeros
+// coefficient by coefficient), so shared-memory traffic stays ~4x below the FMA count.
+// Hermitian systems only (no spectral shift).
+template <class Sys>
+RYDCZ_HD void run_system_big(const Col x, const Col c, const PointView pt, const double* __restrict__ seg,
+                             int n_seg, bool noisy, double& steps) {
+  constexpr int N = Sys::N;
+  static_assert(Sys::HERMITIAN, "run_system_big: density-matrix systems only");
+  {
+    double x0[N];
+    Sys::init(x0);
+    RYDCZ_UNROLL
+    for (int i = 0; i < N; ++i) x[i] = x0[i];
+  }
+  double b1[N], b2[N];
+  double jp = 0.0, jk = 0.0, norm = 0.0, kd = 0.0, tz = 0.0;
+  double &iv_om2 = pt.scratch(0), &iv_da = pt.scratch(1), &iv_db = pt.scratch(2), &iv_R = pt.scratch(3),
+         &iv_damp = pt.scratch(5);
+  iv_om2 = -1.0;
+  int k = 0, K = 0, sub_left = 0, s = 0;
+  bool active = false;
+  for (;;) {
+    if (k < 2) {
+      if (active) {
+        RYDCZ_UNROLL
+        for (int i = 0; i < N; ++i) { b1[i] *= 0.5; b2[i] = fma(jk, x[i], b2[i]); }
+        Sys::apply_cm(c, b1, b2);
+        const double inv = 1.0 / (norm + jk);
+        RYDCZ_UNROLL
+        for (int i = 0; i < N; ++i) x[i] = b2[i] * inv;
+        steps += (double)(K + 1);
+        active = false;
+      }
+      if (sub_left > 0) {
+        --sub_left;
+      } else {
+        double dt = 0.0;
+        double p[Sys::NP];
+        if (!next_segment<Sys>(p, pt, seg, n_seg, s, dt, noisy)) break;
+        const double sgn = dt < 0.0 ? -1.0 : 1.0;
+        const double adt = fabs(dt);
+        const double om2 = p[Sys::IDX_OM_RE] * p[Sys::IDX_OM_RE] + p[Sys::IDX_OM_IM] * p[Sys::IDX_OM_IM];
+        if (!(fabs(om2 - iv_om2) <= 1e-9 * iv_om2 && same_detuning<Sys>(p[Sys::IDX_DET_A], iv_da) &&
+              same_detuning<Sys>(p[Sys::IDX_DET_B], iv_db))) {
+          const double re = p[Sys::IDX_OM_RE], im = p[Sys::IDX_OM_IM];
+          const double mag = sqrt(om2);
+          p[Sys::IDX_OM_RE] = mag; p[Sys::IDX_OM_IM] = mag;
+          double lo, hi;
+          Sys::coefs(p, c);
+          Sys::bounds(c, lo, hi, iv_damp);
+          iv_R = hi;
+          p[Sys::IDX_OM_RE] = re; p[Sys::IDX_OM_IM] = im;
+          iv_om2 = om2; iv_da = p[Sys::IDX_DET_A]; iv_db = p[Sys::IDX_DET_B];
+        }
+        const double damp = iv_damp;
+        double R = iv_R;
+        Sys::coefs(p, c);
+        int nsub = 1;
+        if (damp * adt > 2.0) nsub = (int)ceil(0.5 * damp * adt);
+        const double h = adt / (double)nsub;
+        if (!(R * h >= 1e-2)) R = 1e-2 / h;
+        const double z = R * h;
+        const double sc = sgn * 2.0 / R;
+        RYDCZ_UNROLL
+        for (int q = 0; q < Sys::NC; ++q) c[q] *= sc;
+        K = cheb_terms(z);
+        tz = 2.0 / z;
+        sub_left = nsub - 1;
+      }
+      RYDCZ_UNROLL
+      for (int i = 0; i < N; ++i) { b1[i] = 0.0; b2[i] = 0.0; }
+      jp = 0.0; jk = 1e-30;
+      norm = 0.0;
+      kd = (double)K;
+      k = K;
+      active = true;
+    }
+    double ak = jk + jk;
+    RYDCZ_UNROLL
+    for (int i = 0; i < N; ++i) b2[i] = fma(ak, coef_load(x, i), b2[i]);   // (volatile: one load per use)
+    Sys::apply_cm(c, b1, b2);
+    norm += ak;
+    double jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
+    ak = jk + jk;
+    RYDCZ_UNROLL
+    for (int i = 0; i < N; ++i) b1[i] = fma(ak, coef_load(x, i), b1[i]);
+    Sys::apply_cm(c, b2, b1);
+    jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
+    k -= 2;
   }
 }
 
@@ -442,16 +603,85 @@ RYDCZ_DEFINE_EVALUATE(4)
 RYDCZ_DEFINE_EVALUATE_SYM(3)
 RYDCZ_DEFINE_EVALUATE_SYM(4)
 
+// dim = 5 (identical atoms only): rho_11 through run_system_big with its start vector and
+// coefficients in the shared-memory columns xcol / ccol, everything else in registers as above.
+template <bool NOISY>
+RYDCZ_HD void evaluate_point_sym_d5(const PointView pt, const Col xcol, const Col ccol,
+                                    const double* __restrict__ seg, int n_seg, double* __restrict__ out,
+                                    double* __restrict__ states) {
+  typedef StateLayout<5> SL;
+  double steps = 0.0, flops = 0.0, st;
+  double p01 = 1.0, p11 = 1.0, loss = 0.0, ryd = 0.0;
+  double c01r, c01i, c11r, c11i;
+  if (NOISY) {
+    st = 0.0;
+    run_system_big<Sys_rho11s_d5>(xcol, ccol, pt, seg, n_seg, true, st);
+    steps += st; flops += st * 2.0 * (Sys_rho11s_d5::NNZ + Sys_rho11s_d5::N);
+    double x[Sys_rho11s_d5::N];
+    RYDCZ_UNROLL for (int i = 0; i < Sys_rho11s_d5::N; ++i) x[i] = xcol[i];
+    p11 = x[RHO11S_POP_D5];
+    double xf[Sys_rho11s_d5::FULL_N];
+    Sys_rho11s_d5::expand(x, xf);
+    loss = rho11_loss_d5(xf); ryd = rho11_ryd_d5(xf);
+    if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_rho11s_d5::FULL_N; ++i) states[SL::RHO11 + i] = xf[i]; }
+  }
+  {
+    double x[Sys_coh11s_d5::N]; st = 0.0;
+    run_system<Sys_coh11s_d5>(x, pt, seg, n_seg, NOISY, st);
+    steps += st; flops += st * 2.0 * (Sys_coh11s_d5::NNZ + Sys_coh11s_d5::N);
+    c11r = x[COH11S_RE_D5]; c11i = x[COH11S_IM_D5];
+    if (!NOISY) {
+      double xf[Sys_coh11s_d5::FULL_N];
+      Sys_coh11s_d5::expand(x, xf);
+      ryd = coh11_ryd_d5(xf);
+    }
+    if (states) {
+      double xf[Sys_coh11s_d5::FULL_N];
+      Sys_coh11s_d5::expand(x, xf);
+      RYDCZ_UNROLL for (int i = 0; i < Sys_coh11s_d5::FULL_N; ++i) states[SL::COH11 + i] = xf[i];
+    }
+  }
+  if (NOISY) {
+    double x[Sys_in01_d5::N]; st = 0.0;
+    run_system<Sys_in01_d5>(x, pt, seg, n_seg, true, st);
+    steps += st; flops += st * 2.0 * (Sys_in01_d5::NNZ + Sys_in01_d5::N);
+    p01 = x[RHO01_POP_D5];
+    c01r = x[IN01_COH_OFFSET_D5 + COH01_RE_D5]; c01i = x[IN01_COH_OFFSET_D5 + COH01_IM_D5];
+    if (states) {
+      RYDCZ_UNROLL for (int i = 0; i < Sys_rho01_d5::N; ++i) {
+        states[SL::RHO01 + i] = x[i]; states[SL::RHO10 + i] = x[i]; }
+      RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d5::N; ++i) {
+        states[SL::COH01 + i] = x[IN01_COH_OFFSET_D5 + i]; states[SL::COH10 + i] = x[IN01_COH_OFFSET_D5 + i]; }
+    }
+  } else {
+    double x[Sys_coh01_d5::N]; st = 0.0;
+    run_system<Sys_coh01_d5>(x, pt, seg, n_seg, false, st);
+    steps += st; flops += st * 2.0 * (Sys_coh01_d5::NNZ + Sys_coh01_d5::N);
+    c01r = x[COH01_RE_D5]; c01i = x[COH01_IM_D5];
+    if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d5::N; ++i) {
+      states[SL::COH01 + i] = x[i]; states[SL::COH10 + i] = x[i]; } }
+  }
+  cz_epilogue(NOISY, p01, p01, p11, c01r, c01i, c01r, c01i, c11r, c11i, out);
+  out[OUT_LOSS] = loss; out[OUT_RYD] = ryd; out[OUT_STEPS] = steps; out[OUT_FLOPS] = flops;
+}
+
 // Gershgorin radius of the stiffest system (rho_11, or coh_11 when noiseless) for one segment:
 // the work estimate used to sort points so that the threads of a warp run equally long.
 template <int D>
 RYDCZ_HD double point_work(const double* __restrict__ pt, const double* __restrict__ seg, int n_seg) {
   double w = 0.0;
   const double V = fabs(pt[PT_V]);
-  const double damp = pt[PT_G_R1] + pt[PT_G_R0] + pt[PT_G_PHI] + pt[PT_G_SC];
+  double damp = pt[PT_G_R1] + pt[PT_G_R0] + pt[PT_G_PHI] + pt[PT_G_SC];
+  double extra = 0.0, k2 = 1.0;
+  if (D == 5) {
+    // the two-atom spectrum spans V + 2 Delta_e plus both legs' Rabi frequencies
+    damp += pt[PT5_G_E1] + pt[PT5_G_E0] + pt[PT5_G_RL];
+    extra = 2.0 * fabs(pt[PT5_DET_E]) + 2.0 * fabs(pt[PT5_OM1]);
+    k2 = fabs(2.0 * pt[PT5_DET_E] / pt[PT5_OM1]);
+  }
   for (int s = 0; s < n_seg; ++s) {
     const double* sg = seg + (long long)s * SG_STRIDE;
-    const double R = V + 2.0 * (fabs(sg[SG_RE]) + fabs(sg[SG_IM])) + 2.0 * fabs(sg[SG_DET]) +
+    const double R = V + extra + 2.0 * k2 * (fabs(sg[SG_RE]) + fabs(sg[SG_IM])) + 2.0 * fabs(sg[SG_DET]) +
                      fabs(pt[PT_OFF_A]) + fabs(pt[PT_OFF_B]) + 2.0 * fabs(pt[PT_DELTA1]) + 2.0 * damp;
     w += cheb_work(R, sg[SG_DT]);
   }

@@ -87,7 +87,7 @@ class Evaluator:
         points, p_ptr = _host(points, np.float64)
         segs, s_ptr = _host(segs, np.float64)
         B = points.shape[0]
-        assert points.shape == (B, _lib.POINT_STRIDE) and segs.ndim == 3 and segs.shape[0] == B \
+        assert points.shape == (B, self.lib.rydcz_point_stride_dim(dim)) and segs.ndim == 3 and segs.shape[0] == B \
             and segs.shape[2] == _lib.SEG_STRIDE, (points.shape, segs.shape)
         n_ptr = None
         if n_seg is not None:

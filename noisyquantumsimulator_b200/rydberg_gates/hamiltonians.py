@@ -25,9 +25,10 @@ class HilbertSpace:
 
 
 def build_hilbert_space(dim: int = 3) -> HilbertSpace:
-    if dim not in (3, 4):
-        raise ValueError(f"Unsupported Hilbert space dimension: {dim}. Use 3 or 4.")
-    names = ["0", "1", "r"] if dim == 3 else ["0", "1", "r+", "r-"]
+    if dim not in (3, 4, 5):
+        raise ValueError(f"Unsupported Hilbert space dimension: {dim}. Use 3, 4 or 5.")
+    # dim 5 (extension): the intermediate state |e> of the two-photon excitation and a loss level |l>
+    names = {3: ["0", "1", "r"], 4: ["0", "1", "r+", "r-"], 5: ["0", "1", "e", "r", "l"]}[dim]
     hs = HilbertSpace(dim=dim)
     for i, nm in enumerate(names):
         v = np.zeros((dim, 1), dtype=complex)
@@ -36,7 +37,7 @@ def build_hilbert_space(dim: int = 3) -> HilbertSpace:
         hs.projectors[nm] = v @ v.conj().T
     for frm in names:
         for to in names:
-            if frm != to and (frm.startswith("r") or frm == "1"):
+            if frm != to and (frm.startswith("r") or frm in ("1", "e")):
                 hs.transitions[f"{frm}->{to}"] = hs.basis[to] @ hs.basis[frm].conj().T
     hs.identity = np.eye(dim, dtype=complex)
     return hs
@@ -140,6 +141,26 @@ def build_full_hamiltonian(Omega: complex, Delta: float, V: float, hs: HilbertSp
     return H
 
 
+def build_five_level_hamiltonian(Omega: complex, Delta: float, V: float, Omega_1: float, Delta_e: float,
+                                 hs: HilbertSpace = None, delta_zeeman: float = 0.0, delta_stark: float = 0.0,
+                                 trap_laser_on: bool = True, light_shift_compensation: bool = True):
+    """Two-atom Hamiltonian of the 5-level model (extension: no reference counterpart; the reference
+    eliminates |e> and keeps only Ω = Ω1Ω2/2Δe, RG/laser_physics.py:265-359).  ``Omega`` is the
+    effective two-photon Rabi frequency (complex: carries the pulse phase); the second leg is
+    Ω2 = Ω·2Δe/Ω1.  With ``light_shift_compensation`` the light shifts Ω1²/4Δe (on |1>) and |Ω2|²/4Δe
+    (on |r>) are cancelled, so that Δe -> ∞ reproduces ``build_full_hamiltonian``."""
+    if hs is None:
+        hs = build_hilbert_space(5)
+    om2 = Omega * 2.0 * Delta_e / Omega_1
+    ls = (1.0 if light_shift_compensation else 0.0) / (4.0 * Delta_e)
+    s1, s2 = hs.transitions["1->e"], hs.transitions["e->r"]
+    h = 0.5 * Omega_1 * (s1 + s1.conj().T) + 0.5 * (om2 * s2 + np.conj(om2) * s2.conj().T)
+    h = h - Delta_e * hs.projectors["e"] - (Delta + ls * abs(om2) ** 2) * hs.projectors["r"]
+    d1 = delta_zeeman + (delta_stark if trap_laser_on else 0.0) - ls * Omega_1 ** 2
+    h = h + d1 * hs.projectors["1"]
+    return _both(h, hs) + V * op_two_atom(hs.projectors["r"], hs.projectors["r"])
+
+
 def build_phase_modulated_hamiltonian(Omega: float, phase: float, V: float, hs: HilbertSpace, Delta: float = 0.0,
                                       delta_zeeman: float = 0.0, delta_stark: float = 0.0,
                                       trap_laser_on: bool = True):
@@ -170,5 +191,5 @@ def compute_mJ_coupling_ratio(polarization: str) -> Tuple[float, float]:
 __all__ = ["HilbertSpace", "build_hilbert_space", "HS3", "HS4", "b0", "b1", "br", "op_two_atom",
            "build_laser_hamiltonian", "build_detuning_hamiltonian", "build_interaction_hamiltonian",
            "build_qubit_hamiltonian", "build_zeeman_hamiltonian", "build_stark_hamiltonian",
-           "build_full_hamiltonian", "build_phase_modulated_hamiltonian", "check_rwa_validity",
+           "build_full_hamiltonian", "build_five_level_hamiltonian", "build_phase_modulated_hamiltonian", "check_rwa_validity",
            "compute_mJ_zeeman_splitting", "compute_mJ_coupling_ratio"]

@@ -29,7 +29,7 @@ from .pulse_shaping import area_correction_factor, compute_leakage_detuning, get
 from .trap_physics import (calculate_qubit_stark_shift, calculate_zeeman_shift, compute_trap_dependent_noise,
                            get_polarizability_at_wavelength, tweezer_spacing)
 
-POINT_STRIDE, SEG_STRIDE = 12, 4
+POINT_STRIDE, POINT_STRIDE5, SEG_STRIDE = 12, 20, 4
 PROTOCOL_NAMES = {"lp": "levine_pichler", "jp": "jandura_pupillo", "sjp": "smooth_jp"}
 
 
@@ -41,7 +41,7 @@ class GatePlan:
     dim: int
     B: int
     include_noise: bool
-    points: np.ndarray                 # [B, 12]  C-ABI point rows
+    points: np.ndarray                 # [B, 12]  C-ABI point rows ([B, 20] for dim 5)
     segs: np.ndarray                   # [B, S, 4]
     n_seg: np.ndarray                  # [B] int32
     scalars: Dict[str, np.ndarray] = field(default_factory=dict)
@@ -90,12 +90,14 @@ def build_plan(protocol: str, *, B: int,
                delta_over_omega=None, omega_tau=None, pulse_shape="square",
                switching_times=None, phases=None,
                A=None, omega_mod_ratio=None, phi_offset=None,
-               n_smooth_steps=300, n_shaped_steps=500, warn=True) -> GatePlan:
+               n_smooth_steps=300, n_shaped_steps=500, warn=True,
+               # 5-level model only (hilbert_space_dim=5, extension)
+               intermediate_branching_1=0.5, light_shift_compensation=True) -> GatePlan:
     """Vectorised steps 1-10 of simulate_CZ_gate plus the segment schedule of step 12."""
     if protocol not in PROTOCOL_NAMES:
         raise ValueError(f"Unknown protocol: {protocol}")
-    if hilbert_space_dim not in (3, 4):
-        raise ValueError(f"Unsupported Hilbert space dimension: {hilbert_space_dim}. Use 3 or 4.")
+    if hilbert_space_dim not in (3, 4, 5):
+        raise ValueError(f"Unsupported Hilbert space dimension: {hilbert_space_dim}. Use 3, 4 or 5.")
     if config is None:
         config = AtomicConfiguration(species=species, qubit_0=qubit_0, qubit_1=qubit_1,
                                      n_rydberg=n_rydberg, L_rydberg="S")
@@ -231,7 +233,7 @@ def build_plan(protocol: str, *, B: int,
         g_phi_tot = g_phi_laser + g_thermal_total + g_zee
         b1 = 0.5
         nd = hilbert_space_dim
-        nryd = 1 if nd == 3 else 2
+        nryd = 2 if nd == 4 else 1
         # number of collapse operators under the reference's `> 0` guards (RG/noise_models.py:1199-1446)
         n_ops = (2 * nryd * (2 * (g_r > 0) + (g_bbr > 0) + (g_phi_tot > 0) + (g_anti > 0) + (g_bg > 0)
                              + (g_leak > 0)) + 2 * (g_sc > 0) + (4 * (g_mj > 0) if nd == 4 else 0))
@@ -312,10 +314,27 @@ def build_plan(protocol: str, *, B: int,
                           dark_state_valid=np.where(De > 0, s_doo < 0, s_doo > 0))
     n_seg = np.full(B, segs.shape[1], dtype=np.int32)
 
-    points = np.zeros((B, POINT_STRIDE))
+    points = np.zeros((B, POINT_STRIDE5 if hilbert_space_dim == 5 else POINT_STRIDE))
     points[:, 0], points[:, 1] = V, delta_1
     for k in range(5):
         points[:, 4 + k] = rates5[k]
+    if hilbert_space_dim == 5:
+        # The intermediate state is explicit: scattering is the decay of |e> (rate Γe, split between
+        # |1> and |0>), not a dephasing rate on |1>; the loss channels of |r> that remove the atom
+        # (anti-trapping, background gas, leakage to neighbouring Rydberg states) end in |l>, real
+        # decay to other ground states in |0>.
+        Ge = atom["intermediate_states"][config.intermediate_state]["linewidth"]
+        points[:, 7] = 0.0
+        points[:, 12], points[:, 13] = Om1, De
+        points[:, 17] = 1.0 if light_shift_compensation else 0.0
+        if include_noise:
+            points[:, 14] = Ge * intermediate_branching_1
+            points[:, 15] = Ge * (1.0 - intermediate_branching_1)
+            points[:, 5] = g_r * (1 - b1) + g_bbr
+            points[:, 16] = g_anti + g_bg + g_leak
+            # one jump operator per atom and non-zero collapsed rate
+            n5 = 2 * sum((points[:, k] > 0).astype(int) for k in (4, 5, 6, 14, 15, 16))
+            nb.update({"gamma_e": Ge, "intermediate_branching_1": intermediate_branching_1, "n_collapse_ops": n5})
     # Monte-Carlo shot widths (extension; used only when shots are requested): per-atom Doppler
     # detuning std k_eff v_rms and relative distance std sqrt(2) sigma_r / R
     k1 = 2 * np.pi / (config.excitation_wavelength_1_nm * 1e-9)

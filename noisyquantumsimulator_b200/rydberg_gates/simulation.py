@@ -29,7 +29,8 @@ import numpy as np
 
 from .configurations import (AtomicConfiguration, JPSimulationInputs, LPSimulationInputs,
                              SmoothJPSimulationInputs)
-from .hamiltonians import HilbertSpace, build_full_hamiltonian, build_hilbert_space
+from .hamiltonians import (HilbertSpace, build_five_level_hamiltonian, build_full_hamiltonian,
+                           build_hilbert_space)
 from .noise_models import build_all_noise_operators
 from .prologue import PROTOCOL_NAMES, GatePlan, build_plan
 
@@ -329,6 +330,8 @@ def simulate_CZ_gate(
     *,
     phase_mode: str = None,
     device: int = 0,
+    intermediate_branching_1: float = 0.5,
+    light_shift_compensation: bool = True,
 ) -> Union[SimulationResult, Dict]:
     """One CZ gate evaluation.  Parameters, defaults, errors and result fields follow the
     reference (RG/simulation.py:2534-3676)."""
@@ -355,7 +358,8 @@ def simulate_CZ_gate(
                       tweezer_waist=tweezer_waist, tweezer_wavelength_nm=tweezer_wavelength_nm,
                       temperature=temperature, B_field=B_field, NA=NA, spacing_factor=spacing_factor,
                       include_noise=include_noise, background_loss_rate_hz=background_loss_rate_hz,
-                      trap_laser_on=trap_laser_on, **_plan_kwargs(simulation_inputs), **pk)
+                      trap_laser_on=trap_laser_on, intermediate_branching_1=intermediate_branching_1,
+                      light_shift_compensation=light_shift_compensation, **_plan_kwargs(simulation_inputs), **pk)
     sc = {k: _scalar(v) for k, v in plan.scalars.items()}
     nb = {k: _scalar(v) for k, v in plan.noise_breakdown.items()}
     noisy = bool(include_noise) and nb.get("n_collapse_ops", 0) > 0   # c_ops=[] -> kets (QuTiP 5)
@@ -395,13 +399,28 @@ def simulate_CZ_gate(
     hs = build_hilbert_space(hilbert_space_dim)
     H1 = H2 = None
     xi = sc["xi"] if proto == "lp" else 1.0
-    if proto == "lp":
+    if proto == "lp" and hilbert_space_dim == 5:
+        hk = dict(Delta=sc["Delta"], V=sc["V"], Omega_1=sc["Omega1"], Delta_e=float(plan.points[0, 13]), hs=hs,
+                  delta_zeeman=sc["delta_zeeman"], delta_stark=sc["delta_stark"], trap_laser_on=trap_laser_on,
+                  light_shift_compensation=light_shift_compensation)
+        H1 = build_five_level_hamiltonian(Omega=sc["Omega"], **hk)
+        H2 = build_five_level_hamiltonian(Omega=sc["Omega"] * xi, **hk)
+    elif proto == "lp":
         hk = dict(Delta=sc["Delta"], V=sc["V"], hs=hs, dim=hilbert_space_dim, delta_zeeman=sc["delta_zeeman"],
                   delta_stark=sc["delta_stark"], trap_laser_on=trap_laser_on)
         H1 = build_full_hamiltonian(Omega=sc["Omega"], **hk)
         H2 = build_full_hamiltonian(Omega=sc["Omega"] * xi, **hk)
     c_ops = []
-    if include_noise:
+    if include_noise and hilbert_space_dim == 5:
+        pt = plan.points[0]
+        tr = hs.transitions
+        for rate, key in ((pt[14], "e->1"), (pt[15], "e->0"), (pt[4], "r->1"), (pt[5], "r->0"), (pt[16], "r->l")):
+            if rate > 0:
+                c_ops += [np.sqrt(rate) * np.kron(tr[key], hs.identity), np.sqrt(rate) * np.kron(hs.identity, tr[key])]
+        if pt[6] > 0:
+            P = hs.projectors["r"]
+            c_ops += [np.sqrt(pt[6]) * np.kron(P, hs.identity), np.sqrt(pt[6]) * np.kron(hs.identity, P)]
+    elif include_noise:
         c_ops, _ = build_all_noise_operators(
             hs=hs, gamma_r=nb["gamma_r"], gamma_bbr=nb["gamma_bbr"], gamma_phi_laser=nb["gamma_phi_laser"],
             gamma_phi_thermal=nb["gamma_phi_thermal"], gamma_phi_zeeman=nb["gamma_phi_zeeman"],
@@ -529,8 +548,11 @@ def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, se
     from . import device_prologue as dpro
 
     shaped = protocol == "lp" and kwargs.get("pulse_shape", "square") != "square"
+    five = kwargs.get("hilbert_space_dim", 3) == 5 or (plan is not None and plan.dim == 5)
+    if five and n_shots > 0:
+        raise ValueError("Monte-Carlo shots are not available for hilbert_space_dim=5")
     if prologue == "auto":
-        prologue = "host" if (plan is not None or shaped or return_shots) else "device"
+        prologue = "host" if (plan is not None or shaped or return_shots or five) else "device"
     if B is None and plan is None:
         B = max([np.size(v) for v in kwargs.values() if isinstance(v, np.ndarray) and v.ndim >= 1
                  and np.shape(v)[0] > 1] or [1])
@@ -540,8 +562,8 @@ def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, se
     ev = get_evaluator(device)
     states = shots = None
     if prologue == "device":
-        if shaped:
-            raise ValueError("shaped LP pulses need prologue='host'")
+        if shaped or five:
+            raise ValueError("shaped LP pulses and hilbert_space_dim=5 need prologue='host'")
         if protocol not in PROTOCOL_NAMES:
             raise ValueError(f"Unknown protocol: {protocol}")
         mk, ak = dpro.split_kwargs(kwargs)

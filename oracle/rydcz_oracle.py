@@ -447,3 +447,112 @@ def compute_cost(avg_fid: float, f11: float, cz_phase_fid: float, gate_time_us: 
         return 1e6
     return (10.0 * ((1 - avg_fid) * 100) ** 2 + 5.0 * ((1 - f11) * 100) ** 2
             + 2.0 * ((1 - cz_phase_fid) * 100) ** 2 + time_weight * gate_time_us)
+
+
+# --------------------------------------------------------------------------
+# Five levels per atom (|0>, |1>, |e>, |r>, |l>): the intermediate state of the two-photon
+# excitation kept explicitly.  EXTENSION -- the reference has no such model (SURVEY.md section 8d,
+# config 5; BASELINE.json configs[4]); it uses the reference's own ingredients: the single-photon
+# Rabi frequencies Ω1, Ω2 (RG/simulation.py:2896-2912), the intermediate detuning Δe and linewidth
+# Γe (RG/atom_database.py:230, 402) and the Rydberg rates of RG/simulation.py:3230-3334.  Parity for
+# this model is UNPINNED (no reference output can exist); it is checked against this restatement and
+# against its own Δe -> infinity limit, the reference's 3-level model.
+# --------------------------------------------------------------------------
+LEVEL_E, LEVEL_R5, LEVEL_L = 2, 3, 4
+
+
+@dataclass
+class NoiseRates5:
+    """Collapsed rates of the 5-level model (one jump operator per atom and rate)."""
+
+    g_e1: float = 0.0    # |e> -> |1>   Γe · branching
+    g_e0: float = 0.0    # |e> -> |0>   Γe · (1 - branching)
+    g_r1: float = 0.0    # |r> -> |1>   γ_r · branching_1                 (RG/noise_models.py:1237)
+    g_r0: float = 0.0    # |r> -> |0>   γ_r (1 - branching_1) + γ_bbr      (RG/noise_models.py:1242-1251)
+    g_rl: float = 0.0    # |r> -> |l>   antitrap + background + leakage    (RG/noise_models.py:1583-1592)
+    g_phi: float = 0.0   # dephasing on |r><r|                            (RG/noise_models.py:1579)
+
+    def any(self) -> bool:
+        return any(v > 0 for v in (self.g_e1, self.g_e0, self.g_r1, self.g_r0, self.g_rl, self.g_phi))
+
+
+def hamiltonian5(Omega_eff: complex, Delta: float, V: float, delta_1: float, om1: float, det_e: float,
+                 ls_comp: float = 1.0, detuning_offsets: Tuple[float, float] = (0.0, 0.0)) -> np.ndarray:
+    """H = Σ_atoms [ Ω1/2 (|e><1| + h.c.) + (Ω2/2 |r><e| + h.c.) − Δe |e><e| − Δ' |r><r| + δ1' |1><1| ]
+           + V |rr><rr|,
+    with the second leg chosen so that the effective two-photon Rabi frequency is the pulse's:
+    Ω2 = Ω_eff · 2Δe/Ω1 (Ω = Ω1Ω2/2Δe, RG/laser_physics.py:265-359), and -- ``ls_comp`` = 1 -- the
+    light shifts Ω1²/4Δe on |1> and |Ω2|²/4Δe on |r> compensated (Δ' = Δ + |Ω2|²/4Δe,
+    δ1' = δ1 − Ω1²/4Δe), so that Δe -> ∞ at fixed Ω_eff is the reference's 3-level Hamiltonian."""
+    d = 5
+    I = np.eye(d, dtype=complex)
+    om2 = Omega_eff * 2.0 * det_e / om1
+    ls = ls_comp / (4.0 * det_e)
+    h = 0.5 * om1 * (_op(d, LEVEL_E, 1) + _op(d, 1, LEVEL_E))
+    h = h + 0.5 * (om2 * _op(d, LEVEL_R5, LEVEL_E) + np.conj(om2) * _op(d, LEVEL_E, LEVEL_R5))
+    h = h - det_e * _op(d, LEVEL_E, LEVEL_E) + (delta_1 - ls * om1 * om1) * _op(d, 1, 1)
+    Pr = _op(d, LEVEL_R5, LEVEL_R5)
+    H = _two(h, I) + _two(I, h)
+    for atom, off in enumerate(detuning_offsets):
+        det = Delta + off + ls * abs(om2) ** 2
+        H = H - det * (_two(Pr, I) if atom == 0 else _two(I, Pr))
+    return H + V * _two(Pr, Pr)
+
+
+def collapse_operators5(rates: NoiseRates5) -> List[np.ndarray]:
+    d = 5
+    I = np.eye(d, dtype=complex)
+    ops: List[np.ndarray] = []
+    for rate, (to, frm) in ((rates.g_e1, (1, LEVEL_E)), (rates.g_e0, (0, LEVEL_E)), (rates.g_r1, (1, LEVEL_R5)),
+                            (rates.g_r0, (0, LEVEL_R5)), (rates.g_rl, (LEVEL_L, LEVEL_R5)),
+                            (rates.g_phi, (LEVEL_R5, LEVEL_R5))):
+        if rate > 0:
+            a = math.sqrt(rate) * _op(d, to, frm)
+            ops += [_two(a, I), _two(I, a)]
+    return ops
+
+
+def propagate5(segments: Sequence[Segment], V: float, delta_1: float, om1: float, det_e: float,
+               rates: Optional[NoiseRates5], ls_comp: float = 1.0, mode: str = "exact",
+               detuning_offsets: Tuple[float, float] = (0.0, 0.0),
+               initial: Optional[Dict[str, np.ndarray]] = None, nsteps: int = 200000) -> Dict[str, np.ndarray]:
+    """Same contract as ``propagate`` for the 5-level model."""
+    c_ops = collapse_operators5(rates) if rates is not None else []
+    pure = len(c_ops) == 0 and initial is None
+    kets = initial_kets(5)
+    if initial is not None:
+        states = {k: np.asarray(v, dtype=complex).reshape(-1) for k, v in initial.items()}
+    elif pure:
+        states = {k: v.copy() for k, v in kets.items()}
+    else:
+        states = {k: np.outer(v, v.conj()).reshape(-1) for k, v in kets.items()}
+    for seg in segments:
+        H = hamiltonian5(seg.Omega, seg.Delta, V, delta_1, om1, det_e, ls_comp, detuning_offsets)
+        gen = -1j * H if pure else liouvillian(H, c_ops)
+        if mode == "exact":
+            U = sla.expm(gen * seg.dt)
+            states = {k: U @ v for k, v in states.items()}
+        elif mode == "zvode":
+            states = {k: _zvode_advance(gen, v, seg.dt, seg.n_tlist, nsteps) for k, v in states.items()}
+        else:
+            raise ValueError(mode)
+    if pure:
+        return states
+    return {k: v.reshape(25, 25) for k, v in states.items()}
+
+
+def evaluate5(segments, V, delta_1, om1, det_e, rates: Optional[NoiseRates5], ls_comp: float = 1.0,
+              mode: str = "exact", phase_mode: str = "coherence", detuning_offsets=(0.0, 0.0)):
+    """One 5-level gate evaluation -> (fidelities, avg_fidelity, phase_info, finals)."""
+    finals = propagate5(segments, V, delta_1, om1, det_e, rates, ls_comp, mode, detuning_offsets)
+    if next(iter(finals.values())).ndim == 1:
+        fid, avg, info = cz_fidelity_pure(5, finals)
+    else:
+        coh = None
+        if phase_mode == "coherence":
+            kets = initial_kets(5)
+            init = {k: np.outer(kets[k], kets["00"].conj()) for k in LABELS}
+            fin = propagate5(segments, V, delta_1, om1, det_e, rates, ls_comp, "exact", detuning_offsets, initial=init)
+            coh = {k: complex(np.vdot(kets[k], fin[k].reshape(25, 25) @ kets["00"])) for k in LABELS}
+        fid, avg, info = cz_fidelity_mixed(5, finals, phase_mode, coh)
+    return fid, avg, info, finals

@@ -13,9 +13,10 @@ GOLDEN = os.path.join(HERE, "golden")
 PT_STRIDE, SG_STRIDE, OUT_STRIDE = 12, 4, 16
 OUT = dict(avg=0, f00=1, f01=2, f10=3, f11=4, f11_pop=5, czf=6, ctrl=7, err=8, phi01=9, phi10=10,
            phi11=11, loss=12, ryd=13, steps=14, flops=15)
-STATE_STRIDE = {3: 51, 4: 64}
+STATE_STRIDE = {3: 51, 4: 64, 5: 129}
 STATE_OFFSETS = {3: dict(rho11=0, rho01=25, rho10=30, coh11=35, coh01=43, coh10=47),
-                 4: dict(rho11=0, rho01=36, rho10=42, coh11=48, coh01=56, coh10=60)}
+                 4: dict(rho11=0, rho01=36, rho10=42, coh11=48, coh01=56, coh10=60),
+                 5: dict(rho11=0, rho01=81, rho10=90, coh11=99, coh01=117, coh10=123)}
 
 
 @lru_cache(None)
@@ -94,7 +95,8 @@ def load_hostsim():
     so = os.path.join(d, "libhostsim.so")
     srcs = [os.path.join(d, "hostsim.cpp")] + [
         os.path.join(HERE, "..", "noisyquantumsimulator_b200", "csrc", f)
-        for f in ("rydcz_core.cuh", "rydcz_systems_d3.inc", "rydcz_systems_d4.inc")]
+        for f in ("rydcz_core.cuh", "rydcz_prologue.cuh", "rydcz_systems_d3.inc", "rydcz_systems_d4.inc",
+                  "rydcz_systems_d5.inc")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, srcs[0]])
     lib = ctypes.CDLL(so)
@@ -209,3 +211,43 @@ def _hostsim_simulate_host_cols(self, model, cols, B, n_shots=0, seed=1234, want
 
 
 HostsimEvaluator.simulate_host_cols = _hostsim_simulate_host_cols
+
+
+# ---- 5-level model (hilbert_space_dim = 5) -----------------------------------------------------
+PT5_STRIDE = 20
+ACT2 = [5 * a + b for a in (1, 2, 3) for b in (1, 2, 3)]     # both atoms in {1, e, r}
+ACT01, ACT10 = [1, 2, 3], [5, 10, 15]
+
+
+def pack_batch5(cases):
+    """five_level_cases.json entries -> (points [B,20], segs [B,S,4], n_seg [B]) (ragged batch)."""
+    S = max(len(c["segs"]) for c in cases)
+    pts = np.array([c["point"] for c in cases], dtype=np.float64)
+    seg = np.zeros((len(cases), S, SG_STRIDE))
+    for i, c in enumerate(cases):
+        seg[i, :len(c["segs"])] = c["segs"]
+    return pts, seg, np.array([len(c["segs"]) for c in cases], dtype=np.int32)
+
+
+def _cplx(v):
+    return np.array(v[0]) + 1j * np.array(v[1])
+
+
+def check_five_level_case(case, out_row, st_row, tol_rho=1e-10, tol_f=1e-9):
+    """One 5-level result row + raw state row against the oracle fixture."""
+    exp = case["expected"]
+    ops = states_to_operators(5, st_row)
+    if case["noisy"]:
+        for key, idx in (("rho11", ACT2), ("rho01", ACT01), ("rho10", ACT10)):
+            got = ops[key][np.ix_(idx, idx)]
+            assert np.abs(got - _cplx(exp[key + "_active"])).max() < tol_rho, (case["name"], key)
+        assert abs(out_row[OUT["loss"]] - exp["loss"]) < tol_f
+    else:
+        assert np.abs(ops["coh11"][ACT2, 0] - _cplx(exp["psi11_active"])).max() < tol_rho
+        assert np.abs(ops["coh01"][ACT01, 0] - _cplx(exp["psi01_active"])).max() < tol_rho
+    assert abs(out_row[OUT["avg"]] - exp["avg_fidelity"]) < tol_f, case["name"]
+    for lab, slot in (("00", "f00"), ("01", "f01"), ("10", "f10"), ("11", "f11")):
+        assert abs(out_row[OUT[slot]] - exp["fidelities"][lab]) < tol_f
+    assert abs(out_row[OUT["czf"]] - exp["cz_phase_fidelity"]) < tol_f
+    d = out_row[OUT["ctrl"]] - exp["controlled_phase_rad"]
+    assert abs((d + np.pi) % (2 * np.pi) - np.pi) < 1e-8

@@ -14,9 +14,10 @@ extern "C" int hostsim_evaluate(int dim, int noisy, long long n_points, const do
                                 const double* segs, const int* n_seg, int max_seg, double* out,
                                 double* states) {
   using namespace rydcz;
+  const int stride = dim == 5 ? PT5_STRIDE : PT_STRIDE;
   for (long long i = 0; i < n_points; ++i) {
-    double row[PT_STRIDE + PT_SCRATCH];
-    for (int k = 0; k < PT_STRIDE; ++k) row[k] = points[i * PT_STRIDE + k];
+    double row[PT_MAX_STRIDE + PT_SCRATCH];
+    for (int k = 0; k < (dim == 5 ? (int)PT5_USED : (int)PT_STRIDE); ++k) row[k] = points[i * stride + k];
     const PointView pt{row, 1};
     const double* sg = segs + i * (long long)max_seg * SG_STRIDE;
     double* o = out + i * OUT_STRIDE;
@@ -34,6 +35,12 @@ extern "C" int hostsim_evaluate(int dim, int noisy, long long n_points, const do
                  else evaluate_point_sym_d4<false>(pt, sg, n_seg[i], o, st); }
       else if (noisy) evaluate_point_d4<true>(pt, sg, n_seg[i], o, st);
       else evaluate_point_d4<false>(pt, sg, n_seg[i], o, st);
+    } else if (dim == 5) {
+      if (!(pt[PT_OFF_A] == pt[PT_OFF_B])) return 2;   // identical atoms only, like the CUDA path
+      double* st = states ? states + i * StateLayout<5>::STRIDE : nullptr;
+      double xcol[Sys_rho11s_d5::N], ccol[Sys_rho11s_d5::NC];
+      if (noisy) evaluate_point_sym_d5<true>(pt, Col{xcol, 1}, Col{ccol, 1}, sg, n_seg[i], o, st);
+      else evaluate_point_sym_d5<false>(pt, Col{xcol, 1}, Col{ccol, 1}, sg, n_seg[i], o, st);
     } else return 1;
   }
   return 0;

@@ -29,9 +29,10 @@ def test_layout_queries(lib):
     assert lib.rydcz_version() >= 100
     assert (lib.rydcz_point_stride(), lib.rydcz_seg_stride(), lib.rydcz_out_stride()) == (12, 4, 16)
     assert lib.rydcz_state_stride(3) == 51 and lib.rydcz_state_stride(4) == 64
-    assert lib.rydcz_state_stride(5) == -1
+    assert lib.rydcz_state_stride(5) == 129 and lib.rydcz_state_stride(6) == -1
+    assert [lib.rydcz_point_stride_dim(d) for d in (3, 4, 5, 6)] == [12, 12, 20, -1]
     import _cases as C
-    for dim in (3, 4):
+    for dim in (3, 4, 5):
         for name, off in C.STATE_OFFSETS[dim].items():
             assert lib.rydcz_state_offset(dim, name.encode()) == off
             assert lib.rydcz_system_size(dim, name.encode()) == C.systems(dim)[name].n
@@ -42,7 +43,7 @@ def test_layout_queries(lib):
 def test_generated_sources_are_current():
     """csrc/*.inc is what codegen/emit.py prints today."""
     from noisyquantumsimulator_b200.codegen import emit
-    for d in (3, 4):
+    for d in (3, 4, 5):
         path = os.path.join(ROOT, "noisyquantumsimulator_b200", "csrc", f"rydcz_systems_d{d}.inc")
         assert open(path).read() == emit.emit_dim(d)
 

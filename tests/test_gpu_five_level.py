@@ -1,0 +1,100 @@
+"""5-level model (25x25 rho, BASELINE.json configs[4]) on the CUDA path, through the C ABI."""
+import numpy as np
+import pytest
+
+import _cases as C
+from oracle import rydcz_oracle as orc
+
+pytestmark = pytest.mark.gpu
+CASES = C.load("five_level_cases.json")
+
+
+@pytest.mark.parametrize("noisy", [True, False])
+def test_oracle_fixtures_one_ragged_batch(evaluator, noisy):
+    cases = [c for c in CASES if c["noisy"] == noisy]
+    pts, seg, ns = C.pack_batch5(cases)
+    out, st = evaluator.evaluate_host(5, noisy, pts, seg, ns, want_states=True)
+    for i, c in enumerate(cases):
+        C.check_five_level_case(c, out[i], st[i])
+
+
+def test_random_batch_against_dense_oracle(evaluator):
+    """Seeded Rb/Cs-like parameter points, LP and bang-bang, against the dense 625x625 expm."""
+    rng = np.random.default_rng(55)
+    pts, segs, rates = [], [], []
+    for i in range(10):
+        Om = 2 * np.pi * rng.uniform(1.5e6, 6e6)
+        V = Om * 10 ** rng.uniform(0.8, 2.2)
+        De = 2 * np.pi * rng.uniform(0.8e9, 6e9)
+        om1 = np.sqrt(2 * De * Om) * rng.uniform(0.5, 2.0)
+        r = orc.NoiseRates5(g_e1=rng.uniform(1e7, 2e7), g_e0=rng.uniform(1e7, 2e7), g_r1=rng.uniform(2e3, 5e3),
+                            g_r0=rng.uniform(2e3, 5e3), g_rl=rng.uniform(0, 3e3), g_phi=rng.uniform(1e3, 1e5))
+        if i % 2:
+            sg = orc.segments_lp(Om, rng.uniform(0.2, 0.5) * Om, rng.uniform(3.5, 5.5) / Om)
+        else:
+            ot = rng.uniform(5, 20)
+            sw = np.sort(rng.uniform(0.01, 0.99, 4)) * ot
+            sg = orc.segments_bangbang(Om, ot, list(sw), list(rng.uniform(-np.pi, np.pi, 5)))
+        row = np.zeros(C.PT5_STRIDE)
+        row[[0, 1, 4, 5, 6, 12, 13, 14, 15, 16, 17]] = [V, 2 * np.pi * rng.uniform(0, 3e5), r.g_r1, r.g_r0, r.g_phi,
+                                                        om1, De, r.g_e1, r.g_e0, r.g_rl, float(i % 3 != 0)]
+        pts.append(row); segs.append(sg); rates.append(r)
+    S = max(len(s) for s in segs)
+    G = np.zeros((len(pts), S, 4))
+    for i, sg in enumerate(segs):
+        G[i, :len(sg)] = [[s.dt, s.Omega.real, s.Omega.imag, s.Delta] for s in sg]
+    ns = np.array([len(s) for s in segs], dtype=np.int32)
+    P = np.stack(pts)
+    out, st = evaluator.evaluate_host(5, True, P, G, ns, want_states=True)
+    for i, (row, sg, r) in enumerate(zip(pts, segs, rates)):
+        fid, avg, info, fin = orc.evaluate5(sg, row[0], row[1], row[12], row[13], r, ls_comp=row[17])
+        ops = C.states_to_operators(5, st[i])
+        assert np.abs(ops["rho11"][np.ix_(C.ACT2, C.ACT2)] - fin["11"][np.ix_(C.ACT2, C.ACT2)]).max() < 1e-10
+        assert np.abs(ops["rho01"][np.ix_(C.ACT01, C.ACT01)] - fin["01"][np.ix_(C.ACT01, C.ACT01)]).max() < 1e-10
+        assert abs(out[i, C.OUT["avg"]] - avg) < 1e-9 and abs(out[i, C.OUT["f11"]] - fid["11"]) < 1e-9
+
+
+def test_large_batch_properties(evaluator):
+    """16,384 points: position independence, sorting on/off bit-identical, far-detuned points approach
+    the 3-level kernel's answer, unequal atoms are refused with NaN rows, shots are refused."""
+    from noisyquantumsimulator_b200.engine import RydczError
+    case = next(c for c in CASES if c["name"] == "lp5_rb_noisy")
+    B = 16384
+    rng = np.random.default_rng(9)
+    P = np.repeat(np.array(case["point"])[None], B, 0)
+    G = np.repeat(np.array(case["segs"])[None], B, 0)
+    scale = 10 ** rng.uniform(-0.4, 0.3, B)
+    scale[:512] = 1.0
+    P[:, 0] *= scale
+    out, st = evaluator.evaluate_host(5, True, P, G, None, want_states=True)
+    assert np.all(out[:512] == out[0])
+    C.check_five_level_case(case, out[0], st[0])
+    diag = [0, 17, 32, 45, 56, 65, 72, 77, 80]               # populations of the 9 active two-atom states
+    assert np.abs(st[:, diag].sum(1) + out[:, C.OUT["loss"]] - 1).max() < 1e-12
+    evaluator.set_sort(False)
+    out2, _ = evaluator.evaluate_host(5, True, P, G, None)
+    evaluator.set_sort(True)
+    assert np.array_equal(out, out2)
+    perm = rng.permutation(B)
+    out3, _ = evaluator.evaluate_host(5, True, P[perm], G[perm], None)
+    assert np.array_equal(out3, out[perm])
+    # unequal atoms: the general 81-variable system is not built
+    Q = P[:4].copy()
+    Q[1, 2] = 1e3
+    o, _ = evaluator.evaluate_host(5, True, Q, G[:4], None)
+    assert np.all(np.isnan(o[1])) and np.array_equal(o[0], out[0])
+    with pytest.raises(RydczError):
+        evaluator.evaluate_shots_host(5, True, 4, 1, P[:4], G[:4], None)
+
+
+def test_public_api_rb_vs_cs(evaluator):
+    """Config 5 through simulate_CZ_gate: Rb87 vs Cs133 with the intermediate state kept."""
+    from noisyquantumsimulator_b200 import rydberg_gates as rg
+    exc = rg.TwoPhotonExcitationConfig(laser_1=rg.LaserParameters(power=50e-6, waist=50e-6),
+                                       laser_2=rg.LaserParameters(power=0.3, waist=50e-6), Delta_e=2 * np.pi * 1e9)
+    inp = rg.LPSimulationInputs(excitation=exc, noise=rg.NoiseSourceConfig())
+    for species, name in (("Rb87", "lp5_rb_noisy"), ("Cs133", "lp5_cs_noisy")):
+        res = rg.simulate_CZ_gate(inp, species=species, hilbert_space_dim=5, tweezer_power=0.02, tweezer_waist=0.8e-6)
+        exp = next(c for c in CASES if c["name"] == name)["expected"]
+        assert abs(res.avg_fidelity - exp["avg_fidelity"]) < 1e-9
+        assert res.results["11"].shape == (25, 25)

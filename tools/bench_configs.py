@@ -79,3 +79,12 @@ for proto, nseg in (("lp", 5), ("jp", 5), ("sjp", 5)):
                                      on_batch=lambda X_, r: holder.__setitem__("r", r))
     dt, cost = timed(lambda: f(X), 3)
     line(f"config4_population_8192_{proto}", 8192, dt, holder["r"], dict(best_cost=float(np.min(cost))))
+
+# config 5: Rb vs Cs with the intermediate state kept (5 levels per atom, 25x25 rho), LP protocol, distinct
+# second-leg powers; host prologue (NumPy) + rydcz_evaluate_host
+B5 = 32768
+p2 = 10 ** np.random.default_rng(1234).uniform(np.log10(0.05), np.log10(2.0), B5)
+for species in ("Rb87", "Cs133"):
+    kw = dict(M, species=species, laser_2_power=p2, hilbert_space_dim=5)
+    dt, res = timed(lambda: rg.simulate_CZ_gate_batch("lp", B=B5, warn=False, copy=False, **kw), 3)
+    line(f"config5_lp_5level_{species}_{B5}", B5, dt, res)
