@@ -22,6 +22,7 @@ import numpy as np
 from . import model
 
 
+BIG_CHUNKS = 8        # pieces of one big-system matvec between scheduling fences
 BIG_SYSTEM_N = 40    # more real variables than this: coefficients and start vector live in shared memory
 
 
@@ -198,6 +199,24 @@ def emit_system(sysm: model.RealSystem, struct_name: str) -> str:
             A(f"    cq = coef_load(c, {q});")
             for (i, j, s) in by_q[q]:
                 A(f"    y[{i}] {'+=' if s > 0 else '-='} cq * x[{j}];")
+        A("  }")
+        A("  // One Clenshaw half-step  y <- ak * xs + G x + y  with xs (the segment's start vector) and c in")
+        A("  // shared-memory columns.  The loads are spread over CHUNKS pieces separated by scheduling fences")
+        A("  // so that only a few of them are in flight at a time (otherwise ptxas hoists all ~86 loads to the")
+        A("  // top of the block and spills the Clenshaw vectors).")
+        qs = sorted(by_q)
+        n_chunks = BIG_CHUNKS
+        A("  template <class CV> RYDCZ_HD static void apply_cm_axpy(const CV c, const CV xs, double ak, const double* __restrict__ x, double* __restrict__ y) {")
+        A("    double cq;")
+        for ch in range(n_chunks):
+            for i in range(ch * n // n_chunks, (ch + 1) * n // n_chunks):
+                A(f"    y[{i}] = fma(ak, coef_load(xs, {i}), y[{i}]);")
+            for q in qs[ch * len(qs) // n_chunks:(ch + 1) * len(qs) // n_chunks]:
+                A(f"    cq = coef_load(c, {q});")
+                for (i, j, s) in by_q[q]:
+                    A(f"    y[{i}] {'+=' if s > 0 else '-='} cq * x[{j}];")
+            if ch != n_chunks - 1:
+                A("    RYDCZ_SCHED_FENCE();")
         A("  }")
     A("};")
     A("")

@@ -41,6 +41,17 @@
 #endif
 #endif
 
+// Scheduling fence for the big-system matvec: shared-memory loads may not be moved across a warp
+// barrier, which bounds how many of them ptxas keeps in flight.  Lanes that have left the loop are
+// not in the active mask.  No-op on the host.
+#ifndef RYDCZ_SCHED_FENCE
+#ifdef __CUDA_ARCH__
+#define RYDCZ_SCHED_FENCE() __syncwarp(__activemask())
+#else
+#define RYDCZ_SCHED_FENCE() ((void)0)
+#endif
+#endif
+
 namespace rydcz {
 
 // a writable strided column (per-thread vector in shared memory; stride 1 on the host)
@@ -422,15 +433,11 @@ RYDCZ_HD void run_system_big(const Col x, const Col c, const PointView pt, const
       active = true;
     }
     double ak = jk + jk;
-    RYDCZ_UNROLL
-    for (int i = 0; i < N; ++i) b2[i] = fma(ak, coef_load(x, i), b2[i]);   // (volatile: one load per use)
-    Sys::apply_cm(c, b1, b2);
+    Sys::apply_cm_axpy(c, x, ak, b1, b2);
     norm += ak;
     double jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
     ak = jk + jk;
-    RYDCZ_UNROLL
-    for (int i = 0; i < N; ++i) b1[i] = fma(ak, coef_load(x, i), b1[i]);
-    Sys::apply_cm(c, b2, b1);
+    Sys::apply_cm_axpy(c, x, ak, b2, b1);
     jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
     k -= 2;
   }
