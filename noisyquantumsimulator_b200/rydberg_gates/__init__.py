@@ -2,9 +2,10 @@
 rydberg_gates`` (RG/__init__.py:91-321) for the CZ-gate hot path.
 
 Same names, same argument meaning, same errors; the evolution and fidelity arithmetic runs on the
-B200 through include/rydcz.h.  Not mirrored (out of scope): the SciPy
-differential-evolution drivers (``optimization``, ``optimize_cz_gate``) and ``visualization`` --
-they are callers of this path and run unchanged against it through ``src/qpu_simulator``.
+B200 through include/rydcz.h.  The SciPy differential-evolution drivers (``optimize_cz_gate``,
+``optimization``) are mirrored with the same entry points but evaluate a whole population per
+launch.  Not mirrored (out of scope): ``visualization`` (matplotlib) and
+``optimize_jp_protocols`` (superseded in the reference by ``optimize_cz_gate``).
 """
 from .constants import *  # noqa: F401,F403
 from .atom_database import (ATOM_DB, get_atom_properties, get_quantum_defect, effective_n,  # noqa: F401
@@ -36,3 +37,7 @@ from .protocols import (ProtocolParameters, LPProtocolParameters, JPProtocolPara
 from .simulation import (simulate_CZ_gate, simulate_CZ_gate_batch, compute_CZ_fidelity,  # noqa: F401
                          compute_state_fidelity, SimulationResult, BatchResult)
 from .prologue import build_plan, GatePlan  # noqa: F401
+from .optimize_cz_gate import (ApparatusConstraints, SimulationCache, OptimizationResult,  # noqa: F401
+                               optimize_cz_gate, run_baseline, compute_cost, extract_metrics, warm_start_bounds)
+from .optimization import (HardwareOptimizationResult, optimize_CZ_parameters, EvaluatedPoint,  # noqa: F401
+                           ExplorationResult, explore_parameter_space, combine_explorations)

@@ -10,11 +10,13 @@ starting points are the reference's (RG/optimize_cz_gate.py:458-643); the cost i
 """
 from __future__ import annotations
 
+import hashlib
 from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Tuple
 
 import numpy as np
 
+from .configurations import LaserParameters, NoiseSourceConfig, TwoPhotonExcitationConfig
 from .protocols import (JP_OMEGA_TAU_VALIDATED, JP_PHASES_DEFAULT, JP_PHASES_VALIDATED,
                         JP_SWITCHING_TIMES_DEFAULT, JP_SWITCHING_TIMES_VALIDATED, LEVINE_PICHLER_PARAMS,
                         SMOOTH_JP_PARAMS)
@@ -23,8 +25,7 @@ from .simulation import BatchResult, simulate_CZ_gate_batch
 
 @dataclass
 class ApparatusConstraints:
-    """Fixed hardware of an optimisation run (defaults = the reference's 'medium' apparatus,
-    RG/optimize_cz_gate.py:196-213)."""
+    """Hardware the optimiser may not change (RG/optimize_cz_gate.py:153-281; same defaults)."""
 
     laser_1_power: float = 50e-6
     laser_1_waist: float = 50e-6
@@ -43,16 +44,54 @@ class ApparatusConstraints:
     NA: float = 0.5
     counter_propagating: bool = True
 
-    def plan_kwargs(self, include_noise: bool) -> Dict:
+    def fingerprint(self) -> str:
+        """12 hex digits identifying the apparatus in cache keys (RG/optimize_cz_gate.py:215-225)."""
+        vals = (round(self.laser_1_power, 8), round(self.laser_1_waist, 8), round(self.laser_2_power, 8),
+                round(self.laser_2_waist, 8), round(self.Delta_e, 2), self.n_rydberg, round(self.spacing_factor, 4),
+                round(self.temperature, 10), self.species, round(self.tweezer_power, 6),
+                round(self.tweezer_waist, 8), round(self.NA, 3))
+        return hashlib.md5(str(vals).encode()).hexdigest()[:12]
+
+    def make_excitation_config(self, pol_purity: float = 1.0) -> TwoPhotonExcitationConfig:
+        mk = lambda p, w, pol, lw: LaserParameters(power=p, waist=w, polarization=pol,
+                                                   polarization_purity=pol_purity, linewidth_hz=lw)
+        return TwoPhotonExcitationConfig(
+            laser_1=mk(self.laser_1_power, self.laser_1_waist, "pi", self.laser_1_linewidth_hz),
+            laser_2=mk(self.laser_2_power, self.laser_2_waist, "sigma+", self.laser_2_linewidth_hz),
+            Delta_e=self.Delta_e, counter_propagating=self.counter_propagating)
+
+    @staticmethod
+    def make_noiseless() -> NoiseSourceConfig:
+        return NoiseSourceConfig(include_spontaneous_emission=False, include_intermediate_scattering=False,
+                                 include_motional_dephasing=False, include_doppler_dephasing=False,
+                                 include_intensity_noise=False, intensity_noise_frac=0.0,
+                                 include_laser_dephasing=False, include_magnetic_dephasing=False)
+
+    @staticmethod
+    def make_full_noise() -> NoiseSourceConfig:
+        return NoiseSourceConfig(include_spontaneous_emission=True, include_intermediate_scattering=True,
+                                 include_motional_dephasing=True, include_doppler_dephasing=True,
+                                 include_intensity_noise=True, intensity_noise_frac=0.01,
+                                 include_laser_dephasing=True, include_magnetic_dephasing=True)
+
+    def plan_kwargs(self, include_noise: bool, noise: NoiseSourceConfig = None) -> Dict:
+        """Keywords of ``simulate_CZ_gate_batch`` for this apparatus (what ``simulate_CZ_gate`` would
+        receive through ``make_excitation_config`` + the noise record)."""
         pur = 0.99 if include_noise else 1.0          # RG/optimize_cz_gate.py:885-887
-        return dict(laser_1_power=self.laser_1_power, laser_1_waist=self.laser_1_waist,
-                    laser_2_power=self.laser_2_power, laser_2_waist=self.laser_2_waist, Delta_e=self.Delta_e,
-                    laser_1_linewidth_hz=self.laser_1_linewidth_hz, laser_2_linewidth_hz=self.laser_2_linewidth_hz,
-                    polarization_purity_1=pur, polarization_purity_2=pur,
-                    counter_propagating=self.counter_propagating, temperature=self.temperature,
-                    spacing_factor=self.spacing_factor, n_rydberg=self.n_rydberg, species=self.species,
-                    tweezer_power=self.tweezer_power, tweezer_waist=self.tweezer_waist, B_field=self.B_field,
-                    NA=self.NA, include_noise=include_noise)
+        kw = dict(laser_1_power=self.laser_1_power, laser_1_waist=self.laser_1_waist,
+                  laser_2_power=self.laser_2_power, laser_2_waist=self.laser_2_waist, Delta_e=self.Delta_e,
+                  laser_1_linewidth_hz=self.laser_1_linewidth_hz, laser_2_linewidth_hz=self.laser_2_linewidth_hz,
+                  polarization_purity_1=pur, polarization_purity_2=pur,
+                  counter_propagating=self.counter_propagating, temperature=self.temperature,
+                  spacing_factor=self.spacing_factor, n_rydberg=self.n_rydberg, species=self.species,
+                  tweezer_power=self.tweezer_power, tweezer_waist=self.tweezer_waist, B_field=self.B_field,
+                  NA=self.NA, include_noise=include_noise)
+        if noise is not None:
+            kw.update(include_motional_dephasing=noise.include_motional_dephasing,
+                      include_doppler_dephasing=noise.include_doppler_dephasing,
+                      include_intensity_noise=noise.include_intensity_noise,
+                      intensity_noise_frac=noise.intensity_noise_frac)
+        return kw
 
 
 def bounds_and_x0(protocol: str, n_segments: int = 5) -> Tuple[List[Tuple[float, float]], np.ndarray, List[str]]:

@@ -10,7 +10,8 @@ if _ROOT not in sys.path:
 
 _impl = importlib.import_module("noisyquantumsimulator_b200.rydberg_gates")
 for _name in ("constants", "atom_database", "configurations", "laser_physics", "trap_physics",
-              "noise_models", "hamiltonians", "pulse_shaping", "protocols", "simulation", "prologue"):
+              "noise_models", "hamiltonians", "pulse_shaping", "protocols", "simulation", "prologue",
+              "optimize_cz_gate", "optimization"):
     _mod = importlib.import_module(f"noisyquantumsimulator_b200.rydberg_gates.{_name}")
     sys.modules[f"{__name__}.{_name}"] = _mod
     globals()[_name] = _mod

@@ -187,3 +187,31 @@ def test_pipelined_column_entry_equals_block_entry():
     blk = np.array(ev.simulate_host(model, block, n_shots=4, seed=77)[0])
     assert np.array_equal(one, blk)
     ev.close()
+
+
+def test_optimize_cz_gate_reaches_the_notebook_optimum():
+    """The reference's LP optimisation at spacing 5.373584 (cz_gate_optimization_demo.ipynb cell 10:
+    F = 0.999918 at delta/Omega = 0.369547, Omega*tau = 4.215360) -- population-at-once on the GPU."""
+    import importlib
+    ocg = importlib.import_module("noisyquantumsimulator_b200.rydberg_gates.optimize_cz_gate")
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        r = ocg.optimize_cz_gate("lp", ocg.ApparatusConstraints(spacing_factor=5.373584), maxiter=40, popsize=15,
+                                 verbose=False, cache=ocg.SimulationCache())
+    assert r.best_metrics["avg_fidelity"] >= 0.99990 and r.success
+    assert abs(r.best_params[0] - 0.369547) < 0.01 and abs(r.best_params[1] - 4.215360) < 0.05
+    assert r.n_generations <= 60 and r.n_evaluations > 1000
+
+
+def test_batched_sweep_example_runs(tmp_path):
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = str(tmp_path / "sweeps.json")
+    subprocess.check_call([sys.executable, os.path.join(root, "examples", "research_parameter_sweeps_batched.py"),
+                           "--points", "32", "--out", out], stdout=subprocess.DEVNULL)
+    res = json.load(open(out))
+    assert len(res["temperature_uK"]["lp"]["fidelity"]) == 32 and set(res["species"]) == {"Rb87", "Cs133"}
