@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "librydcz.so")
+# RYDCZ_LIB_PATH: load another build of the same library (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("RYDCZ_LIB_PATH") or os.path.join(HERE, "csrc", "librydcz.so")
 
 POINT_STRIDE, SEG_STRIDE, OUT_STRIDE = 12, 4, 16
 APP_STRIDE, MODEL_STRIDE, SCALAR_STRIDE = 40, 32, 8

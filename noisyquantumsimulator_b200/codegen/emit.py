@@ -22,7 +22,7 @@ import numpy as np
 from . import model
 
 
-BIG_CHUNKS = 8        # pieces of one big-system matvec between scheduling fences
+BIG_CHUNKS = 3        # pieces of one big-system matvec between scheduling fences
 BIG_SYSTEM_N = 40    # more real variables than this: coefficients and start vector live in shared memory
 
 

@@ -82,7 +82,7 @@ for proto, nseg in (("lp", 5), ("jp", 5), ("sjp", 5)):
 
 # config 5: Rb vs Cs with the intermediate state kept (5 levels per atom, 25x25 rho), LP protocol, distinct
 # second-leg powers; host prologue (NumPy) + rydcz_evaluate_host
-B5 = 32768
+B5 = 131072
 p2 = 10 ** np.random.default_rng(1234).uniform(np.log10(0.05), np.log10(2.0), B5)
 for species in ("Rb87", "Cs133"):
     kw = dict(M, species=species, laser_2_power=p2, hilbert_space_dim=5)
