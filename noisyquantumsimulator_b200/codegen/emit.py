@@ -55,7 +55,7 @@ def _linear_forms(sysm: model.RealSystem, shift_matrix):
     return K, form_vecs, entries
 
 
-def emit_system(sysm: model.RealSystem, struct_name: str) -> str:
+def emit_system(sysm: model.RealSystem, struct_name: str, cm: bool = False) -> str:
     n = sysm.n
     # the spectral shift: coherence systems are complex-linear, so multiplying the state by
     # exp(-i c t) commutes with the generator.  In real (re, im) layout "multiply by -i c"
@@ -119,7 +119,7 @@ def emit_system(sysm: model.RealSystem, struct_name: str) -> str:
     # Big systems keep their coefficients (and the segment's start vector) in per-thread shared-memory
     # columns instead of registers: coefs/bounds take any indexable container, and apply_cm walks the
     # nonzeros coefficient by coefficient so that each c[q] is loaded once per matvec.
-    big = n > BIG_SYSTEM_N
+    big = n > BIG_SYSTEM_N or cm     # cm: templated containers although the state fits in registers
     # coefs
     if big:
         A("  template <class CV> RYDCZ_HD static void coefs(const double* __restrict__ p, CV c) {")
@@ -205,8 +205,8 @@ def emit_system(sysm: model.RealSystem, struct_name: str) -> str:
         A("  // so that only a few of them are in flight at a time (otherwise ptxas hoists all ~86 loads to the")
         A("  // top of the block and spills the Clenshaw vectors).")
         qs = sorted(by_q)
-        n_chunks = BIG_CHUNKS
-        A("  template <class CV> RYDCZ_HD static void apply_cm_axpy(const CV c, const CV xs, double ak, const double* __restrict__ x, double* __restrict__ y) {")
+        n_chunks = BIG_CHUNKS if n > BIG_SYSTEM_N else 1
+        A("  template <class CV, class XV> RYDCZ_HD static void apply_cm_axpy(const CV c, const XV xs, double ak, const double* __restrict__ x, double* __restrict__ y) {")
         A("    double cq;")
         for ch in range(n_chunks):
             for i in range(ch * n // n_chunks, (ch + 1) * n // n_chunks):
@@ -233,7 +233,7 @@ def emit_dim(d: int) -> str:
         out.append(emit_system(sysm, f"Sys_{key}_d{d}"))
     folded = model.symmetric_systems(d)
     for key, sysm in folded.items():
-        out.append(emit_system(sysm, f"Sys_{key}_d{d}"))
+        out.append(emit_system(sysm, f"Sys_{key}_d{d}", cm=(key == "rho11s" and d == 3)))
     for key, sysm in model.combined_input_systems(d).items():
         out.append(emit_system(sysm, f"Sys_{key}_d{d}"))
         out.append(f"static constexpr int {key.upper()}_COH_OFFSET_D{d} = {systems['rho' + key[2:]].n};")

@@ -88,16 +88,27 @@ __global__ void work_kernel(int64_t n_points, const double* __restrict__ points,
 // faster on large batches (19.5-20.0 ms vs 20.0 ms for 262,144 bang-bang candidates) and 15 %
 // slower on a 65,536-point batch, where fewer resident slots fill the machine more evenly.
 template <int D, bool NOISY, bool SHOTS, bool SYM>
-__global__ void __launch_bounds__(kBlock, 2)
+#ifndef RYDCZ_D3_VARIANT
+#define RYDCZ_D3_VARIANT 0
+#endif
+__global__ void __launch_bounds__(kBlock, (SYM && D == 3 && RYDCZ_D3_VARIANT != 0) ? 3 : 2)
 evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, int64_t point_base,
                 const uint32_t* __restrict__ order,
                 const double* __restrict__ points, const double* __restrict__ segs,
                 const int32_t* __restrict__ n_seg, int max_seg, double* __restrict__ out,
                 double* __restrict__ states) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_items) return;
-  int64_t point, item;
+  int64_t point = 0, item;
   uint32_t shot = 0;
+  bool keep = g < n_items;
+  if (keep) {
+    if (SHOTS) point = order ? order[g / n_shots] : g / n_shots;
+    else point = order ? order[g] : g;
+    const double* r0 = points + point * PT_STRIDE;
+    keep = ((r0[PT_OFF_A] == r0[PT_OFF_B]) && (!SHOTS || r0[PT_SIG_DET] == 0.0)) == SYM;
+  }
+  const unsigned live = __ballot_sync(0xffffffffu, keep);   // the lanes that evaluate a point in this kernel
+  if (!keep) return;
   if (SHOTS) {
     const int64_t slot = g / n_shots;
     shot = (uint32_t)(g - slot * n_shots);
@@ -109,7 +120,7 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, int64_t point_base,
   }
   // the point row lives in shared memory, transposed ([slot][thread]: conflict-free), so it costs
   // no registers inside the Chebyshev loop; only this thread touches its column
-  __shared__ double s_pt[(PT_MAX_STRIDE + PT_SCRATCH) * kBlock];
+  __shared__ double s_pt[(PT_MAX_STRIDE + PT_SCRATCH + ((SYM && RYDCZ_D3_VARIANT != 0) ? Sys_rho11s_d3::NC : 0)) * kBlock];
   double* mine = s_pt + threadIdx.x;
   const double* row = points + point * PT_STRIDE;
   const bool folded = (row[PT_OFF_A] == row[PT_OFF_B]) && (!SHOTS || row[PT_SIG_DET] == 0.0);
@@ -127,14 +138,15 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, int64_t point_base,
     const double q2 = q * q;
     mine[PT_V * kBlock] = row[PT_V] / (q2 * q2 * q2);
   }
-  const PointView pt{mine, kBlock};
+  const PointView pt{mine, kBlock, live};
   const double* sg = segs + point * (int64_t)max_seg * SG_STRIDE;
   const int ns = n_seg ? n_seg[point] : max_seg;
   double o[OUT_STRIDE];
   double* st = states ? states + item * StateLayout<D>::STRIDE : nullptr;
   if (SYM) {
-    if (D == 3) evaluate_point_sym_d3<NOISY>(pt, sg, ns, o, st);
-    else evaluate_point_sym_d4<NOISY>(pt, sg, ns, o, st);
+    const Col xcol{mine + (PT_MAX_STRIDE + PT_SCRATCH) * kBlock, kBlock};
+    if (D == 3) evaluate_point_sym_d3<NOISY>(pt, xcol, sg, ns, o, st);
+    else evaluate_point_sym_d4<NOISY>(pt, xcol, sg, ns, o, st);
   } else {
     if (D == 3) evaluate_point_d3<NOISY>(pt, sg, ns, o, st);
     else evaluate_point_d4<NOISY>(pt, sg, ns, o, st);
@@ -157,12 +169,15 @@ evaluate5_kernel(int64_t n_items, const uint32_t* __restrict__ order, const doub
                  double* __restrict__ out, double* __restrict__ states) {
   extern __shared__ double s5[];
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_items) return;
-  const int64_t point = order ? order[g] : g;
+  const bool inside = g < n_items;
+  const int64_t point = inside ? (order ? order[g] : g) : 0;
   double* mine = s5 + threadIdx.x;
   const double* row = points + point * PT5_STRIDE;
   double* op = out + point * OUT_STRIDE;
-  if (!(row[PT_OFF_A] == row[PT_OFF_B])) {
+  const bool keep = inside && (row[PT_OFF_A] == row[PT_OFF_B]);
+  const unsigned live = __ballot_sync(0xffffffffu, keep);   // lanes that evaluate a point (reconvergence mask)
+  if (!inside) return;
+  if (!keep) {
     // the 81-variable general system is not built: atoms with different detunings are not evaluated
 #pragma unroll
     for (int k = 0; k < OUT_STRIDE; ++k) op[k] = __longlong_as_double(0x7ff8000000000000LL);
@@ -170,7 +185,7 @@ evaluate5_kernel(int64_t n_items, const uint32_t* __restrict__ order, const doub
   }
 #pragma unroll
   for (int k = 0; k < PT5_USED; ++k) mine[k * kBlock] = row[k];
-  const PointView pt{mine, kBlock};
+  const PointView pt{mine, kBlock, live};
   const Col xcol{mine + (PT_MAX_STRIDE + PT_SCRATCH) * kBlock, kBlock};
   const Col ccol{mine + (PT_MAX_STRIDE + PT_SCRATCH + Sys_rho11s_d5::N) * kBlock, kBlock};
   const double* sg = segs + point * (int64_t)max_seg * SG_STRIDE;

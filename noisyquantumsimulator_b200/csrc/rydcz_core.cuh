@@ -44,6 +44,15 @@
 // Scheduling fence for the big-system matvec: shared-memory loads may not be moved across a warp
 // barrier, which bounds how many of them ptxas keeps in flight.  Lanes that have left the loop are
 // not in the active mask.  No-op on the host.
+// Reconverge the lanes of a warp that evaluate points (between two systems: lanes leave a system's
+// loop at different iterations and must not start the next loop in separate groups).
+#ifndef RYDCZ_RECONVERGE
+#ifdef __CUDA_ARCH__
+#define RYDCZ_RECONVERGE(mask) __syncwarp(mask)
+#else
+#define RYDCZ_RECONVERGE(mask) ((void)0)
+#endif
+#endif
 #ifndef RYDCZ_SCHED_FENCE
 #ifdef __CUDA_ARCH__
 #define RYDCZ_SCHED_FENCE() __syncwarp(__activemask())
@@ -137,6 +146,7 @@ template <> struct StateLayout<5> {   // only the block in which no atom has bee
 struct PointView {
   double* base;
   int stride;
+  unsigned live = 0xffffffffu;   // lanes of this warp that evaluate a point (device: reconvergence mask)
   RYDCZ_HD double operator[](int k) const { return base[(long long)k * stride]; }
   // slots PT_MAX_STRIDE .. PT_MAX_STRIDE+PT_SCRATCH-1 of the same column: per-thread scratch that
   // must survive the Chebyshev loop without holding registers (the cached Chebyshev interval)
@@ -358,8 +368,8 @@ RYDCZ_HD void run_system(double (&x)[Sys::N], const PointView pt,
 // step (the 2 J_k x term) and every c[q] once per matvec (Sys::apply_cm walks the nonzeros
 // coefficient by coefficient), so shared-memory traffic stays ~4x below the FMA count.
 // Hermitian systems only (no spectral shift).
-template <class Sys>
-RYDCZ_HD void run_system_big(const Col x, const Col c, const PointView pt, const double* __restrict__ seg,
+template <class Sys, class XV, class CV>
+RYDCZ_HD void run_system_big(const XV x, const CV c, const PointView pt, const double* __restrict__ seg,
                              int n_seg, bool noisy, double& steps) {
   constexpr int N = Sys::N;
   static_assert(Sys::HERMITIAN, "run_system_big: density-matrix systems only");
@@ -495,7 +505,7 @@ RYDCZ_HD void cz_epilogue(bool noisy, double p01, double p10, double p11,
     double c01r, c01i, c10r, c10i, c11r, c11i;                                                      \
     if (NOISY) {                                                                                    \
       double x[Sys_rho11_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_rho11_d##D>(x, pt, seg, n_seg, true, st);                                      \
+      run_system<Sys_rho11_d##D>(x, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);           \
       steps += st; flops += st * 2.0 * (Sys_rho11_d##D::NNZ + Sys_rho11_d##D::N);                   \
       p11 = x[RHO11_POP_D##D];                                                                      \
       loss = rho11_loss_d##D(x); ryd = rho11_ryd_d##D(x);                                           \
@@ -503,7 +513,7 @@ RYDCZ_HD void cz_epilogue(bool noisy, double p01, double p10, double p11,
     }                                                                                               \
     {                                                                                               \
       double x[Sys_coh11_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_coh11_d##D>(x, pt, seg, n_seg, NOISY, st);                                     \
+      run_system<Sys_coh11_d##D>(x, pt, seg, n_seg, NOISY, st); RYDCZ_RECONVERGE(pt.live);          \
       steps += st; flops += st * 2.0 * (Sys_coh11_d##D::NNZ + Sys_coh11_d##D::N);                   \
       c11r = x[COH11_RE_D##D]; c11i = x[COH11_IM_D##D];                                             \
       if (!NOISY) ryd = 1.0 - (c11r * c11r + c11i * c11i);                                          \
@@ -512,7 +522,7 @@ RYDCZ_HD void cz_epilogue(bool noisy, double p01, double p10, double p11,
     if (NOISY) {                                                                                    \
       /* single-atom inputs: rho_ab and its |ab><00| coherence share one Chebyshev loop */           \
       double x[Sys_in01_d##D::N]; st = 0.0;                                                         \
-      run_system<Sys_in01_d##D>(x, pt, seg, n_seg, true, st);                                       \
+      run_system<Sys_in01_d##D>(x, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);            \
       steps += st; flops += st * 2.0 * (Sys_in01_d##D::NNZ + Sys_in01_d##D::N);                     \
       p01 = x[RHO01_POP_D##D];                                                                      \
       c01r = x[IN01_COH_OFFSET_D##D + COH01_RE_D##D]; c01i = x[IN01_COH_OFFSET_D##D + COH01_IM_D##D]; \
@@ -521,7 +531,7 @@ RYDCZ_HD void cz_epilogue(bool noisy, double p01, double p10, double p11,
         RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d##D::N; ++i) states[SL::COH01 + i] = x[IN01_COH_OFFSET_D##D + i]; \
       }                                                                                             \
       double y[Sys_in10_d##D::N]; st = 0.0;                                                         \
-      run_system<Sys_in10_d##D>(y, pt, seg, n_seg, true, st);                                       \
+      run_system<Sys_in10_d##D>(y, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);            \
       steps += st; flops += st * 2.0 * (Sys_in10_d##D::NNZ + Sys_in10_d##D::N);                     \
       p10 = y[RHO10_POP_D##D];                                                                      \
       c10r = y[IN10_COH_OFFSET_D##D + COH10_RE_D##D]; c10i = y[IN10_COH_OFFSET_D##D + COH10_IM_D##D]; \
@@ -531,12 +541,12 @@ RYDCZ_HD void cz_epilogue(bool noisy, double p01, double p10, double p11,
       }                                                                                             \
     } else {                                                                                        \
       double x[Sys_coh01_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_coh01_d##D>(x, pt, seg, n_seg, false, st);                                     \
+      run_system<Sys_coh01_d##D>(x, pt, seg, n_seg, false, st); RYDCZ_RECONVERGE(pt.live);          \
       steps += st; flops += st * 2.0 * (Sys_coh01_d##D::NNZ + Sys_coh01_d##D::N);                   \
       c01r = x[COH01_RE_D##D]; c01i = x[COH01_IM_D##D];                                             \
       if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d##D::N; ++i) states[SL::COH01 + i] = x[i]; } \
       double y[Sys_coh10_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_coh10_d##D>(y, pt, seg, n_seg, false, st);                                     \
+      run_system<Sys_coh10_d##D>(y, pt, seg, n_seg, false, st); RYDCZ_RECONVERGE(pt.live);          \
       steps += st; flops += st * 2.0 * (Sys_coh10_d##D::NNZ + Sys_coh10_d##D::N);                   \
       c10r = y[COH10_RE_D##D]; c10i = y[COH10_IM_D##D];                                             \
       if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh10_d##D::N; ++i) states[SL::COH10 + i] = y[i]; } \
@@ -554,7 +564,7 @@ RYDCZ_DEFINE_EVALUATE(4)
 // Same outputs, same `states` layout as the general path.
 #define RYDCZ_DEFINE_EVALUATE_SYM(D)                                                                \
   template <bool NOISY>                                                                             \
-  RYDCZ_HD void evaluate_point_sym_d##D(const PointView pt,                                         \
+  RYDCZ_HD void evaluate_point_sym_d##D(const PointView pt, const Col xcol,                         \
                                         const double* __restrict__ seg, int n_seg,                  \
                                         double* __restrict__ out, double* __restrict__ states) {    \
     typedef StateLayout<D> SL;                                                                      \
@@ -563,7 +573,7 @@ RYDCZ_DEFINE_EVALUATE(4)
     double c01r, c01i, c11r, c11i;                                                                  \
     if (NOISY) {                                                                                    \
       double x[Sys_rho11s_d##D::N]; st = 0.0;                                                       \
-      run_system<Sys_rho11s_d##D>(x, pt, seg, n_seg, true, st);                                     \
+      run_rho11s_d##D(x, xcol, pt, seg, n_seg, st);                                                 \
       steps += st; flops += st * 2.0 * (Sys_rho11s_d##D::NNZ + Sys_rho11s_d##D::N);                 \
       p11 = x[RHO11S_POP_D##D];                                                                     \
       double xf[Sys_rho11s_d##D::FULL_N];                                                           \
@@ -573,7 +583,7 @@ RYDCZ_DEFINE_EVALUATE(4)
     }                                                                                               \
     {                                                                                               \
       double x[Sys_coh11s_d##D::N]; st = 0.0;                                                       \
-      run_system<Sys_coh11s_d##D>(x, pt, seg, n_seg, NOISY, st);                                    \
+      run_system<Sys_coh11s_d##D>(x, pt, seg, n_seg, NOISY, st); RYDCZ_RECONVERGE(pt.live);         \
       steps += st; flops += st * 2.0 * (Sys_coh11s_d##D::NNZ + Sys_coh11s_d##D::N);                 \
       c11r = x[COH11S_RE_D##D]; c11i = x[COH11S_IM_D##D];                                           \
       if (!NOISY) ryd = 1.0 - (c11r * c11r + c11i * c11i);                                          \
@@ -585,7 +595,7 @@ RYDCZ_DEFINE_EVALUATE(4)
     }                                                                                               \
     if (NOISY) {                                                                                    \
       double x[Sys_in01_d##D::N]; st = 0.0;                                                         \
-      run_system<Sys_in01_d##D>(x, pt, seg, n_seg, true, st);                                       \
+      run_system<Sys_in01_d##D>(x, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);            \
       steps += st; flops += st * 2.0 * (Sys_in01_d##D::NNZ + Sys_in01_d##D::N);                     \
       p01 = x[RHO01_POP_D##D];                                                                      \
       c01r = x[IN01_COH_OFFSET_D##D + COH01_RE_D##D]; c01i = x[IN01_COH_OFFSET_D##D + COH01_IM_D##D]; \
@@ -597,7 +607,7 @@ RYDCZ_DEFINE_EVALUATE(4)
       }                                                                                             \
     } else {                                                                                        \
       double x[Sys_coh01_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_coh01_d##D>(x, pt, seg, n_seg, false, st);                                     \
+      run_system<Sys_coh01_d##D>(x, pt, seg, n_seg, false, st); RYDCZ_RECONVERGE(pt.live);          \
       steps += st; flops += st * 2.0 * (Sys_coh01_d##D::NNZ + Sys_coh01_d##D::N);                   \
       c01r = x[COH01_RE_D##D]; c01i = x[COH01_IM_D##D];                                             \
       if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d##D::N; ++i) {                      \
@@ -607,6 +617,29 @@ RYDCZ_DEFINE_EVALUATE(4)
     out[OUT_LOSS] = loss; out[OUT_RYD] = ryd; out[OUT_STEPS] = steps; out[OUT_FLOPS] = flops;       \
   }
 
+// rho_11 of the folded 3-level model.  RYDCZ_D3_VARIANT: 0 = everything in registers (run_system),
+// 1 = coefficients in the shared-memory column, 2 = start vector in the shared-memory column.
+#ifndef RYDCZ_D3_VARIANT
+#define RYDCZ_D3_VARIANT 0
+#endif
+RYDCZ_HD void run_rho11s_d3(double (&x)[Sys_rho11s_d3::N], const Col col, const PointView pt,
+                            const double* __restrict__ seg, int n_seg, double& st) {
+#if RYDCZ_D3_VARIANT == 1
+  run_system_big<Sys_rho11s_d3, double*, Col>(x, col, pt, seg, n_seg, true, st);
+#elif RYDCZ_D3_VARIANT == 2
+  double c[Sys_rho11s_d3::NC];
+  run_system_big<Sys_rho11s_d3, Col, double*>(col, c, pt, seg, n_seg, true, st);
+  RYDCZ_UNROLL for (int i = 0; i < Sys_rho11s_d3::N; ++i) x[i] = col[i];
+#else
+  run_system<Sys_rho11s_d3>(x, pt, seg, n_seg, true, st);
+#endif
+  RYDCZ_RECONVERGE(pt.live);
+}
+RYDCZ_HD void run_rho11s_d4(double (&x)[Sys_rho11s_d4::N], const Col, const PointView pt,
+                            const double* __restrict__ seg, int n_seg, double& st) {
+  run_system<Sys_rho11s_d4>(x, pt, seg, n_seg, true, st);
+  RYDCZ_RECONVERGE(pt.live);
+}
 RYDCZ_DEFINE_EVALUATE_SYM(3)
 RYDCZ_DEFINE_EVALUATE_SYM(4)
 
@@ -622,7 +655,8 @@ RYDCZ_HD void evaluate_point_sym_d5(const PointView pt, const Col xcol, const Co
   double c01r, c01i, c11r, c11i;
   if (NOISY) {
     st = 0.0;
-    run_system_big<Sys_rho11s_d5>(xcol, ccol, pt, seg, n_seg, true, st);
+    run_system_big<Sys_rho11s_d5, Col, Col>(xcol, ccol, pt, seg, n_seg, true, st);
+    RYDCZ_RECONVERGE(pt.live);
     steps += st; flops += st * 2.0 * (Sys_rho11s_d5::NNZ + Sys_rho11s_d5::N);
     double x[Sys_rho11s_d5::N];
     RYDCZ_UNROLL for (int i = 0; i < Sys_rho11s_d5::N; ++i) x[i] = xcol[i];
@@ -635,6 +669,7 @@ RYDCZ_HD void evaluate_point_sym_d5(const PointView pt, const Col xcol, const Co
   {
     double x[Sys_coh11s_d5::N]; st = 0.0;
     run_system<Sys_coh11s_d5>(x, pt, seg, n_seg, NOISY, st);
+    RYDCZ_RECONVERGE(pt.live);
     steps += st; flops += st * 2.0 * (Sys_coh11s_d5::NNZ + Sys_coh11s_d5::N);
     c11r = x[COH11S_RE_D5]; c11i = x[COH11S_IM_D5];
     if (!NOISY) {
@@ -651,6 +686,7 @@ RYDCZ_HD void evaluate_point_sym_d5(const PointView pt, const Col xcol, const Co
   if (NOISY) {
     double x[Sys_in01_d5::N]; st = 0.0;
     run_system<Sys_in01_d5>(x, pt, seg, n_seg, true, st);
+    RYDCZ_RECONVERGE(pt.live);
     steps += st; flops += st * 2.0 * (Sys_in01_d5::NNZ + Sys_in01_d5::N);
     p01 = x[RHO01_POP_D5];
     c01r = x[IN01_COH_OFFSET_D5 + COH01_RE_D5]; c01i = x[IN01_COH_OFFSET_D5 + COH01_IM_D5];
@@ -663,6 +699,7 @@ RYDCZ_HD void evaluate_point_sym_d5(const PointView pt, const Col xcol, const Co
   } else {
     double x[Sys_coh01_d5::N]; st = 0.0;
     run_system<Sys_coh01_d5>(x, pt, seg, n_seg, false, st);
+    RYDCZ_RECONVERGE(pt.live);
     steps += st; flops += st * 2.0 * (Sys_coh01_d5::NNZ + Sys_coh01_d5::N);
     c01r = x[COH01_RE_D5]; c01i = x[COH01_IM_D5];
     if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d5::N; ++i) {

@@ -25,14 +25,16 @@ extern "C" int hostsim_evaluate(int dim, int noisy, long long n_points, const do
     const bool sym = g_allow_sym && pt[PT_OFF_A] == pt[PT_OFF_B];
     if (dim == 3) {
       double* st = states ? states + i * StateLayout<3>::STRIDE : nullptr;
-      if (sym) { if (noisy) evaluate_point_sym_d3<true>(pt, sg, n_seg[i], o, st);
-                 else evaluate_point_sym_d3<false>(pt, sg, n_seg[i], o, st); }
+      double cc[Sys_rho11s_d3::NC];
+      if (sym) { if (noisy) evaluate_point_sym_d3<true>(pt, Col{cc, 1}, sg, n_seg[i], o, st);
+                 else evaluate_point_sym_d3<false>(pt, Col{cc, 1}, sg, n_seg[i], o, st); }
       else if (noisy) evaluate_point_d3<true>(pt, sg, n_seg[i], o, st);
       else evaluate_point_d3<false>(pt, sg, n_seg[i], o, st);
     } else if (dim == 4) {
       double* st = states ? states + i * StateLayout<4>::STRIDE : nullptr;
-      if (sym) { if (noisy) evaluate_point_sym_d4<true>(pt, sg, n_seg[i], o, st);
-                 else evaluate_point_sym_d4<false>(pt, sg, n_seg[i], o, st); }
+      double cc[Sys_rho11s_d4::NC];
+      if (sym) { if (noisy) evaluate_point_sym_d4<true>(pt, Col{cc, 1}, sg, n_seg[i], o, st);
+                 else evaluate_point_sym_d4<false>(pt, Col{cc, 1}, sg, n_seg[i], o, st); }
       else if (noisy) evaluate_point_d4<true>(pt, sg, n_seg[i], o, st);
       else evaluate_point_d4<false>(pt, sg, n_seg[i], o, st);
     } else if (dim == 5) {
