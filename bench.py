@@ -140,6 +140,16 @@ def _cpu_one(args):
     return avg
 
 
+def _cpu_one_expm(args):
+    """The same evaluation with the oracle's exact matrix exponentials (what the kernel is checked against)."""
+    from oracle import rydcz_oracle as orc
+    pt, seg = args
+    rates = orc.NoiseRates(gamma_r=2 * pt[4], gamma_bbr=pt[5] - pt[4], gamma_phi_laser=pt[6],
+                           gamma_scatter_intermediate=pt[7])
+    segs = [orc.Segment(s[0], complex(s[1], s[2]), s[3], 51) for s in seg if s[0] >= 1e-18]
+    return orc.evaluate(3, segs, pt[0], pt[1], rates, "exact", "coherence")[1]
+
+
 def cpu_path_rate(pts, segs, n_sample, procs):
     """Evaluate the first n_sample candidates with the oracle's zvode restatement on `procs`
     host processes; returns evals/s."""
@@ -290,9 +300,17 @@ def run_ours(args, rank, world, local_rank):
             n_sample = max(2 * cores, 8)
             pts, segs = host_plan(cand, np.arange(n_sample))
             rate, dt = cpu_path_rate(pts, segs, n_sample, cores)
+            t0 = time.perf_counter()
+            for i in range(4):                      # the exact-expm oracle, one process
+                _cpu_one_expm((pts[i], segs[i]))
+            expm_rate = 4 / (time.perf_counter() - t0)
             cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"first {n_sample} of the {B_PER_GPU} candidates ({dt:.1f} s), oracle zvode/Adams "
-                             f"restatement of the reference's mesolve path, {cores} processes"}
+                             f"restatement of the reference's mesolve path, {cores} processes",
+                   "expm_oracle_evals_per_s_1core": expm_rate,
+                   # Runtime lines saved in the reference's notebooks (author's Mac, one process)
+                   "reference_notebook_evals_per_s": {"lp_noiseless": 123, "smooth_jp_noiseless": 5.4,
+                                                      "lp_noisy_older_notebook": 59, "jp_noisy_older_notebook": 25}}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,

@@ -45,10 +45,17 @@ def grid(values, points):
     return np.geomspace(values[0], values[-1], points)
 
 
-def run(proto, B, n_shots, **kw):
+CAL_DIR = None
+
+
+def run(proto, B, n_shots, sweep=None, **kw):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         r = rg.simulate_CZ_gate_batch(proto, B=B, n_shots=n_shots, seed=1234, warn=False, **kw)
+    if CAL_DIR and sweep:
+        from noisyquantumsimulator_b200.rydberg_gates.calibration import write_cz_calibration
+        write_cz_calibration(CAL_DIR, r, {sweep[0]: sweep[1]}, protocol=proto, n_rydberg=kw["n_rydberg"],
+                             species=kw["species"], tag=sweep[0], n_shots=n_shots)
     return dict(fidelity=r.avg_fidelity.tolist(), gate_time_us=r.gate_time_us.tolist(),
                 V_over_Omega=r.V_over_Omega.tolist(), loss=r.loss_probability.tolist())
 
@@ -58,12 +65,17 @@ def main():
     ap.add_argument("--points", type=int, default=None, help="points per sweep (default: the reference's grids)")
     ap.add_argument("--shots", type=int, default=0, help="Monte-Carlo shots per point (0 = analytic dephasing rates)")
     ap.add_argument("--out", default=None)
+    ap.add_argument("--calibration-dir", default=None,
+                    help="also write calibration_data-style JSON files (reference: calibration_data/README.md)")
     a = ap.parse_args()
+    global CAL_DIR
+    CAL_DIR = a.calibration_dir
     results, t0, n_eval = {}, time.perf_counter(), 0
     for name, (keys, values, scale) in SWEEPS.items():
         g = grid(values, a.points)
         kw = dict(FIXED, **{k: g * scale for k in keys})
-        results[name] = dict(values=g.tolist(), lp=run("lp", len(g), a.shots, **kw), jp=run("jp", len(g), a.shots, **kw))
+        results[name] = dict(values=g.tolist(), lp=run("lp", len(g), a.shots, (name, g), **kw),
+                             jp=run("jp", len(g), a.shots, (name, g), **kw))
         n_eval += 2 * len(g)
     by_n = dict(values=N_VALUES, lp=[], jp=[])
     for n in N_VALUES:

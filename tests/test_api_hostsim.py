@@ -171,3 +171,25 @@ def test_batched_differential_evolution_improves_lp(rg):
     assert res.fun < start and res.fun < 0.05
     # the reference's own DE found cost 0.0044 at (0.369547, 4.215360) for this apparatus (cell 10)
     assert abs(f(np.array([0.369547, 4.215360])) - 0.0044) < 2e-4
+
+
+def test_calibration_file_round_trip(tmp_path, monkeypatch):
+    """calibration_data/neutral_atoms/rydberg_cz/n70_*.json as the reference's calibration_data/README.md
+    describes it: parameters, error rates, gate durations, metadata."""
+    from noisyquantumsimulator_b200 import engine
+    from noisyquantumsimulator_b200 import rydberg_gates as rg
+    from noisyquantumsimulator_b200.rydberg_gates import calibration as cal
+    monkeypatch.setitem(engine._default, 0, C.HostsimEvaluator())
+    p2 = np.geomspace(0.1, 1.0, 5)
+    res = rg.simulate_CZ_gate_batch("lp", B=5, laser_1_power=50e-6, laser_1_waist=50e-6, laser_2_power=p2,
+                                    laser_2_waist=50e-6, Delta_e=2 * np.pi * 1e9, tweezer_power=0.02,
+                                    tweezer_waist=0.8e-6, warn=False, prologue="host")
+    path = cal.write_cz_calibration(str(tmp_path), res, {"laser_2_power_W": p2, "temperature_K": 2e-6},
+                                    protocol="lp", n_rydberg=70, tag="power")
+    assert path.endswith("neutral_atoms/rydberg_cz/n70_lp_power.json")
+    doc = cal.load_cz_calibration(path)
+    assert doc["metadata"]["n_points"] == 5 and doc["metadata"]["species"] == "Rb87"
+    assert np.allclose(doc["arrays"]["gate_infidelity"], 1 - res.avg_fidelity)
+    assert np.allclose(doc["arrays"]["gate_duration_s"], res.tau_total)
+    assert doc["records"][2]["parameters"] == {"laser_2_power_W": float(p2[2]), "temperature_K": 2e-6}
+    assert set(doc["records"][0]["error_rates"]["infidelity_by_input"]) == {"00", "01", "10", "11"}

@@ -61,12 +61,18 @@ for nseg, ot_b in ((5, (5.0, 40.0)), (7, (3.0, 30.0))):
         dt, res = timed(lambda: rg.simulate_CZ_gate_batch("jp", B=B, warn=False, copy=False, **kw))
         line(f"config2_bb{nseg}_65536_{'noisy' if noise else 'noiseless'}", B, dt, res)
 
-# config 3: 16x16x16 sweep (power x delta/omega x omega*tau), atom temperature 10 uK, 64 shots/point
+# config 3: 16x16x16 sweep, 64 shots/point.  BASELINE.json's "Omega x Delta x T" does not say whether T is the pulse
+# area or the atom temperature: both readings are run.
 p2g, dg, og = np.meshgrid(np.geomspace(0.05, 2.0, 16), np.linspace(0.20, 0.50, 16), np.linspace(3.5, 5.5, 16),
                           indexing="ij")
 kw = dict(M, laser_2_power=p2g.ravel(), delta_over_omega=dg.ravel(), omega_tau=og.ravel(), temperature=10e-6)
 dt, res = timed(lambda: rg.simulate_CZ_gate_batch("lp", B=4096, n_shots=64, seed=1234, warn=False, copy=False, **kw), 3)
-line("config3_sweep_4096pts_x64shots", 4096 * 64, dt, res, dict(shots=64, points=4096))
+line("config3_sweep_4096pts_x64shots_T_is_pulse_area", 4096 * 64, dt, res, dict(shots=64, points=4096))
+temps = np.array([2, 5, 10, 20, 50, 100]) * 1e-6
+p2t, dgt, tt = np.meshgrid(np.geomspace(0.05, 2.0, 26), np.linspace(0.20, 0.50, 26), temps, indexing="ij")
+kw = dict(M, laser_2_power=p2t.ravel(), delta_over_omega=dgt.ravel(), temperature=tt.ravel())
+dt, res = timed(lambda: rg.simulate_CZ_gate_batch("lp", B=p2t.size, n_shots=64, seed=1234, warn=False, copy=False, **kw), 3)
+line("config3_sweep_4056pts_x64shots_T_is_temperature", p2t.size * 64, dt, res, dict(shots=64, points=int(p2t.size)))
 
 # config 4: optimiser population of 8192 candidates per iteration (one GPU evaluates all of them here;
 # bench.py --gpus N shards populations across GPUs)
