@@ -206,10 +206,12 @@ __global__ void prologue_kernel(ModelArg md, int64_t n_points, const double* __r
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_points) return;
   const int S = (int)md.v[MD_NSEG];
-  double pt[PT_STRIDE], sc[SC_STRIDE];
+  const int stride = (int)md.v[MD_DIM] == 5 ? (int)PT5_STRIDE : (int)PT_STRIDE;
+  double pt[PT5_STRIDE], sc[SC_STRIDE];
   const int ns = prologue_point(md.v, AppView{app + i, app_stride}, pt, segs + i * (int64_t)S * SG_STRIDE, sc);
 #pragma unroll
-  for (int k = 0; k < PT_STRIDE; ++k) points[i * PT_STRIDE + k] = pt[k];
+  for (int k = 0; k < PT5_STRIDE; ++k)
+    if (k < stride) points[i * stride + k] = pt[k];
   n_seg[i] = ns;
   if (scalars) {
 #pragma unroll
@@ -680,7 +682,7 @@ static int check_model(rydcz_ctx* ctx, const double* m) {
   if (!ctx) return 2;
   if (!m) return fail(ctx, "null model");
   const int dim = (int)m[MD_DIM], proto = (int)m[MD_PROTOCOL], S = (int)m[MD_NSEG];
-  if (dim != 3 && dim != 4) return fail(ctx, "model: dim must be 3 or 4 (the device prologue does not cover dim 5)");
+  if (dim != 3 && dim != 4 && dim != 5) return fail(ctx, "model: dim must be 3, 4 or 5");
   if (proto < 0 || proto > 2) return fail(ctx, "model: protocol must be 0 (lp), 1 (jp) or 2 (sjp)");
   if (S < 1 || (proto == 0 && S != 2)) return fail(ctx, "model: bad segment count");
   if (proto == 1 && 2 * S > APP_STRIDE - APP_PROTO) return fail(ctx, "model: too many bang-bang segments");
@@ -718,13 +720,15 @@ int rydcz_simulate_device(rydcz_ctx* ctx, const double* h_model, int64_t n_point
   if (!d_app || !d_out) return fail(ctx, "null buffer");
   const int dim = (int)h_model[MD_DIM], S = (int)h_model[MD_NSEG], noisy = h_model[MD_INCLUDE_NOISE] != 0;
   const size_t n = (size_t)n_points;
+  if (dim == 5 && n_shots > 0) return fail(ctx, "Monte-Carlo shots are not available for dim 5");
   // evaluator inputs live in context scratch (slots 0..2 are shared with the *_host entry points)
-  if (grow(ctx, &ctx->plan[0], &ctx->plan_cap[0], n * PT_STRIDE * sizeof(double))) return 1;
+  if (grow(ctx, &ctx->plan[0], &ctx->plan_cap[0], n * rydcz_point_stride_dim(dim) * sizeof(double))) return 1;
   if (grow(ctx, &ctx->plan[1], &ctx->plan_cap[1], n * S * SG_STRIDE * sizeof(double))) return 1;
   if (grow(ctx, &ctx->plan[2], &ctx->plan_cap[2], n * sizeof(int32_t))) return 1;
   int rc = rydcz_prologue_device(ctx, h_model, n_points, d_app, (double*)ctx->plan[0], (double*)ctx->plan[1],
                                  (int32_t*)ctx->plan[2], d_scalars, stream);
   if (rc) return rc;
+  if (n_points > 0x7fffffffLL) return fail(ctx, "n_points out of range");
   if (n_shots > 0)
     return rydcz_evaluate_shots_device(ctx, dim, noisy, n_points, n_shots, seed, (const double*)ctx->plan[0],
                                        (const double*)ctx->plan[1], (const int32_t*)ctx->plan[2], S, d_out,
@@ -782,6 +786,8 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
   if (n_points * (int64_t)(n_shots > 0 ? n_shots : 1) > 0x7fffffffLL) return fail(ctx, "n_points * n_shots too large");
   CK(cudaSetDevice(ctx->device));
   const int dim = (int)h_model[MD_DIM], S = (int)h_model[MD_NSEG], noisy = h_model[MD_INCLUDE_NOISE] != 0;
+  if (dim == 5 && n_shots > 0) return fail(ctx, "Monte-Carlo shots are not available for dim 5");
+  const int pstride = rydcz_point_stride_dim(dim);
   const size_t n = (size_t)n_points;
   const size_t sb = (size_t)rydcz_state_stride(dim) * sizeof(double);
   // varying / constant slots
@@ -804,7 +810,7 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
   if (h_scalars && grow(ctx, &ctx->stage[1], &ctx->stage_cap[1], n * SC_STRIDE * sizeof(double))) return 1;
   if (h_states && grow(ctx, &ctx->stage[4], &ctx->stage_cap[4], n * sb)) return 1;
   if (n_shots > 0 && grow(ctx, &ctx->stage[5], &ctx->stage_cap[5], n * n_shots * OUT_STRIDE * sizeof(double))) return 1;
-  if (grow(ctx, &ctx->plan[0], &ctx->plan_cap[0], n * PT_STRIDE * sizeof(double))) return 1;
+  if (grow(ctx, &ctx->plan[0], &ctx->plan_cap[0], n * pstride * sizeof(double))) return 1;
   if (grow(ctx, &ctx->plan[1], &ctx->plan_cap[1], n * S * SG_STRIDE * sizeof(double))) return 1;
   if (grow(ctx, &ctx->plan[2], &ctx->plan_cap[2], n * sizeof(int32_t))) return 1;
   if (order_reserve(ctx, n_points)) return 1;
@@ -852,18 +858,18 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
       ctx->launches++;
     }
     double* c_sc = d_sc ? d_sc + i0 * SC_STRIDE : nullptr;
-    if (prologue_impl(ctx, h_model, nc, d_app + i0, n_points, d_pts + i0 * PT_STRIDE,
+    if (prologue_impl(ctx, h_model, nc, d_app + i0, n_points, d_pts + i0 * pstride,
                       d_segs + i0 * (int64_t)S * SG_STRIDE, d_ns + i0, c_sc, st)) return 1;
     SortScratch sc = context_scratch(ctx, i0);
     sc.tmp = &L.cub_tmp; sc.tmp_cap = &L.cub_cap;
     const int mark = (c == 0 ? 1 : 0) | (c == n_chunks - 1 ? 2 : 0);
     int rc;
     if (n_shots > 0)
-      rc = shots_impl(ctx, sc, dim, noisy, nc, n_shots, seed, i0, d_pts + i0 * PT_STRIDE,
+      rc = shots_impl(ctx, sc, dim, noisy, nc, n_shots, seed, i0, d_pts + i0 * pstride,
                       d_segs + i0 * (int64_t)S * SG_STRIDE, d_ns + i0, S, d_out + i0 * OUT_STRIDE,
                       d_shots + i0 * n_shots * OUT_STRIDE, st, mark);
     else
-      rc = evaluate_impl(ctx, sc, dim, noisy, nc, d_pts + i0 * PT_STRIDE, d_segs + i0 * (int64_t)S * SG_STRIDE,
+      rc = evaluate_impl(ctx, sc, dim, noisy, nc, d_pts + i0 * pstride, d_segs + i0 * (int64_t)S * SG_STRIDE,
                          d_ns + i0, S, d_out + i0 * OUT_STRIDE, d_st ? d_st + i0 * (sb / sizeof(double)) : nullptr,
                          st, mark);
     if (rc) return rc;

@@ -44,6 +44,8 @@ enum ModelSlot {
   MD_ZEEMAN_K = 21 /* clock: Hz/G^2 */, MD_ZEEMAN_LIN = 22 /* non-clock: rad/s per T */,
   MD_STARK_HZ_PER_MK = 23, MD_STARK_ALT = 24 /* Hz per (W/m^2) */, MD_K_EFF = 25, MD_DELTA_LEAK = 26,
   MD_RYD_ZEEMAN_PER_T = 27, MD_BG_DEFAULT = 28,
+  MD_E_BRANCH_1 = 29 /* dim 5: fraction of |e> decays that return to |1> */,
+  MD_LS_COMP = 30 /* dim 5: 1 = light shifts compensated */,
   MD_STRIDE = 32
 };
 
@@ -131,8 +133,8 @@ RYDCZ_HD double leakage_rate(double Omega, double Dleak, int shape, double tau, 
   return (f * f) * gamma_r * S;
 }
 
-// One point: apparatus row -> evaluator point row, segment rows, reported scalars.
-// `seg` must have room for MD_NSEG rows.  Returns the number of segments.
+// One point: apparatus row -> evaluator point row (PT_STRIDE doubles; PT5_STRIDE for dim 5), segment
+// rows, reported scalars.  `seg` must have room for MD_NSEG rows.  Returns the number of segments.
 // The apparatus block is slot-major: slot k of point i is app_base[k * n_points + i] (contiguous
 // columns: cheap to fill on the host, coalesced on the device); `app` below is &app_base[i].
 struct AppView {
@@ -228,7 +230,7 @@ RYDCZ_HD int prologue_point(const double* __restrict__ md, const AppView app,
     }
   }
   // rates (RG/simulation.py:3230-3334)
-  double r5[5] = {0, 0, 0, 0, 0};
+  double r5[7] = {0, 0, 0, 0, 0, 0, 0};   // [5], [6]: dim 5 split of the |r> loss channels (-> |0>, -> |l>)
   if (md[MD_INCLUDE_NOISE] != 0) {
     const double g_phi_laser = PI * lw;
     const double g_bg = (app[APP_BG_LOSS] == app[APP_BG_LOSS]) ? app[APP_BG_LOSS] : md[MD_BG_DEFAULT];
@@ -249,12 +251,27 @@ RYDCZ_HD int prologue_point(const double* __restrict__ md, const AppView app,
     r5[2] = g_phi_laser + g_th_total + g_zee;
     r5[3] = g_scatter;
     r5[4] = g_mj;
+    r5[5] = gamma_r * (1 - 0.5) + 0.0;
+    r5[6] = g_anti + g_bg + g_leak;
   }
   pt[PT_V] = V; pt[PT_DELTA1] = d_zee + d_stark; pt[PT_OFF_A] = 0.0; pt[PT_OFF_B] = 0.0;
   pt[PT_G_R1] = r5[0]; pt[PT_G_R0] = r5[1]; pt[PT_G_PHI] = r5[2]; pt[PT_G_SC] = r5[3]; pt[PT_G_MJ] = r5[4];
   pt[PT_SIG_DET] = k_eff * v_rms;
   pt[PT_SIG_RELR] = sqrt(2.0) * sigma_r / R;
   pt[PT_RESERVED] = 0.0;
+  if (dim == 5) {
+    // the intermediate state is explicit: scattering is the decay of |e>, loss
+    // channels that remove the atom end in |l>
+    const bool noisy5 = md[MD_INCLUDE_NOISE] != 0;
+    pt[PT_G_SC] = 0.0;
+    pt[PT5_OM1] = Om1; pt[PT5_DET_E] = De;
+    pt[PT5_G_E1] = noisy5 ? Ge * md[MD_E_BRANCH_1] : 0.0;
+    pt[PT5_G_E0] = noisy5 ? Ge * (1.0 - md[MD_E_BRANCH_1]) : 0.0;
+    pt[PT_G_R0] = r5[5];
+    pt[PT5_G_RL] = r5[6];
+    pt[PT5_LS_COMP] = md[MD_LS_COMP];
+    pt[18] = 0.0; pt[19] = 0.0;
+  }
   sc[SC_OMEGA] = Om; sc[SC_V] = V; sc[SC_TAU_TOTAL] = tau_total; sc[SC_TAU_SINGLE] = tau_single;
   sc[SC_DELTA] = Delta_gate; sc[SC_XI_RE] = xi_re; sc[SC_XI_IM] = xi_im; sc[SC_OMEGA_TAU] = o_t;
   // pulse schedule

@@ -28,7 +28,8 @@ def model_constants(protocol: str, *, config: AtomicConfiguration = None, specie
                     qubit_0=(1, 0), qubit_1=(2, 0), hilbert_space_dim=3, include_noise=True,
                     include_motional_dephasing=True, include_doppler_dephasing=True,
                     include_intensity_noise=True, counter_propagating=True, trap_laser_on=True,
-                    n_segments: int = None, n_smooth_steps: int = 300) -> np.ndarray:
+                    n_segments: int = None, n_smooth_steps: int = 300, intermediate_branching_1: float = 0.5,
+                    light_shift_compensation: bool = True) -> np.ndarray:
     if config is None:
         config = AtomicConfiguration(species=species, qubit_0=qubit_0, qubit_1=qubit_1, n_rydberg=n_rydberg,
                                      L_rydberg="S")
@@ -66,6 +67,8 @@ def model_constants(protocol: str, *, config: AtomicConfiguration = None, specie
     m[26] = compute_leakage_detuning(config.species, n)
     m[27] = rydberg_zeeman_splitting(1.0, L=0, J=0.5)
     m[28] = 1e3
+    m[29] = intermediate_branching_1          # dim 5 only
+    m[30] = 1.0 if light_shift_compensation else 0.0
     return m
 
 
@@ -137,7 +140,8 @@ def split_kwargs(kwargs: Dict):
     """Separate build_plan-style keywords into (model keywords, apparatus keywords)."""
     model_keys = {"config", "species", "n_rydberg", "qubit_0", "qubit_1", "hilbert_space_dim", "include_noise",
                   "include_motional_dephasing", "include_doppler_dephasing", "include_intensity_noise",
-                  "counter_propagating", "trap_laser_on", "n_smooth_steps"}
+                  "counter_propagating", "trap_laser_on", "n_smooth_steps", "intermediate_branching_1",
+                  "light_shift_compensation"}
     ignored = {"polarization_1", "polarization_2", "warn", "pulse_shape"}
     mk = {k: v for k, v in kwargs.items() if k in model_keys}
     ak = {k: v for k, v in kwargs.items() if k not in model_keys and k not in ignored}

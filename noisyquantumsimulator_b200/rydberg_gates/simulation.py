@@ -552,7 +552,7 @@ def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, se
     if five and n_shots > 0:
         raise ValueError("Monte-Carlo shots are not available for hilbert_space_dim=5")
     if prologue == "auto":
-        prologue = "host" if (plan is not None or shaped or return_shots or five) else "device"
+        prologue = "host" if (plan is not None or shaped or return_shots) else "device"
     if B is None and plan is None:
         B = max([np.size(v) for v in kwargs.values() if isinstance(v, np.ndarray) and v.ndim >= 1
                  and np.shape(v)[0] > 1] or [1])
@@ -562,8 +562,8 @@ def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, se
     ev = get_evaluator(device)
     states = shots = None
     if prologue == "device":
-        if shaped or five:
-            raise ValueError("shaped LP pulses and hilbert_space_dim=5 need prologue='host'")
+        if shaped:
+            raise ValueError("shaped LP pulses need prologue='host'")
         if protocol not in PROTOCOL_NAMES:
             raise ValueError(f"Unknown protocol: {protocol}")
         mk, ak = dpro.split_kwargs(kwargs)

@@ -184,7 +184,7 @@ def hostsim_prologue(model, app):
     app = np.ascontiguousarray(app, dtype=np.float64)
     assert app.shape[0] == 40, "apparatus block is slot-major [40, B]"
     B, S = app.shape[1], int(model[2])
-    pts, segs = np.zeros((B, PT_STRIDE)), np.zeros((B, S, SG_STRIDE))
+    pts, segs = np.zeros((B, 20 if int(model[0]) == 5 else PT_STRIDE)), np.zeros((B, S, SG_STRIDE))
     ns, sc = np.zeros(B, dtype=np.int32), np.zeros((B, 8))
     rc = lib.hostsim_prologue(model.ctypes.data_as(dp), B, app.ctypes.data_as(dp), pts.ctypes.data_as(dp),
                               segs.ctypes.data_as(dp), ns.ctypes.data_as(Ct.POINTER(Ct.c_int)),

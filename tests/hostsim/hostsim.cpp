@@ -53,8 +53,12 @@ extern "C" int hostsim_prologue(const double* model, long long n_points, const d
                                 double* segs, int* n_seg, double* scalars) {
   using namespace rydcz;
   const int S = (int)model[MD_NSEG];
-  for (long long i = 0; i < n_points; ++i)
-    n_seg[i] = prologue_point(model, AppView{app + i, n_points}, points + i * PT_STRIDE,
-                              segs + i * (long long)S * SG_STRIDE, scalars + i * SC_STRIDE);
+  const int stride = (int)model[MD_DIM] == 5 ? (int)PT5_STRIDE : (int)PT_STRIDE;   // rows as the C ABI lays them out
+  for (long long i = 0; i < n_points; ++i) {
+    double pt[PT5_STRIDE];
+    n_seg[i] = prologue_point(model, AppView{app + i, n_points}, pt, segs + i * (long long)S * SG_STRIDE,
+                              scalars + i * SC_STRIDE);
+    for (int k = 0; k < stride; ++k) points[i * stride + k] = pt[k];
+  }
   return 0;
 }

@@ -55,3 +55,25 @@ def test_batch_rows_with_arrays():
     pts, segs, ns, sc = C.hostsim_prologue(dp.model_constants("jp", n_segments=5, **mk), dp.pack_apparatus("jp", B, **ak))
     assert _close(pts, plan.points)
     assert (np.abs(segs - plan.segs) / (np.abs(plan.segs).max((0, 1)) + 1e-300)).max() < 5e-12
+
+
+@pytest.mark.parametrize("proto", ["lp", "jp", "sjp"])
+@pytest.mark.parametrize("noise", [True, False])
+def test_dim5_rows(proto, noise):
+    """hilbert_space_dim=5: the 20-double rows (Omega_1, Delta_e, |e> decay split, |r> loss split, light-shift flag)."""
+    rng = np.random.default_rng(9)
+    B = 33
+    kw = dict(laser_1_power=50e-6, laser_1_waist=50e-6, laser_2_power=10 ** rng.uniform(-1.3, 0.3, B),
+              laser_2_waist=50e-6, Delta_e=2 * np.pi * rng.uniform(0.8e9, 5e9, B), tweezer_power=0.02,
+              tweezer_waist=0.8e-6, temperature=rng.uniform(1e-6, 5e-5, B), spacing_factor=rng.uniform(2.0, 6.0, B),
+              hilbert_space_dim=5, include_noise=noise, intermediate_branching_1=0.3, species="Cs133",
+              light_shift_compensation=bool(noise))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        plan = prologue.build_plan(proto, B=B, warn=False, **kw)
+    assert plan.points.shape == (B, 20)
+    mk, ak = dp.split_kwargs(kw)
+    model = dp.model_constants(proto, n_segments=plan.segs.shape[1], **mk)
+    pts, segs, ns, sc = C.hostsim_prologue(model, dp.pack_apparatus(proto, B, **ak))
+    assert pts.shape == (B, 20) and _close(pts, plan.points, 5e-12)
+    assert (np.abs(segs - plan.segs) / (np.abs(plan.segs).max((0, 1)) + 1e-300)).max() < 5e-12

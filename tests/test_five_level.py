@@ -103,7 +103,7 @@ def test_public_api_dim5_on_host_harness(monkeypatch):
     assert abs(cs.avg_fidelity - exp["avg_fidelity"]) < 1e-10
     pure = rg.simulate_CZ_gate(inp, hilbert_space_dim=5, include_noise=False, **kw)
     assert pure.results["11"].shape == (25,) and abs(np.linalg.norm(pure.results["11"]) - 1) < 1e-11
-    # batch API, host prologue (the device prologue does not cover dim 5)
+    # batch API (device prologue by default)
     b = rg.simulate_CZ_gate_batch("lp", B=3, hilbert_space_dim=5, laser_1_power=50e-6, laser_1_waist=50e-6,
                                   laser_2_power=np.array([0.1, 0.3, 1.0]), laser_2_waist=50e-6,
                                   Delta_e=2 * np.pi * 1e9, warn=False, **kw)

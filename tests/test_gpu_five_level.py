@@ -98,3 +98,27 @@ def test_public_api_rb_vs_cs(evaluator):
         exp = next(c for c in CASES if c["name"] == name)["expected"]
         assert abs(res.avg_fidelity - exp["avg_fidelity"]) < 1e-9
         assert res.results["11"].shape == (25, 25)
+
+
+@pytest.mark.parametrize("proto", ["lp", "jp"])
+def test_batch_device_prologue_equals_host_prologue_dim5(proto):
+    """The pipelined column entry with prologue_kernel writing 20-double rows against the NumPy prologue +
+    rydcz_evaluate_host, for the 5-level model."""
+    from noisyquantumsimulator_b200 import rydberg_gates as rg
+    from noisyquantumsimulator_b200.engine import get_evaluator
+    rng = np.random.default_rng(23)
+    B = 3000
+    kw = dict(laser_1_power=50e-6, laser_1_waist=50e-6, laser_2_power=10 ** rng.uniform(-1.0, 0.3, B),
+              laser_2_waist=50e-6, Delta_e=2 * np.pi * 1e9, tweezer_power=0.02, tweezer_waist=0.8e-6,
+              temperature=rng.uniform(1e-6, 3e-5, B), spacing_factor=rng.uniform(2.5, 5.0, B), warn=False,
+              hilbert_space_dim=5)
+    if proto == "jp":
+        kw.update(omega_tau=rng.uniform(5, 20, B), switching_times=np.sort(rng.uniform(1, 5, (B, 4)), 1),
+                  phases=rng.uniform(-3, 3, (B, 5)))
+    get_evaluator(0).set_chunk(1024)
+    a = rg.simulate_CZ_gate_batch(proto, B=B, prologue="device", return_states=True, **kw)
+    get_evaluator(0).set_chunk(65536)
+    b = rg.simulate_CZ_gate_batch(proto, B=B, prologue="host", return_states=True, **kw)
+    assert a.states.shape == (B, 129)
+    assert np.abs(a.raw[:, :14] - b.raw[:, :14]).max() < 1e-9 and np.abs(a.states - b.states).max() < 1e-9
+    assert np.allclose(a.tau_total, b.tau_total, rtol=1e-13)
