@@ -221,6 +221,13 @@ def run_ours(args, rank, world, local_rank):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     dfma_peak, dmma_peak = ev.fp64_peak()
+    matvec_peak = ev.fp64_matvec_peak()
+    try:     # DRAM traffic of the dominant kernel from the committed ncu capture (scales with the batch)
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tr = json.load(f)
+        traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * B_PER_GPU / tr["candidates"]
+    except Exception:
+        traffic = None
 
     def step():
         # inputs resident in HBM: prologue kernel -> work sort -> evaluate kernels -> score all-gather
@@ -326,14 +333,17 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": launches,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": dfma_peak, "unit": "TFLOP/s",
                          "frac": achieved / dfma_peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this batch size, one
-                         # `ncu --set full` capture (profiles/r01_evaluate_kernel_bb5_262k.txt); scales with B
-                         "traffic": 85.58e6 * B_PER_GPU / 262144,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full`
+                         # capture (profiles/ncu_traffic.json), scaled to this batch size
+                         "traffic": traffic,
                          "algorithmic_bytes": float(B_PER_GPU * (12 * 8 + N_SEG * 32 + 4 + 16 * 8)),
                          "kernel": "rydcz::evaluate_kernel<3,true,false,true>", "kernel_ms": k_ms,
                          "flops_per_launch": flops_per_launch,
                          "peak_source": "DFMA microbenchmark (rydcz_fp64_peak) measured in this run; "
-                                        "MEASURED_PEAKS.json has no FP64 entry", "dmma_peak": dmma_peak},
+                                        "MEASURED_PEAKS.json has no FP64 entry", "dmma_peak": dmma_peak,
+                         # the hot loop's own 78-nonzero matvec run bare at the kernel's occupancy (three
+                         # distinct register operands per DFMA): the ceiling for a loop of this shape
+                         "matvec_mix_peak": matvec_peak, "frac_of_matvec_mix_peak": achieved / matvec_peak},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -170,6 +170,10 @@ int rydcz_last_kernel_ms(rydcz_ctx* ctx, float* ms);    /* device time of the la
 int rydcz_launch_count(const rydcz_ctx* ctx, int64_t* n); /* kernels launched through this context */
 /* register-resident FP64 FMA throughput of this GPU (the roofline denominator), TFLOP/s */
 int rydcz_fp64_peak(rydcz_ctx* ctx, double* dfma_tflops, double* dmma_tflops);
+/* the same pipe driven by the hot loop's own instruction mix (the folded 3-level rho_11 matvec, three
+ * distinct register operands per DFMA, two CTAs of 128 threads per SM): the ceiling for a kernel of
+ * this shape, TFLOP/s */
+int rydcz_fp64_matvec_peak(rydcz_ctx* ctx, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,7 @@ _SIGNATURES = {
     "rydcz_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "rydcz_launch_count": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "rydcz_fp64_peak": (C.c_int, [_vp, _dp, _dp]),
+    "rydcz_fp64_matvec_peak": (C.c_int, [_vp, _dp]),
 }
 
 _lib = None

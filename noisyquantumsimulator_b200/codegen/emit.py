@@ -176,10 +176,12 @@ def emit_system(sysm: model.RealSystem, struct_name: str, cm: bool = False) -> s
     A("  }")
     # apply
     A("  RYDCZ_HD static void apply(const double* __restrict__ c, const double* __restrict__ x, double* __restrict__ y) {")
-    order = os.environ.get("RYDCZ_EMIT_ORDER", "row")
+    order = os.environ.get("RYDCZ_EMIT_ORDER", "col")   # measured on B200: col 19.53 ms, row 19.79, rr 19.80, cm 20.60
     stmts = [(i, j, q, s) for i in range(n) for (j, q, s) in rows.get(i, [])]
     if order == "col":        # walk the source vector: consecutive FMAs hit different accumulators
         stmts.sort(key=lambda t: (t[1], t[0]))
+    elif order == "cm":       # coefficient-major: consecutive FMAs share the coefficient operand
+        stmts.sort(key=lambda t: (t[2], t[0]))
     elif order == "rr":       # round-robin over rows: k-th nonzero of every row, then the (k+1)-th ...
         per = {}
         for t in stmts:

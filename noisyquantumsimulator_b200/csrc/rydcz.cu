@@ -280,6 +280,28 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, 
   out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = c0[0] + c0[1] + c1[0] + c1[1] + c2[0] + c2[1] + c3[0] + c3[1];
 }
 
+// The same FMA pipe driven by the hot loop's own instruction mix: the 78-nonzero matvec of the folded
+// 3-level rho_11 system applied back and forth between two register-resident vectors (18 distinct
+// coefficient registers, 15 + 15 state registers, three distinct 64-bit operands per DFMA), at the
+// evaluate kernel's occupancy.  What a Clenshaw loop of this shape could reach with no recurrence
+// bookkeeping, no segment transitions and no divergence.
+__global__ void __launch_bounds__(kBlock, 2) matvec_peak_kernel(double* out, int iters, double scale) {
+  typedef Sys_rho11s_d3 S;
+  double c[S::NC], b1[S::N], b2[S::N];
+#pragma unroll
+  for (int q = 0; q < S::NC; ++q) c[q] = scale * (1.0 + 0.01 * q);
+#pragma unroll
+  for (int i = 0; i < S::N; ++i) { b1[i] = 1.0 + 1e-3 * (threadIdx.x + i); b2[i] = 0.5 - 1e-3 * i; }
+  for (int it = 0; it < iters; ++it) {
+    S::apply(c, b1, b2);
+    S::apply(c, b2, b1);
+  }
+  double acc = 0.0;
+#pragma unroll
+  for (int i = 0; i < S::N; ++i) acc += b1[i] + b2[i];
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
 }  // namespace rydcz
 
 // ======================================================================= C ABI
@@ -929,6 +951,32 @@ int rydcz_fp64_peak(rydcz_ctx* ctx, double* dfma_tflops, double* dmma_tflops) {
   const double mma_flops = 2.0 * 256 * 8 * 4 * (double)iters * blocks * (threads / 32);
   if (dfma_tflops) *dfma_tflops = fma_flops / (best_f * 1e-3) * 1e-12;
   if (dmma_tflops) *dmma_tflops = mma_flops / (best_m * 1e-3) * 1e-12;
+  return 0;
+}
+
+int rydcz_fp64_matvec_peak(rydcz_ctx* ctx, double* tflops) {
+  if (!ctx || !tflops) return 2;
+  CK(cudaSetDevice(ctx->device));
+  const int blocks = ctx->sm_count * 2 * 8, iters = 2048;
+  // 100 KB of (unused) dynamic shared memory per CTA pins the occupancy at the evaluate kernel's two CTAs per SM
+  const int smem = 100 * 1024;
+  CK(cudaFuncSetAttribute(matvec_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  double* buf = nullptr;
+  CK(cudaMalloc(&buf, (size_t)blocks * kBlock * sizeof(double)));
+  float best = 1e30f, ms;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    matvec_peak_kernel<<<blocks, kBlock, smem, ctx->stream>>>(buf, iters, 1e-3);
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (rep > 0 && ms < best) best = ms;
+    ctx->launches++;
+  }
+  CK(cudaGetLastError());
+  CK(cudaFree(buf));
+  ctx->timed = false;
+  *tflops = 2.0 * 2 * Sys_rho11s_d3::NNZ * (double)iters * blocks * kBlock / (best * 1e-3) * 1e-12;
   return 0;
 }
 

@@ -261,6 +261,12 @@ class Evaluator:
         self._check(self.lib.rydcz_fp64_peak(self.ctx, C.byref(a), C.byref(b)), "rydcz_fp64_peak")
         return float(a.value), float(b.value)
 
+    def fp64_matvec_peak(self) -> float:
+        """TFLOP/s of the hot loop's own matvec (folded 3-level rho_11) run bare at the kernel's occupancy."""
+        a = C.c_double()
+        self._check(self.lib.rydcz_fp64_matvec_peak(self.ctx, C.byref(a)), "rydcz_fp64_matvec_peak")
+        return float(a.value)
+
 
 _default = {}
 
