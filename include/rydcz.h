@@ -91,6 +91,14 @@ int rydcz_create(int device, rydcz_ctx** ctx);
 void rydcz_destroy(rydcz_ctx* ctx);
 const char* rydcz_last_error(const rydcz_ctx* ctx);     /* ctx may be NULL: last create() error */
 int rydcz_set_sort(rydcz_ctx* ctx, int enable);         /* order points by estimated work (default 1) */
+/* Clustered-spectrum propagation (csrc/rydcz_cluster.cuh) for points with identical atoms and a strong
+ * blockade: 0 = never, 1 = where the planner estimates it cheaper than the plain Chebyshev path
+ * (default), 2 = wherever it is eligible.  Same results to rounding; a point whose trace / norm check
+ * fails on that path is re-evaluated on the plain path inside the same call. */
+int rydcz_set_cluster(rydcz_ctx* ctx, int mode);
+/* points planned onto the clustered path / handed back to the plain path since the last call of this
+ * function (synchronises the device) */
+int rydcz_cluster_stats(rydcz_ctx* ctx, int64_t* planned, int64_t* handed_back);
 
 /* One batch of gate evaluations, inputs and outputs resident in device memory.
  * dim: 3 (|0>,|1>,|r>) or 4 (|0>,|1>,|r+>,|r->).  noisy: 0 -> Schroedinger path with the
@@ -167,6 +175,7 @@ int rydcz_pinned_free(void* ptr);
 
 /* measurement */
 int rydcz_last_kernel_ms(rydcz_ctx* ctx, float* ms);    /* device time of the last evaluate kernel */
+int rydcz_last_coef_ms(rydcz_ctx* ctx, float* ms);      /* ... of the last clustered-path coefficient kernel (0 if none) */
 int rydcz_launch_count(const rydcz_ctx* ctx, int64_t* n); /* kernels launched through this context */
 /* register-resident FP64 FMA throughput of this GPU (the roofline denominator), TFLOP/s */
 int rydcz_fp64_peak(rydcz_ctx* ctx, double* dfma_tflops, double* dmma_tflops);

@@ -31,6 +31,8 @@ _SIGNATURES = {
     "rydcz_destroy": (None, [_vp]),
     "rydcz_last_error": (C.c_char_p, [_vp]),
     "rydcz_set_sort": (C.c_int, [_vp, C.c_int]),
+    "rydcz_set_cluster": (C.c_int, [_vp, C.c_int]),
+    "rydcz_cluster_stats": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "rydcz_evaluate_device": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, C.c_int,
                                         _vp, _vp, _vp]),
     "rydcz_evaluate_host": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, C.c_int,
@@ -50,6 +52,7 @@ _SIGNATURES = {
     "rydcz_pinned_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "rydcz_pinned_free": (C.c_int, [_vp]),
     "rydcz_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "rydcz_last_coef_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "rydcz_launch_count": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "rydcz_fp64_peak": (C.c_int, [_vp, _dp, _dp]),
     "rydcz_fp64_matvec_peak": (C.c_int, [_vp, _dp]),

@@ -274,6 +274,12 @@ def emit_dim(d: int) -> str:
         out.append(f"// |11> input: probability that at least one atom sits in |0> / in a Rydberg level")
         out.append(f"RYDCZ_HD double rho11_loss_d{d}(const double* __restrict__ x) {{ return {loss_terms}; }}")
     out.append(f"RYDCZ_HD double rho11_ryd_d{d}(const double* __restrict__ x) {{ return {ryd_terms}; }}")
+    if d != 5:
+        # invariants used by the clustered-spectrum path to validate its result (trace of rho_11; norm of the ket)
+        out.append(f"RYDCZ_HD double rho11_trace_d{d}(const double* __restrict__ x) {{ return "
+                   + " + ".join(f"x[{k}]" for k, i in diag) + "; }")
+        out.append(f"RYDCZ_HD double coh11_norm2_d{d}(const double* __restrict__ x) {{ return "
+                   + " + ".join(f"x[{k}] * x[{k}]" for k in range(systems['coh11'].n)) + "; }")
     if d == 5:
         coh11 = systems["coh11"]
         terms = [f"x[{k}] * x[{k}]" for k, (i, j, part) in enumerate(coh11.var_info) if cls(i)[0]]

@@ -65,19 +65,77 @@ __device__ inline void philox_normal2(uint64_t seed, uint32_t point, uint32_t sh
 }
 
 // ---------------------------------------------------------------- kernels
+// Kind of a point: which kernel evaluates it.
+enum PointKind : uint8_t { KIND_GENERAL = 0, KIND_SYM = 1, KIND_CLUSTER = 3 };
+
+// Per point: its kind, and a sort key (kind in the top bits, work estimate below) so that a warp holds
+// points of one kind and similar cost.  cluster_mode: 0 = plain path only, 1 = clustered path where the
+// planner finds it cheaper, 2 = wherever it is eligible.
 template <int D>
-__global__ void work_kernel(int64_t n_points, const double* __restrict__ points,
+__global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
                             const double* __restrict__ segs, const int32_t* __restrict__ n_seg,
-                            int max_seg, int shots, float* __restrict__ keys, uint32_t* __restrict__ idx) {
+                            int max_seg, int shots, int noisy, int cluster_mode, uint32_t* __restrict__ keys,
+                            uint32_t* __restrict__ idx, uint8_t* __restrict__ kind,
+                            uint32_t* __restrict__ task_key, uint32_t* __restrict__ task_val,
+                            unsigned long long* __restrict__ counters) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_points) return;
-  const double* pt = points + i * PointStride<D>::value;
-  double w = point_work<D>(pt, segs + i * (int64_t)max_seg * SG_STRIDE, n_seg ? n_seg[i] : max_seg);
-  // points whose atoms differ take the general kernel: keep them together (ahead of the folded
-  // ones) so warps stay homogeneous in mixed batches
-  if (!(pt[PT_OFF_A] == pt[PT_OFF_B]) || (shots && pt[PT_SIG_DET] != 0.0)) w = w * 2.0 + 1e15;
-  keys[i] = (float)w;   // non-negative floats order like their bit patterns
-  idx[i] = (uint32_t)i;
+  bool clustered = false;
+  if (i < n_points) {
+    int slot_K[CL_MAX_SLOTS];
+#pragma unroll
+    for (int q = 0; q < CL_MAX_SLOTS; ++q) slot_K[q] = 0;
+    const double* pt = points + i * PointStride<D>::value;
+    const double* sg = segs + i * (int64_t)max_seg * SG_STRIDE;
+    const int ns = n_seg ? n_seg[i] : max_seg;
+    double w = point_work<D>(pt, sg, ns);
+    const bool sym = (pt[PT_OFF_A] == pt[PT_OFF_B]) && !(shots && pt[PT_SIG_DET] != 0.0);
+    uint32_t group = sym ? 1u : 2u;     // general points first (heaviest), then plain folded, then clustered
+    if (D != 5 && cluster_mode && sym && !shots) {
+      double cost = 0.0;
+      const int records = cluster_plan<D>(pt, sg, ns, noisy != 0, true, cost, slot_K);
+      if (records > 0 && records <= CL_RECORDS && (cluster_mode == 2 || cost < 0.8 * w)) {
+        clustered = true; group = 0u; w = cost;
+      }
+    }
+    if (task_key) {
+      // one coefficient task per slot, keyed by its term count: sorted, the threads of a warp of
+      // cluster_coef_kernel run the same trip counts
+#pragma unroll
+      for (int q = 0; q < CL_MAX_SLOTS; ++q) {
+        task_key[i * CL_MAX_SLOTS + q] = clustered ? (uint32_t)slot_K[q] : 0u;
+        task_val[i * CL_MAX_SLOTS + q] = (uint32_t)(i * CL_MAX_SLOTS + q);
+      }
+    }
+    kind[i] = clustered ? KIND_CLUSTER : (sym ? KIND_SYM : KIND_GENERAL);
+    const double wq = fmin(fmax(w, 0.0), 1073741823.0);
+    keys[i] = (group << 30) | (uint32_t)wq;
+    idx[i] = (uint32_t)i;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, clustered);
+  if (counters && (threadIdx.x & 31) == 0 && m) atomicAdd(counters, (unsigned long long)__popc(m));
+}
+
+// Coefficient records of the clustered path: one thread per task (point, slot), tasks sorted by their
+// term count so that a warp runs uniform trip counts (key 0 = no such slot: sorted to the end).
+template <int D>
+__global__ void __launch_bounds__(128)
+cluster_coef_kernel(int64_t n_tasks, const uint32_t* __restrict__ task_key, const uint32_t* __restrict__ task_val,
+                    const double* __restrict__ points, const double* __restrict__ segs,
+                    const int32_t* __restrict__ n_seg, int max_seg, int noisy, double* __restrict__ scratch) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_tasks || task_key[g] == 0u) return;
+  const uint32_t task = task_val[g];
+  const int64_t point = task / CL_MAX_SLOTS;
+  const int slot = (int)(task % CL_MAX_SLOTS);
+  const double* pt = points + point * PointStride<D>::value;
+  ClusterWalker<D> w(pt, segs + point * (int64_t)max_seg * SG_STRIDE, n_seg ? n_seg[point] : max_seg, noisy != 0, true);
+  ClusterSlot sl;
+  double* rec = scratch + point * (int64_t)CL_STRIDE;
+  for (int q = 0; q <= slot; ++q) {
+    if (w.next(sl) != 1) return;
+    if (q < slot) rec += (sl.K + 2) * CL_REC;
+  }
+  cluster_coefficients(sl, rec);
 }
 
 // SYM = true handles the points whose two atoms see identical parameters (exchange-folded
@@ -94,6 +152,7 @@ template <int D, bool NOISY, bool SHOTS, bool SYM>
 __global__ void __launch_bounds__(kBlock, (SYM && D == 3 && RYDCZ_D3_VARIANT != 0) ? 3 : 2)
 evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, int64_t point_base,
                 const uint32_t* __restrict__ order,
+                const uint8_t* __restrict__ kind,
                 const double* __restrict__ points, const double* __restrict__ segs,
                 const int32_t* __restrict__ n_seg, int max_seg, double* __restrict__ out,
                 double* __restrict__ states) {
@@ -104,8 +163,8 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, int64_t point_base,
   if (keep) {
     if (SHOTS) point = order ? order[g / n_shots] : g / n_shots;
     else point = order ? order[g] : g;
-    const double* r0 = points + point * PT_STRIDE;
-    keep = ((r0[PT_OFF_A] == r0[PT_OFF_B]) && (!SHOTS || r0[PT_SIG_DET] == 0.0)) == SYM;
+    // a clustered point whose invariant check failed comes back here as KIND_SYM
+    keep = kind[point] == (SYM ? KIND_SYM : KIND_GENERAL);
   }
   const unsigned live = __ballot_sync(0xffffffffu, keep);   // the lanes that evaluate a point in this kernel
   if (!keep) return;
@@ -123,8 +182,6 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, int64_t point_base,
   __shared__ double s_pt[(PT_MAX_STRIDE + PT_SCRATCH + ((SYM && RYDCZ_D3_VARIANT != 0) ? Sys_rho11s_d3::NC : 0)) * kBlock];
   double* mine = s_pt + threadIdx.x;
   const double* row = points + point * PT_STRIDE;
-  const bool folded = (row[PT_OFF_A] == row[PT_OFF_B]) && (!SHOTS || row[PT_SIG_DET] == 0.0);
-  if (folded != SYM) return;
 #pragma unroll
   for (int k = 0; k < PT_STRIDE; ++k) mine[k * kBlock] = row[k];
   if (SHOTS) {
@@ -152,6 +209,57 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, int64_t point_base,
     else evaluate_point_d4<NOISY>(pt, sg, ns, o, st);
   }
   double* op = out + item * OUT_STRIDE;
+#pragma unroll
+  for (int k = 0; k < OUT_STRIDE; k += 2)
+    *reinterpret_cast<double2*>(op + k) = make_double2(o[k], o[k + 1]);
+}
+
+// Clustered-spectrum path (rydcz_cluster.cuh) for identical atoms.  Per thread, in dynamic shared memory
+// ([slot][thread]): the point row + scratch and the three start vectors X0, X1, X2 of rho_11.  The
+// coefficient records were written by cluster_coef_kernel into the point's region of `scratch`.
+template <int D> struct ClusterSmem {
+  static constexpr int XN = D == 3 ? Sys_rho11s_d3::N : Sys_rho11s_d4::N;
+  static constexpr int SLOTS = PT_MAX_STRIDE + PT_SCRATCH + 3 * XN;
+  static constexpr size_t BYTES = (size_t)SLOTS * kBlock * sizeof(double);
+};
+template <int D, bool NOISY>
+__global__ void __launch_bounds__(kBlock, 2)
+evaluate_cluster_kernel(int64_t n_items, const uint32_t* __restrict__ order, uint8_t* __restrict__ kind,
+                        const double* __restrict__ points, const double* __restrict__ segs,
+                        const int32_t* __restrict__ n_seg, int max_seg, const double* __restrict__ scratch,
+                        double* __restrict__ out, double* __restrict__ states,
+                        unsigned long long* __restrict__ counters) {
+  extern __shared__ double s_cl[];
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t point = 0;
+  bool keep = g < n_items;
+  if (keep) {
+    point = order ? order[g] : g;
+    keep = kind[point] == KIND_CLUSTER;
+  }
+  const unsigned live = __ballot_sync(0xffffffffu, keep);
+  if (!keep) return;
+  double* mine = s_cl + threadIdx.x;
+  const double* row = points + point * PT_STRIDE;
+#pragma unroll
+  for (int k = 0; k < PT_STRIDE; ++k) mine[k * kBlock] = row[k];
+  const PointView pt{mine, kBlock, live};
+  const Col xcol{mine + (PT_MAX_STRIDE + PT_SCRATCH) * kBlock, kBlock};
+  const double* sg = segs + point * (int64_t)max_seg * SG_STRIDE;
+  const int ns = n_seg ? n_seg[point] : max_seg;
+  const double* rec = scratch + point * (int64_t)CL_STRIDE;
+  double o[OUT_STRIDE];
+  double* st = states ? states + point * StateLayout<D>::STRIDE : nullptr;
+  bool ok;
+  if (D == 3) ok = evaluate_point_cluster_d3<NOISY>(pt, xcol, sg, ns, rec, o, st);
+  else ok = evaluate_point_cluster_d4<NOISY>(pt, xcol, sg, ns, rec, o, st);
+  if (!ok) {
+    // invariant check failed: hand the point to the plain folded kernel, which runs after this one
+    kind[point] = KIND_SYM;
+    if (counters) atomicAdd(counters + 1, 1ull);
+    return;
+  }
+  double* op = out + point * OUT_STRIDE;
 #pragma unroll
   for (int k = 0; k < OUT_STRIDE; k += 2)
     *reinterpret_cast<double2*>(op + k) = make_double2(o[k], o[k + 1]);
@@ -318,9 +426,18 @@ struct rydcz_ctx {
   int64_t launches = 0;
   std::string err;
   // scratch
-  float* keys = nullptr; float* keys_sorted = nullptr;
+  uint32_t* keys = nullptr; uint32_t* keys_sorted = nullptr;
   uint32_t* idx = nullptr; uint32_t* idx_sorted = nullptr;
+  uint8_t* kind = nullptr;
   size_t order_cap = 0;
+  uint32_t* task = nullptr; size_t task_cap = 0;        // 4 arrays of CL_MAX_SLOTS * n: keys, sorted keys, values, sorted values
+  // clustered-spectrum path: 0 = off, 1 = where the planner finds it cheaper, 2 = wherever eligible
+  int cluster_mode = 1;
+  double* cl_scratch = nullptr; size_t cl_cap = 0;      // coefficient records, CL_STRIDE doubles per point
+  unsigned long long* cl_counters = nullptr;            // [0] points planned onto the path, [1] handed back
+  bool cl_smem_set = false;
+  cudaEvent_t evc0 = nullptr, evc1 = nullptr;           // around the last coefficient kernel
+  bool coef_timed = false;
   void* cub_tmp = nullptr; size_t cub_cap = 0;
   // staging for the host entry points
   void* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -342,7 +459,11 @@ struct rydcz_ctx {
 
 // scratch of one work sort (the default one belongs to the context; every lane has its own)
 struct SortScratch {
-  float* keys; float* keys_sorted; uint32_t* idx; uint32_t* idx_sorted;
+  uint32_t* keys; uint32_t* keys_sorted; uint32_t* idx; uint32_t* idx_sorted;
+  uint8_t* kind;
+  double* cl;          // coefficient records of these points (nullptr: clustered path unavailable)
+  uint32_t* task;      // coefficient task list of these points: [4][task_n] (keys, sorted keys, values, sorted values)
+  int64_t task_n;      // stride of the four task arrays
   void** tmp; size_t* tmp_cap;
 };
 
@@ -406,63 +527,123 @@ static int sys_lookup(int dim, const char* name, int what) {
   return -1;
 }
 
-static int order_reserve(rydcz_ctx* ctx, int64_t n) {
-  if ((size_t)n <= ctx->order_cap) return 0;
-  cudaFree(ctx->keys); cudaFree(ctx->keys_sorted); cudaFree(ctx->idx); cudaFree(ctx->idx_sorted);
-  ctx->keys = ctx->keys_sorted = nullptr; ctx->idx = ctx->idx_sorted = nullptr; ctx->order_cap = 0;
-  CK(cudaMalloc(&ctx->keys, n * sizeof(float)));
-  CK(cudaMalloc(&ctx->keys_sorted, n * sizeof(float)));
-  CK(cudaMalloc(&ctx->idx, n * sizeof(uint32_t)));
-  CK(cudaMalloc(&ctx->idx_sorted, n * sizeof(uint32_t)));
-  ctx->order_cap = (size_t)n;
+// the clustered path's records take 16 KB per point; beyond this the call stays on the plain path
+static constexpr size_t kClusterScratchMax = (size_t)48 << 30;
+
+static int order_reserve(rydcz_ctx* ctx, int64_t n, bool want_cluster = true) {
+  if ((size_t)n > ctx->order_cap) {
+    cudaFree(ctx->keys); cudaFree(ctx->keys_sorted); cudaFree(ctx->idx); cudaFree(ctx->idx_sorted); cudaFree(ctx->kind);
+    ctx->keys = ctx->keys_sorted = nullptr; ctx->idx = ctx->idx_sorted = nullptr; ctx->kind = nullptr; ctx->order_cap = 0;
+    CK(cudaMalloc(&ctx->keys, n * sizeof(uint32_t)));
+    CK(cudaMalloc(&ctx->keys_sorted, n * sizeof(uint32_t)));
+    CK(cudaMalloc(&ctx->idx, n * sizeof(uint32_t)));
+    CK(cudaMalloc(&ctx->idx_sorted, n * sizeof(uint32_t)));
+    CK(cudaMalloc(&ctx->kind, n * sizeof(uint8_t)));
+    ctx->order_cap = (size_t)n;
+  }
+  if (!ctx->cl_counters) {
+    CK(cudaMalloc(&ctx->cl_counters, 2 * sizeof(unsigned long long)));
+    CK(cudaMemset(ctx->cl_counters, 0, 2 * sizeof(unsigned long long)));
+    CK(cudaEventCreate(&ctx->evc0)); CK(cudaEventCreate(&ctx->evc1));
+  }
+  if (want_cluster && ctx->cluster_mode) {
+    const size_t bytes = (size_t)n * CL_STRIDE * sizeof(double);
+    if (bytes <= kClusterScratchMax) {
+      if (grow(ctx, (void**)&ctx->cl_scratch, &ctx->cl_cap, bytes)) return 1;
+      if (grow(ctx, (void**)&ctx->task, &ctx->task_cap, (size_t)n * CL_MAX_SLOTS * 4 * sizeof(uint32_t))) return 1;
+    }
+  }
   return 0;
 }
 
-static SortScratch context_scratch(rydcz_ctx* ctx, int64_t offset = 0) {
+static SortScratch context_scratch(rydcz_ctx* ctx, int64_t n, int64_t offset = 0) {
+  const bool cl = ctx->cluster_mode && ctx->cl_scratch && ctx->task &&
+                  (size_t)(offset + n) * CL_STRIDE * sizeof(double) <= ctx->cl_cap &&
+                  (size_t)(offset + n) * CL_MAX_SLOTS * 4 * sizeof(uint32_t) <= ctx->task_cap;
+  // the four task arrays of a sub-range are laid out back to back inside its own span of the buffer
   return SortScratch{ctx->keys + offset, ctx->keys_sorted + offset, ctx->idx + offset, ctx->idx_sorted + offset,
+                     ctx->kind + offset, cl ? ctx->cl_scratch + offset * (int64_t)CL_STRIDE : nullptr,
+                     cl ? ctx->task + offset * (int64_t)CL_MAX_SLOTS * 4 : nullptr, n * (int64_t)CL_MAX_SLOTS,
                      &ctx->cub_tmp, &ctx->cub_cap};
 }
 
-// order points heaviest-first; returns the device permutation (or nullptr when sorting is off)
+// Plan the batch: kind of every point, heaviest-first order (nullptr when sorting is off), and the
+// coefficient records of the points that take the clustered path.
 template <int D>
 static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const double* d_points,
-                      const double* d_segs, const int32_t* d_n_seg, int max_seg, int shots, cudaStream_t st,
-                      const uint32_t** order) {
+                      const double* d_segs, const int32_t* d_n_seg, int max_seg, int shots, int noisy,
+                      cudaStream_t st, const uint32_t** order) {
   *order = nullptr;
-  if (!ctx->sort || n < 64) return 0;
-  work_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_points, d_segs, d_n_seg, max_seg, shots,
-                                                              sc.keys, sc.idx);
+  const int mode = (sc.cl && D != 5 && !shots && n < (1 << 27)) ? ctx->cluster_mode : 0;
+  uint32_t* tk = mode ? sc.task : nullptr;
+  uint32_t* tks = mode ? sc.task + sc.task_n : nullptr;
+  uint32_t* tv = mode ? sc.task + 2 * sc.task_n : nullptr;
+  uint32_t* tvs = mode ? sc.task + 3 * sc.task_n : nullptr;
+  plan_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_points, d_segs, d_n_seg, max_seg, shots, noisy,
+                                                              mode, sc.keys, sc.idx, sc.kind, tk, tv,
+                                                              ctx->cl_counters);
   CK(cudaGetLastError());
   ctx->launches++;
-  size_t need = 0;
-  CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, sc.keys, sc.keys_sorted, sc.idx, sc.idx_sorted,
-                                               (int)n, 0, 32, st));
-  if (grow(ctx, sc.tmp, sc.tmp_cap, need)) return 1;
-  CK(cub::DeviceRadixSort::SortPairsDescending(*sc.tmp, need, sc.keys, sc.keys_sorted, sc.idx, sc.idx_sorted,
-                                               (int)n, 0, 32, st));
-  *order = sc.idx_sorted;
+  if (ctx->sort && n >= 64) {
+    size_t need = 0;
+    CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, sc.keys, sc.keys_sorted, sc.idx, sc.idx_sorted,
+                                                 (int)n, 0, 32, st));
+    if (grow(ctx, sc.tmp, sc.tmp_cap, need)) return 1;
+    CK(cub::DeviceRadixSort::SortPairsDescending(*sc.tmp, need, sc.keys, sc.keys_sorted, sc.idx, sc.idx_sorted,
+                                                 (int)n, 0, 32, st));
+    *order = sc.idx_sorted;
+  }
+  if (mode) {
+    const int64_t threads = n * CL_MAX_SLOTS;
+    size_t need = 0;
+    CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, tk, tks, tv, tvs, (int)threads, 0, 7, st));
+    if (grow(ctx, sc.tmp, sc.tmp_cap, need)) return 1;
+    CK(cub::DeviceRadixSort::SortPairsDescending(*sc.tmp, need, tk, tks, tv, tvs, (int)threads, 0, 7, st));
+    CK(cudaEventRecord(ctx->evc0, st));
+    cluster_coef_kernel<D><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(threads, tks, tvs, d_points, d_segs,
+                                                                               d_n_seg, max_seg, noisy, sc.cl);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->evc1, st));
+    ctx->coef_timed = true;
+    ctx->launches++;
+  }
   return 0;
 }
 
 template <int D, bool NOISY, bool SHOTS>
-static int launch_eval(rydcz_ctx* ctx, int64_t n_items, int n_shots, uint64_t seed, const uint32_t* order,
-                       const double* d_points, const double* d_segs, const int32_t* d_n_seg, int max_seg,
-                       double* d_out, double* d_states, cudaStream_t st, int mark = 3,
-                       int64_t point_base = 0) {
+static int launch_eval(rydcz_ctx* ctx, const SortScratch& sc, int64_t n_items, int n_shots, uint64_t seed,
+                       const uint32_t* order, const double* d_points, const double* d_segs,
+                       const int32_t* d_n_seg, int max_seg, double* d_out, double* d_states, cudaStream_t st,
+                       int mark = 3, int64_t point_base = 0) {
   // mark: bit 0 = record the start event, bit 1 = record the end event (a pipelined call marks the
   // first chunk's start and the last chunk's end)
   const unsigned grid = (unsigned)((n_items + kBlock - 1) / kBlock);
   if (mark & 1) CK(cudaEventRecord(ctx->ev0, st));
   evaluate_kernel<D, NOISY, SHOTS, false><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, point_base, order,
-                                                                   d_points, d_segs, d_n_seg, max_seg, d_out,
-                                                                   d_states);
+                                                                   sc.kind, d_points, d_segs, d_n_seg, max_seg,
+                                                                   d_out, d_states);
   CK(cudaGetLastError());
+  ctx->launches++;
+  if (!SHOTS && sc.cl && ctx->cluster_mode) {
+    if (!ctx->cl_smem_set) {
+      CK(cudaFuncSetAttribute(evaluate_cluster_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ClusterSmem<3>::BYTES));
+      CK(cudaFuncSetAttribute(evaluate_cluster_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ClusterSmem<3>::BYTES));
+      CK(cudaFuncSetAttribute(evaluate_cluster_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ClusterSmem<4>::BYTES));
+      CK(cudaFuncSetAttribute(evaluate_cluster_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ClusterSmem<4>::BYTES));
+      ctx->cl_smem_set = true;
+    }
+    // before the plain folded kernel: points whose invariant check fails are handed on to it
+    evaluate_cluster_kernel<D, NOISY><<<grid, kBlock, ClusterSmem<D>::BYTES, st>>>(
+        n_items, order, sc.kind, d_points, d_segs, d_n_seg, max_seg, sc.cl, d_out, d_states, ctx->cl_counters);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
   evaluate_kernel<D, NOISY, SHOTS, true><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, point_base, order,
-                                                                  d_points, d_segs, d_n_seg, max_seg, d_out,
-                                                                  d_states);
+                                                                  sc.kind, d_points, d_segs, d_n_seg, max_seg,
+                                                                  d_out, d_states);
   CK(cudaGetLastError());
   if (mark & 2) { CK(cudaEventRecord(ctx->ev1, st)); ctx->timed = true; }
-  ctx->launches += 2;
+  ctx->launches++;
   return 0;
 }
 
@@ -510,6 +691,9 @@ void rydcz_destroy(rydcz_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->keys); cudaFree(ctx->keys_sorted); cudaFree(ctx->idx); cudaFree(ctx->idx_sorted);
+  cudaFree(ctx->kind); cudaFree(ctx->cl_scratch); cudaFree(ctx->cl_counters); cudaFree(ctx->task);
+  if (ctx->evc0) cudaEventDestroy(ctx->evc0);
+  if (ctx->evc1) cudaEventDestroy(ctx->evc1);
   cudaFree(ctx->cub_tmp);
   for (int i = 0; i < 6; ++i) cudaFree(ctx->stage[i]);
   for (int i = 0; i < 3; ++i) cudaFree(ctx->plan[i]);
@@ -533,6 +717,36 @@ int rydcz_set_sort(rydcz_ctx* ctx, int enable) {
   return 0;
 }
 
+int rydcz_set_cluster(rydcz_ctx* ctx, int mode) {
+  if (!ctx) return 2;
+  if (mode < 0 || mode > 2) return fail(ctx, "cluster mode must be 0 (off), 1 (auto) or 2 (wherever eligible)");
+  ctx->cluster_mode = mode;
+  return 0;
+}
+
+int rydcz_cluster_stats(rydcz_ctx* ctx, int64_t* planned, int64_t* handed_back) {
+  if (!ctx) return 2;
+  unsigned long long h[2] = {0, 0};
+  if (ctx->cl_counters) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h, ctx->cl_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(ctx->cl_counters, 0, sizeof(h)));
+  }
+  if (planned) *planned = (int64_t)h[0];
+  if (handed_back) *handed_back = (int64_t)h[1];
+  return 0;
+}
+
+int rydcz_last_coef_ms(rydcz_ctx* ctx, float* ms) {
+  if (!ctx || !ms) return 2;
+  *ms = 0.0f;
+  if (!ctx->coef_timed) return 0;
+  CK(cudaEventSynchronize(ctx->evc1));
+  CK(cudaEventElapsedTime(ms, ctx->evc0, ctx->evc1));
+  return 0;
+}
+
 static int check_args(rydcz_ctx* ctx, int dim, int64_t n, const void* a, const void* b, int max_seg,
                       const void* out, bool allow5 = false) {
   if (!ctx) return 2;
@@ -549,7 +763,7 @@ static int evaluate_impl(rydcz_ctx* ctx, const SortScratch& sc, int dim, int noi
                          double* d_out, double* d_states, cudaStream_t st, int mark) {
   const uint32_t* order = nullptr;
   if (dim == 5) {
-    if (make_order<5>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 0, st, &order)) return 1;
+    if (make_order<5>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 0, noisy, st, &order)) return 1;
     if (!ctx->smem5_set) {
       CK(cudaFuncSetAttribute(evaluate5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem5));
       CK(cudaFuncSetAttribute(evaluate5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem5));
@@ -566,11 +780,11 @@ static int evaluate_impl(rydcz_ctx* ctx, const SortScratch& sc, int dim, int noi
     ctx->launches++;
     return 0;
   }
-  int rc = dim == 3 ? make_order<3>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 0, st, &order)
-                    : make_order<4>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 0, st, &order);
+  int rc = dim == 3 ? make_order<3>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 0, noisy, st, &order)
+                    : make_order<4>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 0, noisy, st, &order);
   if (rc) return rc;
 #define RYDCZ_GO(D, N)                                                                             \
-  return launch_eval<D, N, false>(ctx, n_points, 1, 0, order, d_points, d_segs, d_n_seg, max_seg,   \
+  return launch_eval<D, N, false>(ctx, sc, n_points, 1, 0, order, d_points, d_segs, d_n_seg, max_seg, \
                                   d_out, d_states, st, mark)
   if (dim == 3) { if (noisy) RYDCZ_GO(3, true); else RYDCZ_GO(3, false); }
   else { if (noisy) RYDCZ_GO(4, true); else RYDCZ_GO(4, false); }
@@ -584,8 +798,8 @@ int rydcz_evaluate_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, 
   if (n_points == 0) return 0;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  if (order_reserve(ctx, n_points)) return 1;
-  return evaluate_impl(ctx, context_scratch(ctx), dim, noisy, n_points, d_points, d_segs, d_n_seg, max_seg,
+  if (order_reserve(ctx, n_points, dim != 5)) return 1;
+  return evaluate_impl(ctx, context_scratch(ctx, n_points), dim, noisy, n_points, d_points, d_segs, d_n_seg, max_seg,
                        d_out, d_states, st, 3);
 }
 
@@ -596,11 +810,11 @@ static int shots_impl(rydcz_ctx* ctx, const SortScratch& sc, int dim, int noisy,
                       int mark) {
   const int64_t n_items = n_points * n_shots;
   const uint32_t* order = nullptr;
-  int rc = dim == 3 ? make_order<3>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 1, st, &order)
-                    : make_order<4>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 1, st, &order);
+  int rc = dim == 3 ? make_order<3>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 1, noisy, st, &order)
+                    : make_order<4>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 1, noisy, st, &order);
   if (rc) return rc;
 #define RYDCZ_GO(D, N)                                                                               \
-  rc = launch_eval<D, N, true>(ctx, n_items, n_shots, seed, order, d_points, d_segs, d_n_seg, max_seg, \
+  rc = launch_eval<D, N, true>(ctx, sc, n_items, n_shots, seed, order, d_points, d_segs, d_n_seg, max_seg, \
                                d_shots, nullptr, st, mark, point_base)
   if (dim == 3) { if (noisy) RYDCZ_GO(3, true); else RYDCZ_GO(3, false); }
   else { if (noisy) RYDCZ_GO(4, true); else RYDCZ_GO(4, false); }
@@ -628,8 +842,8 @@ int rydcz_evaluate_shots_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_po
     if (grow(ctx, &ctx->stage[5], &ctx->stage_cap[5], n_points * n_shots * OUT_STRIDE * sizeof(double))) return 1;
     shots = (double*)ctx->stage[5];
   }
-  if (order_reserve(ctx, n_points)) return 1;
-  return shots_impl(ctx, context_scratch(ctx), dim, noisy, n_points, n_shots, seed, 0, d_points, d_segs, d_n_seg,
+  if (order_reserve(ctx, n_points, false)) return 1;
+  return shots_impl(ctx, context_scratch(ctx, n_points), dim, noisy, n_points, n_shots, seed, 0, d_points, d_segs, d_n_seg,
                     max_seg, d_out_mean, shots, st, 3);
 }
 
@@ -837,7 +1051,7 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
   if (grow(ctx, &ctx->plan[0], &ctx->plan_cap[0], n * pstride * sizeof(double))) return 1;
   if (grow(ctx, &ctx->plan[1], &ctx->plan_cap[1], n * S * SG_STRIDE * sizeof(double))) return 1;
   if (grow(ctx, &ctx->plan[2], &ctx->plan_cap[2], n * sizeof(int32_t))) return 1;
-  if (order_reserve(ctx, n_points)) return 1;
+  if (order_reserve(ctx, n_points, dim != 5 && n_shots == 0)) return 1;
   double* d_app = (double*)ctx->stage[0];
   double* d_out = (double*)ctx->stage[3];
   double* d_sc = h_scalars ? (double*)ctx->stage[1] : nullptr;
@@ -884,7 +1098,7 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
     double* c_sc = d_sc ? d_sc + i0 * SC_STRIDE : nullptr;
     if (prologue_impl(ctx, h_model, nc, d_app + i0, n_points, d_pts + i0 * pstride,
                       d_segs + i0 * (int64_t)S * SG_STRIDE, d_ns + i0, c_sc, st)) return 1;
-    SortScratch sc = context_scratch(ctx, i0);
+    SortScratch sc = context_scratch(ctx, nc, i0);
     sc.tmp = &L.cub_tmp; sc.tmp_cap = &L.cub_cap;
     const int mark = (c == 0 ? 1 : 0) | (c == n_chunks - 1 ? 2 : 0);
     int rc;

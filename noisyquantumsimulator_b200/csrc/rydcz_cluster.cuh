@@ -1,0 +1,492 @@
+// rydcz_cluster.cuh -- exact segment propagation when the blockade splits the spectrum into clusters.
+//
+// The plain path (run_system, rydcz_core.cuh) expands exp(tau G) in Chebyshev polynomials on ONE
+// interval that spans the whole spectrum of the generator: K ~ ||G|| tau ~ V tau matvecs per segment,
+// almost all of them spent resolving the fast phase exp(+-i V t) of the doubly excited state.  For
+// V >> Omega the spectrum of G is not an interval but three short ones: with H = H_small + V |rr><rr|,
+//
+//   * all eigenvalues of H but one stay inside [m, M], the spectral range of H_small (Cauchy
+//     interlacing for the rank-one term V |rr><rr|), and the last one lies in
+//     [E_rr, E_rr + |Omega|^2 / (2 (E_rr - M))], E_rr = V - Delta_A - Delta_B;
+//   * the eigenvalues of the Liouvillian -i[H, .] are differences of those: clusters at 0 and +-i V_c of
+//     half-widths w0 = M - m and w1 = (M - m + eta) / 2; the coherence systems (real form of
+//     v' = -i H_eff v, no spectral shift) have the same three clusters;
+//   * the dissipator moves every eigenvalue by at most ||L_D|| <= 4 sum(rates) (Bauer-Fike, -i[H, .] is normal).
+//
+// The cubic q(x) = x (x^2 + V_c^2) maps all three clusters onto ONE short interval of the imaginary
+// axis, |q| <= rho ~ 2 V_c^2 w.  Every entire f can be written f(x) = a0(q) + x a1(q) + x^2 a2(q) with a_j
+// entire (a_j(s) = coefficients of the quadratic that interpolates f at the three pre-images of s), so
+//
+//     exp(h G) x = sum_k [ d0_k + d1_k G~ + d2_k G~^2 ] phi_k(S~) x,     S~ = q(G) / rho,
+//
+// with phi_k the same Chebyshev recurrence the plain path uses and d_jk the Chebyshev coefficients of
+// a_j(i rho t) on [-1, 1] (computed per segment by a cosine transform over K + 2 Gauss nodes; only
+// half of them by conjugate symmetry).  Their number is K ~ h (M - m) + O((h w)^(1/3)): set by Omega tau
+// and no longer by V tau.  One Clenshaw step costs three sparse matvecs, so the path pays when
+// V >~ 15 Omega; for the reference's medium apparatus (V/Omega = 342) a bang-bang candidate needs ~16x
+// fewer matvecs.  The result is exact to rounding like the plain path (tests: < 1e-12 on rho entries).
+//
+// Plain C++ when RYDCZ_HD is empty (tests/hostsim), like rydcz_core.cuh.
+#pragma once
+
+namespace rydcz {
+
+constexpr int CL_REC = 4;          // doubles per coefficient record (d0, d1, d2, pad): one 32-byte sector
+constexpr int CL_MAX_SLOTS = 8;    // distinct (duration, |Omega|, Delta) groups of consecutive segments per point
+constexpr int CL_MAX_K = 62;       // terms per (sub)step; longer segments are cut into equal sub-steps
+constexpr int CL_HALF_MAX = (CL_MAX_K + 2) / 2;
+constexpr int CL_RECORDS = CL_MAX_SLOTS * (CL_MAX_K + 2);   // records per point: header + K + 1 terms per slot
+constexpr int CL_STRIDE = CL_RECORDS * CL_REC;              // doubles per point in the coefficient scratch
+constexpr int CL_ALIGN = 8;        // Clenshaw steps per (sub)step are padded to a multiple of this, so the
+                                   // lanes of a warp reach their segment transitions at common iterations
+constexpr double CL_Z_MAX = 24.0;  // largest h * freq of one sub-step (keeps K <= CL_MAX_K: 24 + 10.3 * 24^(1/3) + 4 + 2 < 62)
+constexpr double CL_STEP_COST = 3.4;    // one clustered Clenshaw step in units of one plain Chebyshev term
+constexpr double CL_SLOT_COST = 60.0;   // coefficient generation of one slot, same units
+constexpr double CL_SUBSTEP_COST = 3.0; // start vectors of one (sub)step, same units
+
+struct ClusterGeom {
+  double Vc;    // centre of the outer clusters (rad/s)
+  double rho;   // |q(x)| <= rho on all three clusters
+  double freq;  // largest d|x|/d(rho t) * rho on the interval: h * freq bounds the Chebyshev degree
+  double damp;  // bound on the real parts (4 x sum of rates)
+};
+
+// D only selects nothing here (the bounds hold for the 3- and 4-level models); kept for symmetry with the callers.
+RYDCZ_HD bool cluster_geometry(double V, double d1, double rates, double om2, double detA, double detB, bool sym,
+                               ClusterGeom& g) {
+  if (!(V > 0.0)) return false;
+  // single-atom block {|1>, |r>}: [[d1, Omega/2], [Omega*/2, -Delta]], eigenvalues a -+ b (|0> sits at 0)
+  const double sA = d1 + detA, aA = 0.5 * (d1 - detA), bA = 0.5 * sqrt(sA * sA + om2);
+  double m, M;
+  if (sym) {
+    // identical atoms, exchange-symmetric sector: {|11>, |S>} block [[2 d1, Omega/sqrt2], [., d1 - Delta]]
+    const double a2 = 0.5 * (3.0 * d1 - detA), b2 = 0.5 * sqrt(sA * sA + 2.0 * om2);
+    m = fmin(0.0, fmin(aA - bA, a2 - b2));
+    M = fmax(0.0, fmax(aA + bA, a2 + b2));
+  } else {
+    const double sB = d1 + detB, aB = 0.5 * (d1 - detB), bB = 0.5 * sqrt(sB * sB + om2);
+    m = fmin(0.0, aA - bA) + fmin(0.0, aB - bB);
+    M = fmax(0.0, aA + bA) + fmax(0.0, aB + bB);
+  }
+  const double Err = V - detA - detB;
+  const double gap = Err - M;
+  if (!(gap > 0.0)) return false;
+  const double eta = 0.5 * om2 / gap, W = M - m, d = 4.0 * rates;
+  const double Vc = Err + 0.5 * (eta - M - m);
+  const double w0 = 1.02 * (W + d), w1 = 1.02 * (0.5 * (W + eta) + d);
+  const double Vc2 = Vc * Vc;
+  const double rho = fmax(w0 * Vc2, (Vc + w1) * w1 * (2.0 * Vc + w1));
+  // the branch points of q^{-1} sit at |q| = 0.385 Vc^3: stay well inside
+  if (!(rho <= 0.25 * Vc2 * Vc) || !(rho > 0.0)) return false;
+  double y = rho / Vc2;   // largest |y| of the central branch: y (Vc^2 - y^2) = rho
+  for (int i = 0; i < 6; ++i) y -= (y * (Vc2 - y * y) - rho) / (Vc2 - 3.0 * y * y);
+  g.Vc = Vc; g.rho = rho; g.freq = rho / (Vc2 - 3.0 * y * y); g.damp = d;
+  return true;
+}
+
+// cos(pi x): the CUDA intrinsic on the device, libm on the host harness
+RYDCZ_HD double cluster_cospi(double x) {
+#ifdef __CUDA_ARCH__
+  return cospi(x);
+#else
+  return cos(3.141592653589793238462643383279 * x);
+#endif
+}
+
+// prefetch of a coefficient record into L1/L2 (a hint: any address is allowed); no-op on the host
+#ifndef RYDCZ_PREFETCH
+#ifdef __CUDA_ARCH__
+#define RYDCZ_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#else
+#define RYDCZ_PREFETCH(p) ((void)0)
+#endif
+#endif
+
+RYDCZ_HD int cluster_roundup(int steps) { return (steps + CL_ALIGN - 1) / CL_ALIGN * CL_ALIGN; }
+
+// One slot: `count` consecutive active segments with the same duration, |Omega| and Delta, each advanced
+// in `nsub` equal sub-steps of length h with K + 1 coefficient records.
+struct ClusterSlot {
+  ClusterGeom g;
+  double h;
+  int K, nsub, count;
+};
+
+// Walks the active segments of a point (the ones next_segment visits) and groups them into slots.
+template <int D>
+struct ClusterWalker {
+  const double* pt; const double* seg;
+  int n_seg, s;
+  bool sym;
+  double rates;
+  RYDCZ_HD ClusterWalker(const double* pt_, const double* seg_, int n_seg_, bool noisy, bool sym_)
+      : pt(pt_), seg(seg_), n_seg(n_seg_), s(0), sym(sym_), rates(0.0) {
+    if (noisy) {
+      rates = pt[PT_G_R1] + pt[PT_G_R0] + pt[PT_G_PHI] + pt[PT_G_SC];
+      if (D == 4) rates += pt[PT_G_MJ];
+    }
+  }
+  RYDCZ_HD static bool is_active(double dt) { return dt != 0.0 && dt == dt; }
+  // 1 = slot filled, 0 = no segment left, -1 = this point cannot take the clustered path
+  RYDCZ_HD int next(ClusterSlot& sl) {
+    while (s < n_seg && !is_active(seg[(long long)s * SG_STRIDE + SG_DT])) ++s;
+    if (s >= n_seg) return 0;
+    const double* sg = seg + (long long)s * SG_STRIDE;
+    const double dt = sg[SG_DT], det = sg[SG_DET];
+    const double om2 = sg[SG_RE] * sg[SG_RE] + sg[SG_IM] * sg[SG_IM];
+    if (!cluster_geometry(pt[PT_V], pt[PT_DELTA1], rates, om2, det + pt[PT_OFF_A], det + pt[PT_OFF_B], sym, sl.g))
+      return -1;
+    const double adt = fabs(dt);
+    const double z = adt * sl.g.freq, dz = sl.g.damp * adt;
+    if (!(z < 1e6) || !(dz < 1e3)) return -1;
+    // sub-steps: keep K <= CL_MAX_K, and damp * h <= 1 so that the Chebyshev polynomials stay O(e^2) on the
+    // strip the damped spectrum occupies (same reason as the plain path's nsub); nearly free, K ~ z + O(z^(1/3))
+    sl.nsub = z > CL_Z_MAX ? (int)ceil(z / CL_Z_MAX) : 1;
+    if (dz > (double)sl.nsub) sl.nsub = (int)ceil(dz);
+    sl.h = dt / (double)sl.nsub;
+    double zs = z / (double)sl.nsub;
+    if (!(zs >= 1e-2)) zs = 1e-2;
+    sl.K = cheb_terms(zs) + 2;
+    if (sl.K > CL_MAX_K) return -1;
+    sl.count = 1;
+    ++s;
+    // absorb the following active segments that repeat (dt, |Omega|, Delta): smooth-JP steps, the second LP pulse
+    for (;;) {
+      int t = s;
+      while (t < n_seg && !is_active(seg[(long long)t * SG_STRIDE + SG_DT])) ++t;
+      if (t >= n_seg) break;
+      const double* nx = seg + (long long)t * SG_STRIDE;
+      const double o2 = nx[SG_RE] * nx[SG_RE] + nx[SG_IM] * nx[SG_IM];
+      if (!(nx[SG_DT] == dt && nx[SG_DET] == det && fabs(o2 - om2) <= 1e-9 * om2)) break;
+      ++sl.count;
+      s = t + 1;
+    }
+    return 1;
+  }
+};
+
+// Records the clustered path needs for a point (0 = not eligible) and its cost in plain Chebyshev terms.
+template <int D>
+RYDCZ_HD int cluster_plan(const double* pt, const double* seg, int n_seg, bool noisy, bool sym, double& cost,
+                          int* __restrict__ slot_K = nullptr) {
+  ClusterWalker<D> w(pt, seg, n_seg, noisy, sym);
+  ClusterSlot sl;
+  int records = 0, slots = 0;
+  cost = 0.0;
+  for (;;) {
+    const int r = w.next(sl);
+    if (r < 0) return 0;
+    if (r == 0) break;
+    if (++slots > CL_MAX_SLOTS) return 0;
+    if (slot_K) slot_K[slots - 1] = sl.K;
+    records += sl.K + 2;
+    cost += (double)sl.count * (double)sl.nsub * (CL_STEP_COST * (double)cluster_roundup(sl.K + 2) + CL_SUBSTEP_COST) +
+            CL_SLOT_COST;
+  }
+  return slots == 0 ? 0 : records;
+}
+
+// Header + coefficient records of one slot.
+//   header: K + 1024 nsub, kappa = Vc^2 / gs^2, 1 / gs, count          (gs = (rho/2)^(1/3): G~ = G / gs)
+//   record k = 0..K: d0_k, d1_k, d2_k for  C_k = d0_k + d1_k G~ + d2_k G~^2
+// Nodes t_n = cos(pi (n + 1/2) / N), N = K + 2; the three pre-images of s = i rho t are x = i y with
+// y (Vc^2 - y^2) = rho t: y_0 near 0 and y_+- = +-Vc (1 - e_+-), in units of Vc roots of
+//     y - y^3 = c,   phi(e) = 2 e - 3 e^2 + e^3 = +-c,   c = rho t / Vc^3 in [-1/4, 1/4],
+// found by two Newton steps from a polynomial fit (start errors 5e-8 / 5e-6).  The fast phases
+// exp(+-i h Vc) are factored out and evaluated once, so the per-node sincos arguments stay O(h w) and the
+// rounding of h Vc acts as one consistent perturbation of V.
+RYDCZ_HD double cluster_root_e(double c) {
+  double e = c * (0.49996334654598612 + c * (0.37665288212020709 + c * (0.50740503889100941 + c * (0.69820872531829381 +
+             c * (1.1095386292091427 + c * (5.605127239220935 + c * 12.998643520117961)))))) - 3.3907227034220971e-06;
+  // chord iteration with the slope at the start point: the error shrinks by ~2.5e-5 per step
+  const double r = 1.0 / (2.0 + e * (3.0 * e - 6.0));
+  RYDCZ_UNROLL
+  for (int it = 0; it < 3; ++it) e = fma(-(e * (2.0 + e * (e - 3.0)) - c), r, e);
+  return e;
+}
+RYDCZ_HD double cluster_root_y(double c) {
+  const double q = c * c;
+  double y = c * (0.99999984362350458 + q * (1.0001738811032581 + q * (2.9690741824804951 + q * (13.967400857958946 +
+             q * (0.85149574480882961 + q * 886.98095006735718)))));
+  const double r = 1.0 / (1.0 - 3.0 * y * y);
+  RYDCZ_UNROLL
+  for (int it = 0; it < 2; ++it) y = fma(-(fma(-y * y, y, y) - c), r, y);
+  return y;
+}
+
+RYDCZ_HD void cluster_coefficients(const ClusterSlot& sl, double* __restrict__ rec) {
+  const int K = sl.K, N = K + 2, half = N / 2;
+  const double Vc = sl.g.Vc, h = sl.h;
+  const double gs = cbrt(0.5 * sl.g.rho);
+  rec[0] = (double)(K + 1024 * sl.nsub);
+  rec[1] = (Vc / gs) * (Vc / gs);
+  rec[2] = 1.0 / gs;
+  rec[3] = (double)sl.count;
+  double* __restrict__ out = rec + CL_REC;
+  double ar[3][CL_HALF_MAX], ai[3][CL_HALF_MAX];
+  const double rhat = sl.g.rho / (Vc * Vc * Vc);
+  const double hv = h * Vc, iVc = 1.0 / Vc;
+  const double g1 = gs * iVc, g2 = g1 * g1;      // a1 and a2 are built in units of 1/Vc, 1/Vc^2
+  double sV, cV;
+  sincos(hv, &sV, &cV);
+  // node angles theta_n = pi (n + 1/2) / N by rotation: (ct, st) <- (ct, st) rotated by pi / N
+  const double pi = 3.141592653589793238462643383279;
+  double st0, ct0, sd, cd;
+  sincos(0.5 * pi / (double)N, &st0, &ct0);
+  sincos(pi / (double)N, &sd, &cd);
+  {
+    double ct = ct0, st = st0;
+    for (int n = 0; n < half; ++n) {
+      const double c = rhat * ct;
+      const double y0 = cluster_root_y(c), ep = cluster_root_e(c), em = cluster_root_e(-c);
+      // f_m = exp(i h y_m)
+      double s0, c0, sp, cp, sm, cm;
+      sincos(hv * y0, &s0, &c0);
+      sincos(hv * ep, &sp, &cp);
+      sincos(hv * em, &sm, &cm);
+      const double fpr = cV * cp + sV * sp, fpi = sV * cp - cV * sp;      // exp(i hv) exp(-i hv ep)
+      const double fmr = cV * cm + sV * sm, fmi = -(sV * cm - cV * sm);   // exp(-i hv) exp(+i hv em)
+      const double Yp = 1.0 - ep, Ym = -(1.0 - em);                       // roots in units of Vc
+      // divided differences on x = i y:  f[a, b] = -i (f_b - f_a) / (y_b - y_a); one division for the three gaps
+      const double g01 = Yp - y0, g12 = Ym - Yp, g02 = Ym - y0;
+      const double inv = 1.0 / (g01 * g12 * g02);
+      const double i01 = inv * g12 * g02, i12 = inv * g01 * g02, i02 = inv * g01 * g12;
+      const double d01r = (fpi - s0) * i01, d01i = -(fpr - c0) * i01;
+      const double d12r = (fmi - fpi) * i12, d12i = -(fmr - fpr) * i12;
+      const double d012r = (d12i - d01i) * i02, d012i = -(d12r - d01r) * i02;
+      // p(x) = f_0 + f[0,+] (x - x_0) + f[0,+,-] (x - x_0)(x - x_+) = a0 + a1 x + a2 x^2
+      const double ys = y0 + Yp, yp = y0 * Yp;
+      const double a1r = d01r + ys * d012i, a1i = d01i - ys * d012r;            // d01 - i ys d012
+      ar[0][n] = c0 + y0 * d01i - yp * d012r; ai[0][n] = s0 - y0 * d01r - yp * d012i;   // f0 - i y0 d01 - y0 yp d012
+      ar[1][n] = a1r * g1; ai[1][n] = a1i * g1;
+      ar[2][n] = d012r * g2; ai[2][n] = d012i * g2;
+      const double cn = ct * cd - st * sd;
+      st = st * cd + ct * sd; ct = cn;
+    }
+  }
+  // cosine transform, sixteen k at a time for all three j (48 accumulators in registers).  Within a
+  // block the Chebyshev recurrence runs from T_kb, T_kb+1 = cos(kb theta), cos((kb + 1) theta), which are
+  // carried from node to node by rotation, so no per-node state is kept in memory and every record is
+  // written once, whole.  Even k pick up Re a_j, odd k Im a_j (conjugate symmetry of the +-t node pairs).
+  const double scale = 4.0 / (double)N;
+  for (int kb = 0; kb <= K; kb += 16) {
+    double acc[16][3];
+    RYDCZ_UNROLL
+    for (int q = 0; q < 16; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; acc[q][2] = 0.0; }
+    // cos / sin of kb theta_0 and of the step kb pi / N
+    double sk, ck, sdk, cdk;
+    sincos((double)kb * (0.5 * pi / (double)N), &sk, &ck);
+    sincos((double)kb * (pi / (double)N), &sdk, &cdk);
+    double ct = ct0, st = st0;
+    for (int n = 0; n < half; ++n) {
+      const double t2 = ct + ct;
+      double Tc = ck, Tn = ck * ct - sk * st;                        // T_kb, T_kb+1
+      const double r0 = ar[0][n], r1 = ar[1][n], r2 = ar[2][n], i0 = ai[0][n], i1 = ai[1][n], i2 = ai[2][n];
+      RYDCZ_UNROLL
+      for (int q = 0; q < 16; q += 2) {
+        acc[q][0] = fma(r0, Tc, acc[q][0]); acc[q][1] = fma(r1, Tc, acc[q][1]); acc[q][2] = fma(r2, Tc, acc[q][2]);
+        acc[q + 1][0] = fma(i0, Tn, acc[q + 1][0]); acc[q + 1][1] = fma(i1, Tn, acc[q + 1][1]);
+        acc[q + 1][2] = fma(i2, Tn, acc[q + 1][2]);
+        Tc = fma(t2, Tn, -Tc);          // T_{k+2}
+        Tn = fma(t2, Tc, -Tn);          // T_{k+3}
+      }
+      double cn = ct * cd - st * sd;
+      st = st * cd + ct * sd; ct = cn;
+      cn = ck * cdk - sk * sdk;
+      sk = sk * cdk + ck * sdk; ck = cn;
+    }
+    RYDCZ_UNROLL
+    for (int q = 0; q < 16; ++q) {
+      const int k = kb + q;
+      if (k <= K) {
+        const double sc = ((k & 2) ? -scale : scale) * (k == 0 ? 0.5 : 1.0);   // i^{-k} on the surviving part
+        out[k * CL_REC + 0] = acc[q][0] * sc;
+        out[k * CL_REC + 1] = acc[q][1] * sc;
+        out[k * CL_REC + 2] = acc[q][2] * sc;
+        out[k * CL_REC + 3] = 0.0;
+      }
+    }
+  }
+}
+
+// All slots of a point, one after the other (the host harness; the GPU runs one thread per slot).
+template <int D>
+RYDCZ_HD void cluster_prepare(const double* pt, const double* seg, int n_seg, bool noisy, bool sym,
+                              double* __restrict__ rec) {
+  ClusterWalker<D> w(pt, seg, n_seg, noisy, sym);
+  ClusterSlot sl;
+  while (w.next(sl) == 1) {
+    cluster_coefficients(sl, rec);
+    rec += (sl.K + 2) * CL_REC;
+  }
+}
+
+// One Clenshaw step of the clustered expansion:  dst <- C_k x + (2 S~) src + dst,
+// (2 S~) v = G~ (G~^2 + kappa) v,  C_k x = d0 X0 + d1 X1 + d2 X2  (X_j = G~^j x in the columns xc).
+// A PRIMING lane runs the very same instructions with src = x and zero coefficients and keeps the two
+// intermediate products: X1 = G~ x and X2 = G~^2 x, the start vectors of the (sub)step it is about to begin.
+template <class Sys, class XC>
+RYDCZ_HD void cluster_step(const double* __restrict__ c, double kappa, double d0, double d1, double d2, const XC xc,
+                           const double* __restrict__ src, double* __restrict__ dst, bool priming) {
+  constexpr int N = Sys::N;
+  double t[N], u[N];
+  RYDCZ_UNROLL
+  for (int i = 0; i < N; ++i) t[i] = 0.0;
+  Sys::apply(c, src, t);
+  RYDCZ_UNROLL
+  for (int i = 0; i < N; ++i) u[i] = kappa * src[i];
+  Sys::apply(c, t, u);
+  if (priming) {
+    RYDCZ_UNROLL
+    for (int i = 0; i < N; ++i) { xc[i] = src[i]; xc[N + i] = t[i]; xc[2 * N + i] = fma(-kappa, src[i], u[i]); }
+  }
+  RYDCZ_UNROLL
+  for (int i = 0; i < N; ++i) dst[i] = fma(d0, xc[i], fma(d1, xc[N + i], fma(d2, xc[2 * N + i], dst[i])));
+  Sys::apply(c, u, dst);
+}
+
+// run_system for the clustered path.  Same flat loop: one iteration = two Clenshaw steps of whatever
+// (sub)step the lane is in.  A (sub)step takes roundup(K + 2, CL_ALIGN) steps -- the priming step, K + 1
+// recurrence steps, padding with zero coefficients in front -- so the lanes of a warp reach their
+// transitions at common iterations, and a transition itself is only the header / segment bookkeeping.
+// `rec` = the point's coefficient records, `xc` = 3 N per-thread columns for the start vectors.
+template <class Sys, class XC>
+RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const PointView pt,
+                                 const double* __restrict__ seg, int n_seg, bool noisy,
+                                 const double* __restrict__ rec, double& steps) {
+  constexpr int N = Sys::N;
+  double c[Sys::NC], b1[N], b2[N];
+  Sys::init(b1);
+  int k = -1, K = -1, nsub = 1, sub_left = 0, seg_left = 0, s = 0;
+  bool priming = false;
+  double kappa = 0.0, inv_gs = 0.0;
+  const double* terms = rec;
+  double n0 = 0.0, n1 = 0.0, n2 = 0.0;   // record of the step about to run (loaded one step ahead)
+  for (;;) {
+    if (k < 0) {
+      // b1 holds the state.  Next sub-step of this segment, or the next segment (and maybe the next slot).
+      if (sub_left > 0) {
+        --sub_left;
+      } else {
+        double dt = 0.0;
+        double p[Sys::NP];
+        if (!next_segment<Sys>(p, pt, seg, n_seg, s, dt, noisy)) break;
+        if (seg_left == 0) {
+          const double* hdr = K < 0 ? rec : terms + (K + 1) * CL_REC;
+          const int kn = (int)hdr[0];
+          K = kn & 1023; nsub = kn >> 10;
+          kappa = hdr[1]; inv_gs = hdr[2]; seg_left = (int)hdr[3];
+          terms = hdr + CL_REC;
+          RYDCZ_PREFETCH(terms + (K + 1) * CL_REC);              // the next slot's header
+        }
+        --seg_left;
+        if (s < n_seg) RYDCZ_PREFETCH(seg + (long long)s * SG_STRIDE);   // the next segment row
+        if (!Sys::HERMITIAN) p[Sys::NP - 1] = 0.0;   // no spectral shift on this path
+        Sys::coefs(p, c);
+        RYDCZ_UNROLL
+        for (int q = 0; q < Sys::NC; ++q) c[q] *= inv_gs;
+        sub_left = nsub - 1;
+      }
+      steps += (double)(K + 1);
+      RYDCZ_UNROLL
+      for (int i = 0; i < N; ++i) b2[i] = 0.0;
+      k = cluster_roundup(K + 2) - 1;    // the priming step (k > K: zero coefficients), then k - 1 ... 0
+      priming = true;
+      n0 = n1 = n2 = 0.0;
+    }
+    // step k: b2 <- C_k x + 2S~ b1 + b2      (priming: b1 = x, and both vectors restart from zero afterwards)
+    if (k >= 8) RYDCZ_PREFETCH(terms + (k - 8) * CL_REC);   // records are read once, in order: pull the line two ahead
+    double d0 = n0, d1 = n1, d2 = n2;
+    n0 = n1 = n2 = 0.0;
+    if (k - 1 <= K) { n0 = terms[(k - 1) * CL_REC]; n1 = terms[(k - 1) * CL_REC + 1]; n2 = terms[(k - 1) * CL_REC + 2]; }
+    cluster_step<Sys>(c, kappa, d0, d1, d2, xc, b1, b2, priming);
+    if (priming) {
+      RYDCZ_UNROLL
+      for (int i = 0; i < N; ++i) { b1[i] = 0.0; b2[i] = 0.0; }
+      priming = false;
+    }
+    // step k-1: b1 <- C_{k-1} x + 2S~ b2 + b1; the last one (k-1 = 0) takes S~ b2 instead: halve b2
+    d0 = n0; d1 = n1; d2 = n2;
+    n0 = n1 = n2 = 0.0;
+    if (k >= 2 && k - 2 <= K) { n0 = terms[(k - 2) * CL_REC]; n1 = terms[(k - 2) * CL_REC + 1]; n2 = terms[(k - 2) * CL_REC + 2]; }
+    if (k == 1) {
+      RYDCZ_UNROLL
+      for (int i = 0; i < N; ++i) b2[i] *= 0.5;
+    }
+    cluster_step<Sys>(c, kappa, d0, d1, d2, xc, b2, b1, false);
+    k -= 2;
+  }
+  RYDCZ_UNROLL
+  for (int i = 0; i < N; ++i) x[i] = b1[i];
+}
+
+// One full gate evaluation on the clustered path (identical atoms; the |01> input has no blockade shift
+// and stays on the plain path).  Returns false when the invariant check fails (trace of rho_11, norm of
+// the noiseless ket): the caller then leaves the point to the plain kernel.
+#define RYDCZ_DEFINE_EVALUATE_CLUSTER(D)                                                            \
+  template <bool NOISY>                                                                             \
+  RYDCZ_HD bool evaluate_point_cluster_d##D(const PointView pt, const Col xcol,                     \
+                                            const double* __restrict__ seg, int n_seg,              \
+                                            const double* __restrict__ rec,                         \
+                                            double* __restrict__ out, double* __restrict__ states) {\
+    typedef StateLayout<D> SL;                                                                      \
+    double steps = 0.0, flops = 0.0, st;                                                            \
+    double p01 = 1.0, p11 = 1.0, loss = 0.0, ryd = 0.0;                                             \
+    double c01r, c01i, c11r, c11i;                                                                  \
+    bool ok = true;                                                                                 \
+    if (NOISY) {                                                                                    \
+      double x[Sys_rho11s_d##D::N]; st = 0.0;                                                       \
+      run_system_cluster<Sys_rho11s_d##D>(x, xcol, pt, seg, n_seg, true, rec, st);                  \
+      RYDCZ_RECONVERGE(pt.live);                                                                    \
+      steps += st; flops += st * 2.0 * (3 * Sys_rho11s_d##D::NNZ + 4 * Sys_rho11s_d##D::N);         \
+      p11 = x[RHO11S_POP_D##D];                                                                     \
+      double xf[Sys_rho11s_d##D::FULL_N];                                                           \
+      Sys_rho11s_d##D::expand(x, xf);                                                               \
+      loss = rho11_loss_d##D(xf); ryd = rho11_ryd_d##D(xf);                                         \
+      ok = fabs(rho11_trace_d##D(xf) - 1.0) <= 1e-9;                                                \
+      if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_rho11s_d##D::FULL_N; ++i) states[SL::RHO11 + i] = xf[i]; } \
+    }                                                                                               \
+    {                                                                                               \
+      double x[Sys_coh11s_d##D::N]; st = 0.0;                                                       \
+      run_system_cluster<Sys_coh11s_d##D>(x, xcol, pt, seg, n_seg, NOISY, rec, st);                 \
+      RYDCZ_RECONVERGE(pt.live);                                                                    \
+      steps += st; flops += st * 2.0 * (3 * Sys_coh11s_d##D::NNZ + 4 * Sys_coh11s_d##D::N);         \
+      c11r = x[COH11S_RE_D##D]; c11i = x[COH11S_IM_D##D];                                           \
+      if (!NOISY) ryd = 1.0 - (c11r * c11r + c11i * c11i);                                          \
+      if (!NOISY || states) {                                                                       \
+        double xf[Sys_coh11s_d##D::FULL_N];                                                         \
+        Sys_coh11s_d##D::expand(x, xf);                                                             \
+        if (!NOISY) ok = fabs(coh11_norm2_d##D(xf) - 1.0) <= 1e-9;                                  \
+        if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh11s_d##D::FULL_N; ++i) states[SL::COH11 + i] = xf[i]; } \
+      }                                                                                             \
+    }                                                                                               \
+    if (!ok) return false;                                                                          \
+    if (NOISY) {                                                                                    \
+      double x[Sys_in01_d##D::N]; st = 0.0;                                                         \
+      run_system<Sys_in01_d##D>(x, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);            \
+      steps += st; flops += st * 2.0 * (Sys_in01_d##D::NNZ + Sys_in01_d##D::N);                     \
+      p01 = x[RHO01_POP_D##D];                                                                      \
+      c01r = x[IN01_COH_OFFSET_D##D + COH01_RE_D##D]; c01i = x[IN01_COH_OFFSET_D##D + COH01_IM_D##D]; \
+      if (states) {                                                                                 \
+        RYDCZ_UNROLL for (int i = 0; i < Sys_rho01_d##D::N; ++i) {                                  \
+          states[SL::RHO01 + i] = x[i]; states[SL::RHO10 + i] = x[i]; }                             \
+        RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d##D::N; ++i) {                                  \
+          states[SL::COH01 + i] = x[IN01_COH_OFFSET_D##D + i]; states[SL::COH10 + i] = x[IN01_COH_OFFSET_D##D + i]; } \
+      }                                                                                             \
+    } else {                                                                                        \
+      double x[Sys_coh01_d##D::N]; st = 0.0;                                                        \
+      run_system<Sys_coh01_d##D>(x, pt, seg, n_seg, false, st); RYDCZ_RECONVERGE(pt.live);          \
+      steps += st; flops += st * 2.0 * (Sys_coh01_d##D::NNZ + Sys_coh01_d##D::N);                   \
+      c01r = x[COH01_RE_D##D]; c01i = x[COH01_IM_D##D];                                             \
+      if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d##D::N; ++i) {                      \
+        states[SL::COH01 + i] = x[i]; states[SL::COH10 + i] = x[i]; } }                             \
+    }                                                                                               \
+    cz_epilogue(NOISY, p01, p01, p11, c01r, c01i, c01r, c01i, c11r, c11i, out);                     \
+    out[OUT_LOSS] = loss; out[OUT_RYD] = ryd; out[OUT_STEPS] = steps; out[OUT_FLOPS] = flops;       \
+    return true;                                                                                    \
+  }
+
+RYDCZ_DEFINE_EVALUATE_CLUSTER(3)
+RYDCZ_DEFINE_EVALUATE_CLUSTER(4)
+
+}  // namespace rydcz

@@ -733,3 +733,5 @@ RYDCZ_HD double point_work(const double* __restrict__ pt, const double* __restri
 }
 
 }  // namespace rydcz
+
+#include "rydcz_cluster.cuh"

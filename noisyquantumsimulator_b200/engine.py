@@ -245,6 +245,21 @@ class Evaluator:
     def set_sort(self, enable: bool):
         self._check(self.lib.rydcz_set_sort(self.ctx, int(enable)), "rydcz_set_sort")
 
+    def set_cluster(self, mode: int):
+        """Clustered-spectrum propagation: 0 = never, 1 = where cheaper (default), 2 = wherever eligible."""
+        self._check(self.lib.rydcz_set_cluster(self.ctx, int(mode)), "rydcz_set_cluster")
+
+    def cluster_stats(self) -> Tuple[int, int]:
+        """(points planned onto the clustered path, points handed back to the plain path) since the last call."""
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self.lib.rydcz_cluster_stats(self.ctx, C.byref(a), C.byref(b)), "rydcz_cluster_stats")
+        return int(a.value), int(b.value)
+
+    def last_coef_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self.lib.rydcz_last_coef_ms(self.ctx, C.byref(ms)), "rydcz_last_coef_ms")
+        return float(ms.value)
+
     def last_kernel_ms(self) -> float:
         ms = C.c_float()
         self._check(self.lib.rydcz_last_kernel_ms(self.ctx, C.byref(ms)), "rydcz_last_kernel_ms")

@@ -95,7 +95,7 @@ def load_hostsim():
     so = os.path.join(d, "libhostsim.so")
     srcs = [os.path.join(d, "hostsim.cpp")] + [
         os.path.join(HERE, "..", "noisyquantumsimulator_b200", "csrc", f)
-        for f in ("rydcz_core.cuh", "rydcz_prologue.cuh", "rydcz_systems_d3.inc", "rydcz_systems_d4.inc",
+        for f in ("rydcz_core.cuh", "rydcz_cluster.cuh", "rydcz_prologue.cuh", "rydcz_systems_d3.inc", "rydcz_systems_d4.inc",
                   "rydcz_systems_d5.inc")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, srcs[0]])
@@ -105,9 +105,13 @@ def load_hostsim():
                                      ctypes.POINTER(ctypes.c_int), ctypes.c_int, dp, dp]
     lib.hostsim_evaluate.restype = ctypes.c_int
     lib.hostsim_allow_sym.argtypes = [ctypes.c_int]
+    lib.hostsim_set_cluster.argtypes = [ctypes.c_int]
 
-    def evaluate(dim, noisy, points, segs, n_seg, want_states=True, allow_sym=True):
+    def evaluate(dim, noisy, points, segs, n_seg, want_states=True, allow_sym=True, cluster=0):
+        """cluster: 0 = plain Chebyshev path, 1 = clustered-spectrum path where the planner prefers it,
+        2 = wherever it is eligible (csrc/rydcz_cluster.cuh)."""
         lib.hostsim_allow_sym(int(allow_sym))
+        lib.hostsim_set_cluster(int(cluster))
         import ctypes as C
         points = np.ascontiguousarray(points, dtype=np.float64)
         segs = np.ascontiguousarray(segs, dtype=np.float64)
@@ -121,8 +125,16 @@ def load_hostsim():
                                   out.ctypes.data_as(dp),
                                   st.ctypes.data_as(dp) if want_states else None)
         assert rc == 0
+        lib.hostsim_set_cluster(0)
         return out, st
 
+    def cluster_stats():
+        a, b = ctypes.c_longlong(0), ctypes.c_longlong(0)
+        lib.hostsim_cluster_stats(ctypes.byref(a), ctypes.byref(b))
+        return a.value, b.value
+
+    evaluate.cluster_stats = cluster_stats
+    evaluate.lib = lib
     return evaluate
 
 

@@ -7,8 +7,53 @@
 #include "../../noisyquantumsimulator_b200/csrc/rydcz_core.cuh"
 #include "../../noisyquantumsimulator_b200/csrc/rydcz_prologue.cuh"
 
+#include <vector>
+
 static int g_allow_sym = 1;
 extern "C" void hostsim_allow_sym(int on) { g_allow_sym = on; }
+// clustered-spectrum path (csrc/rydcz_cluster.cuh): 0 = off, 1 = where the planner prefers it (the CUDA
+// library's rule), 2 = wherever it is eligible
+static int g_cluster = 0;
+static long long g_cluster_used = 0, g_cluster_retry = 0;
+extern "C" void hostsim_set_cluster(int mode) { g_cluster = mode; }
+extern "C" void hostsim_cluster_stats(long long* used, long long* retried) {
+  *used = g_cluster_used; *retried = g_cluster_retry;
+  g_cluster_used = 0; g_cluster_retry = 0;
+}
+
+template <int D>
+static bool try_cluster(const rydcz::PointView pt, const double* row, const double* sg, int ns, bool noisy,
+                        double* o, double* st) {
+  using namespace rydcz;
+  double cost = 0.0;
+  const int records = cluster_plan<D>(row, sg, ns, noisy, true, cost);
+  if (records <= 0 || records > CL_RECORDS) return false;
+  if (g_cluster == 1 && !(cost < 0.8 * point_work<D>(row, sg, ns))) return false;
+  std::vector<double> rec((size_t)CL_STRIDE, 0.0);
+  cluster_prepare<D>(row, sg, ns, noisy, true, rec.data());
+  double xc[3 * 21];
+  bool ok;
+  if (D == 3) ok = noisy ? evaluate_point_cluster_d3<true>(pt, Col{xc, 1}, sg, ns, rec.data(), o, st)
+                         : evaluate_point_cluster_d3<false>(pt, Col{xc, 1}, sg, ns, rec.data(), o, st);
+  else ok = noisy ? evaluate_point_cluster_d4<true>(pt, Col{xc, 1}, sg, ns, rec.data(), o, st)
+                  : evaluate_point_cluster_d4<false>(pt, Col{xc, 1}, sg, ns, rec.data(), o, st);
+  ++g_cluster_used;
+  if (!ok) ++g_cluster_retry;
+  return ok;
+}
+
+// coefficient records of one point, for tests of the cosine transform (returns the number of records)
+extern "C" int hostsim_cluster_records(int dim, int noisy, const double* point, const double* segs, int n_seg,
+                                       double* rec, double* cost) {
+  using namespace rydcz;
+  const int records = dim == 3 ? cluster_plan<3>(point, segs, n_seg, noisy != 0, true, *cost)
+                               : cluster_plan<4>(point, segs, n_seg, noisy != 0, true, *cost);
+  if (records > 0 && rec) {
+    if (dim == 3) cluster_prepare<3>(point, segs, n_seg, noisy != 0, true, rec);
+    else cluster_prepare<4>(point, segs, n_seg, noisy != 0, true, rec);
+  }
+  return records;
+}
 
 extern "C" int hostsim_evaluate(int dim, int noisy, long long n_points, const double* points,
                                 const double* segs, const int* n_seg, int max_seg, double* out,
@@ -23,6 +68,11 @@ extern "C" int hostsim_evaluate(int dim, int noisy, long long n_points, const do
     double* o = out + i * OUT_STRIDE;
     // same dispatch rule as the CUDA kernels: identical atoms take the exchange-folded path
     const bool sym = g_allow_sym && pt[PT_OFF_A] == pt[PT_OFF_B];
+    if (g_cluster && sym && (dim == 3 || dim == 4)) {
+      double* st = states ? states + i * (dim == 3 ? StateLayout<3>::STRIDE : StateLayout<4>::STRIDE) : nullptr;
+      if (dim == 3 ? try_cluster<3>(pt, row, sg, n_seg[i], noisy != 0, o, st)
+                   : try_cluster<4>(pt, row, sg, n_seg[i], noisy != 0, o, st)) continue;
+    }
     if (dim == 3) {
       double* st = states ? states + i * StateLayout<3>::STRIDE : nullptr;
       double cc[Sys_rho11s_d3::NC];
