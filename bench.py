@@ -226,8 +226,9 @@ def run_ours(args, rank, world, local_rank):
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             tr = json.load(f)
         traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * B_PER_GPU / tr["candidates"]
+        traffic_kernel = tr["kernel"]
     except Exception:
-        traffic = None
+        traffic, traffic_kernel = None, None
 
     def step():
         # inputs resident in HBM: prologue kernel -> work sort -> evaluate kernels -> score all-gather
@@ -248,7 +249,8 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     launches0 = ev.launch_count()
-    kernel_ms = []
+    ev.cluster_stats()
+    kernel_ms, coef_ms = [], []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -257,10 +259,12 @@ def run_ours(args, rank, world, local_rank):
         # per-launch device time of the dominant kernel (events recorded inside the C ABI on the
         # launching stream); reading it synchronises, which is inside the timed region on purpose
         kernel_ms.append(ev.last_kernel_ms())
+        coef_ms.append(ev.last_coef_ms())
     e1.record()
     barrier()
     total_ms = e0.elapsed_time(e1)
     launches = ev.launch_count() - launches0
+    cl_planned, cl_back, cl_records = ev.cluster_stats(with_records=True)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -294,7 +298,12 @@ def run_ours(args, rank, world, local_rank):
     out_np = d_out.cpu().numpy()
     flops_per_launch = float(out_np[:, 15].sum())
     k_ms = float(np.mean(kernel_ms))
+    c_ms = float(np.mean(coef_ms))
     achieved = flops_per_launch / (k_ms * 1e-3) * 1e-12
+    clustered = cl_planned > 0
+    # bytes the evaluate kernel must read / write per launch: point row, segment rows, segment count, result
+    # row, and on the clustered path the 32-byte coefficient records, once for rho_11 and once for the coherence
+    alg_bytes = float(B_PER_GPU * (12 * 8 + N_SEG * 32 + 4 + 16 * 8)) + 2.0 * 32.0 * cl_records / max(args.steps, 1)
     n_var = sum(isinstance(c, np.ndarray) for c in dpro.apparatus_columns("jp", B_PER_GPU, **ak))
     h2d = B_PER_GPU * n_var * 8          # only the apparatus slots that vary over the batch cross PCIe
     d2h = B_PER_GPU * (16 + 8) * 8       # result rows + reported scalars
@@ -323,6 +332,8 @@ def run_ours(args, rank, world, local_rank):
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "jp_bangbang_5seg_lindblad_3level", "candidates_per_gpu": B_PER_GPU,
+                       "propagation": ("clustered-spectrum Chebyshev (csrc/rydcz_cluster.cuh)" if clustered
+                                       else "single-interval Chebyshev"),
                        "segments": N_SEG, "apparatus": "medium (RG/optimize_cz_gate.py:196-213), full noise",
                        "l2": "256 MiB flush write between timed iterations", "parallelism": f"shard{world}",
                        "mean_fidelity": float(out_np[:, 0].mean())},
@@ -335,10 +346,15 @@ def run_ours(args, rank, world, local_rank):
                          "frac": achieved / dfma_peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one `ncu --set full`
                          # capture (profiles/ncu_traffic.json), scaled to this batch size
-                         "traffic": traffic,
-                         "algorithmic_bytes": float(B_PER_GPU * (12 * 8 + N_SEG * 32 + 4 + 16 * 8)),
-                         "kernel": "rydcz::evaluate_kernel<3,true,false,true>", "kernel_ms": k_ms,
-                         "flops_per_launch": flops_per_launch,
+                         "traffic": traffic, "traffic_kernel": traffic_kernel,
+                         "algorithmic_bytes": alg_bytes,
+                         "kernel": ("rydcz::evaluate_cluster_kernel<3,true>" if clustered
+                                    else "rydcz::evaluate_kernel<3,true,false,true>"),
+                         "kernel_ms": k_ms, "flops_per_launch": flops_per_launch,
+                         # the clustered path's second kernel (coefficient records, one thread per pulse segment):
+                         # sincos / division heavy, its flops are not counted in `achieved`
+                         "coef_kernel_ms": c_ms,
+                         "clustered_points_per_step": cl_planned / max(args.steps, 1), "handed_back": cl_back,
                          "peak_source": "DFMA microbenchmark (rydcz_fp64_peak) measured in this run; "
                                         "MEASURED_PEAKS.json has no FP64 entry", "dmma_peak": dmma_peak,
                          # the hot loop's own 78-nonzero matvec run bare at the kernel's occupancy (three

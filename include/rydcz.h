@@ -96,9 +96,9 @@ int rydcz_set_sort(rydcz_ctx* ctx, int enable);         /* order points by estim
  * (default), 2 = wherever it is eligible.  Same results to rounding; a point whose trace / norm check
  * fails on that path is re-evaluated on the plain path inside the same call. */
 int rydcz_set_cluster(rydcz_ctx* ctx, int mode);
-/* points planned onto the clustered path / handed back to the plain path since the last call of this
- * function (synchronises the device) */
-int rydcz_cluster_stats(rydcz_ctx* ctx, int64_t* planned, int64_t* handed_back);
+/* points planned onto the clustered path / handed back to the plain path / 32-byte coefficient records
+ * written for them since the last call of this function (synchronises the device; any pointer may be NULL) */
+int rydcz_cluster_stats(rydcz_ctx* ctx, int64_t* planned, int64_t* handed_back, int64_t* records);
 
 /* One batch of gate evaluations, inputs and outputs resident in device memory.
  * dim: 3 (|0>,|1>,|r>) or 4 (|0>,|1>,|r+>,|r->).  noisy: 0 -> Schroedinger path with the

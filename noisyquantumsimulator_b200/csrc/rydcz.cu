@@ -80,6 +80,7 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
                             unsigned long long* __restrict__ counters) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool clustered = false;
+  int records_planned = 0;
   if (i < n_points) {
     int slot_K[CL_MAX_SLOTS];
 #pragma unroll
@@ -94,7 +95,7 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
       double cost = 0.0;
       const int records = cluster_plan<D>(pt, sg, ns, noisy != 0, true, cost, slot_K);
       if (records > 0 && records <= CL_RECORDS && (cluster_mode == 2 || cost < 0.8 * w)) {
-        clustered = true; group = 0u; w = cost;
+        clustered = true; group = 0u; w = cost; records_planned = records;
       }
     }
     if (task_key) {
@@ -112,7 +113,11 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
     idx[i] = (uint32_t)i;
   }
   const unsigned m = __ballot_sync(0xffffffffu, clustered);
-  if (counters && (threadIdx.x & 31) == 0 && m) atomicAdd(counters, (unsigned long long)__popc(m));
+  const unsigned rsum = __reduce_add_sync(0xffffffffu, (unsigned)records_planned);
+  if (counters && (threadIdx.x & 31) == 0 && m) {
+    atomicAdd(counters, (unsigned long long)__popc(m));
+    atomicAdd(counters + 2, (unsigned long long)rsum);
+  }
 }
 
 // Coefficient records of the clustered path: one thread per task (point, slot), tasks sorted by their
@@ -434,7 +439,7 @@ struct rydcz_ctx {
   // clustered-spectrum path: 0 = off, 1 = where the planner finds it cheaper, 2 = wherever eligible
   int cluster_mode = 1;
   double* cl_scratch = nullptr; size_t cl_cap = 0;      // coefficient records, CL_STRIDE doubles per point
-  unsigned long long* cl_counters = nullptr;            // [0] points planned onto the path, [1] handed back
+  unsigned long long* cl_counters = nullptr;            // [0] points planned onto the path, [1] handed back, [2] records
   bool cl_smem_set = false;
   cudaEvent_t evc0 = nullptr, evc1 = nullptr;           // around the last coefficient kernel
   bool coef_timed = false;
@@ -542,8 +547,8 @@ static int order_reserve(rydcz_ctx* ctx, int64_t n, bool want_cluster = true) {
     ctx->order_cap = (size_t)n;
   }
   if (!ctx->cl_counters) {
-    CK(cudaMalloc(&ctx->cl_counters, 2 * sizeof(unsigned long long)));
-    CK(cudaMemset(ctx->cl_counters, 0, 2 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->cl_counters, 3 * sizeof(unsigned long long)));
+    CK(cudaMemset(ctx->cl_counters, 0, 3 * sizeof(unsigned long long)));
     CK(cudaEventCreate(&ctx->evc0)); CK(cudaEventCreate(&ctx->evc1));
   }
   if (want_cluster && ctx->cluster_mode) {
@@ -724,9 +729,9 @@ int rydcz_set_cluster(rydcz_ctx* ctx, int mode) {
   return 0;
 }
 
-int rydcz_cluster_stats(rydcz_ctx* ctx, int64_t* planned, int64_t* handed_back) {
+int rydcz_cluster_stats(rydcz_ctx* ctx, int64_t* planned, int64_t* handed_back, int64_t* records) {
   if (!ctx) return 2;
-  unsigned long long h[2] = {0, 0};
+  unsigned long long h[3] = {0, 0, 0};
   if (ctx->cl_counters) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());
@@ -735,6 +740,7 @@ int rydcz_cluster_stats(rydcz_ctx* ctx, int64_t* planned, int64_t* handed_back) 
   }
   if (planned) *planned = (int64_t)h[0];
   if (handed_back) *handed_back = (int64_t)h[1];
+  if (records) *records = (int64_t)h[2];
   return 0;
 }
 

@@ -93,10 +93,10 @@ RYDCZ_HD double cluster_cospi(double x) {
 #endif
 }
 
-// prefetch of a coefficient record into L1/L2 (a hint: any address is allowed); no-op on the host
+// prefetch of a coefficient record into L2 (L1 is too small for two lines per resident thread); no-op on the host
 #ifndef RYDCZ_PREFETCH
 #ifdef __CUDA_ARCH__
-#define RYDCZ_PREFETCH(p) asm volatile("prefetch.global.L1 [%0];" ::"l"(p))
+#define RYDCZ_PREFETCH(p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p))
 #else
 #define RYDCZ_PREFETCH(p) ((void)0)
 #endif
@@ -395,7 +395,7 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const PointVi
       n0 = n1 = n2 = 0.0;
     }
     // step k: b2 <- C_k x + 2S~ b1 + b2      (priming: b1 = x, and both vectors restart from zero afterwards)
-    if (k >= 8) RYDCZ_PREFETCH(terms + (k - 8) * CL_REC);   // records are read once, in order: pull the line two ahead
+    if (k >= 16) RYDCZ_PREFETCH(terms + (k - 16) * CL_REC);   // records are read once, in order: pull the line four ahead
     double d0 = n0, d1 = n1, d2 = n2;
     n0 = n1 = n2 = 0.0;
     if (k - 1 <= K) { n0 = terms[(k - 1) * CL_REC]; n1 = terms[(k - 1) * CL_REC + 1]; n2 = terms[(k - 1) * CL_REC + 2]; }

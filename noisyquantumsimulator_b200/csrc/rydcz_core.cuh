@@ -159,6 +159,10 @@ RYDCZ_HD int cheb_terms(double z) {
   int K = (int)ceil(z + 10.3 * (double)(cbrtf((float)z) * 1.000001f) + 4.0);
   return K + (K & 1);
 }
+// The plain loop starts its backward recurrences at a multiple of 8 (more terms are always valid): the
+// lanes of a warp then reach their segment transitions at common iterations, which matters for the short
+// segments of the single-atom systems once the clustered path has made everything else cheap.
+RYDCZ_HD int cheb_terms_aligned(double z) { return (cheb_terms(z) + 7) & ~7; }
 
 // Work estimate used to order points (same formula the evolution uses).
 RYDCZ_HD double cheb_work(double radius, double dt) {
@@ -321,7 +325,7 @@ RYDCZ_HD void run_system(double (&x)[Sys::N], const PointView pt,
         const double sc = sgn * 2.0 / R;
         RYDCZ_UNROLL
         for (int q = 0; q < Sys::NC; ++q) c[q] *= sc;
-        K = cheb_terms(z);
+        K = cheb_terms_aligned(z);
         tz = 2.0 / z;
         rot = cen * h * sgn;
         sub_left = nsub - 1;
@@ -430,7 +434,7 @@ RYDCZ_HD void run_system_big(const XV x, const CV c, const PointView pt, const d
         const double sc = sgn * 2.0 / R;
         RYDCZ_UNROLL
         for (int q = 0; q < Sys::NC; ++q) c[q] *= sc;
-        K = cheb_terms(z);
+        K = cheb_terms_aligned(z);
         tz = 2.0 / z;
         sub_left = nsub - 1;
       }

@@ -249,11 +249,12 @@ class Evaluator:
         """Clustered-spectrum propagation: 0 = never, 1 = where cheaper (default), 2 = wherever eligible."""
         self._check(self.lib.rydcz_set_cluster(self.ctx, int(mode)), "rydcz_set_cluster")
 
-    def cluster_stats(self) -> Tuple[int, int]:
-        """(points planned onto the clustered path, points handed back to the plain path) since the last call."""
-        a, b = C.c_int64(), C.c_int64()
-        self._check(self.lib.rydcz_cluster_stats(self.ctx, C.byref(a), C.byref(b)), "rydcz_cluster_stats")
-        return int(a.value), int(b.value)
+    def cluster_stats(self, with_records: bool = False):
+        """(points planned onto the clustered path, points handed back to the plain path[, coefficient
+        records written]) since the last call."""
+        a, b, r = C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self.lib.rydcz_cluster_stats(self.ctx, C.byref(a), C.byref(b), C.byref(r)), "rydcz_cluster_stats")
+        return (int(a.value), int(b.value), int(r.value)) if with_records else (int(a.value), int(b.value))
 
     def last_coef_ms(self) -> float:
         ms = C.c_float()
