@@ -77,14 +77,14 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
                             int max_seg, int shots, int noisy, int cluster_mode, uint32_t* __restrict__ keys,
                             uint32_t* __restrict__ idx, uint8_t* __restrict__ kind,
                             uint32_t* __restrict__ task_key, uint32_t* __restrict__ task_val,
-                            unsigned long long* __restrict__ counters) {
+                            double* __restrict__ scratch, unsigned long long* __restrict__ counters) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool clustered = false;
   int records_planned = 0;
   if (i < n_points) {
-    int slot_K[CL_MAX_SLOTS];
+    int slot_K[CL_MAX_SLOTS], slot_off[CL_MAX_SLOTS];
 #pragma unroll
-    for (int q = 0; q < CL_MAX_SLOTS; ++q) slot_K[q] = 0;
+    for (int q = 0; q < CL_MAX_SLOTS; ++q) { slot_K[q] = 0; slot_off[q] = 0; }
     const double* pt = points + i * PointStride<D>::value;
     const double* sg = segs + i * (int64_t)max_seg * SG_STRIDE;
     const int ns = n_seg ? n_seg[i] : max_seg;
@@ -93,7 +93,9 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
     uint32_t group = sym ? 1u : 2u;     // general points first (heaviest), then plain folded, then clustered
     if (D != 5 && cluster_mode && sym && !shots) {
       double cost = 0.0;
-      const int records = cluster_plan<D>(pt, sg, ns, noisy != 0, true, cost, slot_K);
+      // the slot headers are written on the way (harmless if the point stays on the plain path)
+      const int records = cluster_plan<D>(pt, sg, ns, noisy != 0, true, cost, slot_K, slot_off,
+                                          scratch + i * (int64_t)CL_STRIDE);
       if (records > 0 && records <= CL_RECORDS && (cluster_mode == 2 || cost < 0.8 * w)) {
         clustered = true; group = 0u; w = cost; records_planned = records;
       }
@@ -104,7 +106,7 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
 #pragma unroll
       for (int q = 0; q < CL_MAX_SLOTS; ++q) {
         task_key[i * CL_MAX_SLOTS + q] = clustered ? (uint32_t)slot_K[q] : 0u;
-        task_val[i * CL_MAX_SLOTS + q] = (uint32_t)(i * CL_MAX_SLOTS + q);
+        task_val[i * CL_MAX_SLOTS + q] = (uint32_t)(i * CL_RECORDS + slot_off[q]);   // record index of the slot header
       }
     }
     kind[i] = clustered ? KIND_CLUSTER : (sym ? KIND_SYM : KIND_GENERAL);
@@ -120,27 +122,15 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
   }
 }
 
-// Coefficient records of the clustered path: one thread per task (point, slot), tasks sorted by their
-// term count so that a warp runs uniform trip counts (key 0 = no such slot: sorted to the end).
-template <int D>
-__global__ void __launch_bounds__(128)
+// Coefficient records of the clustered path: one thread per task = one slot of one point, found through the
+// record index of its header (written by plan_kernel).  Tasks are sorted by their term count so that a
+// warp runs uniform trip counts (key 0 = no such slot: sorted to the end).
+__global__ void __launch_bounds__(128, 3)
 cluster_coef_kernel(int64_t n_tasks, const uint32_t* __restrict__ task_key, const uint32_t* __restrict__ task_val,
-                    const double* __restrict__ points, const double* __restrict__ segs,
-                    const int32_t* __restrict__ n_seg, int max_seg, int noisy, double* __restrict__ scratch) {
+                    double* __restrict__ scratch) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_tasks || task_key[g] == 0u) return;
-  const uint32_t task = task_val[g];
-  const int64_t point = task / CL_MAX_SLOTS;
-  const int slot = (int)(task % CL_MAX_SLOTS);
-  const double* pt = points + point * PointStride<D>::value;
-  ClusterWalker<D> w(pt, segs + point * (int64_t)max_seg * SG_STRIDE, n_seg ? n_seg[point] : max_seg, noisy != 0, true);
-  ClusterSlot sl;
-  double* rec = scratch + point * (int64_t)CL_STRIDE;
-  for (int q = 0; q <= slot; ++q) {
-    if (w.next(sl) != 1) return;
-    if (q < slot) rec += (sl.K + 2) * CL_REC;
-  }
-  cluster_coefficients(sl, rec);
+  cluster_coefficients(scratch + (int64_t)task_val[g] * CL_REC);
 }
 
 // SYM = true handles the points whose two atoms see identical parameters (exchange-folded
@@ -579,13 +569,13 @@ static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const do
                       const double* d_segs, const int32_t* d_n_seg, int max_seg, int shots, int noisy,
                       cudaStream_t st, const uint32_t** order) {
   *order = nullptr;
-  const int mode = (sc.cl && D != 5 && !shots && n < (1 << 27)) ? ctx->cluster_mode : 0;
+  const int mode = (sc.cl && D != 5 && !shots && n * (int64_t)CL_RECORDS < 0xffffffffLL) ? ctx->cluster_mode : 0;
   uint32_t* tk = mode ? sc.task : nullptr;
   uint32_t* tks = mode ? sc.task + sc.task_n : nullptr;
   uint32_t* tv = mode ? sc.task + 2 * sc.task_n : nullptr;
   uint32_t* tvs = mode ? sc.task + 3 * sc.task_n : nullptr;
   plan_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_points, d_segs, d_n_seg, max_seg, shots, noisy,
-                                                              mode, sc.keys, sc.idx, sc.kind, tk, tv,
+                                                              mode, sc.keys, sc.idx, sc.kind, tk, tv, sc.cl,
                                                               ctx->cl_counters);
   CK(cudaGetLastError());
   ctx->launches++;
@@ -605,8 +595,7 @@ static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const do
     if (grow(ctx, sc.tmp, sc.tmp_cap, need)) return 1;
     CK(cub::DeviceRadixSort::SortPairsDescending(*sc.tmp, need, tk, tks, tv, tvs, (int)threads, 0, 7, st));
     CK(cudaEventRecord(ctx->evc0, st));
-    cluster_coef_kernel<D><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(threads, tks, tvs, d_points, d_segs,
-                                                                               d_n_seg, max_seg, noisy, sc.cl);
+    cluster_coef_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(threads, tks, tvs, sc.cl);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->evc1, st));
     ctx->coef_timed = true;

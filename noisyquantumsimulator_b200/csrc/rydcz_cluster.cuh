@@ -7,7 +7,8 @@
 //
 //   * all eigenvalues of H but one stay inside [m, M], the spectral range of H_small (Cauchy
 //     interlacing for the rank-one term V |rr><rr|), and the last one lies in
-//     [E_rr, E_rr + |Omega|^2 / (2 (E_rr - M))], E_rr = V - Delta_A - Delta_B;
+//     [E_rr, E_rr + eta], eta = |Omega|^2 / (2 (E_rr - M)), E_rr = V - Delta_A - Delta_B; for identical
+//     atoms the tighter range of the exchange-symmetric block without |rr> is used, widened by eta below;
 //   * the eigenvalues of the Liouvillian -i[H, .] are differences of those: clusters at 0 and +-i V_c of
 //     half-widths w0 = M - m and w1 = (M - m + eta) / 2; the coherence systems (real form of
 //     v' = -i H_eff v, no spectral shift) have the same three clusters;
@@ -35,7 +36,8 @@ constexpr int CL_REC = 4;          // doubles per coefficient record (d0, d1, d2
 constexpr int CL_MAX_SLOTS = 8;    // distinct (duration, |Omega|, Delta) groups of consecutive segments per point
 constexpr int CL_MAX_K = 62;       // terms per (sub)step; longer segments are cut into equal sub-steps
 constexpr int CL_HALF_MAX = (CL_MAX_K + 2) / 2;
-constexpr int CL_RECORDS = CL_MAX_SLOTS * (CL_MAX_K + 2);   // records per point: header + K + 1 terms per slot
+constexpr int CL_HDR = 8;          // doubles of a slot header (two records)
+constexpr int CL_RECORDS = CL_MAX_SLOTS * (CL_MAX_K + 3);   // records per point: header (2) + K + 1 terms per slot
 constexpr int CL_STRIDE = CL_RECORDS * CL_REC;              // doubles per point in the coefficient scratch
 constexpr int CL_ALIGN = 8;        // Clenshaw steps per (sub)step are padded to a multiple of this, so the
                                    // lanes of a warp reach their segment transitions at common iterations
@@ -71,7 +73,11 @@ RYDCZ_HD bool cluster_geometry(double V, double d1, double rates, double om2, do
   const double Err = V - detA - detB;
   const double gap = Err - M;
   if (!(gap > 0.0)) return false;
-  const double eta = 0.5 * om2 / gap, W = M - m, d = 4.0 * rates;
+  const double eta = 0.5 * om2 / gap, d = 4.0 * rates;
+  // identical atoms: [m, M] is the range of the block WITHOUT |rr>; coupling to |rr> (|F|^2 = |Omega|^2 / 2)
+  // can push its lowest level down by eta as well (Cauchy interlacing for the bordered matrix)
+  if (sym) m -= eta;
+  const double W = M - m;
   const double Vc = Err + 0.5 * (eta - M - m);
   const double w0 = 1.02 * (W + d), w1 = 1.02 * (0.5 * (W + eta) + d);
   const double Vc2 = Vc * Vc;
@@ -165,10 +171,28 @@ struct ClusterWalker {
   }
 };
 
+// Slot header (CL_HDR doubles): K + 1024 nsub, kappa = Vc^2 / gs^2, 1 / gs, count | h, Vc, rho, 0
+// (gs = (rho/2)^(1/3): G~ = G / gs).  The first four are what the evaluator reads; the rest is what
+// cluster_coefficients needs to fill the K + 1 records that follow.
+RYDCZ_HD void cluster_write_header(const ClusterSlot& sl, double* __restrict__ rec) {
+  const double gs = cbrt(0.5 * sl.g.rho);
+  rec[0] = (double)(sl.K + 1024 * sl.nsub);
+  rec[1] = (sl.g.Vc / gs) * (sl.g.Vc / gs);
+  rec[2] = 1.0 / gs;
+  rec[3] = (double)sl.count;
+  rec[4] = sl.h;
+  rec[5] = sl.g.Vc;
+  rec[6] = sl.g.rho;
+  rec[7] = 0.0;
+}
+
 // Records the clustered path needs for a point (0 = not eligible) and its cost in plain Chebyshev terms.
+// With `rec` the slot headers are written on the way (at the positions the evaluator will find them);
+// slot_K / slot_off receive the term count and the record offset of every slot.
 template <int D>
 RYDCZ_HD int cluster_plan(const double* pt, const double* seg, int n_seg, bool noisy, bool sym, double& cost,
-                          int* __restrict__ slot_K = nullptr) {
+                          int* __restrict__ slot_K = nullptr, int* __restrict__ slot_off = nullptr,
+                          double* __restrict__ rec = nullptr) {
   ClusterWalker<D> w(pt, seg, n_seg, noisy, sym);
   ClusterSlot sl;
   int records = 0, slots = 0;
@@ -179,15 +203,16 @@ RYDCZ_HD int cluster_plan(const double* pt, const double* seg, int n_seg, bool n
     if (r == 0) break;
     if (++slots > CL_MAX_SLOTS) return 0;
     if (slot_K) slot_K[slots - 1] = sl.K;
-    records += sl.K + 2;
+    if (slot_off) slot_off[slots - 1] = records;
+    if (rec) cluster_write_header(sl, rec + (long long)records * CL_REC);
+    records += sl.K + 3;
     cost += (double)sl.count * (double)sl.nsub * (CL_STEP_COST * (double)cluster_roundup(sl.K + 2) + CL_SUBSTEP_COST) +
             CL_SLOT_COST;
   }
   return slots == 0 ? 0 : records;
 }
 
-// Header + coefficient records of one slot.
-//   header: K + 1024 nsub, kappa = Vc^2 / gs^2, 1 / gs, count          (gs = (rho/2)^(1/3): G~ = G / gs)
+// Coefficient records of one slot, from its header:
 //   record k = 0..K: d0_k, d1_k, d2_k for  C_k = d0_k + d1_k G~ + d2_k G~^2
 // Nodes t_n = cos(pi (n + 1/2) / N), N = K + 2; the three pre-images of s = i rho t are x = i y with
 // y (Vc^2 - y^2) = rho t: y_0 near 0 and y_+- = +-Vc (1 - e_+-), in units of Vc roots of
@@ -214,17 +239,13 @@ RYDCZ_HD double cluster_root_y(double c) {
   return y;
 }
 
-RYDCZ_HD void cluster_coefficients(const ClusterSlot& sl, double* __restrict__ rec) {
-  const int K = sl.K, N = K + 2, half = N / 2;
-  const double Vc = sl.g.Vc, h = sl.h;
-  const double gs = cbrt(0.5 * sl.g.rho);
-  rec[0] = (double)(K + 1024 * sl.nsub);
-  rec[1] = (Vc / gs) * (Vc / gs);
-  rec[2] = 1.0 / gs;
-  rec[3] = (double)sl.count;
-  double* __restrict__ out = rec + CL_REC;
+RYDCZ_HD void cluster_coefficients(double* __restrict__ rec) {
+  const int K = (int)rec[0] & 1023, N = K + 2, half = N / 2;
+  const double h = rec[4], Vc = rec[5], rho = rec[6];
+  const double gs = cbrt(0.5 * rho);
+  double* __restrict__ out = rec + CL_HDR;
   double ar[3][CL_HALF_MAX], ai[3][CL_HALF_MAX];
-  const double rhat = sl.g.rho / (Vc * Vc * Vc);
+  const double rhat = rho / (Vc * Vc * Vc);
   const double hv = h * Vc, iVc = 1.0 / Vc;
   const double g1 = gs * iVc, g2 = g1 * g1;      // a1 and a2 are built in units of 1/Vc, 1/Vc^2
   double sV, cV;
@@ -278,10 +299,16 @@ RYDCZ_HD void cluster_coefficients(const ClusterSlot& sl, double* __restrict__ r
     sincos((double)kb * (0.5 * pi / (double)N), &sk, &ck);
     sincos((double)kb * (pi / (double)N), &sdk, &cdk);
     double ct = ct0, st = st0;
+    // the node values of the next iteration are loaded while this one computes (they sit in local memory)
+    double r0n = ar[0][0], r1n = ar[1][0], r2n = ar[2][0], i0n = ai[0][0], i1n = ai[1][0], i2n = ai[2][0];
     for (int n = 0; n < half; ++n) {
       const double t2 = ct + ct;
       double Tc = ck, Tn = ck * ct - sk * st;                        // T_kb, T_kb+1
-      const double r0 = ar[0][n], r1 = ar[1][n], r2 = ar[2][n], i0 = ai[0][n], i1 = ai[1][n], i2 = ai[2][n];
+      const double r0 = r0n, r1 = r1n, r2 = r2n, i0 = i0n, i1 = i1n, i2 = i2n;
+      if (n + 1 < half) {
+        r0n = ar[0][n + 1]; r1n = ar[1][n + 1]; r2n = ar[2][n + 1];
+        i0n = ai[0][n + 1]; i1n = ai[1][n + 1]; i2n = ai[2][n + 1];
+      }
       RYDCZ_UNROLL
       for (int q = 0; q < 16; q += 2) {
         acc[q][0] = fma(r0, Tc, acc[q][0]); acc[q][1] = fma(r1, Tc, acc[q][1]); acc[q][2] = fma(r2, Tc, acc[q][2]);
@@ -313,12 +340,11 @@ RYDCZ_HD void cluster_coefficients(const ClusterSlot& sl, double* __restrict__ r
 template <int D>
 RYDCZ_HD void cluster_prepare(const double* pt, const double* seg, int n_seg, bool noisy, bool sym,
                               double* __restrict__ rec) {
-  ClusterWalker<D> w(pt, seg, n_seg, noisy, sym);
-  ClusterSlot sl;
-  while (w.next(sl) == 1) {
-    cluster_coefficients(sl, rec);
-    rec += (sl.K + 2) * CL_REC;
-  }
+  int slot_K[CL_MAX_SLOTS], slot_off[CL_MAX_SLOTS];
+  for (int q = 0; q < CL_MAX_SLOTS; ++q) slot_K[q] = 0;
+  double cost;
+  if (cluster_plan<D>(pt, seg, n_seg, noisy, sym, cost, slot_K, slot_off, rec) <= 0) return;
+  for (int q = 0; q < CL_MAX_SLOTS && slot_K[q] > 0; ++q) cluster_coefficients(rec + (long long)slot_off[q] * CL_REC);
 }
 
 // One Clenshaw step of the clustered expansion:  dst <- C_k x + (2 S~) src + dst,
@@ -376,7 +402,7 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const PointVi
           const int kn = (int)hdr[0];
           K = kn & 1023; nsub = kn >> 10;
           kappa = hdr[1]; inv_gs = hdr[2]; seg_left = (int)hdr[3];
-          terms = hdr + CL_REC;
+          terms = hdr + CL_HDR;
           RYDCZ_PREFETCH(terms + (K + 1) * CL_REC);              // the next slot's header
         }
         --seg_left;

@@ -48,6 +48,7 @@ extern "C" int hostsim_cluster_records(int dim, int noisy, const double* point, 
   using namespace rydcz;
   const int records = dim == 3 ? cluster_plan<3>(point, segs, n_seg, noisy != 0, true, *cost)
                                : cluster_plan<4>(point, segs, n_seg, noisy != 0, true, *cost);
+  if (records > CL_RECORDS) return -records;
   if (records > 0 && rec) {
     if (dim == 3) cluster_prepare<3>(point, segs, n_seg, noisy != 0, true, rec);
     else cluster_prepare<4>(point, segs, n_seg, noisy != 0, true, rec);

@@ -1,0 +1,159 @@
+"""The clustered-spectrum path (csrc/rydcz_cluster.cuh) compiled for the host: spectral enclosure, coefficient
+records, parity with the golden fixtures and the plain Chebyshev path.  CPU only (tests/hostsim)."""
+import ctypes as Ct
+
+import numpy as np
+import pytest
+from scipy.linalg import expm
+
+import _cases as C
+from noisyquantumsimulator_b200.codegen import model as M
+
+REF = C.load("reference_cases.json")
+DP = Ct.POINTER(Ct.c_double)
+
+
+@pytest.fixture(scope="module")
+def hostsim():
+    return C.load_hostsim()
+
+
+def _geometry(om, detA, detB, V, d1, rates, sym):
+    """cluster_geometry (csrc/rydcz_cluster.cuh) restated: centre Vc and half-widths of the three clusters."""
+    def lam(det):
+        a, b = 0.5 * (d1 - det), 0.5 * np.sqrt((d1 + det) ** 2 + om * om)
+        return a - b, a + b
+    lmA, lpA = lam(detA)
+    lmB, lpB = lam(detB)
+    if sym:
+        a, b = 0.5 * (3 * d1 - detA), 0.5 * np.sqrt((d1 + detA) ** 2 + 2 * om * om)
+        m, Mx = min(0.0, lmA, a - b), max(0.0, lpA, a + b)
+    else:
+        m, Mx = min(0.0, lmA) + min(0.0, lmB), max(0.0, lpA) + max(0.0, lpB)
+    Err = V - detA - detB
+    eta = 0.5 * om * om / (Err - Mx)
+    if sym:
+        m -= eta
+    W, d = Mx - m, 4.0 * rates
+    return Err + 0.5 * (eta - Mx - m), W + d, 0.5 * (W + eta) + d
+
+
+def _pvec(s, om, phi, detA, detB, V, d1, r):
+    d = dict(om_re=om * np.cos(phi), om_im=om * np.sin(phi), det=detA, det_a=detA, det_b=detB, V=V, delta1=d1,
+             g_r1=r[0], g_r0=r[1], g_phi=r[2], g_sc=r[3], g_mj=r[4], shift=0.0)
+    return [d.get(k, 0.0) for k in s.params] + ([0.0] if len(s.M) > len(s.params) else [])
+
+
+@pytest.mark.parametrize("dim,sym", [(3, True), (3, False), (4, True), (4, False)])
+def test_every_eigenvalue_lies_in_one_of_the_three_clusters(dim, sym):
+    """The enclosure the path rests on: Im(lambda) within w0 of 0 or within w1 of +-Vc, -damp <= Re(lambda) <= 0,
+    for the density-matrix systems and for the (unshifted) coherence systems."""
+    rng = np.random.default_rng(5 + dim + sym)
+    systems = M.symmetric_systems(dim) if sym else M.standard_systems(dim)
+    names = ["rho11s", "coh11s"] if sym else ["rho11", "coh11"]
+    for _ in range(40):
+        om, phi = 1.0, rng.uniform(-np.pi, np.pi)
+        V = 10 ** rng.uniform(1.0, 3.0)
+        det = rng.choice([0.0, rng.uniform(-1.5, 1.5)])
+        detB = det if sym else det + 0.3 * rng.standard_normal()
+        d1 = rng.choice([0.0, 0.06, rng.uniform(-0.5, 0.5)])
+        r = 10 ** rng.uniform(-5, -1.5, size=5)
+        rates = r[:4].sum() + (r[4] if dim == 4 else 0.0)
+        Vc, w0, w1 = _geometry(om, det, detB, V, d1, rates, sym)
+        for nm in names:
+            s = systems[nm]
+            ev = np.linalg.eigvals(s.generator(_pvec(s, om, phi, det, detB, V, d1, r)[:len(s.M)]))
+            dist0, dist1 = np.abs(ev.imag), np.abs(np.abs(ev.imag) - Vc)
+            assert np.all((dist0 <= w0 * (1 + 1e-9)) | (dist1 <= w1 * (1 + 1e-9))), (nm, V, det, d1)
+            assert ev.real.max() < 1e-9 and ev.real.min() > -4.0 * rates - 1e-9
+
+
+def _records(hostsim, dim, noisy, pt, seg, ns):
+    lib = hostsim.lib
+    lib.hostsim_cluster_records.argtypes = [Ct.c_int, Ct.c_int, DP, DP, Ct.c_int, DP, DP]
+    rec = np.zeros(8 * 65 * 4)
+    cost = Ct.c_double(0)
+    n = lib.hostsim_cluster_records(dim, int(noisy), np.ascontiguousarray(pt).ctypes.data_as(DP),
+                                    np.ascontiguousarray(seg).ctypes.data_as(DP), int(ns), rec.ctypes.data_as(DP),
+                                    Ct.byref(cost))
+    return n, rec.reshape(-1, 4), cost.value
+
+
+def test_coefficient_records_reproduce_the_matrix_exponential(hostsim):
+    """exp(h G) x assembled in NumPy from the records of one LP pulse equals scipy's expm."""
+    case = next(c for c in REF if c["name"] == "lp_noisy")
+    pts, seg, ns = C.pack_batch([case])
+    n, rec, cost = _records(hostsim, 3, True, pts[0], seg[0], ns[0])
+    assert n > 0 and cost > 0
+    K, nsub = int(rec[0, 0]) & 1023, int(rec[0, 0]) >> 10
+    kappa, inv_gs, count = rec[0, 1], rec[0, 2], int(rec[0, 3])
+    assert count == 2 and nsub == 1 and n == K + 3       # both LP pulses share one slot: 2 header records + K + 1 terms
+    assert rec[1, 0] == seg[0, 0, 0] and rec[1, 1] > 0.9 * pts[0, 0]      # h, Vc ~ V
+    d = rec[2:K + 3, :3]
+    assert np.abs(d[-2:]).max() < 1e-13 * np.abs(d).max()     # the series has converged
+    s = M.symmetric_systems(3)["rho11s"]
+    row, sg = pts[0], seg[0, 0]
+    p = dict(om_re=sg[1], om_im=sg[2], det=sg[3], V=row[0], delta1=row[1], g_r1=row[4], g_r0=row[5], g_phi=row[6],
+             g_sc=row[7])
+    G = s.generator([p[k] for k in s.params])
+    Gt = G * inv_gs
+    S2 = Gt @ (Gt @ Gt + kappa * np.eye(s.n))                 # 2 S~
+    x = s.x0.copy()
+    phi_prev, phi = x.copy(), 0.5 * S2 @ x
+    Cx = lambda k, v: d[k, 0] * v + d[k, 1] * (Gt @ v) + d[k, 2] * (Gt @ (Gt @ v))
+    y = Cx(0, phi_prev) + Cx(1, phi)
+    for k in range(2, K + 1):
+        phi, phi_prev = S2 @ phi + phi_prev, phi
+        y = y + Cx(k, phi)
+    assert np.abs(y - expm(sg[0] * G) @ x).max() < 5e-13
+
+
+@pytest.mark.parametrize("case", [c for c in REF if c["dim"] in (3, 4)], ids=lambda c: c["name"])
+def test_states_and_fidelity_match_golden_on_the_clustered_path(hostsim, case):
+    noisy = case["rates"] is not None
+    pts, seg, ns = C.pack_batch([case])
+    out, st = hostsim(case["dim"], noisy, pts, seg, ns, cluster=2)
+    used, handed_back = hostsim.cluster_stats()
+    assert handed_back == 0
+    gold = C.golden_finals(case)
+    ops = C.states_to_operators(case["dim"], st[0])
+    for lab in ("01", "10", "11"):
+        got = ops["rho" + lab] if noisy else ops["coh" + lab][:, 0]
+        assert np.abs(got - gold[lab]).max() < 1e-11
+    res = case["result_coherence"] if noisy else case["result"]
+    assert abs(out[0, C.OUT["avg"]] - res["avg_fidelity"]) < 1e-10
+    assert abs(out[0, C.OUT["czf"]] - res["phase_info"]["cz_phase_fidelity"]) < 1e-10
+
+
+def test_planner_choice_and_work_reduction(hostsim):
+    """cluster=1 takes the path only where it is cheaper: strong blockade yes, V/Omega < 10 and 998 distinct
+    envelope segments no; a bang-bang candidate then needs > 10x fewer operator applications."""
+    want = {"bb5_noisy": True, "lp_noisy": True, "lp_noisy_spacing6p5_vlt10": False, "lp_shaped_cosine_noisy": False}
+    for name, expect in want.items():
+        case = next(c for c in REF if c["name"] == name)
+        pts, seg, ns = C.pack_batch([case])
+        a, _ = hostsim(3, True, pts, seg, ns, cluster=0)
+        hostsim.cluster_stats()
+        b, _ = hostsim(3, True, pts, seg, ns, cluster=1)
+        used, _ = hostsim.cluster_stats()
+        assert (used == 1) == expect, name
+        assert np.abs(a[0, :14] - b[0, :14]).max() < 1e-11
+        if name == "bb5_noisy":
+            assert b[0, C.OUT["steps"]] < 0.1 * a[0, C.OUT["steps"]]
+
+
+def test_strong_dephasing_and_negative_duration_take_substeps(hostsim):
+    """gamma tau > 1 is cut into sub-steps (damp * h <= 1); dt < 0 (the reference's Delta_e < 0 quirk) runs
+    the expansion backwards.  Both against the plain path."""
+    for name in ("lp_noisy_linewidth_1MHz", "lp_noisy_neg_Delta_e"):
+        case = next(c for c in REF if c["name"] == name)
+        pts, seg, ns = C.pack_batch([case])
+        a, sa = hostsim(3, True, pts, seg, ns, cluster=0)
+        hostsim.cluster_stats()
+        b, sb = hostsim(3, True, pts, seg, ns, cluster=2)
+        used, back = hostsim.cluster_stats()
+        assert used == 1 and back == 0
+        assert np.abs(sa - sb).max() < 1e-11
+    n, rec, _ = _records(hostsim, 3, True, *[x[0] for x in C.pack_batch(
+        [next(c for c in REF if c["name"] == "lp_noisy_linewidth_1MHz")])])
+    assert (int(rec[0, 0]) >> 10) > 1
