@@ -214,7 +214,8 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, int64_t point_base,
 // coefficient records were written by cluster_coef_kernel into the point's region of `scratch`.
 template <int D> struct ClusterSmem {
   static constexpr int XN = D == 3 ? Sys_rho11s_d3::N : Sys_rho11s_d4::N;
-  static constexpr int SLOTS = PT_MAX_STRIDE + PT_SCRATCH + 3 * XN;
+  static constexpr int RING0 = PT_MAX_STRIDE + PT_SCRATCH + 3 * XN;      // first column of the record ring
+  static constexpr int SLOTS = RING0 + 3 * ClusterRing<D>::value;
   static constexpr size_t BYTES = (size_t)SLOTS * kBlock * sizeof(double);
 };
 template <int D, bool NOISY>
@@ -240,14 +241,15 @@ evaluate_cluster_kernel(int64_t n_items, const uint32_t* __restrict__ order, uin
   for (int k = 0; k < PT_STRIDE; ++k) mine[k * kBlock] = row[k];
   const PointView pt{mine, kBlock, live};
   const Col xcol{mine + (PT_MAX_STRIDE + PT_SCRATCH) * kBlock, kBlock};
+  const Col rcol{mine + ClusterSmem<D>::RING0 * kBlock, kBlock};
   const double* sg = segs + point * (int64_t)max_seg * SG_STRIDE;
   const int ns = n_seg ? n_seg[point] : max_seg;
   const double* rec = scratch + point * (int64_t)CL_STRIDE;
   double o[OUT_STRIDE];
   double* st = states ? states + point * StateLayout<D>::STRIDE : nullptr;
   bool ok;
-  if (D == 3) ok = evaluate_point_cluster_d3<NOISY>(pt, xcol, sg, ns, rec, o, st);
-  else ok = evaluate_point_cluster_d4<NOISY>(pt, xcol, sg, ns, rec, o, st);
+  if (D == 3) ok = evaluate_point_cluster_d3<NOISY>(pt, xcol, rcol, sg, ns, rec, o, st);
+  else ok = evaluate_point_cluster_d4<NOISY>(pt, xcol, rcol, sg, ns, rec, o, st);
   if (!ok) {
     // invariant check failed: hand the point to the plain folded kernel, which runs after this one
     kind[point] = KIND_SYM;
@@ -431,6 +433,7 @@ struct rydcz_ctx {
   double* cl_scratch = nullptr; size_t cl_cap = 0;      // coefficient records, CL_STRIDE doubles per point
   unsigned long long* cl_counters = nullptr;            // [0] points planned onto the path, [1] handed back, [2] records
   bool cl_smem_set = false;
+  bool coef_attr_set = false;
   cudaEvent_t evc0 = nullptr, evc1 = nullptr;           // around the last coefficient kernel
   bool coef_timed = false;
   void* cub_tmp = nullptr; size_t cub_cap = 0;
@@ -594,6 +597,11 @@ static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const do
     CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, tk, tks, tv, tvs, (int)threads, 0, 7, st));
     if (grow(ctx, sc.tmp, sc.tmp_cap, need)) return 1;
     CK(cub::DeviceRadixSort::SortPairsDescending(*sc.tmp, need, tk, tks, tv, tvs, (int)threads, 0, 7, st));
+    if (!ctx->coef_attr_set) {
+      // the node values live in local memory: give L1 everything (the kernel uses no shared memory)
+      CK(cudaFuncSetAttribute(cluster_coef_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+      ctx->coef_attr_set = true;
+    }
     CK(cudaEventRecord(ctx->evc0, st));
     cluster_coef_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(threads, tks, tvs, sc.cl);
     CK(cudaGetLastError());

@@ -108,6 +108,22 @@ RYDCZ_HD double cluster_cospi(double x) {
 #endif
 #endif
 
+// Asynchronous 8-byte copies global -> shared (cp.async), committed in per-thread groups: the ring of
+// coefficient records that run_system_cluster consumes is filled RING - 1 steps ahead of its use without
+// holding registers.  Plain copies on the host.
+#ifndef RYDCZ_ASYNC_COPY8
+#ifdef __CUDA_ARCH__
+#define RYDCZ_ASYNC_COPY8(dst, src)                                                             \
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory")
+#define RYDCZ_ASYNC_COMMIT() asm volatile("cp.async.commit_group;" ::: "memory")
+#define RYDCZ_ASYNC_WAIT(n) asm volatile("cp.async.wait_group %0;" ::"n"(n) : "memory")
+#else
+#define RYDCZ_ASYNC_COPY8(dst, src) (*(dst) = *(src))
+#define RYDCZ_ASYNC_COMMIT() ((void)0)
+#define RYDCZ_ASYNC_WAIT(n) ((void)0)
+#endif
+#endif
+
 RYDCZ_HD int cluster_roundup(int steps) { return (steps + CL_ALIGN - 1) / CL_ALIGN * CL_ALIGN; }
 
 // One slot: `count` consecutive active segments with the same duration, |Omega| and Delta, each advanced
@@ -152,7 +168,7 @@ struct ClusterWalker {
     sl.h = dt / (double)sl.nsub;
     double zs = z / (double)sl.nsub;
     if (!(zs >= 1e-2)) zs = 1e-2;
-    sl.K = cheb_terms(zs) + 2;
+    sl.K = cheb_terms(zs);
     if (sl.K > CL_MAX_K) return -1;
     sl.count = 1;
     ++s;
@@ -375,19 +391,32 @@ RYDCZ_HD void cluster_step(const double* __restrict__ c, double kappa, double d0
 // (sub)step the lane is in.  A (sub)step takes roundup(K + 2, CL_ALIGN) steps -- the priming step, K + 1
 // recurrence steps, padding with zero coefficients in front -- so the lanes of a warp reach their
 // transitions at common iterations, and a transition itself is only the header / segment bookkeeping.
-// `rec` = the point's coefficient records, `xc` = 3 N per-thread columns for the start vectors.
-template <class Sys, class XC>
-RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const PointView pt,
+// `rec` = the point's coefficient records, `xc` = 3 N per-thread columns for the start vectors, `rc` =
+// 3 RING per-thread columns: the ring through which the records arrive (record k sits in slot k % RING,
+// copied asynchronously RING - 1 steps before step k reads it; every step commits one copy group).
+template <class Sys, int RING, class XC>
+RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const XC rc, const PointView pt,
                                  const double* __restrict__ seg, int n_seg, bool noisy,
                                  const double* __restrict__ rec, double& steps) {
   constexpr int N = Sys::N;
+  static_assert((RING & (RING - 1)) == 0 && RING >= 2, "ring size");
   double c[Sys::NC], b1[N], b2[N];
   Sys::init(b1);
   int k = -1, K = -1, nsub = 1, sub_left = 0, seg_left = 0, s = 0;
   bool priming = false;
   double kappa = 0.0, inv_gs = 0.0;
   const double* terms = rec;
-  double n0 = 0.0, n1 = 0.0, n2 = 0.0;   // record of the step about to run (loaded one step ahead)
+#define RYDCZ_RING_FETCH(kk)                                                                    \
+  do {                                                                                          \
+    const int kf_ = (kk);                                                                       \
+    if (kf_ >= 0 && kf_ <= K) {                                                                 \
+      const int sl_ = (kf_ & (RING - 1)) * 3;                                                   \
+      RYDCZ_ASYNC_COPY8(&rc[sl_], terms + kf_ * CL_REC);                                        \
+      RYDCZ_ASYNC_COPY8(&rc[sl_ + 1], terms + kf_ * CL_REC + 1);                                \
+      RYDCZ_ASYNC_COPY8(&rc[sl_ + 2], terms + kf_ * CL_REC + 2);                                \
+    }                                                                                           \
+    RYDCZ_ASYNC_COMMIT();                                                                       \
+  } while (0)
   for (;;) {
     if (k < 0) {
       // b1 holds the state.  Next sub-step of this segment, or the next segment (and maybe the next slot).
@@ -418,13 +447,15 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const PointVi
       for (int i = 0; i < N; ++i) b2[i] = 0.0;
       k = cluster_roundup(K + 2) - 1;    // the priming step (k > K: zero coefficients), then k - 1 ... 0
       priming = true;
-      n0 = n1 = n2 = 0.0;
+      // fill the ring: records k ... k - (RING - 2); step j then fetches record j - (RING - 1)
+      RYDCZ_UNROLL
+      for (int q = 0; q < RING - 1; ++q) RYDCZ_RING_FETCH(k - q);
     }
     // step k: b2 <- C_k x + 2S~ b1 + b2      (priming: b1 = x, and both vectors restart from zero afterwards)
-    if (k >= 16) RYDCZ_PREFETCH(terms + (k - 16) * CL_REC);   // records are read once, in order: pull the line four ahead
-    double d0 = n0, d1 = n1, d2 = n2;
-    n0 = n1 = n2 = 0.0;
-    if (k - 1 <= K) { n0 = terms[(k - 1) * CL_REC]; n1 = terms[(k - 1) * CL_REC + 1]; n2 = terms[(k - 1) * CL_REC + 2]; }
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0;
+    RYDCZ_ASYNC_WAIT(RING - 2);
+    if (k <= K) { const int sl = (k & (RING - 1)) * 3; d0 = rc[sl]; d1 = rc[sl + 1]; d2 = rc[sl + 2]; }
+    RYDCZ_RING_FETCH(k - (RING - 1));
     cluster_step<Sys>(c, kappa, d0, d1, d2, xc, b1, b2, priming);
     if (priming) {
       RYDCZ_UNROLL
@@ -432,9 +463,10 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const PointVi
       priming = false;
     }
     // step k-1: b1 <- C_{k-1} x + 2S~ b2 + b1; the last one (k-1 = 0) takes S~ b2 instead: halve b2
-    d0 = n0; d1 = n1; d2 = n2;
-    n0 = n1 = n2 = 0.0;
-    if (k >= 2 && k - 2 <= K) { n0 = terms[(k - 2) * CL_REC]; n1 = terms[(k - 2) * CL_REC + 1]; n2 = terms[(k - 2) * CL_REC + 2]; }
+    d0 = 0.0; d1 = 0.0; d2 = 0.0;
+    RYDCZ_ASYNC_WAIT(RING - 2);
+    if (k - 1 <= K) { const int sl = ((k - 1) & (RING - 1)) * 3; d0 = rc[sl]; d1 = rc[sl + 1]; d2 = rc[sl + 2]; }
+    RYDCZ_RING_FETCH(k - 1 - (RING - 1));
     if (k == 1) {
       RYDCZ_UNROLL
       for (int i = 0; i < N; ++i) b2[i] *= 0.5;
@@ -442,6 +474,8 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const PointVi
     cluster_step<Sys>(c, kappa, d0, d1, d2, xc, b2, b1, false);
     k -= 2;
   }
+#undef RYDCZ_RING_FETCH
+  RYDCZ_ASYNC_WAIT(0);
   RYDCZ_UNROLL
   for (int i = 0; i < N; ++i) x[i] = b1[i];
 }
@@ -449,9 +483,13 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const PointVi
 // One full gate evaluation on the clustered path (identical atoms; the |01> input has no blockade shift
 // and stays on the plain path).  Returns false when the invariant check fails (trace of rho_11, norm of
 // the noiseless ket): the caller then leaves the point to the plain kernel.
+// slots of the record ring: 8 for the 3-level model; 4 for the 4-level one, whose 63 start-vector columns
+// leave less shared memory at two CTAs per SM
+template <int D> struct ClusterRing { static constexpr int value = D == 3 ? 8 : 4; };
+
 #define RYDCZ_DEFINE_EVALUATE_CLUSTER(D)                                                            \
   template <bool NOISY>                                                                             \
-  RYDCZ_HD bool evaluate_point_cluster_d##D(const PointView pt, const Col xcol,                     \
+  RYDCZ_HD bool evaluate_point_cluster_d##D(const PointView pt, const Col xcol, const Col rcol,     \
                                             const double* __restrict__ seg, int n_seg,              \
                                             const double* __restrict__ rec,                         \
                                             double* __restrict__ out, double* __restrict__ states) {\
@@ -462,7 +500,7 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const PointVi
     bool ok = true;                                                                                 \
     if (NOISY) {                                                                                    \
       double x[Sys_rho11s_d##D::N]; st = 0.0;                                                       \
-      run_system_cluster<Sys_rho11s_d##D>(x, xcol, pt, seg, n_seg, true, rec, st);                  \
+      run_system_cluster<Sys_rho11s_d##D, ClusterRing<D>::value>(x, xcol, rcol, pt, seg, n_seg, true, rec, st); \
       RYDCZ_RECONVERGE(pt.live);                                                                    \
       steps += st; flops += st * 2.0 * (3 * Sys_rho11s_d##D::NNZ + 4 * Sys_rho11s_d##D::N);         \
       p11 = x[RHO11S_POP_D##D];                                                                     \
@@ -474,7 +512,7 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const PointVi
     }                                                                                               \
     {                                                                                               \
       double x[Sys_coh11s_d##D::N]; st = 0.0;                                                       \
-      run_system_cluster<Sys_coh11s_d##D>(x, xcol, pt, seg, n_seg, NOISY, rec, st);                 \
+      run_system_cluster<Sys_coh11s_d##D, ClusterRing<D>::value>(x, xcol, rcol, pt, seg, n_seg, NOISY, rec, st); \
       RYDCZ_RECONVERGE(pt.live);                                                                    \
       steps += st; flops += st * 2.0 * (3 * Sys_coh11s_d##D::NNZ + 4 * Sys_coh11s_d##D::N);         \
       c11r = x[COH11S_RE_D##D]; c11i = x[COH11S_IM_D##D];                                           \
