@@ -122,15 +122,24 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
   }
 }
 
-// Coefficient records of the clustered path: one thread per task = one slot of one point, found through the
-// record index of its header (written by plan_kernel).  Tasks are sorted by their term count so that a
-// warp runs uniform trip counts (key 0 = no such slot: sorted to the end).
-__global__ void __launch_bounds__(128, 3)
+// Coefficient records of the clustered path: four lanes per task = one slot of one point, found through
+// the record index of its header (written by plan_kernel).  The lanes split the Gauss nodes, exchange the
+// node values through shared memory ([value][node][task], 48 KB per CTA) and then split the blocks of
+// eight coefficients.  Tasks are sorted by their term count so that a warp runs uniform trip counts
+// (key 0 = no such slot: sorted to the end).
+constexpr int kCoefLanes = 4;
+constexpr int kCoefTasksPerCta = kBlock / kCoefLanes;
+__global__ void __launch_bounds__(kBlock, 4)
 cluster_coef_kernel(int64_t n_tasks, const uint32_t* __restrict__ task_key, const uint32_t* __restrict__ task_val,
                     double* __restrict__ scratch) {
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_tasks || task_key[g] == 0u) return;
-  cluster_coefficients(scratch + (int64_t)task_val[g] * CL_REC);
+  __shared__ double s_a[6 * CL_HALF_MAX * kCoefTasksPerCta];
+  const int t_in_cta = threadIdx.x / kCoefLanes, m = threadIdx.x % kCoefLanes;
+  const int64_t g = (int64_t)blockIdx.x * kCoefTasksPerCta + t_in_cta;
+  // the four lanes of a task take the same branch; a warp whose tasks are all absent leaves together
+  const bool have = g < n_tasks && task_key[g] != 0u;
+  if (!__any_sync(0xffffffffu, have)) return;
+  if (have) cluster_coefficients(scratch + (int64_t)task_val[g] * CL_REC, s_a + t_in_cta, kCoefTasksPerCta, m, kCoefLanes);
+  else __syncwarp();     // pairs with the group barrier inside cluster_coefficients
 }
 
 // SYM = true handles the points whose two atoms see identical parameters (exchange-folded
@@ -433,7 +442,6 @@ struct rydcz_ctx {
   double* cl_scratch = nullptr; size_t cl_cap = 0;      // coefficient records, CL_STRIDE doubles per point
   unsigned long long* cl_counters = nullptr;            // [0] points planned onto the path, [1] handed back, [2] records
   bool cl_smem_set = false;
-  bool coef_attr_set = false;
   cudaEvent_t evc0 = nullptr, evc1 = nullptr;           // around the last coefficient kernel
   bool coef_timed = false;
   void* cub_tmp = nullptr; size_t cub_cap = 0;
@@ -597,13 +605,9 @@ static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const do
     CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, tk, tks, tv, tvs, (int)threads, 0, 7, st));
     if (grow(ctx, sc.tmp, sc.tmp_cap, need)) return 1;
     CK(cub::DeviceRadixSort::SortPairsDescending(*sc.tmp, need, tk, tks, tv, tvs, (int)threads, 0, 7, st));
-    if (!ctx->coef_attr_set) {
-      // the node values live in local memory: give L1 everything (the kernel uses no shared memory)
-      CK(cudaFuncSetAttribute(cluster_coef_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
-      ctx->coef_attr_set = true;
-    }
     CK(cudaEventRecord(ctx->evc0, st));
-    cluster_coef_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(threads, tks, tvs, sc.cl);
+    cluster_coef_kernel<<<(unsigned)((threads + kCoefTasksPerCta - 1) / kCoefTasksPerCta), kBlock, 0, st>>>(
+        threads, tks, tvs, sc.cl);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->evc1, st));
     ctx->coef_timed = true;

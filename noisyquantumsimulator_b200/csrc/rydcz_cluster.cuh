@@ -255,25 +255,36 @@ RYDCZ_HD double cluster_root_y(double c) {
   return y;
 }
 
-RYDCZ_HD void cluster_coefficients(double* __restrict__ rec) {
+// G lanes work on one slot (G = 4 consecutive lanes of a warp on the GPU, 1 on the host); lane m takes the
+// nodes n = m, m + G, ... and then the blocks of eight k starting at 8 m, 8 (m + G), ...  The node values
+// a_j(t_n) go through `A` (element (v, n) at A[(v * CL_HALF_MAX + n) * a_stride]; shared memory on the
+// GPU), with a group barrier between the two phases.
+#ifndef RYDCZ_GROUP_SYNC
+#ifdef __CUDA_ARCH__
+#define RYDCZ_GROUP_SYNC() __syncwarp()
+#else
+#define RYDCZ_GROUP_SYNC() ((void)0)
+#endif
+#endif
+RYDCZ_HD void cluster_coefficients(double* __restrict__ rec, double* __restrict__ A, int a_stride, int m, int G) {
   const int K = (int)rec[0] & 1023, N = K + 2, half = N / 2;
   const double h = rec[4], Vc = rec[5], rho = rec[6];
   const double gs = cbrt(0.5 * rho);
   double* __restrict__ out = rec + CL_HDR;
-  double ar[3][CL_HALF_MAX], ai[3][CL_HALF_MAX];
+#define RYDCZ_A(v, n) A[((v) * CL_HALF_MAX + (n)) * a_stride]
   const double rhat = rho / (Vc * Vc * Vc);
   const double hv = h * Vc, iVc = 1.0 / Vc;
   const double g1 = gs * iVc, g2 = g1 * g1;      // a1 and a2 are built in units of 1/Vc, 1/Vc^2
   double sV, cV;
   sincos(hv, &sV, &cV);
-  // node angles theta_n = pi (n + 1/2) / N by rotation: (ct, st) <- (ct, st) rotated by pi / N
+  // node angles theta_n = pi (n + 1/2) / N, advanced by rotation
   const double pi = 3.141592653589793238462643383279;
-  double st0, ct0, sd, cd;
-  sincos(0.5 * pi / (double)N, &st0, &ct0);
-  sincos(pi / (double)N, &sd, &cd);
+  const double dth = pi / (double)N;
   {
-    double ct = ct0, st = st0;
-    for (int n = 0; n < half; ++n) {
+    double st, ct, sd, cd;
+    sincos(((double)m + 0.5) * dth, &st, &ct);
+    sincos((double)G * dth, &sd, &cd);
+    for (int n = m; n < half; n += G) {
       const double c = rhat * ct;
       const double y0 = cluster_root_y(c), ep = cluster_root_e(c), em = cluster_root_e(-c);
       // f_m = exp(i h y_m)
@@ -294,39 +305,39 @@ RYDCZ_HD void cluster_coefficients(double* __restrict__ rec) {
       // p(x) = f_0 + f[0,+] (x - x_0) + f[0,+,-] (x - x_0)(x - x_+) = a0 + a1 x + a2 x^2
       const double ys = y0 + Yp, yp = y0 * Yp;
       const double a1r = d01r + ys * d012i, a1i = d01i - ys * d012r;            // d01 - i ys d012
-      ar[0][n] = c0 + y0 * d01i - yp * d012r; ai[0][n] = s0 - y0 * d01r - yp * d012i;   // f0 - i y0 d01 - y0 yp d012
-      ar[1][n] = a1r * g1; ai[1][n] = a1i * g1;
-      ar[2][n] = d012r * g2; ai[2][n] = d012i * g2;
+      RYDCZ_A(0, n) = c0 + y0 * d01i - yp * d012r;                              // f0 - i y0 d01 - y0 yp d012
+      RYDCZ_A(1, n) = s0 - y0 * d01r - yp * d012i;
+      RYDCZ_A(2, n) = a1r * g1; RYDCZ_A(3, n) = a1i * g1;
+      RYDCZ_A(4, n) = d012r * g2; RYDCZ_A(5, n) = d012i * g2;
       const double cn = ct * cd - st * sd;
       st = st * cd + ct * sd; ct = cn;
     }
   }
-  // cosine transform, sixteen k at a time for all three j (48 accumulators in registers).  Within a
-  // block the Chebyshev recurrence runs from T_kb, T_kb+1 = cos(kb theta), cos((kb + 1) theta), which are
-  // carried from node to node by rotation, so no per-node state is kept in memory and every record is
-  // written once, whole.  Even k pick up Re a_j, odd k Im a_j (conjugate symmetry of the +-t node pairs).
+  RYDCZ_GROUP_SYNC();
+  // cosine transform, eight k at a time for all three j (24 accumulators in registers).  Within a block
+  // the Chebyshev recurrence runs from T_kb, T_kb+1 = cos(kb theta), cos((kb + 1) theta), which are carried
+  // from node to node by rotation, so every record is written once, whole.  Even k pick up Re a_j, odd k
+  // Im a_j (conjugate symmetry of the +-t node pairs).
   const double scale = 4.0 / (double)N;
-  for (int kb = 0; kb <= K; kb += 16) {
-    double acc[16][3];
+  double st0, ct0, sd, cd;
+  sincos(0.5 * dth, &st0, &ct0);
+  sincos(dth, &sd, &cd);
+  for (int kb = 8 * m; kb <= K; kb += 8 * G) {
+    double acc[8][3];
     RYDCZ_UNROLL
-    for (int q = 0; q < 16; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; acc[q][2] = 0.0; }
+    for (int q = 0; q < 8; ++q) { acc[q][0] = 0.0; acc[q][1] = 0.0; acc[q][2] = 0.0; }
     // cos / sin of kb theta_0 and of the step kb pi / N
     double sk, ck, sdk, cdk;
-    sincos((double)kb * (0.5 * pi / (double)N), &sk, &ck);
-    sincos((double)kb * (pi / (double)N), &sdk, &cdk);
+    sincos((double)kb * (0.5 * dth), &sk, &ck);
+    sincos((double)kb * dth, &sdk, &cdk);
     double ct = ct0, st = st0;
-    // the node values of the next iteration are loaded while this one computes (they sit in local memory)
-    double r0n = ar[0][0], r1n = ar[1][0], r2n = ar[2][0], i0n = ai[0][0], i1n = ai[1][0], i2n = ai[2][0];
     for (int n = 0; n < half; ++n) {
       const double t2 = ct + ct;
       double Tc = ck, Tn = ck * ct - sk * st;                        // T_kb, T_kb+1
-      const double r0 = r0n, r1 = r1n, r2 = r2n, i0 = i0n, i1 = i1n, i2 = i2n;
-      if (n + 1 < half) {
-        r0n = ar[0][n + 1]; r1n = ar[1][n + 1]; r2n = ar[2][n + 1];
-        i0n = ai[0][n + 1]; i1n = ai[1][n + 1]; i2n = ai[2][n + 1];
-      }
+      const double r0 = RYDCZ_A(0, n), i0 = RYDCZ_A(1, n), r1 = RYDCZ_A(2, n), i1 = RYDCZ_A(3, n),
+                   r2 = RYDCZ_A(4, n), i2 = RYDCZ_A(5, n);
       RYDCZ_UNROLL
-      for (int q = 0; q < 16; q += 2) {
+      for (int q = 0; q < 8; q += 2) {
         acc[q][0] = fma(r0, Tc, acc[q][0]); acc[q][1] = fma(r1, Tc, acc[q][1]); acc[q][2] = fma(r2, Tc, acc[q][2]);
         acc[q + 1][0] = fma(i0, Tn, acc[q + 1][0]); acc[q + 1][1] = fma(i1, Tn, acc[q + 1][1]);
         acc[q + 1][2] = fma(i2, Tn, acc[q + 1][2]);
@@ -339,7 +350,7 @@ RYDCZ_HD void cluster_coefficients(double* __restrict__ rec) {
       sk = sk * cdk + ck * sdk; ck = cn;
     }
     RYDCZ_UNROLL
-    for (int q = 0; q < 16; ++q) {
+    for (int q = 0; q < 8; ++q) {
       const int k = kb + q;
       if (k <= K) {
         const double sc = ((k & 2) ? -scale : scale) * (k == 0 ? 0.5 : 1.0);   // i^{-k} on the surviving part
@@ -350,6 +361,7 @@ RYDCZ_HD void cluster_coefficients(double* __restrict__ rec) {
       }
     }
   }
+#undef RYDCZ_A
 }
 
 // All slots of a point, one after the other (the host harness; the GPU runs one thread per slot).
@@ -360,7 +372,9 @@ RYDCZ_HD void cluster_prepare(const double* pt, const double* seg, int n_seg, bo
   for (int q = 0; q < CL_MAX_SLOTS; ++q) slot_K[q] = 0;
   double cost;
   if (cluster_plan<D>(pt, seg, n_seg, noisy, sym, cost, slot_K, slot_off, rec) <= 0) return;
-  for (int q = 0; q < CL_MAX_SLOTS && slot_K[q] > 0; ++q) cluster_coefficients(rec + (long long)slot_off[q] * CL_REC);
+  double A[6 * CL_HALF_MAX];
+  for (int q = 0; q < CL_MAX_SLOTS && slot_K[q] > 0; ++q)
+    cluster_coefficients(rec + (long long)slot_off[q] * CL_REC, A, 1, 0, 1);
 }
 
 // One Clenshaw step of the clustered expansion:  dst <- C_k x + (2 S~) src + dst,
