@@ -460,7 +460,7 @@ struct rydcz_ctx {
   };
   static constexpr int kLanes = 3;
   Lane lane[kLanes];
-  int64_t chunk = 65536;                          // points per pipeline chunk
+  int64_t chunk = 32768;                          // points per pipeline chunk (profiles/r01_e2e_chunk_sweep_v9.txt)
 };
 
 // scratch of one work sort (the default one belongs to the context; every lane has its own)
@@ -1041,9 +1041,9 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
     cs.v[k] = h_const[k];
     if (h_cols[k]) var[n_var++] = k; else cs.mask |= 1ull << k;
   }
-  // chunking: a chunk must still fill the GPU (two 128-thread CTAs per SM ~ 38k threads).  (Quarter-size
-  // first and last chunks were tried to shorten the pipeline's fill and drain: 0.6 ms slower per
-  // 262,144 candidates, a 16k-point chunk alone on the GPU wastes more than the shorter copy saves.)
+  // chunking: with the clustered path a 32,768-point chunk takes ~0.5 ms of kernels, the chunks of the three
+  // lanes overlap on the GPU, and a shorter chunk shortens the pipeline's fill and drain (sweep on 262,144
+  // bang-bang candidates: 65,536 -> 45.7, 49,152 -> 50.6, 32,768 -> 56.3, 16,384 -> 47.6 M evaluations/s).
   const int64_t per_item = n_shots > 0 ? n_shots : 1;
   int64_t chunk = ctx->chunk / per_item;
   if (chunk < 1024) chunk = 1024;

@@ -29,9 +29,12 @@ def timed(fn, reps=5):
 def line(name, n_evals, dt, res, extra=None):
     raw = res.raw
     flops = float(raw[:, 15].sum())
-    k_ms = ev.last_kernel_ms()
+    e_ms, c_ms = ev.last_kernel_ms(), ev.last_coef_ms()
+    planned, back = ev.cluster_stats()
+    k_ms = e_ms + (c_ms if planned else 0.0)      # evaluate kernels + (clustered path) coefficient kernel
     d = dict(config=name, evals_per_call=n_evals, api_ms=dt * 1e3, evals_per_s_api=n_evals / dt, kernel_ms=k_ms,
-             evals_per_s_kernel=n_evals / (k_ms * 1e-3), flops=flops, tflops_kernel=flops / (k_ms * 1e-3) * 1e-12,
+             evaluate_ms=e_ms, coef_ms=c_ms if planned else 0.0, clustered=bool(planned), handed_back=back,
+             evals_per_s_kernel=n_evals / (k_ms * 1e-3), flops=flops, tflops_kernel=flops / (e_ms * 1e-3) * 1e-12,
              mean_fidelity=float(res.avg_fidelity.mean()))
     d.update(extra or {})
     print(json.dumps(d), flush=True)
