@@ -15,7 +15,7 @@ DEPS = ["rydcz.cu", "rydcz_core.cuh", "rydcz_cluster.cuh", "rydcz_prologue.cuh",
         os.path.join("..", "..", "include", "rydcz.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+              "--shared", "-Xcompiler", "-fPIC,-fopenmp", "-Xptxas", "-v", "-lgomp"]
 
 
 def nvcc_path() -> str:

@@ -335,13 +335,18 @@ __global__ void prologue_kernel(ModelArg md, int64_t n_points, const double* __r
 
 // apparatus slots that are the same for every point of a batch are not sent over PCIe: the host
 // passes their values once and this kernel writes them into the slot-major block
-struct ConstSlots { double v[APP_STRIDE]; uint64_t mask; };
-__global__ void fill_slots_kernel(ConstSlots cs, int64_t n_points, double* __restrict__ app, int64_t app_stride) {
+// ... and the slots that do vary arrive as one packed block [n_var][packed_stride] (a single H2D copy per
+// chunk) and are scattered to their slot rows here.
+struct ConstSlots { double v[APP_STRIDE]; uint64_t mask; int var[APP_STRIDE]; int n_var; };
+__global__ void fill_slots_kernel(ConstSlots cs, int64_t n_points, double* __restrict__ app, int64_t app_stride,
+                                  const double* __restrict__ packed, int64_t packed_stride) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_points) return;
 #pragma unroll 1
   for (int k = 0; k < APP_STRIDE; ++k)
     if ((cs.mask >> k) & 1ull) app[(int64_t)k * app_stride + i] = cs.v[k];
+#pragma unroll 1
+  for (int j = 0; j < cs.n_var; ++j) app[(int64_t)cs.var[j] * app_stride + i] = packed[(int64_t)j * packed_stride + i];
 }
 
 // deterministic shot mean: one warp per point, fixed-order tree
@@ -456,6 +461,7 @@ struct rydcz_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ring_free = nullptr;              // the H2D copies out of `ring` have completed
     double* ring = nullptr; size_t ring_cap = 0;  // page-locked staging for the packed columns
+    double* d_ring = nullptr;                     // its device twin (scattered to the slot rows by fill_slots_kernel)
     void* cub_tmp = nullptr; size_t cub_cap = 0;
   };
   static constexpr int kLanes = 3;
@@ -708,6 +714,7 @@ void rydcz_destroy(rydcz_ctx* ctx) {
     if (L.stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
     if (L.ring_free) cudaEventDestroy(L.ring_free);
     if (L.ring) cudaFreeHost(L.ring);
+    cudaFree(L.d_ring);
     cudaFree(L.cub_tmp);
   }
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
@@ -1039,8 +1046,10 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
   cs.mask = 0;
   for (int k = 0; k < APP_STRIDE; ++k) {
     cs.v[k] = h_const[k];
-    if (h_cols[k]) var[n_var++] = k; else cs.mask |= 1ull << k;
+    cs.var[k] = 0;
+    if (h_cols[k]) { cs.var[n_var] = k; var[n_var++] = k; } else cs.mask |= 1ull << k;
   }
+  cs.n_var = n_var;
   // chunking: with the clustered path a 32,768-point chunk takes ~0.5 ms of kernels, the chunks of the three
   // lanes overlap on the GPU, and a shorter chunk shortens the pipeline's fill and drain (sweep on 262,144
   // bang-bang candidates: 65,536 -> 45.7, 49,152 -> 50.6, 32,768 -> 56.3, 16,384 -> 47.6 M evaluations/s).
@@ -1079,6 +1088,9 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
       if (L.ring) CK(cudaFreeHost(L.ring));
       L.ring = nullptr; L.ring_cap = 0;
       CK(cudaHostAlloc((void**)&L.ring, need, cudaHostAllocDefault));
+      if (L.d_ring) CK(cudaFree(L.d_ring));
+      L.d_ring = nullptr;
+      CK(cudaMalloc((void**)&L.d_ring, need));
       L.ring_cap = need;
     }
   }
@@ -1088,20 +1100,22 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
     const int64_t i0 = c * chunk;
     const int64_t nc = (i0 + chunk <= n_points) ? chunk : n_points - i0;
     if (c >= rydcz_ctx::kLanes) CK(cudaEventSynchronize(L.ring_free));   // the lane's ring is free again
+    // gather the varying columns into the page-locked ring (strided columns of the caller's row-major
+    // arrays: one host thread per column), one H2D copy, scatter on the device
+#pragma omp parallel for schedule(static) num_threads(n_var < 8 ? n_var : 8) if (n_var > 1 && nc >= 4096)
     for (int j = 0; j < n_var; ++j) {
       const int64_t cstr = col_stride ? col_stride[var[j]] : 1;
       const double* src = h_cols[var[j]] + i0 * cstr;
       double* dst = L.ring + (size_t)j * chunk;
       if (cstr == 1) memcpy(dst, src, nc * sizeof(double));
       else for (int64_t i = 0; i < nc; ++i) dst[i] = src[i * cstr];
-      CK(cudaMemcpyAsync(d_app + (int64_t)var[j] * n_points + i0, dst, nc * sizeof(double), cudaMemcpyHostToDevice, st));
     }
+    if (n_var)
+      CK(cudaMemcpyAsync(L.d_ring, L.ring, ((size_t)(n_var - 1) * chunk + nc) * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaEventRecord(L.ring_free, st));
-    if (cs.mask) {
-      fill_slots_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(cs, nc, d_app + i0, n_points);
-      CK(cudaGetLastError());
-      ctx->launches++;
-    }
+    fill_slots_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(cs, nc, d_app + i0, n_points, L.d_ring, chunk);
+    CK(cudaGetLastError());
+    ctx->launches++;
     double* c_sc = d_sc ? d_sc + i0 * SC_STRIDE : nullptr;
     if (prologue_impl(ctx, h_model, nc, d_app + i0, n_points, d_pts + i0 * pstride,
                       d_segs + i0 * (int64_t)S * SG_STRIDE, d_ns + i0, c_sc, st)) return 1;
