@@ -223,7 +223,8 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, int64_t point_base,
 // coefficient records were written by cluster_coef_kernel into the point's region of `scratch`.
 template <int D> struct ClusterSmem {
   static constexpr int XN = D == 3 ? Sys_rho11s_d3::N : Sys_rho11s_d4::N;
-  static constexpr int RING0 = PT_MAX_STRIDE + PT_SCRATCH + 3 * XN;      // first column of the record ring
+  static constexpr int XN2 = ClusterPair<D>::value ? (D == 3 ? Sys_coh11s_d3::N : Sys_coh11s_d4::N) : 0;
+  static constexpr int RING0 = PT_MAX_STRIDE + PT_SCRATCH + 3 * (XN + XN2);   // first column of the record ring
   static constexpr int SLOTS = RING0 + 3 * ClusterRing<D>::value;
   static constexpr size_t BYTES = (size_t)SLOTS * kBlock * sizeof(double);
 };

@@ -31,7 +31,7 @@ static bool try_cluster(const rydcz::PointView pt, const double* row, const doub
   if (g_cluster == 1 && !(cost < 0.8 * point_work<D>(row, sg, ns))) return false;
   std::vector<double> rec((size_t)CL_STRIDE, 0.0);
   cluster_prepare<D>(row, sg, ns, noisy, true, rec.data());
-  double xc[3 * 21], ring[3 * 8];
+  double xc[3 * (21 + 6)], ring[3 * 8];
   bool ok;
   if (D == 3) ok = noisy ? evaluate_point_cluster_d3<true>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), o, st)
                          : evaluate_point_cluster_d3<false>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), o, st);
