@@ -99,6 +99,10 @@ int rydcz_set_cluster(rydcz_ctx* ctx, int mode);
 /* points planned onto the clustered path / handed back to the plain path / 32-byte coefficient records
  * written for them since the last call of this function (synchronises the device; any pointer may be NULL) */
 int rydcz_cluster_stats(rydcz_ctx* ctx, int64_t* planned, int64_t* handed_back, int64_t* records);
+/* Points evaluated on the repeated-segment path (csrc/rydcz_repeat.cuh: identical atoms, 3-level model, at
+ * least 32 active segments that differ only in the laser phase -- the smooth Jandura-Pupillo protocol) since
+ * the last call of this function.  The path is part of the automatic choice: rydcz_set_cluster(0) disables it. */
+int rydcz_repeat_stats(rydcz_ctx* ctx, int64_t* points);
 
 /* One batch of gate evaluations, inputs and outputs resident in device memory.
  * dim: 3 (|0>,|1>,|r>) or 4 (|0>,|1>,|r+>,|r->).  noisy: 0 -> Schroedinger path with the

@@ -53,6 +53,7 @@ _SIGNATURES = {
     "rydcz_pinned_free": (C.c_int, [_vp]),
     "rydcz_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "rydcz_last_coef_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "rydcz_repeat_stats": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "rydcz_launch_count": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "rydcz_fp64_peak": (C.c_int, [_vp, _dp, _dp]),
     "rydcz_fp64_matvec_peak": (C.c_int, [_vp, _dp]),

@@ -220,6 +220,38 @@ def emit_system(sysm: model.RealSystem, struct_name: str, cm: bool = False) -> s
             if ch != n_chunks - 1:
                 A("    RYDCZ_SCHED_FENCE();")
         A("  }")
+    if sysm.d in (3, 4):
+        # Laser-phase covariance: G(Omega e^{i phi}) = R(phi) G(Omega) R(phi)^T, R rotating the (re, im) pair of
+        # entry X[i,j] by q phi, q = (Rydberg excitations of |i>) - (of |j>).  Used by the repeated-segment path
+        # (csrc/rydcz_repeat.cuh): one propagator serves every segment of a phase-modulated pulse.
+        d = sysm.d
+
+        def n_ryd(i):
+            return sum(1 for lev in divmod(int(i), d) if lev >= 2)
+
+        A("  // x <- R(phi) x given (c1, s1) = (cos phi, sin phi)")
+        A("  RYDCZ_HD static void rotate(double* __restrict__ x, double c1, double s1) {")
+        A("    const double c2 = c1 * c1 - s1 * s1, s2 = 2.0 * s1 * c1;")
+        A("    double re;")
+        used_c2 = False
+        for k, (i, j, part) in enumerate(sysm.var_info):
+            if part != "re":
+                continue
+            q = n_ryd(i) - n_ryd(j)
+            if (i, j, "im") not in sysm.var_info:
+                assert q == 0, (sysm.name, i, j)
+                continue
+            k2 = sysm.var_info.index((i, j, "im"))
+            if q == 0:
+                continue
+            assert abs(q) in (1, 2)
+            c, sn = ("c1", "s1") if abs(q) == 1 else ("c2", "s2")
+            sg = "" if q > 0 else "-"
+            used_c2 |= abs(q) == 2
+            A(f"    re = x[{k}]; x[{k}] = {c} * re - ({sg}{sn}) * x[{k2}]; x[{k2}] = ({sg}{sn}) * re + {c} * x[{k2}];")
+        if not used_c2:
+            A("    (void)c2; (void)s2;")
+        A("  }")
     A("};")
     A("")
     return "\n".join(L)

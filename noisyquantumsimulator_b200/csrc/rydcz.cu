@@ -66,7 +66,7 @@ __device__ inline void philox_normal2(uint64_t seed, uint32_t point, uint32_t sh
 
 // ---------------------------------------------------------------- kernels
 // Kind of a point: which kernel evaluates it.
-enum PointKind : uint8_t { KIND_GENERAL = 0, KIND_SYM = 1, KIND_CLUSTER = 3 };
+enum PointKind : uint8_t { KIND_GENERAL = 0, KIND_SYM = 1, KIND_CLUSTER = 3, KIND_REPEAT = 5 };
 
 // Per point: its kind, and a sort key (kind in the top bits, work estimate below) so that a warp holds
 // points of one kind and similar cost.  cluster_mode: 0 = plain path only, 1 = clustered path where the
@@ -77,9 +77,10 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
                             int max_seg, int shots, int noisy, int cluster_mode, uint32_t* __restrict__ keys,
                             uint32_t* __restrict__ idx, uint8_t* __restrict__ kind,
                             uint32_t* __restrict__ task_key, uint32_t* __restrict__ task_val,
-                            double* __restrict__ scratch, unsigned long long* __restrict__ counters) {
+                            double* __restrict__ scratch, unsigned long long* __restrict__ counters,
+                            unsigned* __restrict__ repeat_count) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool clustered = false;
+  bool clustered = false, repeated = false;
   int records_planned = 0;
   if (i < n_points) {
     int slot_K[CL_MAX_SLOTS], slot_off[CL_MAX_SLOTS];
@@ -90,8 +91,15 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
     const int ns = n_seg ? n_seg[i] : max_seg;
     double w = point_work<D>(pt, sg, ns);
     const bool sym = (pt[PT_OFF_A] == pt[PT_OFF_B]) && !(shots && pt[PT_SIG_DET] != 0.0);
-    uint32_t group = sym ? 1u : 2u;     // general points first (heaviest), then plain folded, then clustered
-    if (D != 5 && cluster_mode && sym && !shots) {
+    uint32_t group = sym ? 1u : 2u;     // repeated-segment points first, general, plain folded, clustered
+    if (D == 3 && repeat_count && sym && !shots) {
+      int first, count;
+      if (repeat_eligible(sg, ns, first, count)) {
+        // one propagator for all segments (rydcz_repeat.cuh): 30 column builds + count dense steps
+        repeated = true; group = 3u; w = 40.0 * 30.0 + 4.0 * (double)count;
+      }
+    }
+    if (D != 5 && cluster_mode && sym && !shots && !repeated) {
       double cost = 0.0;
       // the slot headers are written on the way (harmless if the point stays on the plain path)
       const int records = cluster_plan<D>(pt, sg, ns, noisy != 0, true, cost, slot_K, slot_off,
@@ -109,13 +117,18 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
         task_val[i * CL_MAX_SLOTS + q] = (uint32_t)(i * CL_RECORDS + slot_off[q]);   // record index of the slot header
       }
     }
-    kind[i] = clustered ? KIND_CLUSTER : (sym ? KIND_SYM : KIND_GENERAL);
+    kind[i] = repeated ? KIND_REPEAT : (clustered ? KIND_CLUSTER : (sym ? KIND_SYM : KIND_GENERAL));
     const double wq = fmin(fmax(w, 0.0), 1073741823.0);
     keys[i] = (group << 30) | (uint32_t)wq;
     idx[i] = (uint32_t)i;
   }
   const unsigned m = __ballot_sync(0xffffffffu, clustered);
   const unsigned rsum = __reduce_add_sync(0xffffffffu, (unsigned)records_planned);
+  const unsigned mr = __ballot_sync(0xffffffffu, repeated);
+  if (repeat_count && (threadIdx.x & 31) == 0 && mr) {
+    atomicAdd(repeat_count, (unsigned)__popc(mr));
+    if (counters) atomicAdd(counters + 3, (unsigned long long)__popc(mr));
+  }
   if (counters && (threadIdx.x & 31) == 0 && m) {
     atomicAdd(counters, (unsigned long long)__popc(m));
     atomicAdd(counters + 2, (unsigned long long)rsum);
@@ -270,6 +283,68 @@ evaluate_cluster_kernel(int64_t n_items, const uint32_t* __restrict__ order, uin
 #pragma unroll
   for (int k = 0; k < OUT_STRIDE; k += 2)
     *reinterpret_cast<double2*>(op + k) = make_double2(o[k], o[k + 1]);
+}
+
+// Repeated-segment path (rydcz_repeat.cuh), 3-level model, identical atoms.  Points of this kind sort to the
+// front, and their number is known on the device only: both kernels run grid-stride loops over the first
+// *repeat_count positions of the order (all positions when the batch is not sorted).
+// build: one task per (column, position): the propagator column into E[entry][position].
+template <bool NOISY>
+__global__ void __launch_bounds__(kBlock)
+repeat_build_kernel(int64_t n_points, const unsigned* __restrict__ repeat_count, const uint32_t* __restrict__ order,
+                    const uint8_t* __restrict__ kind, const double* __restrict__ points,
+                    const double* __restrict__ segs, const int32_t* __restrict__ n_seg, int max_seg,
+                    double* __restrict__ E) {
+  __shared__ double s_pt[(PT_MAX_STRIDE + PT_SCRATCH) * kBlock];
+  const int64_t n_eff = order ? (int64_t)*repeat_count : n_points;
+  const int64_t n_tasks = n_eff * RepeatLayout<3>::COLS;
+  double* mine = s_pt + threadIdx.x;
+  for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x; t0 < n_tasks; t0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = t0 + threadIdx.x;
+    bool keep = t < n_tasks;
+    int col = 0; int64_t g = 0, point = 0;
+    if (keep) {
+      col = (int)(t / n_eff); g = t - (int64_t)col * n_eff;
+      point = order ? order[g] : g;
+      keep = kind[point] == KIND_REPEAT;
+    }
+    const unsigned live = __ballot_sync(0xffffffffu, keep);
+    if (!keep) continue;
+    const double* row = points + point * PT_STRIDE;
+#pragma unroll
+    for (int k = 0; k < PT_STRIDE; ++k) mine[k * kBlock] = row[k];
+    const PointView pt{mine, kBlock, live};
+    const double* sg = segs + point * (int64_t)max_seg * SG_STRIDE;
+    const int ns = n_seg ? n_seg[point] : max_seg;
+    int first = 0;
+    while (first < ns && !(sg[(int64_t)first * SG_STRIDE] != 0.0 && sg[(int64_t)first * SG_STRIDE] == sg[(int64_t)first * SG_STRIDE])) ++first;
+    repeat_build_d3<NOISY>(col, pt, sg + (int64_t)first * SG_STRIDE, E + g, n_points);
+  }
+}
+
+// apply: one thread per position.
+template <bool NOISY>
+__global__ void __launch_bounds__(kBlock)
+repeat_apply_kernel(int64_t n_points, const unsigned* __restrict__ repeat_count, const uint32_t* __restrict__ order,
+                    const uint8_t* __restrict__ kind, const double* __restrict__ segs,
+                    const int32_t* __restrict__ n_seg, int max_seg, const double* __restrict__ E,
+                    double* __restrict__ out, double* __restrict__ states) {
+  const int64_t n_eff = order ? (int64_t)*repeat_count : n_points;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_eff; g += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t point = order ? order[g] : g;
+    if (kind[point] != KIND_REPEAT) continue;
+    const double* sg = segs + point * (int64_t)max_seg * SG_STRIDE;
+    const int ns = n_seg ? n_seg[point] : max_seg;
+    int first, count;
+    repeat_eligible(sg, ns, first, count);
+    double o[OUT_STRIDE];
+    double* st = states ? states + point * StateLayout<3>::STRIDE : nullptr;
+    evaluate_point_repeat_d3<NOISY>(E + g, n_points, sg, ns, count, o, st);
+    double* op = out + point * OUT_STRIDE;
+#pragma unroll
+    for (int k = 0; k < OUT_STRIDE; k += 2)
+      *reinterpret_cast<double2*>(op + k) = make_double2(o[k], o[k + 1]);
+  }
 }
 
 // dim = 5 (intermediate state kept; identical atoms).  Per thread, in dynamic shared memory
@@ -446,8 +521,10 @@ struct rydcz_ctx {
   // clustered-spectrum path: 0 = off, 1 = where the planner finds it cheaper, 2 = wherever eligible
   int cluster_mode = 1;
   double* cl_scratch = nullptr; size_t cl_cap = 0;      // coefficient records, CL_STRIDE doubles per point
-  unsigned long long* cl_counters = nullptr;            // [0] points planned onto the path, [1] handed back, [2] records
+  unsigned long long* cl_counters = nullptr;            // [0] clustered points, [1] handed back, [2] records, [3] repeated-segment points
   bool cl_smem_set = false;
+  double* rp_E = nullptr; size_t rp_cap = 0;            // repeated-segment path: propagators, [entry][position]
+  unsigned* rp_count = nullptr;                         // points of that kind per in-flight call (slot 0 + one per lane)
   cudaEvent_t evc0 = nullptr, evc1 = nullptr;           // around the last coefficient kernel
   bool coef_timed = false;
   void* cub_tmp = nullptr; size_t cub_cap = 0;
@@ -477,6 +554,8 @@ struct SortScratch {
   double* cl;          // coefficient records of these points (nullptr: clustered path unavailable)
   uint32_t* task;      // coefficient task list of these points: [4][task_n] (keys, sorted keys, values, sorted values)
   int64_t task_n;      // stride of the four task arrays
+  double* rp;          // propagators of the repeated-segment path for these points (stride = their number)
+  unsigned* rp_count;  // device counter of the points that take it
   void** tmp; size_t* tmp_cap;
 };
 
@@ -555,21 +634,23 @@ static int order_reserve(rydcz_ctx* ctx, int64_t n, bool want_cluster = true) {
     ctx->order_cap = (size_t)n;
   }
   if (!ctx->cl_counters) {
-    CK(cudaMalloc(&ctx->cl_counters, 3 * sizeof(unsigned long long)));
-    CK(cudaMemset(ctx->cl_counters, 0, 3 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->cl_counters, 4 * sizeof(unsigned long long)));
+    CK(cudaMemset(ctx->cl_counters, 0, 4 * sizeof(unsigned long long)));
     CK(cudaEventCreate(&ctx->evc0)); CK(cudaEventCreate(&ctx->evc1));
+    CK(cudaMalloc(&ctx->rp_count, (1 + rydcz_ctx::kLanes) * sizeof(unsigned)));
   }
   if (want_cluster && ctx->cluster_mode) {
     const size_t bytes = (size_t)n * CL_STRIDE * sizeof(double);
     if (bytes <= kClusterScratchMax) {
       if (grow(ctx, (void**)&ctx->cl_scratch, &ctx->cl_cap, bytes)) return 1;
       if (grow(ctx, (void**)&ctx->task, &ctx->task_cap, (size_t)n * CL_MAX_SLOTS * 4 * sizeof(uint32_t))) return 1;
+      if (grow(ctx, (void**)&ctx->rp_E, &ctx->rp_cap, (size_t)n * RepeatLayout<3>::STRIDE * sizeof(double))) return 1;
     }
   }
   return 0;
 }
 
-static SortScratch context_scratch(rydcz_ctx* ctx, int64_t n, int64_t offset = 0) {
+static SortScratch context_scratch(rydcz_ctx* ctx, int64_t n, int64_t offset = 0, int counter_slot = 0) {
   const bool cl = ctx->cluster_mode && ctx->cl_scratch && ctx->task &&
                   (size_t)(offset + n) * CL_STRIDE * sizeof(double) <= ctx->cl_cap &&
                   (size_t)(offset + n) * CL_MAX_SLOTS * 4 * sizeof(uint32_t) <= ctx->task_cap;
@@ -577,7 +658,9 @@ static SortScratch context_scratch(rydcz_ctx* ctx, int64_t n, int64_t offset = 0
   return SortScratch{ctx->keys + offset, ctx->keys_sorted + offset, ctx->idx + offset, ctx->idx_sorted + offset,
                      ctx->kind + offset, cl ? ctx->cl_scratch + offset * (int64_t)CL_STRIDE : nullptr,
                      cl ? ctx->task + offset * (int64_t)CL_MAX_SLOTS * 4 : nullptr, n * (int64_t)CL_MAX_SLOTS,
-                     &ctx->cub_tmp, &ctx->cub_cap};
+                     (cl && ctx->rp_E && (size_t)(offset + n) * RepeatLayout<3>::STRIDE * sizeof(double) <= ctx->rp_cap)
+                         ? ctx->rp_E + offset * (int64_t)RepeatLayout<3>::STRIDE : nullptr,
+                     ctx->rp_count + counter_slot, &ctx->cub_tmp, &ctx->cub_cap};
 }
 
 // Plan the batch: kind of every point, heaviest-first order (nullptr when sorting is off), and the
@@ -588,13 +671,15 @@ static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const do
                       cudaStream_t st, const uint32_t** order) {
   *order = nullptr;
   const int mode = (sc.cl && D != 5 && !shots && n * (int64_t)CL_RECORDS < 0xffffffffLL) ? ctx->cluster_mode : 0;
+  unsigned* rpc = (mode && D == 3 && sc.rp) ? sc.rp_count : nullptr;
+  if (rpc) CK(cudaMemsetAsync(rpc, 0, sizeof(unsigned), st));
   uint32_t* tk = mode ? sc.task : nullptr;
   uint32_t* tks = mode ? sc.task + sc.task_n : nullptr;
   uint32_t* tv = mode ? sc.task + 2 * sc.task_n : nullptr;
   uint32_t* tvs = mode ? sc.task + 3 * sc.task_n : nullptr;
   plan_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_points, d_segs, d_n_seg, max_seg, shots, noisy,
                                                               mode, sc.keys, sc.idx, sc.kind, tk, tv, sc.cl,
-                                                              ctx->cl_counters);
+                                                              ctx->cl_counters, rpc);
   CK(cudaGetLastError());
   ctx->launches++;
   if (ctx->sort && n >= 64) {
@@ -655,6 +740,19 @@ static int launch_eval(rydcz_ctx* ctx, const SortScratch& sc, int64_t n_items, i
                                                                   sc.kind, d_points, d_segs, d_n_seg, max_seg,
                                                                   d_out, d_states);
   CK(cudaGetLastError());
+  if (!SHOTS && D == 3 && sc.cl && sc.rp && ctx->cluster_mode && n_items * (int64_t)CL_RECORDS < 0xffffffffLL) {
+    // fixed grids: the kernels find the number of repeated-segment points on the device
+    const unsigned pg = (unsigned)(ctx->sm_count * 8);
+    const unsigned need_b = (unsigned)((n_items * RepeatLayout<3>::COLS + kBlock - 1) / kBlock);
+    const unsigned need_a = (unsigned)((n_items + kBlock - 1) / kBlock);
+    repeat_build_kernel<NOISY><<<need_b < pg ? need_b : pg, kBlock, 0, st>>>(n_items, sc.rp_count, order, sc.kind, d_points,
+                                                                               d_segs, d_n_seg, max_seg, sc.rp);
+    CK(cudaGetLastError());
+    repeat_apply_kernel<NOISY><<<need_a < pg ? need_a : pg, kBlock, 0, st>>>(n_items, sc.rp_count, order, sc.kind, d_segs,
+                                                                               d_n_seg, max_seg, sc.rp, d_out, d_states);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+  }
   if (mark & 2) { CK(cudaEventRecord(ctx->ev1, st)); ctx->timed = true; }
   ctx->launches++;
   return 0;
@@ -705,6 +803,7 @@ void rydcz_destroy(rydcz_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->keys); cudaFree(ctx->keys_sorted); cudaFree(ctx->idx); cudaFree(ctx->idx_sorted);
   cudaFree(ctx->kind); cudaFree(ctx->cl_scratch); cudaFree(ctx->cl_counters); cudaFree(ctx->task);
+  cudaFree(ctx->rp_E); cudaFree(ctx->rp_count);
   if (ctx->evc0) cudaEventDestroy(ctx->evc0);
   if (ctx->evc1) cudaEventDestroy(ctx->evc1);
   cudaFree(ctx->cub_tmp);
@@ -745,11 +844,24 @@ int rydcz_cluster_stats(rydcz_ctx* ctx, int64_t* planned, int64_t* handed_back, 
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(h, ctx->cl_counters, sizeof(h), cudaMemcpyDeviceToHost));
-    CK(cudaMemset(ctx->cl_counters, 0, sizeof(h)));
+    CK(cudaMemset(ctx->cl_counters, 0, sizeof(h)));     // (the repeated-segment counter sits behind these three)
   }
   if (planned) *planned = (int64_t)h[0];
   if (handed_back) *handed_back = (int64_t)h[1];
   if (records) *records = (int64_t)h[2];
+  return 0;
+}
+
+int rydcz_repeat_stats(rydcz_ctx* ctx, int64_t* points) {
+  if (!ctx) return 2;
+  unsigned long long h = 0;
+  if (ctx->cl_counters) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(&h, ctx->cl_counters + 3, sizeof(h), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(ctx->cl_counters + 3, 0, sizeof(h)));
+  }
+  if (points) *points = (int64_t)h;
   return 0;
 }
 
@@ -1120,7 +1232,7 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
     double* c_sc = d_sc ? d_sc + i0 * SC_STRIDE : nullptr;
     if (prologue_impl(ctx, h_model, nc, d_app + i0, n_points, d_pts + i0 * pstride,
                       d_segs + i0 * (int64_t)S * SG_STRIDE, d_ns + i0, c_sc, st)) return 1;
-    SortScratch sc = context_scratch(ctx, nc, i0);
+    SortScratch sc = context_scratch(ctx, nc, i0, 1 + (int)(c % rydcz_ctx::kLanes));
     sc.tmp = &L.cub_tmp; sc.tmp_cap = &L.cub_cap;
     const int mark = (c == 0 ? 1 : 0) | (c == n_chunks - 1 ? 2 : 0);
     int rc;

@@ -247,9 +247,10 @@ RYDCZ_HD bool next_segment(double* __restrict__ p, const PointView pt, const dou
 // keeps the Chebyshev polynomials O(e^2) ("Chebyshev interval").
 template <class Sys>
 RYDCZ_HD void run_system(double (&x)[Sys::N], const PointView pt,
-                         const double* __restrict__ seg, int n_seg, bool noisy, double& steps) {
+                         const double* __restrict__ seg, int n_seg, bool noisy, double& steps,
+                         bool from_start_operator = true) {
   constexpr int N = Sys::N;
-  Sys::init(x);
+  if (from_start_operator) Sys::init(x);   // false: x holds the vector to propagate (rydcz_repeat.cuh)
   double c[Sys::NC], b1[N], b2[N];
   double jp = 0.0, jk = 0.0, norm = 0.0, kd = 0.0, tz = 0.0, rot = 0.0;
   double &rot_total = pt.scratch(6), &rot_comp = pt.scratch(7);   // Kahan-summed shift phase
@@ -739,3 +740,4 @@ RYDCZ_HD double point_work(const double* __restrict__ pt, const double* __restri
 }  // namespace rydcz
 
 #include "rydcz_cluster.cuh"
+#include "rydcz_repeat.cuh"

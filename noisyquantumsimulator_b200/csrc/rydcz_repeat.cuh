@@ -1,0 +1,197 @@
+// rydcz_repeat.cuh -- one propagator for every segment of a phase-modulated pulse.
+//
+// The smooth Jandura-Pupillo protocol is 300 equal steps that differ only in the laser phase
+// (RG/simulation.py:1693-1733); any schedule whose active segments share (duration, |Omega|, Delta) is the
+// same case.  The generator is covariant under the phase:
+//
+//     G(Omega e^{i phi}) = R(phi) G(Omega) R(phi)^T,     R(phi): the (re, im) pair of X[i,j] turned by q phi,
+//                                                        q = Rydberg excitations of |i> minus those of |j>
+//
+// (U = exp(-i phi sum_atoms |r><r|) conjugates the coupling, commutes with every diagonal term, and the
+// collapse operators only pick up a phase; Sys::rotate is generated from the variable table and checked
+// against the generated systems in tests/test_repeat_hostsim.py).  Hence exp(h G_s) = R(phi_s) E0 R(-phi_s)
+// with ONE dense E0 = exp(h G(|Omega|)) per system and point:
+//
+//   build:  column c of E0 = the plain Chebyshev propagation (run_system) of the unit vector e_c through one
+//           segment; one thread per (point, column), 30 columns for the noisy 3-level evaluation;
+//   apply:  per segment  x <- E0 R(phi_prev - phi_s) x  (the phasors come from the segment rows, no
+//           trigonometry), one thread per point; E0 is streamed from L2 / HBM ([entry][thread]: coalesced).
+//
+// 300 x (N^2 + a rotation) FMAs instead of 300 x ~40 sparse matvecs: ~9x fewer flops for the noisy smooth-JP
+// evaluation, whatever V / Omega.  Exact to rounding like the other paths.
+//
+// Plain C++ when RYDCZ_HD is empty (tests/hostsim).
+#pragma once
+
+namespace rydcz {
+
+constexpr int RP_MIN_COUNT = 32;    // fewer equal segments than this: not worth the N columns of E0
+
+// offsets (doubles per point, times the batch stride) of the four propagators and of the per-column step counts
+template <int D> struct RepeatLayout;
+template <> struct RepeatLayout<3> {
+  static constexpr int NA = Sys_rho11s_d3::N, NB = Sys_coh11s_d3::N, NC_ = Sys_rho01_d3::N, ND = Sys_coh01_d3::N;
+  static constexpr int RHO11 = 0, COH11 = RHO11 + NA * NA, RHO01 = COH11 + NB * NB, COH01 = RHO01 + NC_ * NC_;
+  static constexpr int STEPS = COH01 + ND * ND;       // one entry per column: Chebyshev terms its build took
+  static constexpr int COLS = NA + NB + NC_ + ND;
+  static constexpr int STRIDE = STEPS + COLS;
+};
+
+// All active segments equal in (duration, |Omega|^2 to 1e-9, Delta), |Omega| > 0, at least RP_MIN_COUNT of them.
+// first = index of the first active segment row.
+RYDCZ_HD bool repeat_eligible(const double* __restrict__ seg, int n_seg, int& first, int& count) {
+  first = -1; count = 0;
+  double dt = 0.0, det = 0.0, om2 = 0.0;
+  for (int s = 0; s < n_seg; ++s) {
+    const double* sg = seg + (long long)s * SG_STRIDE;
+    const double d = sg[SG_DT];
+    if (!(d != 0.0 && d == d)) continue;
+    const double o2 = sg[SG_RE] * sg[SG_RE] + sg[SG_IM] * sg[SG_IM];
+    if (first < 0) {
+      first = s; dt = d; det = sg[SG_DET]; om2 = o2;
+      if (!(om2 > 0.0)) return false;
+    } else if (!(d == dt && sg[SG_DET] == det && fabs(o2 - om2) <= 1e-9 * om2)) {
+      return false;
+    }
+    ++count;
+  }
+  return count >= RP_MIN_COUNT;
+}
+
+// Column c of E0 for one system: the unit vector e_c through one segment at phase 0.  E[(r N + c) stride].
+// Returns the Chebyshev terms spent.
+template <class Sys>
+RYDCZ_HD double repeat_build_column(int c, const PointView pt, const double* __restrict__ seg_row, bool noisy,
+                                    double* __restrict__ E, long long stride) {
+  constexpr int N = Sys::N;
+  double row[SG_STRIDE];
+  row[SG_DT] = seg_row[SG_DT];
+  row[SG_RE] = sqrt(seg_row[SG_RE] * seg_row[SG_RE] + seg_row[SG_IM] * seg_row[SG_IM]);
+  row[SG_IM] = 0.0;
+  row[SG_DET] = seg_row[SG_DET];
+  double x[N];
+  RYDCZ_UNROLL
+  for (int i = 0; i < N; ++i) x[i] = i == c ? 1.0 : 0.0;
+  double st = 0.0;
+  run_system<Sys>(x, pt, row, 1, noisy, st, false);
+  RYDCZ_UNROLL
+  for (int r = 0; r < N; ++r) E[(long long)(r * N + c) * stride] = x[r];
+  return st;
+}
+
+// x <- prod_s R(phi_s) E0 R(-phi_s) x_start over the active segments.
+template <class Sys>
+RYDCZ_HD void repeat_apply(double (&x)[Sys::N], const double* __restrict__ E, long long stride,
+                           const double* __restrict__ seg, int n_seg) {
+  constexpr int N = Sys::N;
+  Sys::init(x);
+  double pr = 1.0, pi = 0.0;      // phasor of the previous segment (the state is kept in its frame)
+  for (int s = 0; s < n_seg; ++s) {
+    const double* sg = seg + (long long)s * SG_STRIDE;
+    const double d = sg[SG_DT];
+    if (!(d != 0.0 && d == d)) continue;
+    const double re = sg[SG_RE], im = sg[SG_IM];
+    const double inv = 1.0 / sqrt(re * re + im * im);
+    const double ur = re * inv, ui = im * inv;
+    // into the frame of this segment: turn by phi_prev - phi_s
+    Sys::rotate(x, pr * ur + pi * ui, pi * ur - pr * ui);
+    double y[N];
+    RYDCZ_UNROLL
+    for (int r = 0; r < N; ++r) {
+      double acc = 0.0;
+      RYDCZ_UNROLL
+      for (int c = 0; c < N; ++c) acc = fma(E[(long long)(r * N + c) * stride], x[c], acc);
+      y[r] = acc;
+    }
+    RYDCZ_UNROLL
+    for (int r = 0; r < N; ++r) x[r] = y[r];
+    pr = ur; pi = ui;
+  }
+  Sys::rotate(x, pr, pi);         // back to the laboratory frame
+}
+
+// One full gate evaluation from the four propagators (identical atoms, 3-level model).
+template <bool NOISY>
+RYDCZ_HD void evaluate_point_repeat_d3(const double* __restrict__ E, long long stride, const double* __restrict__ seg,
+                                       int n_seg, int count, double* __restrict__ out, double* __restrict__ states) {
+  typedef StateLayout<3> SL;
+  typedef RepeatLayout<3> RL;
+  double p01 = 1.0, p11 = 1.0, loss = 0.0, ryd = 0.0, flops = 0.0, build_steps = 0.0;
+  double c01r, c01i, c11r, c11i;
+  int n_sys = 2;
+  if (NOISY) {
+    double x[Sys_rho11s_d3::N];
+    repeat_apply<Sys_rho11s_d3>(x, E + (long long)RL::RHO11 * stride, stride, seg, n_seg);
+    p11 = x[RHO11S_POP_D3];
+    double xf[Sys_rho11s_d3::FULL_N];
+    Sys_rho11s_d3::expand(x, xf);
+    loss = rho11_loss_d3(xf); ryd = rho11_ryd_d3(xf);
+    if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_rho11s_d3::FULL_N; ++i) states[SL::RHO11 + i] = xf[i]; }
+    double y[Sys_rho01_d3::N];
+    repeat_apply<Sys_rho01_d3>(y, E + (long long)RL::RHO01 * stride, stride, seg, n_seg);
+    p01 = y[RHO01_POP_D3];
+    if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_rho01_d3::N; ++i) { states[SL::RHO01 + i] = y[i]; states[SL::RHO10 + i] = y[i]; } }
+    n_sys = 4;
+    flops += 2.0 * count * (RL::NA * RL::NA + RL::NC_ * RL::NC_);
+    for (int c = 0; c < RL::NA; ++c) {
+      const double st = E[(long long)(RL::STEPS + c) * stride];
+      build_steps += st; flops += st * 2.0 * (Sys_rho11s_d3::NNZ + Sys_rho11s_d3::N);
+    }
+    for (int c = 0; c < RL::NC_; ++c) {
+      const double st = E[(long long)(RL::STEPS + RL::NA + RL::NB + c) * stride];
+      build_steps += st; flops += st * 2.0 * (Sys_rho01_d3::NNZ + Sys_rho01_d3::N);
+    }
+  }
+  {
+    double x[Sys_coh11s_d3::N];
+    repeat_apply<Sys_coh11s_d3>(x, E + (long long)RL::COH11 * stride, stride, seg, n_seg);
+    c11r = x[COH11S_RE_D3]; c11i = x[COH11S_IM_D3];
+    if (!NOISY) ryd = 1.0 - (c11r * c11r + c11i * c11i);
+    if (states) {
+      double xf[Sys_coh11s_d3::FULL_N];
+      Sys_coh11s_d3::expand(x, xf);
+      RYDCZ_UNROLL for (int i = 0; i < Sys_coh11s_d3::FULL_N; ++i) states[SL::COH11 + i] = xf[i];
+    }
+    double y[Sys_coh01_d3::N];
+    repeat_apply<Sys_coh01_d3>(y, E + (long long)RL::COH01 * stride, stride, seg, n_seg);
+    c01r = y[COH01_RE_D3]; c01i = y[COH01_IM_D3];
+    if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d3::N; ++i) { states[SL::COH01 + i] = y[i]; states[SL::COH10 + i] = y[i]; } }
+    flops += 2.0 * count * (RL::NB * RL::NB + RL::ND * RL::ND);
+    for (int c = 0; c < RL::NB; ++c) {
+      const double st = E[(long long)(RL::STEPS + RL::NA + c) * stride];
+      build_steps += st; flops += st * 2.0 * (Sys_coh11s_d3::NNZ + Sys_coh11s_d3::N);
+    }
+    for (int c = 0; c < RL::ND; ++c) {
+      const double st = E[(long long)(RL::STEPS + RL::NA + RL::NB + RL::NC_ + c) * stride];
+      build_steps += st; flops += st * 2.0 * (Sys_coh01_d3::NNZ + Sys_coh01_d3::N);
+    }
+  }
+  cz_epilogue(NOISY, p01, p01, p11, c01r, c01i, c01r, c01i, c11r, c11i, out);
+  out[OUT_LOSS] = loss; out[OUT_RYD] = ryd;
+  out[OUT_STEPS] = build_steps + (double)count * n_sys;    // operator applications: sparse (build) + dense (apply)
+  out[OUT_FLOPS] = flops;
+}
+
+// The build of one column, dispatched on the column index (the host harness loops over all of them; on the
+// GPU a warp holds one column index, so the branch is uniform).
+template <bool NOISY>
+RYDCZ_HD void repeat_build_d3(int col, const PointView pt, const double* __restrict__ seg_row,
+                              double* __restrict__ E, long long stride) {
+  typedef RepeatLayout<3> RL;
+  double st = 0.0;
+  if (col < RL::NA) {
+    if (!NOISY) return;
+    st = repeat_build_column<Sys_rho11s_d3>(col, pt, seg_row, true, E + (long long)RL::RHO11 * stride, stride);
+  } else if (col < RL::NA + RL::NB) {
+    st = repeat_build_column<Sys_coh11s_d3>(col - RL::NA, pt, seg_row, NOISY, E + (long long)RL::COH11 * stride, stride);
+  } else if (col < RL::NA + RL::NB + RL::NC_) {
+    if (!NOISY) return;
+    st = repeat_build_column<Sys_rho01_d3>(col - RL::NA - RL::NB, pt, seg_row, true, E + (long long)RL::RHO01 * stride, stride);
+  } else {
+    st = repeat_build_column<Sys_coh01_d3>(col - RL::NA - RL::NB - RL::NC_, pt, seg_row, NOISY,
+                                           E + (long long)RL::COH01 * stride, stride);
+  }
+  E[(long long)(RL::STEPS + col) * stride] = st;
+}
+
+}  // namespace rydcz

@@ -256,6 +256,12 @@ class Evaluator:
         self._check(self.lib.rydcz_cluster_stats(self.ctx, C.byref(a), C.byref(b), C.byref(r)), "rydcz_cluster_stats")
         return (int(a.value), int(b.value), int(r.value)) if with_records else (int(a.value), int(b.value))
 
+    def repeat_stats(self) -> int:
+        """Points evaluated on the repeated-segment path (one propagator for all segments) since the last call."""
+        a = C.c_int64()
+        self._check(self.lib.rydcz_repeat_stats(self.ctx, C.byref(a)), "rydcz_repeat_stats")
+        return int(a.value)
+
     def last_coef_ms(self) -> float:
         ms = C.c_float()
         self._check(self.lib.rydcz_last_coef_ms(self.ctx, C.byref(ms)), "rydcz_last_coef_ms")

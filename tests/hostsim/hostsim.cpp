@@ -14,7 +14,8 @@ extern "C" void hostsim_allow_sym(int on) { g_allow_sym = on; }
 // clustered-spectrum path (csrc/rydcz_cluster.cuh): 0 = off, 1 = where the planner prefers it (the CUDA
 // library's rule), 2 = wherever it is eligible
 static int g_cluster = 0;
-static long long g_cluster_used = 0, g_cluster_retry = 0;
+static long long g_cluster_used = 0, g_cluster_retry = 0, g_repeat_used = 0;
+extern "C" long long hostsim_repeat_used() { const long long n = g_repeat_used; g_repeat_used = 0; return n; }
 extern "C" void hostsim_set_cluster(int mode) { g_cluster = mode; }
 extern "C" void hostsim_cluster_stats(long long* used, long long* retried) {
   *used = g_cluster_used; *retried = g_cluster_retry;
@@ -69,6 +70,23 @@ extern "C" int hostsim_evaluate(int dim, int noisy, long long n_points, const do
     double* o = out + i * OUT_STRIDE;
     // same dispatch rule as the CUDA kernels: identical atoms take the exchange-folded path
     const bool sym = g_allow_sym && pt[PT_OFF_A] == pt[PT_OFF_B];
+    if (g_cluster && sym && dim == 3) {
+      // repeated-segment path (csrc/rydcz_repeat.cuh): same rule as the CUDA planner
+      int first = 0, count = 0;
+      if (repeat_eligible(sg, n_seg[i], first, count)) {
+        typedef RepeatLayout<3> RL;
+        std::vector<double> E((size_t)RL::STRIDE, 0.0);
+        for (int col = 0; col < RL::COLS; ++col) {
+          if (noisy) repeat_build_d3<true>(col, pt, sg + (long long)first * SG_STRIDE, E.data(), 1);
+          else repeat_build_d3<false>(col, pt, sg + (long long)first * SG_STRIDE, E.data(), 1);
+        }
+        double* st = states ? states + i * StateLayout<3>::STRIDE : nullptr;
+        if (noisy) evaluate_point_repeat_d3<true>(E.data(), 1, sg, n_seg[i], count, o, st);
+        else evaluate_point_repeat_d3<false>(E.data(), 1, sg, n_seg[i], count, o, st);
+        ++g_repeat_used;
+        continue;
+      }
+    }
     if (g_cluster && sym && (dim == 3 || dim == 4)) {
       double* st = states ? states + i * (dim == 3 ? StateLayout<3>::STRIDE : StateLayout<4>::STRIDE) : nullptr;
       if (dim == 3 ? try_cluster<3>(pt, row, sg, n_seg[i], noisy != 0, o, st)

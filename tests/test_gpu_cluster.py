@@ -54,7 +54,7 @@ def test_planner_prefers_cluster_only_for_strong_blockade(ev):
 def test_mixed_batch_kinds(ev):
     """General (unequal atoms), plain folded and clustered points in one batch, unsorted and sorted."""
     rng = np.random.default_rng(11)
-    cases = [c for c in REF if c["dim"] == 3 and c["rates"] is not None and len(c["segments"]) <= 7]
+    cases = [c for c in REF if c["dim"] == 3 and c["rates"] is not None and len(c["segments"]["dt"]) <= 7]
     pts, seg, ns = C.pack_batch(cases)
     reps = 40
     pts = np.tile(pts, (reps, 1)); seg = np.tile(seg, (reps, 1, 1)); ns = np.tile(ns, reps)
@@ -74,3 +74,30 @@ def test_mixed_batch_kinds(ev):
     finally:
         ev.set_sort(True)
     assert np.array_equal(b[:, :14], c[:, :14])
+
+
+def test_repeated_segment_path_for_smooth_jp(ev):
+    """Smooth-JP fixtures (300 steps that differ only in the laser phase) take the one-propagator path by
+    default; same states as the plain path and the golden finals."""
+    for noisy in (True, False):
+        cases = [c for c in REF if c["dim"] == 3 and (c["rates"] is not None) == noisy and len(c["segments"]["dt"]) == 300]
+        assert len(cases) >= 2
+        pts, seg, ns = C.pack_batch(cases)
+        reps = 70                                   # > 64 points: the sorted order is used
+        P, S, N = np.tile(pts, (reps, 1)), np.tile(seg, (reps, 1, 1)), np.tile(ns, reps)
+        ev.set_cluster(0)
+        a, sa = ev.evaluate_host(3, noisy, P, S, N, want_states=True)
+        ev.repeat_stats()
+        ev.set_cluster(1)
+        b, sb = ev.evaluate_host(3, noisy, P, S, N, want_states=True)
+        assert ev.repeat_stats() == len(P)
+        assert np.abs(a[:, :14] - b[:, :14]).max() < 5e-11 and np.abs(sa - sb).max() < 5e-11
+        assert b[:, 14].sum() < 0.2 * a[:, 14].sum()
+        b1, sb1 = ev.evaluate_host(3, noisy, pts, seg, ns, want_states=True)     # unsorted small batch
+        assert np.array_equal(b1[:, :14], b[:len(cases), :14])
+        for i, c in enumerate(cases):
+            gold = C.golden_finals(c)
+            ops = C.states_to_operators(3, sb[i])
+            for lab in ("01", "10", "11"):
+                got = ops["rho" + lab] if noisy else ops["coh" + lab][:, 0]
+                assert np.abs(got - gold[lab]).max() < 1e-10, c["name"]
