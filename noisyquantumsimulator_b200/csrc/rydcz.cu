@@ -89,9 +89,9 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
     const double* pt = points + i * PointStride<D>::value;
     const double* sg = segs + i * (int64_t)max_seg * SG_STRIDE;
     const int ns = n_seg ? n_seg[i] : max_seg;
-    double w = point_work<D>(pt, sg, ns);
     const bool sym = (pt[PT_OFF_A] == pt[PT_OFF_B]) && !(shots && pt[PT_SIG_DET] != 0.0);
     uint32_t group = sym ? 1u : 2u;     // repeated-segment points first, general, plain folded, clustered
+    double w = 0.0;
     if (D == 3 && repeat_count && sym && !shots) {
       int first, count;
       if (repeat_eligible(sg, ns, first, count)) {
@@ -99,6 +99,7 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
         repeated = true; group = 3u; w = 40.0 * 30.0 + 4.0 * (double)count;
       }
     }
+    if (!repeated) w = point_work<D>(pt, sg, ns);
     if (D != 5 && cluster_mode && sym && !shots && !repeated) {
       double cost = 0.0;
       // the slot headers are written on the way (harmless if the point stays on the plain path)
@@ -322,24 +323,35 @@ repeat_build_kernel(int64_t n_points, const unsigned* __restrict__ repeat_count,
   }
 }
 
-// apply: one thread per position.
+// apply: one thread per position, one warp per CTA.  The warp first copies its 32 propagator sets into shared
+// memory ([entry][lane], 85 KB, two CTAs per SM): the 300 dense steps then read E0 from there instead of
+// streaming 2.4 KB per thread and step from L2.
+constexpr int kRepeatBlock = 32;
+constexpr size_t kRepeatSmem = (size_t)RepeatLayout<3>::STRIDE * kRepeatBlock * sizeof(double);
 template <bool NOISY>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kRepeatBlock)
 repeat_apply_kernel(int64_t n_points, const unsigned* __restrict__ repeat_count, const uint32_t* __restrict__ order,
                     const uint8_t* __restrict__ kind, const double* __restrict__ segs,
                     const int32_t* __restrict__ n_seg, int max_seg, const double* __restrict__ E,
                     double* __restrict__ out, double* __restrict__ states) {
+  extern __shared__ double s_E[];
   const int64_t n_eff = order ? (int64_t)*repeat_count : n_points;
-  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_eff; g += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t point = order ? order[g] : g;
-    if (kind[point] != KIND_REPEAT) continue;
+  for (int64_t g0 = (int64_t)blockIdx.x * kRepeatBlock; g0 < n_eff; g0 += (int64_t)gridDim.x * kRepeatBlock) {
+    const int64_t g = g0 + threadIdx.x;
+    const bool inside = g < n_eff;
+    const int64_t point = inside ? (order ? order[g] : g) : 0;
+    const bool keep = inside && kind[point] == KIND_REPEAT;
+    __syncwarp();                               // the previous iteration's readers are done with s_E
+    if (keep) {
+#pragma unroll 4
+      for (int e = 0; e < RepeatLayout<3>::STRIDE; ++e) s_E[e * kRepeatBlock + threadIdx.x] = E[(int64_t)e * n_points + g];
+    }
+    if (!keep) continue;
     const double* sg = segs + point * (int64_t)max_seg * SG_STRIDE;
     const int ns = n_seg ? n_seg[point] : max_seg;
-    int first, count;
-    repeat_eligible(sg, ns, first, count);
     double o[OUT_STRIDE];
     double* st = states ? states + point * StateLayout<3>::STRIDE : nullptr;
-    evaluate_point_repeat_d3<NOISY>(E + g, n_points, sg, ns, count, o, st);
+    evaluate_point_repeat_d3<NOISY>(s_E + threadIdx.x, kRepeatBlock, sg, ns, o, st);
     double* op = out + point * OUT_STRIDE;
 #pragma unroll
     for (int k = 0; k < OUT_STRIDE; k += 2)
@@ -523,6 +535,7 @@ struct rydcz_ctx {
   double* cl_scratch = nullptr; size_t cl_cap = 0;      // coefficient records, CL_STRIDE doubles per point
   unsigned long long* cl_counters = nullptr;            // [0] clustered points, [1] handed back, [2] records, [3] repeated-segment points
   bool cl_smem_set = false;
+  bool rp_smem_set = false;
   double* rp_E = nullptr; size_t rp_cap = 0;            // repeated-segment path: propagators, [entry][position]
   unsigned* rp_count = nullptr;                         // points of that kind per in-flight call (slot 0 + one per lane)
   cudaEvent_t evc0 = nullptr, evc1 = nullptr;           // around the last coefficient kernel
@@ -744,11 +757,16 @@ static int launch_eval(rydcz_ctx* ctx, const SortScratch& sc, int64_t n_items, i
     // fixed grids: the kernels find the number of repeated-segment points on the device
     const unsigned pg = (unsigned)(ctx->sm_count * 8);
     const unsigned need_b = (unsigned)((n_items * RepeatLayout<3>::COLS + kBlock - 1) / kBlock);
-    const unsigned need_a = (unsigned)((n_items + kBlock - 1) / kBlock);
+    const unsigned need_a = (unsigned)((n_items + kRepeatBlock - 1) / kRepeatBlock);
+    if (!ctx->rp_smem_set) {
+      CK(cudaFuncSetAttribute(repeat_apply_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRepeatSmem));
+      CK(cudaFuncSetAttribute(repeat_apply_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRepeatSmem));
+      ctx->rp_smem_set = true;
+    }
     repeat_build_kernel<NOISY><<<need_b < pg ? need_b : pg, kBlock, 0, st>>>(n_items, sc.rp_count, order, sc.kind, d_points,
                                                                                d_segs, d_n_seg, max_seg, sc.rp);
     CK(cudaGetLastError());
-    repeat_apply_kernel<NOISY><<<need_a < pg ? need_a : pg, kBlock, 0, st>>>(n_items, sc.rp_count, order, sc.kind, d_segs,
+    repeat_apply_kernel<NOISY><<<need_a < pg ? need_a : pg, kRepeatBlock, kRepeatSmem, st>>>(n_items, sc.rp_count, order, sc.kind, d_segs,
                                                                                d_n_seg, max_seg, sc.rp, d_out, d_states);
     CK(cudaGetLastError());
     ctx->launches += 2;

@@ -14,8 +14,8 @@
 //
 //   build:  column c of E0 = the plain Chebyshev propagation (run_system) of the unit vector e_c through one
 //           segment; one thread per (point, column), 30 columns for the noisy 3-level evaluation;
-//   apply:  per segment  x <- E0 R(phi_prev - phi_s) x  (the phasors come from the segment rows, no
-//           trigonometry), one thread per point; E0 is streamed from L2 / HBM ([entry][thread]: coalesced).
+//   apply:  per segment  x <- E0 R(phi_prev - phi_s) x  for the four systems at once (the phasors come from
+//           the segment rows, no trigonometry), one thread per point, E0 in shared memory ([entry][lane]).
 //
 // 300 x (N^2 + a rotation) FMAs instead of 300 x ~40 sparse matvecs: ~9x fewer flops for the noisy smooth-JP
 // evaluation, whatever V / Omega.  Exact to rounding like the other paths.
@@ -79,58 +79,72 @@ RYDCZ_HD double repeat_build_column(int c, const PointView pt, const double* __r
   return st;
 }
 
-// x <- prod_s R(phi_s) E0 R(-phi_s) x_start over the active segments.
+// One dense step of one system: x <- E0 R(phi_prev - phi_s) x, (c1, s1) = cos / sin of the turn.
 template <class Sys>
-RYDCZ_HD void repeat_apply(double (&x)[Sys::N], const double* __restrict__ E, long long stride,
-                           const double* __restrict__ seg, int n_seg) {
+RYDCZ_HD void repeat_step(double (&x)[Sys::N], const double* __restrict__ E, long long stride, double c1, double s1) {
   constexpr int N = Sys::N;
-  Sys::init(x);
-  double pr = 1.0, pi = 0.0;      // phasor of the previous segment (the state is kept in its frame)
-  for (int s = 0; s < n_seg; ++s) {
-    const double* sg = seg + (long long)s * SG_STRIDE;
-    const double d = sg[SG_DT];
-    if (!(d != 0.0 && d == d)) continue;
-    const double re = sg[SG_RE], im = sg[SG_IM];
-    const double inv = 1.0 / sqrt(re * re + im * im);
-    const double ur = re * inv, ui = im * inv;
-    // into the frame of this segment: turn by phi_prev - phi_s
-    Sys::rotate(x, pr * ur + pi * ui, pi * ur - pr * ui);
-    double y[N];
+  Sys::rotate(x, c1, s1);
+  // column by column: N independent accumulators, so consecutive FMAs never wait for one another (one warp
+  // per scheduler here: there is no other warp to fill a dependent chain's latency)
+  double y[N];
+  RYDCZ_UNROLL
+  for (int r = 0; r < N; ++r) y[r] = E[(long long)(r * N) * stride] * x[0];
+  RYDCZ_UNROLL
+  for (int c = 1; c < N; ++c) {
     RYDCZ_UNROLL
-    for (int r = 0; r < N; ++r) {
-      double acc = 0.0;
-      RYDCZ_UNROLL
-      for (int c = 0; c < N; ++c) acc = fma(E[(long long)(r * N + c) * stride], x[c], acc);
-      y[r] = acc;
-    }
-    RYDCZ_UNROLL
-    for (int r = 0; r < N; ++r) x[r] = y[r];
-    pr = ur; pi = ui;
+    for (int r = 0; r < N; ++r) y[r] = fma(E[(long long)(r * N + c) * stride], x[c], y[r]);
   }
-  Sys::rotate(x, pr, pi);         // back to the laboratory frame
+  RYDCZ_UNROLL
+  for (int r = 0; r < N; ++r) x[r] = y[r];
 }
 
-// One full gate evaluation from the four propagators (identical atoms, 3-level model).
+// One full gate evaluation from the four propagators (identical atoms, 3-level model).  All systems advance
+// in ONE pass over the segment rows: x <- prod_s R(phi_s) E0 R(-phi_s) x_start, the state kept in the frame of
+// the previous segment; the next row is loaded while the current step computes.
 template <bool NOISY>
 RYDCZ_HD void evaluate_point_repeat_d3(const double* __restrict__ E, long long stride, const double* __restrict__ seg,
-                                       int n_seg, int count, double* __restrict__ out, double* __restrict__ states) {
+                                       int n_seg, double* __restrict__ out, double* __restrict__ states) {
   typedef StateLayout<3> SL;
   typedef RepeatLayout<3> RL;
+  double xa[Sys_rho11s_d3::N], xb[Sys_coh11s_d3::N], xc[Sys_rho01_d3::N], xd[Sys_coh01_d3::N];
+  Sys_rho11s_d3::init(xa); Sys_coh11s_d3::init(xb); Sys_rho01_d3::init(xc); Sys_coh01_d3::init(xd);
+  double pr = 1.0, pi = 0.0;      // phasor of the previous segment
+  int count = 0;                  // active segments
+  double nd = 0.0, nre = 0.0, nim = 0.0;
+  if (n_seg > 0) { nd = seg[SG_DT]; nre = seg[SG_RE]; nim = seg[SG_IM]; }
+  for (int s = 0; s < n_seg; ++s) {
+    const double d = nd, re = nre, im = nim;
+    if (s + 1 < n_seg) {
+      const double* nx = seg + (long long)(s + 1) * SG_STRIDE;
+      nd = nx[SG_DT]; nre = nx[SG_RE]; nim = nx[SG_IM];
+    }
+    if (!(d != 0.0 && d == d)) continue;
+    ++count;
+    const double inv = 1.0 / sqrt(re * re + im * im);
+    const double ur = re * inv, ui = im * inv;
+    const double c1 = pr * ur + pi * ui, s1 = pi * ur - pr * ui;     // turn by phi_prev - phi_s
+    if (NOISY) {
+      repeat_step<Sys_rho11s_d3>(xa, E + (long long)RL::RHO11 * stride, stride, c1, s1);
+      repeat_step<Sys_rho01_d3>(xc, E + (long long)RL::RHO01 * stride, stride, c1, s1);
+    }
+    repeat_step<Sys_coh11s_d3>(xb, E + (long long)RL::COH11 * stride, stride, c1, s1);
+    repeat_step<Sys_coh01_d3>(xd, E + (long long)RL::COH01 * stride, stride, c1, s1);
+    pr = ur; pi = ui;
+  }
+  // back to the laboratory frame
+  if (NOISY) { Sys_rho11s_d3::rotate(xa, pr, pi); Sys_rho01_d3::rotate(xc, pr, pi); }
+  Sys_coh11s_d3::rotate(xb, pr, pi); Sys_coh01_d3::rotate(xd, pr, pi);
+
   double p01 = 1.0, p11 = 1.0, loss = 0.0, ryd = 0.0, flops = 0.0, build_steps = 0.0;
-  double c01r, c01i, c11r, c11i;
   int n_sys = 2;
   if (NOISY) {
-    double x[Sys_rho11s_d3::N];
-    repeat_apply<Sys_rho11s_d3>(x, E + (long long)RL::RHO11 * stride, stride, seg, n_seg);
-    p11 = x[RHO11S_POP_D3];
+    p11 = xa[RHO11S_POP_D3];
     double xf[Sys_rho11s_d3::FULL_N];
-    Sys_rho11s_d3::expand(x, xf);
+    Sys_rho11s_d3::expand(xa, xf);
     loss = rho11_loss_d3(xf); ryd = rho11_ryd_d3(xf);
     if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_rho11s_d3::FULL_N; ++i) states[SL::RHO11 + i] = xf[i]; }
-    double y[Sys_rho01_d3::N];
-    repeat_apply<Sys_rho01_d3>(y, E + (long long)RL::RHO01 * stride, stride, seg, n_seg);
-    p01 = y[RHO01_POP_D3];
-    if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_rho01_d3::N; ++i) { states[SL::RHO01 + i] = y[i]; states[SL::RHO10 + i] = y[i]; } }
+    p01 = xc[RHO01_POP_D3];
+    if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_rho01_d3::N; ++i) { states[SL::RHO01 + i] = xc[i]; states[SL::RHO10 + i] = xc[i]; } }
     n_sys = 4;
     flops += 2.0 * count * (RL::NA * RL::NA + RL::NC_ * RL::NC_);
     for (int c = 0; c < RL::NA; ++c) {
@@ -142,29 +156,23 @@ RYDCZ_HD void evaluate_point_repeat_d3(const double* __restrict__ E, long long s
       build_steps += st; flops += st * 2.0 * (Sys_rho01_d3::NNZ + Sys_rho01_d3::N);
     }
   }
-  {
-    double x[Sys_coh11s_d3::N];
-    repeat_apply<Sys_coh11s_d3>(x, E + (long long)RL::COH11 * stride, stride, seg, n_seg);
-    c11r = x[COH11S_RE_D3]; c11i = x[COH11S_IM_D3];
-    if (!NOISY) ryd = 1.0 - (c11r * c11r + c11i * c11i);
-    if (states) {
-      double xf[Sys_coh11s_d3::FULL_N];
-      Sys_coh11s_d3::expand(x, xf);
-      RYDCZ_UNROLL for (int i = 0; i < Sys_coh11s_d3::FULL_N; ++i) states[SL::COH11 + i] = xf[i];
-    }
-    double y[Sys_coh01_d3::N];
-    repeat_apply<Sys_coh01_d3>(y, E + (long long)RL::COH01 * stride, stride, seg, n_seg);
-    c01r = y[COH01_RE_D3]; c01i = y[COH01_IM_D3];
-    if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d3::N; ++i) { states[SL::COH01 + i] = y[i]; states[SL::COH10 + i] = y[i]; } }
-    flops += 2.0 * count * (RL::NB * RL::NB + RL::ND * RL::ND);
-    for (int c = 0; c < RL::NB; ++c) {
-      const double st = E[(long long)(RL::STEPS + RL::NA + c) * stride];
-      build_steps += st; flops += st * 2.0 * (Sys_coh11s_d3::NNZ + Sys_coh11s_d3::N);
-    }
-    for (int c = 0; c < RL::ND; ++c) {
-      const double st = E[(long long)(RL::STEPS + RL::NA + RL::NB + RL::NC_ + c) * stride];
-      build_steps += st; flops += st * 2.0 * (Sys_coh01_d3::NNZ + Sys_coh01_d3::N);
-    }
+  const double c11r = xb[COH11S_RE_D3], c11i = xb[COH11S_IM_D3];
+  const double c01r = xd[COH01_RE_D3], c01i = xd[COH01_IM_D3];
+  if (!NOISY) ryd = 1.0 - (c11r * c11r + c11i * c11i);
+  if (states) {
+    double xf[Sys_coh11s_d3::FULL_N];
+    Sys_coh11s_d3::expand(xb, xf);
+    RYDCZ_UNROLL for (int i = 0; i < Sys_coh11s_d3::FULL_N; ++i) states[SL::COH11 + i] = xf[i];
+    RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d3::N; ++i) { states[SL::COH01 + i] = xd[i]; states[SL::COH10 + i] = xd[i]; }
+  }
+  flops += 2.0 * count * (RL::NB * RL::NB + RL::ND * RL::ND);
+  for (int c = 0; c < RL::NB; ++c) {
+    const double st = E[(long long)(RL::STEPS + RL::NA + c) * stride];
+    build_steps += st; flops += st * 2.0 * (Sys_coh11s_d3::NNZ + Sys_coh11s_d3::N);
+  }
+  for (int c = 0; c < RL::ND; ++c) {
+    const double st = E[(long long)(RL::STEPS + RL::NA + RL::NB + RL::NC_ + c) * stride];
+    build_steps += st; flops += st * 2.0 * (Sys_coh01_d3::NNZ + Sys_coh01_d3::N);
   }
   cz_epilogue(NOISY, p01, p01, p11, c01r, c01i, c01r, c01i, c11r, c11i, out);
   out[OUT_LOSS] = loss; out[OUT_RYD] = ryd;

@@ -81,8 +81,8 @@ extern "C" int hostsim_evaluate(int dim, int noisy, long long n_points, const do
           else repeat_build_d3<false>(col, pt, sg + (long long)first * SG_STRIDE, E.data(), 1);
         }
         double* st = states ? states + i * StateLayout<3>::STRIDE : nullptr;
-        if (noisy) evaluate_point_repeat_d3<true>(E.data(), 1, sg, n_seg[i], count, o, st);
-        else evaluate_point_repeat_d3<false>(E.data(), 1, sg, n_seg[i], count, o, st);
+        if (noisy) evaluate_point_repeat_d3<true>(E.data(), 1, sg, n_seg[i], o, st);
+        else evaluate_point_repeat_d3<false>(E.data(), 1, sg, n_seg[i], o, st);
         ++g_repeat_used;
         continue;
       }

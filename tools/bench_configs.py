@@ -89,6 +89,16 @@ for proto, nseg in (("lp", 5), ("jp", 5), ("sjp", 5)):
     dt, cost = timed(lambda: f(X), 3)
     line(f"config4_population_8192_{proto}", 8192, dt, holder["r"], dict(best_cost=float(np.min(cost))))
 
+# smooth JP at batch size: 65,536 candidates inside the optimiser's bounds (300 steps each)
+bounds, x0, _ = bo.bounds_and_x0("sjp", 5)
+lo, hi = np.array(bounds).T
+X = lo[:, None] + (hi - lo)[:, None] * np.random.default_rng(43).uniform(size=(len(bounds), 65536))
+holder = {}
+f = bo.make_vectorized_objective("sjp", include_noise=True, n_segments=5,
+                                 on_batch=lambda X_, r: holder.__setitem__("r", r))
+dt, cost = timed(lambda: f(X), 3)
+line("smooth_jp_65536_noisy", 65536, dt, holder["r"], dict(repeated_segment_points=ev.repeat_stats()))
+
 # config 5: Rb vs Cs with the intermediate state kept (5 levels per atom, 25x25 rho), LP protocol, distinct
 # second-leg powers; host prologue (NumPy) + rydcz_evaluate_host
 B5 = 131072
