@@ -11,6 +11,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -557,6 +558,7 @@ struct rydcz_ctx {
   };
   static constexpr int kLanes = 3;
   Lane lane[kLanes];
+  int pack_threads = 1;                           // host threads that gather the columns (env RYDCZ_PACK_THREADS)
   int64_t chunk = 32768;                          // points per pipeline chunk (profiles/r01_e2e_chunk_sweep_v9.txt)
 };
 
@@ -803,6 +805,10 @@ int rydcz_create(int device, rydcz_ctx** out) {
   if (device < 0 || device >= count) { g_create_error = "device index out of range"; return 2; }
   rydcz_ctx* ctx = new rydcz_ctx();
   ctx->device = device;
+  if (const char* e = getenv("RYDCZ_PACK_THREADS")) {
+    const int t = atoi(e);
+    ctx->pack_threads = t < 1 ? 1 : (t > 16 ? 16 : t);
+  }
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if ((e = cudaSetDevice(device)) != cudaSuccess ||
       (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -1185,7 +1191,9 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
   // lanes overlap on the GPU, and a shorter chunk shortens the pipeline's fill and drain (sweep on 262,144
   // bang-bang candidates: 65,536 -> 45.7, 49,152 -> 50.6, 32,768 -> 56.3, 16,384 -> 47.6 M evaluations/s).
   const int64_t per_item = n_shots > 0 ? n_shots : 1;
-  int64_t chunk = ctx->chunk / per_item;
+  // (the 5-level kernel runs ~25 ms per 65,536 points: there a chunk must be several waves of resident threads,
+  //  32,768-point chunks cost it 19 %)
+  int64_t chunk = (dim == 5 ? 4 * ctx->chunk : ctx->chunk) / per_item;
   if (chunk < 1024) chunk = 1024;
   if (n_points < chunk + chunk / 2) chunk = n_points;
   const int64_t n_chunks = (n_points + chunk - 1) / chunk;
@@ -1232,8 +1240,11 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
     const int64_t nc = (i0 + chunk <= n_points) ? chunk : n_points - i0;
     if (c >= rydcz_ctx::kLanes) CK(cudaEventSynchronize(L.ring_free));   // the lane's ring is free again
     // gather the varying columns into the page-locked ring (strided columns of the caller's row-major
-    // arrays: one host thread per column), one H2D copy, scatter on the device
-#pragma omp parallel for schedule(static) num_threads(n_var < 8 ? n_var : 8) if (n_var > 1 && nc >= 4096)
+    // arrays), one H2D copy, scatter on the device.  RYDCZ_PACK_THREADS > 1 gathers with that many OpenMP
+    // threads: 3 % faster end to end on a 1-GPU box, but with one process per GPU on an 8-GPU box the
+    // teams oversubscribe the host cores (end to end 8x slower), so the default is the calling thread alone.
+#pragma omp parallel for schedule(static) num_threads(ctx->pack_threads < n_var ? ctx->pack_threads : n_var) \
+    if (ctx->pack_threads > 1 && n_var > 1 && nc >= 4096)
     for (int j = 0; j < n_var; ++j) {
       const int64_t cstr = col_stride ? col_stride[var[j]] : 1;
       const double* src = h_cols[var[j]] + i0 * cstr;
