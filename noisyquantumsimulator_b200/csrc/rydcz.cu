@@ -67,7 +67,7 @@ __device__ inline void philox_normal2(uint64_t seed, uint32_t point, uint32_t sh
 
 // ---------------------------------------------------------------- kernels
 // Kind of a point: which kernel evaluates it.
-enum PointKind : uint8_t { KIND_GENERAL = 0, KIND_SYM = 1, KIND_CLUSTER = 3, KIND_REPEAT = 5 };
+enum PointKind : uint8_t { KIND_GENERAL = 0, KIND_SYM = 1, KIND_CLUSTER_GENERAL = 2, KIND_CLUSTER = 3, KIND_REPEAT = 5 };
 
 // Per point: its kind, and a sort key (kind in the top bits, work estimate below) so that a warp holds
 // points of one kind and similar cost.  cluster_mode: 0 = plain path only, 1 = clustered path where the
@@ -75,7 +75,7 @@ enum PointKind : uint8_t { KIND_GENERAL = 0, KIND_SYM = 1, KIND_CLUSTER = 3, KIN
 template <int D>
 __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
                             const double* __restrict__ segs, const int32_t* __restrict__ n_seg,
-                            int max_seg, int shots, int noisy, int cluster_mode, uint32_t* __restrict__ keys,
+                            int max_seg, int seg_div, int shots, int noisy, int cluster_mode, uint32_t* __restrict__ keys,
                             uint32_t* __restrict__ idx, uint8_t* __restrict__ kind,
                             uint32_t* __restrict__ task_key, uint32_t* __restrict__ task_val,
                             double* __restrict__ scratch, unsigned long long* __restrict__ counters,
@@ -88,10 +88,11 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
 #pragma unroll
     for (int q = 0; q < CL_MAX_SLOTS; ++q) { slot_K[q] = 0; slot_off[q] = 0; }
     const double* pt = points + i * PointStride<D>::value;
-    const double* sg = segs + i * (int64_t)max_seg * SG_STRIDE;
-    const int ns = n_seg ? n_seg[i] : max_seg;
+    const int64_t sp = i / seg_div;       // row of the pulse schedule (the shots of a point share it)
+    const double* sg = segs + sp * (int64_t)max_seg * SG_STRIDE;
+    const int ns = n_seg ? n_seg[sp] : max_seg;
     const bool sym = (pt[PT_OFF_A] == pt[PT_OFF_B]) && !(shots && pt[PT_SIG_DET] != 0.0);
-    uint32_t group = sym ? 1u : 2u;     // repeated-segment points first, general, plain folded, clustered
+    uint32_t group = sym ? 1u : 2u;     // 4 clustered general, 3 repeated-segment, 2 general, 1 plain folded, 0 clustered
     double w = 0.0;
     if (D == 3 && repeat_count && sym && !shots) {
       int first, count;
@@ -101,13 +102,14 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
       }
     }
     if (!repeated) w = point_work<D>(pt, sg, ns);
-    if (D != 5 && cluster_mode && sym && !shots && !repeated) {
+    if (D != 5 && cluster_mode && (sym || D == 3) && !shots && !repeated) {
       double cost = 0.0;
-      // the slot headers are written on the way (harmless if the point stays on the plain path)
-      const int records = cluster_plan<D>(pt, sg, ns, noisy != 0, true, cost, slot_K, slot_off,
+      // the slot headers are written on the way (harmless if the point stays on the plain path); unequal atoms
+      // (3-level model only) take the two-atom bounds and the general kernel
+      const int records = cluster_plan<D>(pt, sg, ns, noisy != 0, sym, cost, slot_K, slot_off,
                                           scratch + i * (int64_t)CL_STRIDE);
       if (records > 0 && records <= CL_RECORDS && (cluster_mode == 2 || cost < 0.8 * w)) {
-        clustered = true; group = 0u; w = cost; records_planned = records;
+        clustered = true; group = sym ? 0u : 4u; w = sym ? cost : 2.0 * cost; records_planned = records;
       }
     }
     if (task_key) {
@@ -119,9 +121,10 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
         task_val[i * CL_MAX_SLOTS + q] = (uint32_t)(i * CL_RECORDS + slot_off[q]);   // record index of the slot header
       }
     }
-    kind[i] = repeated ? KIND_REPEAT : (clustered ? KIND_CLUSTER : (sym ? KIND_SYM : KIND_GENERAL));
-    const double wq = fmin(fmax(w, 0.0), 1073741823.0);
-    keys[i] = (group << 30) | (uint32_t)wq;
+    kind[i] = repeated ? KIND_REPEAT
+                       : (clustered ? (sym ? KIND_CLUSTER : KIND_CLUSTER_GENERAL) : (sym ? KIND_SYM : KIND_GENERAL));
+    const double wq = fmin(fmax(w, 0.0), 536870911.0);
+    keys[i] = (group << 29) | (uint32_t)wq;
     idx[i] = (uint32_t)i;
   }
   const unsigned m = __ballot_sync(0xffffffffu, clustered);
@@ -173,7 +176,7 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, int64_t point_base,
                 const uint32_t* __restrict__ order,
                 const uint8_t* __restrict__ kind,
                 const double* __restrict__ points, const double* __restrict__ segs,
-                const int32_t* __restrict__ n_seg, int max_seg, double* __restrict__ out,
+                const int32_t* __restrict__ n_seg, int max_seg, int seg_div, double* __restrict__ out,
                 double* __restrict__ states) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int64_t point = 0, item;
@@ -215,8 +218,9 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, int64_t point_base,
     mine[PT_V * kBlock] = row[PT_V] / (q2 * q2 * q2);
   }
   const PointView pt{mine, kBlock, live};
-  const double* sg = segs + point * (int64_t)max_seg * SG_STRIDE;
-  const int ns = n_seg ? n_seg[point] : max_seg;
+  const int64_t sp = point / seg_div;     // seg_div > 1: `points` holds one (perturbed) row per shot
+  const double* sg = segs + sp * (int64_t)max_seg * SG_STRIDE;
+  const int ns = n_seg ? n_seg[sp] : max_seg;
   double o[OUT_STRIDE];
   double* st = states ? states + item * StateLayout<D>::STRIDE : nullptr;
   if (SYM) {
@@ -236,18 +240,21 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, int64_t point_base,
 // Clustered-spectrum path (rydcz_cluster.cuh) for identical atoms.  Per thread, in dynamic shared memory
 // ([slot][thread]): the point row + scratch and the three start vectors X0, X1, X2 of rho_11.  The
 // coefficient records were written by cluster_coef_kernel into the point's region of `scratch`.
-template <int D> struct ClusterSmem {
-  static constexpr int XN = D == 3 ? Sys_rho11s_d3::N : Sys_rho11s_d4::N;
-  static constexpr int XN2 = ClusterPair<D>::value ? (D == 3 ? Sys_coh11s_d3::N : Sys_coh11s_d4::N) : 0;
+template <int D, bool SYM = true> struct ClusterSmem {
+  static constexpr int XN = !SYM ? Sys_rho11_d3::N : (D == 3 ? Sys_rho11s_d3::N : Sys_rho11s_d4::N);
+  static constexpr int XN2 = (SYM && ClusterPair<D>::value) ? (D == 3 ? Sys_coh11s_d3::N : Sys_coh11s_d4::N) : 0;
   static constexpr int RING0 = PT_MAX_STRIDE + PT_SCRATCH + 3 * (XN + XN2);   // first column of the record ring
-  static constexpr int SLOTS = RING0 + 3 * ClusterRing<D>::value;
+  static constexpr int SLOTS = RING0 + 3 * (SYM ? ClusterRing<D>::value : CL_RING_GENERAL);
   static constexpr size_t BYTES = (size_t)SLOTS * kBlock * sizeof(double);
 };
-template <int D, bool NOISY>
+// SYM = false: unequal atoms (3-level model), the general systems; `points` may hold one row per shot
+// (seg_div = shots per point: the schedule row is point / seg_div).
+template <int D, bool NOISY, bool SYM>
 __global__ void __launch_bounds__(kBlock, 2)
 evaluate_cluster_kernel(int64_t n_items, const uint32_t* __restrict__ order, uint8_t* __restrict__ kind,
                         const double* __restrict__ points, const double* __restrict__ segs,
-                        const int32_t* __restrict__ n_seg, int max_seg, const double* __restrict__ scratch,
+                        const int32_t* __restrict__ n_seg, int max_seg, int seg_div,
+                        const double* __restrict__ scratch,
                         double* __restrict__ out, double* __restrict__ states,
                         unsigned long long* __restrict__ counters) {
   extern __shared__ double s_cl[];
@@ -256,7 +263,7 @@ evaluate_cluster_kernel(int64_t n_items, const uint32_t* __restrict__ order, uin
   bool keep = g < n_items;
   if (keep) {
     point = order ? order[g] : g;
-    keep = kind[point] == KIND_CLUSTER;
+    keep = kind[point] == (SYM ? KIND_CLUSTER : KIND_CLUSTER_GENERAL);
   }
   const unsigned live = __ballot_sync(0xffffffffu, keep);
   if (!keep) return;
@@ -266,18 +273,20 @@ evaluate_cluster_kernel(int64_t n_items, const uint32_t* __restrict__ order, uin
   for (int k = 0; k < PT_STRIDE; ++k) mine[k * kBlock] = row[k];
   const PointView pt{mine, kBlock, live};
   const Col xcol{mine + (PT_MAX_STRIDE + PT_SCRATCH) * kBlock, kBlock};
-  const Col rcol{mine + ClusterSmem<D>::RING0 * kBlock, kBlock};
-  const double* sg = segs + point * (int64_t)max_seg * SG_STRIDE;
-  const int ns = n_seg ? n_seg[point] : max_seg;
+  const Col rcol{mine + ClusterSmem<D, SYM>::RING0 * kBlock, kBlock};
+  const int64_t sp = point / seg_div;
+  const double* sg = segs + sp * (int64_t)max_seg * SG_STRIDE;
+  const int ns = n_seg ? n_seg[sp] : max_seg;
   const double* rec = scratch + point * (int64_t)CL_STRIDE;
   double o[OUT_STRIDE];
   double* st = states ? states + point * StateLayout<D>::STRIDE : nullptr;
   bool ok;
-  if (D == 3) ok = evaluate_point_cluster_d3<NOISY>(pt, xcol, rcol, sg, ns, rec, o, st);
+  if (!SYM) ok = evaluate_point_cluster_general_d3<NOISY>(pt, xcol, rcol, sg, ns, rec, o, st);
+  else if (D == 3) ok = evaluate_point_cluster_d3<NOISY>(pt, xcol, rcol, sg, ns, rec, o, st);
   else ok = evaluate_point_cluster_d4<NOISY>(pt, xcol, rcol, sg, ns, rec, o, st);
   if (!ok) {
-    // invariant check failed: hand the point to the plain folded kernel, which runs after this one
-    kind[point] = KIND_SYM;
+    // invariant check failed: hand the point to the plain kernel of its kind, which runs after this one
+    kind[point] = SYM ? KIND_SYM : KIND_GENERAL;
     if (counters) atomicAdd(counters + 1, 1ull);
     return;
   }
@@ -285,6 +294,29 @@ evaluate_cluster_kernel(int64_t n_items, const uint32_t* __restrict__ order, uin
 #pragma unroll
   for (int k = 0; k < OUT_STRIDE; k += 2)
     *reinterpret_cast<double2*>(op + k) = make_double2(o[k], o[k + 1]);
+}
+
+// Monte-Carlo shots on the planned paths: one perturbed point row per (point, shot) -- the same Philox draws
+// evaluate_kernel<SHOTS> makes -- so that the planner sees the parameters each shot actually runs with.
+__global__ void shot_rows_kernel(int64_t n_points, int n_shots, uint64_t seed, int64_t point_base,
+                                 const double* __restrict__ points, double* __restrict__ rows) {
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= n_points * n_shots) return;
+  const int64_t point = item / n_shots;
+  const uint32_t shot = (uint32_t)(item - point * n_shots);
+  const double* row = points + point * PT_STRIDE;
+  double* o = rows + item * PT_STRIDE;
+  double da, db, er, unused;
+  philox_normal2(seed, (uint32_t)(point_base + point), shot, 0u, da, db);
+  philox_normal2(seed, (uint32_t)(point_base + point), shot, 1u, er, unused);
+#pragma unroll
+  for (int k = 0; k < PT_STRIDE; ++k) o[k] = row[k];
+  o[PT_OFF_A] = row[PT_OFF_A] + row[PT_SIG_DET] * da;
+  o[PT_OFF_B] = row[PT_OFF_B] + row[PT_SIG_DET] * db;
+  const double q = 1.0 + row[PT_SIG_RELR] * er;
+  const double q2 = q * q;
+  o[PT_V] = row[PT_V] / (q2 * q2 * q2);
+  o[PT_SIG_DET] = 0.0; o[PT_SIG_RELR] = 0.0;
 }
 
 // Repeated-segment path (rydcz_repeat.cuh), 3-level model, identical atoms.  Points of this kind sort to the
@@ -536,7 +568,9 @@ struct rydcz_ctx {
   double* cl_scratch = nullptr; size_t cl_cap = 0;      // coefficient records, CL_STRIDE doubles per point
   unsigned long long* cl_counters = nullptr;            // [0] clustered points, [1] handed back, [2] records, [3] repeated-segment points
   bool cl_smem_set = false;
+  bool cl_smem_gen_set = false;
   bool rp_smem_set = false;
+  double* shot_rows = nullptr; size_t shot_rows_cap = 0;   // one perturbed point row per (point, shot)
   double* rp_E = nullptr; size_t rp_cap = 0;            // repeated-segment path: propagators, [entry][position]
   unsigned* rp_count = nullptr;                         // points of that kind per in-flight call (slot 0 + one per lane)
   cudaEvent_t evc0 = nullptr, evc1 = nullptr;           // around the last coefficient kernel
@@ -683,16 +717,16 @@ static SortScratch context_scratch(rydcz_ctx* ctx, int64_t n, int64_t offset = 0
 template <int D>
 static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const double* d_points,
                       const double* d_segs, const int32_t* d_n_seg, int max_seg, int shots, int noisy,
-                      cudaStream_t st, const uint32_t** order) {
+                      cudaStream_t st, const uint32_t** order, int seg_div = 1) {
   *order = nullptr;
   const int mode = (sc.cl && D != 5 && !shots && n * (int64_t)CL_RECORDS < 0xffffffffLL) ? ctx->cluster_mode : 0;
-  unsigned* rpc = (mode && D == 3 && sc.rp) ? sc.rp_count : nullptr;
+  unsigned* rpc = (mode && D == 3 && sc.rp && seg_div == 1) ? sc.rp_count : nullptr;
   if (rpc) CK(cudaMemsetAsync(rpc, 0, sizeof(unsigned), st));
   uint32_t* tk = mode ? sc.task : nullptr;
   uint32_t* tks = mode ? sc.task + sc.task_n : nullptr;
   uint32_t* tv = mode ? sc.task + 2 * sc.task_n : nullptr;
   uint32_t* tvs = mode ? sc.task + 3 * sc.task_n : nullptr;
-  plan_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_points, d_segs, d_n_seg, max_seg, shots, noisy,
+  plan_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_points, d_segs, d_n_seg, max_seg, seg_div, shots, noisy,
                                                               mode, sc.keys, sc.idx, sc.kind, tk, tv, sc.cl,
                                                               ctx->cl_counters, rpc);
   CK(cudaGetLastError());
@@ -727,35 +761,47 @@ template <int D, bool NOISY, bool SHOTS>
 static int launch_eval(rydcz_ctx* ctx, const SortScratch& sc, int64_t n_items, int n_shots, uint64_t seed,
                        const uint32_t* order, const double* d_points, const double* d_segs,
                        const int32_t* d_n_seg, int max_seg, double* d_out, double* d_states, cudaStream_t st,
-                       int mark = 3, int64_t point_base = 0) {
+                       int mark = 3, int64_t point_base = 0, int seg_div = 1) {
   // mark: bit 0 = record the start event, bit 1 = record the end event (a pipelined call marks the
   // first chunk's start and the last chunk's end)
   const unsigned grid = (unsigned)((n_items + kBlock - 1) / kBlock);
   if (mark & 1) CK(cudaEventRecord(ctx->ev0, st));
+  if (!SHOTS && D == 3 && sc.cl && ctx->cluster_mode) {
+    // unequal atoms on the clustered path; before the plain general kernel, which takes the hand-backs
+    if (!ctx->cl_smem_gen_set) {
+      CK(cudaFuncSetAttribute(evaluate_cluster_kernel<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ClusterSmem<3, false>::BYTES));
+      CK(cudaFuncSetAttribute(evaluate_cluster_kernel<3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ClusterSmem<3, false>::BYTES));
+      ctx->cl_smem_gen_set = true;
+    }
+    evaluate_cluster_kernel<3, NOISY, false><<<grid, kBlock, ClusterSmem<3, false>::BYTES, st>>>(
+        n_items, order, sc.kind, d_points, d_segs, d_n_seg, max_seg, seg_div, sc.cl, d_out, d_states, ctx->cl_counters);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
   evaluate_kernel<D, NOISY, SHOTS, false><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, point_base, order,
                                                                    sc.kind, d_points, d_segs, d_n_seg, max_seg,
-                                                                   d_out, d_states);
+                                                                   seg_div, d_out, d_states);
   CK(cudaGetLastError());
   ctx->launches++;
   if (!SHOTS && sc.cl && ctx->cluster_mode) {
     if (!ctx->cl_smem_set) {
-      CK(cudaFuncSetAttribute(evaluate_cluster_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ClusterSmem<3>::BYTES));
-      CK(cudaFuncSetAttribute(evaluate_cluster_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ClusterSmem<3>::BYTES));
-      CK(cudaFuncSetAttribute(evaluate_cluster_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ClusterSmem<4>::BYTES));
-      CK(cudaFuncSetAttribute(evaluate_cluster_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ClusterSmem<4>::BYTES));
+      CK(cudaFuncSetAttribute(evaluate_cluster_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ClusterSmem<3>::BYTES));
+      CK(cudaFuncSetAttribute(evaluate_cluster_kernel<3, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ClusterSmem<3>::BYTES));
+      CK(cudaFuncSetAttribute(evaluate_cluster_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ClusterSmem<4>::BYTES));
+      CK(cudaFuncSetAttribute(evaluate_cluster_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ClusterSmem<4>::BYTES));
       ctx->cl_smem_set = true;
     }
     // before the plain folded kernel: points whose invariant check fails are handed on to it
-    evaluate_cluster_kernel<D, NOISY><<<grid, kBlock, ClusterSmem<D>::BYTES, st>>>(
-        n_items, order, sc.kind, d_points, d_segs, d_n_seg, max_seg, sc.cl, d_out, d_states, ctx->cl_counters);
+    evaluate_cluster_kernel<D, NOISY, true><<<grid, kBlock, ClusterSmem<D>::BYTES, st>>>(
+        n_items, order, sc.kind, d_points, d_segs, d_n_seg, max_seg, seg_div, sc.cl, d_out, d_states, ctx->cl_counters);
     CK(cudaGetLastError());
     ctx->launches++;
   }
   evaluate_kernel<D, NOISY, SHOTS, true><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, point_base, order,
                                                                   sc.kind, d_points, d_segs, d_n_seg, max_seg,
-                                                                  d_out, d_states);
+                                                                  seg_div, d_out, d_states);
   CK(cudaGetLastError());
-  if (!SHOTS && D == 3 && sc.cl && sc.rp && ctx->cluster_mode && n_items * (int64_t)CL_RECORDS < 0xffffffffLL) {
+  if (!SHOTS && D == 3 && seg_div == 1 && sc.cl && sc.rp && ctx->cluster_mode && n_items * (int64_t)CL_RECORDS < 0xffffffffLL) {
     // fixed grids: the kernels find the number of repeated-segment points on the device
     const unsigned pg = (unsigned)(ctx->sm_count * 8);
     const unsigned need_b = (unsigned)((n_items * RepeatLayout<3>::COLS + kBlock - 1) / kBlock);
@@ -827,7 +873,7 @@ void rydcz_destroy(rydcz_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->keys); cudaFree(ctx->keys_sorted); cudaFree(ctx->idx); cudaFree(ctx->idx_sorted);
   cudaFree(ctx->kind); cudaFree(ctx->cl_scratch); cudaFree(ctx->cl_counters); cudaFree(ctx->task);
-  cudaFree(ctx->rp_E); cudaFree(ctx->rp_count);
+  cudaFree(ctx->rp_E); cudaFree(ctx->rp_count); cudaFree(ctx->shot_rows);
   if (ctx->evc0) cudaEventDestroy(ctx->evc0);
   if (ctx->evc1) cudaEventDestroy(ctx->evc1);
   cudaFree(ctx->cub_tmp);
@@ -955,22 +1001,41 @@ int rydcz_evaluate_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, 
 }
 
 // d_shots [n_points][n_shots][16] must be given (scratch or caller's)
+// `sc` covers n_points * n_shots items starting at item_base; d_rows = room for that many point rows (or
+// nullptr: the in-kernel sampling of evaluate_kernel<SHOTS> on the plain path).
 static int shots_impl(rydcz_ctx* ctx, const SortScratch& sc, int dim, int noisy, int64_t n_points, int n_shots,
                       uint64_t seed, int64_t point_base, const double* d_points, const double* d_segs,
-                      const int32_t* d_n_seg, int max_seg, double* d_out_mean, double* d_shots, cudaStream_t st,
-                      int mark) {
+                      const int32_t* d_n_seg, int max_seg, double* d_out_mean, double* d_shots, double* d_rows,
+                      cudaStream_t st, int mark) {
   const int64_t n_items = n_points * n_shots;
   const uint32_t* order = nullptr;
-  int rc = dim == 3 ? make_order<3>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 1, noisy, st, &order)
-                    : make_order<4>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 1, noisy, st, &order);
-  if (rc) return rc;
+  int rc;
+  if (dim == 3 && ctx->cluster_mode && sc.cl && d_rows) {
+    // every shot becomes a point of its own (perturbed row), planned and evaluated like any other point:
+    // strong-blockade shots take the clustered general kernel, the rest the plain one
+    shot_rows_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(n_points, n_shots, seed, point_base,
+                                                                        d_points, d_rows);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    rc = make_order<3>(ctx, sc, n_items, d_rows, d_segs, d_n_seg, max_seg, 0, noisy, st, &order, n_shots);
+    if (rc) return rc;
+    rc = noisy ? launch_eval<3, true, false>(ctx, sc, n_items, 1, 0, order, d_rows, d_segs, d_n_seg, max_seg, d_shots,
+                                             nullptr, st, mark, 0, n_shots)
+               : launch_eval<3, false, false>(ctx, sc, n_items, 1, 0, order, d_rows, d_segs, d_n_seg, max_seg, d_shots,
+                                              nullptr, st, mark, 0, n_shots);
+    if (rc) return rc;
+  } else {
+    rc = dim == 3 ? make_order<3>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 1, noisy, st, &order)
+                  : make_order<4>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 1, noisy, st, &order);
+    if (rc) return rc;
 #define RYDCZ_GO(D, N)                                                                               \
   rc = launch_eval<D, N, true>(ctx, sc, n_items, n_shots, seed, order, d_points, d_segs, d_n_seg, max_seg, \
                                d_shots, nullptr, st, mark, point_base)
-  if (dim == 3) { if (noisy) RYDCZ_GO(3, true); else RYDCZ_GO(3, false); }
-  else { if (noisy) RYDCZ_GO(4, true); else RYDCZ_GO(4, false); }
+    if (dim == 3) { if (noisy) RYDCZ_GO(3, true); else RYDCZ_GO(3, false); }
+    else { if (noisy) RYDCZ_GO(4, true); else RYDCZ_GO(4, false); }
 #undef RYDCZ_GO
-  if (rc) return rc;
+    if (rc) return rc;
+  }
   const int64_t threads = n_points * 32;
   shot_mean_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(n_points, n_shots, d_shots, d_out_mean);
   CK(cudaGetLastError());
@@ -993,9 +1058,15 @@ int rydcz_evaluate_shots_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_po
     if (grow(ctx, &ctx->stage[5], &ctx->stage_cap[5], n_points * n_shots * OUT_STRIDE * sizeof(double))) return 1;
     shots = (double*)ctx->stage[5];
   }
-  if (order_reserve(ctx, n_points, false)) return 1;
-  return shots_impl(ctx, context_scratch(ctx, n_points), dim, noisy, n_points, n_shots, seed, 0, d_points, d_segs, d_n_seg,
-                    max_seg, d_out_mean, shots, st, 3);
+  const int64_t n_items = n_points * n_shots;
+  if (order_reserve(ctx, n_items, dim == 3)) return 1;
+  double* rows = nullptr;
+  if (dim == 3 && ctx->cluster_mode) {
+    if (grow(ctx, (void**)&ctx->shot_rows, &ctx->shot_rows_cap, (size_t)n_items * PT_STRIDE * sizeof(double))) return 1;
+    rows = ctx->shot_rows;
+  }
+  return shots_impl(ctx, context_scratch(ctx, n_items), dim, noisy, n_points, n_shots, seed, 0, d_points, d_segs, d_n_seg,
+                    max_seg, d_out_mean, shots, rows, st, 3);
 }
 
 static int stage_in(rydcz_ctx* ctx, int slot, const void* h, size_t bytes) {
@@ -1206,7 +1277,9 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
   if (grow(ctx, &ctx->plan[0], &ctx->plan_cap[0], n * pstride * sizeof(double))) return 1;
   if (grow(ctx, &ctx->plan[1], &ctx->plan_cap[1], n * S * SG_STRIDE * sizeof(double))) return 1;
   if (grow(ctx, &ctx->plan[2], &ctx->plan_cap[2], n * sizeof(int32_t))) return 1;
-  if (order_reserve(ctx, n_points, dim != 5 && n_shots == 0)) return 1;
+  if (order_reserve(ctx, n_points * per_item, dim != 5 && (n_shots == 0 || dim == 3))) return 1;
+  if (n_shots > 0 && dim == 3 && ctx->cluster_mode &&
+      grow(ctx, (void**)&ctx->shot_rows, &ctx->shot_rows_cap, n * per_item * PT_STRIDE * sizeof(double))) return 1;
   double* d_app = (double*)ctx->stage[0];
   double* d_out = (double*)ctx->stage[3];
   double* d_sc = h_scalars ? (double*)ctx->stage[1] : nullptr;
@@ -1261,14 +1334,16 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
     double* c_sc = d_sc ? d_sc + i0 * SC_STRIDE : nullptr;
     if (prologue_impl(ctx, h_model, nc, d_app + i0, n_points, d_pts + i0 * pstride,
                       d_segs + i0 * (int64_t)S * SG_STRIDE, d_ns + i0, c_sc, st)) return 1;
-    SortScratch sc = context_scratch(ctx, nc, i0, 1 + (int)(c % rydcz_ctx::kLanes));
+    SortScratch sc = context_scratch(ctx, nc * per_item, i0 * per_item, 1 + (int)(c % rydcz_ctx::kLanes));
     sc.tmp = &L.cub_tmp; sc.tmp_cap = &L.cub_cap;
     const int mark = (c == 0 ? 1 : 0) | (c == n_chunks - 1 ? 2 : 0);
     int rc;
     if (n_shots > 0)
       rc = shots_impl(ctx, sc, dim, noisy, nc, n_shots, seed, i0, d_pts + i0 * pstride,
                       d_segs + i0 * (int64_t)S * SG_STRIDE, d_ns + i0, S, d_out + i0 * OUT_STRIDE,
-                      d_shots + i0 * n_shots * OUT_STRIDE, st, mark);
+                      d_shots + i0 * n_shots * OUT_STRIDE,
+                      (dim == 3 && ctx->cluster_mode && ctx->shot_rows) ? ctx->shot_rows + i0 * n_shots * PT_STRIDE : nullptr,
+                      st, mark);
     else
       rc = evaluate_impl(ctx, sc, dim, noisy, nc, d_pts + i0 * pstride, d_segs + i0 * (int64_t)S * SG_STRIDE,
                          d_ns + i0, S, d_out + i0 * OUT_STRIDE, d_st ? d_st + i0 * (sb / sizeof(double)) : nullptr,

@@ -689,4 +689,75 @@ template <int D> struct ClusterPair { static constexpr bool value = false; };
 RYDCZ_DEFINE_EVALUATE_CLUSTER(3)
 RYDCZ_DEFINE_EVALUATE_CLUSTER(4)
 
+// The same for atoms that see different detunings (Monte-Carlo shots with Doppler offsets): the general
+// 25-variable rho_11 and 8-variable coherence on the clustered expansion with the two-atom bounds of
+// cluster_geometry(sym = false); the |01> and |10> inputs are different single-atom problems and stay on the
+// plain loop.  3-level model only (the general 4-level rho_11 has 36 variables: four vectors of it do not fit).
+constexpr int CL_RING_GENERAL = 2;   // 75 start-vector columns leave room for a two-slot record ring
+template <bool NOISY>
+RYDCZ_HD bool evaluate_point_cluster_general_d3(const PointView pt, const Col xcol, const Col rcol,
+                                                const double* __restrict__ seg, int n_seg,
+                                                const double* __restrict__ rec, double* __restrict__ out,
+                                                double* __restrict__ states) {
+  typedef StateLayout<3> SL;
+  double steps = 0.0, flops = 0.0, st;
+  double p01 = 1.0, p10 = 1.0, p11 = 1.0, loss = 0.0, ryd = 0.0;
+  double c01r, c01i, c10r, c10i, c11r, c11i;
+  bool ok = true;
+  if (NOISY) {
+    double x[Sys_rho11_d3::N]; st = 0.0;
+    run_system_cluster<Sys_rho11_d3, CL_RING_GENERAL>(x, xcol, rcol, pt, seg, n_seg, true, rec, st);
+    RYDCZ_RECONVERGE(pt.live);
+    steps += st; flops += st * 2.0 * (3 * Sys_rho11_d3::NNZ + 4 * Sys_rho11_d3::N);
+    p11 = x[RHO11_POP_D3];
+    loss = rho11_loss_d3(x); ryd = rho11_ryd_d3(x);
+    ok = fabs(rho11_trace_d3(x) - 1.0) <= 1e-9;
+    if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_rho11_d3::N; ++i) states[SL::RHO11 + i] = x[i]; }
+  }
+  {
+    double x[Sys_coh11_d3::N]; st = 0.0;
+    run_system_cluster<Sys_coh11_d3, CL_RING_GENERAL>(x, xcol, rcol, pt, seg, n_seg, NOISY, rec, st);
+    RYDCZ_RECONVERGE(pt.live);
+    steps += st; flops += st * 2.0 * (3 * Sys_coh11_d3::NNZ + 4 * Sys_coh11_d3::N);
+    c11r = x[COH11_RE_D3]; c11i = x[COH11_IM_D3];
+    if (!NOISY) { ryd = 1.0 - (c11r * c11r + c11i * c11i); ok = fabs(coh11_norm2_d3(x) - 1.0) <= 1e-9; }
+    if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh11_d3::N; ++i) states[SL::COH11 + i] = x[i]; }
+  }
+  if (!ok) return false;
+  if (NOISY) {
+    double x[Sys_in01_d3::N]; st = 0.0;
+    run_system<Sys_in01_d3>(x, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);
+    steps += st; flops += st * 2.0 * (Sys_in01_d3::NNZ + Sys_in01_d3::N);
+    p01 = x[RHO01_POP_D3];
+    c01r = x[IN01_COH_OFFSET_D3 + COH01_RE_D3]; c01i = x[IN01_COH_OFFSET_D3 + COH01_IM_D3];
+    if (states) {
+      RYDCZ_UNROLL for (int i = 0; i < Sys_rho01_d3::N; ++i) states[SL::RHO01 + i] = x[i];
+      RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d3::N; ++i) states[SL::COH01 + i] = x[IN01_COH_OFFSET_D3 + i];
+    }
+    double y[Sys_in10_d3::N]; st = 0.0;
+    run_system<Sys_in10_d3>(y, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);
+    steps += st; flops += st * 2.0 * (Sys_in10_d3::NNZ + Sys_in10_d3::N);
+    p10 = y[RHO10_POP_D3];
+    c10r = y[IN10_COH_OFFSET_D3 + COH10_RE_D3]; c10i = y[IN10_COH_OFFSET_D3 + COH10_IM_D3];
+    if (states) {
+      RYDCZ_UNROLL for (int i = 0; i < Sys_rho10_d3::N; ++i) states[SL::RHO10 + i] = y[i];
+      RYDCZ_UNROLL for (int i = 0; i < Sys_coh10_d3::N; ++i) states[SL::COH10 + i] = y[IN10_COH_OFFSET_D3 + i];
+    }
+  } else {
+    double x[Sys_coh01_d3::N]; st = 0.0;
+    run_system<Sys_coh01_d3>(x, pt, seg, n_seg, false, st); RYDCZ_RECONVERGE(pt.live);
+    steps += st; flops += st * 2.0 * (Sys_coh01_d3::NNZ + Sys_coh01_d3::N);
+    c01r = x[COH01_RE_D3]; c01i = x[COH01_IM_D3];
+    if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d3::N; ++i) states[SL::COH01 + i] = x[i]; }
+    double y[Sys_coh10_d3::N]; st = 0.0;
+    run_system<Sys_coh10_d3>(y, pt, seg, n_seg, false, st); RYDCZ_RECONVERGE(pt.live);
+    steps += st; flops += st * 2.0 * (Sys_coh10_d3::NNZ + Sys_coh10_d3::N);
+    c10r = y[COH10_RE_D3]; c10i = y[COH10_IM_D3];
+    if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh10_d3::N; ++i) states[SL::COH10 + i] = y[i]; }
+  }
+  cz_epilogue(NOISY, p01, p10, p11, c01r, c01i, c10r, c10i, c11r, c11i, out);
+  out[OUT_LOSS] = loss; out[OUT_RYD] = ryd; out[OUT_STEPS] = steps; out[OUT_FLOPS] = flops;
+  return true;
+}
+
 }  // namespace rydcz

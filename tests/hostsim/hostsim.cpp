@@ -43,6 +43,24 @@ static bool try_cluster(const rydcz::PointView pt, const double* row, const doub
   return ok;
 }
 
+// unequal atoms, 3-level model: the general systems on the clustered path
+static bool try_cluster_general(const rydcz::PointView pt, const double* row, const double* sg, int ns, bool noisy,
+                                double* o, double* st) {
+  using namespace rydcz;
+  double cost = 0.0;
+  const int records = cluster_plan<3>(row, sg, ns, noisy, false, cost);
+  if (records <= 0 || records > CL_RECORDS) return false;
+  if (g_cluster == 1 && !(cost < 0.8 * point_work<3>(row, sg, ns))) return false;
+  std::vector<double> rec((size_t)CL_STRIDE, 0.0);
+  cluster_prepare<3>(row, sg, ns, noisy, false, rec.data());
+  double xc[3 * 25], ring[3 * 8];
+  const bool ok = noisy ? evaluate_point_cluster_general_d3<true>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), o, st)
+                        : evaluate_point_cluster_general_d3<false>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), o, st);
+  ++g_cluster_used;
+  if (!ok) ++g_cluster_retry;
+  return ok;
+}
+
 // coefficient records of one point, for tests of the cosine transform (returns the number of records)
 extern "C" int hostsim_cluster_records(int dim, int noisy, const double* point, const double* segs, int n_seg,
                                        double* rec, double* cost) {
@@ -86,6 +104,10 @@ extern "C" int hostsim_evaluate(int dim, int noisy, long long n_points, const do
         ++g_repeat_used;
         continue;
       }
+    }
+    if (g_cluster && !sym && dim == 3 && g_allow_sym) {
+      double* st = states ? states + i * StateLayout<3>::STRIDE : nullptr;
+      if (try_cluster_general(pt, row, sg, n_seg[i], noisy != 0, o, st)) continue;
     }
     if (g_cluster && sym && (dim == 3 || dim == 4)) {
       double* st = states ? states + i * (dim == 3 ? StateLayout<3>::STRIDE : StateLayout<4>::STRIDE) : nullptr;

@@ -158,3 +158,24 @@ def test_strong_dephasing_and_negative_duration_take_substeps(hostsim):
     n, rec, _ = _records(hostsim, 3, True, *[x[0] for x in C.pack_batch(
         [next(c for c in REF if c["name"] == "lp_noisy_linewidth_1MHz")])])
     assert (int(rec[0, 0]) >> 10) > 1
+
+
+def test_unequal_atoms_take_the_general_systems_on_the_clustered_path(hostsim):
+    """Doppler-shifted atoms (off_a != off_b, as in a Monte-Carlo shot) and a perturbed blockade: the general
+    25-variable rho_11 and 8-variable coherence on the clustered expansion against the plain path."""
+    rng = np.random.default_rng(7)
+    for name in ("lp_noisy", "bb5_noisy", "bb7_noisy", "vb_bb5_default", "lp_noisy_cs133"):
+        case = next(c for c in REF if c["name"] == name)
+        noisy = case["rates"] is not None
+        pts, seg, ns = C.pack_batch([case])
+        pts, seg, ns = np.tile(pts, (4, 1)), np.tile(seg, (4, 1, 1)), np.tile(ns, 4)
+        pts[:, 2] += 2 * np.pi * 3e4 * rng.standard_normal(4)          # PT_OFF_A
+        pts[:, 3] += 2 * np.pi * 3e4 * rng.standard_normal(4)          # PT_OFF_B
+        pts[:, 0] *= 1 + 0.01 * rng.standard_normal(4)                 # PT_V
+        a, sa = hostsim(3, noisy, pts, seg, ns, cluster=0)
+        hostsim.cluster_stats()
+        b, sb = hostsim(3, noisy, pts, seg, ns, cluster=2)
+        used, back = hostsim.cluster_stats()
+        assert used == 4 and back == 0, name
+        assert np.abs(sa - sb).max() < 1e-11 and np.abs(a[:, :14] - b[:, :14]).max() < 1e-11, name
+        assert b[:, C.OUT["steps"]].sum() < 0.2 * a[:, C.OUT["steps"]].sum()

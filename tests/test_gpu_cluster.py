@@ -101,3 +101,26 @@ def test_repeated_segment_path_for_smooth_jp(ev):
             for lab in ("01", "10", "11"):
                 got = ops["rho" + lab] if noisy else ops["coh" + lab][:, 0]
                 assert np.abs(got - gold[lab]).max() < 1e-10, c["name"]
+
+
+def test_shots_planned_per_shot_match_the_in_kernel_sampling(ev):
+    """Monte-Carlo shots: with the clustered path on, every shot is planned as a point of its own (perturbed row,
+    general clustered kernel); same Philox draws as the plain path's in-kernel sampling, same per-shot rows."""
+    case = next(c for c in REF if c["name"] == "lp_noisy")
+    pts, seg, ns = C.pack_batch([case])
+    rng = np.random.default_rng(3)
+    B, shots = 96, 16
+    P, S, N = np.tile(pts, (B, 1)), np.tile(seg, (B, 1, 1)), np.tile(ns, B)
+    P[:, 0] *= 10 ** rng.uniform(-0.3, 0.3, B)
+    P[:, 9] = 2 * np.pi * rng.uniform(2e4, 8e4, B)       # PT_SIG_DET
+    P[:, 10] = rng.uniform(0.002, 0.01, B)               # PT_SIG_RELR
+    ev.set_cluster(0)
+    m0, s0 = ev.evaluate_shots_host(3, True, shots, 99, P, S, N, want_shots=True)
+    ev.cluster_stats()
+    ev.set_cluster(1)
+    m1, s1 = ev.evaluate_shots_host(3, True, shots, 99, P, S, N, want_shots=True)
+    planned, back = ev.cluster_stats()
+    assert planned == B * shots and back == 0
+    assert np.abs(s0[..., :14] - s1[..., :14]).max() < 5e-11
+    assert np.abs(m0[:, :14] - m1[:, :14]).max() < 5e-11
+    assert s1[..., 14].sum() < 0.2 * s0[..., 14].sum()
