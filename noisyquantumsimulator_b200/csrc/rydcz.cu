@@ -691,9 +691,13 @@ static int order_reserve(rydcz_ctx* ctx, int64_t n, bool want_cluster = true) {
   if (want_cluster && ctx->cluster_mode) {
     const size_t bytes = (size_t)n * CL_STRIDE * sizeof(double);
     if (bytes <= kClusterScratchMax) {
-      if (grow(ctx, (void**)&ctx->cl_scratch, &ctx->cl_cap, bytes)) return 1;
-      if (grow(ctx, (void**)&ctx->task, &ctx->task_cap, (size_t)n * CL_MAX_SLOTS * 4 * sizeof(uint32_t))) return 1;
-      if (grow(ctx, (void**)&ctx->rp_E, &ctx->rp_cap, (size_t)n * RepeatLayout<3>::STRIDE * sizeof(double))) return 1;
+      // no memory for the records (16.6 KB per point): not an error, the call stays on the plain path
+      if (grow(ctx, (void**)&ctx->cl_scratch, &ctx->cl_cap, bytes) ||
+          grow(ctx, (void**)&ctx->task, &ctx->task_cap, (size_t)n * CL_MAX_SLOTS * 4 * sizeof(uint32_t)) ||
+          grow(ctx, (void**)&ctx->rp_E, &ctx->rp_cap, (size_t)n * RepeatLayout<3>::STRIDE * sizeof(double))) {
+        cudaGetLastError();
+        ctx->err.clear();
+      }
     }
   }
   return 0;
