@@ -1,12 +1,21 @@
 // rydcz.cu -- sm_100a kernels and the C ABI (include/rydcz.h) of the Rydberg-CZ evaluator.
 //
-// Mapping.  One thread = one gate evaluation (or one Monte-Carlo shot of one).  The six reduced
-// Lindblad systems of a point (rydcz_core.cuh) are advanced one after the other with all state
-// in registers; the kernel reads ~0.2-10 KB per point and writes 128 B, so HBM is idle and the
-// bound is the FP64 FMA pipe.  Work per point varies with ||H|| tau by orders of magnitude, so a
-// pre-pass estimates it and points are processed heaviest-first in sorted order: the 32 threads
-// of a warp then run (almost) the same trip counts and the tail of the grid is made of cheap
-// points.
+// Mapping.  One thread = one gate evaluation (or one Monte-Carlo shot of one).  The reduced Lindblad systems
+// of a point (rydcz_core.cuh) are advanced one after the other with all state in registers and per-thread
+// shared-memory columns; HBM traffic is small and the bound is the FP64 FMA pipe.
+//
+// A batch is PLANNED first (plan_kernel): every point gets a kind and a cost estimate, and points are
+// processed in sorted order (kind, heaviest first), so the 32 threads of a warp run the same kernel path
+// with (almost) the same trip counts and the tail of the grid is made of cheap points.  Kinds:
+//   * clustered (rydcz_cluster.cuh): strong blockade -- the cubic map of the three spectral clusters onto one
+//     Chebyshev interval; cost follows Omega tau instead of V tau.  cluster_coef_kernel writes the coefficient
+//     records of every pulse segment group, evaluate_cluster_kernel consumes them (identical atoms: folded
+//     systems; unequal atoms / Monte-Carlo shots: the general systems, every shot planned as its own point);
+//   * repeated-segment (rydcz_repeat.cuh): >= 32 segments that differ only in the laser phase (smooth JP) --
+//     one dense propagator per system, built column by column and applied 300 times;
+//   * plain (rydcz_core.cuh): single-interval Chebyshev for everything else (weak blockade, shaped pulses,
+//     4-level shots, the 5-level model), folded or general; also takes back any clustered point whose
+//     trace / norm check fails.
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
 #include <stdint.h>
