@@ -1274,6 +1274,8 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
   // chunking: with the clustered path a 32,768-point chunk takes ~0.5 ms of kernels, the chunks of the three
   // lanes overlap on the GPU, and a shorter chunk shortens the pipeline's fill and drain (sweep on 262,144
   // bang-bang candidates: 65,536 -> 45.7, 49,152 -> 50.6, 32,768 -> 56.3, 16,384 -> 47.6 M evaluations/s).
+  // Splitting the first chunk in four, so that the GPU starts sooner, was tried again with these kernels:
+  // 4.83 ms against 4.56 ms per call -- the small pieces add more launches than they save in fill time.
   const int64_t per_item = n_shots > 0 ? n_shots : 1;
   // (the 5-level kernel runs ~25 ms per 65,536 points: there a chunk must be several waves of resident threads,
   //  32,768-point chunks cost it 19 %)
