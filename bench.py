@@ -222,6 +222,22 @@ def run_ours(args, rank, world, local_rank):
 
     dfma_peak, dmma_peak = ev.fp64_peak()
     matvec_peak = ev.fp64_matvec_peak()
+    # second reference point asked for by SURVEY 8d: cuBLAS DGEMM 8192^3 (context only; the denominator is the DFMA peak)
+    dgemm_peak = None
+    if rank == 0:
+        try:
+            a = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+            b = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+            torch.matmul(a, b)
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            best = 1e30
+            for _ in range(3):
+                g0.record(); c = torch.matmul(a, b); g1.record(); torch.cuda.synchronize()
+                best = min(best, g0.elapsed_time(g1))
+            dgemm_peak = 2.0 * 8192.0 ** 3 / (best * 1e-3) * 1e-12
+            del a, b, c
+        except Exception:
+            dgemm_peak = None
     try:     # DRAM traffic of the dominant kernel from the committed ncu capture (scales with the batch)
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             tr = json.load(f)
@@ -348,7 +364,7 @@ def run_ours(args, rank, world, local_rank):
                          # capture (profiles/ncu_traffic.json), scaled to this batch size
                          "traffic": traffic, "traffic_kernel": traffic_kernel,
                          "algorithmic_bytes": alg_bytes,
-                         "kernel": ("rydcz::evaluate_cluster_kernel<3,true>" if clustered
+                         "kernel": ("rydcz::evaluate_cluster_kernel<3,true,true>" if clustered
                                     else "rydcz::evaluate_kernel<3,true,false,true>"),
                          "kernel_ms": k_ms, "flops_per_launch": flops_per_launch,
                          # the clustered path's second kernel (coefficient records, one thread per pulse segment):
@@ -356,7 +372,7 @@ def run_ours(args, rank, world, local_rank):
                          "coef_kernel_ms": c_ms,
                          "clustered_points_per_step": cl_planned / max(args.steps, 1), "handed_back": cl_back,
                          "peak_source": "DFMA microbenchmark (rydcz_fp64_peak) measured in this run; "
-                                        "MEASURED_PEAKS.json has no FP64 entry", "dmma_peak": dmma_peak,
+                                        "MEASURED_PEAKS.json has no FP64 entry", "dmma_peak": dmma_peak, "cublas_dgemm_8192_tflops": dgemm_peak,
                          # the hot loop's own 78-nonzero matvec run bare at the kernel's occupancy (three
                          # distinct register operands per DFMA): the ceiling for a loop of this shape
                          "matvec_mix_peak": matvec_peak, "frac_of_matvec_mix_peak": achieved / matvec_peak},
