@@ -21,3 +21,7 @@ ncu --set full --clock-control none --import-source on -k regex:cluster_coef_ker
 ncu --set full --clock-control none --import-source on -k regex:evaluate5_kernel -c 1 -f -o $O/prof_${TAG}_eval5 \
     python tools/prof_eval5.py --iters 1 --points 262144 > $O/ncu_eval5_$TAG.log 2>&1; tail -1 $O/ncu_eval5_$TAG.log
 python tools/bench_configs.py > $O/configs_$TAG.jsonl 2> $O/configs_$TAG.err; cat $O/configs_$TAG.jsonl | cut -c1-420
+# planned paths against the single-interval path on random batches; launch list of a smooth-JP batch
+python tools/stress_paths.py 20000 > $O/stress_paths_$TAG.log 2>&1; tail -1 $O/stress_paths_$TAG.log
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/launches_sjp_$TAG.csv \
+    python tools/prof_sjp.py > $O/prof_sjp_$TAG.log 2>&1; tail -1 $O/prof_sjp_$TAG.log
