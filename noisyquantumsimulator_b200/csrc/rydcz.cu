@@ -367,7 +367,10 @@ repeat_build_kernel(int64_t n_points, const unsigned* __restrict__ repeat_count,
 
 // apply: one thread per position, one warp per CTA.  The warp first copies its 32 propagator sets into shared
 // memory ([entry][lane], 85 KB, two CTAs per SM): the 300 dense steps then read E0 from there instead of
-// streaming 2.4 KB per thread and step from L2.
+// streaming 2.4 KB per thread and step from L2.  Tried and dropped (65,536 smooth-JP candidates, kernel span
+// 3.81 ms): only rho_11's propagator in shared memory and the small ones from global / L1 for three CTAs per
+// SM: 3.87 ms; two warps per 32 positions splitting the rows of rho_11's matvec, state exchanged through
+// shared memory with one barrier per segment: 4.12 ms.
 constexpr int kRepeatBlock = 32;
 constexpr size_t kRepeatSmem = (size_t)RepeatLayout<3>::STRIDE * kRepeatBlock * sizeof(double);
 template <bool NOISY>

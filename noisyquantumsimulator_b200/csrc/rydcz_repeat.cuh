@@ -98,6 +98,12 @@ RYDCZ_HD void repeat_step(double (&x)[Sys::N], const double* __restrict__ E, lon
   for (int r = 0; r < N; ++r) x[r] = y[r];
 }
 
+template <bool NOISY>
+RYDCZ_HD void repeat_finish_d3(const double (&xa)[Sys_rho11s_d3::N], const double (&xb)[Sys_coh11s_d3::N],
+                               const double (&xc)[Sys_rho01_d3::N], const double (&xd)[Sys_coh01_d3::N], int count,
+                               const double* __restrict__ E, long long stride, double* __restrict__ out,
+                               double* __restrict__ states);
+
 // One full gate evaluation from the four propagators (identical atoms, 3-level model).  All systems advance
 // in ONE pass over the segment rows: x <- prod_s R(phi_s) E0 R(-phi_s) x_start, the state kept in the frame of
 // the previous segment; the next row is loaded while the current step computes.
@@ -134,7 +140,17 @@ RYDCZ_HD void evaluate_point_repeat_d3(const double* __restrict__ E, long long s
   // back to the laboratory frame
   if (NOISY) { Sys_rho11s_d3::rotate(xa, pr, pi); Sys_rho01_d3::rotate(xc, pr, pi); }
   Sys_coh11s_d3::rotate(xb, pr, pi); Sys_coh01_d3::rotate(xd, pr, pi);
+  repeat_finish_d3<NOISY>(xa, xb, xc, xd, count, E, stride, out, states);
+}
 
+// Readouts, epilogue and work counters from the four final states (laboratory frame).
+template <bool NOISY>
+RYDCZ_HD void repeat_finish_d3(const double (&xa)[Sys_rho11s_d3::N], const double (&xb)[Sys_coh11s_d3::N],
+                               const double (&xc)[Sys_rho01_d3::N], const double (&xd)[Sys_coh01_d3::N], int count,
+                               const double* __restrict__ E, long long stride, double* __restrict__ out,
+                               double* __restrict__ states) {
+  typedef StateLayout<3> SL;
+  typedef RepeatLayout<3> RL;
   double p01 = 1.0, p11 = 1.0, loss = 0.0, ryd = 0.0, flops = 0.0, build_steps = 0.0;
   int n_sys = 2;
   if (NOISY) {
