@@ -91,10 +91,12 @@ int rydcz_create(int device, rydcz_ctx** ctx);
 void rydcz_destroy(rydcz_ctx* ctx);
 const char* rydcz_last_error(const rydcz_ctx* ctx);     /* ctx may be NULL: last create() error */
 int rydcz_set_sort(rydcz_ctx* ctx, int enable);         /* order points by estimated work (default 1) */
-/* Clustered-spectrum propagation (csrc/rydcz_cluster.cuh) for points with identical atoms and a strong
- * blockade: 0 = never, 1 = where the planner estimates it cheaper than the plain Chebyshev path
- * (default), 2 = wherever it is eligible.  Same results to rounding; a point whose trace / norm check
- * fails on that path is re-evaluated on the plain path inside the same call. */
+/* Clustered-spectrum propagation (csrc/rydcz_cluster.cuh) for points with a strong blockade (identical atoms:
+ * 3- and 4-level models; unequal atoms and Monte-Carlo shots: 3-level model): 0 = never, 1 = where the planner
+ * estimates it cheaper than the plain Chebyshev path (default), 2 = wherever it is eligible.  Same results to
+ * rounding; a point whose trace / norm check fails on that path is re-evaluated on the plain path inside the
+ * same call.  Device memory: 16.6 KB of coefficient records per point (per shot with shots), kept by the
+ * context; if it cannot be allocated (or would exceed 48 GB) the call stays on the plain path. */
 int rydcz_set_cluster(rydcz_ctx* ctx, int mode);
 /* points planned onto the clustered path / handed back to the plain path / 32-byte coefficient records
  * written for them since the last call of this function (synchronises the device; any pointer may be NULL) */
