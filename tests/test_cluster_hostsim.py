@@ -179,3 +179,44 @@ def test_unequal_atoms_take_the_general_systems_on_the_clustered_path(hostsim):
         assert used == 4 and back == 0, name
         assert np.abs(sa - sb).max() < 1e-11 and np.abs(a[:, :14] - b[:, :14]).max() < 1e-11, name
         assert b[:, C.OUT["steps"]].sum() < 0.2 * a[:, C.OUT["steps"]].sum()
+
+
+@pytest.mark.parametrize("dim,noisy", [(3, True), (3, False), (4, True)])
+def test_random_points_agree_on_both_paths(hostsim, dim, noisy):
+    """Seeded random LP and bang-bang points in the SURVEY 8d ranges (V/Omega 4-800, identical and, for the
+    3-level model, unequal atoms): the planner's choice (cluster=1) against the single-interval path."""
+    rng = np.random.default_rng(100 * dim + noisy)
+    n = 60
+    Om = 2 * np.pi * rng.uniform(1.5e6, 9e6, n)
+    P = np.zeros((n, 12))
+    P[:, 0] = Om * 10 ** rng.uniform(0.6, 2.9, n)
+    P[:, 1] = 2 * np.pi * rng.uniform(0, 3e5, n)
+    P[:, 4], P[:, 5] = rng.uniform(2e3, 5e3, n), rng.uniform(2e3, 9e3, n)
+    P[:, 6], P[:, 7], P[:, 8] = 10 ** rng.uniform(2, 6, n), 10 ** rng.uniform(3, 5.5, n), rng.uniform(0, 5e3, n)
+    if dim == 3:
+        odd = rng.random(n) < 0.4
+        P[odd, 2] = 2 * np.pi * 5e4 * rng.standard_normal(odd.sum())
+        P[odd, 3] = 2 * np.pi * 5e4 * rng.standard_normal(odd.sum())
+    S = 5
+    G = np.zeros((n, S, 4))
+    ns = np.full(n, S, dtype=np.int32)
+    lp = rng.random(n) < 0.4
+    ns[lp] = 2
+    tau = rng.uniform(3.5, 5.5, n) / Om
+    xi = np.exp(1j * rng.uniform(-np.pi, np.pi, n))
+    ot = rng.uniform(5, 40, n)
+    b = np.concatenate([np.zeros((n, 1)), np.sort(rng.uniform(0.01, 0.99, (n, S - 1)), 1), np.ones((n, 1))], 1)
+    ph = rng.uniform(-np.pi, np.pi, (n, S))
+    G[:, :, 0] = np.diff(b, axis=1) * (ot / Om)[:, None]
+    G[:, :, 1], G[:, :, 2] = Om[:, None] * np.cos(ph), Om[:, None] * np.sin(ph)
+    G[lp, 0, 0] = G[lp, 1, 0] = tau[lp]
+    G[lp, 0, 1], G[lp, 0, 2] = Om[lp], 0.0
+    G[lp, 1, 1], G[lp, 1, 2] = (Om * xi).real[lp], (Om * xi).imag[lp]
+    G[lp, :2, 3] = (rng.uniform(0.2, 0.5, n) * Om)[lp, None]
+    a, sa = hostsim(dim, noisy, P, G, ns, cluster=0)
+    hostsim.cluster_stats()
+    b_, sb = hostsim(dim, noisy, P, G, ns, cluster=1)
+    used, back = hostsim.cluster_stats()
+    assert n // 3 < used < n and back == 0            # weak-blockade points stay on the plain path
+    assert np.abs(sa - sb).max() < 1e-11
+    assert np.abs(a[:, :14] - b_[:, :14]).max() < 5e-11
