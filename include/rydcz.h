@@ -75,6 +75,22 @@ enum rydcz_out_slot {
 
 typedef struct rydcz_ctx rydcz_ctx;
 
+/* per-point status of the last evaluation call (rydcz_point_status): which path evaluated the point */
+enum rydcz_status {
+  RYDCZ_STATUS_PLAIN = 0,            /* single-interval Chebyshev, general two-atom systems              */
+  RYDCZ_STATUS_PLAIN_FOLDED = 1,     /* single-interval Chebyshev, exchange-folded systems               */
+  RYDCZ_STATUS_CLUSTER_GENERAL = 2,  /* clustered-spectrum expansion, unequal atoms / Monte-Carlo shot   */
+  RYDCZ_STATUS_CLUSTER = 3,          /* clustered-spectrum expansion, identical atoms                    */
+  RYDCZ_STATUS_REPEAT = 5,           /* one propagator for a phase-modulated pulse (smooth JP)           */
+  RYDCZ_STATUS_UNSUPPORTED = 6,      /* not evaluated: the row is NaN (dim 5 with OFF_A != OFF_B)        */
+  RYDCZ_STATUS_HANDED_BACK = 0x10    /* flag: the clustered path's invariant check failed and the plain
+                                        kernel re-evaluated the point inside the same call             */
+};
+/* call-level flags of the last evaluation call (rydcz_call_flags) */
+#define RYDCZ_FLAG_NO_CLUSTER_SCRATCH 1   /* the coefficient scratch of the clustered path could not be allocated
+                                             (or would exceed 48 GB): the whole call ran on the plain path */
+#define RYDCZ_FLAG_UNSUPPORTED_POINTS 2   /* some rows are NaN because no kernel evaluates them (see status) */
+
 /* library / layout queries (no GPU needed) */
 int rydcz_version(void);
 int rydcz_point_stride(void);
@@ -105,11 +121,22 @@ int rydcz_cluster_stats(rydcz_ctx* ctx, int64_t* planned, int64_t* handed_back, 
  * least 32 active segments that differ only in the laser phase -- the smooth Jandura-Pupillo protocol) since
  * the last call of this function.  The path is part of the automatic choice: rydcz_set_cluster(0) disables it. */
 int rydcz_repeat_stats(rydcz_ctx* ctx, int64_t* points);
+/* Status column: the path that evaluated each of the first n items of the last evaluation
+ * call (points; shots when a Monte-Carlo call was planned per shot), an enum rydcz_status value, possibly with
+ * RYDCZ_STATUS_HANDED_BACK or'ed in.  Nothing degrades silently: a call that could not use the clustered path,
+ * or that left rows unevaluated, says so in rydcz_call_flags.  Both synchronise the device. */
+int rydcz_point_status(rydcz_ctx* ctx, int64_t n, int32_t* h_status);
+int rydcz_call_flags(rydcz_ctx* ctx, int* flags, int64_t* unsupported_points);
 
 /* One batch of gate evaluations, inputs and outputs resident in device memory.
  * dim: 3 (|0>,|1>,|r>) or 4 (|0>,|1>,|r+>,|r->).  noisy: 0 -> Schroedinger path with the
  * pure-state epilogue (QuTiP's c_ops=[] branch); 1 -> Lindblad path.  stream: a cudaStream_t
- * (as void*) to enqueue on, or NULL for the context's own stream.  Asynchronous. */
+ * (as void*) to enqueue on, or NULL for the context's own stream.  Asynchronous.
+ * Streams: a context owns ONE set of planning scratch (work order, kinds, coefficient records).  The
+ * asynchronous entry points (*_device) may be given different streams from call to call: each call waits, on
+ * the device, for the previous call of the same context (an event recorded at its end), so calls of one context
+ * never overlap.  For concurrent evaluation on several streams create one context per stream.  Host threads
+ * must not call into one context concurrently. */
 int rydcz_evaluate_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points,
                           const double* d_points, const double* d_segs, const int32_t* d_n_seg,
                           int max_seg, double* d_out, double* d_states, void* stream);
@@ -174,6 +201,14 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
                              const double* const* h_cols, const int64_t* col_stride, const double* h_const,
                              int n_shots, uint64_t seed, double* h_out, double* h_scalars, double* h_states);
 int rydcz_set_chunk(rydcz_ctx* ctx, int64_t points_per_chunk);
+/* The same call returning only the result columns the caller reads, COLUMN-MAJOR: h_out_cm[j * n_points + i] =
+ * out[i][out_slots[j]] (enum rydcz_out_slot), h_scalars_cm[j * n_points + i] = scalars[i][scalar_slots[j]].
+ * The device gathers the columns, so D2H traffic is 8 (n_out + n_scalars) bytes per point instead of 192
+ * (the reference's callers read ~6 numbers per evaluation, RG/optimize_cz_gate.py:434-451). */
+int rydcz_simulate_host_select(rydcz_ctx* ctx, const double* h_model, int64_t n_points,
+                               const double* const* h_cols, const int64_t* col_stride, const double* h_const,
+                               int n_shots, uint64_t seed, const int32_t* out_slots, int n_out, double* h_out_cm,
+                               const int32_t* scalar_slots, int n_scalars, double* h_scalars_cm);
 
 /* page-locked host buffers for the *_host entry points (plain malloc memory works too, slower) */
 int rydcz_pinned_alloc(size_t bytes, void** ptr);

@@ -12,6 +12,12 @@ LIB_PATH = os.environ.get("RYDCZ_LIB_PATH") or os.path.join(HERE, "csrc", "libry
 POINT_STRIDE, SEG_STRIDE, OUT_STRIDE = 12, 4, 16
 APP_STRIDE, MODEL_STRIDE, SCALAR_STRIDE = 40, 32, 8
 SYSTEMS = ("rho11", "rho01", "rho10", "coh11", "coh01", "coh10")
+# enum rydcz_status / RYDCZ_FLAG_* (include/rydcz.h)
+STATUS = {0: "plain", 1: "plain_folded", 2: "cluster_general", 3: "cluster", 5: "repeat", 6: "unsupported"}
+STATUS_HANDED_BACK = 0x10
+FLAG_NO_CLUSTER_SCRATCH, FLAG_UNSUPPORTED_POINTS = 1, 2
+# scalar columns the prologue kernel reports (csrc/rydcz_prologue.cuh: enum ScalarSlot)
+SCALARS = dict(Omega=0, V=1, tau_total=2, tau_single=3, Delta=4, xi_re=5, xi_im=6, omega_tau=7)
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
@@ -48,7 +54,11 @@ _SIGNATURES = {
     "rydcz_simulate_device": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int, C.c_uint64, _vp, _vp, _vp, _vp]),
     "rydcz_simulate_host": (C.c_int, [_vp, _vp, C.c_int64, _vp, C.c_int, C.c_uint64, _vp, _vp, _vp]),
     "rydcz_simulate_host_cols": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, C.c_uint64, _vp, _vp, _vp]),
+    "rydcz_simulate_host_select": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, C.c_uint64, _vp, C.c_int,
+                                             _vp, _vp, C.c_int, _vp]),
     "rydcz_set_chunk": (C.c_int, [_vp, C.c_int64]),
+    "rydcz_point_status": (C.c_int, [_vp, C.c_int64, _vp]),
+    "rydcz_call_flags": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "rydcz_pinned_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "rydcz_pinned_free": (C.c_int, [_vp]),
     "rydcz_last_kernel_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),

@@ -76,7 +76,10 @@ __device__ inline void philox_normal2(uint64_t seed, uint32_t point, uint32_t sh
 
 // ---------------------------------------------------------------- kernels
 // Kind of a point: which kernel evaluates it.
-enum PointKind : uint8_t { KIND_GENERAL = 0, KIND_SYM = 1, KIND_CLUSTER_GENERAL = 2, KIND_CLUSTER = 3, KIND_REPEAT = 5 };
+enum PointKind : uint8_t { KIND_GENERAL = 0, KIND_SYM = 1, KIND_CLUSTER_GENERAL = 2, KIND_CLUSTER = 3, KIND_REPEAT = 5,
+                           KIND_UNSUPPORTED = 6,   // no kernel evaluates this point (dim 5 with unequal atoms): NaN row
+                           KIND_MASK = 0x0f,
+                           KIND_RETRY = 0x10 };    // flag: handed back by the clustered path to the plain kernel of its kind
 
 // Per point: its kind, and a sort key (kind in the top bits, work estimate below) so that a warp holds
 // points of one kind and similar cost.  cluster_mode: 0 = plain path only, 1 = clustered path where the
@@ -101,13 +104,14 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
     const double* sg = segs + sp * (int64_t)max_seg * SG_STRIDE;
     const int ns = n_seg ? n_seg[sp] : max_seg;
     const bool sym = (pt[PT_OFF_A] == pt[PT_OFF_B]) && !(shots && pt[PT_SIG_DET] != 0.0);
-    uint32_t group = sym ? 1u : 2u;     // 4 clustered general, 3 repeated-segment, 2 general, 1 plain folded, 0 clustered
+    uint32_t group = sym ? 1u : 2u;     // 4 repeated-segment (must sort to the FRONT: the repeat kernels walk the first
+    // *repeat_count positions), 3 clustered general, 2 general, 1 plain folded, 0 clustered
     double w = 0.0;
     if (D == 3 && repeat_count && sym && !shots) {
       int first, count;
       if (repeat_eligible(sg, ns, first, count)) {
         // one propagator for all segments (rydcz_repeat.cuh): 30 column builds + count dense steps
-        repeated = true; group = 3u; w = 40.0 * 30.0 + 4.0 * (double)count;
+        repeated = true; group = 4u; w = 40.0 * 30.0 + 4.0 * (double)count;
       }
     }
     if (!repeated) w = point_work<D>(pt, sg, ns);
@@ -118,7 +122,7 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
       const int records = cluster_plan<D>(pt, sg, ns, noisy != 0, sym, cost, slot_K, slot_off,
                                           scratch + i * (int64_t)CL_STRIDE);
       if (records > 0 && records <= CL_RECORDS && (cluster_mode == 2 || cost < 0.8 * w)) {
-        clustered = true; group = sym ? 0u : 4u; w = sym ? cost : 2.0 * cost; records_planned = records;
+        clustered = true; group = sym ? 0u : 3u; w = sym ? cost : 2.0 * cost; records_planned = records;
       }
     }
     if (task_key) {
@@ -195,7 +199,7 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, int64_t point_base,
     if (SHOTS) point = order ? order[g / n_shots] : g / n_shots;
     else point = order ? order[g] : g;
     // a clustered point whose invariant check failed comes back here as KIND_SYM
-    keep = kind[point] == (SYM ? KIND_SYM : KIND_GENERAL);
+    keep = (kind[point] & KIND_MASK) == (SYM ? KIND_SYM : KIND_GENERAL);
   }
   const unsigned live = __ballot_sync(0xffffffffu, keep);   // the lanes that evaluate a point in this kernel
   if (!keep) return;
@@ -295,7 +299,7 @@ evaluate_cluster_kernel(int64_t n_items, const uint32_t* __restrict__ order, uin
   else ok = evaluate_point_cluster_d4<NOISY>(pt, xcol, rcol, sg, ns, rec, o, st);
   if (!ok) {
     // invariant check failed: hand the point to the plain kernel of its kind, which runs after this one
-    kind[point] = SYM ? KIND_SYM : KIND_GENERAL;
+    kind[point] = (SYM ? KIND_SYM : KIND_GENERAL) | KIND_RETRY;
     if (counters) atomicAdd(counters + 1, 1ull);
     return;
   }
@@ -413,7 +417,8 @@ template <bool NOISY>
 __global__ void __launch_bounds__(kBlock, 2)
 evaluate5_kernel(int64_t n_items, const uint32_t* __restrict__ order, const double* __restrict__ points,
                  const double* __restrict__ segs, const int32_t* __restrict__ n_seg, int max_seg,
-                 double* __restrict__ out, double* __restrict__ states) {
+                 double* __restrict__ out, double* __restrict__ states, uint8_t* __restrict__ kind,
+                 unsigned long long* __restrict__ counters) {
   extern __shared__ double s5[];
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool inside = g < n_items;
@@ -425,9 +430,12 @@ evaluate5_kernel(int64_t n_items, const uint32_t* __restrict__ order, const doub
   const unsigned live = __ballot_sync(0xffffffffu, keep);   // lanes that evaluate a point (reconvergence mask)
   if (!inside) return;
   if (!keep) {
-    // the 81-variable general system is not built: atoms with different detunings are not evaluated
+    // the 81-variable general system is not built: atoms with different detunings are not evaluated.  The row
+    // is NaN, the point's status says why (rydcz_point_status), and the call reports it (rydcz_call_flags).
 #pragma unroll
     for (int k = 0; k < OUT_STRIDE; ++k) op[k] = __longlong_as_double(0x7ff8000000000000LL);
+    if (kind) kind[point] = KIND_UNSUPPORTED;
+    if (counters) atomicAdd(counters + 4, 1ull);
     return;
   }
 #pragma unroll
@@ -498,6 +506,19 @@ __global__ void shot_mean_kernel(int64_t n_points, int n_shots, const double* __
   }
 }
 
+// Result columns a caller asked for, gathered from the row-major result block into a column-major staging
+// block ([column][point], column stride = points of the whole batch): only those columns cross PCIe, and
+// each arrives as one contiguous host array.
+struct ColumnSelect { int slot[OUT_STRIDE]; int n; };
+__global__ void gather_columns_kernel(ColumnSelect sel, int64_t n_points, const double* __restrict__ rows, int row_stride,
+                                      double* __restrict__ cols, int64_t col_stride) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_points) return;
+  const double* r = rows + i * row_stride;
+#pragma unroll 1
+  for (int j = 0; j < sel.n; ++j) cols[(int64_t)j * col_stride + i] = r[sel.slot[j]];
+}
+
 // ---------------------------------------------------------------- FP64 peak microbenchmarks
 __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
   double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
@@ -566,6 +587,12 @@ struct rydcz_ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool timed = false;
   bool sort = true;
+  // One set of planning scratch per context: calls enqueued on different streams are ordered on the device
+  // through this event (recorded at the end of every asynchronous entry point, waited for at the start of the next).
+  cudaEvent_t busy = nullptr;
+  bool busy_set = false;
+  int call_flags = 0;          // RYDCZ_FLAG_* of the last evaluation call
+  int64_t status_n = 0;        // items of the last call whose kind[] entries are valid (rydcz_point_status)
   bool smem5_set = false;
   int64_t launches = 0;
   std::string err;
@@ -578,11 +605,14 @@ struct rydcz_ctx {
   // clustered-spectrum path: 0 = off, 1 = where the planner finds it cheaper, 2 = wherever eligible
   int cluster_mode = 1;
   double* cl_scratch = nullptr; size_t cl_cap = 0;      // coefficient records, CL_STRIDE doubles per point
-  unsigned long long* cl_counters = nullptr;            // [0] clustered points, [1] handed back, [2] records, [3] repeated-segment points
+  unsigned long long* cl_counters = nullptr;            // [0] clustered points, [1] handed back, [2] records, [3] repeated-segment points,
+                                                        // [4] unsupported points (NaN rows), [5] spare
   bool cl_smem_set = false;
   bool cl_smem_gen_set = false;
   bool rp_smem_set = false;
   double* shot_rows = nullptr; size_t shot_rows_cap = 0;   // one perturbed point row per (point, shot)
+  void* sel_out = nullptr; size_t sel_out_cap = 0;         // column-major staging of the selected result columns
+  void* sel_sc = nullptr; size_t sel_sc_cap = 0;           // ... and of the selected scalar columns
   double* rp_E = nullptr; size_t rp_cap = 0;            // repeated-segment path: propagators, [entry][position]
   unsigned* rp_count = nullptr;                         // points of that kind per in-flight call (slot 0 + one per lane)
   cudaEvent_t evc0 = nullptr, evc1 = nullptr;           // around the last coefficient kernel
@@ -645,6 +675,18 @@ static int grow(rydcz_ctx* ctx, void** p, size_t* cap, size_t bytes) {
   return 0;
 }
 
+// Serialise the calls of one context on the device (they share the planning scratch).
+static int enter_call(rydcz_ctx* ctx, cudaStream_t st) {
+  if (ctx->busy_set) CK(cudaStreamWaitEvent(st, ctx->busy, 0));
+  return 0;
+}
+static int leave_call(rydcz_ctx* ctx, cudaStream_t st) {
+  if (!ctx->busy) CK(cudaEventCreateWithFlags(&ctx->busy, cudaEventDisableTiming));
+  CK(cudaEventRecord(ctx->busy, st));
+  ctx->busy_set = true;
+  return 0;
+}
+
 static const char* kSysNames[6] = {"rho11", "rho01", "rho10", "coh11", "coh01", "coh10"};
 template <int D> static void sys_tables(int (&off)[6], int (&n)[6], int (&nnz)[6]);
 template <> void sys_tables<3>(int (&off)[6], int (&n)[6], int (&nnz)[6]) {
@@ -695,21 +737,25 @@ static int order_reserve(rydcz_ctx* ctx, int64_t n, bool want_cluster = true) {
     ctx->order_cap = (size_t)n;
   }
   if (!ctx->cl_counters) {
-    CK(cudaMalloc(&ctx->cl_counters, 4 * sizeof(unsigned long long)));
-    CK(cudaMemset(ctx->cl_counters, 0, 4 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->cl_counters, 6 * sizeof(unsigned long long)));
+    CK(cudaMemset(ctx->cl_counters, 0, 6 * sizeof(unsigned long long)));
     CK(cudaEventCreate(&ctx->evc0)); CK(cudaEventCreate(&ctx->evc1));
     CK(cudaMalloc(&ctx->rp_count, (1 + rydcz_ctx::kLanes) * sizeof(unsigned)));
   }
   if (want_cluster && ctx->cluster_mode) {
     const size_t bytes = (size_t)n * CL_STRIDE * sizeof(double);
     if (bytes <= kClusterScratchMax) {
-      // no memory for the records (16.6 KB per point): not an error, the call stays on the plain path
+      // no memory for the records (16.6 KB per point): not an error, the call stays on the plain path and
+      // says so (rydcz_call_flags: RYDCZ_FLAG_NO_CLUSTER_SCRATCH)
       if (grow(ctx, (void**)&ctx->cl_scratch, &ctx->cl_cap, bytes) ||
           grow(ctx, (void**)&ctx->task, &ctx->task_cap, (size_t)n * CL_MAX_SLOTS * 4 * sizeof(uint32_t)) ||
           grow(ctx, (void**)&ctx->rp_E, &ctx->rp_cap, (size_t)n * RepeatLayout<3>::STRIDE * sizeof(double))) {
         cudaGetLastError();
         ctx->err.clear();
+        ctx->call_flags |= RYDCZ_FLAG_NO_CLUSTER_SCRATCH;
       }
+    } else {
+      ctx->call_flags |= RYDCZ_FLAG_NO_CLUSTER_SCRATCH;
     }
   }
   return 0;
@@ -889,7 +935,8 @@ void rydcz_destroy(rydcz_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->keys); cudaFree(ctx->keys_sorted); cudaFree(ctx->idx); cudaFree(ctx->idx_sorted);
   cudaFree(ctx->kind); cudaFree(ctx->cl_scratch); cudaFree(ctx->cl_counters); cudaFree(ctx->task);
-  cudaFree(ctx->rp_E); cudaFree(ctx->rp_count); cudaFree(ctx->shot_rows);
+  cudaFree(ctx->rp_E); cudaFree(ctx->rp_count); cudaFree(ctx->shot_rows); cudaFree(ctx->sel_out); cudaFree(ctx->sel_sc);
+  if (ctx->busy) cudaEventDestroy(ctx->busy);
   if (ctx->evc0) cudaEventDestroy(ctx->evc0);
   if (ctx->evc1) cudaEventDestroy(ctx->evc1);
   cudaFree(ctx->cub_tmp);
@@ -960,6 +1007,42 @@ int rydcz_last_coef_ms(rydcz_ctx* ctx, float* ms) {
   return 0;
 }
 
+int rydcz_call_flags(rydcz_ctx* ctx, int* flags, int64_t* unsupported_points) {
+  if (!ctx) return 2;
+  unsigned long long h = 0;
+  if (ctx->cl_counters) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(&h, ctx->cl_counters + 4, sizeof(h), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(ctx->cl_counters + 4, 0, sizeof(h)));
+  }
+  if (flags) *flags = ctx->call_flags | (h ? RYDCZ_FLAG_UNSUPPORTED_POINTS : 0);
+  if (unsupported_points) *unsupported_points = (int64_t)h;
+  return 0;
+}
+
+int rydcz_point_status(rydcz_ctx* ctx, int64_t n, int32_t* h_status) {
+  if (!ctx || !h_status) return 2;
+  if (n < 0 || n > ctx->status_n) return fail(ctx, "rydcz_point_status: n exceeds the items of the last call");
+  if (n == 0) return 0;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  uint8_t* tmp = (uint8_t*)malloc((size_t)n);
+  if (!tmp) return fail(ctx, "out of host memory");
+  cudaError_t e = cudaMemcpy(tmp, ctx->kind, (size_t)n, cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { free(tmp); ctx->err = std::string("cudaMemcpy: ") + cudaGetErrorString(e); return 1; }
+  for (int64_t i = 0; i < n; ++i) {
+    const int k = tmp[i] & KIND_MASK;
+    int st = k == KIND_GENERAL ? RYDCZ_STATUS_PLAIN : k == KIND_SYM ? RYDCZ_STATUS_PLAIN_FOLDED
+           : k == KIND_CLUSTER_GENERAL ? RYDCZ_STATUS_CLUSTER_GENERAL : k == KIND_CLUSTER ? RYDCZ_STATUS_CLUSTER
+           : k == KIND_REPEAT ? RYDCZ_STATUS_REPEAT : RYDCZ_STATUS_UNSUPPORTED;
+    if (tmp[i] & KIND_RETRY) st |= RYDCZ_STATUS_HANDED_BACK;
+    h_status[i] = st;
+  }
+  free(tmp);
+  return 0;
+}
+
 static int check_args(rydcz_ctx* ctx, int dim, int64_t n, const void* a, const void* b, int max_seg,
                       const void* out, bool allow5 = false) {
   if (!ctx) return 2;
@@ -985,9 +1068,9 @@ static int evaluate_impl(rydcz_ctx* ctx, const SortScratch& sc, int dim, int noi
     const unsigned grid = (unsigned)((n_points + kBlock - 1) / kBlock);
     if (mark & 1) CK(cudaEventRecord(ctx->ev0, st));
     if (noisy) evaluate5_kernel<true><<<grid, kBlock, kSmem5, st>>>(n_points, order, d_points, d_segs, d_n_seg,
-                                                                   max_seg, d_out, d_states);
+                                                                   max_seg, d_out, d_states, sc.kind, ctx->cl_counters);
     else evaluate5_kernel<false><<<grid, kBlock, kSmem5, st>>>(n_points, order, d_points, d_segs, d_n_seg, max_seg,
-                                                              d_out, d_states);
+                                                              d_out, d_states, sc.kind, ctx->cl_counters);
     CK(cudaGetLastError());
     if (mark & 2) { CK(cudaEventRecord(ctx->ev1, st)); ctx->timed = true; }
     ctx->launches++;
@@ -1011,9 +1094,13 @@ int rydcz_evaluate_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, 
   if (n_points == 0) return 0;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  ctx->call_flags = 0;
+  if (enter_call(ctx, st)) return 1;
   if (order_reserve(ctx, n_points, dim != 5)) return 1;
-  return evaluate_impl(ctx, context_scratch(ctx, n_points), dim, noisy, n_points, d_points, d_segs, d_n_seg, max_seg,
-                       d_out, d_states, st, 3);
+  if (int rc = evaluate_impl(ctx, context_scratch(ctx, n_points), dim, noisy, n_points, d_points, d_segs, d_n_seg,
+                             max_seg, d_out, d_states, st, 3)) return rc;
+  ctx->status_n = n_points;
+  return leave_call(ctx, st);
 }
 
 // d_shots [n_points][n_shots][16] must be given (scratch or caller's)
@@ -1075,14 +1162,18 @@ int rydcz_evaluate_shots_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_po
     shots = (double*)ctx->stage[5];
   }
   const int64_t n_items = n_points * n_shots;
+  ctx->call_flags = 0;
+  if (enter_call(ctx, st)) return 1;
   if (order_reserve(ctx, n_items, dim == 3)) return 1;
   double* rows = nullptr;
   if (dim == 3 && ctx->cluster_mode) {
     if (grow(ctx, (void**)&ctx->shot_rows, &ctx->shot_rows_cap, (size_t)n_items * PT_STRIDE * sizeof(double))) return 1;
     rows = ctx->shot_rows;
   }
-  return shots_impl(ctx, context_scratch(ctx, n_items), dim, noisy, n_points, n_shots, seed, 0, d_points, d_segs, d_n_seg,
-                    max_seg, d_out_mean, shots, rows, st, 3);
+  if (int rc = shots_impl(ctx, context_scratch(ctx, n_items), dim, noisy, n_points, n_shots, seed, 0, d_points, d_segs,
+                          d_n_seg, max_seg, d_out_mean, shots, rows, st, 3)) return rc;
+  ctx->status_n = (rows && ctx->cl_scratch) ? n_items : n_points;   // planned per shot, or per point
+  return leave_call(ctx, st);
 }
 
 static int stage_in(rydcz_ctx* ctx, int slot, const void* h, size_t bytes) {
@@ -1096,6 +1187,12 @@ int rydcz_evaluate_host(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, co
                         double* h_states) {
   if (int rc = check_args(ctx, dim, n_points, h_points, h_segs, max_seg, h_out, true)) return rc;
   if (n_points == 0) return 0;
+  if (dim == 5) {
+    // only the exchange-folded 5-level systems are built: refuse unequal atoms here instead of returning NaN rows
+    for (int64_t i = 0; i < n_points; ++i)
+      if (h_points[i * PT5_STRIDE + PT_OFF_A] != h_points[i * PT5_STRIDE + PT_OFF_B])
+        return fail(ctx, "dim 5: atoms with different detunings (OFF_A != OFF_B) are not supported");
+  }
   CK(cudaSetDevice(ctx->device));
   const size_t n = (size_t)n_points;
   const size_t sb = (size_t)rydcz_state_stride(dim) * sizeof(double);
@@ -1183,7 +1280,9 @@ int rydcz_prologue_device(rydcz_ctx* ctx, const double* h_model, int64_t n_point
   if (!d_app || !d_points || !d_segs || !d_n_seg) return fail(ctx, "null buffer");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  return prologue_impl(ctx, h_model, n_points, d_app, n_points, d_points, d_segs, d_n_seg, d_scalars, st);
+  if (enter_call(ctx, st)) return 1;      // d_points / d_segs may be the context's own plan buffers
+  if (int rc = prologue_impl(ctx, h_model, n_points, d_app, n_points, d_points, d_segs, d_n_seg, d_scalars, st)) return rc;
+  return leave_call(ctx, st);
 }
 
 int rydcz_simulate_device(rydcz_ctx* ctx, const double* h_model, int64_t n_points, const double* d_app,
@@ -1248,9 +1347,10 @@ int rydcz_set_chunk(rydcz_ctx* ctx, int64_t points_per_chunk) {
 // cross PCIe; the batch is cut into chunks and chunk c (pack on the host -> H2D -> prologue ->
 // work sort -> evaluate -> D2H) runs on lane c % kLanes, so the copies and the host-side packing
 // of one chunk overlap the kernels of its neighbours.
-int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_points,
-                             const double* const* h_cols, const int64_t* col_stride, const double* h_const,
-                             int n_shots, uint64_t seed, double* h_out, double* h_scalars, double* h_states) {
+static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_points,
+                              const double* const* h_cols, const int64_t* col_stride, const double* h_const,
+                              int n_shots, uint64_t seed, double* h_out, double* h_scalars, double* h_states,
+                              const ColumnSelect* sel_out, const ColumnSelect* sel_sc) {
   if (int rc = check_model(ctx, h_model)) return rc;
   if (n_points < 0 || n_points > 0x7fffffffLL) return fail(ctx, "n_points out of range");
   if (n_points == 0) return 0;
@@ -1295,9 +1395,12 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
   if (grow(ctx, &ctx->plan[0], &ctx->plan_cap[0], n * pstride * sizeof(double))) return 1;
   if (grow(ctx, &ctx->plan[1], &ctx->plan_cap[1], n * S * SG_STRIDE * sizeof(double))) return 1;
   if (grow(ctx, &ctx->plan[2], &ctx->plan_cap[2], n * sizeof(int32_t))) return 1;
+  ctx->call_flags = 0;
   if (order_reserve(ctx, n_points * per_item, dim != 5 && (n_shots == 0 || dim == 3))) return 1;
   if (n_shots > 0 && dim == 3 && ctx->cluster_mode &&
       grow(ctx, (void**)&ctx->shot_rows, &ctx->shot_rows_cap, n * per_item * PT_STRIDE * sizeof(double))) return 1;
+  if (sel_out && grow(ctx, &ctx->sel_out, &ctx->sel_out_cap, n * (sel_out->n ? sel_out->n : 1) * sizeof(double))) return 1;
+  if (sel_sc && h_scalars && grow(ctx, &ctx->sel_sc, &ctx->sel_sc_cap, n * (sel_sc->n ? sel_sc->n : 1) * sizeof(double))) return 1;
   double* d_app = (double*)ctx->stage[0];
   double* d_out = (double*)ctx->stage[3];
   double* d_sc = h_scalars ? (double*)ctx->stage[1] : nullptr;
@@ -1330,6 +1433,7 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
     const int64_t i0 = c * chunk;
     const int64_t nc = (i0 + chunk <= n_points) ? chunk : n_points - i0;
     if (c >= rydcz_ctx::kLanes) CK(cudaEventSynchronize(L.ring_free));   // the lane's ring is free again
+    else if (enter_call(ctx, st)) return 1;                               // earlier asynchronous calls use the same scratch
     // gather the varying columns into the page-locked ring (strided columns of the caller's row-major
     // arrays), one H2D copy, scatter on the device.  RYDCZ_PACK_THREADS > 1 gathers with that many OpenMP
     // threads: 3 % faster end to end on a 1-GPU box, but with one process per GPU on an 8-GPU box the
@@ -1367,15 +1471,74 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
                          d_ns + i0, S, d_out + i0 * OUT_STRIDE, d_st ? d_st + i0 * (sb / sizeof(double)) : nullptr,
                          st, mark);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h_out + i0 * OUT_STRIDE, d_out + i0 * OUT_STRIDE, nc * OUT_STRIDE * sizeof(double),
-                       cudaMemcpyDeviceToHost, st));
-    if (h_scalars)
+    if (sel_out) {
+      // only the requested columns go back, column-major: h_out[j][i] = out[i][slot j]
+      if (sel_out->n > 0) {
+        double* d_cm = (double*)ctx->sel_out;
+        gather_columns_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(*sel_out, nc, d_out + i0 * OUT_STRIDE, OUT_STRIDE,
+                                                                            d_cm + i0, n_points);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        CK(cudaMemcpy2DAsync(h_out + i0, n * sizeof(double), d_cm + i0, n * sizeof(double), nc * sizeof(double),
+                             (size_t)sel_out->n, cudaMemcpyDeviceToHost, st));
+      }
+    } else {
+      CK(cudaMemcpyAsync(h_out + i0 * OUT_STRIDE, d_out + i0 * OUT_STRIDE, nc * OUT_STRIDE * sizeof(double),
+                         cudaMemcpyDeviceToHost, st));
+    }
+    if (h_scalars && sel_sc) {
+      if (sel_sc->n > 0) {
+        double* d_cm = (double*)ctx->sel_sc;
+        gather_columns_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(*sel_sc, nc, c_sc, SC_STRIDE, d_cm + i0, n_points);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        CK(cudaMemcpy2DAsync(h_scalars + i0, n * sizeof(double), d_cm + i0, n * sizeof(double), nc * sizeof(double),
+                             (size_t)sel_sc->n, cudaMemcpyDeviceToHost, st));
+      }
+    } else if (h_scalars) {
       CK(cudaMemcpyAsync(h_scalars + i0 * SC_STRIDE, c_sc, nc * SC_STRIDE * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
     if (h_states)
       CK(cudaMemcpyAsync((char*)h_states + i0 * sb, (char*)d_st + i0 * sb, nc * sb, cudaMemcpyDeviceToHost, st));
   }
   for (int l = 0; l < n_lanes; ++l) CK(cudaStreamSynchronize(ctx->lane[l].stream));
+  ctx->busy_set = false;                 // everything this context enqueued has completed
+  ctx->status_n = n_points * per_item;
+  if (n_shots > 0 && !(dim == 3 && ctx->cluster_mode && ctx->shot_rows && ctx->cl_scratch)) ctx->status_n = n_points;
   return 0;
+}
+
+int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_points,
+                             const double* const* h_cols, const int64_t* col_stride, const double* h_const,
+                             int n_shots, uint64_t seed, double* h_out, double* h_scalars, double* h_states) {
+  return simulate_cols_impl(ctx, h_model, n_points, h_cols, col_stride, h_const, n_shots, seed, h_out, h_scalars,
+                            h_states, nullptr, nullptr);
+}
+
+static int make_select(rydcz_ctx* ctx, const int32_t* slots, int n, int limit, ColumnSelect* sel) {
+  if (n < 0 || n > limit || (n > 0 && !slots)) return fail(ctx, "column selection: bad count");
+  sel->n = n;
+  for (int j = 0; j < OUT_STRIDE; ++j) sel->slot[j] = 0;
+  for (int j = 0; j < n; ++j) {
+    if (slots[j] < 0 || slots[j] >= limit) return fail(ctx, "column selection: slot out of range");
+    sel->slot[j] = slots[j];
+  }
+  return 0;
+}
+
+int rydcz_simulate_host_select(rydcz_ctx* ctx, const double* h_model, int64_t n_points,
+                               const double* const* h_cols, const int64_t* col_stride, const double* h_const,
+                               int n_shots, uint64_t seed, const int32_t* out_slots, int n_out, double* h_out_cm,
+                               const int32_t* scalar_slots, int n_scalars, double* h_scalars_cm) {
+  if (!ctx) return 2;
+  ColumnSelect so, ss;
+  if (int rc = make_select(ctx, out_slots, n_out, OUT_STRIDE, &so)) return rc;
+  if (int rc = make_select(ctx, scalar_slots, n_scalars, SC_STRIDE, &ss)) return rc;
+  if (n_points > 0 && ((n_out > 0 && !h_out_cm) || (n_scalars > 0 && !h_scalars_cm))) return fail(ctx, "null buffer");
+  // (h_out must be non-null for the shared argument check; with n_out = 0 nothing is written to it)
+  double dummy = 0.0;
+  return simulate_cols_impl(ctx, h_model, n_points, h_cols, col_stride, h_const, n_shots, seed,
+                            h_out_cm ? h_out_cm : &dummy, n_scalars > 0 ? h_scalars_cm : nullptr, nullptr, &so, &ss);
 }
 
 int rydcz_last_kernel_ms(rydcz_ctx* ctx, float* ms) {

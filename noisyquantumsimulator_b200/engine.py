@@ -41,6 +41,7 @@ class Evaluator:
                              f"{msg.decode() if msg else rc} -- a CUDA GPU is required")
         self.ctx = ctx
         self._pinned = {}
+        self._retired = []      # outgrown page-locked buffers: callers may still hold views of them
 
     def pinned(self, key: str, shape, dtype=np.float64) -> np.ndarray:
         """A page-locked NumPy array owned by this evaluator, reused across calls (grown on demand):
@@ -50,7 +51,9 @@ class Evaluator:
         buf = self._pinned.get(key)
         if buf is None or buf[1] < need:
             if buf is not None:
-                self.lib.rydcz_pinned_free(buf[0])
+                # NumPy views of the old buffer (simulate_host*, copy=False results) may still be alive:
+                # keep it until close() instead of freeing memory somebody can still read
+                self._retired.append(buf[0])
             p = C.c_void_p()
             cap = max(need, 8)
             if self.lib.rydcz_pinned_alloc(cap, C.byref(p)) != 0:
@@ -63,7 +66,9 @@ class Evaluator:
     def close(self):
         for p, _ in getattr(self, "_pinned", {}).values():
             self.lib.rydcz_pinned_free(p)
-        self._pinned = {}
+        for p in getattr(self, "_retired", []):
+            self.lib.rydcz_pinned_free(p)
+        self._pinned, self._retired = {}, []
         if getattr(self, "ctx", None):
             self.lib.rydcz_destroy(self.ctx)
             self.ctx = None
@@ -79,6 +84,18 @@ class Evaluator:
             msg = self.lib.rydcz_last_error(self.ctx)
             raise RydczError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
 
+    def _check_batch(self, dim, points, segs, n_seg):
+        """Shapes of one batch as the C ABI reads them (a wrong n_seg means out-of-bounds device reads)."""
+        B = points.shape[0]
+        assert points.ndim == 2 and points.shape[1] == self.lib.rydcz_point_stride_dim(dim), points.shape
+        assert segs.ndim == 3 and segs.shape[0] == B and segs.shape[2] == _lib.SEG_STRIDE, (points.shape, segs.shape)
+        if n_seg is not None:
+            assert tuple(n_seg.shape) == (B,), n_seg.shape
+            if B:
+                lo, hi = int(n_seg.min()), int(n_seg.max())
+                assert 0 <= lo and hi <= segs.shape[1], (lo, hi, segs.shape)
+        return B
+
     # ------------------------------------------------------------------ host buffers
     def evaluate_host(self, dim: int, noisy: bool, points, segs, n_seg=None,
                       want_states: bool = False) -> Tuple[np.ndarray, Optional[np.ndarray]]:
@@ -86,13 +103,10 @@ class Evaluator:
         states [B,stride] or None).  H2D, kernels and D2H all happen inside the C call."""
         points, p_ptr = _host(points, np.float64)
         segs, s_ptr = _host(segs, np.float64)
-        B = points.shape[0]
-        assert points.shape == (B, self.lib.rydcz_point_stride_dim(dim)) and segs.ndim == 3 and segs.shape[0] == B \
-            and segs.shape[2] == _lib.SEG_STRIDE, (points.shape, segs.shape)
         n_ptr = None
         if n_seg is not None:
             n_seg, n_ptr = _host(n_seg, np.int32)
-            assert n_seg.shape == (B,) and (B == 0 or int(n_seg.max()) <= segs.shape[1])
+        B = self._check_batch(dim, points, segs, n_seg)
         out = np.empty((B, _lib.OUT_STRIDE))
         states = np.empty((B, self.lib.rydcz_state_stride(dim))) if want_states else None
         self._check(self.lib.rydcz_evaluate_host(
@@ -104,10 +118,11 @@ class Evaluator:
                             n_seg=None, want_shots: bool = False):
         points, p_ptr = _host(points, np.float64)
         segs, s_ptr = _host(segs, np.float64)
-        B = points.shape[0]
         n_ptr = None
         if n_seg is not None:
             n_seg, n_ptr = _host(n_seg, np.int32)
+        B = self._check_batch(dim, points, segs, n_seg)
+        assert n_shots >= 1
         mean = np.empty((B, _lib.OUT_STRIDE))
         shots = np.empty((B, n_shots, _lib.OUT_STRIDE)) if want_shots else None
         self._check(self.lib.rydcz_evaluate_shots_host(
@@ -123,9 +138,11 @@ class Evaluator:
         returns (out, states) tensors without synchronising."""
         import torch
 
-        assert points.is_cuda and segs.is_cuda and points.dtype == torch.float64
+        assert points.is_cuda and segs.is_cuda and points.dtype == torch.float64 and segs.dtype == torch.float64
         points, segs = points.contiguous(), segs.contiguous()
-        B = points.shape[0]
+        if n_seg is not None:
+            assert n_seg.dtype == torch.int32 and n_seg.is_cuda
+        B = self._check_batch(dim, points, segs, None if n_seg is None else n_seg.cpu().numpy())
         if out is None:
             out = torch.empty((B, _lib.OUT_STRIDE), dtype=torch.float64, device=points.device)
         if want_states and states is None:
@@ -145,8 +162,13 @@ class Evaluator:
                               n_seg=None, mean=None, shots=None, want_shots=False, stream=None):
         import torch
 
+        assert points.is_cuda and segs.is_cuda and points.dtype == torch.float64 and segs.dtype == torch.float64
         points, segs = points.contiguous(), segs.contiguous()
-        B = points.shape[0]
+        if n_seg is not None:
+            assert n_seg.dtype == torch.int32 and n_seg.is_cuda
+            n_seg = n_seg.contiguous()
+        B = self._check_batch(dim, points, segs, None if n_seg is None else n_seg.cpu().numpy())
+        assert n_shots >= 1
         if mean is None:
             mean = torch.empty((B, _lib.OUT_STRIDE), dtype=torch.float64, device=points.device)
         if want_shots and shots is None:
@@ -188,20 +210,7 @@ class Evaluator:
         page-locked buffers owned by the evaluator (valid until the next call)."""
         model, m_ptr = _host(model, np.float64)
         assert model.shape == (_lib.MODEL_STRIDE,) and len(cols) == _lib.APP_STRIDE
-        ptrs = (C.c_void_p * _lib.APP_STRIDE)()
-        strides = (C.c_int64 * _lib.APP_STRIDE)()
-        consts = (C.c_double * _lib.APP_STRIDE)()
-        keep = []
-        for k, v in enumerate(cols):
-            if isinstance(v, np.ndarray):
-                if v.dtype != np.float64 or v.ndim != 1 or v.strides[0] % 8 or v.strides[0] <= 0 \
-                        or not v.flags.aligned:
-                    v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1)
-                assert v.shape == (B,)
-                keep.append(v)
-                ptrs[k], strides[k], consts[k] = v.ctypes.data, v.strides[0] // 8, np.nan
-            else:
-                ptrs[k], strides[k], consts[k] = None, 1, float(v)
+        ptrs, strides, consts, keep = self._column_args(cols, B)
         out = self.pinned("sim_out", (B, _lib.OUT_STRIDE))
         sc = self.pinned("sim_sc", (B, _lib.SCALAR_STRIDE)) if want_scalars else None
         st = self.pinned("sim_st", (B, self.lib.rydcz_state_stride(int(model[0])))) if want_states else None
@@ -211,6 +220,43 @@ class Evaluator:
             "rydcz_simulate_host_cols")
         del keep
         return out, sc, st
+
+    def _column_args(self, cols, B):
+        ptrs, strides, consts, keep = self._column_args(cols, B)
+        return ptrs, strides, consts, keep
+
+    def simulate_host_select(self, model, cols, B: int, out_slots, scalar_slots=(), n_shots: int = 0,
+                             seed: int = 1234):
+        """``simulate_host_cols`` returning only the requested columns (rydcz_simulate_host_select):
+        ``out_slots`` index the 16 result slots (``engine.OUT``), ``scalar_slots`` the 8 prologue scalars
+        (``_lib.SCALARS``).  Returns two page-locked arrays, column-major: ``out[j]`` is the contiguous
+        column of ``out_slots[j]`` over the B points (valid until the next call)."""
+        model, m_ptr = _host(model, np.float64)
+        assert model.shape == (_lib.MODEL_STRIDE,) and len(cols) == _lib.APP_STRIDE
+        ptrs, strides, consts, keep = self._column_args(cols, B)
+        o_idx = np.ascontiguousarray(out_slots, dtype=np.int32).reshape(-1)
+        s_idx = np.ascontiguousarray(scalar_slots, dtype=np.int32).reshape(-1)
+        out = self.pinned("sel_out", (max(len(o_idx), 1), B))
+        sc = self.pinned("sel_sc", (max(len(s_idx), 1), B))
+        self._check(self.lib.rydcz_simulate_host_select(
+            self.ctx, m_ptr, B, ptrs, strides, consts, int(n_shots), int(seed),
+            o_idx.ctypes.data if len(o_idx) else None, len(o_idx), out.ctypes.data,
+            s_idx.ctypes.data if len(s_idx) else None, len(s_idx), sc.ctypes.data),
+            "rydcz_simulate_host_select")
+        del keep
+        return out[:len(o_idx)], sc[:len(s_idx)]
+
+    def point_status(self, n: int) -> np.ndarray:
+        """enum rydcz_status of the first n items of the last evaluation call (int32 array)."""
+        st = np.empty(int(n), dtype=np.int32)
+        self._check(self.lib.rydcz_point_status(self.ctx, int(n), st.ctypes.data), "rydcz_point_status")
+        return st
+
+    def call_flags(self):
+        """(flags, unsupported_points) of the last evaluation call: RYDCZ_FLAG_* bits (_lib.FLAG_*)."""
+        f, u = C.c_int(), C.c_int64()
+        self._check(self.lib.rydcz_call_flags(self.ctx, C.byref(f), C.byref(u)), "rydcz_call_flags")
+        return int(f.value), int(u.value)
 
     def set_chunk(self, points_per_chunk: int):
         self._check(self.lib.rydcz_set_chunk(self.ctx, int(points_per_chunk)), "rydcz_set_chunk")

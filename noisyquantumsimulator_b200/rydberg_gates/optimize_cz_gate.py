@@ -19,66 +19,92 @@ import json
 import os
 import time
 from dataclasses import dataclass, field
-from typing import Any, Dict, List, Optional, Tuple
+from typing import Any, Dict, List, NamedTuple, Optional, Tuple
 
 import numpy as np
 
 from .batched_objective import ApparatusConstraints, bounds_and_x0, protocol_kwargs
 from .configurations import (JPSimulationInputs, LaserParameters, LPSimulationInputs, NoiseSourceConfig,
                              SmoothJPSimulationInputs, TwoPhotonExcitationConfig)
-from .simulation import SimulationResult, simulate_CZ_gate, simulate_CZ_gate_batch
+from .simulation import METRIC_OUTPUTS, SimulationResult, simulate_CZ_gate, simulate_CZ_gate_batch
 
 METRIC_KEYS = ("controlled_phase_deg", "phase_error_deg", "cz_phase_fidelity", "f00", "f01", "f10", "f11",
                "avg_fidelity", "gate_time_us", "V_over_Omega", "Omega_MHz")
 
 
 # ---------------------------------------------------------------------------- cache
+class _CacheEntry(NamedTuple):
+    cost: float
+    metrics: Dict[str, Any]
+
+
+def _format_key(prefix: str, protocol: str, values, digits: int) -> str:
+    """'<apparatus>|<protocol>|(<v0>, <v1>, ...)' with every value rounded to `digits` decimals: the text of
+    the reference's keys (RG/optimize_cz_gate.py:306-312), so JSON files written by either side stay readable
+    by the other.  The parameter list is printed the way Python prints a tuple of floats."""
+    body = ", ".join(repr(round(float(v), digits)) for v in values)
+    if len(values) == 1:
+        body += ","
+    return f"{prefix}|{protocol}|({body})"
+
+
 class SimulationCache:
-    """(cost, metrics) memo keyed by rounded parameters (RG/optimize_cz_gate.py:284-352): same key
-    format, same JSON file layout, same hit/miss counters."""
+    """Memo of evaluated candidates for the optimiser's objective.  Public surface of the reference's class
+    (RG/optimize_cz_gate.py:284-352): ``make_key``, ``in`` / ``[]`` access returning ``(cost, metrics)``,
+    ``hits`` / ``misses`` / ``hit_rate``, ``precision``, ``save`` / ``load`` on the same JSON layout
+    ``{"precision": p, "entries": {key: {"cost": c, "metrics": {...}}}}``.  A caller's own cache object with
+    this surface can be passed to ``optimize_cz_gate(cache=...)`` instead."""
 
     def __init__(self, precision: int = 4):
-        self._store: Dict[str, Tuple[float, Dict]] = {}
-        self.precision = precision
-        self.hits = 0
-        self.misses = 0
+        self.precision = int(precision)
+        self.hits = 0          # successful lookups (counted by __getitem__, as the reference does)
+        self.misses = 0        # bumped by the objective when it has to simulate
+        self._entries: Dict[str, _CacheEntry] = {}
 
+    # -- keys
     def make_key(self, protocol: str, params: list, apparatus_hash: str = "") -> str:
-        rounded = tuple(round(float(p), self.precision) for p in params)
-        return f"{apparatus_hash}|{protocol}|{rounded}"
+        return _format_key(apparatus_hash, protocol, list(params), self.precision)
+
+    # -- mapping protocol
+    def __len__(self) -> int:
+        return len(self._entries)
 
     def __contains__(self, key: str) -> bool:
-        return key in self._store
+        return key in self._entries
 
     def __getitem__(self, key: str) -> Tuple[float, Dict]:
+        entry = self._entries[key]
         self.hits += 1
-        return self._store[key]
+        return entry.cost, entry.metrics
 
     def __setitem__(self, key: str, value: Tuple[float, Dict]):
-        self._store[key] = value
-
-    def __len__(self) -> int:
-        return len(self._store)
+        cost, metrics = value
+        self._entries[key] = _CacheEntry(cost, metrics)
 
     @property
     def hit_rate(self) -> float:
-        total = self.hits + self.misses
-        return self.hits / total if total > 0 else 0.0
+        lookups = self.hits + self.misses
+        return self.hits / lookups if lookups else 0.0
 
+    # -- persistence
     def save(self, path: str):
-        data = {"precision": self.precision,
-                "entries": {k: {"cost": v[0], "metrics": v[1]} for k, v in self._store.items()}}
-        with open(path, "w") as f:
-            json.dump(data, f, indent=2, default=str)
+        payload = {"precision": self.precision,
+                   "entries": {key: {"cost": e.cost, "metrics": e.metrics} for key, e in self._entries.items()}}
+        tmp = f"{path}.tmp"
+        with open(tmp, "w") as fh:
+            json.dump(payload, fh, indent=2, default=str)
+        os.replace(tmp, path)             # never leave a half-written cache behind
 
     def load(self, path: str):
-        if not os.path.exists(path):
+        """Merge the entries of a saved cache (a missing file is not an error)."""
+        try:
+            with open(path) as fh:
+                payload = json.load(fh)
+        except FileNotFoundError:
             return
-        with open(path) as f:
-            data = json.load(f)
-        self.precision = data.get("precision", self.precision)
-        for k, v in data.get("entries", {}).items():
-            self._store[k] = (v["cost"], v["metrics"])
+        self.precision = int(payload.get("precision", self.precision))
+        for key, rec in payload.get("entries", {}).items():
+            self._entries[key] = _CacheEntry(rec["cost"], rec["metrics"])
 
 
 _global_cache = SimulationCache(precision=4)
@@ -107,15 +133,23 @@ def extract_metrics(result: SimulationResult) -> Dict[str, float]:
             "Omega_MHz": result.Omega / (2 * np.pi * 1e6)}
 
 
+def batch_metric_rows(res) -> np.ndarray:
+    """[B, len(METRIC_KEYS)] array of ``extract_metrics`` values for a ``BatchResult`` (any return mode)."""
+    c = res.column
+    omega, V = c("Omega"), c("V")
+    with np.errstate(divide="ignore", invalid="ignore"):
+        voo = np.where(omega > 0, V / omega, np.inf)
+    cols = {"controlled_phase_deg": np.degrees(c("controlled_phase_rad")),
+            "phase_error_deg": np.degrees(c("phase_error_from_pi_rad")), "cz_phase_fidelity": c("cz_phase_fidelity"),
+            "f00": c("f00"), "f01": c("f01"), "f10": c("f10"), "f11": c("f11"), "avg_fidelity": c("avg_fidelity"),
+            "gate_time_us": c("tau_total") * 1e6, "V_over_Omega": voo, "Omega_MHz": omega / (2 * np.pi * 1e6)}
+    return np.stack([np.asarray(cols[k], dtype=float) for k in METRIC_KEYS], axis=1)
+
+
 def batch_metrics(res) -> List[Dict[str, float]]:
     """``extract_metrics`` for every row of a ``BatchResult``."""
-    cols = {"controlled_phase_deg": np.degrees(res.controlled_phase_rad),
-            "phase_error_deg": np.degrees(res.phase_error_from_pi_rad), "cz_phase_fidelity": res.cz_phase_fidelity,
-            "f00": res.fidelities[:, 0], "f01": res.fidelities[:, 1], "f10": res.fidelities[:, 2],
-            "f11": res.fidelities[:, 3], "avg_fidelity": res.avg_fidelity, "gate_time_us": res.tau_total * 1e6,
-            "V_over_Omega": res.V_over_Omega, "Omega_MHz": res.Omega / (2 * np.pi * 1e6)}
-    n = len(res.avg_fidelity)
-    return [{k: float(cols[k][i]) for k in METRIC_KEYS} for i in range(n)]
+    rows = batch_metric_rows(res)
+    return [dict(zip(METRIC_KEYS, map(float, r))) for r in rows]
 
 
 # ---------------------------------------------------------------------------- parameter builders
@@ -253,6 +287,12 @@ class PopulationObjective:
         self.eval_count = self.cache_hits = self.generations = 0
         self.best_so_far = 1e9
 
+    @staticmethod
+    def _outputs(kw):
+        """Only the columns ``extract_metrics`` reads cross PCIe when the device prologue serves the call."""
+        shaped = kw.get("pulse_shape", "square") != "square"
+        return None if shaped else METRIC_OUTPUTS
+
     def _key(self, x: np.ndarray) -> str:
         if self.optimize_spacing:
             h = f"{self.apparatus_hash}_sf{float(x[-1]):.6f}"
@@ -269,15 +309,28 @@ class PopulationObjective:
             per = (n + self.world - 1) // self.world
             lo, hi = min(n, self.rank * per), min(n, (self.rank + 1) * per)
         rows = np.full((n, len(METRIC_KEYS)), np.nan)
+        failure = None
         if hi > lo:
-            Xs = X[:, lo:hi]
-            kw = dict(self.base)
-            n_proto = Xs.shape[0] - (1 if self.optimize_spacing else 0)
-            if self.optimize_spacing:
-                kw["spacing_factor"] = Xs[-1]
-            kw.update(protocol_kwargs(self.proto, Xs[:n_proto], self.n_segments))
-            res = simulate_CZ_gate_batch(self.proto, B=hi - lo, device=self.device, warn=False, **kw)
-            rows[lo:hi] = [[m[k] for k in METRIC_KEYS] for m in batch_metrics(res)]
+            try:
+                Xs = X[:, lo:hi]
+                kw = dict(self.base)
+                n_proto = Xs.shape[0] - (1 if self.optimize_spacing else 0)
+                if self.optimize_spacing:
+                    kw["spacing_factor"] = Xs[-1]
+                kw.update(protocol_kwargs(self.proto, Xs[:n_proto], self.n_segments))
+                res = simulate_CZ_gate_batch(self.proto, B=hi - lo, device=self.device, warn=False,
+                                             outputs=self._outputs(kw), **kw)
+                rows[lo:hi] = batch_metric_rows(res)
+            except Exception as e:
+                # With several ranks a failure must not keep this rank out of the collective below (the
+                # others would wait in it forever, and the ranks' caches would diverge): the shard
+                # contributes NaN rows, which every rank maps to the reference's failure cost 1e6.
+                if self.world == 1:
+                    raise
+                failure = e
+                rows[lo:hi] = np.nan
+                if self.verbose:
+                    print(f"    rank {self.rank}: shard evaluation failed ({e}); contributing NaN rows")
         if self.world > 1:
             import torch
             import torch.distributed as dist

@@ -489,26 +489,53 @@ def _pulse_info(proto, plan, sc, trap_laser_on):
 
 
 # ---------------------------------------------------------------------------- batch API
+# result columns a batch call can return by name (``outputs=``): the 16 kernel slots (include/rydcz.h, enum
+# rydcz_out_slot) and the 8 scalars of the device prologue
+OUTPUT_SLOTS = dict(avg_fidelity=0, f00=1, f01=2, f10=3, f11=4, f11_population=5, cz_phase_fidelity=6,
+                    controlled_phase_rad=7, phase_error_from_pi_rad=8, phi01=9, phi10=10, phi11=11,
+                    loss_probability=12, rydberg_residual=13, steps=14, flops=15)
+SCALAR_SLOTS = dict(Omega=0, V=1, tau_total=2, tau_single=3, Delta=4, xi_re=5, xi_im=6, omega_tau=7)
+# what the reference's optimiser reads from one evaluation (extract_metrics, RG/optimize_cz_gate.py:434-451)
+METRIC_OUTPUTS = ("avg_fidelity", "f00", "f01", "f10", "f11", "cz_phase_fidelity", "controlled_phase_rad",
+                  "phase_error_from_pi_rad", "tau_total", "Omega", "V")
+
+
 @dataclass
 class BatchResult:
-    """Arrays of length B (one entry per parameter point)."""
+    """Arrays of length B (one entry per parameter point).  With ``outputs=...`` only the requested columns
+    were copied back from the GPU: they are in ``columns`` (and in the attribute of the same name); the other
+    attributes are None."""
 
-    avg_fidelity: np.ndarray
-    fidelities: np.ndarray            # [B, 4] in the order 00, 01, 10, 11 (F11 includes the phase penalty)
-    f11_population: np.ndarray
-    cz_phase_fidelity: np.ndarray
-    controlled_phase_rad: np.ndarray
-    phase_error_from_pi_rad: np.ndarray
-    loss_probability: np.ndarray
-    rydberg_residual: np.ndarray
-    tau_total: np.ndarray
-    Omega: np.ndarray
-    V: np.ndarray
-    raw: np.ndarray                   # [B, 16] kernel output rows (include/rydcz.h)
+    avg_fidelity: Optional[np.ndarray] = None
+    fidelities: Optional[np.ndarray] = None   # [B, 4] in the order 00, 01, 10, 11 (F11 includes the phase penalty)
+    f11_population: Optional[np.ndarray] = None
+    cz_phase_fidelity: Optional[np.ndarray] = None
+    controlled_phase_rad: Optional[np.ndarray] = None
+    phase_error_from_pi_rad: Optional[np.ndarray] = None
+    loss_probability: Optional[np.ndarray] = None
+    rydberg_residual: Optional[np.ndarray] = None
+    tau_total: Optional[np.ndarray] = None
+    Omega: Optional[np.ndarray] = None
+    V: Optional[np.ndarray] = None
+    raw: Optional[np.ndarray] = None          # [B, 16] kernel output rows (include/rydcz.h); None with ``outputs=``
     plan: GatePlan = None
     states: Optional[np.ndarray] = None
     shots: Optional[np.ndarray] = None
     _voo: Optional[np.ndarray] = None
+    columns: Optional[Dict[str, np.ndarray]] = None
+
+    def column(self, name: str) -> np.ndarray:
+        """One result column by its ``outputs`` name, whichever way the batch was returned."""
+        if self.columns is not None:
+            if name not in self.columns:
+                raise KeyError(f"column '{name}' was not requested (outputs={tuple(self.columns)})")
+            return self.columns[name]
+        if name in OUTPUT_SLOTS:
+            return self.raw[:, OUTPUT_SLOTS[name]]
+        v = getattr(self, name, None)
+        if v is None:
+            raise KeyError(f"column '{name}' is not available for this batch")
+        return v
 
     @property
     def V_over_Omega(self) -> np.ndarray:
@@ -530,7 +557,7 @@ class BatchResult:
 
     def cost(self, time_weight: float = 0.01) -> np.ndarray:
         """The optimiser's objective (RG/optimize_cz_gate.py:406-431), elementwise."""
-        F, f11, czf = self.avg_fidelity, self.fidelities[:, 3], self.cz_phase_fidelity
+        F, f11, czf = self.column("avg_fidelity"), self.column("f11"), self.column("cz_phase_fidelity")
         c = (10.0 * ((1 - F) * 100) ** 2 + 5.0 * ((1 - f11) * 100) ** 2 + 2.0 * ((1 - czf) * 100) ** 2
              + time_weight * self.gate_time_us)
         bad = np.isnan(F) | np.isnan(f11) | np.isnan(czf) | (F < 0.5)
@@ -540,7 +567,7 @@ class BatchResult:
 def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, seed: int = 1234,
                            return_states: bool = False, return_shots: bool = False, device: int = 0,
                            plan: GatePlan = None, prologue: str = "auto", copy: bool = True,
-                           **kwargs) -> BatchResult:
+                           outputs=None, **kwargs) -> BatchResult:
     """Evaluate B parameter points in one launch.
 
     ``protocol`` is "lp", "jp" (bang-bang) or "sjp"; every physical keyword of ``build_plan``
@@ -554,6 +581,10 @@ def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, se
     ``GatePlan`` with ``noise_breakdown`` is wanted), "auto" picks the device when it can.
     ``copy=False`` returns views of the evaluator's page-locked result buffers (valid until the
     next call on that device) instead of fresh arrays.
+    ``outputs``: names from ``OUTPUT_SLOTS`` / ``SCALAR_SLOTS`` (e.g. ``METRIC_OUTPUTS``, what the reference's
+    optimiser reads).  Only those columns are gathered on the device and copied back (8 bytes per point and
+    column instead of 192 bytes per point), each as one contiguous array in ``BatchResult.columns``; needs the
+    device prologue.
     """
     from ..engine import get_evaluator
     from . import device_prologue as dpro
@@ -564,6 +595,13 @@ def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, se
         raise ValueError("Monte-Carlo shots are not available for hilbert_space_dim=5")
     if prologue == "auto":
         prologue = "host" if (plan is not None or shaped or return_shots) else "device"
+    if outputs is not None:
+        outputs = tuple(outputs)
+        unknown = [o for o in outputs if o not in OUTPUT_SLOTS and o not in SCALAR_SLOTS]
+        if unknown:
+            raise ValueError(f"unknown output column(s) {unknown}; choose from {tuple(OUTPUT_SLOTS) + tuple(SCALAR_SLOTS)}")
+        if prologue != "device" or return_states:
+            raise ValueError("outputs=... needs the device prologue (square LP, bang-bang, smooth JP) and no states")
     if B is None and plan is None:
         B = max([np.size(v) for v in kwargs.values() if isinstance(v, np.ndarray) and v.ndim >= 1
                  and np.shape(v)[0] > 1] or [1])
@@ -586,6 +624,21 @@ def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, se
         # apparatus slots go to the C ABI as columns (views of the caller's arrays, or one float for a
         # slot that is the same for every point): nothing is packed or broadcast in Python
         cols = dpro.apparatus_columns(protocol, B, **ak)
+        if outputs is not None:
+            o_names = [o for o in outputs if o in OUTPUT_SLOTS]
+            s_names = [o for o in outputs if o in SCALAR_SLOTS]
+            o_cm, s_cm = ev.simulate_host_select(model, cols, B, [OUTPUT_SLOTS[o] for o in o_names],
+                                                 [SCALAR_SLOTS[o] for o in s_names], n_shots, seed)
+            columns = {o: (np.array(o_cm[j]) if copy else o_cm[j]) for j, o in enumerate(o_names)}
+            columns.update({o: (np.array(s_cm[j]) if copy else s_cm[j]) for j, o in enumerate(s_names)})
+            g = columns.get
+            fid = np.stack([g("f00"), g("f01"), g("f10"), g("f11")], axis=1) if all(
+                k in columns for k in ("f00", "f01", "f10", "f11")) else None
+            return BatchResult(avg_fidelity=g("avg_fidelity"), fidelities=fid, f11_population=g("f11_population"),
+                               cz_phase_fidelity=g("cz_phase_fidelity"), controlled_phase_rad=g("controlled_phase_rad"),
+                               phase_error_from_pi_rad=g("phase_error_from_pi_rad"),
+                               loss_probability=g("loss_probability"), rydberg_residual=g("rydberg_residual"),
+                               tau_total=g("tau_total"), Omega=g("Omega"), V=g("V"), columns=columns)
         out, sc, states = ev.simulate_host_cols(model, cols, B, n_shots, seed, want_scalars=True,
                                                 want_states=return_states and n_shots == 0)
         if copy:                                       # detach from the reusable staging buffers

@@ -227,6 +227,16 @@ def _hostsim_simulate_host_cols(self, model, cols, B, n_shots=0, seed=1234, want
 HostsimEvaluator.simulate_host_cols = _hostsim_simulate_host_cols
 
 
+def _hostsim_simulate_host_select(self, model, cols, B, out_slots, scalar_slots=(), n_shots=0, seed=1234):
+    """Column-major selection, as rydcz_simulate_host_select returns it."""
+    out, sc, _ = _hostsim_simulate_host_cols(self, model, cols, B, n_shots, seed, True, False)
+    return (np.ascontiguousarray(out[:, list(out_slots)].T).reshape(len(out_slots), B),
+            np.ascontiguousarray(sc[:, list(scalar_slots)].T).reshape(len(scalar_slots), B))
+
+
+HostsimEvaluator.simulate_host_select = _hostsim_simulate_host_select
+
+
 # ---- 5-level model (hilbert_space_dim = 5) -----------------------------------------------------
 PT5_STRIDE = 20
 ACT2 = [5 * a + b for a in (1, 2, 3) for b in (1, 2, 3)]     # both atoms in {1, e, r}

@@ -227,3 +227,70 @@ def test_population_sharded_over_two_gloo_ranks(host_eval):
         assert p.exitcode == 0
     for r in range(2):
         assert np.array_equal(got[r][0], ref.best_params) and got[r][1] == ref.best_cost
+
+
+def _failing_worker(rank, world, port, q):
+    """Rank 1's evaluator raises inside the batch call: both ranks must still leave the all-gather, with the
+    reference's failure cost 1e6 for that shard and identical costs on every rank."""
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import _cases as C2
+    from noisyquantumsimulator_b200 import engine
+    ev = C2.HostsimEvaluator()
+    if rank == 1:
+        def boom(*a, **k):
+            raise RuntimeError("injected CUDA failure")
+        ev.simulate_host_select = boom
+        ev.simulate_host_cols = boom
+    engine._default[0] = ev
+    ocg = importlib.import_module("noisyquantumsimulator_b200.rydberg_gates.optimize_cz_gate")
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    a = ocg.ApparatusConstraints(spacing_factor=5.373584)
+    f = ocg.PopulationObjective("lp", a, a.make_noiseless(), False, 0.01, 5, ocg.SimulationCache(),
+                                population_shards=(rank, world))
+    X = np.array([[0.36, 0.37, 0.38, 0.39], [4.1, 4.2, 4.3, 4.4]])
+    q.put((rank, f(X)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_failing_rank_does_not_hang_the_collective(host_eval):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_failing_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(got[0], got[1])
+    assert (got[0][:2] < 1e5).all() and (got[0][2:] == 1e6).all()      # rank 0's shard evaluated, rank 1's failed
+
+
+def test_selected_output_columns_equal_the_full_rows(host_eval):
+    """outputs=... (rydcz_simulate_host_select on the GPU) returns the same numbers as the full result rows."""
+    from noisyquantumsimulator_b200 import rydberg_gates as rg
+    from noisyquantumsimulator_b200.rydberg_gates.simulation import METRIC_OUTPUTS
+    ocg = importlib.import_module("noisyquantumsimulator_b200.rydberg_gates.optimize_cz_gate")
+    a = ocg.ApparatusConstraints()
+    kw = a.plan_kwargs(True, a.make_full_noise())
+    rng = np.random.default_rng(5)
+    ot = rng.uniform(5, 30, 6)
+    sw = np.sort(rng.uniform(0.05, 0.95, (6, 4)), axis=1) * ot[:, None]
+    ph = rng.uniform(-np.pi, np.pi, (6, 5))
+    full = rg.simulate_CZ_gate_batch("jp", B=6, warn=False, omega_tau=ot, switching_times=sw, phases=ph, **kw)
+    sel = rg.simulate_CZ_gate_batch("jp", B=6, warn=False, omega_tau=ot, switching_times=sw, phases=ph,
+                                    outputs=METRIC_OUTPUTS + ("loss_probability",), **kw)
+    assert sel.raw is None and set(sel.columns) == set(METRIC_OUTPUTS) | {"loss_probability"}
+    for name in METRIC_OUTPUTS + ("loss_probability",):
+        assert np.array_equal(sel.column(name), full.column(name)), name
+        assert sel.column(name).flags.c_contiguous
+    assert np.array_equal(sel.fidelities, full.fidelities) and np.array_equal(sel.cost(), full.cost())
+    assert np.array_equal(ocg.batch_metric_rows(sel), ocg.batch_metric_rows(full))
+    with pytest.raises(KeyError):
+        sel.column("phi11")
+    with pytest.raises(ValueError, match="unknown output"):
+        rg.simulate_CZ_gate_batch("jp", B=6, warn=False, omega_tau=ot, outputs=("nonsense",), **kw)
