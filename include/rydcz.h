@@ -157,6 +157,10 @@ int rydcz_evaluate_shots_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_po
                                 uint64_t seed, const double* d_points, const double* d_segs,
                                 const int32_t* d_n_seg, int max_seg, double* d_out_mean,
                                 double* d_out_shots, void* stream);
+/* Sharded Monte-Carlo calls: shot s of point i is keyed by (seed; first_point + i, s).  A rank that evaluates the
+ * points [lo, hi) of a larger batch sets first_point = lo and draws exactly the shots the unsharded call draws
+ * (default 0; stays set until changed). */
+int rydcz_set_point_base(rydcz_ctx* ctx, int64_t first_point);
 int rydcz_evaluate_shots_host(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, int n_shots,
                               uint64_t seed, const double* h_points, const double* h_segs,
                               const int32_t* h_n_seg, int max_seg, double* h_out_mean,

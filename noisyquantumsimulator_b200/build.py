@@ -49,6 +49,46 @@ def build(force: bool = False, verbose: bool = True) -> str:
     return LIB
 
 
+# ---- the PyTorch face of the C ABI: torch.ops.rydcz.* (csrc/rydcz_torch.cpp) -------------------------------
+TORCH_LIB = os.path.join(CSRC, "librydcz_torch.so")
+TORCH_DEPS = ["rydcz_torch.cpp", os.path.join("..", "..", "include", "rydcz.h")]
+
+
+def torch_is_stale() -> bool:
+    if not os.path.exists(TORCH_LIB):
+        return True
+    t = os.path.getmtime(TORCH_LIB)
+    return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in TORCH_DEPS)
+
+
+def build_torch_extension(force: bool = False, verbose: bool = True) -> str:
+    """Compile csrc/rydcz_torch.cpp -> csrc/librydcz_torch.so (host C++ only: a dispatcher registration that
+    calls the C ABI of librydcz.so next to it; the kernels are all in librydcz.so)."""
+    if not force and not torch_is_stale():
+        return TORCH_LIB
+    import sysconfig
+
+    import torch
+    from torch.utils import cpp_extension as ce
+
+    inc = ce.include_paths("cuda") + [sysconfig.get_paths()["include"]]
+    tlib = os.path.join(os.path.dirname(torch.__file__), "lib")
+    cmd = (["g++", "-O2", "-std=c++17", "-shared", "-fPIC",
+            f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}"]
+           + [f"-I{p}" for p in inc] + ["rydcz_torch.cpp", "-o", TORCH_LIB, f"-L{tlib}", f"-L{CSRC}",
+                                        "-ltorch", "-ltorch_cpu", "-ltorch_cuda", "-lc10", "-lc10_cuda", "-lrydcz",
+                                        "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tlib}"])
+    if verbose:
+        print("[rydcz build]", " ".join(cmd), flush=True)
+    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building librydcz_torch.so")
+    return TORCH_LIB
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv)
+    build_torch_extension(force="--force" in sys.argv)
     print(LIB)
+    print(TORCH_LIB)

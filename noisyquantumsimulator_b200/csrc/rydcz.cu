@@ -593,6 +593,7 @@ struct rydcz_ctx {
   bool busy_set = false;
   int call_flags = 0;          // RYDCZ_FLAG_* of the last evaluation call
   int64_t status_n = 0;        // items of the last call whose kind[] entries are valid (rydcz_point_status)
+  int64_t point_base = 0;      // index of this call's first point in the caller's whole batch (Philox counter; sharded shots)
   bool smem5_set = false;
   int64_t launches = 0;
   std::string err;
@@ -963,6 +964,13 @@ int rydcz_set_sort(rydcz_ctx* ctx, int enable) {
   return 0;
 }
 
+int rydcz_set_point_base(rydcz_ctx* ctx, int64_t first_point) {
+  if (!ctx) return 2;
+  if (first_point < 0 || first_point > 0xffffffffLL) return fail(ctx, "point base out of range");
+  ctx->point_base = first_point;
+  return 0;
+}
+
 int rydcz_set_cluster(rydcz_ctx* ctx, int mode) {
   if (!ctx) return 2;
   if (mode < 0 || mode > 2) return fail(ctx, "cluster mode must be 0 (off), 1 (auto) or 2 (wherever eligible)");
@@ -1170,7 +1178,7 @@ int rydcz_evaluate_shots_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_po
     if (grow(ctx, (void**)&ctx->shot_rows, &ctx->shot_rows_cap, (size_t)n_items * PT_STRIDE * sizeof(double))) return 1;
     rows = ctx->shot_rows;
   }
-  if (int rc = shots_impl(ctx, context_scratch(ctx, n_items), dim, noisy, n_points, n_shots, seed, 0, d_points, d_segs,
+  if (int rc = shots_impl(ctx, context_scratch(ctx, n_items), dim, noisy, n_points, n_shots, seed, ctx->point_base, d_points, d_segs,
                           d_n_seg, max_seg, d_out_mean, shots, rows, st, 3)) return rc;
   ctx->status_n = (rows && ctx->cl_scratch) ? n_items : n_points;   // planned per shot, or per point
   return leave_call(ctx, st);
@@ -1461,7 +1469,7 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
     const int mark = (c == 0 ? 1 : 0) | (c == n_chunks - 1 ? 2 : 0);
     int rc;
     if (n_shots > 0)
-      rc = shots_impl(ctx, sc, dim, noisy, nc, n_shots, seed, i0, d_pts + i0 * pstride,
+      rc = shots_impl(ctx, sc, dim, noisy, nc, n_shots, seed, ctx->point_base + i0, d_pts + i0 * pstride,
                       d_segs + i0 * (int64_t)S * SG_STRIDE, d_ns + i0, S, d_out + i0 * OUT_STRIDE,
                       d_shots + i0 * n_shots * OUT_STRIDE,
                       (dim == 3 && ctx->cluster_mode && ctx->shot_rows) ? ctx->shot_rows + i0 * n_shots * PT_STRIDE : nullptr,

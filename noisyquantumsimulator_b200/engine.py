@@ -258,6 +258,11 @@ class Evaluator:
         self._check(self.lib.rydcz_call_flags(self.ctx, C.byref(f), C.byref(u)), "rydcz_call_flags")
         return int(f.value), int(u.value)
 
+    def set_point_base(self, first_point: int):
+        """Index of this evaluator's first point in the caller's whole batch (Monte-Carlo shots are keyed by the
+        global point index, so a rank evaluating the slice [lo, hi) draws the shots of the unsharded call)."""
+        self._check(self.lib.rydcz_set_point_base(self.ctx, int(first_point)), "rydcz_set_point_base")
+
     def set_chunk(self, points_per_chunk: int):
         self._check(self.lib.rydcz_set_chunk(self.ctx, int(points_per_chunk)), "rydcz_set_chunk")
 

@@ -20,7 +20,8 @@ from .laser_physics import (laser_E0, single_photon_rabi, two_photon_rabi, rydbe
 from .trap_physics import (tweezer_spacing, trap_depth, trap_frequencies, position_uncertainty,  # noqa: F401
                            anti_trap_potential, atom_loss_probability, compute_trap_dependent_noise,
                            calculate_zeeman_shift, calculate_stark_shift)
-from .noise_models import (build_all_noise_operators, intermediate_state_scattering_rate,  # noqa: F401
+from .noise_models import (build_all_noise_operators, build_decay_operators, build_dephasing_operators,  # noqa: F401
+                           build_loss_operators, build_scatter_operators, intermediate_state_scattering_rate,
                            leakage_rate_to_adjacent_states, NoiseRates, compute_noise_rates)
 from .hamiltonians import (HilbertSpace, build_hilbert_space, HS3, HS4, build_laser_hamiltonian,  # noqa: F401
                            build_detuning_hamiltonian, build_interaction_hamiltonian,

@@ -233,6 +233,71 @@ def build_collapse_matrices(dim: int, channels) -> List[np.ndarray]:
     return ops
 
 
+def _rydberg_levels(hs) -> List[str]:
+    return ["r"] if hs.dim == 3 else ["r+", "r-"]
+
+
+def _on_each_atom(rate: float, single_atom_op, hs) -> List[np.ndarray]:
+    """sqrt(rate) * (op x 1) and sqrt(rate) * (1 x op): atom A first, as the reference orders its lists."""
+    amp = np.sqrt(rate)
+    return [amp * np.kron(single_atom_op, hs.identity), amp * np.kron(hs.identity, single_atom_op)]
+
+
+def build_decay_operators(gamma_optical: float, hs, gamma_bbr: float = 0, branching_1: float = 0.5,
+                          leakage_rate: float = 0) -> List[np.ndarray]:
+    """|r> -> |1> (branching_1) and |r> -> |0> radiative decay, black-body decay to |0>, and for the 4-level model
+    the r+ <-> r- mixing (RG/noise_models.py:1199-1297).  NumPy matrices in the reference's order."""
+    ops: List[np.ndarray] = []
+    levels = _rydberg_levels(hs)
+    if gamma_optical > 0:
+        for r in levels:
+            ops += _on_each_atom(gamma_optical * branching_1, hs.transitions[f"{r}->1"], hs)
+            ops += _on_each_atom(gamma_optical * (1 - branching_1), hs.transitions[f"{r}->0"], hs)
+    if gamma_bbr > 0:
+        for r in levels:
+            ops += _on_each_atom(gamma_bbr, hs.transitions[f"{r}->0"], hs)
+    if hs.dim == 4 and leakage_rate > 0:
+        for key in ("r+->r-", "r-->r+"):
+            ops += _on_each_atom(leakage_rate, hs.transitions[key], hs)
+    return ops
+
+
+def build_dephasing_operators(gamma_phi: float, hs, gamma_phi_minus: float = None) -> List[np.ndarray]:
+    """sqrt(gamma) |r><r| on each atom (r+ with gamma_phi, r- with gamma_phi_minus for the 4-level model;
+    RG/noise_models.py:1300-1356)."""
+    if gamma_phi <= 0:
+        return []
+    rates = [gamma_phi] if hs.dim == 3 else [gamma_phi, gamma_phi if gamma_phi_minus is None else gamma_phi_minus]
+    ops: List[np.ndarray] = []
+    for r, g in zip(_rydberg_levels(hs), rates):
+        ops += _on_each_atom(g, hs.projectors[r], hs)
+    return ops
+
+
+def build_loss_operators(gamma_loss: float, hs, loss_source: str = "rydberg") -> List[np.ndarray]:
+    """Loss channels land in |0>: from the Rydberg level(s) or from |1> (RG/noise_models.py:1359-1412)."""
+    if gamma_loss <= 0:
+        return []
+    ops: List[np.ndarray] = []
+    if loss_source == "rydberg":
+        for r in _rydberg_levels(hs):
+            ops += _on_each_atom(gamma_loss, hs.transitions[f"{r}->0"], hs)
+    elif loss_source == "qubit":
+        sigma = hs.transitions.get("1->0")
+        if sigma is None:
+            sigma = hs.basis["0"] @ hs.basis["1"].conj().T
+        ops += _on_each_atom(gamma_loss, sigma, hs)
+    return ops
+
+
+def build_scatter_operators(gamma_scatter: float, hs) -> List[np.ndarray]:
+    """Intermediate-state scattering as dephasing of |1>: sqrt(gamma) |1><1| on each atom
+    (RG/noise_models.py:1415-1446)."""
+    if gamma_scatter <= 0:
+        return []
+    return _on_each_atom(gamma_scatter, hs.projectors["1"], hs)
+
+
 def build_all_noise_operators(params: dict = None, hs=None, dim: int = 3, gamma_r=None, gamma_bbr=None,
                               gamma_phi_laser=None, gamma_phi_thermal=None, gamma_phi_zeeman=None,
                               gamma_loss_antitrap=None, gamma_loss_background=None,
@@ -301,4 +366,5 @@ __all__ = ["NoiseRates", "rydberg_decay_rate", "bbr_decay_rate", "laser_dephasin
            "zeeman_dephasing_rate", "intermediate_state_scattering_rate", "dark_state_suppression_factor",
            "enhanced_scattering_rate", "leakage_rate_to_adjacent_states", "mJ_mixing_rate",
            "rydberg_zeeman_splitting", "compute_noise_rates", "collapse_channels",
-           "build_collapse_matrices", "build_all_noise_operators", "kernel_rates"]
+           "build_collapse_matrices", "build_decay_operators", "build_dephasing_operators", "build_loss_operators",
+           "build_scatter_operators", "build_all_noise_operators", "kernel_rates"]

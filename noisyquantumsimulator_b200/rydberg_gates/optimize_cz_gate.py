@@ -302,45 +302,26 @@ class PopulationObjective:
         return self.cache.make_key(self.cache_protocol, x.tolist(), f"{h}_n{self.noise_hash}")
 
     def _evaluate(self, X: np.ndarray) -> List[Dict[str, float]]:
-        """Metrics of every column of X through one batched launch (sharded over ranks if asked)."""
+        """Metrics of every column of X through one batched launch; with ``population_shards`` every rank evaluates
+        its block of the generation and the metric columns are all-gathered (``sharding.simulate_sharded``, which
+        keeps a failing rank inside the collective: its block comes back NaN -> the reference's failure cost 1e6
+        on every rank alike)."""
+        from .. import sharding
+
         n = X.shape[1]
-        lo, hi = 0, n
+        kw = dict(self.base)
+        n_proto = X.shape[0] - (1 if self.optimize_spacing else 0)
+        if self.optimize_spacing:
+            kw["spacing_factor"] = np.ascontiguousarray(X[-1])
+        kw.update(protocol_kwargs(self.proto, X[:n_proto], self.n_segments))
         if self.world > 1:
-            per = (n + self.world - 1) // self.world
-            lo, hi = min(n, self.rank * per), min(n, (self.rank + 1) * per)
-        rows = np.full((n, len(METRIC_KEYS)), np.nan)
-        failure = None
-        if hi > lo:
-            try:
-                Xs = X[:, lo:hi]
-                kw = dict(self.base)
-                n_proto = Xs.shape[0] - (1 if self.optimize_spacing else 0)
-                if self.optimize_spacing:
-                    kw["spacing_factor"] = Xs[-1]
-                kw.update(protocol_kwargs(self.proto, Xs[:n_proto], self.n_segments))
-                res = simulate_CZ_gate_batch(self.proto, B=hi - lo, device=self.device, warn=False,
-                                             outputs=self._outputs(kw), **kw)
-                rows[lo:hi] = batch_metric_rows(res)
-            except Exception as e:
-                # With several ranks a failure must not keep this rank out of the collective below (the
-                # others would wait in it forever, and the ranks' caches would diverge): the shard
-                # contributes NaN rows, which every rank maps to the reference's failure cost 1e6.
-                if self.world == 1:
-                    raise
-                failure = e
-                rows[lo:hi] = np.nan
-                if self.verbose:
-                    print(f"    rank {self.rank}: shard evaluation failed ({e}); contributing NaN rows")
-        if self.world > 1:
-            import torch
-            import torch.distributed as dist
-            per = (n + self.world - 1) // self.world
-            dev = torch.device("cuda", self.device) if dist.get_backend() == "nccl" else torch.device("cpu")
-            mine = torch.full((per, len(METRIC_KEYS)), float("nan"), dtype=torch.float64, device=dev)
-            mine[:hi - lo] = torch.from_numpy(rows[lo:hi]).to(dev)
-            full = torch.empty((self.world * per, len(METRIC_KEYS)), dtype=torch.float64, device=dev)
-            dist.all_gather_into_tensor(full, mine)
-            rows = full.cpu().numpy()[:n]
+            res = sharding.simulate_sharded(self.proto, n, rank=self.rank, world=self.world, device=self.device,
+                                            outputs=METRIC_OUTPUTS, **kw)
+            if res.local_failure is not None and self.verbose:
+                print(f"    rank {self.rank}: shard evaluation failed ({res.local_failure}); contributed NaN rows")
+        else:
+            res = simulate_CZ_gate_batch(self.proto, B=n, device=self.device, warn=False, outputs=self._outputs(kw), **kw)
+        rows = batch_metric_rows(res)
         return [dict(zip(METRIC_KEYS, map(float, r))) for r in rows]
 
     def __call__(self, X: np.ndarray):

@@ -564,6 +564,29 @@ class BatchResult:
         return np.where(bad, 1e6, c)
 
 
+def device_prologue_inputs(protocol: str, B: int, kwargs: dict):
+    """(model constants [32], apparatus columns [40]) of a batch for the device prologue (prologue_kernel):
+    slots go to the C ABI as columns (views of the caller's arrays, or one float for a slot that is the same for
+    every point), so nothing is packed or broadcast in Python."""
+    from . import device_prologue as dpro
+
+    if protocol not in PROTOCOL_NAMES:
+        raise ValueError(f"Unknown protocol: {protocol}")
+    mk, ak = dpro.split_kwargs(kwargs)
+    nseg = None
+    if protocol == "jp":
+        ph = ak.get("phases")
+        nseg = 5 if ph is None or np.size(ph) == 0 else np.shape(ph)[-1]
+    return dpro.model_constants(protocol, n_segments=nseg, **mk), dpro.apparatus_columns(protocol, B, **ak)
+
+
+def shot_kwargs(kwargs: dict, n_shots: int) -> dict:
+    """Monte-Carlo shots carry Doppler and position noise explicitly: their analytic dephasing rates are dropped."""
+    if n_shots > 0:
+        return dict(kwargs, include_doppler_dephasing=False, include_motional_dephasing=False)
+    return kwargs
+
+
 def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, seed: int = 1234,
                            return_states: bool = False, return_shots: bool = False, device: int = 0,
                            plan: GatePlan = None, prologue: str = "auto", copy: bool = True,
@@ -605,25 +628,13 @@ def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, se
     if B is None and plan is None:
         B = max([np.size(v) for v in kwargs.values() if isinstance(v, np.ndarray) and v.ndim >= 1
                  and np.shape(v)[0] > 1] or [1])
-    if n_shots > 0:
-        # shots carry Doppler and position noise explicitly: drop their analytic rates
-        kwargs = dict(kwargs, include_doppler_dephasing=False, include_motional_dephasing=False)
+    kwargs = shot_kwargs(kwargs, n_shots)
     ev = get_evaluator(device)
     states = shots = None
     if prologue == "device":
         if shaped:
             raise ValueError("shaped LP pulses need prologue='host'")
-        if protocol not in PROTOCOL_NAMES:
-            raise ValueError(f"Unknown protocol: {protocol}")
-        mk, ak = dpro.split_kwargs(kwargs)
-        nseg = None
-        if protocol == "jp":
-            ph = ak.get("phases")
-            nseg = 5 if ph is None or np.size(ph) == 0 else np.shape(ph)[-1]
-        model = dpro.model_constants(protocol, n_segments=nseg, **mk)
-        # apparatus slots go to the C ABI as columns (views of the caller's arrays, or one float for a
-        # slot that is the same for every point): nothing is packed or broadcast in Python
-        cols = dpro.apparatus_columns(protocol, B, **ak)
+        model, cols = device_prologue_inputs(protocol, B, kwargs)
         if outputs is not None:
             o_names = [o for o in outputs if o in OUTPUT_SLOTS]
             s_names = [o for o in outputs if o in SCALAR_SLOTS]
@@ -664,15 +675,9 @@ def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, se
         states=states, shots=shots, _voo=voo)
 
 
-def evolve_state(*args, **kwargs):
-    raise NotImplementedError(
-        "evolve_state wraps QuTiP mesolve in the reference (RG/simulation.py:647-690); on the B200 path "
-        "the evolution of all inputs and segments is one fused kernel -- call simulate_CZ_gate or "
-        "simulate_CZ_gate_batch.")
-
-
-evolve_two_pulse = evolve_two_pulse_lp = evolve_smooth_sinusoidal_jp = evolve_bangbang_jp = \
-    evolve_shaped_pulse = evolve_state
+# the reference's evolve_* helpers (RG/simulation.py:647-776, 1502-2235), served by the kernel (evolution.py)
+from .evolution import (evolve_bangbang_jp, evolve_shaped_pulse, evolve_smooth_sinusoidal_jp,  # noqa: E402
+                        evolve_state, evolve_two_pulse, evolve_two_pulse_lp)
 
 __all__ = ["b0", "b1", "br", "b0_4", "b1_4", "br_plus", "br_minus", "compute_state_fidelity",
            "compute_CZ_fidelity", "evolve_state", "evolve_two_pulse", "evolve_two_pulse_lp",

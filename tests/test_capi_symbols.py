@@ -55,3 +55,28 @@ def test_no_gpu_means_loud_failure(lib):
     from noisyquantumsimulator_b200.engine import Evaluator, RydczError
     with pytest.raises(RydczError):
         Evaluator(0)
+
+
+def test_torch_ops_are_registered_and_have_no_cpu_kernel(lib):
+    """torch.ops.rydcz.* (csrc/rydcz_torch.cpp): registered in the dispatcher, shapes propagate through the Meta
+    kernels, and CPU tensors are refused -- there is no CPU path behind the operators."""
+    import torch
+    from noisyquantumsimulator_b200 import build
+    build.build_torch_extension(verbose=False)
+    from noisyquantumsimulator_b200 import torch_ops  # noqa: F401
+    for name in ("evaluate", "evaluate_shots", "simulate", "point_status"):
+        assert hasattr(torch.ops.rydcz, name)
+    p = torch.empty(7, 12, dtype=torch.float64, device="meta")
+    s = torch.empty(7, 5, 4, dtype=torch.float64, device="meta")
+    out, st = torch.ops.rydcz.evaluate(p, s, None, 3, True, True)
+    assert out.shape == (7, 16) and st.shape == (7, 51)
+    out, st = torch.ops.rydcz.evaluate(torch.empty(7, 20, dtype=torch.float64, device="meta"), s, None, 5, True, False)
+    assert out.shape == (7, 16) and st.shape == (0, 129)
+    mean, shots = torch.ops.rydcz.evaluate_shots(p, s, None, 3, True, 8, 1234, True)
+    assert mean.shape == (7, 16) and shots.shape == (7, 8, 16)
+    out, sc = torch.ops.rydcz.simulate(torch.empty(32, dtype=torch.float64, device="meta"),
+                                       torch.empty(40, 9, dtype=torch.float64, device="meta"), 0, 1234)
+    assert out.shape == (9, 16) and sc.shape == (9, 8)
+    with pytest.raises(NotImplementedError):
+        torch.ops.rydcz.evaluate(torch.zeros(2, 12, dtype=torch.float64), torch.zeros(2, 1, 4, dtype=torch.float64),
+                                 None, 3, True, False)
