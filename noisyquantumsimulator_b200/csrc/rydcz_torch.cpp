@@ -13,6 +13,7 @@
 // Replaces, for a batch, RG/simulation.py:3364-3572 (evolve_* + compute_CZ_fidelity) and, for simulate,
 // RG/simulation.py:2820-3572.
 #include <ATen/cuda/CUDAContext.h>
+#include <cuda_runtime_api.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/library.h>
 #include <torch/torch.h>
@@ -36,6 +37,13 @@ rydcz_ctx* context_for(int device) {
   TORCH_CHECK(rc == 0 && ctx, "rydcz_create(device=", device, ") failed: ", rydcz_last_error(nullptr));
   g_ctx[device] = ctx;
   return ctx;
+}
+
+// torch's default stream has the handle 0, which the C ABI reads as "the context's own stream": name it explicitly
+// (cudaStreamLegacy) so that the work is ordered with whatever the caller enqueues on the default stream next.
+void* current_stream(int device) {
+  cudaStream_t s = at::cuda::getCurrentCUDAStream(device).stream();
+  return s ? (void*)s : (void*)cudaStreamLegacy;
 }
 
 void check_rc(rydcz_ctx* ctx, int rc, const char* what) {
@@ -72,7 +80,7 @@ std::tuple<at::Tensor, at::Tensor> evaluate(const at::Tensor& points_, const at:
   check_rc(ctx, rydcz_evaluate_device(ctx, (int)dim, noisy ? 1 : 0, B, points.data_ptr<double>(), segs.data_ptr<double>(),
                                       n_seg_.has_value() ? ns.data_ptr<int32_t>() : nullptr, (int)segs.size(1),
                                       out.data_ptr<double>(), want_states ? states.data_ptr<double>() : nullptr,
-                                      (void*)at::cuda::getCurrentCUDAStream(points.get_device()).stream()),
+                                      current_stream(points.get_device())),
            "rydcz_evaluate_device");
   return std::make_tuple(out, states);
 }
@@ -94,7 +102,7 @@ std::tuple<at::Tensor, at::Tensor> evaluate_shots(const at::Tensor& points_, con
                                             points.data_ptr<double>(), segs.data_ptr<double>(),
                                             n_seg_.has_value() ? ns.data_ptr<int32_t>() : nullptr, (int)segs.size(1),
                                             mean.data_ptr<double>(), want_shots ? shots.data_ptr<double>() : nullptr,
-                                            (void*)at::cuda::getCurrentCUDAStream(points.get_device()).stream()),
+                                            current_stream(points.get_device())),
            "rydcz_evaluate_shots_device");
   return std::make_tuple(mean, shots);
 }
@@ -114,7 +122,7 @@ std::tuple<at::Tensor, at::Tensor> simulate(const at::Tensor& model_, const at::
   rydcz_ctx* ctx = context_for(app.get_device());
   check_rc(ctx, rydcz_simulate_device(ctx, model.data_ptr<double>(), B, app.data_ptr<double>(), (int)n_shots, (uint64_t)seed,
                                       out.data_ptr<double>(), scalars.data_ptr<double>(), nullptr,
-                                      (void*)at::cuda::getCurrentCUDAStream(app.get_device()).stream()),
+                                      current_stream(app.get_device())),
            "rydcz_simulate_device");
   return std::make_tuple(out, scalars);
 }

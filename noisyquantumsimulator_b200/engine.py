@@ -22,6 +22,18 @@ class RydczError(RuntimeError):
     pass
 
 
+CUDA_STREAM_LEGACY = 1      # cudaStreamLegacy: the explicit handle of the default stream
+
+
+def _torch_stream(device, stream=None) -> int:
+    """Stream handle for the C ABI.  torch's default stream has the handle 0, which the C ABI reads as "the
+    context's own (non-blocking) stream": pass cudaStreamLegacy instead, so that the kernels are ordered with the
+    torch operations the caller enqueues on the default stream before and after the call."""
+    import torch
+    h = stream if stream is not None else torch.cuda.current_stream(device).cuda_stream
+    return int(h) if h else CUDA_STREAM_LEGACY
+
+
 def _host(a, dtype):
     a = np.ascontiguousarray(a, dtype=dtype)
     return a, a.ctypes.data
@@ -140,9 +152,9 @@ class Evaluator:
 
         assert points.is_cuda and segs.is_cuda and points.dtype == torch.float64 and segs.dtype == torch.float64
         points, segs = points.contiguous(), segs.contiguous()
-        if n_seg is not None:
-            assert n_seg.dtype == torch.int32 and n_seg.is_cuda
-        B = self._check_batch(dim, points, segs, None if n_seg is None else n_seg.cpu().numpy())
+        if n_seg is not None:      # (values stay on the device: checking them would synchronise)
+            assert n_seg.dtype == torch.int32 and n_seg.is_cuda and tuple(n_seg.shape) == (points.shape[0],)
+        B = self._check_batch(dim, points, segs, None)
         if out is None:
             out = torch.empty((B, _lib.OUT_STRIDE), dtype=torch.float64, device=points.device)
         if want_states and states is None:
@@ -151,7 +163,7 @@ class Evaluator:
         if n_seg is not None:
             n_seg = n_seg.contiguous()
             assert n_seg.dtype == torch.int32
-        st = stream if stream is not None else torch.cuda.current_stream(points.device).cuda_stream
+        st = _torch_stream(points.device, stream)
         self._check(self.lib.rydcz_evaluate_device(
             self.ctx, dim, int(bool(noisy)), B, points.data_ptr(), segs.data_ptr(),
             n_seg.data_ptr() if n_seg is not None else None, segs.shape[1], out.data_ptr(),
@@ -165,16 +177,16 @@ class Evaluator:
         assert points.is_cuda and segs.is_cuda and points.dtype == torch.float64 and segs.dtype == torch.float64
         points, segs = points.contiguous(), segs.contiguous()
         if n_seg is not None:
-            assert n_seg.dtype == torch.int32 and n_seg.is_cuda
+            assert n_seg.dtype == torch.int32 and n_seg.is_cuda and tuple(n_seg.shape) == (points.shape[0],)
             n_seg = n_seg.contiguous()
-        B = self._check_batch(dim, points, segs, None if n_seg is None else n_seg.cpu().numpy())
+        B = self._check_batch(dim, points, segs, None)
         assert n_shots >= 1
         if mean is None:
             mean = torch.empty((B, _lib.OUT_STRIDE), dtype=torch.float64, device=points.device)
         if want_shots and shots is None:
             shots = torch.empty((B, n_shots, _lib.OUT_STRIDE), dtype=torch.float64,
                                 device=points.device)
-        st = stream if stream is not None else torch.cuda.current_stream(points.device).cuda_stream
+        st = _torch_stream(points.device, stream)
         self._check(self.lib.rydcz_evaluate_shots_device(
             self.ctx, dim, int(bool(noisy)), B, int(n_shots), int(seed), points.data_ptr(),
             segs.data_ptr(), n_seg.data_ptr() if n_seg is not None else None, segs.shape[1],
@@ -222,7 +234,22 @@ class Evaluator:
         return out, sc, st
 
     def _column_args(self, cols, B):
-        ptrs, strides, consts, keep = self._column_args(cols, B)
+        """ctypes arrays (pointer, stride in doubles, batch-wide constant) for the 40 apparatus slots, plus the
+        arrays that must stay alive during the call."""
+        ptrs = (C.c_void_p * _lib.APP_STRIDE)()
+        strides = (C.c_int64 * _lib.APP_STRIDE)()
+        consts = (C.c_double * _lib.APP_STRIDE)()
+        keep = []
+        for k, v in enumerate(cols):
+            if isinstance(v, np.ndarray):
+                if v.dtype != np.float64 or v.ndim != 1 or v.strides[0] % 8 or v.strides[0] <= 0 \
+                        or not v.flags.aligned:
+                    v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1)
+                assert v.shape == (B,)
+                keep.append(v)
+                ptrs[k], strides[k], consts[k] = v.ctypes.data, v.strides[0] // 8, np.nan
+            else:
+                ptrs[k], strides[k], consts[k] = None, 1, float(v)
         return ptrs, strides, consts, keep
 
     def simulate_host_select(self, model, cols, B: int, out_slots, scalar_slots=(), n_shots: int = 0,
@@ -277,7 +304,7 @@ class Evaluator:
         assert app.shape[0] == _lib.APP_STRIDE
         if out is None:
             out = torch.empty((B, _lib.OUT_STRIDE), dtype=torch.float64, device=app.device)
-        st = stream if stream is not None else torch.cuda.current_stream(app.device).cuda_stream
+        st = _torch_stream(app.device, stream)
         self._check(self.lib.rydcz_simulate_device(
             self.ctx, m_ptr, B, app.data_ptr(), int(n_shots), int(seed), out.data_ptr(),
             scalars.data_ptr() if scalars is not None else None, None, st), "rydcz_simulate_device")
@@ -287,7 +314,7 @@ class Evaluator:
         import torch
 
         model, m_ptr = _host(model, np.float64)
-        st = stream if stream is not None else torch.cuda.current_stream(app.device).cuda_stream
+        st = _torch_stream(app.device, stream)
         self._check(self.lib.rydcz_prologue_device(
             self.ctx, m_ptr, app.shape[1], app.data_ptr(), points.data_ptr(), segs.data_ptr(), n_seg.data_ptr(),
             scalars.data_ptr() if scalars is not None else None, st), "rydcz_prologue_device")

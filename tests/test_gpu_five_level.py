@@ -56,7 +56,7 @@ def test_random_batch_against_dense_oracle(evaluator):
 
 def test_large_batch_properties(evaluator):
     """16,384 points: position independence, sorting on/off bit-identical, far-detuned points approach
-    the 3-level kernel's answer, unequal atoms are refused with NaN rows, shots are refused."""
+    the 3-level kernel's answer, unequal atoms are refused with an error, shots are refused."""
     from noisyquantumsimulator_b200.engine import RydczError
     case = next(c for c in CASES if c["name"] == "lp5_rb_noisy")
     B = 16384
@@ -81,8 +81,8 @@ def test_large_batch_properties(evaluator):
     # unequal atoms: the general 81-variable system is not built
     Q = P[:4].copy()
     Q[1, 2] = 1e3
-    o, _ = evaluator.evaluate_host(5, True, Q, G[:4], None)
-    assert np.all(np.isnan(o[1])) and np.array_equal(o[0], out[0])
+    with pytest.raises(RydczError, match="different detunings"):      # refused, not a silent NaN row
+        evaluator.evaluate_host(5, True, Q, G[:4], None)
     with pytest.raises(RydczError):
         evaluator.evaluate_shots_host(5, True, 4, 1, P[:4], G[:4], None)
 
