@@ -224,10 +224,19 @@ def _cpu_one_expm(args):
     return avg, fid["11"], info["cz_phase_fidelity"], fid["01"]
 
 
+def _single_thread_blas():
+    """Pool workers run one evaluation each: BLAS / OpenMP teams inside them would oversubscribe the cores."""
+    try:
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(1)
+    except Exception:
+        pass
+
+
 def _pool_map(fn, work, procs):
     import multiprocessing as mp
     if procs > 1:
-        with mp.get_context("fork").Pool(procs) as pool:
+        with mp.get_context("fork").Pool(procs, initializer=_single_thread_blas) as pool:
             return pool.map(fn, work, chunksize=1)
     return [fn(w) for w in work]
 

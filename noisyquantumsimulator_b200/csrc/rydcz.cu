@@ -17,7 +17,6 @@
 //     4-level shots, the 5-level model), folded or general; also takes back any clustered point whose
 //     trace / norm check fails.
 #include <cuda_runtime.h>
-#include <cub/device/device_radix_sort.cuh>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -81,7 +80,53 @@ enum PointKind : uint8_t { KIND_GENERAL = 0, KIND_SYM = 1, KIND_CLUSTER_GENERAL 
                            KIND_MASK = 0x0f,
                            KIND_RETRY = 0x10 };    // flag: handed back by the clustered path to the plain kernel of its kind
 
-// Per point: its kind, and a sort key (kind in the top bits, work estimate below) so that a warp holds
+// ---- planning without a sort ---------------------------------------------------------------------------------
+// Points are processed in an order that keeps the lanes of a warp on one kernel path with (almost) equal trip
+// counts: grouped by kind, heaviest first.  A full radix sort of 32-bit keys is more than that needs: the key is
+// coarsened to a BIN (kind group x 16 bins per octave of the work estimate: lanes of a warp differ by < 4.4 % in
+// work), the bins are counted by the planner itself, one small CTA turns the counts into offsets, and a scatter
+// pass writes the order -- three launches, no library call.  The coefficient tasks of the clustered path are
+// binned by their term count K the same way.  The scan also leaves, per kind group, the range of positions its
+// points occupy: each evaluate kernel covers only its own range (CTAs beyond it leave after one load).
+constexpr int kWorkBins = 512;                     // 16 per octave, 32 octaves of the work estimate
+constexpr int kGroups = 8;                         // kind groups (5 used)
+constexpr int kBins = kGroups * kWorkBins;
+constexpr int kTaskBins = 64;                      // term counts K <= CL_MAX_K
+enum Group : int { GROUP_CLUSTER = 0, GROUP_SYM = 1, GROUP_GENERAL = 2, GROUP_CLUSTER_GENERAL = 3, GROUP_REPEAT = 4 };
+struct PlanCounts {
+  unsigned hist[kBins];          // points per bin; turned into running write cursors by plan_scan_kernel
+  unsigned thist[kTaskBins];     // coefficient tasks per term count; likewise
+  unsigned group_start[kGroups]; // first position of each kind group in the order
+  unsigned group_count[kGroups];
+  unsigned n_tasks;              // coefficient tasks of this batch
+  unsigned retries;              // clustered points handed back to the plain kernels in this call
+  unsigned pad[2];
+};
+
+__device__ __forceinline__ unsigned work_bin(double w) {
+  // 16 bins per octave: floor(16 log2(w)), w >= 1
+  const double x = fmax(w, 1.0);
+  const int b = (int)(16.0 * log2(x));
+  return (unsigned)(b < 0 ? 0 : (b > kWorkBins - 1 ? kWorkBins - 1 : b));
+}
+
+// one atomic per distinct key among the active lanes of a warp
+__device__ __forceinline__ void warp_count(unsigned* __restrict__ hist, unsigned key, bool valid) {
+  const unsigned m = __match_any_sync(0xffffffffu, valid ? key : 0xffffffffu);
+  if (valid && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) atomicAdd(hist + key, (unsigned)__popc(m));
+}
+// position for this lane in the bin of `key`: one atomic per distinct key, lanes of a key take consecutive slots
+__device__ __forceinline__ unsigned warp_claim(unsigned* __restrict__ cursor, unsigned key, bool valid) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned m = __match_any_sync(0xffffffffu, valid ? key : 0xffffffffu);
+  const int leader = __ffs(m) - 1;
+  unsigned base = 0;
+  if (valid && lane == (unsigned)leader) base = atomicAdd(cursor + key, (unsigned)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return base + (unsigned)__popc(m & ((1u << lane) - 1u));
+}
+
+// Per point: its kind and its bin (kind group in the top bits, work bin below) so that a warp holds
 // points of one kind and similar cost.  cluster_mode: 0 = plain path only, 1 = clustered path where the
 // planner finds it cheaper, 2 = wherever it is eligible.
 template <int D>
@@ -91,27 +136,29 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
                             uint32_t* __restrict__ idx, uint8_t* __restrict__ kind,
                             uint32_t* __restrict__ task_key, uint32_t* __restrict__ task_val,
                             double* __restrict__ scratch, unsigned long long* __restrict__ counters,
-                            unsigned* __restrict__ repeat_count) {
+                            unsigned* __restrict__ repeat_count, PlanCounts* __restrict__ plan) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool clustered = false, repeated = false;
   int records_planned = 0;
-  if (i < n_points) {
-    int slot_K[CL_MAX_SLOTS], slot_off[CL_MAX_SLOTS];
+  unsigned bin = 0;
+  int slot_K[CL_MAX_SLOTS], slot_off[CL_MAX_SLOTS];
 #pragma unroll
-    for (int q = 0; q < CL_MAX_SLOTS; ++q) { slot_K[q] = 0; slot_off[q] = 0; }
+  for (int q = 0; q < CL_MAX_SLOTS; ++q) { slot_K[q] = 0; slot_off[q] = 0; }
+  if (i < n_points) {
     const double* pt = points + i * PointStride<D>::value;
     const int64_t sp = i / seg_div;       // row of the pulse schedule (the shots of a point share it)
     const double* sg = segs + sp * (int64_t)max_seg * SG_STRIDE;
     const int ns = n_seg ? n_seg[sp] : max_seg;
     const bool sym = (pt[PT_OFF_A] == pt[PT_OFF_B]) && !(shots && pt[PT_SIG_DET] != 0.0);
-    uint32_t group = sym ? 1u : 2u;     // 4 repeated-segment (must sort to the FRONT: the repeat kernels walk the first
-    // *repeat_count positions), 3 clustered general, 2 general, 1 plain folded, 0 clustered
+    // groups in the order's sequence (highest first): repeated-segment (must come FIRST: the repeat kernels walk the
+    // first *repeat_count positions), clustered general, general, plain folded, clustered
+    uint32_t group = sym ? GROUP_SYM : GROUP_GENERAL;
     double w = 0.0;
     if (D == 3 && repeat_count && sym && !shots) {
       int first, count;
       if (repeat_eligible(sg, ns, first, count)) {
         // one propagator for all segments (rydcz_repeat.cuh): 30 column builds + count dense steps
-        repeated = true; group = 4u; w = 40.0 * 30.0 + 4.0 * (double)count;
+        repeated = true; group = GROUP_REPEAT; w = 40.0 * 30.0 + 4.0 * (double)count;
       }
     }
     if (!repeated) w = point_work<D>(pt, sg, ns);
@@ -122,7 +169,7 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
       const int records = cluster_plan<D>(pt, sg, ns, noisy != 0, sym, cost, slot_K, slot_off,
                                           scratch + i * (int64_t)CL_STRIDE);
       if (records > 0 && records <= CL_RECORDS && (cluster_mode == 2 || cost < 0.8 * w)) {
-        clustered = true; group = sym ? 0u : 3u; w = sym ? cost : 2.0 * cost; records_planned = records;
+        clustered = true; group = sym ? GROUP_CLUSTER : GROUP_CLUSTER_GENERAL; w = sym ? cost : 2.0 * cost; records_planned = records;
       }
     }
     if (task_key) {
@@ -136,9 +183,17 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
     }
     kind[i] = repeated ? KIND_REPEAT
                        : (clustered ? (sym ? KIND_CLUSTER : KIND_CLUSTER_GENERAL) : (sym ? KIND_SYM : KIND_GENERAL));
-    const double wq = fmin(fmax(w, 0.0), 536870911.0);
-    keys[i] = (group << 29) | (uint32_t)wq;
+    bin = group * kWorkBins + work_bin(w);
+    keys[i] = bin;
     idx[i] = (uint32_t)i;
+  }
+  if (plan) {
+    warp_count(plan->hist, bin, i < n_points);
+    if (task_key) {
+#pragma unroll
+      for (int q = 0; q < CL_MAX_SLOTS; ++q)
+        warp_count(plan->thist, (unsigned)slot_K[q], i < n_points && clustered && slot_K[q] > 0);
+    }
   }
   const unsigned m = __ballot_sync(0xffffffffu, clustered);
   const unsigned rsum = __reduce_add_sync(0xffffffffu, (unsigned)records_planned);
@@ -158,18 +213,90 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
 // node values through shared memory ([value][node][task], 48 KB per CTA) and then split the blocks of
 // eight coefficients.  Tasks are sorted by their term count so that a warp runs uniform trip counts
 // (key 0 = no such slot: sorted to the end).
+// Offsets from counts, one CTA: bins in DESCENDING key order (highest group first, heaviest first inside a group).
+// hist[] / thist[] become the running write cursors of plan_scatter_kernel.
+__global__ void __launch_bounds__(1024) plan_scan_kernel(PlanCounts* __restrict__ plan) {
+  __shared__ unsigned s_warp[32];
+  __shared__ unsigned s_group[kGroups];
+  __shared__ unsigned s_total;
+  constexpr int PER = kBins / 1024;               // bins per thread
+  const int t = threadIdx.x;
+  // thread t owns the positions-order slots p = PER t .. PER t + PER - 1, bin = kBins - 1 - p
+  unsigned c[PER], sum = 0;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) { c[j] = plan->hist[kBins - 1 - (PER * t + j)]; sum += c[j]; }
+  unsigned incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, incl, o); if ((t & 31) >= o) incl += v; }
+  if ((t & 31) == 31) s_warp[t >> 5] = incl;
+  __syncthreads();
+  if (t < 32) {
+    unsigned w = s_warp[t], wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned v = __shfl_up_sync(0xffffffffu, wi, o); if (t >= o) wi += v; }
+    s_warp[t] = wi - w;                            // exclusive prefix of the warp totals
+  }
+  __syncthreads();
+  unsigned off = s_warp[t >> 5] + incl - sum;
+#pragma unroll
+  for (int j = 0; j < PER; ++j) {
+    const int p = PER * t + j, bin = kBins - 1 - p;
+    plan->hist[bin] = off;
+    if (bin % kWorkBins == kWorkBins - 1) s_group[bin / kWorkBins] = off;      // first bin of its group in the order
+    off += c[j];
+  }
+  if (t == 1023) s_total = off;                    // total number of points (the last thread's running offset)
+  __syncthreads();
+  // groups descend in the order: group g ends where group g - 1 starts (group 0 ends at the total)
+  if (t < kGroups) {
+    plan->group_start[t] = s_group[t];
+    plan->group_count[t] = (t == 0 ? s_total : s_group[t - 1]) - s_group[t];
+  }
+  if (t == 0) {
+    // coefficient tasks: descending term count, so that a warp of cluster_coef_kernel runs uniform trip counts
+    unsigned o = 0;
+    for (int K = kTaskBins - 1; K >= 1; --K) { const unsigned n = plan->thist[K]; plan->thist[K] = o; o += n; }
+    plan->n_tasks = o;
+  }
+}
+
+// order[position] = point, task_sorted[position] = record index of the task's slot header
+__global__ void plan_scatter_kernel(int64_t n_points, const uint32_t* __restrict__ keys, uint32_t* __restrict__ order,
+                                    const uint32_t* __restrict__ task_key, const uint32_t* __restrict__ task_val,
+                                    uint32_t* __restrict__ task_sorted, PlanCounts* __restrict__ plan) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = i < n_points;
+  const unsigned bin = in ? keys[i] : 0u;
+  const unsigned pos = warp_claim(plan->hist, bin, in);
+  if (in) order[pos] = (uint32_t)i;
+  if (task_key) {
+#pragma unroll
+    for (int q = 0; q < CL_MAX_SLOTS; ++q) {
+      const unsigned K = in ? task_key[i * CL_MAX_SLOTS + q] : 0u;
+      const bool have = in && K > 0u;
+      const unsigned tp = warp_claim(plan->thist, K, have);
+      if (have) task_sorted[tp] = task_val[i * CL_MAX_SLOTS + q];
+    }
+  }
+}
+
 constexpr int kCoefLanes = 4;
 constexpr int kCoefTasksPerCta = kBlock / kCoefLanes;
+// Coefficient records of the clustered path: four lanes per task = one slot of one point, found through
+// the record index of its header (written by plan_kernel).  The lanes split the Gauss nodes, exchange the
+// node values through shared memory ([value][node][task], 48 KB per CTA) and then split the blocks of
+// eight coefficients.  Tasks come binned by their term count so that a warp runs uniform trip counts; the
+// grid is sized for the largest possible task count and CTAs beyond the real one leave at once.
 __global__ void __launch_bounds__(kBlock, 4)
-cluster_coef_kernel(int64_t n_tasks, const uint32_t* __restrict__ task_key, const uint32_t* __restrict__ task_val,
+cluster_coef_kernel(const PlanCounts* __restrict__ plan, const uint32_t* __restrict__ task_sorted,
                     double* __restrict__ scratch) {
   __shared__ double s_a[6 * CL_HALF_MAX * kCoefTasksPerCta];
   const int t_in_cta = threadIdx.x / kCoefLanes, m = threadIdx.x % kCoefLanes;
   const int64_t g = (int64_t)blockIdx.x * kCoefTasksPerCta + t_in_cta;
   // the four lanes of a task take the same branch; a warp whose tasks are all absent leaves together
-  const bool have = g < n_tasks && task_key[g] != 0u;
+  const bool have = g < (int64_t)plan->n_tasks;
   if (!__any_sync(0xffffffffu, have)) return;
-  if (have) cluster_coefficients(scratch + (int64_t)task_val[g] * CL_REC, s_a + t_in_cta, kCoefTasksPerCta, m, kCoefLanes);
+  if (have) cluster_coefficients(scratch + (int64_t)task_sorted[g] * CL_REC, s_a + t_in_cta, kCoefTasksPerCta, m, kCoefLanes);
   else __syncwarp();     // pairs with the group barrier inside cluster_coefficients
 }
 
@@ -187,18 +314,34 @@ template <int D, bool NOISY, bool SHOTS, bool SYM>
 __global__ void __launch_bounds__(kBlock, (SYM && D == 3 && RYDCZ_D3_VARIANT != 0) ? 3 : 2)
 evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, int64_t point_base,
                 const uint32_t* __restrict__ order,
-                const uint8_t* __restrict__ kind,
+                const uint8_t* __restrict__ kind, const PlanCounts* __restrict__ plan,
                 const double* __restrict__ points, const double* __restrict__ segs,
                 const int32_t* __restrict__ n_seg, int max_seg, int seg_div, double* __restrict__ out,
                 double* __restrict__ states) {
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // item (position x shot) this thread looks at
+  int64_t limit = n_items;
+  if (plan) {
+    // The order keeps the kinds apart: this kernel's own points and, next to them, the clustered points of the same
+    // symmetry, which only matter when some of them were handed back (plan->retries).  Positions in the order:
+    // ... [clustered general][general][folded][clustered].  CTAs outside the range leave at once.
+    const int own = SYM ? GROUP_SYM : GROUP_GENERAL, fed = SYM ? GROUP_CLUSTER : GROUP_CLUSTER_GENERAL;
+    const int64_t per = SHOTS ? n_shots : 1;
+    const bool retry = plan->retries != 0;
+    const int64_t lo_own = plan->group_start[own], n_own = plan->group_count[own];
+    const int64_t lo_fed = plan->group_start[fed], n_fed = plan->group_count[fed];
+    int64_t lo = lo_own, n = n_own;
+    if (retry) { lo = lo_own < lo_fed ? lo_own : lo_fed; n = n_own + n_fed; }     // the two ranges are adjacent
+    if ((int64_t)blockIdx.x * blockDim.x >= n * per) return;
+    g += lo * per;
+    limit = (lo + n) * per;
+  }
   int64_t point = 0, item;
   uint32_t shot = 0;
-  bool keep = g < n_items;
+  bool keep = g < limit;
   if (keep) {
     if (SHOTS) point = order ? order[g / n_shots] : g / n_shots;
     else point = order ? order[g] : g;
-    // a clustered point whose invariant check failed comes back here as KIND_SYM
+    // a clustered point whose invariant check failed comes back here as KIND_SYM | KIND_RETRY
     keep = (kind[point] & KIND_MASK) == (SYM ? KIND_SYM : KIND_GENERAL);
   }
   const unsigned live = __ballot_sync(0xffffffffu, keep);   // the lanes that evaluate a point in this kernel
@@ -255,9 +398,10 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, int64_t point_base,
 // coefficient records were written by cluster_coef_kernel into the point's region of `scratch`.
 template <int D, bool SYM = true> struct ClusterSmem {
   static constexpr int XN = !SYM ? Sys_rho11_d3::N : (D == 3 ? Sys_rho11s_d3::N : Sys_rho11s_d4::N);
-  static constexpr int XN2 = (SYM && ClusterPair<D>::value) ? (D == 3 ? Sys_coh11s_d3::N : Sys_coh11s_d4::N) : 0;
-  static constexpr int RING0 = PT_MAX_STRIDE + PT_SCRATCH + 3 * (XN + XN2);   // first column of the record ring
-  static constexpr int SLOTS = RING0 + 3 * (SYM ? ClusterRing<D>::value : CL_RING_GENERAL);
+  static constexpr int X0 = PT_STRIDE + PT_SCRATCH;                   // first start-vector column (3- / 4-level rows: 12 slots)
+  static constexpr int RING0 = X0 + 3 * XN;                           // first column of the record ring
+  // the ring, then the lookahead columns (next segment row + next slot header, rydcz_cluster.cuh)
+  static constexpr int SLOTS = RING0 + 3 * (SYM ? ClusterRing<D>::value : CL_RING_GENERAL) + CL_LOOKAHEAD;
   static constexpr size_t BYTES = (size_t)SLOTS * kBlock * sizeof(double);
 };
 // SYM = false: unequal atoms (3-level model), the general systems; `points` may hold one row per shot
@@ -265,15 +409,24 @@ template <int D, bool SYM = true> struct ClusterSmem {
 template <int D, bool NOISY, bool SYM>
 __global__ void __launch_bounds__(kBlock, 2)
 evaluate_cluster_kernel(int64_t n_items, const uint32_t* __restrict__ order, uint8_t* __restrict__ kind,
+                        PlanCounts* __restrict__ plan,
                         const double* __restrict__ points, const double* __restrict__ segs,
                         const int32_t* __restrict__ n_seg, int max_seg, int seg_div,
                         const double* __restrict__ scratch,
                         double* __restrict__ out, double* __restrict__ states,
                         unsigned long long* __restrict__ counters) {
   extern __shared__ double s_cl[];
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t limit = n_items;
+  if (plan) {       // only the positions of this kernel's kind group
+    const int grp = SYM ? GROUP_CLUSTER : GROUP_CLUSTER_GENERAL;
+    const int64_t lo = plan->group_start[grp], n = plan->group_count[grp];
+    if ((int64_t)blockIdx.x * blockDim.x >= n) return;
+    g += lo;
+    limit = lo + n;
+  }
   int64_t point = 0;
-  bool keep = g < n_items;
+  bool keep = g < limit;
   if (keep) {
     point = order ? order[g] : g;
     keep = kind[point] == (SYM ? KIND_CLUSTER : KIND_CLUSTER_GENERAL);
@@ -284,8 +437,8 @@ evaluate_cluster_kernel(int64_t n_items, const uint32_t* __restrict__ order, uin
   const double* row = points + point * PT_STRIDE;
 #pragma unroll
   for (int k = 0; k < PT_STRIDE; ++k) mine[k * kBlock] = row[k];
-  const PointView pt{mine, kBlock, live};
-  const Col xcol{mine + (PT_MAX_STRIDE + PT_SCRATCH) * kBlock, kBlock};
+  const PointView pt{mine, kBlock, live, PT_STRIDE};
+  const Col xcol{mine + ClusterSmem<D, SYM>::X0 * kBlock, kBlock};
   const Col rcol{mine + ClusterSmem<D, SYM>::RING0 * kBlock, kBlock};
   const int64_t sp = point / seg_div;
   const double* sg = segs + sp * (int64_t)max_seg * SG_STRIDE;
@@ -300,6 +453,7 @@ evaluate_cluster_kernel(int64_t n_items, const uint32_t* __restrict__ order, uin
   if (!ok) {
     // invariant check failed: hand the point to the plain kernel of its kind, which runs after this one
     kind[point] = (SYM ? KIND_SYM : KIND_GENERAL) | KIND_RETRY;
+    if (plan) atomicAdd(&plan->retries, 1u);
     if (counters) atomicAdd(counters + 1, 1ull);
     return;
   }
@@ -618,7 +772,7 @@ struct rydcz_ctx {
   unsigned* rp_count = nullptr;                         // points of that kind per in-flight call (slot 0 + one per lane)
   cudaEvent_t evc0 = nullptr, evc1 = nullptr;           // around the last coefficient kernel
   bool coef_timed = false;
-  void* cub_tmp = nullptr; size_t cub_cap = 0;
+  PlanCounts* plan_counts = nullptr;                    // one per in-flight work order (slot 0 + one per lane)
   // staging for the host entry points
   void* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t stage_cap[6] = {0, 0, 0, 0, 0, 0};
@@ -631,7 +785,6 @@ struct rydcz_ctx {
     cudaEvent_t ring_free = nullptr;              // the H2D copies out of `ring` have completed
     double* ring = nullptr; size_t ring_cap = 0;  // page-locked staging for the packed columns
     double* d_ring = nullptr;                     // its device twin (scattered to the slot rows by fill_slots_kernel)
-    void* cub_tmp = nullptr; size_t cub_cap = 0;
   };
   static constexpr int kLanes = 3;
   Lane lane[kLanes];
@@ -648,7 +801,7 @@ struct SortScratch {
   int64_t task_n;      // stride of the four task arrays
   double* rp;          // propagators of the repeated-segment path for these points (stride = their number)
   unsigned* rp_count;  // device counter of the points that take it
-  void** tmp; size_t* tmp_cap;
+  PlanCounts* plan;    // bin counts / cursors / kind ranges of this work order
 };
 
 static std::string g_create_error;
@@ -742,9 +895,11 @@ static int order_reserve(rydcz_ctx* ctx, int64_t n, bool want_cluster = true) {
     CK(cudaMemset(ctx->cl_counters, 0, 6 * sizeof(unsigned long long)));
     CK(cudaEventCreate(&ctx->evc0)); CK(cudaEventCreate(&ctx->evc1));
     CK(cudaMalloc(&ctx->rp_count, (1 + rydcz_ctx::kLanes) * sizeof(unsigned)));
+    CK(cudaMalloc(&ctx->plan_counts, (1 + rydcz_ctx::kLanes) * sizeof(PlanCounts)));
   }
   if (want_cluster && ctx->cluster_mode) {
-    const size_t bytes = (size_t)n * CL_STRIDE * sizeof(double);
+    // (+ a pad: the lookahead of the last slot of the last point reads one header past its records)
+    const size_t bytes = (size_t)n * CL_STRIDE * sizeof(double) + 256;
     if (bytes <= kClusterScratchMax) {
       // no memory for the records (16.6 KB per point): not an error, the call stays on the plain path and
       // says so (rydcz_call_flags: RYDCZ_FLAG_NO_CLUSTER_SCRATCH)
@@ -764,7 +919,7 @@ static int order_reserve(rydcz_ctx* ctx, int64_t n, bool want_cluster = true) {
 
 static SortScratch context_scratch(rydcz_ctx* ctx, int64_t n, int64_t offset = 0, int counter_slot = 0) {
   const bool cl = ctx->cluster_mode && ctx->cl_scratch && ctx->task &&
-                  (size_t)(offset + n) * CL_STRIDE * sizeof(double) <= ctx->cl_cap &&
+                  (size_t)(offset + n) * CL_STRIDE * sizeof(double) + 256 <= ctx->cl_cap &&
                   (size_t)(offset + n) * CL_MAX_SLOTS * 4 * sizeof(uint32_t) <= ctx->task_cap;
   // the four task arrays of a sub-range are laid out back to back inside its own span of the buffer
   return SortScratch{ctx->keys + offset, ctx->keys_sorted + offset, ctx->idx + offset, ctx->idx_sorted + offset,
@@ -772,7 +927,7 @@ static SortScratch context_scratch(rydcz_ctx* ctx, int64_t n, int64_t offset = 0
                      cl ? ctx->task + offset * (int64_t)CL_MAX_SLOTS * 4 : nullptr, n * (int64_t)CL_MAX_SLOTS,
                      (cl && ctx->rp_E && (size_t)(offset + n) * RepeatLayout<3>::STRIDE * sizeof(double) <= ctx->rp_cap)
                          ? ctx->rp_E + offset * (int64_t)RepeatLayout<3>::STRIDE : nullptr,
-                     ctx->rp_count + counter_slot, &ctx->cub_tmp, &ctx->cub_cap};
+                     ctx->rp_count + counter_slot, ctx->plan_counts + counter_slot};
 }
 
 // Plan the batch: kind of every point, heaviest-first order (nullptr when sorting is off), and the
@@ -785,33 +940,29 @@ static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const do
   const int mode = (sc.cl && D != 5 && !shots && n * (int64_t)CL_RECORDS < 0xffffffffLL) ? ctx->cluster_mode : 0;
   unsigned* rpc = (mode && D == 3 && sc.rp && seg_div == 1) ? sc.rp_count : nullptr;
   if (rpc) CK(cudaMemsetAsync(rpc, 0, sizeof(unsigned), st));
-  uint32_t* tk = mode ? sc.task : nullptr;
-  uint32_t* tks = mode ? sc.task + sc.task_n : nullptr;
-  uint32_t* tv = mode ? sc.task + 2 * sc.task_n : nullptr;
-  uint32_t* tvs = mode ? sc.task + 3 * sc.task_n : nullptr;
+  uint32_t* tk = mode ? sc.task : nullptr;                     // term count of every (point, slot); 0 = no such slot
+  uint32_t* tks = mode ? sc.task + sc.task_n : nullptr;        // tasks binned by term count: record index of the slot header
+  uint32_t* tv = mode ? sc.task + 2 * sc.task_n : nullptr;     // record index of every (point, slot)
+  CK(cudaMemsetAsync(sc.plan, 0, sizeof(PlanCounts), st));
   plan_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_points, d_segs, d_n_seg, max_seg, seg_div, shots, noisy,
                                                               mode, sc.keys, sc.idx, sc.kind, tk, tv, sc.cl,
-                                                              ctx->cl_counters, rpc);
+                                                              ctx->cl_counters, rpc, sc.plan);
   CK(cudaGetLastError());
   ctx->launches++;
-  if (ctx->sort && n >= 64) {
-    size_t need = 0;
-    CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, sc.keys, sc.keys_sorted, sc.idx, sc.idx_sorted,
-                                                 (int)n, 0, 32, st));
-    if (grow(ctx, sc.tmp, sc.tmp_cap, need)) return 1;
-    CK(cub::DeviceRadixSort::SortPairsDescending(*sc.tmp, need, sc.keys, sc.keys_sorted, sc.idx, sc.idx_sorted,
-                                                 (int)n, 0, 32, st));
-    *order = sc.idx_sorted;
+  const bool sorted = ctx->sort && n >= 64;
+  if (sorted || mode) {
+    // counts -> offsets -> order (and the coefficient task list): no library sort
+    plan_scan_kernel<<<1, 1024, 0, st>>>(sc.plan);
+    plan_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, sc.keys, sc.idx_sorted, tk, tv, tks, sc.plan);
+    CK(cudaGetLastError());
+    ctx->launches += 2;
+    if (sorted) *order = sc.idx_sorted;
   }
   if (mode) {
-    const int64_t threads = n * CL_MAX_SLOTS;
-    size_t need = 0;
-    CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, need, tk, tks, tv, tvs, (int)threads, 0, 7, st));
-    if (grow(ctx, sc.tmp, sc.tmp_cap, need)) return 1;
-    CK(cub::DeviceRadixSort::SortPairsDescending(*sc.tmp, need, tk, tks, tv, tvs, (int)threads, 0, 7, st));
+    const int64_t max_tasks = n * CL_MAX_SLOTS;
     CK(cudaEventRecord(ctx->evc0, st));
-    cluster_coef_kernel<<<(unsigned)((threads + kCoefTasksPerCta - 1) / kCoefTasksPerCta), kBlock, 0, st>>>(
-        threads, tks, tvs, sc.cl);
+    cluster_coef_kernel<<<(unsigned)((max_tasks + kCoefTasksPerCta - 1) / kCoefTasksPerCta), kBlock, 0, st>>>(
+        sc.plan, tks, sc.cl);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->evc1, st));
     ctx->coef_timed = true;
@@ -828,6 +979,8 @@ static int launch_eval(rydcz_ctx* ctx, const SortScratch& sc, int64_t n_items, i
   // mark: bit 0 = record the start event, bit 1 = record the end event (a pipelined call marks the
   // first chunk's start and the last chunk's end)
   const unsigned grid = (unsigned)((n_items + kBlock - 1) / kBlock);
+  // with an order, every kernel covers only the positions of its own kind group (ranges left by plan_scan_kernel)
+  PlanCounts* plan = order ? sc.plan : nullptr;
   if (mark & 1) CK(cudaEventRecord(ctx->ev0, st));
   if (!SHOTS && D == 3 && sc.cl && ctx->cluster_mode) {
     // unequal atoms on the clustered path; before the plain general kernel, which takes the hand-backs
@@ -837,12 +990,12 @@ static int launch_eval(rydcz_ctx* ctx, const SortScratch& sc, int64_t n_items, i
       ctx->cl_smem_gen_set = true;
     }
     evaluate_cluster_kernel<3, NOISY, false><<<grid, kBlock, ClusterSmem<3, false>::BYTES, st>>>(
-        n_items, order, sc.kind, d_points, d_segs, d_n_seg, max_seg, seg_div, sc.cl, d_out, d_states, ctx->cl_counters);
+        n_items, order, sc.kind, plan, d_points, d_segs, d_n_seg, max_seg, seg_div, sc.cl, d_out, d_states, ctx->cl_counters);
     CK(cudaGetLastError());
     ctx->launches++;
   }
   evaluate_kernel<D, NOISY, SHOTS, false><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, point_base, order,
-                                                                   sc.kind, d_points, d_segs, d_n_seg, max_seg,
+                                                                   sc.kind, plan, d_points, d_segs, d_n_seg, max_seg,
                                                                    seg_div, d_out, d_states);
   CK(cudaGetLastError());
   ctx->launches++;
@@ -856,12 +1009,12 @@ static int launch_eval(rydcz_ctx* ctx, const SortScratch& sc, int64_t n_items, i
     }
     // before the plain folded kernel: points whose invariant check fails are handed on to it
     evaluate_cluster_kernel<D, NOISY, true><<<grid, kBlock, ClusterSmem<D>::BYTES, st>>>(
-        n_items, order, sc.kind, d_points, d_segs, d_n_seg, max_seg, seg_div, sc.cl, d_out, d_states, ctx->cl_counters);
+        n_items, order, sc.kind, plan, d_points, d_segs, d_n_seg, max_seg, seg_div, sc.cl, d_out, d_states, ctx->cl_counters);
     CK(cudaGetLastError());
     ctx->launches++;
   }
   evaluate_kernel<D, NOISY, SHOTS, true><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, point_base, order,
-                                                                  sc.kind, d_points, d_segs, d_n_seg, max_seg,
+                                                                  sc.kind, plan, d_points, d_segs, d_n_seg, max_seg,
                                                                   seg_div, d_out, d_states);
   CK(cudaGetLastError());
   if (!SHOTS && D == 3 && seg_div == 1 && sc.cl && sc.rp && ctx->cluster_mode && n_items * (int64_t)CL_RECORDS < 0xffffffffLL) {
@@ -940,7 +1093,7 @@ void rydcz_destroy(rydcz_ctx* ctx) {
   if (ctx->busy) cudaEventDestroy(ctx->busy);
   if (ctx->evc0) cudaEventDestroy(ctx->evc0);
   if (ctx->evc1) cudaEventDestroy(ctx->evc1);
-  cudaFree(ctx->cub_tmp);
+  cudaFree(ctx->plan_counts);
   for (int i = 0; i < 6; ++i) cudaFree(ctx->stage[i]);
   for (int i = 0; i < 3; ++i) cudaFree(ctx->plan[i]);
   for (int l = 0; l < rydcz_ctx::kLanes; ++l) {
@@ -949,7 +1102,6 @@ void rydcz_destroy(rydcz_ctx* ctx) {
     if (L.ring_free) cudaEventDestroy(L.ring_free);
     if (L.ring) cudaFreeHost(L.ring);
     cudaFree(L.d_ring);
-    cudaFree(L.cub_tmp);
   }
   cudaEventDestroy(ctx->ev0); cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->stream);
@@ -1465,7 +1617,6 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
     if (prologue_impl(ctx, h_model, nc, d_app + i0, n_points, d_pts + i0 * pstride,
                       d_segs + i0 * (int64_t)S * SG_STRIDE, d_ns + i0, c_sc, st)) return 1;
     SortScratch sc = context_scratch(ctx, nc * per_item, i0 * per_item, 1 + (int)(c % rydcz_ctx::kLanes));
-    sc.tmp = &L.cub_tmp; sc.tmp_cap = &L.cub_cap;
     const int mark = (c == 0 ? 1 : 0) | (c == n_chunks - 1 ? 2 : 0);
     int rc;
     if (n_shots > 0)

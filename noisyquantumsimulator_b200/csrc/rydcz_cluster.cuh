@@ -411,12 +411,17 @@ RYDCZ_HD void cluster_step(const double* __restrict__ c, double kappa, double d0
 // transitions at common iterations, and a transition itself is only the header / segment bookkeeping.
 // `rec` = the point's coefficient records, `xc` = 3 N per-thread columns for the start vectors, `rc` =
 // 3 RING per-thread columns: the ring through which the records arrive (record k sits in slot k % RING,
-// copied asynchronously RING - 1 steps before step k reads it; every step commits one copy group).
+// copied asynchronously RING - 1 steps before step k reads it; every step commits one copy group), followed
+// by CL_LOOKAHEAD columns: the NEXT segment row and the NEXT slot header, copied asynchronously one transition
+// ahead, so that a transition reads shared memory instead of waiting for two dependent global loads (ncu,
+// round 2: those two loads were 12 % of the kernel's stall samples).
+constexpr int CL_LOOKAHEAD = 8;     // per-thread columns behind the record ring: segment row (4) + slot header (4)
 template <class Sys, int RING, class XC>
 RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const XC rc, const PointView pt,
                                  const double* __restrict__ seg, int n_seg, bool noisy,
                                  const double* __restrict__ rec, double& steps) {
   constexpr int N = Sys::N;
+  constexpr int LA = 3 * RING;      // first lookahead column
   static_assert((RING & (RING - 1)) == 0 && RING >= 2, "ring size");
   double c[Sys::NC], b1[N], b2[N];
   Sys::init(b1);
@@ -424,6 +429,7 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const XC rc, 
   bool priming = false;
   double kappa = 0.0, inv_gs = 0.0;
   const double* terms = rec;
+  const double* hdr_next = rec;       // header of the slot after the current one
 #define RYDCZ_RING_FETCH(kk)                                                                    \
   do {                                                                                          \
     const int kf_ = (kk);                                                                       \
@@ -435,25 +441,57 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const XC rc, 
     }                                                                                           \
     RYDCZ_ASYNC_COMMIT();                                                                       \
   } while (0)
+#define RYDCZ_LOOKAHEAD_ROW(ss)                                                                 \
+  do {                                                                                          \
+    const double* sg_ = seg + (long long)(ss) * SG_STRIDE;                                      \
+    RYDCZ_UNROLL                                                                                \
+    for (int q_ = 0; q_ < SG_STRIDE; ++q_) RYDCZ_ASYNC_COPY8(&rc[LA + q_], sg_ + q_);           \
+  } while (0)
+#define RYDCZ_LOOKAHEAD_HEADER(hh)                                                              \
+  do {                                                                                          \
+    RYDCZ_UNROLL                                                                                \
+    for (int q_ = 0; q_ < 4; ++q_) RYDCZ_ASYNC_COPY8(&rc[LA + 4 + q_], (hh) + q_);              \
+  } while (0)
+  // the first row and the first header: their latency is paid once per system, before the first transition
+  if (n_seg > 0) RYDCZ_LOOKAHEAD_ROW(0);
+  RYDCZ_LOOKAHEAD_HEADER(rec);
+  RYDCZ_ASYNC_COMMIT();
+  RYDCZ_ASYNC_WAIT(0);
   for (;;) {
     if (k < 0) {
       // b1 holds the state.  Next sub-step of this segment, or the next segment (and maybe the next slot).
       if (sub_left > 0) {
         --sub_left;
       } else {
-        double dt = 0.0;
+        // Row s sits in the lookahead columns (copied one transition ago: its copy group was waited for by the
+        // first step of the (sub)step that just ended).  Inactive rows (zero or NaN duration: the reference
+        // skips them) are rare and walked with direct loads.
+        double dt = 0.0, re = 0.0, im = 0.0, det = 0.0;
+        bool found = false;
+        if (s < n_seg) {
+          dt = rc[LA]; re = rc[LA + 1]; im = rc[LA + 2]; det = rc[LA + 3];
+          ++s;
+          found = segment_active(dt);
+        }
+        while (!found && s < n_seg) {
+          const double* sg = seg + (long long)s * SG_STRIDE;
+          dt = sg[SG_DT]; re = sg[SG_RE]; im = sg[SG_IM]; det = sg[SG_DET];
+          ++s;
+          found = segment_active(dt);
+        }
+        if (!found) break;
         double p[Sys::NP];
-        if (!next_segment<Sys>(p, pt, seg, n_seg, s, dt, noisy)) break;
+        segment_params<Sys>(p, pt, re, im, det, noisy);
         if (seg_left == 0) {
-          const double* hdr = K < 0 ? rec : terms + (K + 1) * CL_REC;
-          const int kn = (int)hdr[0];
+          const int kn = (int)rc[LA + 4];
           K = kn & 1023; nsub = kn >> 10;
-          kappa = hdr[1]; inv_gs = hdr[2]; seg_left = (int)hdr[3];
-          terms = hdr + CL_HDR;
-          RYDCZ_PREFETCH(terms + (K + 1) * CL_REC);              // the next slot's header
+          kappa = rc[LA + 5]; inv_gs = rc[LA + 6]; seg_left = (int)rc[LA + 7];
+          terms = hdr_next + CL_HDR;
+          hdr_next = terms + (K + 1) * CL_REC;
+          RYDCZ_LOOKAHEAD_HEADER(hdr_next);          // (past the last slot: the next point's region, or the pad)
         }
         --seg_left;
-        if (s < n_seg) RYDCZ_PREFETCH(seg + (long long)s * SG_STRIDE);   // the next segment row
+        if (s < n_seg) RYDCZ_LOOKAHEAD_ROW(s);       // these copies join the first ring group committed below
         if (!Sys::HERMITIAN) p[Sys::NP - 1] = 0.0;   // no spectral shift on this path
         Sys::coefs(p, c);
         RYDCZ_UNROLL
@@ -493,115 +531,11 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const XC rc, 
     k -= 2;
   }
 #undef RYDCZ_RING_FETCH
+#undef RYDCZ_LOOKAHEAD_ROW
+#undef RYDCZ_LOOKAHEAD_HEADER
   RYDCZ_ASYNC_WAIT(0);
   RYDCZ_UNROLL
   for (int i = 0; i < N; ++i) x[i] = b1[i];
-}
-
-// Two systems advanced in ONE loop (rho_11 and the |11><00| coherence of a noisy evaluation): they share
-// the slots, the coefficient records and every transition, so the records are read once, the bookkeeping
-// runs once, and the two independent dependency chains interleave in the FP64 pipe.
-template <class SysA, class SysB, int RING, class XC>
-RYDCZ_HD void run_pair_cluster(double (&xa)[SysA::N], double (&xb)[SysB::N], const XC xca, const XC xcb, const XC rc,
-                               const PointView pt, const double* __restrict__ seg, int n_seg, bool noisy,
-                               const double* __restrict__ rec, double& steps) {
-  constexpr int NA = SysA::N, NB = SysB::N;
-  static_assert((RING & (RING - 1)) == 0 && RING >= 2, "ring size");
-  double ca[SysA::NC], cb[SysB::NC], a1[NA], a2[NA], b1[NB], b2[NB];
-  SysA::init(a1);
-  SysB::init(b1);
-  int k = -1, K = -1, nsub = 1, sub_left = 0, seg_left = 0, s = 0;
-  bool priming = false;
-  double kappa = 0.0, inv_gs = 0.0;
-  const double* terms = rec;
-#define RYDCZ_RING_FETCH(kk)                                                                    \
-  do {                                                                                          \
-    const int kf_ = (kk);                                                                       \
-    if (kf_ >= 0 && kf_ <= K) {                                                                 \
-      const int sl_ = (kf_ & (RING - 1)) * 3;                                                   \
-      RYDCZ_ASYNC_COPY8(&rc[sl_], terms + kf_ * CL_REC);                                        \
-      RYDCZ_ASYNC_COPY8(&rc[sl_ + 1], terms + kf_ * CL_REC + 1);                                \
-      RYDCZ_ASYNC_COPY8(&rc[sl_ + 2], terms + kf_ * CL_REC + 2);                                \
-    }                                                                                           \
-    RYDCZ_ASYNC_COMMIT();                                                                       \
-  } while (0)
-  for (;;) {
-    if (k < 0) {
-      if (sub_left > 0) {
-        --sub_left;
-      } else {
-        double dt = 0.0;
-        int s2 = s;
-        {
-          double p[SysA::NP];
-          if (!next_segment<SysA>(p, pt, seg, n_seg, s, dt, noisy)) break;
-          SysA::coefs(p, ca);
-        }
-        {
-          double p[SysB::NP];
-          next_segment<SysB>(p, pt, seg, n_seg, s2, dt, noisy);
-          if (!SysB::HERMITIAN) p[SysB::NP - 1] = 0.0;   // no spectral shift on this path
-          SysB::coefs(p, cb);
-        }
-        if (seg_left == 0) {
-          const double* hdr = K < 0 ? rec : terms + (K + 1) * CL_REC;
-          const int kn = (int)hdr[0];
-          K = kn & 1023; nsub = kn >> 10;
-          kappa = hdr[1]; inv_gs = hdr[2]; seg_left = (int)hdr[3];
-          terms = hdr + CL_HDR;
-          RYDCZ_PREFETCH(terms + (K + 1) * CL_REC);              // the next slot's header
-        }
-        --seg_left;
-        if (s < n_seg) RYDCZ_PREFETCH(seg + (long long)s * SG_STRIDE);   // the next segment row
-        RYDCZ_UNROLL
-        for (int q = 0; q < SysA::NC; ++q) ca[q] *= inv_gs;
-        RYDCZ_UNROLL
-        for (int q = 0; q < SysB::NC; ++q) cb[q] *= inv_gs;
-        sub_left = nsub - 1;
-      }
-      steps += (double)(K + 1);
-      RYDCZ_UNROLL
-      for (int i = 0; i < NA; ++i) a2[i] = 0.0;
-      RYDCZ_UNROLL
-      for (int i = 0; i < NB; ++i) b2[i] = 0.0;
-      k = cluster_roundup(K + 2) - 1;
-      priming = true;
-      RYDCZ_UNROLL
-      for (int q = 0; q < RING - 1; ++q) RYDCZ_RING_FETCH(k - q);
-    }
-    double d0 = 0.0, d1 = 0.0, d2 = 0.0;
-    RYDCZ_ASYNC_WAIT(RING - 2);
-    if (k <= K) { const int sl = (k & (RING - 1)) * 3; d0 = rc[sl]; d1 = rc[sl + 1]; d2 = rc[sl + 2]; }
-    RYDCZ_RING_FETCH(k - (RING - 1));
-    cluster_step<SysA>(ca, kappa, d0, d1, d2, xca, a1, a2, priming);
-    cluster_step<SysB>(cb, kappa, d0, d1, d2, xcb, b1, b2, priming);
-    if (priming) {
-      RYDCZ_UNROLL
-      for (int i = 0; i < NA; ++i) { a1[i] = 0.0; a2[i] = 0.0; }
-      RYDCZ_UNROLL
-      for (int i = 0; i < NB; ++i) { b1[i] = 0.0; b2[i] = 0.0; }
-      priming = false;
-    }
-    d0 = 0.0; d1 = 0.0; d2 = 0.0;
-    RYDCZ_ASYNC_WAIT(RING - 2);
-    if (k - 1 <= K) { const int sl = ((k - 1) & (RING - 1)) * 3; d0 = rc[sl]; d1 = rc[sl + 1]; d2 = rc[sl + 2]; }
-    RYDCZ_RING_FETCH(k - 1 - (RING - 1));
-    if (k == 1) {
-      RYDCZ_UNROLL
-      for (int i = 0; i < NA; ++i) a2[i] *= 0.5;
-      RYDCZ_UNROLL
-      for (int i = 0; i < NB; ++i) b2[i] *= 0.5;
-    }
-    cluster_step<SysA>(ca, kappa, d0, d1, d2, xca, a2, a1, false);
-    cluster_step<SysB>(cb, kappa, d0, d1, d2, xcb, b2, b1, false);
-    k -= 2;
-  }
-#undef RYDCZ_RING_FETCH
-  RYDCZ_ASYNC_WAIT(0);
-  RYDCZ_UNROLL
-  for (int i = 0; i < NA; ++i) xa[i] = a1[i];
-  RYDCZ_UNROLL
-  for (int i = 0; i < NB; ++i) xb[i] = b1[i];
 }
 
 // One full gate evaluation on the clustered path (identical atoms; the |01> input has no blockade shift
@@ -610,11 +544,9 @@ RYDCZ_HD void run_pair_cluster(double (&xa)[SysA::N], double (&xb)[SysB::N], con
 // slots of the record ring: 8 for the 3-level model; 4 for the 4-level one, whose 63 start-vector columns
 // leave less shared memory at two CTAs per SM
 template <int D> struct ClusterRing { static constexpr int value = D == 3 ? 8 : 4; };
-// rho_11 and the coherence in one loop (run_pair_cluster: records read once, transitions shared, two
-// independent chains): measured on B200 it is SLOWER for the 3-level model, 2.44 ms against 2.22 ms per
-// 262,144 bang-bang candidates -- 255 registers with 45 doubles spilled and a 4-slot ring to stay at two
-// CTAs per SM (gpurun_out/cluster_ab_r01p.log).  Kept for a build with fewer live coefficients.
-template <int D> struct ClusterPair { static constexpr bool value = false; };
+// (rho_11 and the coherence advanced in ONE loop -- records read once, transitions shared, two independent
+// chains -- was measured on B200 in round 1: slower, 2.44 ms against 2.22 ms per 262,144 bang-bang candidates,
+// 255 registers with 45 doubles spilled; gpurun_out/cluster_ab_r01p.log.  The code was removed in round 2.)
 
 #define RYDCZ_DEFINE_EVALUATE_CLUSTER(D)                                                            \
   template <bool NOISY>                                                                             \
@@ -630,14 +562,7 @@ template <int D> struct ClusterPair { static constexpr bool value = false; };
     double xcoh[Sys_coh11s_d##D::N];                                                                \
     if (NOISY) {                                                                                    \
       double x[Sys_rho11s_d##D::N]; st = 0.0;                                                       \
-      if (ClusterPair<D>::value) {                                                                  \
-        const Col xcol2{xcol.base + (long long)3 * Sys_rho11s_d##D::N * xcol.stride, xcol.stride};  \
-        run_pair_cluster<Sys_rho11s_d##D, Sys_coh11s_d##D, ClusterRing<D>::value>(x, xcoh, xcol, xcol2, rcol, pt, \
-                                                                                   seg, n_seg, true, rec, st); \
-        flops += st * 2.0 * (3 * Sys_coh11s_d##D::NNZ + 4 * Sys_coh11s_d##D::N); steps += st;       \
-      } else {                                                                                      \
-        run_system_cluster<Sys_rho11s_d##D, ClusterRing<D>::value>(x, xcol, rcol, pt, seg, n_seg, true, rec, st); \
-      }                                                                                             \
+      run_system_cluster<Sys_rho11s_d##D, ClusterRing<D>::value>(x, xcol, rcol, pt, seg, n_seg, true, rec, st); \
       RYDCZ_RECONVERGE(pt.live);                                                                    \
       steps += st; flops += st * 2.0 * (3 * Sys_rho11s_d##D::NNZ + 4 * Sys_rho11s_d##D::N);         \
       p11 = x[RHO11S_POP_D##D];                                                                     \
@@ -649,12 +574,10 @@ template <int D> struct ClusterPair { static constexpr bool value = false; };
     }                                                                                               \
     {                                                                                               \
       double (&x)[Sys_coh11s_d##D::N] = xcoh;                                                       \
-      if (!(NOISY && ClusterPair<D>::value)) {                                                      \
-        st = 0.0;                                                                                   \
-        run_system_cluster<Sys_coh11s_d##D, ClusterRing<D>::value>(x, xcol, rcol, pt, seg, n_seg, NOISY, rec, st); \
-        RYDCZ_RECONVERGE(pt.live);                                                                  \
-        steps += st; flops += st * 2.0 * (3 * Sys_coh11s_d##D::NNZ + 4 * Sys_coh11s_d##D::N);       \
-      }                                                                                             \
+      st = 0.0;                                                                                     \
+      run_system_cluster<Sys_coh11s_d##D, ClusterRing<D>::value>(x, xcol, rcol, pt, seg, n_seg, NOISY, rec, st); \
+      RYDCZ_RECONVERGE(pt.live);                                                                    \
+      steps += st; flops += st * 2.0 * (3 * Sys_coh11s_d##D::NNZ + 4 * Sys_coh11s_d##D::N);         \
       c11r = x[COH11S_RE_D##D]; c11i = x[COH11S_IM_D##D];                                           \
       if (!NOISY) ryd = 1.0 - (c11r * c11r + c11i * c11i);                                          \
       if (!NOISY || states) {                                                                       \

@@ -147,10 +147,11 @@ struct PointView {
   double* base;
   int stride;
   unsigned live = 0xffffffffu;   // lanes of this warp that evaluate a point (device: reconvergence mask)
+  int sbase = PT_MAX_STRIDE;     // first scratch slot (kernels that only see 12-slot rows put it at PT_STRIDE)
   RYDCZ_HD double operator[](int k) const { return base[(long long)k * stride]; }
-  // slots PT_MAX_STRIDE .. PT_MAX_STRIDE+PT_SCRATCH-1 of the same column: per-thread scratch that
+  // slots sbase .. sbase+PT_SCRATCH-1 of the same column: per-thread scratch that
   // must survive the Chebyshev loop without holding registers (the cached Chebyshev interval)
-  RYDCZ_HD double& scratch(int k) const { return base[(long long)(PT_MAX_STRIDE + k) * stride]; }
+  RYDCZ_HD double& scratch(int k) const { return base[(long long)(sbase + k) * stride]; }
 };
 
 RYDCZ_HD int cheb_terms(double z) {
@@ -178,26 +179,13 @@ RYDCZ_HD bool same_detuning(double a, double b) {
   return Sys::DIM == 5 ? fabs(a - b) <= 1e-9 * fabs(b) || a == b : a == b;
 }
 
-// Advance `s` to the next segment with a non-zero duration and fill the generator's parameter
-// vector p for it; false when the schedule is exhausted.
+// The generator's parameter vector p for one active segment row (re, im = Omega; det = Delta).
 template <class Sys>
-RYDCZ_HD bool next_segment(double* __restrict__ p, const PointView pt, const double* __restrict__ seg, int n_seg,
-                           int& s, double& dt, bool noisy) {
-  bool found = false;
-  const double offa = pt[PT_OFF_A], offb = pt[PT_OFF_B];
-  while (s < n_seg && !found) {
-    const double* sg = seg + (long long)s * SG_STRIDE;
-    dt = sg[SG_DT];
-    if (dt != 0.0 && dt == dt) {
-      p[Sys::IDX_OM_RE] = sg[SG_RE];
-      p[Sys::IDX_OM_IM] = sg[SG_IM];
-      p[Sys::IDX_DET_A] = sg[SG_DET] + offa;
-      p[Sys::IDX_DET_B] = sg[SG_DET] + offb;   // same slot as DET_A for exchange-folded systems
-      found = true;
-    }
-    ++s;
-  }
-  if (!found) return false;
+RYDCZ_HD void segment_params(double* __restrict__ p, const PointView pt, double re, double im, double det, bool noisy) {
+  p[Sys::IDX_OM_RE] = re;
+  p[Sys::IDX_OM_IM] = im;
+  p[Sys::IDX_DET_A] = det + pt[PT_OFF_A];
+  p[Sys::IDX_DET_B] = det + pt[PT_OFF_B];   // same slot as DET_A for exchange-folded systems
   p[Sys::IDX_V] = pt[PT_V];
   p[Sys::IDX_DELTA1] = pt[PT_DELTA1];
   p[Sys::IDX_G_R1] = noisy ? pt[PT_G_R1] : 0.0;
@@ -228,7 +216,28 @@ RYDCZ_HD bool next_segment(double* __restrict__ p, const PointView pt, const dou
     p[kE0] = noisy ? pt[PT5_G_E0] : 0.0;
     p[kRl] = noisy ? pt[PT5_G_RL] : 0.0;
   }
-  return true;
+}
+
+// A segment row is active when its duration is neither zero nor NaN.
+RYDCZ_HD bool segment_active(double dt) { return dt != 0.0 && dt == dt; }
+
+// Advance `s` to the next segment with a non-zero duration and fill the generator's parameter
+// vector p for it; false when the schedule is exhausted.  The four fields of a row are loaded together
+// (one memory latency per row, not one for the duration and a second one for the rest).
+template <class Sys>
+RYDCZ_HD bool next_segment(double* __restrict__ p, const PointView pt, const double* __restrict__ seg, int n_seg,
+                           int& s, double& dt, bool noisy) {
+  while (s < n_seg) {
+    const double* sg = seg + (long long)s * SG_STRIDE;
+    const double d = sg[SG_DT], re = sg[SG_RE], im = sg[SG_IM], det = sg[SG_DET];
+    ++s;
+    if (segment_active(d)) {
+      dt = d;
+      segment_params<Sys>(p, pt, re, im, det, noisy);
+      return true;
+    }
+  }
+  return false;
 }
 
 // Run one system through all segments of a point.

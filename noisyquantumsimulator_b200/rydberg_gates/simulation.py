@@ -507,7 +507,6 @@ class BatchResult:
     attributes are None."""
 
     avg_fidelity: Optional[np.ndarray] = None
-    fidelities: Optional[np.ndarray] = None   # [B, 4] in the order 00, 01, 10, 11 (F11 includes the phase penalty)
     f11_population: Optional[np.ndarray] = None
     cz_phase_fidelity: Optional[np.ndarray] = None
     controlled_phase_rad: Optional[np.ndarray] = None
@@ -523,6 +522,18 @@ class BatchResult:
     shots: Optional[np.ndarray] = None
     _voo: Optional[np.ndarray] = None
     columns: Optional[Dict[str, np.ndarray]] = None
+    _fid: Optional[np.ndarray] = None
+
+    @property
+    def fidelities(self) -> Optional[np.ndarray]:
+        """[B, 4] in the order 00, 01, 10, 11 (F11 includes the phase penalty).  With ``outputs=`` the four columns
+        are stacked on first use (callers that only read ``avg_fidelity`` do not pay the pass over memory)."""
+        if self._fid is None:
+            if self.raw is not None:
+                self._fid = self.raw[:, 1:5]
+            elif self.columns is not None and all(k in self.columns for k in ("f00", "f01", "f10", "f11")):
+                self._fid = np.stack([self.columns[k] for k in ("f00", "f01", "f10", "f11")], axis=1)
+        return self._fid
 
     def column(self, name: str) -> np.ndarray:
         """One result column by its ``outputs`` name, whichever way the batch was returned."""
@@ -643,9 +654,7 @@ def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, se
             columns = {o: (np.array(o_cm[j]) if copy else o_cm[j]) for j, o in enumerate(o_names)}
             columns.update({o: (np.array(s_cm[j]) if copy else s_cm[j]) for j, o in enumerate(s_names)})
             g = columns.get
-            fid = np.stack([g("f00"), g("f01"), g("f10"), g("f11")], axis=1) if all(
-                k in columns for k in ("f00", "f01", "f10", "f11")) else None
-            return BatchResult(avg_fidelity=g("avg_fidelity"), fidelities=fid, f11_population=g("f11_population"),
+            return BatchResult(avg_fidelity=g("avg_fidelity"), f11_population=g("f11_population"),
                                cz_phase_fidelity=g("cz_phase_fidelity"), controlled_phase_rad=g("controlled_phase_rad"),
                                phase_error_from_pi_rad=g("phase_error_from_pi_rad"),
                                loss_probability=g("loss_probability"), rydberg_residual=g("rydberg_residual"),
@@ -669,7 +678,7 @@ def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, se
         tau_total, Omega, voo = plan.scalars["tau_total"], plan.scalars["Omega"], plan.scalars["V_over_Omega"]
         V = plan.scalars["V"]
     return BatchResult(
-        avg_fidelity=out[:, 0], fidelities=out[:, 1:5], f11_population=out[:, 5], cz_phase_fidelity=out[:, 6],
+        avg_fidelity=out[:, 0], f11_population=out[:, 5], cz_phase_fidelity=out[:, 6],
         controlled_phase_rad=out[:, 7], phase_error_from_pi_rad=out[:, 8], loss_probability=out[:, 12],
         rydberg_residual=out[:, 13], tau_total=tau_total, Omega=Omega, V=V, raw=out, plan=plan,
         states=states, shots=shots, _voo=voo)

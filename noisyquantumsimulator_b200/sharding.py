@@ -170,9 +170,7 @@ def simulate_sharded(protocol: str, B: int, *, rank: int = 0, world: int = 1, gr
     for j, name in enumerate(names):
         columns[name] = np.concatenate([host[r, j, :max(0, min(B, (r + 1) * per) - r * per)] for r in range(world)])
     g = columns.get
-    fid = np.stack([g("f00"), g("f01"), g("f10"), g("f11")], axis=1) if all(
-        k in columns for k in ("f00", "f01", "f10", "f11")) else None
-    res = sim.BatchResult(avg_fidelity=g("avg_fidelity"), fidelities=fid, f11_population=g("f11_population"),
+    res = sim.BatchResult(avg_fidelity=g("avg_fidelity"), f11_population=g("f11_population"),
                           cz_phase_fidelity=g("cz_phase_fidelity"), controlled_phase_rad=g("controlled_phase_rad"),
                           phase_error_from_pi_rad=g("phase_error_from_pi_rad"), loss_probability=g("loss_probability"),
                           rydberg_residual=g("rydberg_residual"), tau_total=g("tau_total"), Omega=g("Omega"), V=g("V"),
