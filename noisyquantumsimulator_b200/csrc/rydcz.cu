@@ -110,20 +110,20 @@ __device__ __forceinline__ unsigned work_bin(double w) {
   return (unsigned)(b < 0 ? 0 : (b > kWorkBins - 1 ? kWorkBins - 1 : b));
 }
 
-// one atomic per distinct key among the active lanes of a warp
-__device__ __forceinline__ void warp_count(unsigned* __restrict__ hist, unsigned key, bool valid) {
-  const unsigned m = __match_any_sync(0xffffffffu, valid ? key : 0xffffffffu);
-  if (valid && (threadIdx.x & 31) == (unsigned)(__ffs(m) - 1)) atomicAdd(hist + key, (unsigned)__popc(m));
-}
-// position for this lane in the bin of `key`: one atomic per distinct key, lanes of a key take consecutive slots
-__device__ __forceinline__ unsigned warp_claim(unsigned* __restrict__ cursor, unsigned key, bool valid) {
-  const unsigned lane = threadIdx.x & 31;
-  const unsigned m = __match_any_sync(0xffffffffu, valid ? key : 0xffffffffu);
-  const int leader = __ffs(m) - 1;
-  unsigned base = 0;
-  if (valid && lane == (unsigned)leader) base = atomicAdd(cursor + key, (unsigned)__popc(m));
-  base = __shfl_sync(0xffffffffu, base, leader);
-  return base + (unsigned)__popc(m & ((1u << lane) - 1u));
+// Block-level counting: every CTA counts its keys in shared memory and touches the global counters once per
+// non-empty bin (262,144 points x 6 keys straight onto ~100 global addresses serialise in the L2 atomic units:
+// measured 0.2 ms per pass; per-CTA shared-memory histograms bring that to ~1/30 of the global atomics).
+constexpr int kPlanBlock = 256;
+struct PlanShared {
+  unsigned pts[kBins];        // points per bin in this CTA; later: running rank inside the CTA's range
+  unsigned pbase[kBins];      // scatter: first global position of this CTA's points of the bin
+  unsigned tsk[kTaskBins];
+  unsigned tbase[kTaskBins];
+};
+__device__ __forceinline__ void plan_shared_clear(PlanShared& sh, bool with_base) {
+  for (int b = threadIdx.x; b < kBins; b += kPlanBlock) { sh.pts[b] = 0u; if (with_base) sh.pbase[b] = 0u; }
+  if (threadIdx.x < kTaskBins) { sh.tsk[threadIdx.x] = 0u; sh.tbase[threadIdx.x] = 0u; }
+  __syncthreads();
 }
 
 // Per point: its kind and its bin (kind group in the top bits, work bin below) so that a warp holds
@@ -135,8 +135,11 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
                             int max_seg, int seg_div, int shots, int noisy, int cluster_mode, uint32_t* __restrict__ keys,
                             uint32_t* __restrict__ idx, uint8_t* __restrict__ kind,
                             uint32_t* __restrict__ task_key, uint32_t* __restrict__ task_val,
+                            double* __restrict__ task_hdr,
                             double* __restrict__ scratch, unsigned long long* __restrict__ counters,
                             unsigned* __restrict__ repeat_count, PlanCounts* __restrict__ plan) {
+  __shared__ PlanShared sh;
+  if (plan) plan_shared_clear(sh, false);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool clustered = false, repeated = false;
   int records_planned = 0;
@@ -167,7 +170,8 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
       // the slot headers are written on the way (harmless if the point stays on the plain path); unequal atoms
       // (3-level model only) take the two-atom bounds and the general kernel
       const int records = cluster_plan<D>(pt, sg, ns, noisy != 0, sym, cost, slot_K, slot_off,
-                                          scratch + i * (int64_t)CL_STRIDE);
+                                          scratch + i * (int64_t)CL_STRIDE,
+                                          task_hdr ? task_hdr + i * (int64_t)(CL_MAX_SLOTS * 4) : nullptr);
       if (records > 0 && records <= CL_RECORDS && (cluster_mode == 2 || cost < 0.8 * w)) {
         clustered = true; group = sym ? GROUP_CLUSTER : GROUP_CLUSTER_GENERAL; w = sym ? cost : 2.0 * cost; records_planned = records;
       }
@@ -188,12 +192,17 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
     idx[i] = (uint32_t)i;
   }
   if (plan) {
-    warp_count(plan->hist, bin, i < n_points);
-    if (task_key) {
+    if (i < n_points) {
+      atomicAdd(&sh.pts[bin], 1u);
+      if (task_key && clustered) {
 #pragma unroll
-      for (int q = 0; q < CL_MAX_SLOTS; ++q)
-        warp_count(plan->thist, (unsigned)slot_K[q], i < n_points && clustered && slot_K[q] > 0);
+        for (int q = 0; q < CL_MAX_SLOTS; ++q)
+          if (slot_K[q] > 0) atomicAdd(&sh.tsk[slot_K[q]], 1u);
+      }
     }
+    __syncthreads();
+    for (int b = threadIdx.x; b < kBins; b += kPlanBlock) { const unsigned c = sh.pts[b]; if (c) atomicAdd(plan->hist + b, c); }
+    if (threadIdx.x < kTaskBins) { const unsigned c = sh.tsk[threadIdx.x]; if (c) atomicAdd(plan->thist + threadIdx.x, c); }
   }
   const unsigned m = __ballot_sync(0xffffffffu, clustered);
   const unsigned rsum = __reduce_add_sync(0xffffffffu, (unsigned)records_planned);
@@ -261,21 +270,49 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(PlanCounts* __restrict_
 }
 
 // order[position] = point, task_sorted[position] = record index of the task's slot header
-__global__ void plan_scatter_kernel(int64_t n_points, const uint32_t* __restrict__ keys, uint32_t* __restrict__ order,
-                                    const uint32_t* __restrict__ task_key, const uint32_t* __restrict__ task_val,
-                                    uint32_t* __restrict__ task_sorted, PlanCounts* __restrict__ plan) {
+// ... and task_hdr_sorted[position] = (K + 1024 nsub, h, Vc, rho) of that slot, dense and in task order
+__global__ void __launch_bounds__(kPlanBlock)
+plan_scatter_kernel(int64_t n_points, const uint32_t* __restrict__ keys, uint32_t* __restrict__ order,
+                    const uint32_t* __restrict__ task_key, const uint32_t* __restrict__ task_val,
+                    uint32_t* __restrict__ task_sorted, const double* __restrict__ task_hdr,
+                    double* __restrict__ task_hdr_sorted, PlanCounts* __restrict__ plan) {
+  __shared__ PlanShared sh;
+  plan_shared_clear(sh, true);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool in = i < n_points;
   const unsigned bin = in ? keys[i] : 0u;
-  const unsigned pos = warp_claim(plan->hist, bin, in);
-  if (in) order[pos] = (uint32_t)i;
-  if (task_key) {
+  unsigned K[CL_MAX_SLOTS];
+#pragma unroll
+  for (int q = 0; q < CL_MAX_SLOTS; ++q) K[q] = (in && task_key) ? task_key[i * CL_MAX_SLOTS + q] : 0u;
+  // 1. this CTA's counts
+  if (in) {
+    atomicAdd(&sh.pts[bin], 1u);
+#pragma unroll
+    for (int q = 0; q < CL_MAX_SLOTS; ++q) if (K[q] > 0u) atomicAdd(&sh.tsk[K[q]], 1u);
+  }
+  __syncthreads();
+  // 2. one range per non-empty bin from the global cursors
+  for (int b = threadIdx.x; b < kBins; b += kPlanBlock) {
+    const unsigned c = sh.pts[b];
+    if (c) { sh.pbase[b] = atomicAdd(plan->hist + b, c); sh.pts[b] = 0u; }
+  }
+  if (threadIdx.x < kTaskBins) {
+    const unsigned c = sh.tsk[threadIdx.x];
+    if (c) { sh.tbase[threadIdx.x] = atomicAdd(plan->thist + threadIdx.x, c); sh.tsk[threadIdx.x] = 0u; }
+  }
+  __syncthreads();
+  // 3. ranks inside the ranges
+  if (in) {
+    order[sh.pbase[bin] + atomicAdd(&sh.pts[bin], 1u)] = (uint32_t)i;
 #pragma unroll
     for (int q = 0; q < CL_MAX_SLOTS; ++q) {
-      const unsigned K = in ? task_key[i * CL_MAX_SLOTS + q] : 0u;
-      const bool have = in && K > 0u;
-      const unsigned tp = warp_claim(plan->thist, K, have);
-      if (have) task_sorted[tp] = task_val[i * CL_MAX_SLOTS + q];
+      if (K[q] > 0u) {
+        const unsigned tp = sh.tbase[K[q]] + atomicAdd(&sh.tsk[K[q]], 1u);
+        task_sorted[tp] = task_val[i * CL_MAX_SLOTS + q];
+        const double2* src = reinterpret_cast<const double2*>(task_hdr + (i * CL_MAX_SLOTS + q) * 4);
+        double2* dst = reinterpret_cast<double2*>(task_hdr_sorted + (int64_t)tp * 4);
+        dst[0] = src[0]; dst[1] = src[1];
+      }
     }
   }
 }
@@ -289,15 +326,23 @@ constexpr int kCoefTasksPerCta = kBlock / kCoefLanes;
 // grid is sized for the largest possible task count and CTAs beyond the real one leave at once.
 __global__ void __launch_bounds__(kBlock, 4)
 cluster_coef_kernel(const PlanCounts* __restrict__ plan, const uint32_t* __restrict__ task_sorted,
-                    double* __restrict__ scratch) {
+                    const double* __restrict__ task_hdr_sorted, double* __restrict__ scratch) {
   __shared__ double s_a[6 * CL_HALF_MAX * kCoefTasksPerCta];
   const int t_in_cta = threadIdx.x / kCoefLanes, m = threadIdx.x % kCoefLanes;
   const int64_t g = (int64_t)blockIdx.x * kCoefTasksPerCta + t_in_cta;
   // the four lanes of a task take the same branch; a warp whose tasks are all absent leaves together
   const bool have = g < (int64_t)plan->n_tasks;
   if (!__any_sync(0xffffffffu, have)) return;
-  if (have) cluster_coefficients(scratch + (int64_t)task_sorted[g] * CL_REC, s_a + t_in_cta, kCoefTasksPerCta, m, kCoefLanes);
-  else __syncwarp();     // pairs with the group barrier inside cluster_coefficients
+  if (have) {
+    // (K, h, Vc, rho) from the dense task list: one coalesced 32-byte read per task instead of a scattered read of
+    // the slot header in the records (ncu, round 2: that read was 17 % of this kernel's stall samples)
+    const double2 h0 = reinterpret_cast<const double2*>(task_hdr_sorted + g * 4)[0];
+    const double2 h1 = reinterpret_cast<const double2*>(task_hdr_sorted + g * 4)[1];
+    cluster_coefficients_of((int)h0.x & 1023, h0.y, h1.x, h1.y,
+                            scratch + (int64_t)task_sorted[g] * CL_REC + CL_HDR, s_a + t_in_cta, kCoefTasksPerCta, m, kCoefLanes);
+  } else {
+    __syncwarp();     // pairs with the group barrier inside cluster_coefficients
+  }
 }
 
 // SYM = true handles the points whose two atoms see identical parameters (exchange-folded
@@ -757,6 +802,7 @@ struct rydcz_ctx {
   uint8_t* kind = nullptr;
   size_t order_cap = 0;
   uint32_t* task = nullptr; size_t task_cap = 0;        // 4 arrays of CL_MAX_SLOTS * n: keys, sorted keys, values, sorted values
+  double* task_hdr = nullptr; size_t task_hdr_cap = 0;  // 2 arrays of CL_MAX_SLOTS * n x 4 doubles: slot headers, dense
   // clustered-spectrum path: 0 = off, 1 = where the planner finds it cheaper, 2 = wherever eligible
   int cluster_mode = 1;
   double* cl_scratch = nullptr; size_t cl_cap = 0;      // coefficient records, CL_STRIDE doubles per point
@@ -799,6 +845,7 @@ struct SortScratch {
   double* cl;          // coefficient records of these points (nullptr: clustered path unavailable)
   uint32_t* task;      // coefficient task list of these points: [4][task_n] (keys, sorted keys, values, sorted values)
   int64_t task_n;      // stride of the four task arrays
+  double* task_hdr;    // [2][task_n][4]: (K + 1024 nsub, h, Vc, rho) per (point, slot), then the same in task order
   double* rp;          // propagators of the repeated-segment path for these points (stride = their number)
   unsigned* rp_count;  // device counter of the points that take it
   PlanCounts* plan;    // bin counts / cursors / kind ranges of this work order
@@ -905,6 +952,7 @@ static int order_reserve(rydcz_ctx* ctx, int64_t n, bool want_cluster = true) {
       // says so (rydcz_call_flags: RYDCZ_FLAG_NO_CLUSTER_SCRATCH)
       if (grow(ctx, (void**)&ctx->cl_scratch, &ctx->cl_cap, bytes) ||
           grow(ctx, (void**)&ctx->task, &ctx->task_cap, (size_t)n * CL_MAX_SLOTS * 4 * sizeof(uint32_t)) ||
+          grow(ctx, (void**)&ctx->task_hdr, &ctx->task_hdr_cap, (size_t)n * CL_MAX_SLOTS * 8 * sizeof(double)) ||
           grow(ctx, (void**)&ctx->rp_E, &ctx->rp_cap, (size_t)n * RepeatLayout<3>::STRIDE * sizeof(double))) {
         cudaGetLastError();
         ctx->err.clear();
@@ -918,13 +966,15 @@ static int order_reserve(rydcz_ctx* ctx, int64_t n, bool want_cluster = true) {
 }
 
 static SortScratch context_scratch(rydcz_ctx* ctx, int64_t n, int64_t offset = 0, int counter_slot = 0) {
-  const bool cl = ctx->cluster_mode && ctx->cl_scratch && ctx->task &&
+  const bool cl = ctx->cluster_mode && ctx->cl_scratch && ctx->task && ctx->task_hdr &&
+                  (size_t)(offset + n) * CL_MAX_SLOTS * 8 * sizeof(double) <= ctx->task_hdr_cap &&
                   (size_t)(offset + n) * CL_STRIDE * sizeof(double) + 256 <= ctx->cl_cap &&
                   (size_t)(offset + n) * CL_MAX_SLOTS * 4 * sizeof(uint32_t) <= ctx->task_cap;
   // the four task arrays of a sub-range are laid out back to back inside its own span of the buffer
   return SortScratch{ctx->keys + offset, ctx->keys_sorted + offset, ctx->idx + offset, ctx->idx_sorted + offset,
                      ctx->kind + offset, cl ? ctx->cl_scratch + offset * (int64_t)CL_STRIDE : nullptr,
                      cl ? ctx->task + offset * (int64_t)CL_MAX_SLOTS * 4 : nullptr, n * (int64_t)CL_MAX_SLOTS,
+                     cl ? ctx->task_hdr + offset * (int64_t)CL_MAX_SLOTS * 8 : nullptr,
                      (cl && ctx->rp_E && (size_t)(offset + n) * RepeatLayout<3>::STRIDE * sizeof(double) <= ctx->rp_cap)
                          ? ctx->rp_E + offset * (int64_t)RepeatLayout<3>::STRIDE : nullptr,
                      ctx->rp_count + counter_slot, ctx->plan_counts + counter_slot};
@@ -943,9 +993,11 @@ static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const do
   uint32_t* tk = mode ? sc.task : nullptr;                     // term count of every (point, slot); 0 = no such slot
   uint32_t* tks = mode ? sc.task + sc.task_n : nullptr;        // tasks binned by term count: record index of the slot header
   uint32_t* tv = mode ? sc.task + 2 * sc.task_n : nullptr;     // record index of every (point, slot)
+  double* th = mode ? sc.task_hdr : nullptr;                   // slot headers, dense, per (point, slot)
+  double* ths = mode ? sc.task_hdr + sc.task_n * 4 : nullptr;  // ... in task order
   CK(cudaMemsetAsync(sc.plan, 0, sizeof(PlanCounts), st));
-  plan_kernel<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, d_points, d_segs, d_n_seg, max_seg, seg_div, shots, noisy,
-                                                              mode, sc.keys, sc.idx, sc.kind, tk, tv, sc.cl,
+  plan_kernel<D><<<(unsigned)((n + kPlanBlock - 1) / kPlanBlock), kPlanBlock, 0, st>>>(n, d_points, d_segs, d_n_seg, max_seg, seg_div, shots, noisy,
+                                                              mode, sc.keys, sc.idx, sc.kind, tk, tv, th, sc.cl,
                                                               ctx->cl_counters, rpc, sc.plan);
   CK(cudaGetLastError());
   ctx->launches++;
@@ -953,7 +1005,7 @@ static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const do
   if (sorted || mode) {
     // counts -> offsets -> order (and the coefficient task list): no library sort
     plan_scan_kernel<<<1, 1024, 0, st>>>(sc.plan);
-    plan_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, sc.keys, sc.idx_sorted, tk, tv, tks, sc.plan);
+    plan_scatter_kernel<<<(unsigned)((n + kPlanBlock - 1) / kPlanBlock), kPlanBlock, 0, st>>>(n, sc.keys, sc.idx_sorted, tk, tv, tks, th, ths, sc.plan);
     CK(cudaGetLastError());
     ctx->launches += 2;
     if (sorted) *order = sc.idx_sorted;
@@ -962,7 +1014,7 @@ static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const do
     const int64_t max_tasks = n * CL_MAX_SLOTS;
     CK(cudaEventRecord(ctx->evc0, st));
     cluster_coef_kernel<<<(unsigned)((max_tasks + kCoefTasksPerCta - 1) / kCoefTasksPerCta), kBlock, 0, st>>>(
-        sc.plan, tks, sc.cl);
+        sc.plan, tks, ths, sc.cl);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->evc1, st));
     ctx->coef_timed = true;
@@ -1088,7 +1140,7 @@ void rydcz_destroy(rydcz_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->keys); cudaFree(ctx->keys_sorted); cudaFree(ctx->idx); cudaFree(ctx->idx_sorted);
-  cudaFree(ctx->kind); cudaFree(ctx->cl_scratch); cudaFree(ctx->cl_counters); cudaFree(ctx->task);
+  cudaFree(ctx->kind); cudaFree(ctx->cl_scratch); cudaFree(ctx->cl_counters); cudaFree(ctx->task); cudaFree(ctx->task_hdr);
   cudaFree(ctx->rp_E); cudaFree(ctx->rp_count); cudaFree(ctx->shot_rows); cudaFree(ctx->sel_out); cudaFree(ctx->sel_sc);
   if (ctx->busy) cudaEventDestroy(ctx->busy);
   if (ctx->evc0) cudaEventDestroy(ctx->evc0);

@@ -209,10 +209,12 @@ RYDCZ_HD void cluster_write_header(const ClusterSlot& sl, double* __restrict__ r
 // Records the clustered path needs for a point (0 = not eligible) and its cost in plain Chebyshev terms.
 // With `rec` the slot headers are written on the way (at the positions the evaluator will find them);
 // slot_K / slot_off receive the term count and the record offset of every slot.
+// `dense` (optional, 4 doubles per slot): what cluster_coefficients needs of each header -- K + 1024 nsub, h, Vc,
+// rho -- in a compact array, so that the coefficient kernel does not start with a scattered read of the records.
 template <int D>
 RYDCZ_HD int cluster_plan(const double* pt, const double* seg, int n_seg, bool noisy, bool sym, double& cost,
                           int* __restrict__ slot_K = nullptr, int* __restrict__ slot_off = nullptr,
-                          double* __restrict__ rec = nullptr) {
+                          double* __restrict__ rec = nullptr, double* __restrict__ dense = nullptr) {
   ClusterWalker<D> w(pt, seg, n_seg, noisy, sym);
   ClusterSlot sl;
   int records = 0, slots = 0;
@@ -225,6 +227,10 @@ RYDCZ_HD int cluster_plan(const double* pt, const double* seg, int n_seg, bool n
     if (slot_K) slot_K[slots - 1] = sl.K;
     if (slot_off) slot_off[slots - 1] = records;
     if (rec) cluster_write_header(sl, rec + (long long)records * CL_REC);
+    if (dense) {
+      double* d = dense + (slots - 1) * 4;
+      d[0] = (double)(sl.K + 1024 * sl.nsub); d[1] = sl.h; d[2] = sl.g.Vc; d[3] = sl.g.rho;
+    }
     records += sl.K + 3;
     cost += (double)sl.count * (double)sl.nsub * (CL_STEP_COST * (double)cluster_roundup(sl.K + 2) + CL_SUBSTEP_COST) +
             CL_SLOT_COST;
@@ -270,11 +276,17 @@ RYDCZ_HD double cluster_root_y(double c) {
 #define RYDCZ_GROUP_SYNC() ((void)0)
 #endif
 #endif
+RYDCZ_HD void cluster_coefficients_of(int K, double h, double Vc, double rho, double* __restrict__ out,
+                                      double* __restrict__ A, int a_stride, int m, int G);
+// ... from the slot header in the records themselves (the host harness)
 RYDCZ_HD void cluster_coefficients(double* __restrict__ rec, double* __restrict__ A, int a_stride, int m, int G) {
-  const int K = (int)rec[0] & 1023, N = K + 2, half = N / 2;
-  const double h = rec[4], Vc = rec[5], rho = rec[6];
+  cluster_coefficients_of((int)rec[0] & 1023, rec[4], rec[5], rec[6], rec + CL_HDR, A, a_stride, m, G);
+}
+// ... from (K, h, Vc, rho) handed over directly; `out` = the K + 1 records behind the slot header
+RYDCZ_HD void cluster_coefficients_of(int K, double h, double Vc, double rho, double* __restrict__ out,
+                                      double* __restrict__ A, int a_stride, int m, int G) {
+  const int N = K + 2, half = N / 2;
   const double gs = cbrt(0.5 * rho);
-  double* __restrict__ out = rec + CL_HDR;
 #define RYDCZ_A(v, n) A[((v) * CL_HALF_MAX + (n)) * a_stride]
   const double rhat = rho / (Vc * Vc * Vc);
   const double hv = h * Vc, iVc = 1.0 / Vc;

@@ -273,6 +273,14 @@ RYDCZ_HD void run_system(double (&x)[Sys::N], const PointView pt,
   int sub_left = 0;  // further sub-steps of the current segment
   int s = 0;         // next segment row to load
   bool active = false;
+  // Small systems (the single-atom inputs, the coherences) keep the NEXT segment row in registers, loaded one
+  // transition ahead: their segments are short, and the two dependent global loads at every transition showed
+  // up as long-scoreboard stalls once the clustered path had made everything else cheap (ncu, round 2).
+  constexpr bool PREFETCH = Sys::N <= 10;
+  double nrow[SG_STRIDE] = {0.0, 0.0, 0.0, 0.0};
+  if (PREFETCH && n_seg > 0) {
+    nrow[0] = seg[SG_DT]; nrow[1] = seg[SG_RE]; nrow[2] = seg[SG_IM]; nrow[3] = seg[SG_DET];
+  }
   for (;;) {
     if (k < 2) {
       if (active) {
@@ -298,7 +306,25 @@ RYDCZ_HD void run_system(double (&x)[Sys::N], const PointView pt,
       } else {
         double dt = 0.0;
         double p[Sys::NP];          // rebuilt per segment so it is not live across the hot loop
-        if (!next_segment<Sys>(p, pt, seg, n_seg, s, dt, noisy)) break;
+        if (PREFETCH) {
+          // the row was loaded one transition ago; the loads for the row after it are issued now and are
+          // consumed at the next transition (small systems only: eight registers live across the hot loop)
+          bool found = false;
+          double re = 0.0, im = 0.0, det = 0.0;
+          while (s < n_seg && !found) {
+            dt = nrow[0]; re = nrow[1]; im = nrow[2]; det = nrow[3];
+            ++s;
+            if (s < n_seg) {
+              const double* sg = seg + (long long)s * SG_STRIDE;
+              nrow[0] = sg[SG_DT]; nrow[1] = sg[SG_RE]; nrow[2] = sg[SG_IM]; nrow[3] = sg[SG_DET];
+            }
+            found = segment_active(dt);
+          }
+          if (!found) break;
+          segment_params<Sys>(p, pt, re, im, det, noisy);
+        } else if (!next_segment<Sys>(p, pt, seg, n_seg, s, dt, noisy)) {
+          break;
+        }
         const double sgn = dt < 0.0 ? -1.0 : 1.0;
         const double adt = fabs(dt);
         // Chebyshev interval.  The Gershgorin bound is taken with |Re Ω| = |Im Ω| = |Ω| (valid for
