@@ -300,6 +300,8 @@ class Bench:
         if world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
         self.ev = get_evaluator(local_rank)        # the evaluator the public API uses on this device
+        # one process per GPU on a multi-socket host: keep this rank's threads and pinned staging next to its GPU
+        self.bound_cpus = self.ev.bind_host_to_gpu() if world > 1 else 0
         self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)   # > 126 MB L2
 
     def barrier(self):
@@ -587,6 +589,7 @@ def run_ours(args, rank, world, local_rank):
                                        else "single-interval Chebyshev"),
                        "segments": N_SEG, "apparatus": "medium (RG/optimize_cz_gate.py:196-213), full noise",
                        "l2": "256 MiB flush write between timed iterations", "parallelism": f"shard{world}",
+                       "host_cpus_bound_to_gpu": b.bound_cpus,
                        "mean_fidelity": float(out_np[:, 0].mean())},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

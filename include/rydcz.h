@@ -205,6 +205,14 @@ int rydcz_simulate_host_cols(rydcz_ctx* ctx, const double* h_model, int64_t n_po
                              const double* const* h_cols, const int64_t* col_stride, const double* h_const,
                              int n_shots, uint64_t seed, double* h_out, double* h_scalars, double* h_states);
 int rydcz_set_chunk(rydcz_ctx* ctx, int64_t points_per_chunk);
+/* Host threads that gather the varying columns into the page-locked staging (the caller's thread included).
+ * Default: (CPUs this process may run on) / LOCAL_WORLD_SIZE - 1, clamped to 1..4 -- one process per GPU must not
+ * oversubscribe the host; env RYDCZ_PACK_THREADS overrides.  The workers sleep between calls. */
+int rydcz_set_pack_threads(rydcz_ctx* ctx, int threads);
+/* Bind the calling thread, and threads created by it afterwards, to the CPUs local to the context's GPU
+ * (/sys/bus/pci/devices/<gpu>/local_cpulist): call once per rank, right after rydcz_create, on multi-socket hosts.
+ * *n_cpus = CPUs in the new mask, 0 if the topology could not be read (then nothing changes). */
+int rydcz_bind_host_to_gpu(rydcz_ctx* ctx, int* n_cpus);
 /* The same call returning only the result columns the caller reads, COLUMN-MAJOR: h_out_cm[j * n_points + i] =
  * out[i][out_slots[j]] (enum rydcz_out_slot), h_scalars_cm[j * n_points + i] = scalars[i][scalar_slots[j]].
  * The device gathers the columns, so D2H traffic is 8 (n_out + n_scalars) bytes per point instead of 192

@@ -58,6 +58,8 @@ _SIGNATURES = {
     "rydcz_simulate_host_select": (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp, _vp, C.c_int, C.c_uint64, _vp, C.c_int,
                                              _vp, _vp, C.c_int, _vp]),
     "rydcz_set_chunk": (C.c_int, [_vp, C.c_int64]),
+    "rydcz_set_pack_threads": (C.c_int, [_vp, C.c_int]),
+    "rydcz_bind_host_to_gpu": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "rydcz_point_status": (C.c_int, [_vp, C.c_int64, _vp]),
     "rydcz_call_flags": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
     "rydcz_pinned_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),

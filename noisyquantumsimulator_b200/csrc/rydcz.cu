@@ -22,7 +22,13 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
+#include <vector>
+#include <sched.h>
 
 #include "../../include/rydcz.h"
 #include "rydcz_core.cuh"
@@ -779,6 +785,69 @@ __global__ void __launch_bounds__(kBlock, 2) matvec_peak_kernel(double* out, int
 // ======================================================================= C ABI
 using namespace rydcz;
 
+// A small persistent pool for the host-side column gather of rydcz_simulate_host_cols.  Workers sleep on a
+// condition variable between jobs (an OpenMP team spin-waits, which hurts when eight ranks share the host cores).
+class PackPool {
+ public:
+  explicit PackPool(int workers) {
+    for (int w = 0; w < workers; ++w) threads_.emplace_back([this] { loop(); });
+  }
+  ~PackPool() {
+    { std::lock_guard<std::mutex> l(m_); stop_ = true; }
+    cv_.notify_all();
+    for (auto& t : threads_) t.join();
+  }
+  int workers() const { return (int)threads_.size(); }
+  // run fn(j) for j in [0, n): the caller takes part; returns when all are done
+  void run(int n, const std::function<void(int)>& fn) {
+    if (n <= 0) return;
+    {
+      std::lock_guard<std::mutex> l(m_);
+      fn_ = &fn; next_ = 0; n_ = n; pending_ = n; ++epoch_;
+    }
+    cv_.notify_all();
+    work();
+    std::unique_lock<std::mutex> l(m_);
+    done_.wait(l, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+  }
+
+ private:
+  void work() {
+    for (;;) {
+      int j;
+      const std::function<void(int)>* fn;
+      {
+        std::lock_guard<std::mutex> l(m_);
+        if (!fn_ || next_ >= n_) return;
+        j = next_++; fn = fn_;
+      }
+      (*fn)(j);
+      std::lock_guard<std::mutex> l(m_);
+      if (--pending_ == 0) done_.notify_all();
+    }
+  }
+  void loop() {
+    unsigned long long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return stop_ || epoch_ != seen; });
+        if (stop_) return;
+        seen = epoch_;
+      }
+      work();
+    }
+  }
+  std::vector<std::thread> threads_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  int next_ = 0, n_ = 0, pending_ = 0;
+  unsigned long long epoch_ = 0;
+  bool stop_ = false;
+};
+
 struct rydcz_ctx {
   int device = 0;
   int sm_count = 148;
@@ -834,7 +903,8 @@ struct rydcz_ctx {
   };
   static constexpr int kLanes = 3;
   Lane lane[kLanes];
-  int pack_threads = 1;                           // host threads that gather the columns (env RYDCZ_PACK_THREADS)
+  int pack_threads = 1;                           // host threads that gather the columns (rydcz_set_pack_threads)
+  PackPool* pool = nullptr;
   int64_t chunk = 32768;                          // points per pipeline chunk (profiles/r01_e2e_chunk_sweep_v9.txt)
 };
 
@@ -1119,9 +1189,18 @@ int rydcz_create(int device, rydcz_ctx** out) {
   if (device < 0 || device >= count) { g_create_error = "device index out of range"; return 2; }
   rydcz_ctx* ctx = new rydcz_ctx();
   ctx->device = device;
-  if (const char* e = getenv("RYDCZ_PACK_THREADS")) {
-    const int t = atoi(e);
-    ctx->pack_threads = t < 1 ? 1 : (t > 16 ? 16 : t);
+  // Host threads for the column gather: the cores this process can count on, at most 4.  One process per GPU is
+  // the deployment (torchrun exports LOCAL_WORLD_SIZE): eight ranks on a 32-core host get 3 threads each, not 8 x 8.
+  {
+    int cores = (int)std::thread::hardware_concurrency();
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) cores = CPU_COUNT(&set);
+    int ranks = 1;
+    if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e) > 0 ? atoi(e) : 1;
+    int t = (cores > 0 ? cores : 1) / ranks - 1;      // leave one core per rank to the interpreter and the driver
+    t = t < 1 ? 1 : (t > 4 ? 4 : t);
+    if (const char* e = getenv("RYDCZ_PACK_THREADS")) { t = atoi(e); t = t < 1 ? 1 : (t > 16 ? 16 : t); }
+    ctx->pack_threads = t;
   }
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if ((e = cudaSetDevice(device)) != cudaSuccess ||
@@ -1137,6 +1216,8 @@ int rydcz_create(int device, rydcz_ctx** out) {
 
 void rydcz_destroy(rydcz_ctx* ctx) {
   if (!ctx) return;
+  delete ctx->pool;
+  ctx->pool = nullptr;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->keys); cudaFree(ctx->keys_sorted); cudaFree(ctx->idx); cudaFree(ctx->idx_sorted);
@@ -1165,6 +1246,52 @@ const char* rydcz_last_error(const rydcz_ctx* ctx) { return ctx ? ctx->err.c_str
 int rydcz_set_sort(rydcz_ctx* ctx, int enable) {
   if (!ctx) return 2;
   ctx->sort = enable != 0;
+  return 0;
+}
+
+int rydcz_set_pack_threads(rydcz_ctx* ctx, int threads) {
+  if (!ctx) return 2;
+  if (threads < 1 || threads > 64) return fail(ctx, "pack threads must be in 1..64");
+  if (ctx->pool && ctx->pool->workers() != threads - 1) { delete ctx->pool; ctx->pool = nullptr; }
+  ctx->pack_threads = threads;
+  return 0;
+}
+
+// Bind the calling thread (and the threads it creates from now on) to the CPUs next to this context's GPU:
+// /sys/bus/pci/devices/<gpu>/local_cpulist.  With one process per GPU on a two-socket host this keeps the page-locked
+// staging buffers, the column gather and the driver threads on the GPU's own socket.  Returns the number of CPUs in
+// the mask through n_cpus (0 and no change when the topology cannot be read).
+int rydcz_bind_host_to_gpu(rydcz_ctx* ctx, int* n_cpus) {
+  if (!ctx) return 2;
+  if (n_cpus) *n_cpus = 0;
+  char bus[32] = {0};
+  if (cudaDeviceGetPCIBusId(bus, sizeof(bus), ctx->device) != cudaSuccess) { cudaGetLastError(); return 0; }
+  for (char* c = bus; *c; ++c) if (*c >= 'A' && *c <= 'F') *c = (char)(*c - 'A' + 'a');
+  const std::string path = std::string("/sys/bus/pci/devices/") + bus + "/local_cpulist";
+  FILE* f = fopen(path.c_str(), "r");
+  if (!f) return 0;
+  char line[1024] = {0};
+  const bool ok = fgets(line, sizeof(line), f) != nullptr;
+  fclose(f);
+  if (!ok) return 0;
+  cpu_set_t allowed, set;
+  CPU_ZERO(&set);
+  if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0) return 0;
+  int count = 0;
+  for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    int a = 0, b = 0;
+    const int got = sscanf(tok, "%d-%d", &a, &b);
+    if (got < 1) continue;
+    if (got == 1) b = a;
+    for (int c = a; c <= b && c < CPU_SETSIZE; ++c)
+      if (CPU_ISSET(c, &allowed)) { CPU_SET(c, &set); ++count; }
+  }
+  if (count == 0) return 0;
+  if (sched_setaffinity(0, sizeof(set), &set) != 0) return 0;
+  if (n_cpus) *n_cpus = count;
+  // the pool's workers were created under the old mask: recreate them on the next call
+  delete ctx->pool;
+  ctx->pool = nullptr;
   return 0;
 }
 
@@ -1647,17 +1774,24 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
     if (c >= rydcz_ctx::kLanes) CK(cudaEventSynchronize(L.ring_free));   // the lane's ring is free again
     else if (enter_call(ctx, st)) return 1;                               // earlier asynchronous calls use the same scratch
     // gather the varying columns into the page-locked ring (strided columns of the caller's row-major
-    // arrays), one H2D copy, scatter on the device.  RYDCZ_PACK_THREADS > 1 gathers with that many OpenMP
-    // threads: 3 % faster end to end on a 1-GPU box, but with one process per GPU on an 8-GPU box the
-    // teams oversubscribe the host cores (end to end 8x slower), so the default is the calling thread alone.
-#pragma omp parallel for schedule(static) num_threads(ctx->pack_threads < n_var ? ctx->pack_threads : n_var) \
-    if (ctx->pack_threads > 1 && n_var > 1 && nc >= 4096)
-    for (int j = 0; j < n_var; ++j) {
-      const int64_t cstr = col_stride ? col_stride[var[j]] : 1;
-      const double* src = h_cols[var[j]] + i0 * cstr;
-      double* dst = L.ring + (size_t)j * chunk;
-      if (cstr == 1) memcpy(dst, src, nc * sizeof(double));
-      else for (int64_t i = 0; i < nc; ++i) dst[i] = src[i * cstr];
+    // arrays), one H2D copy, scatter on the device.  The columns are gathered by a small sleeping thread pool
+    // sized to the cores of this rank (rydcz_create; round 1 measured 8 OpenMP threads per rank on an 8-GPU box
+    // oversubscribing the host 8x: the pool is bounded by cores / LOCAL_WORLD_SIZE and does not spin).
+    {
+      double* ring = L.ring;
+      const std::function<void(int)> gather = [&](int j) {
+        const int64_t cstr = col_stride ? col_stride[var[j]] : 1;
+        const double* src = h_cols[var[j]] + i0 * cstr;
+        double* dst = ring + (size_t)j * chunk;
+        if (cstr == 1) memcpy(dst, src, nc * sizeof(double));
+        else for (int64_t i = 0; i < nc; ++i) dst[i] = src[i * cstr];
+      };
+      if (ctx->pack_threads > 1 && n_var > 1 && nc >= 4096) {
+        if (!ctx->pool) ctx->pool = new PackPool(ctx->pack_threads - 1);
+        ctx->pool->run(n_var, gather);
+      } else {
+        for (int j = 0; j < n_var; ++j) gather(j);
+      }
     }
     if (n_var)
       CK(cudaMemcpyAsync(L.d_ring, L.ring, ((size_t)(n_var - 1) * chunk + nc) * sizeof(double), cudaMemcpyHostToDevice, st));

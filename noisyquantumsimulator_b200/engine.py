@@ -290,6 +290,17 @@ class Evaluator:
         global point index, so a rank evaluating the slice [lo, hi) draws the shots of the unsharded call)."""
         self._check(self.lib.rydcz_set_point_base(self.ctx, int(first_point)), "rydcz_set_point_base")
 
+    def set_pack_threads(self, threads: int):
+        """Host threads that gather the varying columns into pinned staging (rydcz_set_pack_threads)."""
+        self._check(self.lib.rydcz_set_pack_threads(self.ctx, int(threads)), "rydcz_set_pack_threads")
+
+    def bind_host_to_gpu(self) -> int:
+        """Bind this process's calling thread (and threads created later) to the CPUs next to this GPU; returns
+        the number of CPUs in the new mask (0: topology unknown, nothing changed).  One call per rank."""
+        n = C.c_int()
+        self._check(self.lib.rydcz_bind_host_to_gpu(self.ctx, C.byref(n)), "rydcz_bind_host_to_gpu")
+        return int(n.value)
+
     def set_chunk(self, points_per_chunk: int):
         self._check(self.lib.rydcz_set_chunk(self.ctx, int(points_per_chunk)), "rydcz_set_chunk")
 
