@@ -1594,7 +1594,12 @@ static int check_model(rydcz_ctx* ctx, const double* m) {
   const int dim = (int)m[MD_DIM], proto = (int)m[MD_PROTOCOL], S = (int)m[MD_NSEG];
   if (dim != 3 && dim != 4 && dim != 5) return fail(ctx, "model: dim must be 3, 4 or 5");
   if (proto < 0 || proto > 2) return fail(ctx, "model: protocol must be 0 (lp), 1 (jp) or 2 (sjp)");
-  if (S < 1 || (proto == 0 && S != 2)) return fail(ctx, "model: bad segment count");
+  if (S < 1 || (proto == 0 && S != 2 && (S < 4 || (S & 1)))) return fail(ctx, "model: bad segment count");
+  if (proto == 0 && S != 2) {
+    const int shape = (int)m[MD_LEAK_SHAPE];
+    if (shape < 1 || shape > 3) return fail(ctx, "model: shaped LP pulses are gaussian (1), cosine (2) or blackman (3)");
+    if (!(m[MD_AREA_CORRECTION] > 0.0)) return fail(ctx, "model: shaped LP needs the area correction factor");
+  }
   if (proto == 1 && 2 * S > APP_STRIDE - APP_PROTO) return fail(ctx, "model: too many bang-bang segments");
   return 0;
 }

@@ -46,6 +46,7 @@ enum ModelSlot {
   MD_RYD_ZEEMAN_PER_T = 27, MD_BG_DEFAULT = 28,
   MD_E_BRANCH_1 = 29 /* dim 5: fraction of |e> decays that return to |1> */,
   MD_LS_COMP = 30 /* dim 5: 1 = light shifts compensated */,
+  MD_AREA_CORRECTION = 31 /* shaped LP: square area / envelope area (RG/pulse_shaping.py:795-842), 1 for square */,
   MD_STRIDE = 32
 };
 
@@ -275,10 +276,31 @@ RYDCZ_HD int prologue_point(const double* __restrict__ md, const AppView app,
   sc[SC_OMEGA] = Om; sc[SC_V] = V; sc[SC_TAU_TOTAL] = tau_total; sc[SC_TAU_SINGLE] = tau_single;
   sc[SC_DELTA] = Delta_gate; sc[SC_XI_RE] = xi_re; sc[SC_XI_IM] = xi_im; sc[SC_OMEGA_TAU] = o_t;
   // pulse schedule
-  if (protocol == 0) {
+  if (protocol == 0 && S == 2) {
     seg[0] = tau_single; seg[1] = Om; seg[2] = 0.0; seg[3] = Delta_gate;
     seg[4] = tau_single; seg[5] = Om * xi_re; seg[6] = Om * xi_im; seg[7] = Delta_gate;
     return 2;
+  }
+  if (protocol == 0) {
+    // Shaped LP (RG/simulation.py:2099-2231): two pulses of n - 1 midpoint-sampled steps on a grid of n = S / 2 + 1
+    // points, each step lasting tau / n (the reference's dt: 499 steps of tau / 500), amplitude Omega x (area
+    // correction) x envelope(t_mid).  The reference evaluates the envelope on a SCALAR time, so the shapes that
+    // normalise by their own maximum (gaussian, blackman; RG/pulse_shaping.py:184-186, 291-293) return 1: they run
+    // as square pulses of the corrected amplitude.  Only the cosine envelope sin^2(pi t / tau) really shapes.
+    const int n = S / 2 + 1, shape = (int)md[MD_LEAK_SHAPE];
+    const double step = tau_single / (double)(n - 1), dt = tau_single / (double)n, peak = Om * md[MD_AREA_CORRECTION];
+    for (int k = 0; k < n - 1; ++k) {
+      const double t0 = (double)k * step, t1 = (k + 1 == n - 1) ? tau_single : (double)(k + 1) * step;   // np.linspace
+      const double t_mid = (t0 + t1) / 2;
+      double env = 1.0;
+      if (shape == 2) { const double sn = sin(PI * t_mid / tau_single); env = sn * sn; }
+      const double a = peak * env;
+      double* s1 = seg + 4 * k;
+      double* s2 = seg + 4 * (n - 1 + k);
+      s1[0] = dt; s1[1] = a; s1[2] = 0.0; s1[3] = Delta_gate;
+      s2[0] = dt; s2[1] = a * xi_re; s2[2] = a * xi_im; s2[3] = Delta_gate;
+    }
+    return 2 * (n - 1);
   }
   if (protocol == 1) {
     // boundaries [0] + switching + [Ωτ], over Ω; dt < 1e-18 skipped (RG/simulation.py:1859-1903)

@@ -29,7 +29,8 @@ def model_constants(protocol: str, *, config: AtomicConfiguration = None, specie
                     include_motional_dephasing=True, include_doppler_dephasing=True,
                     include_intensity_noise=True, counter_propagating=True, trap_laser_on=True,
                     n_segments: int = None, n_smooth_steps: int = 300, intermediate_branching_1: float = 0.5,
-                    light_shift_compensation: bool = True) -> np.ndarray:
+                    light_shift_compensation: bool = True, pulse_shape: str = "square",
+                    n_shaped_steps: int = 500) -> np.ndarray:
     if config is None:
         config = AtomicConfiguration(species=species, qubit_0=qubit_0, qubit_1=qubit_1, n_rydberg=n_rydberg,
                                      L_rydberg="S")
@@ -38,10 +39,17 @@ def model_constants(protocol: str, *, config: AtomicConfiguration = None, specie
     m = np.zeros(MODEL_STRIDE)
     m[0] = hilbert_space_dim
     m[1] = PROTOCOL_CODE[protocol]
-    m[2] = {"lp": 2, "jp": n_segments or 5, "sjp": n_smooth_steps}[protocol]
+    shaped = protocol == "lp" and pulse_shape != "square"
+    if shaped and pulse_shape not in ("gaussian", "cosine", "blackman"):
+        # 'drag' needs a Delta_leak the reference never passes (RG/simulation.py:2205): same failure as there
+        from .pulse_shaping import get_pulse_envelope
+        get_pulse_envelope(pulse_shape, 0.5, 1.0)
+        raise ValueError(f"pulse shape '{pulse_shape}' is not available in the device prologue")
+    m[2] = {"lp": 2 * (n_shaped_steps - 1) if shaped else 2, "jp": n_segments or 5, "sjp": n_smooth_steps}[protocol]
     m[3:9] = [include_noise, include_motional_dephasing, include_doppler_dephasing, include_intensity_noise,
               trap_laser_on, config.is_clock_transition]
-    m[9] = {"lp": 0, "jp": 5, "sjp": 5}[protocol]      # 'bangbang' / 'smooth_sinusoidal' take the generic sinc²
+    # leakage spectral factor: the LP pulse shape; 'bangbang' / 'smooth_sinusoidal' take the generic sinc²
+    m[9] = {"lp": LEAK_SHAPE_CODE[pulse_shape], "jp": 5, "sjp": 5}[protocol]
     inter = get_default_intermediate_state(config.species)
     m[10] = atom["mass"]
     m[11] = atom["alpha_ground"]
@@ -69,6 +77,9 @@ def model_constants(protocol: str, *, config: AtomicConfiguration = None, specie
     m[28] = 1e3
     m[29] = intermediate_branching_1          # dim 5 only
     m[30] = 1.0 if light_shift_compensation else 0.0
+    # shaped LP: square area / envelope area on the reference's 1000-point grid (independent of tau)
+    from .pulse_shaping import area_correction_factor
+    m[31] = area_correction_factor(pulse_shape, 1.0) if shaped else 1.0
     return m
 
 
@@ -141,8 +152,8 @@ def split_kwargs(kwargs: Dict):
     model_keys = {"config", "species", "n_rydberg", "qubit_0", "qubit_1", "hilbert_space_dim", "include_noise",
                   "include_motional_dephasing", "include_doppler_dephasing", "include_intensity_noise",
                   "counter_propagating", "trap_laser_on", "n_smooth_steps", "intermediate_branching_1",
-                  "light_shift_compensation"}
-    ignored = {"polarization_1", "polarization_2", "warn", "pulse_shape"}
+                  "light_shift_compensation", "pulse_shape", "n_shaped_steps"}
+    ignored = {"polarization_1", "polarization_2", "warn"}
     mk = {k: v for k, v in kwargs.items() if k in model_keys}
     ak = {k: v for k, v in kwargs.items() if k not in model_keys and k not in ignored}
     return mk, ak

@@ -290,8 +290,8 @@ class PopulationObjective:
     @staticmethod
     def _outputs(kw):
         """Only the columns ``extract_metrics`` reads cross PCIe when the device prologue serves the call."""
-        shaped = kw.get("pulse_shape", "square") != "square"
-        return None if shaped else METRIC_OUTPUTS
+        host_only = kw.get("pulse_shape", "square") not in ("square", "gaussian", "cosine", "blackman")
+        return None if host_only else METRIC_OUTPUTS
 
     def _key(self, x: np.ndarray) -> str:
         if self.optimize_spacing:

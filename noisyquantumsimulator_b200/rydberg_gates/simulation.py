@@ -623,7 +623,9 @@ def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, se
     from ..engine import get_evaluator
     from . import device_prologue as dpro
 
-    shaped = protocol == "lp" and kwargs.get("pulse_shape", "square") != "square"
+    # shaped LP pulses (gaussian / cosine / blackman) run through the device prologue as well; 'drag' cannot run
+    # at all (it fails in the reference too) and is left to the host prologue to raise the reference's error
+    shaped = protocol == "lp" and kwargs.get("pulse_shape", "square") not in ("square", "gaussian", "cosine", "blackman")
     five = kwargs.get("hilbert_space_dim", 3) == 5 or (plan is not None and plan.dim == 5)
     if five and n_shots > 0:
         raise ValueError("Monte-Carlo shots are not available for hilbert_space_dim=5")
@@ -635,7 +637,7 @@ def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, se
         if unknown:
             raise ValueError(f"unknown output column(s) {unknown}; choose from {tuple(OUTPUT_SLOTS) + tuple(SCALAR_SLOTS)}")
         if prologue != "device" or return_states:
-            raise ValueError("outputs=... needs the device prologue (square LP, bang-bang, smooth JP) and no states")
+            raise ValueError("outputs=... needs the device prologue (LP, bang-bang, smooth JP) and no states")
     if B is None and plan is None:
         B = max([np.size(v) for v in kwargs.values() if isinstance(v, np.ndarray) and v.ndim >= 1
                  and np.shape(v)[0] > 1] or [1])
