@@ -449,7 +449,9 @@ evaluate_kernel(int64_t n_items, int n_shots, uint64_t seed, int64_t point_base,
 // coefficient records were written by cluster_coef_kernel into the point's region of `scratch`.
 template <int D, bool SYM = true> struct ClusterSmem {
   static constexpr int XN = !SYM ? Sys_rho11_d3::N : (D == 3 ? Sys_rho11s_d3::N : Sys_rho11s_d4::N);
-  static constexpr int X0 = PT_STRIDE + PT_SCRATCH;                   // first start-vector column (3- / 4-level rows: 12 slots)
+  // first start-vector column (3- / 4-level rows: 12 slots).  The plain loop's scratch slots (cached Chebyshev
+  // interval; used by the single-atom passes, which run after the clustered ones) alias the start-vector columns.
+  static constexpr int X0 = PT_STRIDE;
   static constexpr int RING0 = X0 + 3 * XN;                           // first column of the record ring
   // the ring, then the lookahead columns (next segment row + next slot header, rydcz_cluster.cuh)
   static constexpr int SLOTS = RING0 + 3 * (SYM ? ClusterRing<D>::value : CL_RING_GENERAL) + CL_LOOKAHEAD;
@@ -1015,8 +1017,9 @@ static int order_reserve(rydcz_ctx* ctx, int64_t n, bool want_cluster = true) {
     CK(cudaMalloc(&ctx->plan_counts, (1 + rydcz_ctx::kLanes) * sizeof(PlanCounts)));
   }
   if (want_cluster && ctx->cluster_mode) {
-    // (+ a pad: the lookahead of the last slot of the last point reads one header past its records)
-    const size_t bytes = (size_t)n * CL_STRIDE * sizeof(double) + 256;
+    // (+ a pad: the lookahead of the last slot of the last point reads one header, and the ring at most 64 records,
+    //  past its records)
+    const size_t bytes = (size_t)n * CL_STRIDE * sizeof(double) + 4096;
     if (bytes <= kClusterScratchMax) {
       // no memory for the records (16.6 KB per point): not an error, the call stays on the plain path and
       // says so (rydcz_call_flags: RYDCZ_FLAG_NO_CLUSTER_SCRATCH)
@@ -1038,7 +1041,7 @@ static int order_reserve(rydcz_ctx* ctx, int64_t n, bool want_cluster = true) {
 static SortScratch context_scratch(rydcz_ctx* ctx, int64_t n, int64_t offset = 0, int counter_slot = 0) {
   const bool cl = ctx->cluster_mode && ctx->cl_scratch && ctx->task && ctx->task_hdr &&
                   (size_t)(offset + n) * CL_MAX_SLOTS * 8 * sizeof(double) <= ctx->task_hdr_cap &&
-                  (size_t)(offset + n) * CL_STRIDE * sizeof(double) + 256 <= ctx->cl_cap &&
+                  (size_t)(offset + n) * CL_STRIDE * sizeof(double) + 4096 <= ctx->cl_cap &&
                   (size_t)(offset + n) * CL_MAX_SLOTS * 4 * sizeof(uint32_t) <= ctx->task_cap;
   // the four task arrays of a sub-range are laid out back to back inside its own span of the buffer
   return SortScratch{ctx->keys + offset, ctx->keys_sorted + offset, ctx->idx + offset, ctx->idx_sorted + offset,

@@ -142,6 +142,11 @@ struct ClusterWalker {
   int n_seg, s;
   bool sym;
   double rates;
+  // the geometry of the previous slot: consecutive slots of a bang-bang pulse share (|Omega|, Delta) and differ
+  // only in their duration, so the bounds (square roots, a cube root's worth of Newton steps) are computed once
+  double last_om2 = -1.0, last_det = 0.0;
+  bool last_ok = false;
+  ClusterGeom last_g;
   RYDCZ_HD ClusterWalker(const double* pt_, const double* seg_, int n_seg_, bool noisy, bool sym_)
       : pt(pt_), seg(seg_), n_seg(n_seg_), s(0), sym(sym_), rates(0.0) {
     if (noisy) {
@@ -157,8 +162,13 @@ struct ClusterWalker {
     const double* sg = seg + (long long)s * SG_STRIDE;
     const double dt = sg[SG_DT], det = sg[SG_DET];
     const double om2 = sg[SG_RE] * sg[SG_RE] + sg[SG_IM] * sg[SG_IM];
-    if (!cluster_geometry(pt[PT_V], pt[PT_DELTA1], rates, om2, det + pt[PT_OFF_A], det + pt[PT_OFF_B], sym, sl.g))
-      return -1;
+    // (|Omega|^2 of equal-amplitude segments differs by rounding: the bounds carry 2 % of slack)
+    if (!(det == last_det && fabs(om2 - last_om2) <= 1e-12 * last_om2)) {
+      last_ok = cluster_geometry(pt[PT_V], pt[PT_DELTA1], rates, om2, det + pt[PT_OFF_A], det + pt[PT_OFF_B], sym, last_g);
+      last_om2 = om2; last_det = det;
+    }
+    if (!last_ok) return -1;
+    sl.g = last_g;
     const double adt = fabs(dt);
     const double z = adt * sl.g.freq, dz = sl.g.damp * adt;
     if (!(z < 1e6) || !(dz < 1e3)) return -1;
@@ -442,14 +452,23 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const XC rc, 
   double kappa = 0.0, inv_gs = 0.0;
   const double* terms = rec;
   const double* hdr_next = rec;       // header of the slot after the current one
+  // the (sub)step after the current one, for the ring: its records and term count (nK < 0: there is none)
+  const double* nterms = rec;
+  int nK = -1;
+  // Record kk of the current (sub)step into its ring slot.  kk < 0 continues the countdown ACROSS the boundary: the
+  // first records of the next (sub)step (index roundup(nK + 2) + kk), so that a (sub)step never starts by waiting
+  // for records it has only just asked for (ncu, round 2: that wait was 7 % of the kernel's stall samples).
 #define RYDCZ_RING_FETCH(kk)                                                                    \
   do {                                                                                          \
-    const int kf_ = (kk);                                                                       \
-    if (kf_ >= 0 && kf_ <= K) {                                                                 \
+    int kf_ = (kk);                                                                             \
+    const double* tf_ = terms;                                                                  \
+    int Kf_ = K;                                                                                \
+    if (kf_ < 0) { kf_ += cluster_roundup(nK + 2); tf_ = nterms; Kf_ = nK; }                    \
+    if (kf_ >= 0 && kf_ <= Kf_) {                                                               \
       const int sl_ = (kf_ & (RING - 1)) * 3;                                                   \
-      RYDCZ_ASYNC_COPY8(&rc[sl_], terms + kf_ * CL_REC);                                        \
-      RYDCZ_ASYNC_COPY8(&rc[sl_ + 1], terms + kf_ * CL_REC + 1);                                \
-      RYDCZ_ASYNC_COPY8(&rc[sl_ + 2], terms + kf_ * CL_REC + 2);                                \
+      RYDCZ_ASYNC_COPY8(&rc[sl_], tf_ + kf_ * CL_REC);                                          \
+      RYDCZ_ASYNC_COPY8(&rc[sl_ + 1], tf_ + kf_ * CL_REC + 1);                                  \
+      RYDCZ_ASYNC_COPY8(&rc[sl_ + 2], tf_ + kf_ * CL_REC + 2);                                  \
     }                                                                                           \
     RYDCZ_ASYNC_COMMIT();                                                                       \
   } while (0)
@@ -469,6 +488,7 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const XC rc, 
   RYDCZ_LOOKAHEAD_HEADER(rec);
   RYDCZ_ASYNC_COMMIT();
   RYDCZ_ASYNC_WAIT(0);
+  bool first_substep = true;
   for (;;) {
     if (k < 0) {
       // b1 holds the state.  Next sub-step of this segment, or the next segment (and maybe the next slot).
@@ -515,9 +535,25 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const XC rc, 
       for (int i = 0; i < N; ++i) b2[i] = 0.0;
       k = cluster_roundup(K + 2) - 1;    // the priming step (k > K: zero coefficients), then k - 1 ... 0
       priming = true;
-      // fill the ring: records k ... k - (RING - 2); step j then fetches record j - (RING - 1)
-      RYDCZ_UNROLL
-      for (int q = 0; q < RING - 1; ++q) RYDCZ_RING_FETCH(k - q);
+      nK = -1;                           // the (sub)step after this one is looked up when the ring first needs it
+      if (first_substep) {
+        // fill the ring: records k ... k - (RING - 2); step j then fetches record j - (RING - 1).  Later (sub)steps
+        // find their first records already in the ring (fetched across the boundary, below).
+        RYDCZ_UNROLL
+        for (int q = 0; q < RING - 1; ++q) RYDCZ_RING_FETCH(k - q);
+        first_substep = false;
+      }
+    }
+    if (k - (RING - 1) < 0 && nK < 0) {
+      // The ring is about to run past this (sub)step: what comes next?  The same records again (further sub-steps,
+      // or further segments of this slot), or the next slot, whose header has been in the lookahead columns since
+      // this slot began (its term count is clamped: past the last slot the columns hold another point's header).
+      if (sub_left > 0 || seg_left > 0) { nterms = terms; nK = K; }
+      else if (s < n_seg) {
+        nterms = hdr_next + CL_HDR;
+        nK = (int)rc[LA + 4] & 1023;
+        if (nK > CL_MAX_K) nK = CL_MAX_K;
+      } else { nterms = terms; nK = 0; }
     }
     // step k: b2 <- C_k x + 2S~ b1 + b2      (priming: b1 = x, and both vectors restart from zero afterwards)
     double d0 = 0.0, d1 = 0.0, d2 = 0.0;
@@ -632,7 +668,7 @@ RYDCZ_DEFINE_EVALUATE_CLUSTER(4)
 // 25-variable rho_11 and 8-variable coherence on the clustered expansion with the two-atom bounds of
 // cluster_geometry(sym = false); the |01> and |10> inputs are different single-atom problems and stay on the
 // plain loop.  3-level model only (the general 4-level rho_11 has 36 variables: four vectors of it do not fit).
-constexpr int CL_RING_GENERAL = 2;   // 75 start-vector columns leave room for a two-slot record ring
+constexpr int CL_RING_GENERAL = 4;   // 75 start-vector columns + a four-slot record ring + the lookahead: 107 columns, two CTAs per SM
 template <bool NOISY>
 RYDCZ_HD bool evaluate_point_cluster_general_d3(const PointView pt, const Col xcol, const Col rcol,
                                                 const double* __restrict__ seg, int n_seg,

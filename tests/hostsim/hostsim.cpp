@@ -30,7 +30,7 @@ static bool try_cluster(const rydcz::PointView pt, const double* row, const doub
   const int records = cluster_plan<D>(row, sg, ns, noisy, true, cost);
   if (records <= 0 || records > CL_RECORDS) return false;
   if (g_cluster == 1 && !(cost < 0.8 * point_work<D>(row, sg, ns))) return false;
-  std::vector<double> rec((size_t)CL_STRIDE + 8, 0.0);      // (+ pad: the header lookahead of the last slot)
+  std::vector<double> rec((size_t)CL_STRIDE + 512, 0.0);    // (+ pad: header lookahead and ring prefetch past the last slot)
   cluster_prepare<D>(row, sg, ns, noisy, true, rec.data());
   double xc[3 * (21 + 6)], ring[3 * 8 + CL_LOOKAHEAD];
   bool ok;
@@ -51,7 +51,7 @@ static bool try_cluster_general(const rydcz::PointView pt, const double* row, co
   const int records = cluster_plan<3>(row, sg, ns, noisy, false, cost);
   if (records <= 0 || records > CL_RECORDS) return false;
   if (g_cluster == 1 && !(cost < 0.8 * point_work<3>(row, sg, ns))) return false;
-  std::vector<double> rec((size_t)CL_STRIDE + 8, 0.0);      // (+ pad: the header lookahead of the last slot)
+  std::vector<double> rec((size_t)CL_STRIDE + 512, 0.0);    // (+ pad: header lookahead and ring prefetch past the last slot)
   cluster_prepare<3>(row, sg, ns, noisy, false, rec.data());
   double xc[3 * 25], ring[3 * 8 + CL_LOOKAHEAD];
   const bool ok = noisy ? evaluate_point_cluster_general_d3<true>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), o, st)
