@@ -201,7 +201,9 @@ struct ClusterWalker {
   }
 };
 
-// Slot header (CL_HDR doubles): K + 1024 nsub, kappa = Vc^2 / gs^2, 1 / gs, count | h, Vc, rho, 0
+// Slot header (CL_HDR doubles): K + 1024 nsub, kappa = Vc^2 / gs^2, 1 / gs, count + 65536 K_next | h, Vc, rho, 0
+// (K_next = term count of the slot that follows, 0 if there is none: the evaluator's record ring runs across slot
+//  boundaries and must know it before that slot's own header has been read; filled in by cluster_plan)
 // (gs = (rho/2)^(1/3): G~ = G / gs).  The first four are what the evaluator reads; the rest is what
 // cluster_coefficients needs to fill the K + 1 records that follow.
 RYDCZ_HD void cluster_write_header(const ClusterSlot& sl, double* __restrict__ rec) {
@@ -228,6 +230,7 @@ RYDCZ_HD int cluster_plan(const double* pt, const double* seg, int n_seg, bool n
   ClusterWalker<D> w(pt, seg, n_seg, noisy, sym);
   ClusterSlot sl;
   int records = 0, slots = 0;
+  double* prev_hdr = nullptr;
   cost = 0.0;
   for (;;) {
     const int r = w.next(sl);
@@ -236,7 +239,11 @@ RYDCZ_HD int cluster_plan(const double* pt, const double* seg, int n_seg, bool n
     if (++slots > CL_MAX_SLOTS) return 0;
     if (slot_K) slot_K[slots - 1] = sl.K;
     if (slot_off) slot_off[slots - 1] = records;
-    if (rec) cluster_write_header(sl, rec + (long long)records * CL_REC);
+    if (rec) {
+      cluster_write_header(sl, rec + (long long)records * CL_REC);
+      if (prev_hdr) prev_hdr[3] += 65536.0 * (double)sl.K;       // the previous slot learns this slot's term count
+      prev_hdr = rec + (long long)records * CL_REC;
+    }
     if (dense) {
       double* d = dense + (slots - 1) * 4;
       d[0] = (double)(sl.K + 1024 * sl.nsub); d[1] = sl.h; d[2] = sl.g.Vc; d[3] = sl.g.rho;
@@ -454,7 +461,7 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const XC rc, 
   const double* hdr_next = rec;       // header of the slot after the current one
   // the (sub)step after the current one, for the ring: its records and term count (nK < 0: there is none)
   const double* nterms = rec;
-  int nK = -1;
+  int nK = -1, K_next = 0;
   // Record kk of the current (sub)step into its ring slot.  kk < 0 continues the countdown ACROSS the boundary: the
   // first records of the next (sub)step (index roundup(nK + 2) + kk), so that a (sub)step never starts by waiting
   // for records it has only just asked for (ncu, round 2: that wait was 7 % of the kernel's stall samples).
@@ -517,7 +524,9 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const XC rc, 
         if (seg_left == 0) {
           const int kn = (int)rc[LA + 4];
           K = kn & 1023; nsub = kn >> 10;
-          kappa = rc[LA + 5]; inv_gs = rc[LA + 6]; seg_left = (int)rc[LA + 7];
+          kappa = rc[LA + 5]; inv_gs = rc[LA + 6];
+          const int cn = (int)rc[LA + 7];
+          seg_left = cn & 0xffff; K_next = cn >> 16;
           terms = hdr_next + CL_HDR;
           hdr_next = terms + (K + 1) * CL_REC;
           RYDCZ_LOOKAHEAD_HEADER(hdr_next);          // (past the last slot: the next point's region, or the pad)
@@ -546,14 +555,10 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const XC rc, 
     }
     if (k - (RING - 1) < 0 && nK < 0) {
       // The ring is about to run past this (sub)step: what comes next?  The same records again (further sub-steps,
-      // or further segments of this slot), or the next slot, whose header has been in the lookahead columns since
-      // this slot began (its term count is clamped: past the last slot the columns hold another point's header).
+      // or further segments of this slot), or the next slot, whose term count this slot's header carries.
       if (sub_left > 0 || seg_left > 0) { nterms = terms; nK = K; }
-      else if (s < n_seg) {
-        nterms = hdr_next + CL_HDR;
-        nK = (int)rc[LA + 4] & 1023;
-        if (nK > CL_MAX_K) nK = CL_MAX_K;
-      } else { nterms = terms; nK = 0; }
+      else if (K_next > 0) { nterms = hdr_next + CL_HDR; nK = K_next; }
+      else { nterms = terms; nK = 0; }
     }
     // step k: b2 <- C_k x + 2S~ b1 + b2      (priming: b1 = x, and both vectors restart from zero afterwards)
     double d0 = 0.0, d1 = 0.0, d2 = 0.0;

@@ -294,3 +294,33 @@ def test_paths_agree_on_random_batches(evaluator):
         assert planned > n // 4 and back == 0
         worst = max(worst, np.abs(out[:, :14] - out0[:, :14]).max(), np.abs(st - st0).max())
     assert worst < 5e-11
+
+
+def test_shaped_lp_pulses_on_the_device_prologue(evaluator):
+    """Shaped LP pulses (998 envelope-sampled segments, scalar-envelope quirk) generated by prologue_kernel: equal to
+    the host-prologue route and to the reference-run fixtures; the shapes that degenerate to a constant amplitude
+    (gaussian, blackman) take the repeated-segment path, the cosine envelope the plain one."""
+    from noisyquantumsimulator_b200 import rydberg_gates as rg
+    rng = np.random.default_rng(2)
+    B = 96
+    base = dict(laser_1_power=50e-6, laser_1_waist=50e-6, laser_2_power=10 ** rng.uniform(-0.8, 0.3, B), laser_2_waist=50e-6,
+                Delta_e=2 * np.pi * 1e9, tweezer_power=0.02, tweezer_waist=0.8e-6, warn=False)
+    for shape, want in (("gaussian", 5), ("cosine", 1), ("blackman", 5)):
+        for noise in (True, False):
+            a = rg.simulate_CZ_gate_batch("lp", B=B, pulse_shape=shape, prologue="device", include_noise=noise, **base)
+            status = evaluator.point_status(B) & 0x0f
+            b = rg.simulate_CZ_gate_batch("lp", B=B, pulse_shape=shape, prologue="host", include_noise=noise, **base)
+            assert np.abs(a.raw[:, :14] - b.raw[:, :14]).max() < 1e-9, (shape, noise)
+            assert (status == want).all(), (shape, noise, np.unique(status))
+    # the fixtures generated by the reference's own evolve_shaped_pulse
+    for name in ("lp_shaped_gaussian", "lp_shaped_cosine", "lp_shaped_blackman", "lp_shaped_cosine_noisy"):
+        case = REF[name]
+        proto, kw = C.plan_kwargs(case)
+        r = rg.simulate_CZ_gate_batch(proto, B=1, prologue="device", return_states=True, warn=False, **kw)
+        gold = case["result_coherence"] if case["rates"] is not None else case["result"]
+        assert abs(r.avg_fidelity[0] - gold["avg_fidelity"]) < 1e-9, name
+        fin = C.golden_finals(case)
+        ops = C.states_to_operators(case["dim"], r.states[0])
+        for lab in ("01", "10", "11"):
+            got = ops["rho" + lab] if case["rates"] is not None else ops["coh" + lab][:, 0]
+            assert np.abs(got - fin[lab]).max() < 1e-10, (name, lab)
