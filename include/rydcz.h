@@ -114,6 +114,19 @@ int rydcz_set_sort(rydcz_ctx* ctx, int enable);         /* order points by estim
  * same call.  Device memory: 16.6 KB of coefficient records per point (per shot with shots), kept by the
  * context; if it cannot be allocated (or would exceed 48 GB) the call stays on the plain path. */
 int rydcz_set_cluster(rydcz_ctx* ctx, int mode);
+/* Shared coefficient table of the clustered path (csrc/rydcz_cluster.cuh): the coefficient records of a (sub)step
+ * depend only on (h Vc, rho / Vc^3), and a (sub)step may use the records of the nearest grid entry EXACTLY if its
+ * operator is rescaled by lambda = h Vc / theta_n and the entry's clusters are a little wider -- so slots that
+ * share the blockade and the drive (every candidate of an optimiser population, every chunk of a sweep at fixed
+ * apparatus) share a few thousand table entries instead of generating 1-8 sets of records per point.
+ * 0 = off (every slot generates its own records, round-1 behaviour), 1 = table entries generated once per
+ * evaluation call (default; nothing is carried from one call to the next), 2 = entries kept across calls
+ * (an optimiser's generations re-use them).  Device memory: 1.2 GB, allocated at the first clustered call; if
+ * that fails the context silently behaves like mode 0 (results identical to rounding in every mode). */
+int rydcz_set_table(rydcz_ctx* ctx, int mode);
+/* table entries generated / slots of clustered points that took their records from the table, since the last
+ * call of this function (synchronises the device; any pointer may be NULL) */
+int rydcz_table_stats(rydcz_ctx* ctx, int64_t* entries_generated, int64_t* slots_shared);
 /* points planned onto the clustered path / handed back to the plain path / 32-byte coefficient records
  * written for them since the last call of this function (synchronises the device; any pointer may be NULL) */
 int rydcz_cluster_stats(rydcz_ctx* ctx, int64_t* planned, int64_t* handed_back, int64_t* records);

@@ -38,6 +38,8 @@ _SIGNATURES = {
     "rydcz_last_error": (C.c_char_p, [_vp]),
     "rydcz_set_sort": (C.c_int, [_vp, C.c_int]),
     "rydcz_set_cluster": (C.c_int, [_vp, C.c_int]),
+    "rydcz_set_table": (C.c_int, [_vp, C.c_int]),
+    "rydcz_table_stats": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "rydcz_set_point_base": (C.c_int, [_vp, C.c_int64]),
     "rydcz_cluster_stats": (C.c_int, [_vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "rydcz_evaluate_device": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int64, _vp, _vp, _vp, C.c_int,

@@ -142,17 +142,19 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
                             uint32_t* __restrict__ idx, uint8_t* __restrict__ kind,
                             uint32_t* __restrict__ task_key, uint32_t* __restrict__ task_val,
                             double* __restrict__ task_hdr,
-                            double* __restrict__ scratch, unsigned long long* __restrict__ counters,
+                            double* __restrict__ scratch, const ClusterTable table,
+                            unsigned long long* __restrict__ counters,
                             unsigned* __restrict__ repeat_count, PlanCounts* __restrict__ plan) {
   __shared__ PlanShared sh;
   if (plan) plan_shared_clear(sh, false);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool clustered = false, repeated = false;
   int records_planned = 0;
-  unsigned bin = 0;
-  int slot_K[CL_MAX_SLOTS], slot_off[CL_MAX_SLOTS];
+  unsigned bin = 0, shared_tasks = 0u, shared_slots = 0u;
+  int slot_K[CL_MAX_SLOTS];
+  unsigned slot_val[CL_MAX_SLOTS];
 #pragma unroll
-  for (int q = 0; q < CL_MAX_SLOTS; ++q) { slot_K[q] = 0; slot_off[q] = 0; }
+  for (int q = 0; q < CL_MAX_SLOTS; ++q) { slot_K[q] = 0; slot_val[q] = 0u; }
   if (i < n_points) {
     const double* pt = points + i * PointStride<D>::value;
     const int64_t sp = i / seg_div;       // row of the pulse schedule (the shots of a point share it)
@@ -175,20 +177,28 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
       double cost = 0.0;
       // the slot headers are written on the way (harmless if the point stays on the plain path); unequal atoms
       // (3-level model only) take the two-atom bounds and the general kernel
-      const int records = cluster_plan<D>(pt, sg, ns, noisy != 0, sym, cost, slot_K, slot_off,
+      const int records = cluster_plan<D>(pt, sg, ns, noisy != 0, sym, cost, table, shared_tasks, slot_K, slot_val,
                                           scratch + i * (int64_t)CL_STRIDE,
                                           task_hdr ? task_hdr + i * (int64_t)(CL_MAX_SLOTS * 4) : nullptr);
       if (records > 0 && records <= CL_RECORDS && (cluster_mode == 2 || cost < 0.8 * w)) {
-        clustered = true; group = sym ? GROUP_CLUSTER : GROUP_CLUSTER_GENERAL; w = sym ? cost : 2.0 * cost; records_planned = records;
+        clustered = true; group = sym ? GROUP_CLUSTER : GROUP_CLUSTER_GENERAL; w = sym ? cost : 2.0 * cost;
+        records_planned = records - CL_OWN0;
       }
     }
     if (task_key) {
-      // one coefficient task per slot, keyed by its term count: sorted, the threads of a warp of
-      // cluster_coef_kernel run the same trip counts
+      // one coefficient task per slot that needs records generated, keyed by its term count: binned, the threads
+      // of a warp of cluster_coef_kernel run the same trip counts.  A slot whose records come from the shared table
+      // has a task only if this thread was the first to claim the entry -- and then whatever path the point takes:
+      // other points already count on that entry.
 #pragma unroll
       for (int q = 0; q < CL_MAX_SLOTS; ++q) {
-        task_key[i * CL_MAX_SLOTS + q] = clustered ? (uint32_t)slot_K[q] : 0u;
-        task_val[i * CL_MAX_SLOTS + q] = (uint32_t)(i * CL_RECORDS + slot_off[q]);   // record index of the slot header
+        const bool shared = (slot_val[q] & 0x80000000u) != 0u;
+        if (shared && clustered) ++shared_slots;
+        const bool run = shared ? ((shared_tasks >> q) & 1u) != 0u : clustered;
+        if (!run) slot_K[q] = 0;
+        task_key[i * CL_MAX_SLOTS + q] = (uint32_t)slot_K[q];
+        // where the task writes: a record index of the coefficient scratch, or 0x80000000 | table entry
+        task_val[i * CL_MAX_SLOTS + q] = shared ? slot_val[q] : (uint32_t)(i * CL_RECORDS + slot_val[q]);
       }
     }
     kind[i] = repeated ? KIND_REPEAT
@@ -200,7 +210,7 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
   if (plan) {
     if (i < n_points) {
       atomicAdd(&sh.pts[bin], 1u);
-      if (task_key && clustered) {
+      if (task_key) {
 #pragma unroll
         for (int q = 0; q < CL_MAX_SLOTS; ++q)
           if (slot_K[q] > 0) atomicAdd(&sh.tsk[slot_K[q]], 1u);
@@ -217,9 +227,15 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
     atomicAdd(repeat_count, (unsigned)__popc(mr));
     if (counters) atomicAdd(counters + 3, (unsigned long long)__popc(mr));
   }
+  const unsigned tsum = __reduce_add_sync(0xffffffffu, (unsigned)__popc(shared_tasks));
+  const unsigned ssum = __reduce_add_sync(0xffffffffu, shared_slots);
   if (counters && (threadIdx.x & 31) == 0 && m) {
     atomicAdd(counters, (unsigned long long)__popc(m));
     atomicAdd(counters + 2, (unsigned long long)rsum);
+  }
+  if (counters && (threadIdx.x & 31) == 0 && (tsum | ssum)) {
+    atomicAdd(counters + 6, (unsigned long long)tsum);      // table entries generated
+    atomicAdd(counters + 7, (unsigned long long)ssum);      // slots of clustered points that read the table
   }
 }
 
@@ -332,7 +348,8 @@ constexpr int kCoefTasksPerCta = kBlock / kCoefLanes;
 // grid is sized for the largest possible task count and CTAs beyond the real one leave at once.
 __global__ void __launch_bounds__(kBlock, 4)
 cluster_coef_kernel(const PlanCounts* __restrict__ plan, const uint32_t* __restrict__ task_sorted,
-                    const double* __restrict__ task_hdr_sorted, double* __restrict__ scratch) {
+                    const double* __restrict__ task_hdr_sorted, double* __restrict__ scratch,
+                    double* __restrict__ table) {
   __shared__ double s_a[6 * CL_HALF_MAX * kCoefTasksPerCta];
   const int t_in_cta = threadIdx.x / kCoefLanes, m = threadIdx.x % kCoefLanes;
   const int64_t g = (int64_t)blockIdx.x * kCoefTasksPerCta + t_in_cta;
@@ -344,8 +361,10 @@ cluster_coef_kernel(const PlanCounts* __restrict__ plan, const uint32_t* __restr
     // the slot header in the records (ncu, round 2: that read was 17 % of this kernel's stall samples)
     const double2 h0 = reinterpret_cast<const double2*>(task_hdr_sorted + g * 4)[0];
     const double2 h1 = reinterpret_cast<const double2*>(task_hdr_sorted + g * 4)[1];
-    cluster_coefficients_of((int)h0.x & 1023, h0.y, h1.x, h1.y,
-                            scratch + (int64_t)task_sorted[g] * CL_REC + CL_HDR, s_a + t_in_cta, kCoefTasksPerCta, m, kCoefLanes);
+    const uint32_t where = task_sorted[g];
+    double* out = (where & 0x80000000u) ? table + (int64_t)(where & 0x7fffffffu) * (CT_ENTRY_REC * CL_REC)
+                                        : scratch + (int64_t)where * CL_REC;
+    cluster_coefficients_of((int)h0.x & 1023, h0.y, h1.x, h1.y, out, s_a + t_in_cta, kCoefTasksPerCta, m, kCoefLanes);
   } else {
     __syncwarp();     // pairs with the group barrier inside cluster_coefficients
   }
@@ -465,7 +484,7 @@ evaluate_cluster_kernel(int64_t n_items, const uint32_t* __restrict__ order, uin
                         PlanCounts* __restrict__ plan,
                         const double* __restrict__ points, const double* __restrict__ segs,
                         const int32_t* __restrict__ n_seg, int max_seg, int seg_div,
-                        const double* __restrict__ scratch,
+                        const double* __restrict__ scratch, const double* __restrict__ table,
                         double* __restrict__ out, double* __restrict__ states,
                         unsigned long long* __restrict__ counters) {
   extern __shared__ double s_cl[];
@@ -500,9 +519,9 @@ evaluate_cluster_kernel(int64_t n_items, const uint32_t* __restrict__ order, uin
   double o[OUT_STRIDE];
   double* st = states ? states + point * StateLayout<D>::STRIDE : nullptr;
   bool ok;
-  if (!SYM) ok = evaluate_point_cluster_general_d3<NOISY>(pt, xcol, rcol, sg, ns, rec, o, st);
-  else if (D == 3) ok = evaluate_point_cluster_d3<NOISY>(pt, xcol, rcol, sg, ns, rec, o, st);
-  else ok = evaluate_point_cluster_d4<NOISY>(pt, xcol, rcol, sg, ns, rec, o, st);
+  if (!SYM) ok = evaluate_point_cluster_general_d3<NOISY>(pt, xcol, rcol, sg, ns, rec, table, o, st);
+  else if (D == 3) ok = evaluate_point_cluster_d3<NOISY>(pt, xcol, rcol, sg, ns, rec, table, o, st);
+  else ok = evaluate_point_cluster_d4<NOISY>(pt, xcol, rcol, sg, ns, rec, table, o, st);
   if (!ok) {
     // invariant check failed: hand the point to the plain kernel of its kind, which runs after this one
     kind[point] = (SYM ? KIND_SYM : KIND_GENERAL) | KIND_RETRY;
@@ -879,6 +898,15 @@ struct rydcz_ctx {
   double* cl_scratch = nullptr; size_t cl_cap = 0;      // coefficient records, CL_STRIDE doubles per point
   unsigned long long* cl_counters = nullptr;            // [0] clustered points, [1] handed back, [2] records, [3] repeated-segment points,
                                                         // [4] unsupported points (NaN rows), [5] spare
+  // shared coefficient table (rydcz_cluster.cuh): 0 = off, 1 = entries generated once per call, 2 = kept across calls
+  int table_mode = 1;
+  ClusterTableDir* tb_dir = nullptr;                    // device copy of the directory
+  unsigned* tb_stamp = nullptr;                         // generation stamp per entry
+  double* tb_records = nullptr;                         // CT_ENTRY_REC records per entry
+  unsigned tb_epoch = 1;
+  bool tb_failed = false;                               // allocation failed once: slots keep records of their own
+  cudaEvent_t tb_ready = nullptr;                       // after the last coefficient kernel: the entries claimed so far exist
+  bool tb_ready_set = false;
   bool cl_smem_set = false;
   bool cl_smem_gen_set = false;
   bool rp_smem_set = false;
@@ -960,6 +988,20 @@ static int leave_call(rydcz_ctx* ctx, cudaStream_t st) {
   return 0;
 }
 
+// A new evaluation call: with table mode 1 the shared coefficient entries of earlier calls are forgotten (every
+// call pays for the entries it uses); mode 2 keeps them (rydcz_set_table).
+static int table_new_call(rydcz_ctx* ctx) {
+  if (ctx->table_mode != 1 || !ctx->tb_stamp) return 0;
+  if (++ctx->tb_epoch == 0u) {
+    ClusterTableDir dir;
+    cluster_table_dir_init(dir);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemset(ctx->tb_stamp, 0, (size_t)dir.base[CT_CLASSES] * sizeof(unsigned)));
+    ctx->tb_epoch = 1u;
+  }
+  return 0;
+}
+
 static const char* kSysNames[6] = {"rho11", "rho01", "rho10", "coh11", "coh01", "coh10"};
 template <int D> static void sys_tables(int (&off)[6], int (&n)[6], int (&nnz)[6]);
 template <> void sys_tables<3>(int (&off)[6], int (&n)[6], int (&nnz)[6]) {
@@ -1010,11 +1052,28 @@ static int order_reserve(rydcz_ctx* ctx, int64_t n, bool want_cluster = true) {
     ctx->order_cap = (size_t)n;
   }
   if (!ctx->cl_counters) {
-    CK(cudaMalloc(&ctx->cl_counters, 6 * sizeof(unsigned long long)));
-    CK(cudaMemset(ctx->cl_counters, 0, 6 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->cl_counters, 8 * sizeof(unsigned long long)));
+    CK(cudaMemset(ctx->cl_counters, 0, 8 * sizeof(unsigned long long)));
     CK(cudaEventCreate(&ctx->evc0)); CK(cudaEventCreate(&ctx->evc1));
     CK(cudaMalloc(&ctx->rp_count, (1 + rydcz_ctx::kLanes) * sizeof(unsigned)));
     CK(cudaMalloc(&ctx->plan_counts, (1 + rydcz_ctx::kLanes) * sizeof(PlanCounts)));
+  }
+  if (want_cluster && ctx->cluster_mode && ctx->table_mode && !ctx->tb_dir && !ctx->tb_failed) {
+    // the shared coefficient table: directory, stamps, records (1.2 GB; without it every slot generates its own)
+    ClusterTableDir dir;
+    cluster_table_dir_init(dir);
+    const size_t entries = (size_t)dir.base[CT_CLASSES];
+    if (cudaMalloc(&ctx->tb_dir, sizeof(dir)) != cudaSuccess || cudaMalloc(&ctx->tb_stamp, entries * sizeof(unsigned)) != cudaSuccess ||
+        cudaMalloc(&ctx->tb_records, entries * CT_ENTRY_REC * CL_REC * sizeof(double) + 4096) != cudaSuccess) {
+      cudaGetLastError();
+      cudaFree(ctx->tb_dir); cudaFree(ctx->tb_stamp); cudaFree(ctx->tb_records);
+      ctx->tb_dir = nullptr; ctx->tb_stamp = nullptr; ctx->tb_records = nullptr;
+      ctx->tb_failed = true;
+    } else {
+      CK(cudaMemcpy(ctx->tb_dir, &dir, sizeof(dir), cudaMemcpyHostToDevice));
+      CK(cudaMemset(ctx->tb_stamp, 0, entries * sizeof(unsigned)));
+      CK(cudaEventCreateWithFlags(&ctx->tb_ready, cudaEventDisableTiming));
+    }
   }
   if (want_cluster && ctx->cluster_mode) {
     // (+ a pad: the lookahead of the last slot of the last point reads one header, and the ring at most 64 records,
@@ -1060,7 +1119,13 @@ static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const do
                       const double* d_segs, const int32_t* d_n_seg, int max_seg, int shots, int noisy,
                       cudaStream_t st, const uint32_t** order, int seg_div = 1) {
   *order = nullptr;
-  const int mode = (sc.cl && D != 5 && !shots && n * (int64_t)CL_RECORDS < 0xffffffffLL) ? ctx->cluster_mode : 0;
+  const int mode = (sc.cl && D != 5 && !shots && n * (int64_t)CL_RECORDS < 0x7fffffffLL) ? ctx->cluster_mode : 0;
+  // The table is shared by every work order of the context (the chunks of a pipelined call run on three streams):
+  // a planner may rely on an entry another order has claimed, so every order plans after the previous order's
+  // coefficient kernel (the chain below) and generates what it claims before its own evaluate kernels.
+  const bool use_table = mode && ctx->table_mode && ctx->tb_dir;
+  const ClusterTable table{use_table ? ctx->tb_dir : nullptr, use_table ? ctx->tb_stamp : nullptr, ctx->tb_epoch};
+  if (use_table && ctx->tb_ready_set) CK(cudaStreamWaitEvent(st, ctx->tb_ready, 0));
   unsigned* rpc = (mode && D == 3 && sc.rp && seg_div == 1) ? sc.rp_count : nullptr;
   if (rpc) CK(cudaMemsetAsync(rpc, 0, sizeof(unsigned), st));
   uint32_t* tk = mode ? sc.task : nullptr;                     // term count of every (point, slot); 0 = no such slot
@@ -1070,7 +1135,7 @@ static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const do
   double* ths = mode ? sc.task_hdr + sc.task_n * 4 : nullptr;  // ... in task order
   CK(cudaMemsetAsync(sc.plan, 0, sizeof(PlanCounts), st));
   plan_kernel<D><<<(unsigned)((n + kPlanBlock - 1) / kPlanBlock), kPlanBlock, 0, st>>>(n, d_points, d_segs, d_n_seg, max_seg, seg_div, shots, noisy,
-                                                              mode, sc.keys, sc.idx, sc.kind, tk, tv, th, sc.cl,
+                                                              mode, sc.keys, sc.idx, sc.kind, tk, tv, th, sc.cl, table,
                                                               ctx->cl_counters, rpc, sc.plan);
   CK(cudaGetLastError());
   ctx->launches++;
@@ -1087,9 +1152,10 @@ static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const do
     const int64_t max_tasks = n * CL_MAX_SLOTS;
     CK(cudaEventRecord(ctx->evc0, st));
     cluster_coef_kernel<<<(unsigned)((max_tasks + kCoefTasksPerCta - 1) / kCoefTasksPerCta), kBlock, 0, st>>>(
-        sc.plan, tks, ths, sc.cl);
+        sc.plan, tks, ths, sc.cl, ctx->tb_records);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->evc1, st));
+    if (use_table) { CK(cudaEventRecord(ctx->tb_ready, st)); ctx->tb_ready_set = true; }
     ctx->coef_timed = true;
     ctx->launches++;
   }
@@ -1115,7 +1181,7 @@ static int launch_eval(rydcz_ctx* ctx, const SortScratch& sc, int64_t n_items, i
       ctx->cl_smem_gen_set = true;
     }
     evaluate_cluster_kernel<3, NOISY, false><<<grid, kBlock, ClusterSmem<3, false>::BYTES, st>>>(
-        n_items, order, sc.kind, plan, d_points, d_segs, d_n_seg, max_seg, seg_div, sc.cl, d_out, d_states, ctx->cl_counters);
+        n_items, order, sc.kind, plan, d_points, d_segs, d_n_seg, max_seg, seg_div, sc.cl, ctx->tb_records, d_out, d_states, ctx->cl_counters);
     CK(cudaGetLastError());
     ctx->launches++;
   }
@@ -1134,7 +1200,7 @@ static int launch_eval(rydcz_ctx* ctx, const SortScratch& sc, int64_t n_items, i
     }
     // before the plain folded kernel: points whose invariant check fails are handed on to it
     evaluate_cluster_kernel<D, NOISY, true><<<grid, kBlock, ClusterSmem<D>::BYTES, st>>>(
-        n_items, order, sc.kind, plan, d_points, d_segs, d_n_seg, max_seg, seg_div, sc.cl, d_out, d_states, ctx->cl_counters);
+        n_items, order, sc.kind, plan, d_points, d_segs, d_n_seg, max_seg, seg_div, sc.cl, ctx->tb_records, d_out, d_states, ctx->cl_counters);
     CK(cudaGetLastError());
     ctx->launches++;
   }
@@ -1142,7 +1208,7 @@ static int launch_eval(rydcz_ctx* ctx, const SortScratch& sc, int64_t n_items, i
                                                                   sc.kind, plan, d_points, d_segs, d_n_seg, max_seg,
                                                                   seg_div, d_out, d_states);
   CK(cudaGetLastError());
-  if (!SHOTS && D == 3 && seg_div == 1 && sc.cl && sc.rp && ctx->cluster_mode && n_items * (int64_t)CL_RECORDS < 0xffffffffLL) {
+  if (!SHOTS && D == 3 && seg_div == 1 && sc.cl && sc.rp && ctx->cluster_mode && n_items * (int64_t)CL_RECORDS < 0x7fffffffLL) {
     // fixed grids: the kernels find the number of repeated-segment points on the device
     const unsigned pg = (unsigned)(ctx->sm_count * 8);
     const unsigned need_b = (unsigned)((n_items * RepeatLayout<3>::COLS + kBlock - 1) / kBlock);
@@ -1230,6 +1296,8 @@ void rydcz_destroy(rydcz_ctx* ctx) {
   if (ctx->evc0) cudaEventDestroy(ctx->evc0);
   if (ctx->evc1) cudaEventDestroy(ctx->evc1);
   cudaFree(ctx->plan_counts);
+  cudaFree(ctx->tb_dir); cudaFree(ctx->tb_stamp); cudaFree(ctx->tb_records);
+  if (ctx->tb_ready) cudaEventDestroy(ctx->tb_ready);
   for (int i = 0; i < 6; ++i) cudaFree(ctx->stage[i]);
   for (int i = 0; i < 3; ++i) cudaFree(ctx->plan[i]);
   for (int l = 0; l < rydcz_ctx::kLanes; ++l) {
@@ -1309,6 +1377,28 @@ int rydcz_set_cluster(rydcz_ctx* ctx, int mode) {
   if (!ctx) return 2;
   if (mode < 0 || mode > 2) return fail(ctx, "cluster mode must be 0 (off), 1 (auto) or 2 (wherever eligible)");
   ctx->cluster_mode = mode;
+  return 0;
+}
+
+int rydcz_set_table(rydcz_ctx* ctx, int mode) {
+  if (!ctx) return 2;
+  if (mode < 0 || mode > 2) return fail(ctx, "table mode must be 0 (off), 1 (entries generated per call) or 2 (kept across calls)");
+  if (mode == 1 && ctx->table_mode == 2 && ctx->tb_stamp) ++ctx->tb_epoch;   // forget what the persistent mode kept
+  ctx->table_mode = mode;
+  return 0;
+}
+
+int rydcz_table_stats(rydcz_ctx* ctx, int64_t* entries_generated, int64_t* slots_shared) {
+  if (!ctx) return 2;
+  unsigned long long h[2] = {0, 0};
+  if (ctx->cl_counters) {
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h, ctx->cl_counters + 6, sizeof(h), cudaMemcpyDeviceToHost));
+    CK(cudaMemset(ctx->cl_counters + 6, 0, sizeof(h)));
+  }
+  if (entries_generated) *entries_generated = (int64_t)h[0];
+  if (slots_shared) *slots_shared = (int64_t)h[1];
   return 0;
 }
 
@@ -1439,6 +1529,7 @@ int rydcz_evaluate_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, 
   ctx->call_flags = 0;
   if (enter_call(ctx, st)) return 1;
   if (order_reserve(ctx, n_points, dim != 5)) return 1;
+  if (table_new_call(ctx)) return 1;
   if (int rc = evaluate_impl(ctx, context_scratch(ctx, n_points), dim, noisy, n_points, d_points, d_segs, d_n_seg,
                              max_seg, d_out, d_states, st, 3)) return rc;
   ctx->status_n = n_points;
@@ -1507,6 +1598,7 @@ int rydcz_evaluate_shots_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_po
   ctx->call_flags = 0;
   if (enter_call(ctx, st)) return 1;
   if (order_reserve(ctx, n_items, dim == 3)) return 1;
+  if (table_new_call(ctx)) return 1;
   double* rows = nullptr;
   if (dim == 3 && ctx->cluster_mode) {
     if (grow(ctx, (void**)&ctx->shot_rows, &ctx->shot_rows_cap, (size_t)n_items * PT_STRIDE * sizeof(double))) return 1;
@@ -1744,6 +1836,7 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
   if (grow(ctx, &ctx->plan[2], &ctx->plan_cap[2], n * sizeof(int32_t))) return 1;
   ctx->call_flags = 0;
   if (order_reserve(ctx, n_points * per_item, dim != 5 && (n_shots == 0 || dim == 3))) return 1;
+  if (table_new_call(ctx)) return 1;      // one generation for the whole pipelined call: its chunks share the entries
   if (n_shots > 0 && dim == 3 && ctx->cluster_mode &&
       grow(ctx, (void**)&ctx->shot_rows, &ctx->shot_rows_cap, n * per_item * PT_STRIDE * sizeof(double))) return 1;
   if (sel_out && grow(ctx, &ctx->sel_out, &ctx->sel_out_cap, n * (sel_out->n ? sel_out->n : 1) * sizeof(double))) return 1;

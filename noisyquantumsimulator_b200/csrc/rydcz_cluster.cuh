@@ -37,6 +37,7 @@ constexpr int CL_MAX_SLOTS = 8;    // distinct (duration, |Omega|, Delta) groups
 constexpr int CL_MAX_K = 62;       // terms per (sub)step; longer segments are cut into equal sub-steps
 constexpr int CL_HALF_MAX = (CL_MAX_K + 2) / 2;
 constexpr int CL_HDR = 8;          // doubles of a slot header (two records)
+constexpr int CL_OWN0 = CL_MAX_SLOTS * CL_HDR / CL_REC;     // a point's region: its slot headers first, then its own records
 constexpr int CL_RECORDS = CL_MAX_SLOTS * (CL_MAX_K + 3);   // records per point: header (2) + K + 1 terms per slot
 constexpr int CL_STRIDE = CL_RECORDS * CL_REC;              // doubles per point in the coefficient scratch
 constexpr int CL_ALIGN = 8;        // Clenshaw steps per (sub)step are padded to a multiple of this, so the
@@ -45,6 +46,7 @@ constexpr int CL_ALIGN = 8;        // Clenshaw steps per (sub)step are padded to
 constexpr double CL_Z_MAX = 26.0;  // largest h * freq of one sub-step (keeps K <= CL_MAX_K: 26 + 10.3 * 26^(1/3) + 4 - 2 < 62)
 constexpr double CL_STEP_COST = 3.4;    // one clustered Clenshaw step in units of one plain Chebyshev term
 constexpr double CL_SLOT_COST = 60.0;   // coefficient generation of one slot, same units
+constexpr double CL_SLOT_COST_SHARED = 2.0;   // ... when the slot takes its records from the shared table
 constexpr double CL_SUBSTEP_COST = 3.0; // start vectors of one (sub)step, same units
 
 struct ClusterGeom {
@@ -52,6 +54,7 @@ struct ClusterGeom {
   double rho;   // |q(x)| <= rho on all three clusters
   double freq;  // largest d|x|/d(rho t) * rho on the interval: h * freq bounds the Chebyshev degree
   double damp;  // bound on the real parts (4 x sum of rates)
+  double w0, w1; // half-widths of the central and of the outer clusters (rad/s, slack included)
 };
 
 // D only selects nothing here (the bounds hold for the 3- and 4-level models); kept for symmetry with the callers.
@@ -87,7 +90,7 @@ RYDCZ_HD bool cluster_geometry(double V, double d1, double rates, double om2, do
   if (!(rho <= 0.25 * Vc2 * Vc) || !(rho > 0.0)) return false;
   double y = rho / Vc2;   // largest |y| of the central branch: y (Vc^2 - y^2) = rho
   for (int i = 0; i < 6; ++i) y -= (y * (Vc2 - y * y) - rho) / (Vc2 - 3.0 * y * y);
-  g.Vc = Vc; g.rho = rho; g.freq = rho / (Vc2 - 3.0 * y * y); g.damp = d;
+  g.Vc = Vc; g.rho = rho; g.freq = rho / (Vc2 - 3.0 * y * y); g.damp = d; g.w0 = w0; g.w1 = w1;
   return true;
 }
 
@@ -127,13 +130,101 @@ RYDCZ_HD double cluster_cospi(double x) {
 
 RYDCZ_HD int cluster_roundup(int steps) { return (steps + CL_ALIGN - 1) / CL_ALIGN * CL_ALIGN; }
 
+// ---- the shared coefficient table ------------------------------------------------------------------------------
+// The records of a (sub)step depend on three numbers only: K, theta = h Vc and rho^ = rho / Vc^3 (everything in
+// units of Vc).  And the expansion they encode is a polynomial approximation of exp(theta x) that is accurate
+// wherever x lies in the three clusters it was built for -- so a (sub)step does not need records of its own:
+//
+//     exp(h G) = exp(theta_n (lambda G / Vc)),   theta_n = n CT_DTHETA the grid value next to theta = |h| Vc,
+//                                                lambda = +-theta / theta_n,
+//
+// is evaluated EXACTLY (to the same truncation error) with the records of (theta_n, rho^_c) applied to the operator
+// lambda G / Vc, as long as the spectrum of THAT operator lies inside the table entry's clusters: centre i lambda
+// instead of i (|lambda - 1| <= CT_DTHETA / 2 theta_n) and widths scaled by lambda.  The planner picks the
+// narrowest class c = floor(8 log2(0.25 / rho^_req)) that still contains them; the price is z = theta_n freq^_c up
+// by <= CT_DTHETA plus <= 9 % (one class), about half a term of the ~20-60 a (sub)step needs.
+// In an optimiser population and in the bench every candidate shares (V, |Omega|, Delta): 1.3 M slots of a
+// 262,144-candidate bang-bang batch map onto ~2,000 table entries, which are generated once per call (or kept
+// across calls, rydcz_set_table) and stay in L2 -- the per-slot coefficient kernel (29 % of the step in round 1)
+// and its 4 GB of records per step are gone.  Slots that do not fit the table (theta < 0.25, rho^ < 1e-3,
+// ...) keep records of their own, as before.
+constexpr int CT_CLASSES = 64;               // rho^_c = 0.25 * 2^(-c / 8), c = 0 .. 63 (down to 1.07e-3: V/Omega ~ 2000)
+constexpr double CT_PER_OCTAVE = 8.0;
+constexpr double CT_DTHETA = 0.5;            // grid step in theta = h Vc
+constexpr double CT_Z_MAX = 27.0;            // largest theta_n * freq^_c of an entry (K <= CL_MAX_K)
+constexpr int CT_ENTRY_REC = CL_MAX_K + 1;   // records per entry
+struct ClusterTableDir {
+  double rho[CT_CLASSES], freq[CT_CLASSES], kappa[CT_CLASSES], inv_gs[CT_CLASSES];
+  int base[CT_CLASSES + 1];                  // entry (c, n), n = 1 .. base[c + 1] - base[c], sits at base[c] + n - 1
+};
+inline void cluster_table_dir_init(ClusterTableDir& d) {
+  d.base[0] = 0;
+  for (int c = 0; c < CT_CLASSES; ++c) {
+    const double rho = 0.25 * exp2(-(double)c / CT_PER_OCTAVE);
+    double y = rho;                          // central branch: y (1 - y^2) = rho^
+    for (int i = 0; i < 40; ++i) y -= (y * (1.0 - y * y) - rho) / (1.0 - 3.0 * y * y);
+    const double gs = cbrt(0.5 * rho);
+    d.rho[c] = rho; d.freq[c] = rho / (1.0 - 3.0 * y * y); d.kappa[c] = 1.0 / (gs * gs); d.inv_gs[c] = 1.0 / gs;
+    d.base[c + 1] = d.base[c] + (int)floor(CT_Z_MAX / (d.freq[c] * CT_DTHETA));
+  }
+}
+// The planner's view: the directory, one generation stamp per entry (an entry is valid when its stamp equals
+// `epoch`; whoever changes the stamp generates the records) -- dir == nullptr: no table.
+struct ClusterTable {
+  const ClusterTableDir* dir;
+  unsigned* stamp;
+  unsigned epoch;
+  RYDCZ_HD bool claim(long long e) const {
+    if (!stamp) return false;              // a dry run (cost and eligibility only)
+#ifdef __CUDA_ARCH__
+    return atomicExch(stamp + e, epoch) != epoch;
+#else
+    const bool fresh = stamp[e] != epoch;
+    stamp[e] = epoch;
+    return fresh;
+#endif
+  }
+};
+
 // One slot: `count` consecutive active segments with the same duration, |Omega| and Delta, each advanced
-// in `nsub` equal sub-steps of length h with K + 1 coefficient records.
+// in `nsub` equal sub-steps of length h with K + 1 coefficient records -- its own (entry < 0) or a table entry's.
 struct ClusterSlot {
   ClusterGeom g;
   double h;
   int K, nsub, count;
+  long long entry;        // table entry, -1 = records of its own
+  double kappa, inv_gs;   // what the evaluator needs: (Vc / gs)^2 and the factor that turns G into G~
+  double th, rh;          // what the coefficient generator needs with Vc = 1 (table entries): theta_n, rho^_c
 };
+
+// The table entry for a (sub)step of length h under geometry g, if there is one.
+RYDCZ_HD bool cluster_table_lookup(const ClusterTable& tb, const ClusterGeom& g, double h, ClusterSlot& sl) {
+  if (!tb.dir) return false;
+  const double theta = fabs(h) * g.Vc;
+  const double nn = rint(theta / CT_DTHETA);
+  if (!(nn >= 1.0) || !(nn < 1e8)) return false;
+  const double theta_n = nn * CT_DTHETA, lam = theta / theta_n;
+  const double w1 = fabs(lam - 1.0) + lam * (g.w1 / g.Vc);
+  const double need = fmax(lam * (g.w0 / g.Vc), (1.0 + w1) * w1 * (2.0 + w1));
+  if (!(need <= 0.25) || !(need > 0.0)) return false;
+  int c = (int)floor(CT_PER_OCTAVE * log2(0.25 / need));
+  if (c >= CT_CLASSES) c = CT_CLASSES - 1;
+  if (tb.dir->rho[c] < need) --c;            // (rounding of log2 at a class boundary)
+  if (c < 0) return false;
+  const int n = (int)nn;
+  if (n > tb.dir->base[c + 1] - tb.dir->base[c]) return false;     // theta_n freq^_c > CT_Z_MAX: more sub-steps needed
+  double zs = theta_n * tb.dir->freq[c];
+  if (!(zs >= 1e-2)) zs = 1e-2;
+  int K = cheb_terms(zs) - 2;
+  if (K < 6) K = 6;
+  if (K > CL_MAX_K) return false;
+  sl.K = K;
+  sl.entry = (long long)tb.dir->base[c] + (n - 1);
+  sl.kappa = tb.dir->kappa[c];
+  sl.inv_gs = (h < 0.0 ? -lam : lam) / g.Vc * tb.dir->inv_gs[c];
+  sl.th = theta_n; sl.rh = tb.dir->rho[c];
+  return true;
+}
 
 // Walks the active segments of a point (the ones next_segment visits) and groups them into slots.
 template <int D>
@@ -147,8 +238,9 @@ struct ClusterWalker {
   double last_om2 = -1.0, last_det = 0.0;
   bool last_ok = false;
   ClusterGeom last_g;
-  RYDCZ_HD ClusterWalker(const double* pt_, const double* seg_, int n_seg_, bool noisy, bool sym_)
-      : pt(pt_), seg(seg_), n_seg(n_seg_), s(0), sym(sym_), rates(0.0) {
+  ClusterTable tb;
+  RYDCZ_HD ClusterWalker(const double* pt_, const double* seg_, int n_seg_, bool noisy, bool sym_, const ClusterTable& tb_)
+      : pt(pt_), seg(seg_), n_seg(n_seg_), s(0), sym(sym_), rates(0.0), tb(tb_) {
     if (noisy) {
       rates = pt[PT_G_R1] + pt[PT_G_R0] + pt[PT_G_PHI] + pt[PT_G_SC];
       if (D == 4) rates += pt[PT_G_MJ];
@@ -184,6 +276,20 @@ struct ClusterWalker {
     sl.K = cheb_terms(zs) - 2;
     if (sl.K < 6) sl.K = 6;
     if (sl.K > CL_MAX_K) return -1;
+    sl.entry = -1;
+    {
+      const double gs = cbrt(0.5 * sl.g.rho);
+      sl.kappa = (sl.g.Vc / gs) * (sl.g.Vc / gs);
+      sl.inv_gs = 1.0 / gs;
+      sl.th = 0.0; sl.rh = 0.0;
+    }
+    // records from the shared table where an entry contains this (sub)step; the grid value next to h Vc widens the
+    // clusters a little, so a (sub)step at the very edge of the table's range is tried once more, one piece shorter
+    if (tb.dir && !cluster_table_lookup(tb, sl.g, sl.h, sl) && zs > 0.5 * CL_Z_MAX) {
+      ClusterSlot t2 = sl;
+      t2.h = dt / (double)(sl.nsub + 1);
+      if (cluster_table_lookup(tb, sl.g, t2.h, t2)) { t2.nsub = sl.nsub + 1; sl = t2; }
+    }
     sl.count = 1;
     ++s;
     // absorb the following active segments that repeat (dt, |Omega|, Delta): smooth-JP steps, the second LP pulse
@@ -201,56 +307,75 @@ struct ClusterWalker {
   }
 };
 
-// Slot header (CL_HDR doubles): K + 1024 nsub, kappa = Vc^2 / gs^2, 1 / gs, count + 65536 K_next | h, Vc, rho, 0
-// (K_next = term count of the slot that follows, 0 if there is none: the evaluator's record ring runs across slot
-//  boundaries and must know it before that slot's own header has been read; filled in by cluster_plan)
-// (gs = (rho/2)^(1/3): G~ = G / gs).  The first four are what the evaluator reads; the rest is what
-// cluster_coefficients needs to fill the K + 1 records that follow.
-RYDCZ_HD void cluster_write_header(const ClusterSlot& sl, double* __restrict__ rec) {
-  const double gs = cbrt(0.5 * sl.g.rho);
+// Slot header (CL_HDR doubles; slot q of a point sits at q * CL_HDR of the point's region):
+//   K + 1024 nsub, kappa = (Vc / gs)^2, the factor that turns G into G~ (1 / gs; table: +-lambda / (Vc gs^)),
+//   count + 65536 K_next | where this slot's records are, where the NEXT slot's records are, 0, 0
+// (gs = (rho/2)^(1/3).  K_next = term count of the slot that follows, 0 if there is none: the evaluator's record
+//  ring runs across slot boundaries and must know it, and where those records are, before that slot's own header
+//  has been read.)  A record position >= 0 counts records from the start of the point's region (records of its
+//  own, from CL_OWN0 on); -(1 + r) is record r of the shared table.
+RYDCZ_HD double cluster_terms_position(const ClusterSlot& sl, int own_offset) {
+  return sl.entry >= 0 ? -(double)(1 + sl.entry * CT_ENTRY_REC) : (double)own_offset;
+}
+RYDCZ_HD void cluster_write_header(const ClusterSlot& sl, double position, double* __restrict__ rec) {
   rec[0] = (double)(sl.K + 1024 * sl.nsub);
-  rec[1] = (sl.g.Vc / gs) * (sl.g.Vc / gs);
-  rec[2] = 1.0 / gs;
+  rec[1] = sl.kappa;
+  rec[2] = sl.inv_gs;
   rec[3] = (double)sl.count;
-  rec[4] = sl.h;
-  rec[5] = sl.g.Vc;
-  rec[6] = sl.g.rho;
+  rec[4] = position;
+  rec[5] = 0.0;
+  rec[6] = 0.0;
   rec[7] = 0.0;
 }
+RYDCZ_HD const double* cluster_terms_at(double position, const double* __restrict__ rec, const double* __restrict__ table) {
+  const long long v = (long long)position;
+  return v >= 0 ? rec + v * CL_REC : table + (-(v + 1)) * CL_REC;
+}
 
-// Records the clustered path needs for a point (0 = not eligible) and its cost in plain Chebyshev terms.
-// With `rec` the slot headers are written on the way (at the positions the evaluator will find them);
-// slot_K / slot_off receive the term count and the record offset of every slot.
-// `dense` (optional, 4 doubles per slot): what cluster_coefficients needs of each header -- K + 1024 nsub, h, Vc,
-// rho -- in a compact array, so that the coefficient kernel does not start with a scattered read of the records.
+// Records the clustered path needs in the point's region (0 = not eligible) and its cost in plain Chebyshev terms.
+// With `rec` the slot headers are written on the way.  Per slot q: slot_K[q] = term count of a coefficient task to
+// run (0: none -- no such slot, or a table entry somebody else generates), slot_val[q] = where that task writes
+// (record index in the point's region, or 0x80000000 | table entry), `dense` (4 doubles per slot) = what
+// cluster_coefficients_of needs for it: K (+ 1024 nsub), h, Vc, rho.  `shared_tasks` gets a bit per slot whose
+// task fills a TABLE entry: those must run even if the caller does not take the clustered path for this point
+// (other points may already count on the entry).
 template <int D>
 RYDCZ_HD int cluster_plan(const double* pt, const double* seg, int n_seg, bool noisy, bool sym, double& cost,
-                          int* __restrict__ slot_K = nullptr, int* __restrict__ slot_off = nullptr,
+                          const ClusterTable& tb, unsigned& shared_tasks,
+                          int* __restrict__ slot_K = nullptr, unsigned* __restrict__ slot_val = nullptr,
                           double* __restrict__ rec = nullptr, double* __restrict__ dense = nullptr) {
-  ClusterWalker<D> w(pt, seg, n_seg, noisy, sym);
+  ClusterWalker<D> w(pt, seg, n_seg, noisy, sym, tb);
   ClusterSlot sl;
-  int records = 0, slots = 0;
+  int records = CL_OWN0, slots = 0;
   double* prev_hdr = nullptr;
   cost = 0.0;
+  shared_tasks = 0u;
   for (;;) {
     const int r = w.next(sl);
     if (r < 0) return 0;
     if (r == 0) break;
     if (++slots > CL_MAX_SLOTS) return 0;
-    if (slot_K) slot_K[slots - 1] = sl.K;
-    if (slot_off) slot_off[slots - 1] = records;
+    const int q = slots - 1;
+    const bool shared = sl.entry >= 0;
+    const bool generate = shared ? tb.claim(sl.entry) : true;
+    if (shared && generate) shared_tasks |= 1u << q;
+    if (slot_K) slot_K[q] = generate ? sl.K : 0;
+    if (slot_val) slot_val[q] = shared ? (0x80000000u | (unsigned)sl.entry) : (unsigned)records;
+    const double position = cluster_terms_position(sl, records);
     if (rec) {
-      cluster_write_header(sl, rec + (long long)records * CL_REC);
-      if (prev_hdr) prev_hdr[3] += 65536.0 * (double)sl.K;       // the previous slot learns this slot's term count
-      prev_hdr = rec + (long long)records * CL_REC;
+      cluster_write_header(sl, position, rec + q * CL_HDR);
+      if (prev_hdr) { prev_hdr[3] += 65536.0 * (double)sl.K; prev_hdr[5] = position; }   // the previous slot learns about this one
+      prev_hdr = rec + q * CL_HDR;
     }
     if (dense) {
-      double* d = dense + (slots - 1) * 4;
-      d[0] = (double)(sl.K + 1024 * sl.nsub); d[1] = sl.h; d[2] = sl.g.Vc; d[3] = sl.g.rho;
+      double* d = dense + q * 4;
+      d[0] = (double)(sl.K + 1024 * sl.nsub);
+      if (shared) { d[1] = sl.th; d[2] = 1.0; d[3] = sl.rh; }
+      else { d[1] = sl.h; d[2] = sl.g.Vc; d[3] = sl.g.rho; }
     }
-    records += sl.K + 3;
+    if (!shared) records += sl.K + 1;
     cost += (double)sl.count * (double)sl.nsub * (CL_STEP_COST * (double)cluster_roundup(sl.K + 2) + CL_SUBSTEP_COST) +
-            CL_SLOT_COST;
+            (shared ? CL_SLOT_COST_SHARED : CL_SLOT_COST);
   }
   return slots == 0 ? 0 : records;
 }
@@ -295,10 +420,6 @@ RYDCZ_HD double cluster_root_y(double c) {
 #endif
 RYDCZ_HD void cluster_coefficients_of(int K, double h, double Vc, double rho, double* __restrict__ out,
                                       double* __restrict__ A, int a_stride, int m, int G);
-// ... from the slot header in the records themselves (the host harness)
-RYDCZ_HD void cluster_coefficients(double* __restrict__ rec, double* __restrict__ A, int a_stride, int m, int G) {
-  cluster_coefficients_of((int)rec[0] & 1023, rec[4], rec[5], rec[6], rec + CL_HDR, A, a_stride, m, G);
-}
 // ... from (K, h, Vc, rho) handed over directly; `out` = the K + 1 records behind the slot header
 RYDCZ_HD void cluster_coefficients_of(int K, double h, double Vc, double rho, double* __restrict__ out,
                                       double* __restrict__ A, int a_stride, int m, int G) {
@@ -397,17 +518,30 @@ RYDCZ_HD void cluster_coefficients_of(int K, double h, double Vc, double rho, do
 #undef RYDCZ_A
 }
 
-// All slots of a point, one after the other (the host harness; the GPU runs one thread per slot).
+// All coefficient tasks of a point, one after the other (the host harness; the GPU runs four lanes per task).
+// `table` = the shared table's records (entries generated here when this point is the first to claim them).
+// Returns the number of table entries it generated.
 template <int D>
-RYDCZ_HD void cluster_prepare(const double* pt, const double* seg, int n_seg, bool noisy, bool sym,
-                              double* __restrict__ rec) {
-  int slot_K[CL_MAX_SLOTS], slot_off[CL_MAX_SLOTS];
+RYDCZ_HD int cluster_prepare(const double* pt, const double* seg, int n_seg, bool noisy, bool sym,
+                             double* __restrict__ rec, const ClusterTable& tb, double* __restrict__ table) {
+  int slot_K[CL_MAX_SLOTS];
+  unsigned slot_val[CL_MAX_SLOTS], shared_tasks = 0u;
+  double dense[CL_MAX_SLOTS * 4];
   for (int q = 0; q < CL_MAX_SLOTS; ++q) slot_K[q] = 0;
   double cost;
-  if (cluster_plan<D>(pt, seg, n_seg, noisy, sym, cost, slot_K, slot_off, rec) <= 0) return;
+  const int records = cluster_plan<D>(pt, seg, n_seg, noisy, sym, cost, tb, shared_tasks, slot_K, slot_val, rec, dense);
   double A[6 * CL_HALF_MAX];
-  for (int q = 0; q < CL_MAX_SLOTS && slot_K[q] > 0; ++q)
-    cluster_coefficients(rec + (long long)slot_off[q] * CL_REC, A, 1, 0, 1);
+  int generated = 0;
+  for (int q = 0; q < CL_MAX_SLOTS; ++q) {
+    if (slot_K[q] <= 0) continue;
+    const bool shared = (slot_val[q] & 0x80000000u) != 0u;
+    if (!shared && records <= 0) continue;
+    if (shared) ++generated;
+    double* out = shared ? table + (long long)(slot_val[q] & 0x7fffffffu) * (CT_ENTRY_REC * CL_REC)
+                         : rec + (long long)slot_val[q] * CL_REC;
+    cluster_coefficients_of(slot_K[q], dense[q * 4 + 1], dense[q * 4 + 2], dense[q * 4 + 3], out, A, 1, 0, 1);
+  }
+  return generated;
 }
 
 // One Clenshaw step of the clustered expansion:  dst <- C_k x + (2 S~) src + dst,
@@ -444,11 +578,11 @@ RYDCZ_HD void cluster_step(const double* __restrict__ c, double kappa, double d0
 // by CL_LOOKAHEAD columns: the NEXT segment row and the NEXT slot header, copied asynchronously one transition
 // ahead, so that a transition reads shared memory instead of waiting for two dependent global loads (ncu,
 // round 2: those two loads were 12 % of the kernel's stall samples).
-constexpr int CL_LOOKAHEAD = 8;     // per-thread columns behind the record ring: segment row (4) + slot header (4)
+constexpr int CL_LOOKAHEAD = 10;    // per-thread columns behind the record ring: segment row (4) + slot header (6)
 template <class Sys, int RING, class XC>
 RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const XC rc, const PointView pt,
                                  const double* __restrict__ seg, int n_seg, bool noisy,
-                                 const double* __restrict__ rec, double& steps) {
+                                 const double* __restrict__ rec, const double* __restrict__ table, double& steps) {
   constexpr int N = Sys::N;
   constexpr int LA = 3 * RING;      // first lookahead column
   static_assert((RING & (RING - 1)) == 0 && RING >= 2, "ring size");
@@ -459,6 +593,7 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const XC rc, 
   double kappa = 0.0, inv_gs = 0.0;
   const double* terms = rec;
   const double* hdr_next = rec;       // header of the slot after the current one
+  double next_position = 0.0;         // where that slot's records are (cluster_terms_at)
   // the (sub)step after the current one, for the ring: its records and term count (nK < 0: there is none)
   const double* nterms = rec;
   int nK = -1, K_next = 0;
@@ -488,7 +623,7 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const XC rc, 
 #define RYDCZ_LOOKAHEAD_HEADER(hh)                                                              \
   do {                                                                                          \
     RYDCZ_UNROLL                                                                                \
-    for (int q_ = 0; q_ < 4; ++q_) RYDCZ_ASYNC_COPY8(&rc[LA + 4 + q_], (hh) + q_);              \
+    for (int q_ = 0; q_ < 6; ++q_) RYDCZ_ASYNC_COPY8(&rc[LA + 4 + q_], (hh) + q_);              \
   } while (0)
   // the first row and the first header: their latency is paid once per system, before the first transition
   if (n_seg > 0) RYDCZ_LOOKAHEAD_ROW(0);
@@ -527,9 +662,10 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const XC rc, 
           kappa = rc[LA + 5]; inv_gs = rc[LA + 6];
           const int cn = (int)rc[LA + 7];
           seg_left = cn & 0xffff; K_next = cn >> 16;
-          terms = hdr_next + CL_HDR;
-          hdr_next = terms + (K + 1) * CL_REC;
-          RYDCZ_LOOKAHEAD_HEADER(hdr_next);          // (past the last slot: the next point's region, or the pad)
+          terms = cluster_terms_at(rc[LA + 8], rec, table);
+          next_position = rc[LA + 9];
+          hdr_next += CL_HDR;
+          RYDCZ_LOOKAHEAD_HEADER(hdr_next);          // (past the last slot: the point's own records, harmless)
         }
         --seg_left;
         if (s < n_seg) RYDCZ_LOOKAHEAD_ROW(s);       // these copies join the first ring group committed below
@@ -557,7 +693,7 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const XC rc, 
       // The ring is about to run past this (sub)step: what comes next?  The same records again (further sub-steps,
       // or further segments of this slot), or the next slot, whose term count this slot's header carries.
       if (sub_left > 0 || seg_left > 0) { nterms = terms; nK = K; }
-      else if (K_next > 0) { nterms = hdr_next + CL_HDR; nK = K_next; }
+      else if (K_next > 0) { nterms = cluster_terms_at(next_position, rec, table); nK = K_next; }
       else { nterms = terms; nK = 0; }
     }
     // step k: b2 <- C_k x + 2S~ b1 + b2      (priming: b1 = x, and both vectors restart from zero afterwards)
@@ -606,6 +742,7 @@ template <int D> struct ClusterRing { static constexpr int value = D == 3 ? 8 : 
   RYDCZ_HD bool evaluate_point_cluster_d##D(const PointView pt, const Col xcol, const Col rcol,     \
                                             const double* __restrict__ seg, int n_seg,              \
                                             const double* __restrict__ rec,                         \
+                                            const double* __restrict__ table,                       \
                                             double* __restrict__ out, double* __restrict__ states) {\
     typedef StateLayout<D> SL;                                                                      \
     double steps = 0.0, flops = 0.0, st;                                                            \
@@ -615,7 +752,7 @@ template <int D> struct ClusterRing { static constexpr int value = D == 3 ? 8 : 
     double xcoh[Sys_coh11s_d##D::N];                                                                \
     if (NOISY) {                                                                                    \
       double x[Sys_rho11s_d##D::N]; st = 0.0;                                                       \
-      run_system_cluster<Sys_rho11s_d##D, ClusterRing<D>::value>(x, xcol, rcol, pt, seg, n_seg, true, rec, st); \
+      run_system_cluster<Sys_rho11s_d##D, ClusterRing<D>::value>(x, xcol, rcol, pt, seg, n_seg, true, rec, table, st); \
       RYDCZ_RECONVERGE(pt.live);                                                                    \
       steps += st; flops += st * 2.0 * (3 * Sys_rho11s_d##D::NNZ + 4 * Sys_rho11s_d##D::N);         \
       p11 = x[RHO11S_POP_D##D];                                                                     \
@@ -628,7 +765,7 @@ template <int D> struct ClusterRing { static constexpr int value = D == 3 ? 8 : 
     {                                                                                               \
       double (&x)[Sys_coh11s_d##D::N] = xcoh;                                                       \
       st = 0.0;                                                                                     \
-      run_system_cluster<Sys_coh11s_d##D, ClusterRing<D>::value>(x, xcol, rcol, pt, seg, n_seg, NOISY, rec, st); \
+      run_system_cluster<Sys_coh11s_d##D, ClusterRing<D>::value>(x, xcol, rcol, pt, seg, n_seg, NOISY, rec, table, st); \
       RYDCZ_RECONVERGE(pt.live);                                                                    \
       steps += st; flops += st * 2.0 * (3 * Sys_coh11s_d##D::NNZ + 4 * Sys_coh11s_d##D::N);         \
       c11r = x[COH11S_RE_D##D]; c11i = x[COH11S_IM_D##D];                                           \
@@ -677,8 +814,8 @@ constexpr int CL_RING_GENERAL = 4;   // 75 start-vector columns + a four-slot re
 template <bool NOISY>
 RYDCZ_HD bool evaluate_point_cluster_general_d3(const PointView pt, const Col xcol, const Col rcol,
                                                 const double* __restrict__ seg, int n_seg,
-                                                const double* __restrict__ rec, double* __restrict__ out,
-                                                double* __restrict__ states) {
+                                                const double* __restrict__ rec, const double* __restrict__ table,
+                                                double* __restrict__ out, double* __restrict__ states) {
   typedef StateLayout<3> SL;
   double steps = 0.0, flops = 0.0, st;
   double p01 = 1.0, p10 = 1.0, p11 = 1.0, loss = 0.0, ryd = 0.0;
@@ -686,7 +823,7 @@ RYDCZ_HD bool evaluate_point_cluster_general_d3(const PointView pt, const Col xc
   bool ok = true;
   if (NOISY) {
     double x[Sys_rho11_d3::N]; st = 0.0;
-    run_system_cluster<Sys_rho11_d3, CL_RING_GENERAL>(x, xcol, rcol, pt, seg, n_seg, true, rec, st);
+    run_system_cluster<Sys_rho11_d3, CL_RING_GENERAL>(x, xcol, rcol, pt, seg, n_seg, true, rec, table, st);
     RYDCZ_RECONVERGE(pt.live);
     steps += st; flops += st * 2.0 * (3 * Sys_rho11_d3::NNZ + 4 * Sys_rho11_d3::N);
     p11 = x[RHO11_POP_D3];
@@ -696,7 +833,7 @@ RYDCZ_HD bool evaluate_point_cluster_general_d3(const PointView pt, const Col xc
   }
   {
     double x[Sys_coh11_d3::N]; st = 0.0;
-    run_system_cluster<Sys_coh11_d3, CL_RING_GENERAL>(x, xcol, rcol, pt, seg, n_seg, NOISY, rec, st);
+    run_system_cluster<Sys_coh11_d3, CL_RING_GENERAL>(x, xcol, rcol, pt, seg, n_seg, NOISY, rec, table, st);
     RYDCZ_RECONVERGE(pt.live);
     steps += st; flops += st * 2.0 * (3 * Sys_coh11_d3::NNZ + 4 * Sys_coh11_d3::N);
     c11r = x[COH11_RE_D3]; c11i = x[COH11_IM_D3];

@@ -338,6 +338,17 @@ class Evaluator:
         """Clustered-spectrum propagation: 0 = never, 1 = where cheaper (default), 2 = wherever eligible."""
         self._check(self.lib.rydcz_set_cluster(self.ctx, int(mode)), "rydcz_set_cluster")
 
+    def set_table(self, mode: int):
+        """Shared coefficient table of the clustered path: 0 = off (records per slot), 1 = entries generated once
+        per call (default), 2 = kept across calls."""
+        self._check(self.lib.rydcz_set_table(self.ctx, int(mode)), "rydcz_set_table")
+
+    def table_stats(self):
+        """(table entries generated, slots of clustered points that read the table) since the last call."""
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self.lib.rydcz_table_stats(self.ctx, C.byref(a), C.byref(b)), "rydcz_table_stats")
+        return int(a.value), int(b.value)
+
     def cluster_stats(self, with_records: bool = False):
         """(points planned onto the clustered path, points handed back to the plain path[, coefficient
         records written]) since the last call."""

@@ -107,11 +107,16 @@ def load_hostsim():
     lib.hostsim_allow_sym.argtypes = [ctypes.c_int]
     lib.hostsim_set_cluster.argtypes = [ctypes.c_int]
 
-    def evaluate(dim, noisy, points, segs, n_seg, want_states=True, allow_sym=True, cluster=0):
+    lib.hostsim_set_table.argtypes = [ctypes.c_int]
+    lib.hostsim_table_generated.restype = ctypes.c_longlong
+
+    def evaluate(dim, noisy, points, segs, n_seg, want_states=True, allow_sym=True, cluster=0, table=1):
         """cluster: 0 = plain Chebyshev path, 1 = clustered-spectrum path where the planner prefers it,
-        2 = wherever it is eligible (csrc/rydcz_cluster.cuh)."""
+        2 = wherever it is eligible (csrc/rydcz_cluster.cuh).  table: 0 = every slot generates coefficient records
+        of its own, 1 = shared table, entries generated once per call, 2 = kept across calls."""
         lib.hostsim_allow_sym(int(allow_sym))
         lib.hostsim_set_cluster(int(cluster))
+        lib.hostsim_set_table(int(table))
         import ctypes as C
         points = np.ascontiguousarray(points, dtype=np.float64)
         segs = np.ascontiguousarray(segs, dtype=np.float64)
@@ -135,6 +140,7 @@ def load_hostsim():
 
     lib.hostsim_repeat_used.restype = ctypes.c_longlong
     evaluate.repeat_used = lambda: int(lib.hostsim_repeat_used())
+    evaluate.table_generated = lambda: int(lib.hostsim_table_generated())
     evaluate.cluster_stats = cluster_stats
     evaluate.lib = lib
     return evaluate

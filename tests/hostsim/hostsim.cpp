@@ -7,6 +7,7 @@
 #include "../../noisyquantumsimulator_b200/csrc/rydcz_core.cuh"
 #include "../../noisyquantumsimulator_b200/csrc/rydcz_prologue.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 static int g_allow_sym = 1;
@@ -22,22 +23,49 @@ extern "C" void hostsim_cluster_stats(long long* used, long long* retried) {
   g_cluster_used = 0; g_cluster_retry = 0;
 }
 
+// shared coefficient table (csrc/rydcz_cluster.cuh): 0 = every slot generates records of its own, 1 = table entries
+// generated once per hostsim_evaluate call, 2 = kept across calls.  The records live in one lazily committed
+// calloc block (1.2 GB of address space, only the entries that are used get touched).
+static int g_table_mode = 1;
+static rydcz::ClusterTableDir g_dir;
+static std::vector<unsigned> g_stamp;
+static double* g_table = nullptr;
+static unsigned g_epoch = 1;
+static long long g_table_generated = 0;
+extern "C" void hostsim_set_table(int mode) { g_table_mode = mode; }
+extern "C" long long hostsim_table_generated() { const long long n = g_table_generated; g_table_generated = 0; return n; }
+static rydcz::ClusterTable host_table() {
+  using namespace rydcz;
+  if (!g_table_mode) return ClusterTable{nullptr, nullptr, 0u};
+  if (!g_table) {
+    cluster_table_dir_init(g_dir);
+    g_stamp.assign((size_t)g_dir.base[CT_CLASSES], 0u);
+    g_table = (double*)calloc((size_t)g_dir.base[CT_CLASSES] * CT_ENTRY_REC * CL_REC + 512, sizeof(double));
+  }
+  return ClusterTable{&g_dir, g_stamp.data(), g_epoch};
+}
+// the same directory without the stamps: cluster_plan then claims nothing (cost and eligibility only)
+static rydcz::ClusterTable dry(const rydcz::ClusterTable& tb) { return rydcz::ClusterTable{tb.dir, nullptr, 0u}; }
+
 template <int D>
 static bool try_cluster(const rydcz::PointView pt, const double* row, const double* sg, int ns, bool noisy,
                         double* o, double* st) {
   using namespace rydcz;
   double cost = 0.0;
-  const int records = cluster_plan<D>(row, sg, ns, noisy, true, cost);
+  const ClusterTable tb = host_table();
+  // (like plan_kernel: the headers are written, and table entries claimed and generated, before the path is chosen)
+  std::vector<double> rec((size_t)CL_STRIDE + 512, 0.0);    // (+ pad: header lookahead and ring prefetch past the last slot)
+  unsigned shared_tasks = 0u;
+  const int records = cluster_plan<D>(row, sg, ns, noisy, true, cost, dry(tb), shared_tasks);
   if (records <= 0 || records > CL_RECORDS) return false;
   if (g_cluster == 1 && !(cost < 0.8 * point_work<D>(row, sg, ns))) return false;
-  std::vector<double> rec((size_t)CL_STRIDE + 512, 0.0);    // (+ pad: header lookahead and ring prefetch past the last slot)
-  cluster_prepare<D>(row, sg, ns, noisy, true, rec.data());
+  g_table_generated += cluster_prepare<D>(row, sg, ns, noisy, true, rec.data(), tb, g_table);
   double xc[3 * (21 + 6)], ring[3 * 8 + CL_LOOKAHEAD];
   bool ok;
-  if (D == 3) ok = noisy ? evaluate_point_cluster_d3<true>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), o, st)
-                         : evaluate_point_cluster_d3<false>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), o, st);
-  else ok = noisy ? evaluate_point_cluster_d4<true>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), o, st)
-                  : evaluate_point_cluster_d4<false>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), o, st);
+  if (D == 3) ok = noisy ? evaluate_point_cluster_d3<true>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), g_table, o, st)
+                         : evaluate_point_cluster_d3<false>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), g_table, o, st);
+  else ok = noisy ? evaluate_point_cluster_d4<true>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), g_table, o, st)
+                  : evaluate_point_cluster_d4<false>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), g_table, o, st);
   ++g_cluster_used;
   if (!ok) ++g_cluster_retry;
   return ok;
@@ -48,14 +76,16 @@ static bool try_cluster_general(const rydcz::PointView pt, const double* row, co
                                 double* o, double* st) {
   using namespace rydcz;
   double cost = 0.0;
-  const int records = cluster_plan<3>(row, sg, ns, noisy, false, cost);
+  const ClusterTable tb = host_table();
+  unsigned shared_tasks = 0u;
+  const int records = cluster_plan<3>(row, sg, ns, noisy, false, cost, dry(tb), shared_tasks);
   if (records <= 0 || records > CL_RECORDS) return false;
   if (g_cluster == 1 && !(cost < 0.8 * point_work<3>(row, sg, ns))) return false;
   std::vector<double> rec((size_t)CL_STRIDE + 512, 0.0);    // (+ pad: header lookahead and ring prefetch past the last slot)
-  cluster_prepare<3>(row, sg, ns, noisy, false, rec.data());
+  g_table_generated += cluster_prepare<3>(row, sg, ns, noisy, false, rec.data(), tb, g_table);
   double xc[3 * 25], ring[3 * 8 + CL_LOOKAHEAD];
-  const bool ok = noisy ? evaluate_point_cluster_general_d3<true>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), o, st)
-                        : evaluate_point_cluster_general_d3<false>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), o, st);
+  const bool ok = noisy ? evaluate_point_cluster_general_d3<true>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), g_table, o, st)
+                        : evaluate_point_cluster_general_d3<false>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), g_table, o, st);
   ++g_cluster_used;
   if (!ok) ++g_cluster_retry;
   return ok;
@@ -65,12 +95,15 @@ static bool try_cluster_general(const rydcz::PointView pt, const double* row, co
 extern "C" int hostsim_cluster_records(int dim, int noisy, const double* point, const double* segs, int n_seg,
                                        double* rec, double* cost) {
   using namespace rydcz;
-  const int records = dim == 3 ? cluster_plan<3>(point, segs, n_seg, noisy != 0, true, *cost)
-                               : cluster_plan<4>(point, segs, n_seg, noisy != 0, true, *cost);
+  // (records of the point's own: the table is left out, so the test sees every slot's coefficients in `rec`)
+  const ClusterTable none{nullptr, nullptr, 0u};
+  unsigned shared_tasks = 0u;
+  const int records = dim == 3 ? cluster_plan<3>(point, segs, n_seg, noisy != 0, true, *cost, none, shared_tasks)
+                               : cluster_plan<4>(point, segs, n_seg, noisy != 0, true, *cost, none, shared_tasks);
   if (records > CL_RECORDS) return -records;
   if (records > 0 && rec) {
-    if (dim == 3) cluster_prepare<3>(point, segs, n_seg, noisy != 0, true, rec);
-    else cluster_prepare<4>(point, segs, n_seg, noisy != 0, true, rec);
+    if (dim == 3) cluster_prepare<3>(point, segs, n_seg, noisy != 0, true, rec, none, nullptr);
+    else cluster_prepare<4>(point, segs, n_seg, noisy != 0, true, rec, none, nullptr);
   }
   return records;
 }
@@ -80,6 +113,7 @@ extern "C" int hostsim_evaluate(int dim, int noisy, long long n_points, const do
                                 double* states) {
   using namespace rydcz;
   const int stride = dim == 5 ? PT5_STRIDE : PT_STRIDE;
+  if (g_table_mode == 1) ++g_epoch;      // table entries are generated once per call
   for (long long i = 0; i < n_points; ++i) {
     double row[PT_MAX_STRIDE + PT_SCRATCH];
     for (int k = 0; k < (dim == 5 ? (int)PT5_USED : (int)PT_STRIDE); ++k) row[k] = points[i * stride + k];

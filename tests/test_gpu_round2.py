@@ -301,6 +301,7 @@ def test_shaped_lp_pulses_on_the_device_prologue(evaluator):
     the host-prologue route and to the reference-run fixtures; the shapes that degenerate to a constant amplitude
     (gaussian, blackman) take the repeated-segment path, the cosine envelope the plain one."""
     from noisyquantumsimulator_b200 import rydberg_gates as rg
+    from noisyquantumsimulator_b200.engine import get_evaluator
     rng = np.random.default_rng(2)
     B = 96
     base = dict(laser_1_power=50e-6, laser_1_waist=50e-6, laser_2_power=10 ** rng.uniform(-0.8, 0.3, B), laser_2_waist=50e-6,
@@ -308,7 +309,7 @@ def test_shaped_lp_pulses_on_the_device_prologue(evaluator):
     for shape, want in (("gaussian", 5), ("cosine", 1), ("blackman", 5)):
         for noise in (True, False):
             a = rg.simulate_CZ_gate_batch("lp", B=B, pulse_shape=shape, prologue="device", include_noise=noise, **base)
-            status = evaluator.point_status(B) & 0x0f
+            status = get_evaluator(0).point_status(B) & 0x0f     # (the context simulate_CZ_gate_batch runs on)
             b = rg.simulate_CZ_gate_batch("lp", B=B, pulse_shape=shape, prologue="host", include_noise=noise, **base)
             assert np.abs(a.raw[:, :14] - b.raw[:, :14]).max() < 1e-9, (shape, noise)
             assert (status == want).all(), (shape, noise, np.unique(status))
