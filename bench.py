@@ -417,12 +417,21 @@ def run_ours(args, rank, world, local_rank):
     from noisyquantumsimulator_b200.rydberg_gates import device_prologue as dpro
     from noisyquantumsimulator_b200.rydberg_gates.simulation import METRIC_OUTPUTS
 
-    cand = make_candidates(B_PER_GPU, 1234 + rank)
+    # N_ROT distinct candidate batches, used in turn: the apparatus block of one batch is 84 MB (40 slots x 262,144
+    # doubles), so consecutive timed iterations never find their inputs in the 126 MB L2 -- no flush kernel inside
+    # the step (timing rule: "flush L2 or use inputs larger than L2").  The last batch is the one checked for parity.
+    N_ROT = max(2, math.ceil(3 * 126e6 / (40 * 8 * B_PER_GPU)))
+    cands = [make_candidates(B_PER_GPU, 1234 + rank + 1000 * j) for j in range(N_ROT)]
+    cand = cands[0]
     mk, ak = dpro.split_kwargs(dict(MEDIUM, **cand))
     model = dpro.model_constants("jp", n_segments=N_SEG, **mk)
-    app = dpro.pack_apparatus("jp", B_PER_GPU, **ak)                 # [40, B] apparatus block
-    d_app = torch.from_numpy(app).to(dev)
+    d_apps = []
+    for cj in cands:
+        _, akj = dpro.split_kwargs(dict(MEDIUM, **cj))
+        d_apps.append(torch.from_numpy(dpro.pack_apparatus("jp", B_PER_GPU, **akj)).to(dev))   # [40, B] apparatus block
+    d_app = d_apps[0]
     d_out = torch.empty((B_PER_GPU, 16), dtype=torch.float64, device=dev)
+    step_no = [0]
     gathered = torch.empty((world * B_PER_GPU,), dtype=torch.float64, device=dev) if world > 1 else None
 
     dfma_peak, dmma_peak = ev.fp64_peak()
@@ -453,19 +462,21 @@ def run_ours(args, rank, world, local_rank):
 
     def step():
         # inputs resident in HBM: prologue kernel -> planner -> evaluate kernels -> score all-gather
-        b.flush.zero_()
-        ev.simulate_device(model, d_app, out=d_out)
+        ev.simulate_device(model, d_apps[step_no[0] % N_ROT], out=d_out)
+        step_no[0] += 1
         if world > 1:
             dist.all_gather_into_tensor(gathered, d_out[:, 0].contiguous())
 
     for _ in range(max(args.warmup, 3)):
         step()
+    step_no[0] = 1        # the timed loop ends on batch 0 when steps is a multiple of N_ROT; otherwise re-run it below
     b.barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = ev.launch_count()
     ev.cluster_stats()
+    ev.table_stats()
     kernel_ms, coef_ms = [], []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     b.barrier()
@@ -481,6 +492,7 @@ def run_ours(args, rank, world, local_rank):
     total_ms = b.max_over_ranks(e0.elapsed_time(e1))
     launches = ev.launch_count() - launches0
     cl_planned, cl_back, cl_records = ev.cluster_stats(with_records=True)
+    tb_entries, tb_slots = ev.table_stats()
     flags, n_unsupported = ev.call_flags()
     value = world * B_PER_GPU * args.steps / (total_ms * 1e-3)
 
@@ -504,8 +516,14 @@ def run_ours(args, rank, world, local_rank):
         sampler.stop_flag = True
         sampler.join(timeout=2)
 
+    # kernel-counted flops per launch: mean over the batches the timed loop cycled through (re-run here, not timed);
+    # batch 0 last: it is the one the end-to-end call and the parity check use
+    fl = []
+    for j in list(range(1, N_ROT)) + [0]:
+        ev.simulate_device(model, d_apps[j], out=d_out)
+        fl.append(float(d_out[:, 15].sum().item()))
+    flops_per_launch = float(np.mean(fl))
     out_np = d_out.cpu().numpy()
-    flops_per_launch = float(out_np[:, 15].sum())
     k_ms = float(np.mean(kernel_ms))
     c_ms = float(np.mean(coef_ms))
     achieved = flops_per_launch / (k_ms * 1e-3) * 1e-12
@@ -588,7 +606,9 @@ def run_ours(args, rank, world, local_rank):
                        "propagation": ("clustered-spectrum Chebyshev (csrc/rydcz_cluster.cuh)" if clustered
                                        else "single-interval Chebyshev"),
                        "segments": N_SEG, "apparatus": "medium (RG/optimize_cz_gate.py:196-213), full noise",
-                       "l2": "256 MiB flush write between timed iterations", "parallelism": f"shard{world}",
+                       "l2": f"{N_ROT} distinct input batches of {40 * 8 * B_PER_GPU / 1e6:.0f} MB used in turn "
+                             "(inputs larger than the 126 MB L2; no flush kernel inside the step)",
+                       "parallelism": f"shard{world}",
                        "host_cpus_bound_to_gpu": b.bound_cpus,
                        "mean_fidelity": float(out_np[:, 0].mean())},
             "clocks": sampler.summary(),
@@ -607,6 +627,10 @@ def run_ours(args, rank, world, local_rank):
                          # capture of this command (profiles/ncu_traffic.json), scaled to this batch size
                          "traffic": traffic, "traffic_kernel": traffic_kernel, "traffic_source": traffic_src,
                          "algorithmic_bytes": alg_bytes, "coefficient_record_bytes": record_bytes,
+                         # shared coefficient table (rydcz_set_table mode 1: entries generated again in EVERY step):
+                         # slots of the step's candidates that read the table / entries generated for them
+                         "table_slots_per_step": tb_slots / max(args.steps, 1),
+                         "table_entries_generated_per_step": tb_entries / max(args.steps, 1),
                          "kernel": ("rydcz::evaluate_cluster_kernel<3,true,true>" if clustered
                                     else "rydcz::evaluate_kernel<3,true,false,true>"),
                          # device span from the first to the last evaluate kernel of the step (several launches:

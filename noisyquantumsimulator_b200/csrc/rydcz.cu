@@ -106,13 +106,13 @@ struct PlanCounts {
   unsigned group_count[kGroups];
   unsigned n_tasks;              // coefficient tasks of this batch
   unsigned retries;              // clustered points handed back to the plain kernels in this call
-  unsigned pad[2];
+  unsigned tb_nlo, tb_hi1;       // shared coefficient table: ~(lowest requested entry), highest requested entry + 1 (0: none)
 };
 
 __device__ __forceinline__ unsigned work_bin(double w) {
   // 16 bins per octave: floor(16 log2(w)), w >= 1
-  const double x = fmax(w, 1.0);
-  const int b = (int)(16.0 * log2(x));
+  const float x = fmaxf((float)w, 1.0f);
+  const int b = (int)(16.0f * log2f(x));
   return (unsigned)(b < 0 ? 0 : (b > kWorkBins - 1 ? kWorkBins - 1 : b));
 }
 
@@ -126,6 +126,7 @@ struct PlanShared {
   unsigned tsk[kTaskBins];
   unsigned tbase[kTaskBins];
 };
+static_assert(sizeof(ClusterTableDir) % sizeof(int) == 0, "directory is copied word by word");
 __device__ __forceinline__ void plan_shared_clear(PlanShared& sh, bool with_base) {
   for (int b = threadIdx.x; b < kBins; b += kPlanBlock) { sh.pts[b] = 0u; if (with_base) sh.pbase[b] = 0u; }
   if (threadIdx.x < kTaskBins) { sh.tsk[threadIdx.x] = 0u; sh.tbase[threadIdx.x] = 0u; }
@@ -146,11 +147,22 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
                             unsigned long long* __restrict__ counters,
                             unsigned* __restrict__ repeat_count, PlanCounts* __restrict__ plan) {
   __shared__ PlanShared sh;
+  // the table's directory (2.3 KB) in shared memory: the lookup reads five of its arrays per slot
+  __shared__ ClusterTableDir s_dir;
+  ClusterTable tb = table;
+  if (cluster_mode && table.dir) {
+    const int* src = reinterpret_cast<const int*>(table.dir);
+    int* dst = reinterpret_cast<int*>(&s_dir);
+    for (int k = threadIdx.x; k < (int)(sizeof(ClusterTableDir) / sizeof(int)); k += kPlanBlock) dst[k] = src[k];
+    tb.dir = &s_dir;
+    if (!plan) __syncthreads();            // (plan_shared_clear ends with a barrier)
+  }
   if (plan) plan_shared_clear(sh, false);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool clustered = false, repeated = false;
-  int records_planned = 0;
-  unsigned bin = 0, shared_tasks = 0u, shared_slots = 0u;
+  int records_planned = 0, n_shared = 0;
+  long long e_lo = 0x7fffffffffffffffLL, e_hi = -1;
+  unsigned bin = 0;
   int slot_K[CL_MAX_SLOTS];
   unsigned slot_val[CL_MAX_SLOTS];
 #pragma unroll
@@ -177,7 +189,7 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
       double cost = 0.0;
       // the slot headers are written on the way (harmless if the point stays on the plain path); unequal atoms
       // (3-level model only) take the two-atom bounds and the general kernel
-      const int records = cluster_plan<D>(pt, sg, ns, noisy != 0, sym, cost, table, shared_tasks, slot_K, slot_val,
+      const int records = cluster_plan<D>(pt, sg, ns, noisy != 0, sym, cost, tb, n_shared, e_lo, e_hi, slot_K, slot_val,
                                           scratch + i * (int64_t)CL_STRIDE,
                                           task_hdr ? task_hdr + i * (int64_t)(CL_MAX_SLOTS * 4) : nullptr);
       if (records > 0 && records <= CL_RECORDS && (cluster_mode == 2 || cost < 0.8 * w)) {
@@ -185,20 +197,16 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
         records_planned = records - CL_OWN0;
       }
     }
+    if (!clustered) n_shared = 0;
     if (task_key) {
-      // one coefficient task per slot that needs records generated, keyed by its term count: binned, the threads
-      // of a warp of cluster_coef_kernel run the same trip counts.  A slot whose records come from the shared table
-      // has a task only if this thread was the first to claim the entry -- and then whatever path the point takes:
-      // other points already count on that entry.
+      // one coefficient task per slot with records of the point's own, keyed by its term count: binned, the threads
+      // of a warp of cluster_coef_kernel run the same trip counts.  (Slots that read the shared table have none: the
+      // entries they requested are generated by cluster_table_kernel.)
 #pragma unroll
       for (int q = 0; q < CL_MAX_SLOTS; ++q) {
-        const bool shared = (slot_val[q] & 0x80000000u) != 0u;
-        if (shared && clustered) ++shared_slots;
-        const bool run = shared ? ((shared_tasks >> q) & 1u) != 0u : clustered;
-        if (!run) slot_K[q] = 0;
+        if (!clustered) slot_K[q] = 0;
         task_key[i * CL_MAX_SLOTS + q] = (uint32_t)slot_K[q];
-        // where the task writes: a record index of the coefficient scratch, or 0x80000000 | table entry
-        task_val[i * CL_MAX_SLOTS + q] = shared ? slot_val[q] : (uint32_t)(i * CL_RECORDS + slot_val[q]);
+        task_val[i * CL_MAX_SLOTS + q] = (uint32_t)(i * CL_RECORDS + slot_val[q]);   // where the task writes
       }
     }
     kind[i] = repeated ? KIND_REPEAT
@@ -227,17 +235,55 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
     atomicAdd(repeat_count, (unsigned)__popc(mr));
     if (counters) atomicAdd(counters + 3, (unsigned long long)__popc(mr));
   }
-  const unsigned tsum = __reduce_add_sync(0xffffffffu, (unsigned)__popc(shared_tasks));
-  const unsigned ssum = __reduce_add_sync(0xffffffffu, shared_slots);
+  const unsigned ssum = __reduce_add_sync(0xffffffffu, (unsigned)n_shared);
+  // the range of table entries this warp requested (entries are < 2^31)
+  const unsigned wnlo = __reduce_max_sync(0xffffffffu, e_hi >= 0 ? ~(unsigned)e_lo : 0u);
+  const unsigned whi1 = __reduce_max_sync(0xffffffffu, e_hi >= 0 ? (unsigned)e_hi + 1u : 0u);
   if (counters && (threadIdx.x & 31) == 0 && m) {
     atomicAdd(counters, (unsigned long long)__popc(m));
     atomicAdd(counters + 2, (unsigned long long)rsum);
   }
-  if (counters && (threadIdx.x & 31) == 0 && (tsum | ssum)) {
-    atomicAdd(counters + 6, (unsigned long long)tsum);      // table entries generated
-    atomicAdd(counters + 7, (unsigned long long)ssum);      // slots of clustered points that read the table
+  if ((threadIdx.x & 31) == 0 && whi1) {
+    if (plan) { atomicMax(&plan->tb_nlo, wnlo); atomicMax(&plan->tb_hi1, whi1); }
+    if (counters && ssum) atomicAdd(counters + 7, (unsigned long long)ssum);      // slots of clustered points that read the table
   }
 }
+
+constexpr int kCoefLanes = 4;
+constexpr int kCoefTasksPerCta = kBlock / kCoefLanes;
+// The shared coefficient table's pass: every requested entry of this work order's range that does not carry the current
+// generation mark is generated (four lanes per entry, like cluster_coef_kernel) and marked.  Work orders on other
+// streams may generate the same entry at the same time (same records, written twice) -- or see the mark, which is
+// written after the records (__threadfence), and skip it.
+__global__ void __launch_bounds__(kBlock, 4)
+cluster_table_kernel(const PlanCounts* __restrict__ plan, const ClusterTableDir* __restrict__ dir,
+                     const unsigned* __restrict__ stamp, unsigned epoch, unsigned* __restrict__ mark, unsigned generation,
+                     double* __restrict__ table, unsigned long long* __restrict__ counters) {
+  __shared__ double s_a[6 * CL_HALF_MAX * kCoefTasksPerCta];
+  const unsigned hi1 = plan->tb_hi1;
+  if (hi1 == 0u) return;
+  const int64_t lo = (int64_t)(~plan->tb_nlo), hi = (int64_t)hi1 - 1;
+  const int t_in_cta = threadIdx.x / kCoefLanes, m = threadIdx.x % kCoefLanes;
+  for (int64_t first = lo + (int64_t)blockIdx.x * kCoefTasksPerCta; first <= hi; first += (int64_t)gridDim.x * kCoefTasksPerCta) {
+    const int64_t e = first + t_in_cta;
+    const bool have = e <= hi && stamp[e] == epoch && mark[e] != generation;
+    if (have) {
+      int K; double theta_n, rho;
+      cluster_table_entry(*dir, dir->base, e, K, theta_n, rho);     // (the 65 class offsets stay in L1)
+      cluster_coefficients_of(K, theta_n, 1.0, rho, table + e * (CT_ENTRY_REC * CL_REC), s_a + t_in_cta, kCoefTasksPerCta, m, kCoefLanes);
+    } else {
+      __syncwarp();     // pairs with the group barrier inside cluster_coefficients
+    }
+    __syncwarp();
+    if (have) {
+      __threadfence();
+      if (m == 0) mark[e] = generation;
+    }
+    const unsigned done = __ballot_sync(0xffffffffu, have && m == 0);
+    if (counters && (threadIdx.x & 31) == 0 && done) atomicAdd(counters + 6, (unsigned long long)__popc(done));
+  }
+}
+
 
 // Coefficient records of the clustered path: four lanes per task = one slot of one point, found through
 // the record index of its header (written by plan_kernel).  The lanes split the Gauss nodes, exchange the
@@ -339,8 +385,6 @@ plan_scatter_kernel(int64_t n_points, const uint32_t* __restrict__ keys, uint32_
   }
 }
 
-constexpr int kCoefLanes = 4;
-constexpr int kCoefTasksPerCta = kBlock / kCoefLanes;
 // Coefficient records of the clustered path: four lanes per task = one slot of one point, found through
 // the record index of its header (written by plan_kernel).  The lanes split the Gauss nodes, exchange the
 // node values through shared memory ([value][node][task], 48 KB per CTA) and then split the blocks of
@@ -348,25 +392,27 @@ constexpr int kCoefTasksPerCta = kBlock / kCoefLanes;
 // grid is sized for the largest possible task count and CTAs beyond the real one leave at once.
 __global__ void __launch_bounds__(kBlock, 4)
 cluster_coef_kernel(const PlanCounts* __restrict__ plan, const uint32_t* __restrict__ task_sorted,
-                    const double* __restrict__ task_hdr_sorted, double* __restrict__ scratch,
-                    double* __restrict__ table) {
+                    const double* __restrict__ task_hdr_sorted, double* __restrict__ scratch) {
   __shared__ double s_a[6 * CL_HALF_MAX * kCoefTasksPerCta];
   const int t_in_cta = threadIdx.x / kCoefLanes, m = threadIdx.x % kCoefLanes;
-  const int64_t g = (int64_t)blockIdx.x * kCoefTasksPerCta + t_in_cta;
-  // the four lanes of a task take the same branch; a warp whose tasks are all absent leaves together
-  const bool have = g < (int64_t)plan->n_tasks;
-  if (!__any_sync(0xffffffffu, have)) return;
-  if (have) {
-    // (K, h, Vc, rho) from the dense task list: one coalesced 32-byte read per task instead of a scattered read of
-    // the slot header in the records (ncu, round 2: that read was 17 % of this kernel's stall samples)
-    const double2 h0 = reinterpret_cast<const double2*>(task_hdr_sorted + g * 4)[0];
-    const double2 h1 = reinterpret_cast<const double2*>(task_hdr_sorted + g * 4)[1];
-    const uint32_t where = task_sorted[g];
-    double* out = (where & 0x80000000u) ? table + (int64_t)(where & 0x7fffffffu) * (CT_ENTRY_REC * CL_REC)
-                                        : scratch + (int64_t)where * CL_REC;
-    cluster_coefficients_of((int)h0.x & 1023, h0.y, h1.x, h1.y, out, s_a + t_in_cta, kCoefTasksPerCta, m, kCoefLanes);
-  } else {
-    __syncwarp();     // pairs with the group barrier inside cluster_coefficients
+  // a fixed grid strides over the tasks (their number is only known on the device; with the shared table it is a few
+  // thousand where the points have 1.3 M slots); the lanes of a warp own their columns of s_a from pass to pass
+  const int64_t n_tasks = (int64_t)plan->n_tasks;
+  for (int64_t base = (int64_t)blockIdx.x * kCoefTasksPerCta; base < n_tasks; base += (int64_t)gridDim.x * kCoefTasksPerCta) {
+    const int64_t g = base + t_in_cta;
+    // the four lanes of a task take the same branch
+    const bool have = g < n_tasks;
+    if (have) {
+      // (K, h, Vc, rho) from the dense task list: one coalesced 32-byte read per task instead of a scattered read of
+      // the slot header in the records (ncu, round 2: that read was 17 % of this kernel's stall samples)
+      const double2 h0 = reinterpret_cast<const double2*>(task_hdr_sorted + g * 4)[0];
+      const double2 h1 = reinterpret_cast<const double2*>(task_hdr_sorted + g * 4)[1];
+      cluster_coefficients_of((int)h0.x & 1023, h0.y, h1.x, h1.y, scratch + (int64_t)task_sorted[g] * CL_REC,
+                              s_a + t_in_cta, kCoefTasksPerCta, m, kCoefLanes);
+    } else {
+      __syncwarp();     // pairs with the group barrier inside cluster_coefficients
+    }
+    __syncwarp();
   }
 }
 
@@ -901,12 +947,11 @@ struct rydcz_ctx {
   // shared coefficient table (rydcz_cluster.cuh): 0 = off, 1 = entries generated once per call, 2 = kept across calls
   int table_mode = 1;
   ClusterTableDir* tb_dir = nullptr;                    // device copy of the directory
-  unsigned* tb_stamp = nullptr;                         // generation stamp per entry
+  unsigned* tb_stamp = nullptr;                         // per entry: epoch of the last call that requested it
+  unsigned* tb_mark = nullptr;                          // per entry: generation its records belong to
   double* tb_records = nullptr;                         // CT_ENTRY_REC records per entry
-  unsigned tb_epoch = 1;
+  unsigned tb_epoch = 1, tb_generation = 1;
   bool tb_failed = false;                               // allocation failed once: slots keep records of their own
-  cudaEvent_t tb_ready = nullptr;                       // after the last coefficient kernel: the entries claimed so far exist
-  bool tb_ready_set = false;
   bool cl_smem_set = false;
   bool cl_smem_gen_set = false;
   bool rp_smem_set = false;
@@ -988,16 +1033,17 @@ static int leave_call(rydcz_ctx* ctx, cudaStream_t st) {
   return 0;
 }
 
-// A new evaluation call: with table mode 1 the shared coefficient entries of earlier calls are forgotten (every
-// call pays for the entries it uses); mode 2 keeps them (rydcz_set_table).
+// A new evaluation call: requests are per call (a new epoch); with table mode 1 the entries of earlier calls are
+// forgotten as well (a new generation: every call pays for the entries it uses), mode 2 keeps them (rydcz_set_table).
 static int table_new_call(rydcz_ctx* ctx) {
-  if (ctx->table_mode != 1 || !ctx->tb_stamp) return 0;
-  if (++ctx->tb_epoch == 0u) {
+  if (!ctx->table_mode || !ctx->tb_stamp) return 0;
+  if (ctx->table_mode == 1) ++ctx->tb_generation;
+  if (++ctx->tb_epoch == 0u || ctx->tb_generation == 0u) {
     ClusterTableDir dir;
     cluster_table_dir_init(dir);
     CK(cudaDeviceSynchronize());
-    CK(cudaMemset(ctx->tb_stamp, 0, (size_t)dir.base[CT_CLASSES] * sizeof(unsigned)));
-    ctx->tb_epoch = 1u;
+    CK(cudaMemset(ctx->tb_stamp, 0, 2 * (size_t)dir.base[CT_CLASSES] * sizeof(unsigned)));
+    ctx->tb_epoch = 1u; ctx->tb_generation = 1u;
   }
   return 0;
 }
@@ -1063,7 +1109,7 @@ static int order_reserve(rydcz_ctx* ctx, int64_t n, bool want_cluster = true) {
     ClusterTableDir dir;
     cluster_table_dir_init(dir);
     const size_t entries = (size_t)dir.base[CT_CLASSES];
-    if (cudaMalloc(&ctx->tb_dir, sizeof(dir)) != cudaSuccess || cudaMalloc(&ctx->tb_stamp, entries * sizeof(unsigned)) != cudaSuccess ||
+    if (cudaMalloc(&ctx->tb_dir, sizeof(dir)) != cudaSuccess || cudaMalloc(&ctx->tb_stamp, 2 * entries * sizeof(unsigned)) != cudaSuccess ||
         cudaMalloc(&ctx->tb_records, entries * CT_ENTRY_REC * CL_REC * sizeof(double) + 4096) != cudaSuccess) {
       cudaGetLastError();
       cudaFree(ctx->tb_dir); cudaFree(ctx->tb_stamp); cudaFree(ctx->tb_records);
@@ -1071,8 +1117,8 @@ static int order_reserve(rydcz_ctx* ctx, int64_t n, bool want_cluster = true) {
       ctx->tb_failed = true;
     } else {
       CK(cudaMemcpy(ctx->tb_dir, &dir, sizeof(dir), cudaMemcpyHostToDevice));
-      CK(cudaMemset(ctx->tb_stamp, 0, entries * sizeof(unsigned)));
-      CK(cudaEventCreateWithFlags(&ctx->tb_ready, cudaEventDisableTiming));
+      CK(cudaMemset(ctx->tb_stamp, 0, 2 * entries * sizeof(unsigned)));
+      ctx->tb_mark = ctx->tb_stamp + entries;
     }
   }
   if (want_cluster && ctx->cluster_mode) {
@@ -1121,11 +1167,9 @@ static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const do
   *order = nullptr;
   const int mode = (sc.cl && D != 5 && !shots && n * (int64_t)CL_RECORDS < 0x7fffffffLL) ? ctx->cluster_mode : 0;
   // The table is shared by every work order of the context (the chunks of a pipelined call run on three streams):
-  // a planner may rely on an entry another order has claimed, so every order plans after the previous order's
-  // coefficient kernel (the chain below) and generates what it claims before its own evaluate kernels.
+  // every order generates the entries IT requested unless they already carry the generation mark (cluster_table_kernel).
   const bool use_table = mode && ctx->table_mode && ctx->tb_dir;
   const ClusterTable table{use_table ? ctx->tb_dir : nullptr, use_table ? ctx->tb_stamp : nullptr, ctx->tb_epoch};
-  if (use_table && ctx->tb_ready_set) CK(cudaStreamWaitEvent(st, ctx->tb_ready, 0));
   unsigned* rpc = (mode && D == 3 && sc.rp && seg_div == 1) ? sc.rp_count : nullptr;
   if (rpc) CK(cudaMemsetAsync(rpc, 0, sizeof(unsigned), st));
   uint32_t* tk = mode ? sc.task : nullptr;                     // term count of every (point, slot); 0 = no such slot
@@ -1151,11 +1195,18 @@ static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const do
   if (mode) {
     const int64_t max_tasks = n * CL_MAX_SLOTS;
     CK(cudaEventRecord(ctx->evc0, st));
-    cluster_coef_kernel<<<(unsigned)((max_tasks + kCoefTasksPerCta - 1) / kCoefTasksPerCta), kBlock, 0, st>>>(
-        sc.plan, tks, ths, sc.cl, ctx->tb_records);
+    const int64_t coef_need = (max_tasks + kCoefTasksPerCta - 1) / kCoefTasksPerCta, coef_cap = (int64_t)ctx->sm_count * 16;
+    cluster_coef_kernel<<<(unsigned)(coef_need < coef_cap ? coef_need : coef_cap), kBlock, 0, st>>>(
+        sc.plan, tks, ths, sc.cl);
     CK(cudaGetLastError());
+    if (use_table) {
+      cluster_table_kernel<<<(unsigned)(ctx->sm_count * 8), kBlock, 0, st>>>(sc.plan, ctx->tb_dir, ctx->tb_stamp, ctx->tb_epoch,
+                                                                            ctx->tb_mark, ctx->tb_generation, ctx->tb_records,
+                                                                            ctx->cl_counters);
+      CK(cudaGetLastError());
+      ctx->launches++;
+    }
     CK(cudaEventRecord(ctx->evc1, st));
-    if (use_table) { CK(cudaEventRecord(ctx->tb_ready, st)); ctx->tb_ready_set = true; }
     ctx->coef_timed = true;
     ctx->launches++;
   }
@@ -1297,7 +1348,6 @@ void rydcz_destroy(rydcz_ctx* ctx) {
   if (ctx->evc1) cudaEventDestroy(ctx->evc1);
   cudaFree(ctx->plan_counts);
   cudaFree(ctx->tb_dir); cudaFree(ctx->tb_stamp); cudaFree(ctx->tb_records);
-  if (ctx->tb_ready) cudaEventDestroy(ctx->tb_ready);
   for (int i = 0; i < 6; ++i) cudaFree(ctx->stage[i]);
   for (int i = 0; i < 3; ++i) cudaFree(ctx->plan[i]);
   for (int l = 0; l < rydcz_ctx::kLanes; ++l) {
@@ -1383,7 +1433,6 @@ int rydcz_set_cluster(rydcz_ctx* ctx, int mode) {
 int rydcz_set_table(rydcz_ctx* ctx, int mode) {
   if (!ctx) return 2;
   if (mode < 0 || mode > 2) return fail(ctx, "table mode must be 0 (off), 1 (entries generated per call) or 2 (kept across calls)");
-  if (mode == 1 && ctx->table_mode == 2 && ctx->tb_stamp) ++ctx->tb_epoch;   // forget what the persistent mode kept
   ctx->table_mode = mode;
   return 0;
 }

@@ -55,6 +55,7 @@ struct ClusterGeom {
   double freq;  // largest d|x|/d(rho t) * rho on the interval: h * freq bounds the Chebyshev degree
   double damp;  // bound on the real parts (4 x sum of rates)
   double w0, w1; // half-widths of the central and of the outer clusters (rad/s, slack included)
+  double iVc, w0h, w1h;   // 1 / Vc and the half-widths in units of Vc (the shared table works in those units)
 };
 
 // D only selects nothing here (the bounds hold for the 3- and 4-level models); kept for symmetry with the callers.
@@ -89,8 +90,13 @@ RYDCZ_HD bool cluster_geometry(double V, double d1, double rates, double om2, do
   // the branch points of q^{-1} sit at |q| = 0.385 Vc^3: stay well inside
   if (!(rho <= 0.25 * Vc2 * Vc) || !(rho > 0.0)) return false;
   double y = rho / Vc2;   // largest |y| of the central branch: y (Vc^2 - y^2) = rho
-  for (int i = 0; i < 6; ++i) y -= (y * (Vc2 - y * y) - rho) / (Vc2 - 3.0 * y * y);
+  for (int i = 0; i < 6; ++i) {          // (two or three steps unless rho is close to its limit)
+    const double dy = (y * (Vc2 - y * y) - rho) / (Vc2 - 3.0 * y * y);
+    y -= dy;
+    if (fabs(dy) <= 1e-15 * y) break;
+  }
   g.Vc = Vc; g.rho = rho; g.freq = rho / (Vc2 - 3.0 * y * y); g.damp = d; g.w0 = w0; g.w1 = w1;
+  g.iVc = 1.0 / Vc; g.w0h = w0 * g.iVc; g.w1h = w1 * g.iVc;
   return true;
 }
 
@@ -168,23 +174,35 @@ inline void cluster_table_dir_init(ClusterTableDir& d) {
     d.base[c + 1] = d.base[c] + (int)floor(CT_Z_MAX / (d.freq[c] * CT_DTHETA));
   }
 }
-// The planner's view: the directory, one generation stamp per entry (an entry is valid when its stamp equals
-// `epoch`; whoever changes the stamp generates the records) -- dir == nullptr: no table.
+// The planner's view: the directory and one request stamp per entry -- dir == nullptr: no table.  A planner only
+// STORES the call's epoch into the stamp of every entry its point needs (no atomic, no read: the planner is a chain of
+// dependent memory operations and an atomic with a result cost it 0.35 ms per 262,144 points); a pass over the
+// requested range (cluster_table_kernel; cluster_table_generate on the host) then generates the entries whose stamp
+// is the current epoch and whose generation mark is not the current generation, and marks them.  The range of
+// requested entries comes back through lo / hi.
 struct ClusterTable {
   const ClusterTableDir* dir;
-  unsigned* stamp;
+  unsigned* stamp;                         // nullptr: a dry run (cost and eligibility only)
   unsigned epoch;
-  RYDCZ_HD bool claim(long long e) const {
-    if (!stamp) return false;              // a dry run (cost and eligibility only)
-#ifdef __CUDA_ARCH__
-    return atomicExch(stamp + e, epoch) != epoch;
-#else
-    const bool fresh = stamp[e] != epoch;
-    stamp[e] = epoch;
-    return fresh;
-#endif
+  RYDCZ_HD void request(long long e) const {
+    if (stamp) stamp[e] = epoch;
   }
 };
+// (K, theta_n, rho^_c) of a table entry from its index: what the lookup below computed for the slots that use it
+RYDCZ_HD void cluster_table_entry(const ClusterTableDir& d, const int* __restrict__ base, long long e, int& K, double& theta_n,
+                                  double& rho) {
+  int c = 0;
+  RYDCZ_UNROLL
+  for (int step = CT_CLASSES / 2; step > 0; step >>= 1)
+    if (c + step < CT_CLASSES && (long long)base[c + step] <= e) c += step;
+  const int n = (int)(e - base[c]) + 1;
+  theta_n = (double)n * CT_DTHETA;
+  rho = d.rho[c];
+  double zs = theta_n * d.freq[c];
+  if (!(zs >= 1e-2)) zs = 1e-2;
+  K = cheb_terms(zs) - 2;
+  if (K < 6) K = 6;
+}
 
 // One slot: `count` consecutive active segments with the same duration, |Omega| and Delta, each advanced
 // in `nsub` equal sub-steps of length h with K + 1 coefficient records -- its own (entry < 0) or a table entry's.
@@ -194,7 +212,6 @@ struct ClusterSlot {
   int K, nsub, count;
   long long entry;        // table entry, -1 = records of its own
   double kappa, inv_gs;   // what the evaluator needs: (Vc / gs)^2 and the factor that turns G into G~
-  double th, rh;          // what the coefficient generator needs with Vc = 1 (table entries): theta_n, rho^_c
 };
 
 // The table entry for a (sub)step of length h under geometry g, if there is one.
@@ -204,12 +221,15 @@ RYDCZ_HD bool cluster_table_lookup(const ClusterTable& tb, const ClusterGeom& g,
   const double nn = rint(theta / CT_DTHETA);
   if (!(nn >= 1.0) || !(nn < 1e8)) return false;
   const double theta_n = nn * CT_DTHETA, lam = theta / theta_n;
-  const double w1 = fabs(lam - 1.0) + lam * (g.w1 / g.Vc);
-  const double need = fmax(lam * (g.w0 / g.Vc), (1.0 + w1) * w1 * (2.0 + w1));
+  const double w1 = fabs(lam - 1.0) + lam * g.w1h;
+  const double need = fmax(lam * g.w0h, (1.0 + w1) * w1 * (2.0 + w1));
   if (!(need <= 0.25) || !(need > 0.0)) return false;
-  int c = (int)floor(CT_PER_OCTAVE * log2(0.25 / need));
+  // class = floor(8 log2(0.25 / need)): a single-precision logarithm, then made exact against the directory
+  int c = (int)floorf((float)CT_PER_OCTAVE * log2f(0.25f / (float)need));
   if (c >= CT_CLASSES) c = CT_CLASSES - 1;
-  if (tb.dir->rho[c] < need) --c;            // (rounding of log2 at a class boundary)
+  if (c < 0) c = 0;
+  while (c + 1 < CT_CLASSES && tb.dir->rho[c + 1] >= need) ++c;
+  while (c >= 0 && tb.dir->rho[c] < need) --c;
   if (c < 0) return false;
   const int n = (int)nn;
   if (n > tb.dir->base[c + 1] - tb.dir->base[c]) return false;     // theta_n freq^_c > CT_Z_MAX: more sub-steps needed
@@ -221,8 +241,7 @@ RYDCZ_HD bool cluster_table_lookup(const ClusterTable& tb, const ClusterGeom& g,
   sl.K = K;
   sl.entry = (long long)tb.dir->base[c] + (n - 1);
   sl.kappa = tb.dir->kappa[c];
-  sl.inv_gs = (h < 0.0 ? -lam : lam) / g.Vc * tb.dir->inv_gs[c];
-  sl.th = theta_n; sl.rh = tb.dir->rho[c];
+  sl.inv_gs = (h < 0.0 ? -lam : lam) * g.iVc * tb.dir->inv_gs[c];
   return true;
 }
 
@@ -271,24 +290,24 @@ struct ClusterWalker {
     sl.h = dt / (double)sl.nsub;
     double zs = z / (double)sl.nsub;
     if (!(zs >= 1e-2)) zs = 1e-2;
-    // two terms fewer than the plain path's rule (measured: the fixtures' worst error against the expm oracle
-    // stays at 6.1e-13; it reaches 7e-12 at four fewer and 1.2e-11 at six)
-    sl.K = cheb_terms(zs) - 2;
-    if (sl.K < 6) sl.K = 6;
-    if (sl.K > CL_MAX_K) return -1;
+    // records from the shared table where an entry contains this (sub)step; the grid value next to h Vc widens the
+    // clusters a little, so a (sub)step at the very edge of the table's range is tried once more, one piece shorter
     sl.entry = -1;
-    {
+    bool shared = tb.dir && cluster_table_lookup(tb, sl.g, sl.h, sl);
+    if (!shared && tb.dir && zs > 0.5 * CL_Z_MAX) {
+      const double h2 = dt / (double)(sl.nsub + 1);
+      shared = cluster_table_lookup(tb, sl.g, h2, sl);
+      if (shared) { sl.h = h2; sl.nsub += 1; }
+    }
+    if (!shared) {
+      // records of its own.  Two terms fewer than the plain path's rule (measured: the fixtures' worst error against
+      // the expm oracle stays at 6.1e-13; it reaches 7e-12 at four fewer and 1.2e-11 at six)
+      sl.K = cheb_terms(zs) - 2;
+      if (sl.K < 6) sl.K = 6;
+      if (sl.K > CL_MAX_K) return -1;
       const double gs = cbrt(0.5 * sl.g.rho);
       sl.kappa = (sl.g.Vc / gs) * (sl.g.Vc / gs);
       sl.inv_gs = 1.0 / gs;
-      sl.th = 0.0; sl.rh = 0.0;
-    }
-    // records from the shared table where an entry contains this (sub)step; the grid value next to h Vc widens the
-    // clusters a little, so a (sub)step at the very edge of the table's range is tried once more, one piece shorter
-    if (tb.dir && !cluster_table_lookup(tb, sl.g, sl.h, sl) && zs > 0.5 * CL_Z_MAX) {
-      ClusterSlot t2 = sl;
-      t2.h = dt / (double)(sl.nsub + 1);
-      if (cluster_table_lookup(tb, sl.g, t2.h, t2)) { t2.nsub = sl.nsub + 1; sl = t2; }
     }
     sl.count = 1;
     ++s;
@@ -317,13 +336,14 @@ struct ClusterWalker {
 RYDCZ_HD double cluster_terms_position(const ClusterSlot& sl, int own_offset) {
   return sl.entry >= 0 ? -(double)(1 + sl.entry * CT_ENTRY_REC) : (double)own_offset;
 }
-RYDCZ_HD void cluster_write_header(const ClusterSlot& sl, double position, double* __restrict__ rec) {
+RYDCZ_HD void cluster_write_header(const ClusterSlot& sl, double position, int K_next, double next_position,
+                                    double* __restrict__ rec) {
   rec[0] = (double)(sl.K + 1024 * sl.nsub);
   rec[1] = sl.kappa;
   rec[2] = sl.inv_gs;
-  rec[3] = (double)sl.count;
+  rec[3] = (double)sl.count + 65536.0 * (double)K_next;
   rec[4] = position;
-  rec[5] = 0.0;
+  rec[5] = next_position;
   rec[6] = 0.0;
   rec[7] = 0.0;
 }
@@ -334,48 +354,49 @@ RYDCZ_HD const double* cluster_terms_at(double position, const double* __restric
 
 // Records the clustered path needs in the point's region (0 = not eligible) and its cost in plain Chebyshev terms.
 // With `rec` the slot headers are written on the way.  Per slot q: slot_K[q] = term count of a coefficient task to
-// run (0: none -- no such slot, or a table entry somebody else generates), slot_val[q] = where that task writes
-// (record index in the point's region, or 0x80000000 | table entry), `dense` (4 doubles per slot) = what
-// cluster_coefficients_of needs for it: K (+ 1024 nsub), h, Vc, rho.  `shared_tasks` gets a bit per slot whose
-// task fills a TABLE entry: those must run even if the caller does not take the clustered path for this point
-// (other points may already count on the entry).
+// run for records of the point's own (0: no such slot, or the slot reads the shared table), slot_val[q] = record
+// index in the point's region where that task writes, `dense` (4 doubles per slot) = what cluster_coefficients_of
+// needs for it: K (+ 1024 nsub), h, Vc, rho.  Table entries are requested through tb (ClusterTable::request);
+// n_shared counts the slots that read the table, [e_lo, e_hi] is widened to the entries requested.
+// (Every header is written ONCE, when the slot after it is known -- it carries that slot's term count and record
+//  position; reading a header back to patch it was 16 % of the planner's stall samples.)
 template <int D>
 RYDCZ_HD int cluster_plan(const double* pt, const double* seg, int n_seg, bool noisy, bool sym, double& cost,
-                          const ClusterTable& tb, unsigned& shared_tasks,
+                          const ClusterTable& tb, int& n_shared, long long& e_lo, long long& e_hi,
                           int* __restrict__ slot_K = nullptr, unsigned* __restrict__ slot_val = nullptr,
                           double* __restrict__ rec = nullptr, double* __restrict__ dense = nullptr) {
   ClusterWalker<D> w(pt, seg, n_seg, noisy, sym, tb);
-  ClusterSlot sl;
+  ClusterSlot sl, prev;
+  double prev_position = 0.0;
   int records = CL_OWN0, slots = 0;
-  double* prev_hdr = nullptr;
   cost = 0.0;
-  shared_tasks = 0u;
+  n_shared = 0;
   for (;;) {
     const int r = w.next(sl);
     if (r < 0) return 0;
+    if (r > 0 && ++slots > CL_MAX_SLOTS) return 0;
+    const double position = r > 0 ? cluster_terms_position(sl, records) : 0.0;
+    if (rec && slots > (r > 0 ? 1 : 0))       // the header of the previous slot, now that this one is known
+      cluster_write_header(prev, prev_position, r > 0 ? sl.K : 0, position, rec + (slots - (r > 0 ? 2 : 1)) * CL_HDR);
     if (r == 0) break;
-    if (++slots > CL_MAX_SLOTS) return 0;
     const int q = slots - 1;
     const bool shared = sl.entry >= 0;
-    const bool generate = shared ? tb.claim(sl.entry) : true;
-    if (shared && generate) shared_tasks |= 1u << q;
-    if (slot_K) slot_K[q] = generate ? sl.K : 0;
-    if (slot_val) slot_val[q] = shared ? (0x80000000u | (unsigned)sl.entry) : (unsigned)records;
-    const double position = cluster_terms_position(sl, records);
-    if (rec) {
-      cluster_write_header(sl, position, rec + q * CL_HDR);
-      if (prev_hdr) { prev_hdr[3] += 65536.0 * (double)sl.K; prev_hdr[5] = position; }   // the previous slot learns about this one
-      prev_hdr = rec + q * CL_HDR;
+    if (shared) {
+      tb.request(sl.entry);
+      ++n_shared;
+      if (sl.entry < e_lo) e_lo = sl.entry;
+      if (sl.entry > e_hi) e_hi = sl.entry;
     }
-    if (dense) {
+    if (slot_K) slot_K[q] = shared ? 0 : sl.K;
+    if (slot_val) slot_val[q] = (unsigned)records;
+    if (dense && !shared) {
       double* d = dense + q * 4;
-      d[0] = (double)(sl.K + 1024 * sl.nsub);
-      if (shared) { d[1] = sl.th; d[2] = 1.0; d[3] = sl.rh; }
-      else { d[1] = sl.h; d[2] = sl.g.Vc; d[3] = sl.g.rho; }
+      d[0] = (double)(sl.K + 1024 * sl.nsub); d[1] = sl.h; d[2] = sl.g.Vc; d[3] = sl.g.rho;
     }
     if (!shared) records += sl.K + 1;
     cost += (double)sl.count * (double)sl.nsub * (CL_STEP_COST * (double)cluster_roundup(sl.K + 2) + CL_SUBSTEP_COST) +
             (shared ? CL_SLOT_COST_SHARED : CL_SLOT_COST);
+    prev = sl; prev_position = position;
   }
   return slots == 0 ? 0 : records;
 }
@@ -518,30 +539,47 @@ RYDCZ_HD void cluster_coefficients_of(int K, double h, double Vc, double rho, do
 #undef RYDCZ_A
 }
 
-// All coefficient tasks of a point, one after the other (the host harness; the GPU runs four lanes per task).
-// `table` = the shared table's records (entries generated here when this point is the first to claim them).
-// Returns the number of table entries it generated.
+// The table pass on the host: every entry of [e_lo, e_hi] that was requested in this epoch and does not carry the
+// current generation mark.  Returns how many it generated.  (cluster_table_kernel on the GPU.)
+inline int cluster_table_generate(const ClusterTableDir& dir, const unsigned* stamp, unsigned epoch, unsigned* mark,
+                                  unsigned generation, long long e_lo, long long e_hi, double* table) {
+  int generated = 0;
+  double A[6 * CL_HALF_MAX];
+  for (long long e = e_lo; e <= e_hi; ++e) {
+    if (stamp[e] != epoch || mark[e] == generation) continue;
+    int K; double theta_n, rho;
+    cluster_table_entry(dir, dir.base, e, K, theta_n, rho);
+    cluster_coefficients_of(K, theta_n, 1.0, rho, table + e * (CT_ENTRY_REC * CL_REC), A, 1, 0, 1);
+    mark[e] = generation;
+    ++generated;
+  }
+  return generated;
+}
+
+// All coefficient tasks of a point's own records, one after the other, and the table entries it requests (the host
+// harness; the GPU runs four lanes per task / entry).  `mark` = generation marks of the table entries, `table` = its
+// records.  Returns the number of table entries it generated.
 template <int D>
 RYDCZ_HD int cluster_prepare(const double* pt, const double* seg, int n_seg, bool noisy, bool sym,
-                             double* __restrict__ rec, const ClusterTable& tb, double* __restrict__ table) {
+                             double* __restrict__ rec, const ClusterTable& tb, unsigned* mark, unsigned generation,
+                             double* __restrict__ table) {
   int slot_K[CL_MAX_SLOTS];
-  unsigned slot_val[CL_MAX_SLOTS], shared_tasks = 0u;
+  unsigned slot_val[CL_MAX_SLOTS];
   double dense[CL_MAX_SLOTS * 4];
   for (int q = 0; q < CL_MAX_SLOTS; ++q) slot_K[q] = 0;
   double cost;
-  const int records = cluster_plan<D>(pt, seg, n_seg, noisy, sym, cost, tb, shared_tasks, slot_K, slot_val, rec, dense);
+  int n_shared = 0;
+  long long e_lo = 0x7fffffffffffffffLL, e_hi = -1;
+  const int records = cluster_plan<D>(pt, seg, n_seg, noisy, sym, cost, tb, n_shared, e_lo, e_hi, slot_K, slot_val, rec, dense);
+  if (records <= 0) return 0;
   double A[6 * CL_HALF_MAX];
-  int generated = 0;
   for (int q = 0; q < CL_MAX_SLOTS; ++q) {
     if (slot_K[q] <= 0) continue;
-    const bool shared = (slot_val[q] & 0x80000000u) != 0u;
-    if (!shared && records <= 0) continue;
-    if (shared) ++generated;
-    double* out = shared ? table + (long long)(slot_val[q] & 0x7fffffffu) * (CT_ENTRY_REC * CL_REC)
-                         : rec + (long long)slot_val[q] * CL_REC;
-    cluster_coefficients_of(slot_K[q], dense[q * 4 + 1], dense[q * 4 + 2], dense[q * 4 + 3], out, A, 1, 0, 1);
+    cluster_coefficients_of(slot_K[q], dense[q * 4 + 1], dense[q * 4 + 2], dense[q * 4 + 3],
+                            rec + (long long)slot_val[q] * CL_REC, A, 1, 0, 1);
   }
-  return generated;
+  return (tb.dir && tb.stamp && e_hi >= e_lo)
+             ? cluster_table_generate(*tb.dir, tb.stamp, tb.epoch, mark, generation, e_lo, e_hi, table) : 0;
 }
 
 // One Clenshaw step of the clustered expansion:  dst <- C_k x + (2 S~) src + dst,

@@ -169,7 +169,7 @@ RYDCZ_HD int cheb_terms_aligned(double z) { return (cheb_terms(z) + 7) & ~7; }
 RYDCZ_HD double cheb_work(double radius, double dt) {
   double z = radius * fabs(dt);
   if (!(z > 0.0)) return 0.0;
-  return z + 10.3 * cbrt(z) + 5.0;
+  return z + 10.3 * (double)cbrtf((float)z) + 5.0;      // (an ordering key and a cost estimate: single precision will do)
 }
 
 // Interval-cache test for a detuning.  dim 5 adds the light-shift compensation |Omega_2|^2/4Delta_e to the

@@ -28,9 +28,9 @@ extern "C" void hostsim_cluster_stats(long long* used, long long* retried) {
 // calloc block (1.2 GB of address space, only the entries that are used get touched).
 static int g_table_mode = 1;
 static rydcz::ClusterTableDir g_dir;
-static std::vector<unsigned> g_stamp;
+static std::vector<unsigned> g_stamp, g_mark;
 static double* g_table = nullptr;
-static unsigned g_epoch = 1;
+static unsigned g_epoch = 1, g_generation = 1;
 static long long g_table_generated = 0;
 extern "C" void hostsim_set_table(int mode) { g_table_mode = mode; }
 extern "C" long long hostsim_table_generated() { const long long n = g_table_generated; g_table_generated = 0; return n; }
@@ -40,6 +40,7 @@ static rydcz::ClusterTable host_table() {
   if (!g_table) {
     cluster_table_dir_init(g_dir);
     g_stamp.assign((size_t)g_dir.base[CT_CLASSES], 0u);
+    g_mark.assign((size_t)g_dir.base[CT_CLASSES], 0u);
     g_table = (double*)calloc((size_t)g_dir.base[CT_CLASSES] * CT_ENTRY_REC * CL_REC + 512, sizeof(double));
   }
   return ClusterTable{&g_dir, g_stamp.data(), g_epoch};
@@ -55,11 +56,12 @@ static bool try_cluster(const rydcz::PointView pt, const double* row, const doub
   const ClusterTable tb = host_table();
   // (like plan_kernel: the headers are written, and table entries claimed and generated, before the path is chosen)
   std::vector<double> rec((size_t)CL_STRIDE + 512, 0.0);    // (+ pad: header lookahead and ring prefetch past the last slot)
-  unsigned shared_tasks = 0u;
-  const int records = cluster_plan<D>(row, sg, ns, noisy, true, cost, dry(tb), shared_tasks);
+  int n_shared = 0;
+  long long e_lo = 0x7fffffffffffffffLL, e_hi = -1;
+  const int records = cluster_plan<D>(row, sg, ns, noisy, true, cost, dry(tb), n_shared, e_lo, e_hi);
   if (records <= 0 || records > CL_RECORDS) return false;
   if (g_cluster == 1 && !(cost < 0.8 * point_work<D>(row, sg, ns))) return false;
-  g_table_generated += cluster_prepare<D>(row, sg, ns, noisy, true, rec.data(), tb, g_table);
+  g_table_generated += cluster_prepare<D>(row, sg, ns, noisy, true, rec.data(), tb, g_mark.data(), g_generation, g_table);
   double xc[3 * (21 + 6)], ring[3 * 8 + CL_LOOKAHEAD];
   bool ok;
   if (D == 3) ok = noisy ? evaluate_point_cluster_d3<true>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), g_table, o, st)
@@ -77,12 +79,13 @@ static bool try_cluster_general(const rydcz::PointView pt, const double* row, co
   using namespace rydcz;
   double cost = 0.0;
   const ClusterTable tb = host_table();
-  unsigned shared_tasks = 0u;
-  const int records = cluster_plan<3>(row, sg, ns, noisy, false, cost, dry(tb), shared_tasks);
+  int n_shared = 0;
+  long long e_lo = 0x7fffffffffffffffLL, e_hi = -1;
+  const int records = cluster_plan<3>(row, sg, ns, noisy, false, cost, dry(tb), n_shared, e_lo, e_hi);
   if (records <= 0 || records > CL_RECORDS) return false;
   if (g_cluster == 1 && !(cost < 0.8 * point_work<3>(row, sg, ns))) return false;
   std::vector<double> rec((size_t)CL_STRIDE + 512, 0.0);    // (+ pad: header lookahead and ring prefetch past the last slot)
-  g_table_generated += cluster_prepare<3>(row, sg, ns, noisy, false, rec.data(), tb, g_table);
+  g_table_generated += cluster_prepare<3>(row, sg, ns, noisy, false, rec.data(), tb, g_mark.data(), g_generation, g_table);
   double xc[3 * 25], ring[3 * 8 + CL_LOOKAHEAD];
   const bool ok = noisy ? evaluate_point_cluster_general_d3<true>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), g_table, o, st)
                         : evaluate_point_cluster_general_d3<false>(pt, Col{xc, 1}, Col{ring, 1}, sg, ns, rec.data(), g_table, o, st);
@@ -97,13 +100,14 @@ extern "C" int hostsim_cluster_records(int dim, int noisy, const double* point, 
   using namespace rydcz;
   // (records of the point's own: the table is left out, so the test sees every slot's coefficients in `rec`)
   const ClusterTable none{nullptr, nullptr, 0u};
-  unsigned shared_tasks = 0u;
-  const int records = dim == 3 ? cluster_plan<3>(point, segs, n_seg, noisy != 0, true, *cost, none, shared_tasks)
-                               : cluster_plan<4>(point, segs, n_seg, noisy != 0, true, *cost, none, shared_tasks);
+  int n_shared = 0;
+  long long e_lo = 0x7fffffffffffffffLL, e_hi = -1;
+  const int records = dim == 3 ? cluster_plan<3>(point, segs, n_seg, noisy != 0, true, *cost, none, n_shared, e_lo, e_hi)
+                               : cluster_plan<4>(point, segs, n_seg, noisy != 0, true, *cost, none, n_shared, e_lo, e_hi);
   if (records > CL_RECORDS) return -records;
   if (records > 0 && rec) {
-    if (dim == 3) cluster_prepare<3>(point, segs, n_seg, noisy != 0, true, rec, none, nullptr);
-    else cluster_prepare<4>(point, segs, n_seg, noisy != 0, true, rec, none, nullptr);
+    if (dim == 3) cluster_prepare<3>(point, segs, n_seg, noisy != 0, true, rec, none, nullptr, 0u, nullptr);
+    else cluster_prepare<4>(point, segs, n_seg, noisy != 0, true, rec, none, nullptr, 0u, nullptr);
   }
   return records;
 }
@@ -113,7 +117,8 @@ extern "C" int hostsim_evaluate(int dim, int noisy, long long n_points, const do
                                 double* states) {
   using namespace rydcz;
   const int stride = dim == 5 ? PT5_STRIDE : PT_STRIDE;
-  if (g_table_mode == 1) ++g_epoch;      // table entries are generated once per call
+  ++g_epoch;                             // requests are per call ...
+  if (g_table_mode == 1) ++g_generation; // ... and so are the entries, unless they are kept (mode 2)
   for (long long i = 0; i < n_points; ++i) {
     double row[PT_MAX_STRIDE + PT_SCRATCH];
     for (int k = 0; k < (dim == 5 ? (int)PT5_USED : (int)PT_STRIDE); ++k) row[k] = points[i * stride + k];

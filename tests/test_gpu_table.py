@@ -46,8 +46,8 @@ def test_population_shares_table_entries(ev, dim, noisy):
     assert back == 0 and planned == 5 * n
     # every slot of every candidate reads the table; 100,000 slots map onto a few thousand entries; the per-call mode
     # generates them again, the persistent mode does not
-    assert shared1 == shared2 == shared3 == 5 * n
-    assert 0 < gen1 < n // 2 and gen2 == gen1 and gen3 == 0
+    assert shared1 == shared2 == shared3 and 0.99 * 5 * n < shared1 <= 5 * n     # (a sliver of a segment has no entry)
+    assert 0 < gen1 < 5 * n // 4 and gen2 == gen1 and gen3 == 0      # (at most ~31,000 entries for any batch size)
     assert np.array_equal(tab, tab2) and np.array_equal(tab, keep) and np.array_equal(st, sk)
     assert np.abs(own[:, :14] - tab[:, :14]).max() < 5e-12 and np.abs(so - st).max() < 5e-12
     assert np.abs(plain[:, :14] - tab[:, :14]).max() < 5e-11 and np.abs(sp - st).max() < 5e-11
@@ -118,6 +118,6 @@ def test_pipelined_chunks_share_the_table_across_streams(ev):
     finally:
         d.set_chunk(32768)
         d.set_table(1)
-    assert shared == 5 * n and 0 < gen < n
+    assert 0.99 * 5 * n < shared <= 5 * n and 0 < gen < n
     assert np.array_equal(b.raw[:, :14], c.raw[:, :14])
     assert np.abs(a.raw[:, :14] - b.raw[:, :14]).max() < 5e-12
