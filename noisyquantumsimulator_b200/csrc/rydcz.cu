@@ -120,6 +120,7 @@ __device__ __forceinline__ unsigned work_bin(double w) {
 // non-empty bin (262,144 points x 6 keys straight onto ~100 global addresses serialise in the L2 atomic units:
 // measured 0.2 ms per pass; per-CTA shared-memory histograms bring that to ~1/30 of the global atomics).
 constexpr int kPlanBlock = 256;
+constexpr int kPlanStageSegs = 8;      // schedules up to this many rows are staged in shared memory by plan_kernel
 struct PlanShared {
   unsigned pts[kBins];        // points per bin in this CTA; later: running rank inside the CTA's range
   unsigned pbase[kBins];      // scatter: first global position of this CTA's points of the bin
@@ -139,7 +140,8 @@ __device__ __forceinline__ void plan_shared_clear(PlanShared& sh, bool with_base
 template <int D>
 __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
                             const double* __restrict__ segs, const int32_t* __restrict__ n_seg,
-                            int max_seg, int seg_div, int shots, int noisy, int cluster_mode, uint32_t* __restrict__ keys,
+                            int max_seg, int seg_div, int seg_staged, int shots, int noisy, int cluster_mode,
+                            uint32_t* __restrict__ keys,
                             uint32_t* __restrict__ idx, uint8_t* __restrict__ kind,
                             uint32_t* __restrict__ task_key, uint32_t* __restrict__ task_val,
                             double* __restrict__ task_hdr,
@@ -149,13 +151,31 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
   __shared__ PlanShared sh;
   // the table's directory (2.3 KB) in shared memory: the lookup reads five of its arrays per slot
   __shared__ ClusterTableDir s_dir;
-  ClusterTable tb = table;
-  if (cluster_mode && table.dir) {
+  struct SharedTable {                     // ClusterTable's interface over the shared-memory copy
+    bool enabled; unsigned* stamp; unsigned epoch;
+    __device__ bool on() const { return enabled; }
+    __device__ const ClusterTableDir& d() const { return s_dir; }
+    __device__ void request(long long e) const { if (stamp) stamp[e] = epoch; }
+  };
+  const SharedTable tb{cluster_mode && table.dir, table.stamp, table.epoch};
+  if (tb.enabled) {
     const int* src = reinterpret_cast<const int*>(table.dir);
     int* dst = reinterpret_cast<int*>(&s_dir);
     for (int k = threadIdx.x; k < (int)(sizeof(ClusterTableDir) / sizeof(int)); k += kPlanBlock) dst[k] = src[k];
-    tb.dir = &s_dir;
     if (!plan) __syncthreads();            // (plan_shared_clear ends with a barrier)
+  }
+  // Short schedules (max_seg <= kPlanStageSegs, one row per point): the CTA's segment rows are staged in shared
+  // memory, one padded run per thread.  The walkers below read every row three or four times in dependent loops;
+  // from L1 through the read-only path that was 21 % of this kernel's stall samples (ncu, round 2).
+  extern __shared__ double s_seg[];
+  const int seg_run = max_seg * SG_STRIDE + 1;       // (+ 1: conflict-free 64-bit accesses across the lanes)
+  if (seg_staged) {
+    const int64_t first = (int64_t)blockIdx.x * kPlanBlock;
+    const int64_t rows = (n_points - first < kPlanBlock ? n_points - first : kPlanBlock);
+    const double* src = segs + first * (int64_t)max_seg * SG_STRIDE;
+    const int per = max_seg * SG_STRIDE, total = (int)rows * per;
+    for (int k = threadIdx.x; k < total; k += kPlanBlock) s_seg[(k / per) * seg_run + k % per] = src[k];
+    if (!plan) __syncthreads();
   }
   if (plan) plan_shared_clear(sh, false);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -170,7 +190,7 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
   if (i < n_points) {
     const double* pt = points + i * PointStride<D>::value;
     const int64_t sp = i / seg_div;       // row of the pulse schedule (the shots of a point share it)
-    const double* sg = segs + sp * (int64_t)max_seg * SG_STRIDE;
+    const double* sg = seg_staged ? s_seg + threadIdx.x * seg_run : segs + sp * (int64_t)max_seg * SG_STRIDE;
     const int ns = n_seg ? n_seg[sp] : max_seg;
     const bool sym = (pt[PT_OFF_A] == pt[PT_OFF_B]) && !(shots && pt[PT_SIG_DET] != 0.0);
     // groups in the order's sequence (highest first): repeated-segment (must come FIRST: the repeat kernels walk the
@@ -928,6 +948,8 @@ struct rydcz_ctx {
   bool busy_set = false;
   int call_flags = 0;          // RYDCZ_FLAG_* of the last evaluation call
   int64_t status_n = 0;        // items of the last call whose kind[] entries are valid (rydcz_point_status)
+  bool atoms_identical = false; // set by the simulate entry points: the device prologue writes OFF_A = OFF_B = 0, so no
+                               // point of the call can be of a general (unequal-atom) kind: those kernels are not launched
   int64_t point_base = 0;      // index of this call's first point in the caller's whole batch (Philox counter; sharded shots)
   bool smem5_set = false;
   int64_t launches = 0;
@@ -952,6 +974,7 @@ struct rydcz_ctx {
   double* tb_records = nullptr;                         // CT_ENTRY_REC records per entry
   unsigned tb_epoch = 1, tb_generation = 1;
   bool tb_failed = false;                               // allocation failed once: slots keep records of their own
+  bool plan_smem_set[3] = {false, false, false};
   bool cl_smem_set = false;
   bool cl_smem_gen_set = false;
   bool rp_smem_set = false;
@@ -980,7 +1003,7 @@ struct rydcz_ctx {
   Lane lane[kLanes];
   int pack_threads = 1;                           // host threads that gather the columns (rydcz_set_pack_threads)
   PackPool* pool = nullptr;
-  int64_t chunk = 32768;                          // points per pipeline chunk (profiles/r01_e2e_chunk_sweep_v9.txt)
+  int64_t chunk = 49152;                          // points per pipeline chunk (profiles/r02_e2e_chunk_sweep.txt)
 };
 
 // scratch of one work sort (the default one belongs to the context; every lane has its own)
@@ -1170,7 +1193,8 @@ static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const do
   // every order generates the entries IT requested unless they already carry the generation mark (cluster_table_kernel).
   const bool use_table = mode && ctx->table_mode && ctx->tb_dir;
   const ClusterTable table{use_table ? ctx->tb_dir : nullptr, use_table ? ctx->tb_stamp : nullptr, ctx->tb_epoch};
-  unsigned* rpc = (mode && D == 3 && sc.rp && seg_div == 1) ? sc.rp_count : nullptr;
+  // (fewer rows than the repeated-segment path's minimum: no point can take it, and its kernels are not launched)
+  unsigned* rpc = (mode && D == 3 && sc.rp && seg_div == 1 && max_seg >= RP_MIN_COUNT) ? sc.rp_count : nullptr;
   if (rpc) CK(cudaMemsetAsync(rpc, 0, sizeof(unsigned), st));
   uint32_t* tk = mode ? sc.task : nullptr;                     // term count of every (point, slot); 0 = no such slot
   uint32_t* tks = mode ? sc.task + sc.task_n : nullptr;        // tasks binned by term count: record index of the slot header
@@ -1178,7 +1202,14 @@ static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const do
   double* th = mode ? sc.task_hdr : nullptr;                   // slot headers, dense, per (point, slot)
   double* ths = mode ? sc.task_hdr + sc.task_n * 4 : nullptr;  // ... in task order
   CK(cudaMemsetAsync(sc.plan, 0, sizeof(PlanCounts), st));
-  plan_kernel<D><<<(unsigned)((n + kPlanBlock - 1) / kPlanBlock), kPlanBlock, 0, st>>>(n, d_points, d_segs, d_n_seg, max_seg, seg_div, shots, noisy,
+  const int seg_staged = (seg_div == 1 && max_seg >= 1 && max_seg <= kPlanStageSegs) ? 1 : 0;
+  const size_t plan_smem = seg_staged ? (size_t)kPlanBlock * (max_seg * SG_STRIDE + 1) * sizeof(double) : 0;
+  if (seg_staged && !ctx->plan_smem_set[D == 3 ? 0 : (D == 4 ? 1 : 2)]) {
+    CK(cudaFuncSetAttribute(plan_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            (int)(kPlanBlock * (kPlanStageSegs * SG_STRIDE + 1) * sizeof(double))));
+    ctx->plan_smem_set[D == 3 ? 0 : (D == 4 ? 1 : 2)] = true;
+  }
+  plan_kernel<D><<<(unsigned)((n + kPlanBlock - 1) / kPlanBlock), kPlanBlock, plan_smem, st>>>(n, d_points, d_segs, d_n_seg, max_seg, seg_div, seg_staged, shots, noisy,
                                                               mode, sc.keys, sc.idx, sc.kind, tk, tv, th, sc.cl, table,
                                                               ctx->cl_counters, rpc, sc.plan);
   CK(cudaGetLastError());
@@ -1224,7 +1255,8 @@ static int launch_eval(rydcz_ctx* ctx, const SortScratch& sc, int64_t n_items, i
   // with an order, every kernel covers only the positions of its own kind group (ranges left by plan_scan_kernel)
   PlanCounts* plan = order ? sc.plan : nullptr;
   if (mark & 1) CK(cudaEventRecord(ctx->ev0, st));
-  if (!SHOTS && D == 3 && sc.cl && ctx->cluster_mode) {
+  const bool general = !ctx->atoms_identical || SHOTS;     // can the call hold points of an unequal-atom kind at all?
+  if (!SHOTS && D == 3 && sc.cl && ctx->cluster_mode && general) {
     // unequal atoms on the clustered path; before the plain general kernel, which takes the hand-backs
     if (!ctx->cl_smem_gen_set) {
       CK(cudaFuncSetAttribute(evaluate_cluster_kernel<3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ClusterSmem<3, false>::BYTES));
@@ -1236,11 +1268,13 @@ static int launch_eval(rydcz_ctx* ctx, const SortScratch& sc, int64_t n_items, i
     CK(cudaGetLastError());
     ctx->launches++;
   }
-  evaluate_kernel<D, NOISY, SHOTS, false><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, point_base, order,
-                                                                   sc.kind, plan, d_points, d_segs, d_n_seg, max_seg,
-                                                                   seg_div, d_out, d_states);
-  CK(cudaGetLastError());
-  ctx->launches++;
+  if (general) {
+    evaluate_kernel<D, NOISY, SHOTS, false><<<grid, kBlock, 0, st>>>(n_items, n_shots, seed, point_base, order,
+                                                                     sc.kind, plan, d_points, d_segs, d_n_seg, max_seg,
+                                                                     seg_div, d_out, d_states);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
   if (!SHOTS && sc.cl && ctx->cluster_mode) {
     if (!ctx->cl_smem_set) {
       CK(cudaFuncSetAttribute(evaluate_cluster_kernel<3, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ClusterSmem<3>::BYTES));
@@ -1259,7 +1293,8 @@ static int launch_eval(rydcz_ctx* ctx, const SortScratch& sc, int64_t n_items, i
                                                                   sc.kind, plan, d_points, d_segs, d_n_seg, max_seg,
                                                                   seg_div, d_out, d_states);
   CK(cudaGetLastError());
-  if (!SHOTS && D == 3 && seg_div == 1 && sc.cl && sc.rp && ctx->cluster_mode && n_items * (int64_t)CL_RECORDS < 0x7fffffffLL) {
+  if (!SHOTS && D == 3 && seg_div == 1 && sc.cl && sc.rp && ctx->cluster_mode && max_seg >= RP_MIN_COUNT &&
+      n_items * (int64_t)CL_RECORDS < 0x7fffffffLL) {
     // fixed grids: the kernels find the number of repeated-segment points on the device
     const unsigned pg = (unsigned)(ctx->sm_count * 8);
     const unsigned need_b = (unsigned)((n_items * RepeatLayout<3>::COLS + kBlock - 1) / kBlock);
@@ -1794,8 +1829,11 @@ int rydcz_simulate_device(rydcz_ctx* ctx, const double* h_model, int64_t n_point
     return rydcz_evaluate_shots_device(ctx, dim, noisy, n_points, n_shots, seed, (const double*)ctx->plan[0],
                                        (const double*)ctx->plan[1], (const int32_t*)ctx->plan[2], S, d_out,
                                        nullptr, stream);
-  return rydcz_evaluate_device(ctx, dim, noisy, n_points, (const double*)ctx->plan[0], (const double*)ctx->plan[1],
-                               (const int32_t*)ctx->plan[2], S, d_out, d_states, stream);
+  ctx->atoms_identical = true;      // rows written by prologue_kernel: OFF_A = OFF_B = 0
+  rc = rydcz_evaluate_device(ctx, dim, noisy, n_points, (const double*)ctx->plan[0], (const double*)ctx->plan[1],
+                             (const int32_t*)ctx->plan[2], S, d_out, d_states, stream);
+  ctx->atoms_identical = false;
+  return rc;
 }
 
 int rydcz_simulate_host(rydcz_ctx* ctx, const double* h_model, int64_t n_points, const double* h_app,
@@ -1865,6 +1903,8 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
   // chunking: with the clustered path a 32,768-point chunk takes ~0.5 ms of kernels, the chunks of the three
   // lanes overlap on the GPU, and a shorter chunk shortens the pipeline's fill and drain (sweep on 262,144
   // bang-bang candidates: 65,536 -> 45.7, 49,152 -> 50.6, 32,768 -> 56.3, 16,384 -> 47.6 M evaluations/s).
+  // Round 2, shared coefficient table (a chunk's kernels ~0.45 ms per 49,152): 131,072 -> 68.0, 65,536 -> 74.7,
+  // 49,152 -> 76.2, 32,768 -> 72.5, 16,384 -> 63.6 M evaluations/s (profiles/r02_e2e_chunk_sweep.txt): default 49,152.
   // Splitting the first chunk in four, so that the GPU starts sooner, was tried again with these kernels:
   // 4.83 ms against 4.56 ms per call -- the small pieces add more launches than they save in fill time.
   const int64_t per_item = n_shots > 0 ? n_shots : 1;
@@ -1961,10 +2001,13 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
                       d_shots + i0 * n_shots * OUT_STRIDE,
                       (dim == 3 && ctx->cluster_mode && ctx->shot_rows) ? ctx->shot_rows + i0 * n_shots * PT_STRIDE : nullptr,
                       st, mark);
-    else
+    else {
+      ctx->atoms_identical = true;      // rows written by prologue_kernel: OFF_A = OFF_B = 0
       rc = evaluate_impl(ctx, sc, dim, noisy, nc, d_pts + i0 * pstride, d_segs + i0 * (int64_t)S * SG_STRIDE,
                          d_ns + i0, S, d_out + i0 * OUT_STRIDE, d_st ? d_st + i0 * (sb / sizeof(double)) : nullptr,
                          st, mark);
+      ctx->atoms_identical = false;
+    }
     if (rc) return rc;
     if (sel_out) {
       // only the requested columns go back, column-major: h_out[j][i] = out[i][slot j]

@@ -184,10 +184,14 @@ struct ClusterTable {
   const ClusterTableDir* dir;
   unsigned* stamp;                         // nullptr: a dry run (cost and eligibility only)
   unsigned epoch;
+  RYDCZ_HD bool on() const { return dir != nullptr; }
+  RYDCZ_HD const ClusterTableDir& d() const { return *dir; }
   RYDCZ_HD void request(long long e) const {
     if (stamp) stamp[e] = epoch;
   }
 };
+// (The planner kernel passes a view of the same shape whose directory is a __shared__ copy: the walker, the lookup
+//  and cluster_plan take the view's type as a template parameter so that those reads compile to shared-memory loads.)
 // (K, theta_n, rho^_c) of a table entry from its index: what the lookup below computed for the slots that use it
 RYDCZ_HD void cluster_table_entry(const ClusterTableDir& d, const int* __restrict__ base, long long e, int& K, double& theta_n,
                                   double& rho) {
@@ -215,8 +219,10 @@ struct ClusterSlot {
 };
 
 // The table entry for a (sub)step of length h under geometry g, if there is one.
-RYDCZ_HD bool cluster_table_lookup(const ClusterTable& tb, const ClusterGeom& g, double h, ClusterSlot& sl) {
-  if (!tb.dir) return false;
+template <class TB>
+RYDCZ_HD bool cluster_table_lookup(const TB& tb, const ClusterGeom& g, double h, ClusterSlot& sl) {
+  if (!tb.on()) return false;
+  const ClusterTableDir& dir = tb.d();
   const double theta = fabs(h) * g.Vc;
   const double nn = rint(theta / CT_DTHETA);
   if (!(nn >= 1.0) || !(nn < 1e8)) return false;
@@ -228,25 +234,25 @@ RYDCZ_HD bool cluster_table_lookup(const ClusterTable& tb, const ClusterGeom& g,
   int c = (int)floorf((float)CT_PER_OCTAVE * log2f(0.25f / (float)need));
   if (c >= CT_CLASSES) c = CT_CLASSES - 1;
   if (c < 0) c = 0;
-  while (c + 1 < CT_CLASSES && tb.dir->rho[c + 1] >= need) ++c;
-  while (c >= 0 && tb.dir->rho[c] < need) --c;
+  while (c + 1 < CT_CLASSES && dir.rho[c + 1] >= need) ++c;
+  while (c >= 0 && dir.rho[c] < need) --c;
   if (c < 0) return false;
   const int n = (int)nn;
-  if (n > tb.dir->base[c + 1] - tb.dir->base[c]) return false;     // theta_n freq^_c > CT_Z_MAX: more sub-steps needed
-  double zs = theta_n * tb.dir->freq[c];
+  if (n > dir.base[c + 1] - dir.base[c]) return false;     // theta_n freq^_c > CT_Z_MAX: more sub-steps needed
+  double zs = theta_n * dir.freq[c];
   if (!(zs >= 1e-2)) zs = 1e-2;
   int K = cheb_terms(zs) - 2;
   if (K < 6) K = 6;
   if (K > CL_MAX_K) return false;
   sl.K = K;
-  sl.entry = (long long)tb.dir->base[c] + (n - 1);
-  sl.kappa = tb.dir->kappa[c];
-  sl.inv_gs = (h < 0.0 ? -lam : lam) * g.iVc * tb.dir->inv_gs[c];
+  sl.entry = (long long)dir.base[c] + (n - 1);
+  sl.kappa = dir.kappa[c];
+  sl.inv_gs = (h < 0.0 ? -lam : lam) * g.iVc * dir.inv_gs[c];
   return true;
 }
 
 // Walks the active segments of a point (the ones next_segment visits) and groups them into slots.
-template <int D>
+template <int D, class TB = ClusterTable>
 struct ClusterWalker {
   const double* pt; const double* seg;
   int n_seg, s;
@@ -257,8 +263,8 @@ struct ClusterWalker {
   double last_om2 = -1.0, last_det = 0.0;
   bool last_ok = false;
   ClusterGeom last_g;
-  ClusterTable tb;
-  RYDCZ_HD ClusterWalker(const double* pt_, const double* seg_, int n_seg_, bool noisy, bool sym_, const ClusterTable& tb_)
+  const TB& tb;
+  RYDCZ_HD ClusterWalker(const double* pt_, const double* seg_, int n_seg_, bool noisy, bool sym_, const TB& tb_)
       : pt(pt_), seg(seg_), n_seg(n_seg_), s(0), sym(sym_), rates(0.0), tb(tb_) {
     if (noisy) {
       rates = pt[PT_G_R1] + pt[PT_G_R0] + pt[PT_G_PHI] + pt[PT_G_SC];
@@ -293,8 +299,8 @@ struct ClusterWalker {
     // records from the shared table where an entry contains this (sub)step; the grid value next to h Vc widens the
     // clusters a little, so a (sub)step at the very edge of the table's range is tried once more, one piece shorter
     sl.entry = -1;
-    bool shared = tb.dir && cluster_table_lookup(tb, sl.g, sl.h, sl);
-    if (!shared && tb.dir && zs > 0.5 * CL_Z_MAX) {
+    bool shared = tb.on() && cluster_table_lookup(tb, sl.g, sl.h, sl);
+    if (!shared && tb.on() && zs > 0.5 * CL_Z_MAX) {
       const double h2 = dt / (double)(sl.nsub + 1);
       shared = cluster_table_lookup(tb, sl.g, h2, sl);
       if (shared) { sl.h = h2; sl.nsub += 1; }
@@ -360,12 +366,12 @@ RYDCZ_HD const double* cluster_terms_at(double position, const double* __restric
 // n_shared counts the slots that read the table, [e_lo, e_hi] is widened to the entries requested.
 // (Every header is written ONCE, when the slot after it is known -- it carries that slot's term count and record
 //  position; reading a header back to patch it was 16 % of the planner's stall samples.)
-template <int D>
+template <int D, class TB>
 RYDCZ_HD int cluster_plan(const double* pt, const double* seg, int n_seg, bool noisy, bool sym, double& cost,
-                          const ClusterTable& tb, int& n_shared, long long& e_lo, long long& e_hi,
+                          const TB& tb, int& n_shared, long long& e_lo, long long& e_hi,
                           int* __restrict__ slot_K = nullptr, unsigned* __restrict__ slot_val = nullptr,
                           double* __restrict__ rec = nullptr, double* __restrict__ dense = nullptr) {
-  ClusterWalker<D> w(pt, seg, n_seg, noisy, sym, tb);
+  ClusterWalker<D, TB> w(pt, seg, n_seg, noisy, sym, tb);
   ClusterSlot sl, prev;
   double prev_position = 0.0;
   int records = CL_OWN0, slots = 0;
@@ -578,7 +584,7 @@ RYDCZ_HD int cluster_prepare(const double* pt, const double* seg, int n_seg, boo
     cluster_coefficients_of(slot_K[q], dense[q * 4 + 1], dense[q * 4 + 2], dense[q * 4 + 3],
                             rec + (long long)slot_val[q] * CL_REC, A, 1, 0, 1);
   }
-  return (tb.dir && tb.stamp && e_hi >= e_lo)
+  return (tb.on() && tb.stamp && e_hi >= e_lo)
              ? cluster_table_generate(*tb.dir, tb.stamp, tb.epoch, mark, generation, e_lo, e_hi, table) : 0;
 }
 
