@@ -614,7 +614,7 @@ def run_ours(args, rank, world, local_rank):
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "rydberg_gates.simulate_CZ_gate_batch(outputs=METRIC_OUTPUTS) -> rydcz_simulate_host_select "
-                           "(C ABI): varying apparatus columns in, the optimiser's 11 metric columns out, 49152-point "
+                           "(C ABI): varying apparatus columns in, the optimiser's 11 metric columns out, 32768-point "
                            "chunks pipelined on 3 streams, pinned staging"},
             "gpu_launches": launches,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": dfma_peak, "unit": "TFLOP/s",

@@ -770,16 +770,19 @@ __global__ void prologue_kernel(ModelArg md, int64_t n_points, const double* __r
 // passes their values once and this kernel writes them into the slot-major block
 // ... and the slots that do vary arrive as one packed block [n_var][packed_stride] (a single H2D copy per
 // chunk) and are scattered to their slot rows here.
-struct ConstSlots { double v[APP_STRIDE]; uint64_t mask; int var[APP_STRIDE]; int n_var; };
+// Varying slot j of point i sits at packed[off[j] + i * str[j]]: a contiguous column (str = 1), or a column of a block
+// of the caller's row-major rows that was copied as it is (str = row length) -- the transposition happens here, on
+// the device, not in a strided gather on the host (which was what limited eight ranks sharing one host, round 2).
+struct ConstSlots { double v[APP_STRIDE]; uint64_t mask; int var[APP_STRIDE]; int n_var; long long off[APP_STRIDE]; int str[APP_STRIDE]; };
 __global__ void fill_slots_kernel(ConstSlots cs, int64_t n_points, double* __restrict__ app, int64_t app_stride,
-                                  const double* __restrict__ packed, int64_t packed_stride) {
+                                  const double* __restrict__ packed) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_points) return;
 #pragma unroll 1
   for (int k = 0; k < APP_STRIDE; ++k)
     if ((cs.mask >> k) & 1ull) app[(int64_t)k * app_stride + i] = cs.v[k];
 #pragma unroll 1
-  for (int j = 0; j < cs.n_var; ++j) app[(int64_t)cs.var[j] * app_stride + i] = packed[(int64_t)j * packed_stride + i];
+  for (int j = 0; j < cs.n_var; ++j) app[(int64_t)cs.var[j] * app_stride + i] = packed[cs.off[j] + i * (int64_t)cs.str[j]];
 }
 
 // deterministic shot mean: one warp per point, fixed-order tree
@@ -1003,7 +1006,7 @@ struct rydcz_ctx {
   Lane lane[kLanes];
   int pack_threads = 1;                           // host threads that gather the columns (rydcz_set_pack_threads)
   PackPool* pool = nullptr;
-  int64_t chunk = 49152;                          // points per pipeline chunk (profiles/r02_e2e_chunk_sweep.txt)
+  int64_t chunk = 32768;                          // points per pipeline chunk (profiles/r02_e2e_ranks_n1.txt, _n8.txt)
 };
 
 // scratch of one work sort (the default one belongs to the context; every lane has its own)
@@ -1344,16 +1347,21 @@ int rydcz_create(int device, rydcz_ctx** out) {
   if (device < 0 || device >= count) { g_create_error = "device index out of range"; return 2; }
   rydcz_ctx* ctx = new rydcz_ctx();
   ctx->device = device;
-  // Host threads for the column gather: the cores this process can count on, at most 4.  One process per GPU is
-  // the deployment (torchrun exports LOCAL_WORLD_SIZE): eight ranks on a 32-core host get 3 threads each, not 8 x 8.
+  // Host threads that copy the caller's columns into the pinned ring.  One process per GPU is the deployment
+  // (torchrun exports LOCAL_WORLD_SIZE), and every rank also runs its interpreter, the CUDA driver's and NCCL's
+  // threads: measured on the 8-GPU box (32 CPUs; tools/e2e_ranks.py, profiles/r02_e2e_ranks_n8.txt) three extra
+  // threads per rank oversubscribe the host -- 16.0 ms per call against 7.3 ms with none.  And since the columns
+  // of one array are copied as a block (simulate_cols_impl) the copy is a few memcpy calls per chunk: even alone on
+  // a 16-CPU host one thread is fastest (76.5 M evaluations/s end to end against 67.1 M with three helpers).
+  // Default 1; RYDCZ_PACK_THREADS / rydcz_set_pack_threads for callers whose columns are scattered.
   {
     int cores = (int)std::thread::hardware_concurrency();
     cpu_set_t set;
     if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) cores = CPU_COUNT(&set);
     int ranks = 1;
     if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = atoi(e) > 0 ? atoi(e) : 1;
-    int t = (cores > 0 ? cores : 1) / ranks - 1;      // leave one core per rank to the interpreter and the driver
-    t = t < 1 ? 1 : (t > 4 ? 4 : t);
+    int t = 1;
+    (void)cores; (void)ranks;
     if (const char* e = getenv("RYDCZ_PACK_THREADS")) { t = atoi(e); t = t < 1 ? 1 : (t > 16 ? 16 : t); }
     ctx->pack_threads = t;
   }
@@ -1900,11 +1908,44 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
     if (h_cols[k]) { cs.var[n_var] = k; var[n_var++] = k; } else cs.mask |= 1ull << k;
   }
   cs.n_var = n_var;
+  // Columns of one row-major array of the caller (same stride, addresses inside one row) form a BLOCK: its rows are
+  // copied as they are -- one memcpy per chunk -- and fill_slots_kernel picks the columns out on the device.  A
+  // block must be mostly used (row length <= 2 x its columns); other strided columns are gathered one by one.
+  struct Block { const double* base; int64_t stride; int first_col; };
+  Block blocks[APP_STRIDE];
+  int n_blocks = 0, col_block[APP_STRIDE], col_off[APP_STRIDE];
+  int block_last[APP_STRIDE] = {0};                         // last used column of every block
+  for (int j = 0; j < n_var; ++j) {
+    col_block[j] = -1; col_off[j] = 0;
+    const int64_t cstr = col_stride ? col_stride[var[j]] : 1;
+    if (cstr <= 1 || cstr > 64 || n_points < 256) continue;   // (tiny batches: separate arrays may sit within one "row")
+    const double* p = h_cols[var[j]];
+    for (int b = 0; b < n_blocks; ++b) {
+      if (blocks[b].stride != cstr) continue;
+      const int64_t d = p - blocks[b].base;
+      if (d > -cstr && d < cstr) { col_block[j] = b; break; }
+    }
+    if (col_block[j] < 0) { blocks[n_blocks] = Block{p, cstr, j}; col_block[j] = n_blocks++; }
+    if (p < blocks[col_block[j]].base) blocks[col_block[j]].base = p;
+  }
+  {
+    int used[APP_STRIDE] = {0};
+    for (int j = 0; j < n_var; ++j) if (col_block[j] >= 0) ++used[col_block[j]];
+    for (int j = 0; j < n_var; ++j) {
+      if (col_block[j] < 0) continue;
+      const Block& b = blocks[col_block[j]];
+      const int64_t d = h_cols[var[j]] - b.base;
+      if (2 * used[col_block[j]] < b.stride || d >= b.stride) col_block[j] = -1;      // sparse use of a wide row: gather
+      else { col_off[j] = (int)d; if ((int)d > block_last[col_block[j]]) block_last[col_block[j]] = (int)d; }
+    }
+  }
   // chunking: with the clustered path a 32,768-point chunk takes ~0.5 ms of kernels, the chunks of the three
   // lanes overlap on the GPU, and a shorter chunk shortens the pipeline's fill and drain (sweep on 262,144
   // bang-bang candidates: 65,536 -> 45.7, 49,152 -> 50.6, 32,768 -> 56.3, 16,384 -> 47.6 M evaluations/s).
   // Round 2, shared coefficient table (a chunk's kernels ~0.45 ms per 49,152): 131,072 -> 68.0, 65,536 -> 74.7,
-  // 49,152 -> 76.2, 32,768 -> 72.5, 16,384 -> 63.6 M evaluations/s (profiles/r02_e2e_chunk_sweep.txt): default 49,152.
+  // 49,152 -> 76.2, 32,768 -> 72.5, 16,384 -> 63.6 M evaluations/s (profiles/r02_e2e_chunk_sweep.txt).  With the
+  // block copy and one host thread: 131,072 -> 69.7, 49,152 -> 76.5, 32,768 -> 81.0 M (and 224 / 288 / 332 M on
+  // eight GPUs sharing one host): default 32,768.
   // Splitting the first chunk in four, so that the GPU starts sooner, was tried again with these kernels:
   // 4.83 ms against 4.56 ms per call -- the small pieces add more launches than they save in fill time.
   const int64_t per_item = n_shots > 0 ? n_shots : 1;
@@ -1945,7 +1986,10 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
       CK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
       CK(cudaEventCreateWithFlags(&L.ring_free, cudaEventDisableTiming));
     }
-    const size_t need = (size_t)(n_var ? n_var : 1) * chunk * sizeof(double);
+    size_t need_cols = 0;                                   // ring: the blocks' rows, then the single columns
+    for (int b = 0; b < n_blocks; ++b) need_cols += (size_t)blocks[b].stride;
+    for (int j = 0; j < n_var; ++j) if (col_block[j] < 0) ++need_cols;
+    const size_t need = (need_cols ? need_cols : 1) * (size_t)chunk * sizeof(double);
     if (need > L.ring_cap) {
       if (L.ring) CK(cudaFreeHost(L.ring));
       L.ring = nullptr; L.ring_cap = 0;
@@ -1967,26 +2011,61 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
     // arrays), one H2D copy, scatter on the device.  The columns are gathered by a small sleeping thread pool
     // sized to the cores of this rank (rydcz_create; round 1 measured 8 OpenMP threads per rank on an 8-GPU box
     // oversubscribing the host 8x: the pool is bounded by cores / LOCAL_WORLD_SIZE and does not spin).
+    size_t ring_used = 0;
     {
       double* ring = L.ring;
-      const std::function<void(int)> gather = [&](int j) {
-        const int64_t cstr = col_stride ? col_stride[var[j]] : 1;
-        const double* src = h_cols[var[j]] + i0 * cstr;
-        double* dst = ring + (size_t)j * chunk;
-        if (cstr == 1) memcpy(dst, src, nc * sizeof(double));
-        else for (int64_t i = 0; i < nc; ++i) dst[i] = src[i * cstr];
+      // pieces of work: row ranges of the blocks (plain memcpy) and single columns (memcpy or strided gather)
+      struct Piece { int kind; int idx; int64_t r0, r1; size_t at; };
+      Piece pieces[4 * APP_STRIDE];
+      int n_pieces = 0;
+      size_t at = 0;
+      bool block_live[APP_STRIDE] = {false};
+      for (int j = 0; j < n_var; ++j) if (col_block[j] >= 0) block_live[col_block[j]] = true;
+      size_t block_at[APP_STRIDE] = {0};
+      for (int b = 0; b < n_blocks; ++b) {
+        if (!block_live[b]) continue;
+        block_at[b] = at;
+        const int parts = (nc * blocks[b].stride >= 65536 && ctx->pack_threads > 1) ? 4 : 1;
+        for (int q = 0; q < parts; ++q)
+          pieces[n_pieces++] = Piece{0, b, nc * q / parts, nc * (q + 1) / parts, at};
+        at += (size_t)blocks[b].stride * (size_t)chunk;
+      }
+      for (int j = 0; j < n_var; ++j) {
+        if (col_block[j] >= 0) { cs.off[j] = (long long)block_at[col_block[j]] + col_off[j]; cs.str[j] = (int)blocks[col_block[j]].stride; continue; }
+        cs.off[j] = (long long)at; cs.str[j] = 1;
+        pieces[n_pieces++] = Piece{1, j, 0, nc, at};
+        at += (size_t)chunk;
+      }
+      ring_used = at;
+      const std::function<void(int)> copy = [&](int k) {
+        const Piece& pc = pieces[k];
+        if (pc.kind == 0) {
+          const Block& b = blocks[pc.idx];
+          // (the very last row only up to the block's last used column: the array may end there)
+          const size_t cut = (i0 + pc.r1 == n_points) ? (size_t)(b.stride - 1 - block_last[pc.idx]) : 0;
+          memcpy(ring + pc.at + (size_t)pc.r0 * b.stride, b.base + (i0 + pc.r0) * b.stride,
+                 ((size_t)(pc.r1 - pc.r0) * b.stride - cut) * sizeof(double));
+        } else {
+          const int64_t cstr = col_stride ? col_stride[var[pc.idx]] : 1;
+          const double* src = h_cols[var[pc.idx]] + i0 * cstr;
+          double* dst = ring + pc.at;
+          if (cstr == 1) memcpy(dst, src, nc * sizeof(double));
+          else for (int64_t i = 0; i < nc; ++i) dst[i] = src[i * cstr];
+        }
       };
-      if (ctx->pack_threads > 1 && n_var > 1 && nc >= 4096) {
+      if (ctx->pack_threads > 1 && n_pieces > 1 && nc >= 4096) {
         if (!ctx->pool) ctx->pool = new PackPool(ctx->pack_threads - 1);
-        ctx->pool->run(n_var, gather);
+        ctx->pool->run(n_pieces, copy);
       } else {
-        for (int j = 0; j < n_var; ++j) gather(j);
+        for (int k = 0; k < n_pieces; ++k) copy(k);
       }
     }
-    if (n_var)
-      CK(cudaMemcpyAsync(L.d_ring, L.ring, ((size_t)(n_var - 1) * chunk + nc) * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (n_var) {
+      // (the last block / column of the ring is only filled up to nc rows)
+      CK(cudaMemcpyAsync(L.d_ring, L.ring, ring_used * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
     CK(cudaEventRecord(L.ring_free, st));
-    fill_slots_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(cs, nc, d_app + i0, n_points, L.d_ring, chunk);
+    fill_slots_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(cs, nc, d_app + i0, n_points, L.d_ring);
     CK(cudaGetLastError());
     ctx->launches++;
     double* c_sc = d_sc ? d_sc + i0 * SC_STRIDE : nullptr;

@@ -116,7 +116,7 @@ def test_pipelined_chunks_share_the_table_across_streams(ev):
         d.set_chunk(1 << 20)
         c = rg.simulate_CZ_gate_batch("jp", B=n, warn=False, **bench.MEDIUM, **cand)
     finally:
-        d.set_chunk(49152)
+        d.set_chunk(32768)
         d.set_table(1)
     assert 0.99 * 5 * n < shared <= 5 * n and 0 < gen < n
     assert np.array_equal(b.raw[:, :14], c.raw[:, :14])
