@@ -500,9 +500,13 @@ def run_ours(args, rank, world, local_rank):
     # (apparatus slots as columns -> rydcz_simulate_host_select: per chunk, pack the varying slots into pinned
     # staging, H2D, prologue + planner + evaluate kernels, gather of the requested columns, D2H; chunks pipelined on
     # three streams) -> the metric columns the reference's optimiser reads (extract_metrics), in host memory
+    # The step's inputs sit in page-locked host memory (contract: "host->device copy of that step's inputs from pinned
+    # host memory"): the candidate arrays as the optimiser would hold them, row-major [B], [B, 4], [B, 5].
+    cand_host = {k: ev.pinned_copy("bench_" + k, v) for k, v in cand.items()}
+
     def e2e_step():
         res = rg.simulate_CZ_gate_batch("jp", B=B_PER_GPU, device=local_rank, prologue="device", copy=False,
-                                        outputs=METRIC_OUTPUTS, **MEDIUM, **cand)
+                                        outputs=METRIC_OUTPUTS, **MEDIUM, **cand_host)
         return res.avg_fidelity
     for _ in range(2):
         e2e_step()
@@ -614,8 +618,9 @@ def run_ours(args, rank, world, local_rank):
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "rydberg_gates.simulate_CZ_gate_batch(outputs=METRIC_OUTPUTS) -> rydcz_simulate_host_select "
-                           "(C ABI): varying apparatus columns in, the optimiser's 11 metric columns out, 32768-point "
-                           "chunks pipelined on 3 streams, pinned staging"},
+                           "(C ABI): the candidates' row-major arrays in page-locked host memory -> H2D per 32768-point chunk "
+                           "(transposed into apparatus slots on the device), the optimiser's 11 metric columns out into "
+                           "page-locked memory, chunks pipelined on 3 streams"},
             "gpu_launches": launches,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": dfma_peak, "unit": "TFLOP/s",
                          "frac": achieved / dfma_peak,

@@ -1939,6 +1939,17 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
       else { col_off[j] = (int)d; if ((int)d > block_last[col_block[j]]) block_last[col_block[j]] = (int)d; }
     }
   }
+  // Page-locked inputs (rydcz_pinned_alloc / cudaHostAlloc / cudaHostRegister) go to the device as they are: no copy
+  // into the ring, the H2D engine reads the caller's memory.  (Unit = a block, or a contiguous single column.)
+  auto is_pinned = [](const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+  };
+  bool block_pinned[APP_STRIDE] = {false}, col_pinned[APP_STRIDE] = {false};
+  for (int b = 0; b < n_blocks; ++b) block_pinned[b] = is_pinned(blocks[b].base);
+  for (int j = 0; j < n_var; ++j)
+    col_pinned[j] = col_block[j] < 0 && (col_stride ? col_stride[var[j]] : 1) == 1 && is_pinned(h_cols[var[j]]);
   // chunking: with the clustered path a 32,768-point chunk takes ~0.5 ms of kernels, the chunks of the three
   // lanes overlap on the GPU, and a shorter chunk shortens the pipeline's fill and drain (sweep on 262,144
   // bang-bang candidates: 65,536 -> 45.7, 49,152 -> 50.6, 32,768 -> 56.3, 16,384 -> 47.6 M evaluations/s).
@@ -2025,7 +2036,7 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
       for (int b = 0; b < n_blocks; ++b) {
         if (!block_live[b]) continue;
         block_at[b] = at;
-        const int parts = (nc * blocks[b].stride >= 65536 && ctx->pack_threads > 1) ? 4 : 1;
+        const int parts = block_pinned[b] ? 0 : ((nc * blocks[b].stride >= 65536 && ctx->pack_threads > 1) ? 4 : 1);
         for (int q = 0; q < parts; ++q)
           pieces[n_pieces++] = Piece{0, b, nc * q / parts, nc * (q + 1) / parts, at};
         at += (size_t)blocks[b].stride * (size_t)chunk;
@@ -2033,7 +2044,7 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
       for (int j = 0; j < n_var; ++j) {
         if (col_block[j] >= 0) { cs.off[j] = (long long)block_at[col_block[j]] + col_off[j]; cs.str[j] = (int)blocks[col_block[j]].stride; continue; }
         cs.off[j] = (long long)at; cs.str[j] = 1;
-        pieces[n_pieces++] = Piece{1, j, 0, nc, at};
+        if (!col_pinned[j]) pieces[n_pieces++] = Piece{1, j, 0, nc, at};
         at += (size_t)chunk;
       }
       ring_used = at;
@@ -2061,8 +2072,32 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
       }
     }
     if (n_var) {
-      // (the last block / column of the ring is only filled up to nc rows)
-      CK(cudaMemcpyAsync(L.d_ring, L.ring, ring_used * sizeof(double), cudaMemcpyHostToDevice, st));
+      // one copy per unit: out of the ring, or straight out of the caller's page-locked memory
+      bool any_pinned = false;
+      for (int b = 0; b < n_blocks; ++b) any_pinned |= block_pinned[b];
+      for (int j = 0; j < n_var; ++j) any_pinned |= col_pinned[j];
+      if (!any_pinned) {
+        // (the last block / column of the ring is only filled up to nc rows)
+        CK(cudaMemcpyAsync(L.d_ring, L.ring, ring_used * sizeof(double), cudaMemcpyHostToDevice, st));
+      } else {
+        size_t at = 0;
+        bool live[APP_STRIDE] = {false};
+        for (int j = 0; j < n_var; ++j) if (col_block[j] >= 0) live[col_block[j]] = true;
+        for (int b = 0; b < n_blocks; ++b) {
+          if (!live[b]) continue;
+          const size_t cut = (i0 + nc == n_points) ? (size_t)(blocks[b].stride - 1 - block_last[b]) : 0;
+          const size_t cnt = (size_t)nc * blocks[b].stride - cut;
+          const double* src = block_pinned[b] ? blocks[b].base + i0 * blocks[b].stride : L.ring + at;
+          CK(cudaMemcpyAsync(L.d_ring + at, src, cnt * sizeof(double), cudaMemcpyHostToDevice, st));
+          at += (size_t)blocks[b].stride * (size_t)chunk;
+        }
+        for (int j = 0; j < n_var; ++j) {
+          if (col_block[j] >= 0) continue;
+          const double* src = col_pinned[j] ? h_cols[var[j]] + i0 : L.ring + at;
+          CK(cudaMemcpyAsync(L.d_ring + at, src, (size_t)nc * sizeof(double), cudaMemcpyHostToDevice, st));
+          at += (size_t)chunk;
+        }
+      }
     }
     CK(cudaEventRecord(L.ring_free, st));
     fill_slots_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, st>>>(cs, nc, d_app + i0, n_points, L.d_ring);

@@ -75,6 +75,15 @@ class Evaluator:
         raw = (C.c_char * buf[1]).from_address(buf[0].value)
         return np.frombuffer(raw, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
 
+    def pinned_copy(self, key: str, array) -> np.ndarray:
+        """A page-locked copy of `array` (same shape and dtype), owned by this evaluator.  Inputs that live in
+        page-locked memory go to the device as they are: rydcz_simulate_host_cols / _select copy them with the H2D
+        engine straight out of the caller's memory instead of staging them through the context's ring first."""
+        a = np.ascontiguousarray(array)
+        buf = self.pinned(key, a.shape, a.dtype)
+        buf[...] = a
+        return buf
+
     def close(self):
         for p, _ in getattr(self, "_pinned", {}).values():
             self.lib.rydcz_pinned_free(p)

@@ -20,7 +20,7 @@ torch.cuda.set_device(local)
 if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 B = 262144
-cand = bench.make_candidates(B, 1234 + rank)
+cand = {k: get_evaluator(local).pinned_copy("c_" + k, v) for k, v in bench.make_candidates(B, 1234 + rank).items()} if os.environ.get("E2E_PINNED", "1") == "1" else bench.make_candidates(B, 1234 + rank)
 kw = dict(bench.MEDIUM, **cand)
 ev = get_evaluator(local)
 
