@@ -598,10 +598,63 @@ def shot_kwargs(kwargs: dict, n_shots: int) -> dict:
     return kwargs
 
 
+def _compat_epilogue(res: "BatchResult", dim: int, keep_states: bool) -> "BatchResult":
+    """The reference's mixed-branch epilogue (RG/simulation.py:395-470) for every point of a batch: populations
+    <ab|rho_ab|ab>, phases from the dominant eigenvector of rho_ab (LAPACK's phase convention, as in the reference),
+    controlled phase, F11 <- F11 * cos^2(err / 2), mean of the four.  Rows that were evaluated without noise (kets)
+    keep the kernel's pure-state numbers."""
+    import scipy.linalg as sla
+    st = res.states
+    if st is None:
+        return res
+    raw = np.array(res.raw)
+    systems, off, kets = _systems(dim), _state_offsets(dim), _kets(dim)
+    Bn = st.shape[0]
+    pops, phis = {}, {}
+    for lab in ("01", "10", "11"):
+        sysm = systems["rho" + lab]
+        block = st[:, off["rho" + lab]:off["rho" + lab] + sysm.n]
+        if not np.isfinite(block).all() or np.abs(block).sum() == 0.0:
+            return res                                 # noiseless call: there is no rho to take eigenvectors of
+        rho = np.stack([sysm.to_operator(block[i]) for i in range(Bn)])
+        k = kets[lab].reshape(-1)
+        pops[lab] = np.real(np.einsum("i,bij,j->b", k.conj(), rho, k))
+        # scipy's eigh, point by point, like compute_CZ_fidelity: the eigenvector's global phase is the LAPACK
+        # driver's convention and numpy's batched eigh (another driver) returns other phases for the same rho
+        ph = np.empty(Bn)
+        for i in range(Bn):
+            try:
+                w, v = sla.eigh(rho[i])
+                ph[i] = np.angle(np.vdot(k, v[:, int(np.argmax(w))]))
+            except Exception:
+                ph[i] = 0.0
+        phis[lab] = ph
+    # |00> is inert: rho_00 = |00><00| for every point; its "dominant eigenvector phase" is LAPACK's sign convention
+    k00 = kets["00"].reshape(-1)
+    w0, v0 = sla.eigh(np.outer(k00, k00.conj()))
+    phi00 = float(np.angle(np.vdot(k00, v0[:, int(np.argmax(w0))])))
+    ctrl = _wrap_pi(phis["11"] - phis["01"] - phis["10"] + phi00)
+    err = np.minimum(np.abs(ctrl - np.pi), np.abs(ctrl + np.pi))
+    czf = np.cos(err / 2) ** 2
+    f11 = pops["11"] * czf
+    avg = (1.0 + pops["01"] + pops["10"] + f11) / 4.0
+    raw[:, _OUT["avg"]] = avg
+    raw[:, _OUT["f11"]] = f11
+    raw[:, _OUT["czf"]] = czf
+    raw[:, _OUT["ctrl"]] = ctrl
+    raw[:, _OUT["err"]] = err
+    return BatchResult(avg_fidelity=raw[:, _OUT["avg"]], f11_population=raw[:, _OUT["f11_pop"]],
+                       cz_phase_fidelity=raw[:, _OUT["czf"]], controlled_phase_rad=raw[:, _OUT["ctrl"]],
+                       phase_error_from_pi_rad=raw[:, _OUT["err"]], loss_probability=res.loss_probability,
+                       rydberg_residual=res.rydberg_residual, tau_total=res.tau_total, Omega=res.Omega, V=res.V,
+                       raw=raw, plan=res.plan, states=st if keep_states else None, shots=None,
+                       _voo=getattr(res, "_voo", None))
+
+
 def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, seed: int = 1234,
                            return_states: bool = False, return_shots: bool = False, device: int = 0,
                            plan: GatePlan = None, prologue: str = "auto", copy: bool = True,
-                           outputs=None, **kwargs) -> BatchResult:
+                           outputs=None, phase_mode: str = None, **kwargs) -> BatchResult:
     """Evaluate B parameter points in one launch.
 
     ``protocol`` is "lp", "jp" (bang-bang) or "sjp"; every physical keyword of ``build_plan``
@@ -619,9 +672,21 @@ def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, se
     optimiser reads).  Only those columns are gathered on the device and copied back (8 bytes per point and
     column instead of 192 bytes per point), each as one contiguous array in ``BatchResult.columns``; needs the
     device prologue.
+    ``phase_mode="compat"`` (noisy runs): the reference's own mixed-state formula -- phases from the dominant
+    eigenvector of every final rho (RG/simulation.py:424-434) -- applied on the host to the rho's the kernel returns
+    (``scipy.linalg.eigh`` per point, the driver the single-point API uses); it replaces ``avg_fidelity``, ``cz_phase_fidelity``, ``controlled_phase_rad``
+    and ``phase_error_from_pi_rad``.  The default ("coherence") is the kernel's gauge-free epilogue.
     """
     from ..engine import get_evaluator
     from . import device_prologue as dpro
+
+    if (phase_mode or DEFAULT_PHASE_MODE) == "compat":
+        if outputs is not None or n_shots > 0:
+            raise ValueError("phase_mode='compat' works on the final states: no outputs=..., no shots")
+        res = simulate_CZ_gate_batch(protocol, B=B, seed=seed, return_states=True, device=device, plan=plan,
+                                     prologue=prologue, copy=True, **kwargs)
+        return _compat_epilogue(res, kwargs.get("hilbert_space_dim", 3) if plan is None else plan.dim,
+                                keep_states=return_states)
 
     # shaped LP pulses (gaussian / cosine / blackman) run through the device prologue as well; 'drag' cannot run
     # at all (it fails in the reference too) and is left to the host prologue to raise the reference's error

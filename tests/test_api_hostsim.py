@@ -193,3 +193,32 @@ def test_calibration_file_round_trip(tmp_path, monkeypatch):
     assert np.allclose(doc["arrays"]["gate_duration_s"], res.tau_total)
     assert doc["records"][2]["parameters"] == {"laser_2_power_W": float(p2[2]), "temperature_K": 2e-6}
     assert set(doc["records"][0]["error_rates"]["infidelity_by_input"]) == {"00", "01", "10", "11"}
+
+
+def test_batch_compat_epilogue_equals_the_single_point_formula(rg):
+    """simulate_CZ_gate_batch(phase_mode="compat"): the reference's dominant-eigenvector formula (RG/simulation.py:
+    424-434) applied to the batch's rho's equals the oracle's restatement of that formula applied to the same rho's,
+    point by point; the default mode is untouched."""
+    from oracle import rydcz_oracle as orc
+    rng = np.random.default_rng(3)
+    B = 6
+    kw = dict(laser_1_power=50e-6, laser_1_waist=50e-6, laser_2_power=10 ** rng.uniform(-0.6, 0.2, B), laser_2_waist=50e-6,
+              Delta_e=2 * np.pi * 1e9, tweezer_power=0.02, tweezer_waist=0.8e-6, warn=False)
+    a = rg.simulate_CZ_gate_batch("lp", B=B, include_noise=True, return_states=True, **kw)
+    b = rg.simulate_CZ_gate_batch("lp", B=B, include_noise=True, return_states=True, phase_mode="compat", **kw)
+    assert np.array_equal(a.states, b.states)
+    assert np.allclose(a.f11_population, b.f11_population, atol=0, rtol=0)
+    for i in range(B):
+        ops = C.states_to_operators(3, b.states[i])
+        k00 = np.zeros(9, dtype=complex); k00[0] = 1
+        results = {"00": np.outer(k00, k00.conj()), "01": ops["rho01"], "10": ops["rho10"], "11": ops["rho11"]}
+        fid, avg, info = orc.cz_fidelity_mixed(3, results, "compat")
+        assert abs(b.avg_fidelity[i] - avg) < 1e-12
+        assert abs(b.cz_phase_fidelity[i] - info["cz_phase_fidelity"]) < 1e-12
+        assert abs(b.controlled_phase_rad[i] - info["controlled_phase_rad"]) < 1e-12
+    with pytest.raises(ValueError):
+        rg.simulate_CZ_gate_batch("lp", B=B, include_noise=True, phase_mode="compat", n_shots=4, **kw)
+    # without noise there are kets, not rho's: the pure-state epilogue stands
+    c = rg.simulate_CZ_gate_batch("lp", B=B, include_noise=False, **kw)
+    d = rg.simulate_CZ_gate_batch("lp", B=B, include_noise=False, phase_mode="compat", **kw)
+    assert np.array_equal(c.avg_fidelity, d.avg_fidelity)

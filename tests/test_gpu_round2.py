@@ -325,3 +325,27 @@ def test_shaped_lp_pulses_on_the_device_prologue(evaluator):
         for lab in ("01", "10", "11"):
             got = ops["rho" + lab] if case["rates"] is not None else ops["coh" + lab][:, 0]
             assert np.abs(got - fin[lab]).max() < 1e-10, (name, lab)
+
+
+def test_batch_compat_epilogue_on_the_gpu():
+    """simulate_CZ_gate_batch(phase_mode="compat") against simulate_CZ_gate(phase_mode="compat") point by point
+    (the reference's dominant-eigenvector formula, RG/simulation.py:424-434, on the rho's the kernel returns)."""
+    from noisyquantumsimulator_b200 import rydberg_gates as rg
+    from noisyquantumsimulator_b200.rydberg_gates.configurations import (LPSimulationInputs, LaserParameters,
+                                                                         TwoPhotonExcitationConfig)
+    from noisyquantumsimulator_b200.rydberg_gates.simulation import _plan_kwargs
+    p2 = np.array([0.2, 0.35, 0.6, 1.1])
+
+    def inputs(p):
+        return LPSimulationInputs(excitation=TwoPhotonExcitationConfig(
+            laser_1=LaserParameters(power=50e-6, waist=50e-6), laser_2=LaserParameters(power=float(p), waist=50e-6),
+            Delta_e=2 * np.pi * 1e9))
+    kw = dict(_plan_kwargs(inputs(p2[0])), laser_2_power=p2, tweezer_power=0.02, tweezer_waist=0.8e-6, warn=False)
+    b = rg.simulate_CZ_gate_batch("lp", B=4, include_noise=True, phase_mode="compat", prologue="host", **kw)
+    d = rg.simulate_CZ_gate_batch("lp", B=4, include_noise=True, prologue="host", **kw)
+    assert np.abs(b.f11_population - d.f11_population).max() < 1e-12
+    for i, p in enumerate(p2):
+        one = rg.simulate_CZ_gate(inputs(p), tweezer_power=0.02, tweezer_waist=0.8e-6, include_noise=True,
+                                  phase_mode="compat")
+        assert abs(one.avg_fidelity - b.avg_fidelity[i]) < 1e-9
+        assert abs(one.phase_info["cz_phase_fidelity"] - b.cz_phase_fidelity[i]) < 1e-9
