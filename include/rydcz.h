@@ -226,6 +226,10 @@ int rydcz_set_pack_threads(rydcz_ctx* ctx, int threads);
  * (/sys/bus/pci/devices/<gpu>/local_cpulist): call once per rank, right after rydcz_create, on multi-socket hosts.
  * *n_cpus = CPUs in the new mask, 0 if the topology could not be read (then nothing changes). */
 int rydcz_bind_host_to_gpu(rydcz_ctx* ctx, int* n_cpus);
+/* How the pipelined host entry points wait for the GPU: 0 = the driver's default (the calling thread spins on a
+ * core until the streams drain: lowest latency, one process per host), 1 = sleep on blocking-sync events (the
+ * core goes back to the other ranks of a shared host).  Env RYDCZ_HOST_WAIT=spin|sleep sets the initial mode. */
+int rydcz_set_host_wait(rydcz_ctx* ctx, int mode);
 /* The same call returning only the result columns the caller reads, COLUMN-MAJOR: h_out_cm[j * n_points + i] =
  * out[i][out_slots[j]] (enum rydcz_out_slot), h_scalars_cm[j * n_points + i] = scalars[i][scalar_slots[j]].
  * The device gathers the columns, so D2H traffic is 8 (n_out + n_scalars) bytes per point instead of 192

@@ -61,6 +61,7 @@ _SIGNATURES = {
                                              _vp, _vp, C.c_int, _vp]),
     "rydcz_set_chunk": (C.c_int, [_vp, C.c_int64]),
     "rydcz_set_pack_threads": (C.c_int, [_vp, C.c_int]),
+    "rydcz_set_host_wait": (C.c_int, [_vp, C.c_int]),
     "rydcz_bind_host_to_gpu": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "rydcz_point_status": (C.c_int, [_vp, C.c_int64, _vp]),
     "rydcz_call_flags": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),

@@ -220,6 +220,19 @@ def emit_system(sysm: model.RealSystem, struct_name: str, cm: bool = False) -> s
             if ch != n_chunks - 1:
                 A("    RYDCZ_SCHED_FENCE();")
         A("  }")
+    if n > 2 * BIG_SYSTEM_N:
+        # A system whose three Clenshaw vectors do not fit in registers at all (the general rho_11 of the 5-level
+        # model: 81 variables): the vectors live in per-thread shared-memory columns and the matvec is emitted ROW
+        # by row -- one accumulator, one load per nonzero, one store per row; the coefficients stay in registers.
+        A("  // One Clenshaw half-step  bo <- ak * xs + G bi + bo  with every vector in a container (shared-memory columns)")
+        A("  template <class XV> RYDCZ_HD static void apply_rows_axpy(const double* __restrict__ c, const XV xs, double ak, const XV bi, const XV bo) {")
+        A("    double a;")
+        for i in range(n):
+            A(f"    a = fma(ak, xs[{i}], bo[{i}]);")
+            for (j, q, sgn) in sorted(rows.get(i, [])):
+                A(f"    a {'+=' if sgn > 0 else '-='} c[{q}] * bi[{j}];")
+            A(f"    bo[{i}] = a;")
+        A("  }")
     if sysm.d in (3, 4):
         # Laser-phase covariance: G(Omega e^{i phi}) = R(phi) G(Omega) R(phi)^T, R rotating the (re, im) pair of
         # entry X[i,j] by q phi, q = (Rydberg excitations of |i>) - (of |j>).  Used by the repeated-segment path

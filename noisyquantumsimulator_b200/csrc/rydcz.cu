@@ -604,18 +604,17 @@ evaluate_cluster_kernel(int64_t n_items, const uint32_t* __restrict__ order, uin
 // Monte-Carlo shots on the planned paths: one perturbed point row per (point, shot) -- the same Philox draws
 // evaluate_kernel<SHOTS> makes -- so that the planner sees the parameters each shot actually runs with.
 __global__ void shot_rows_kernel(int64_t n_points, int n_shots, uint64_t seed, int64_t point_base,
-                                 const double* __restrict__ points, double* __restrict__ rows) {
+                                 const double* __restrict__ points, double* __restrict__ rows, int stride) {
   const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= n_points * n_shots) return;
   const int64_t point = item / n_shots;
   const uint32_t shot = (uint32_t)(item - point * n_shots);
-  const double* row = points + point * PT_STRIDE;
-  double* o = rows + item * PT_STRIDE;
+  const double* row = points + point * stride;        // (12 slots; 20 for the 5-level model: same first twelve)
+  double* o = rows + item * stride;
   double da, db, er, unused;
   philox_normal2(seed, (uint32_t)(point_base + point), shot, 0u, da, db);
   philox_normal2(seed, (uint32_t)(point_base + point), shot, 1u, er, unused);
-#pragma unroll
-  for (int k = 0; k < PT_STRIDE; ++k) o[k] = row[k];
+  for (int k = 0; k < stride; ++k) o[k] = row[k];
   o[PT_OFF_A] = row[PT_OFF_A] + row[PT_SIG_DET] * da;
   o[PT_OFF_B] = row[PT_OFF_B] + row[PT_SIG_DET] * db;
   const double q = 1.0 + row[PT_SIG_RELR] * er;
@@ -708,9 +707,8 @@ constexpr size_t kSmem5 = (size_t)kSlots5 * kBlock * sizeof(double);
 template <bool NOISY>
 __global__ void __launch_bounds__(kBlock, 2)
 evaluate5_kernel(int64_t n_items, const uint32_t* __restrict__ order, const double* __restrict__ points,
-                 const double* __restrict__ segs, const int32_t* __restrict__ n_seg, int max_seg,
-                 double* __restrict__ out, double* __restrict__ states, uint8_t* __restrict__ kind,
-                 unsigned long long* __restrict__ counters) {
+                 const double* __restrict__ segs, const int32_t* __restrict__ n_seg, int max_seg, int seg_div,
+                 double* __restrict__ out, double* __restrict__ states, const uint8_t* __restrict__ kind) {
   extern __shared__ double s5[];
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool inside = g < n_items;
@@ -718,28 +716,70 @@ evaluate5_kernel(int64_t n_items, const uint32_t* __restrict__ order, const doub
   double* mine = s5 + threadIdx.x;
   const double* row = points + point * PT5_STRIDE;
   double* op = out + point * OUT_STRIDE;
-  const bool keep = inside && (row[PT_OFF_A] == row[PT_OFF_B]);
+  // atoms that see different detunings belong to evaluate5_general_kernel (the planner marked them KIND_GENERAL)
+  const bool keep = inside && (kind[point] & KIND_MASK) == KIND_SYM;
   const unsigned live = __ballot_sync(0xffffffffu, keep);   // lanes that evaluate a point (reconvergence mask)
-  if (!inside) return;
-  if (!keep) {
-    // the 81-variable general system is not built: atoms with different detunings are not evaluated.  The row
-    // is NaN, the point's status says why (rydcz_point_status), and the call reports it (rydcz_call_flags).
-#pragma unroll
-    for (int k = 0; k < OUT_STRIDE; ++k) op[k] = __longlong_as_double(0x7ff8000000000000LL);
-    if (kind) kind[point] = KIND_UNSUPPORTED;
-    if (counters) atomicAdd(counters + 4, 1ull);
-    return;
-  }
+  if (!keep) return;
 #pragma unroll
   for (int k = 0; k < PT5_USED; ++k) mine[k * kBlock] = row[k];
   const PointView pt{mine, kBlock, live};
   const Col xcol{mine + (PT_MAX_STRIDE + PT_SCRATCH) * kBlock, kBlock};
   const Col ccol{mine + (PT_MAX_STRIDE + PT_SCRATCH + Sys_rho11s_d5::N) * kBlock, kBlock};
-  const double* sg = segs + point * (int64_t)max_seg * SG_STRIDE;
-  const int ns = n_seg ? n_seg[point] : max_seg;
+  const int64_t sp = point / seg_div;       // seg_div > 1: `points` holds one (perturbed) row per shot
+  const double* sg = segs + sp * (int64_t)max_seg * SG_STRIDE;
+  const int ns = n_seg ? n_seg[sp] : max_seg;
   double o[OUT_STRIDE];
   double* st = states ? states + point * StateLayout<5>::STRIDE : nullptr;
   evaluate_point_sym_d5<NOISY>(pt, xcol, ccol, sg, ns, o, st);
+#pragma unroll
+  for (int k = 0; k < OUT_STRIDE; k += 2)
+    *reinterpret_cast<double2*>(op + k) = make_double2(o[k], o[k + 1]);
+}
+
+// dim 5, atoms that see different detunings (Monte-Carlo shots, or rows the caller made unequal): the general systems
+// (rydcz_core.cuh: evaluate_point_d5).  Per thread in dynamic shared memory: the point row + scratch (26 slots) and the
+// three 81-variable vectors of rho_11 -- 2.2 KB per thread, so 64-thread CTAs, one per SM.  An order of magnitude
+// slower than the identical-atom kernel (two warps per SM, one shared-memory load per FMA): the complete model, not a
+// fast path.
+constexpr int kBlock5g = 64;
+constexpr int kSlots5g = PT_MAX_STRIDE + PT_SCRATCH + 3 * Sys_rho11_d5::N;
+constexpr size_t kSmem5g = (size_t)kSlots5g * kBlock5g * sizeof(double);
+template <bool NOISY>
+__global__ void __launch_bounds__(kBlock5g, 1)
+evaluate5_general_kernel(int64_t n_items, const uint32_t* __restrict__ order, const PlanCounts* __restrict__ plan,
+                         const double* __restrict__ points, const double* __restrict__ segs,
+                         const int32_t* __restrict__ n_seg, int max_seg, int seg_div, double* __restrict__ out,
+                         double* __restrict__ states, const uint8_t* __restrict__ kind) {
+  extern __shared__ double s5g[];
+  int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t limit = n_items;
+  if (plan) {       // only the positions of the general kind group
+    const int64_t lo = plan->group_start[GROUP_GENERAL], n = plan->group_count[GROUP_GENERAL];
+    if ((int64_t)blockIdx.x * blockDim.x >= n) return;
+    g += lo;
+    limit = lo + n;
+  }
+  const bool inside = g < limit;
+  const int64_t point = inside ? (order ? order[g] : g) : 0;
+  const bool keep = inside && (kind[point] & KIND_MASK) == KIND_GENERAL;
+  const unsigned live = __ballot_sync(0xffffffffu, keep);
+  if (!keep) return;
+  double* mine = s5g + threadIdx.x;
+  const double* row = points + point * PT5_STRIDE;
+#pragma unroll
+  for (int k = 0; k < PT5_USED; ++k) mine[k * kBlock5g] = row[k];
+  const PointView pt{mine, kBlock5g, live};
+  constexpr int X0 = PT_MAX_STRIDE + PT_SCRATCH, N = Sys_rho11_d5::N;
+  const Col xcol{mine + X0 * kBlock5g, kBlock5g};
+  const Col b1col{mine + (X0 + N) * kBlock5g, kBlock5g};
+  const Col b2col{mine + (X0 + 2 * N) * kBlock5g, kBlock5g};
+  const int64_t sp = point / seg_div;
+  const double* sg = segs + sp * (int64_t)max_seg * SG_STRIDE;
+  const int ns = n_seg ? n_seg[sp] : max_seg;
+  double o[OUT_STRIDE];
+  double* st = states ? states + point * StateLayout<5>::STRIDE : nullptr;
+  evaluate_point_d5<NOISY>(pt, xcol, b1col, b2col, sg, ns, o, st);
+  double* op = out + point * OUT_STRIDE;
 #pragma unroll
   for (int k = 0; k < OUT_STRIDE; k += 2)
     *reinterpret_cast<double2*>(op + k) = make_double2(o[k], o[k + 1]);
@@ -999,6 +1039,8 @@ struct rydcz_ctx {
   struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t ring_free = nullptr;              // the H2D copies out of `ring` have completed
+    cudaEvent_t done = nullptr;                   // everything enqueued on the lane has completed (blocking-sync wait)
+    int wait_mode = -1;                           // host_wait the two events were created for
     double* ring = nullptr; size_t ring_cap = 0;  // page-locked staging for the packed columns
     double* d_ring = nullptr;                     // its device twin (scattered to the slot rows by fill_slots_kernel)
   };
@@ -1007,6 +1049,9 @@ struct rydcz_ctx {
   int pack_threads = 1;                           // host threads that gather the columns (rydcz_set_pack_threads)
   PackPool* pool = nullptr;
   int64_t chunk = 32768;                          // points per pipeline chunk (profiles/r02_e2e_ranks_n1.txt, _n8.txt)
+  // how the host entry points wait for the GPU: 0 = the driver's default (spins on a core), 1 = sleep on a
+  // blocking-sync event (rydcz_set_host_wait: eight ranks spinning on one shared host starve one another)
+  int host_wait = 0;
 };
 
 // scratch of one work sort (the default one belongs to the context; every lane has its own)
@@ -1364,6 +1409,7 @@ int rydcz_create(int device, rydcz_ctx** out) {
     (void)cores; (void)ranks;
     if (const char* e = getenv("RYDCZ_PACK_THREADS")) { t = atoi(e); t = t < 1 ? 1 : (t > 16 ? 16 : t); }
     ctx->pack_threads = t;
+    if (const char* e = getenv("RYDCZ_HOST_WAIT")) ctx->host_wait = (strcmp(e, "sleep") == 0 || strcmp(e, "1") == 0) ? 1 : 0;
   }
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   if ((e = cudaSetDevice(device)) != cudaSuccess ||
@@ -1397,6 +1443,7 @@ void rydcz_destroy(rydcz_ctx* ctx) {
     rydcz_ctx::Lane& L = ctx->lane[l];
     if (L.stream) { cudaStreamSynchronize(L.stream); cudaStreamDestroy(L.stream); }
     if (L.ring_free) cudaEventDestroy(L.ring_free);
+    if (L.done) cudaEventDestroy(L.done);
     if (L.ring) cudaFreeHost(L.ring);
     cudaFree(L.d_ring);
   }
@@ -1425,6 +1472,13 @@ int rydcz_set_pack_threads(rydcz_ctx* ctx, int threads) {
 // /sys/bus/pci/devices/<gpu>/local_cpulist.  With one process per GPU on a two-socket host this keeps the page-locked
 // staging buffers, the column gather and the driver threads on the GPU's own socket.  Returns the number of CPUs in
 // the mask through n_cpus (0 and no change when the topology cannot be read).
+int rydcz_set_host_wait(rydcz_ctx* ctx, int mode) {
+  if (!ctx) return 2;
+  if (mode != 0 && mode != 1) return fail(ctx, "host wait mode must be 0 (spin) or 1 (sleep)");
+  ctx->host_wait = mode;
+  return 0;
+}
+
 int rydcz_bind_host_to_gpu(rydcz_ctx* ctx, int* n_cpus) {
   if (!ctx) return 2;
   if (n_cpus) *n_cpus = 0;
@@ -1578,28 +1632,48 @@ static int check_args(rydcz_ctx* ctx, int dim, int64_t n, const void* a, const v
   return 0;
 }
 
+// The 5-level model: plan (kind = folded / general, order), then the identical-atom kernel and -- unless the caller
+// guarantees identical atoms -- the general one.  seg_div > 1: `d_points` holds one row per shot.
+static int launch_eval5(rydcz_ctx* ctx, const SortScratch& sc, int64_t n_items, int noisy, const double* d_points,
+                        const double* d_segs, const int32_t* d_n_seg, int max_seg, double* d_out, double* d_states,
+                        cudaStream_t st, int mark, int seg_div) {
+  const uint32_t* order = nullptr;
+  if (make_order<5>(ctx, sc, n_items, d_points, d_segs, d_n_seg, max_seg, 0, noisy, st, &order, seg_div)) return 1;
+  if (!ctx->smem5_set) {
+    CK(cudaFuncSetAttribute(evaluate5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem5));
+    CK(cudaFuncSetAttribute(evaluate5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem5));
+    CK(cudaFuncSetAttribute(evaluate5_general_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem5g));
+    CK(cudaFuncSetAttribute(evaluate5_general_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem5g));
+    ctx->smem5_set = true;
+  }
+  const unsigned grid = (unsigned)((n_items + kBlock - 1) / kBlock);
+  if (mark & 1) CK(cudaEventRecord(ctx->ev0, st));
+  if (!ctx->atoms_identical) {
+    // first: its points are the heaviest, and the order puts them in front
+    const unsigned gg = (unsigned)((n_items + kBlock5g - 1) / kBlock5g);
+    const PlanCounts* plan = order ? sc.plan : nullptr;
+    if (noisy) evaluate5_general_kernel<true><<<gg, kBlock5g, kSmem5g, st>>>(n_items, order, plan, d_points, d_segs, d_n_seg,
+                                                                            max_seg, seg_div, d_out, d_states, sc.kind);
+    else evaluate5_general_kernel<false><<<gg, kBlock5g, kSmem5g, st>>>(n_items, order, plan, d_points, d_segs, d_n_seg,
+                                                                       max_seg, seg_div, d_out, d_states, sc.kind);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
+  if (noisy) evaluate5_kernel<true><<<grid, kBlock, kSmem5, st>>>(n_items, order, d_points, d_segs, d_n_seg, max_seg,
+                                                                 seg_div, d_out, d_states, sc.kind);
+  else evaluate5_kernel<false><<<grid, kBlock, kSmem5, st>>>(n_items, order, d_points, d_segs, d_n_seg, max_seg, seg_div,
+                                                            d_out, d_states, sc.kind);
+  CK(cudaGetLastError());
+  if (mark & 2) { CK(cudaEventRecord(ctx->ev1, st)); ctx->timed = true; }
+  ctx->launches++;
+  return 0;
+}
+
 static int evaluate_impl(rydcz_ctx* ctx, const SortScratch& sc, int dim, int noisy, int64_t n_points,
                          const double* d_points, const double* d_segs, const int32_t* d_n_seg, int max_seg,
                          double* d_out, double* d_states, cudaStream_t st, int mark) {
   const uint32_t* order = nullptr;
-  if (dim == 5) {
-    if (make_order<5>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 0, noisy, st, &order)) return 1;
-    if (!ctx->smem5_set) {
-      CK(cudaFuncSetAttribute(evaluate5_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem5));
-      CK(cudaFuncSetAttribute(evaluate5_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem5));
-      ctx->smem5_set = true;
-    }
-    const unsigned grid = (unsigned)((n_points + kBlock - 1) / kBlock);
-    if (mark & 1) CK(cudaEventRecord(ctx->ev0, st));
-    if (noisy) evaluate5_kernel<true><<<grid, kBlock, kSmem5, st>>>(n_points, order, d_points, d_segs, d_n_seg,
-                                                                   max_seg, d_out, d_states, sc.kind, ctx->cl_counters);
-    else evaluate5_kernel<false><<<grid, kBlock, kSmem5, st>>>(n_points, order, d_points, d_segs, d_n_seg, max_seg,
-                                                              d_out, d_states, sc.kind, ctx->cl_counters);
-    CK(cudaGetLastError());
-    if (mark & 2) { CK(cudaEventRecord(ctx->ev1, st)); ctx->timed = true; }
-    ctx->launches++;
-    return 0;
-  }
+  if (dim == 5) return launch_eval5(ctx, sc, n_points, noisy, d_points, d_segs, d_n_seg, max_seg, d_out, d_states, st, mark, 1);
   int rc = dim == 3 ? make_order<3>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 0, noisy, st, &order)
                     : make_order<4>(ctx, sc, n_points, d_points, d_segs, d_n_seg, max_seg, 0, noisy, st, &order);
   if (rc) return rc;
@@ -1638,11 +1712,20 @@ static int shots_impl(rydcz_ctx* ctx, const SortScratch& sc, int dim, int noisy,
   const int64_t n_items = n_points * n_shots;
   const uint32_t* order = nullptr;
   int rc;
-  if (dim == 3 && ctx->cluster_mode && sc.cl && d_rows) {
+  if (dim == 5) {
+    // the 5-level model: always one perturbed row per shot; rows with Doppler offsets take the general kernel
+    if (!d_rows) return fail(ctx, "dim 5 shots need the shot-row scratch");
+    shot_rows_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(n_points, n_shots, seed, point_base,
+                                                                        d_points, d_rows, PT5_STRIDE);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    rc = launch_eval5(ctx, sc, n_items, noisy, d_rows, d_segs, d_n_seg, max_seg, d_shots, nullptr, st, mark, n_shots);
+    if (rc) return rc;
+  } else if (dim == 3 && ctx->cluster_mode && sc.cl && d_rows) {
     // every shot becomes a point of its own (perturbed row), planned and evaluated like any other point:
     // strong-blockade shots take the clustered general kernel, the rest the plain one
     shot_rows_kernel<<<(unsigned)((n_items + 255) / 256), 256, 0, st>>>(n_points, n_shots, seed, point_base,
-                                                                        d_points, d_rows);
+                                                                        d_points, d_rows, PT_STRIDE);
     CK(cudaGetLastError());
     ctx->launches++;
     rc = make_order<3>(ctx, sc, n_items, d_rows, d_segs, d_n_seg, max_seg, 0, noisy, st, &order, n_shots);
@@ -1675,7 +1758,7 @@ int rydcz_evaluate_shots_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_po
                                 uint64_t seed, const double* d_points, const double* d_segs,
                                 const int32_t* d_n_seg, int max_seg, double* d_out_mean,
                                 double* d_out_shots, void* stream) {
-  if (int rc = check_args(ctx, dim, n_points, d_points, d_segs, max_seg, d_out_mean)) return rc;
+  if (int rc = check_args(ctx, dim, n_points, d_points, d_segs, max_seg, d_out_mean, true)) return rc;
   if (n_shots < 1) return fail(ctx, "n_shots must be >= 1");
   if (n_points * (int64_t)n_shots > 0x7fffffffLL) return fail(ctx, "n_points * n_shots too large");
   if (n_points == 0) return 0;
@@ -1692,13 +1775,14 @@ int rydcz_evaluate_shots_device(rydcz_ctx* ctx, int dim, int noisy, int64_t n_po
   if (order_reserve(ctx, n_items, dim == 3)) return 1;
   if (table_new_call(ctx)) return 1;
   double* rows = nullptr;
-  if (dim == 3 && ctx->cluster_mode) {
-    if (grow(ctx, (void**)&ctx->shot_rows, &ctx->shot_rows_cap, (size_t)n_items * PT_STRIDE * sizeof(double))) return 1;
+  if ((dim == 3 && ctx->cluster_mode) || dim == 5) {
+    if (grow(ctx, (void**)&ctx->shot_rows, &ctx->shot_rows_cap,
+             (size_t)n_items * (dim == 5 ? PT5_STRIDE : PT_STRIDE) * sizeof(double))) return 1;
     rows = ctx->shot_rows;
   }
   if (int rc = shots_impl(ctx, context_scratch(ctx, n_items), dim, noisy, n_points, n_shots, seed, ctx->point_base, d_points, d_segs,
                           d_n_seg, max_seg, d_out_mean, shots, rows, st, 3)) return rc;
-  ctx->status_n = (rows && ctx->cl_scratch) ? n_items : n_points;   // planned per shot, or per point
+  ctx->status_n = (rows && (ctx->cl_scratch || dim == 5)) ? n_items : n_points;   // planned per shot, or per point
   return leave_call(ctx, st);
 }
 
@@ -1713,12 +1797,6 @@ int rydcz_evaluate_host(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, co
                         double* h_states) {
   if (int rc = check_args(ctx, dim, n_points, h_points, h_segs, max_seg, h_out, true)) return rc;
   if (n_points == 0) return 0;
-  if (dim == 5) {
-    // only the exchange-folded 5-level systems are built: refuse unequal atoms here instead of returning NaN rows
-    for (int64_t i = 0; i < n_points; ++i)
-      if (h_points[i * PT5_STRIDE + PT_OFF_A] != h_points[i * PT5_STRIDE + PT_OFF_B])
-        return fail(ctx, "dim 5: atoms with different detunings (OFF_A != OFF_B) are not supported");
-  }
   CK(cudaSetDevice(ctx->device));
   const size_t n = (size_t)n_points;
   const size_t sb = (size_t)rydcz_state_stride(dim) * sizeof(double);
@@ -1741,12 +1819,12 @@ int rydcz_evaluate_host(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, co
 int rydcz_evaluate_shots_host(rydcz_ctx* ctx, int dim, int noisy, int64_t n_points, int n_shots, uint64_t seed,
                               const double* h_points, const double* h_segs, const int32_t* h_n_seg,
                               int max_seg, double* h_out_mean, double* h_out_shots) {
-  if (int rc = check_args(ctx, dim, n_points, h_points, h_segs, max_seg, h_out_mean)) return rc;
+  if (int rc = check_args(ctx, dim, n_points, h_points, h_segs, max_seg, h_out_mean, true)) return rc;
   if (n_shots < 1) return fail(ctx, "n_shots must be >= 1");
   if (n_points == 0) return 0;
   CK(cudaSetDevice(ctx->device));
   const size_t n = (size_t)n_points;
-  if (stage_in(ctx, 0, h_points, n * PT_STRIDE * sizeof(double))) return 1;
+  if (stage_in(ctx, 0, h_points, n * rydcz_point_stride_dim(dim) * sizeof(double))) return 1;
   if (stage_in(ctx, 1, h_segs, n * max_seg * SG_STRIDE * sizeof(double))) return 1;
   if (h_n_seg && stage_in(ctx, 2, h_n_seg, n * sizeof(int32_t))) return 1;
   if (grow(ctx, &ctx->stage[3], &ctx->stage_cap[3], n * OUT_STRIDE * sizeof(double))) return 1;
@@ -1824,7 +1902,6 @@ int rydcz_simulate_device(rydcz_ctx* ctx, const double* h_model, int64_t n_point
   if (!d_app || !d_out) return fail(ctx, "null buffer");
   const int dim = (int)h_model[MD_DIM], S = (int)h_model[MD_NSEG], noisy = h_model[MD_INCLUDE_NOISE] != 0;
   const size_t n = (size_t)n_points;
-  if (dim == 5 && n_shots > 0) return fail(ctx, "Monte-Carlo shots are not available for dim 5");
   // evaluator inputs live in context scratch (slots 0..2 are shared with the *_host entry points)
   if (grow(ctx, &ctx->plan[0], &ctx->plan_cap[0], n * rydcz_point_stride_dim(dim) * sizeof(double))) return 1;
   if (grow(ctx, &ctx->plan[1], &ctx->plan_cap[1], n * S * SG_STRIDE * sizeof(double))) return 1;
@@ -1894,7 +1971,6 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
   if (n_points * (int64_t)(n_shots > 0 ? n_shots : 1) > 0x7fffffffLL) return fail(ctx, "n_points * n_shots too large");
   CK(cudaSetDevice(ctx->device));
   const int dim = (int)h_model[MD_DIM], S = (int)h_model[MD_NSEG], noisy = h_model[MD_INCLUDE_NOISE] != 0;
-  if (dim == 5 && n_shots > 0) return fail(ctx, "Monte-Carlo shots are not available for dim 5");
   const int pstride = rydcz_point_stride_dim(dim);
   const size_t n = (size_t)n_points;
   const size_t sb = (size_t)rydcz_state_stride(dim) * sizeof(double);
@@ -1978,8 +2054,8 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
   ctx->call_flags = 0;
   if (order_reserve(ctx, n_points * per_item, dim != 5 && (n_shots == 0 || dim == 3))) return 1;
   if (table_new_call(ctx)) return 1;      // one generation for the whole pipelined call: its chunks share the entries
-  if (n_shots > 0 && dim == 3 && ctx->cluster_mode &&
-      grow(ctx, (void**)&ctx->shot_rows, &ctx->shot_rows_cap, n * per_item * PT_STRIDE * sizeof(double))) return 1;
+  if (n_shots > 0 && ((dim == 3 && ctx->cluster_mode) || dim == 5) &&
+      grow(ctx, (void**)&ctx->shot_rows, &ctx->shot_rows_cap, n * per_item * pstride * sizeof(double))) return 1;
   if (sel_out && grow(ctx, &ctx->sel_out, &ctx->sel_out_cap, n * (sel_out->n ? sel_out->n : 1) * sizeof(double))) return 1;
   if (sel_sc && h_scalars && grow(ctx, &ctx->sel_sc, &ctx->sel_sc_cap, n * (sel_sc->n ? sel_sc->n : 1) * sizeof(double))) return 1;
   double* d_app = (double*)ctx->stage[0];
@@ -1993,9 +2069,14 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
   const int n_lanes = n_chunks < rydcz_ctx::kLanes ? (int)n_chunks : rydcz_ctx::kLanes;
   for (int l = 0; l < n_lanes; ++l) {
     rydcz_ctx::Lane& L = ctx->lane[l];
-    if (!L.stream) {
-      CK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
-      CK(cudaEventCreateWithFlags(&L.ring_free, cudaEventDisableTiming));
+    if (!L.stream) CK(cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking));
+    if (L.wait_mode != ctx->host_wait) {
+      if (L.ring_free) CK(cudaEventDestroy(L.ring_free));
+      if (L.done) CK(cudaEventDestroy(L.done));
+      const unsigned flags = cudaEventDisableTiming | (ctx->host_wait ? cudaEventBlockingSync : 0u);
+      CK(cudaEventCreateWithFlags(&L.ring_free, flags));
+      CK(cudaEventCreateWithFlags(&L.done, flags));
+      L.wait_mode = ctx->host_wait;
     }
     size_t need_cols = 0;                                   // ring: the blocks' rows, then the single columns
     for (int b = 0; b < n_blocks; ++b) need_cols += (size_t)blocks[b].stride;
@@ -2113,7 +2194,7 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
       rc = shots_impl(ctx, sc, dim, noisy, nc, n_shots, seed, ctx->point_base + i0, d_pts + i0 * pstride,
                       d_segs + i0 * (int64_t)S * SG_STRIDE, d_ns + i0, S, d_out + i0 * OUT_STRIDE,
                       d_shots + i0 * n_shots * OUT_STRIDE,
-                      (dim == 3 && ctx->cluster_mode && ctx->shot_rows) ? ctx->shot_rows + i0 * n_shots * PT_STRIDE : nullptr,
+                      (((dim == 3 && ctx->cluster_mode) || dim == 5) && ctx->shot_rows) ? ctx->shot_rows + i0 * n_shots * pstride : nullptr,
                       st, mark);
     else {
       ctx->atoms_identical = true;      // rows written by prologue_kernel: OFF_A = OFF_B = 0
@@ -2153,7 +2234,13 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
     if (h_states)
       CK(cudaMemcpyAsync((char*)h_states + i0 * sb, (char*)d_st + i0 * sb, nc * sb, cudaMemcpyDeviceToHost, st));
   }
-  for (int l = 0; l < n_lanes; ++l) CK(cudaStreamSynchronize(ctx->lane[l].stream));
+  if (ctx->host_wait) {
+    // sleep until the lanes have drained (the thread leaves its core to the other ranks of the host)
+    for (int l = 0; l < n_lanes; ++l) CK(cudaEventRecord(ctx->lane[l].done, ctx->lane[l].stream));
+    for (int l = 0; l < n_lanes; ++l) CK(cudaEventSynchronize(ctx->lane[l].done));
+  } else {
+    for (int l = 0; l < n_lanes; ++l) CK(cudaStreamSynchronize(ctx->lane[l].stream));
+  }
   ctx->busy_set = false;                 // everything this context enqueued has completed
   ctx->status_n = n_points * per_item;
   if (n_shots > 0 && !(dim == 3 && ctx->cluster_mode && ctx->shot_rows && ctx->cl_scratch)) ctx->status_n = n_points;

@@ -40,7 +40,10 @@ constexpr int CL_HDR = 8;          // doubles of a slot header (two records)
 constexpr int CL_OWN0 = CL_MAX_SLOTS * CL_HDR / CL_REC;     // a point's region: its slot headers first, then its own records
 constexpr int CL_RECORDS = CL_MAX_SLOTS * (CL_MAX_K + 3);   // records per point: header (2) + K + 1 terms per slot
 constexpr int CL_STRIDE = CL_RECORDS * CL_REC;              // doubles per point in the coefficient scratch
-constexpr int CL_ALIGN = 8;        // Clenshaw steps per (sub)step are padded to a multiple of this, so the
+#ifndef RYDCZ_CL_ALIGN
+#define RYDCZ_CL_ALIGN 8
+#endif
+constexpr int CL_ALIGN = RYDCZ_CL_ALIGN;        // Clenshaw steps per (sub)step are padded to a multiple of this, so the
                                    // lanes of a warp reach their segment transitions at common iterations
                                    // (4: less padding but more scattered transitions, 2.36 ms against 2.24 ms)
 constexpr double CL_Z_MAX = 26.0;  // largest h * freq of one sub-step (keeps K <= CL_MAX_K: 26 + 10.3 * 26^(1/3) + 4 - 2 < 62)

@@ -163,7 +163,10 @@ RYDCZ_HD int cheb_terms(double z) {
 // The plain loop starts its backward recurrences at a multiple of 8 (more terms are always valid): the
 // lanes of a warp then reach their segment transitions at common iterations, which matters for the short
 // segments of the single-atom systems once the clustered path has made everything else cheap.
-RYDCZ_HD int cheb_terms_aligned(double z) { return (cheb_terms(z) + 7) & ~7; }
+#ifndef RYDCZ_PLAIN_ALIGN
+#define RYDCZ_PLAIN_ALIGN 8
+#endif
+RYDCZ_HD int cheb_terms_aligned(double z) { return (cheb_terms(z) + RYDCZ_PLAIN_ALIGN - 1) & ~(RYDCZ_PLAIN_ALIGN - 1); }
 
 // Work estimate used to order points (same formula the evolution uses).
 RYDCZ_HD double cheb_work(double radius, double dt) {
@@ -493,6 +496,95 @@ RYDCZ_HD void run_system_big(const XV x, const CV c, const PointView pt, const d
   }
 }
 
+// run_system for a system whose Clenshaw vectors do not fit in registers at all (the general rho_11 of the 5-level
+// model: 81 real variables, unequal atoms / Monte-Carlo shots).  The start vector x and both Clenshaw vectors live in
+// per-thread shared-memory columns; the 45 coefficients stay in registers and the matvec walks the rows
+// (Sys::apply_rows_axpy: one accumulator, one shared-memory load per nonzero, one store per row).  Same arithmetic as
+// run_system_big; an order of magnitude slower (two warps per SM, a load per FMA) -- it exists so that the 5-level
+// model is complete, the identical-atom kernel is the fast path.
+template <class Sys, class XV>
+RYDCZ_HD void run_system_huge(const XV x, const XV b1, const XV b2, const PointView pt, const double* __restrict__ seg,
+                              int n_seg, bool noisy, double& steps) {
+  constexpr int N = Sys::N;
+  static_assert(Sys::HERMITIAN, "run_system_huge: density-matrix systems only");
+  {
+    double x0[N];
+    Sys::init(x0);
+    RYDCZ_UNROLL
+    for (int i = 0; i < N; ++i) x[i] = x0[i];
+  }
+  double c[Sys::NC];
+  double jp = 0.0, jk = 0.0, norm = 0.0, kd = 0.0, tz = 0.0;
+  double &iv_om2 = pt.scratch(0), &iv_da = pt.scratch(1), &iv_db = pt.scratch(2), &iv_R = pt.scratch(3),
+         &iv_damp = pt.scratch(5);
+  iv_om2 = -1.0;
+  int k = 0, K = 0, sub_left = 0, s = 0;
+  bool active = false;
+  for (;;) {
+    if (k < 2) {
+      if (active) {
+        // k = 0:  exp(hG) x = (J_0 x + A b1 + b2) / (J_0 + 2 sum_even J_k),  A b1 = (2A)(b1/2)
+        for (int i = 0; i < N; ++i) b1[i] *= 0.5;
+        Sys::apply_rows_axpy(c, x, jk, b1, b2);
+        const double inv = 1.0 / (norm + jk);
+        for (int i = 0; i < N; ++i) x[i] = b2[i] * inv;
+        steps += (double)(K + 1);
+        active = false;
+      }
+      if (sub_left > 0) {
+        --sub_left;
+      } else {
+        double dt = 0.0;
+        double p[Sys::NP];
+        if (!next_segment<Sys>(p, pt, seg, n_seg, s, dt, noisy)) break;
+        const double sgn = dt < 0.0 ? -1.0 : 1.0;
+        const double adt = fabs(dt);
+        const double om2 = p[Sys::IDX_OM_RE] * p[Sys::IDX_OM_RE] + p[Sys::IDX_OM_IM] * p[Sys::IDX_OM_IM];
+        if (!(fabs(om2 - iv_om2) <= 1e-9 * iv_om2 && same_detuning<Sys>(p[Sys::IDX_DET_A], iv_da) &&
+              same_detuning<Sys>(p[Sys::IDX_DET_B], iv_db))) {
+          const double re = p[Sys::IDX_OM_RE], im = p[Sys::IDX_OM_IM];
+          const double mag = sqrt(om2);
+          p[Sys::IDX_OM_RE] = mag; p[Sys::IDX_OM_IM] = mag;
+          double lo, hi;
+          Sys::coefs(p, c);
+          Sys::bounds(c, lo, hi, iv_damp);
+          iv_R = hi;
+          p[Sys::IDX_OM_RE] = re; p[Sys::IDX_OM_IM] = im;
+          iv_om2 = om2; iv_da = p[Sys::IDX_DET_A]; iv_db = p[Sys::IDX_DET_B];
+        }
+        const double damp = iv_damp;
+        double R = iv_R;
+        Sys::coefs(p, c);
+        int nsub = 1;
+        if (damp * adt > 2.0) nsub = (int)ceil(0.5 * damp * adt);
+        const double h = adt / (double)nsub;
+        if (!(R * h >= 1e-2)) R = 1e-2 / h;
+        const double z = R * h;
+        const double sc = sgn * 2.0 / R;
+        RYDCZ_UNROLL
+        for (int q = 0; q < Sys::NC; ++q) c[q] *= sc;
+        K = cheb_terms_aligned(z);
+        tz = 2.0 / z;
+        sub_left = nsub - 1;
+      }
+      for (int i = 0; i < N; ++i) { b1[i] = 0.0; b2[i] = 0.0; }
+      jp = 0.0; jk = 1e-30;
+      norm = 0.0;
+      kd = (double)K;
+      k = K;
+      active = true;
+    }
+    double ak = jk + jk;
+    Sys::apply_rows_axpy(c, x, ak, b1, b2);
+    norm += ak;
+    double jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
+    ak = jk + jk;
+    Sys::apply_rows_axpy(c, x, ak, b2, b1);
+    jm = fma(kd * tz, jk, -jp); jp = jk; jk = jm; kd -= 1.0;
+    k -= 2;
+  }
+}
+
 RYDCZ_HD double wrap_pi(double x) {
   // Python: (x + pi) % (2 pi) - pi, with % taking the sign of the divisor  (RG/simulation.py:608)
   const double twopi = 6.283185307179586476925286766559;
@@ -746,6 +838,72 @@ RYDCZ_HD void evaluate_point_sym_d5(const PointView pt, const Col xcol, const Co
       states[SL::COH01 + i] = x[i]; states[SL::COH10 + i] = x[i]; } }
   }
   cz_epilogue(NOISY, p01, p01, p11, c01r, c01i, c01r, c01i, c11r, c11i, out);
+  out[OUT_LOSS] = loss; out[OUT_RYD] = ryd; out[OUT_STEPS] = steps; out[OUT_FLOPS] = flops;
+}
+
+// dim = 5, atoms that see different detunings (Monte-Carlo shots with Doppler offsets): the general systems.  rho_11
+// (81 variables) through run_system_huge with x, b1, b2 in the shared-memory columns xcol / b1col / b2col; the
+// coherence (18 variables) and the two single-atom inputs (15 each) in registers.
+template <bool NOISY>
+RYDCZ_HD void evaluate_point_d5(const PointView pt, const Col xcol, const Col b1col, const Col b2col,
+                                const double* __restrict__ seg, int n_seg, double* __restrict__ out,
+                                double* __restrict__ states) {
+  typedef StateLayout<5> SL;
+  double steps = 0.0, flops = 0.0, st;
+  double p01 = 1.0, p10 = 1.0, p11 = 1.0, loss = 0.0, ryd = 0.0;
+  double c01r, c01i, c10r, c10i, c11r, c11i;
+  if (NOISY) {
+    st = 0.0;
+    run_system_huge<Sys_rho11_d5, Col>(xcol, b1col, b2col, pt, seg, n_seg, true, st);
+    RYDCZ_RECONVERGE(pt.live);
+    steps += st; flops += st * 2.0 * (Sys_rho11_d5::NNZ + Sys_rho11_d5::N);
+    double x[Sys_rho11_d5::N];
+    for (int i = 0; i < Sys_rho11_d5::N; ++i) x[i] = xcol[i];
+    p11 = x[RHO11_POP_D5];
+    loss = rho11_loss_d5(x); ryd = rho11_ryd_d5(x);
+    if (states) { for (int i = 0; i < Sys_rho11_d5::N; ++i) states[SL::RHO11 + i] = x[i]; }
+  }
+  {
+    double x[Sys_coh11_d5::N]; st = 0.0;
+    run_system<Sys_coh11_d5>(x, pt, seg, n_seg, NOISY, st);
+    RYDCZ_RECONVERGE(pt.live);
+    steps += st; flops += st * 2.0 * (Sys_coh11_d5::NNZ + Sys_coh11_d5::N);
+    c11r = x[COH11_RE_D5]; c11i = x[COH11_IM_D5];
+    if (!NOISY) ryd = coh11_ryd_d5(x);
+    if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh11_d5::N; ++i) states[SL::COH11 + i] = x[i]; }
+  }
+  if (NOISY) {
+    double x[Sys_in01_d5::N]; st = 0.0;
+    run_system<Sys_in01_d5>(x, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);
+    steps += st; flops += st * 2.0 * (Sys_in01_d5::NNZ + Sys_in01_d5::N);
+    p01 = x[RHO01_POP_D5];
+    c01r = x[IN01_COH_OFFSET_D5 + COH01_RE_D5]; c01i = x[IN01_COH_OFFSET_D5 + COH01_IM_D5];
+    if (states) {
+      RYDCZ_UNROLL for (int i = 0; i < Sys_rho01_d5::N; ++i) states[SL::RHO01 + i] = x[i];
+      RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d5::N; ++i) states[SL::COH01 + i] = x[IN01_COH_OFFSET_D5 + i];
+    }
+    double y[Sys_in10_d5::N]; st = 0.0;
+    run_system<Sys_in10_d5>(y, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);
+    steps += st; flops += st * 2.0 * (Sys_in10_d5::NNZ + Sys_in10_d5::N);
+    p10 = y[RHO10_POP_D5];
+    c10r = y[IN10_COH_OFFSET_D5 + COH10_RE_D5]; c10i = y[IN10_COH_OFFSET_D5 + COH10_IM_D5];
+    if (states) {
+      RYDCZ_UNROLL for (int i = 0; i < Sys_rho10_d5::N; ++i) states[SL::RHO10 + i] = y[i];
+      RYDCZ_UNROLL for (int i = 0; i < Sys_coh10_d5::N; ++i) states[SL::COH10 + i] = y[IN10_COH_OFFSET_D5 + i];
+    }
+  } else {
+    double x[Sys_coh01_d5::N]; st = 0.0;
+    run_system<Sys_coh01_d5>(x, pt, seg, n_seg, false, st); RYDCZ_RECONVERGE(pt.live);
+    steps += st; flops += st * 2.0 * (Sys_coh01_d5::NNZ + Sys_coh01_d5::N);
+    c01r = x[COH01_RE_D5]; c01i = x[COH01_IM_D5];
+    if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d5::N; ++i) states[SL::COH01 + i] = x[i]; }
+    double y[Sys_coh10_d5::N]; st = 0.0;
+    run_system<Sys_coh10_d5>(y, pt, seg, n_seg, false, st); RYDCZ_RECONVERGE(pt.live);
+    steps += st; flops += st * 2.0 * (Sys_coh10_d5::NNZ + Sys_coh10_d5::N);
+    c10r = y[COH10_RE_D5]; c10i = y[COH10_IM_D5];
+    if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh10_d5::N; ++i) states[SL::COH10 + i] = y[i]; }
+  }
+  cz_epilogue(NOISY, p01, p10, p11, c01r, c01i, c10r, c10i, c11r, c11i, out);
   out[OUT_LOSS] = loss; out[OUT_RYD] = ryd; out[OUT_STEPS] = steps; out[OUT_FLOPS] = flops;
 }
 

@@ -303,6 +303,11 @@ class Evaluator:
         """Host threads that gather the varying columns into pinned staging (rydcz_set_pack_threads)."""
         self._check(self.lib.rydcz_set_pack_threads(self.ctx, int(threads)), "rydcz_set_pack_threads")
 
+    def set_host_wait(self, sleep: bool):
+        """True: the pipelined host entry points sleep while the GPU works instead of spinning on a core
+        (rydcz_set_host_wait; for several ranks on one host)."""
+        self._check(self.lib.rydcz_set_host_wait(self.ctx, 1 if sleep else 0), "rydcz_set_host_wait")
+
     def bind_host_to_gpu(self) -> int:
         """Bind this process's calling thread (and threads created later) to the CPUs next to this GPU; returns
         the number of CPUs in the new mask (0: topology unknown, nothing changed).  One call per rank."""

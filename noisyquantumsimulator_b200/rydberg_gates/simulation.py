@@ -691,9 +691,6 @@ def simulate_CZ_gate_batch(protocol: str, *, B: int = None, n_shots: int = 0, se
     # shaped LP pulses (gaussian / cosine / blackman) run through the device prologue as well; 'drag' cannot run
     # at all (it fails in the reference too) and is left to the host prologue to raise the reference's error
     shaped = protocol == "lp" and kwargs.get("pulse_shape", "square") not in ("square", "gaussian", "cosine", "blackman")
-    five = kwargs.get("hilbert_space_dim", 3) == 5 or (plan is not None and plan.dim == 5)
-    if five and n_shots > 0:
-        raise ValueError("Monte-Carlo shots are not available for hilbert_space_dim=5")
     if prologue == "auto":
         prologue = "host" if (plan is not None or shaped or return_shots) else "device"
     if outputs is not None:

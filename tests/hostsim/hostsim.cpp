@@ -168,8 +168,14 @@ extern "C" int hostsim_evaluate(int dim, int noisy, long long n_points, const do
       else if (noisy) evaluate_point_d4<true>(pt, sg, n_seg[i], o, st);
       else evaluate_point_d4<false>(pt, sg, n_seg[i], o, st);
     } else if (dim == 5) {
-      if (!(pt[PT_OFF_A] == pt[PT_OFF_B])) return 2;   // identical atoms only, like the CUDA path
       double* st = states ? states + i * StateLayout<5>::STRIDE : nullptr;
+      if (!sym) {
+        // unequal atoms: the general systems, rho_11's three vectors in "shared-memory" columns
+        double xg[Sys_rho11_d5::N], b1g[Sys_rho11_d5::N], b2g[Sys_rho11_d5::N];
+        if (noisy) evaluate_point_d5<true>(pt, Col{xg, 1}, Col{b1g, 1}, Col{b2g, 1}, sg, n_seg[i], o, st);
+        else evaluate_point_d5<false>(pt, Col{xg, 1}, Col{b1g, 1}, Col{b2g, 1}, sg, n_seg[i], o, st);
+        continue;
+      }
       double xcol[Sys_rho11s_d5::N], ccol[Sys_rho11s_d5::NC];
       if (noisy) evaluate_point_sym_d5<true>(pt, Col{xcol, 1}, Col{ccol, 1}, sg, n_seg[i], o, st);
       else evaluate_point_sym_d5<false>(pt, Col{xcol, 1}, Col{ccol, 1}, sg, n_seg[i], o, st);

@@ -108,7 +108,39 @@ def test_public_api_dim5_on_host_harness(monkeypatch):
                                   laser_2_power=np.array([0.1, 0.3, 1.0]), laser_2_waist=50e-6,
                                   Delta_e=2 * np.pi * 1e9, warn=False, **kw)
     assert abs(b.avg_fidelity[1] - rb.avg_fidelity) < 1e-12 and b.raw.shape == (3, 16)
-    with pytest.raises(ValueError):
-        rg.simulate_CZ_gate_batch("lp", B=1, hilbert_space_dim=5, n_shots=4, laser_1_power=50e-6,
-                                  laser_1_waist=50e-6, laser_2_power=0.3, laser_2_waist=50e-6,
-                                  Delta_e=2 * np.pi * 1e9, warn=False)
+
+
+
+def _oracle5(case, pt):
+    segs = [orc.Segment(s[0], complex(s[1], s[2]), s[3]) for s in case["segs"]]
+    rates = orc.NoiseRates5(g_e1=pt[14], g_e0=pt[15], g_r1=pt[4], g_r0=pt[5], g_rl=pt[16], g_phi=pt[6]) \
+        if case["noisy"] else None
+    return orc.evaluate5(segs, pt[0], pt[1], pt[12], pt[13], rates, ls_comp=pt[17], detuning_offsets=(pt[2], pt[3]))
+
+
+@pytest.mark.parametrize("name", ["lp5_rb_noisy", "lp5_rb_noiseless"])
+def test_unequal_atoms_take_the_general_five_level_systems(hostsim, name):
+    """Atoms that see different detunings (a Monte-Carlo shot's Doppler offsets): the general 81-variable rho_11 with
+    its three Clenshaw vectors in columns (run_system_huge), the 18-variable coherence and both single-atom inputs,
+    against the oracle's dense 625x625 expm at the same per-atom offsets.  (Round 1 returned NaN rows here.)"""
+    case = next(c for c in CASES if c["name"] == name)
+    pts, seg, ns = C.pack_batch5([case])
+    pts[0, 2], pts[0, 3] = 2 * np.pi * 41e3, -2 * np.pi * 23e3            # PT_OFF_A, PT_OFF_B
+    out, st = hostsim(5, case["noisy"], pts, seg, ns)
+    fid, avg, info, fin = _oracle5(case, pts[0])
+    assert abs(out[0, C.OUT["avg"]] - avg) < 1e-9
+    assert abs(out[0, C.OUT["f01"]] - fid["01"]) < 1e-9 and abs(out[0, C.OUT["f10"]] - fid["10"]) < 1e-9
+    assert abs(fid["01"] - fid["10"]) > 1e-7                              # the two atoms really differ
+    ops = C.states_to_operators(5, st[0])
+    if case["noisy"]:
+        for key, lab, idx in (("rho11", "11", C.ACT2), ("rho01", "01", C.ACT01), ("rho10", "10", C.ACT10)):
+            assert np.abs(ops[key][np.ix_(idx, idx)] - fin[lab][np.ix_(idx, idx)]).max() < 1e-10, key
+        assert abs(out[0, C.OUT["loss"]] - (1.0 - np.trace(fin["11"][np.ix_(C.ACT2, C.ACT2)]).real)) < 1e-9
+    else:
+        assert np.abs(ops["coh11"][C.ACT2, 0] - fin["11"][C.ACT2]).max() < 1e-10
+        assert np.abs(ops["coh10"][C.ACT10, 0] - fin["10"][C.ACT10]).max() < 1e-10
+    # identical atoms through the general systems = the folded path
+    pts[0, 2] = pts[0, 3] = 0.0
+    a, sa = hostsim(5, case["noisy"], pts, seg, ns)
+    b, sb = hostsim(5, case["noisy"], pts, seg, ns, allow_sym=False)
+    assert np.abs(a[0, :14] - b[0, :14]).max() < 1e-11

@@ -66,6 +66,10 @@ def measure(label, reps=6):
 if rank == 0:
     print("world", world, "cpus allowed", len(os.sched_getaffinity(0)), "of", os.cpu_count(), flush=True)
 measure("default (pool)")
+ev.set_host_wait(True)
+measure("host wait = sleep")
+ev.set_host_wait(False)
+measure("host wait = spin")
 ev.set_pack_threads(1)
 measure("pack_threads=1")
 ev.set_pack_threads(2)
