@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "librydcz.so")
 SOURCES = ["rydcz.cu"]
-DEPS = ["rydcz.cu", "rydcz_core.cuh", "rydcz_cluster.cuh", "rydcz_repeat.cuh", "rydcz_prologue.cuh", "rydcz_systems_d3.inc", "rydcz_systems_d4.inc",
+DEPS = ["rydcz.cu", "rydcz_core.cuh", "rydcz_closed.cuh", "rydcz_cluster.cuh", "rydcz_repeat.cuh", "rydcz_prologue.cuh", "rydcz_systems_d3.inc", "rydcz_systems_d4.inc",
         "rydcz_systems_d5.inc",
         os.path.join("..", "..", "include", "rydcz.h")]
 

@@ -197,15 +197,18 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
     // first *repeat_count positions), clustered general, general, plain folded, clustered
     uint32_t group = sym ? GROUP_SYM : GROUP_GENERAL;
     double w = 0.0;
-    if (D == 3 && repeat_count && sym && !shots) {
+    // noiseless, identical atoms, 3-level model: every system is a coherence with a closed form (rydcz_closed.cuh);
+    // the plain folded kernel evaluates the point in a few hundred instructions per segment, no planned path pays
+    const bool closed_all = D == 3 && RYDCZ_CLOSED_COHERENCE != 0 && sym && !noisy;
+    if (D == 3 && repeat_count && sym && !shots && !closed_all) {
       int first, count;
       if (repeat_eligible(sg, ns, first, count)) {
         // one propagator for all segments (rydcz_repeat.cuh): 30 column builds + count dense steps
         repeated = true; group = GROUP_REPEAT; w = 40.0 * 30.0 + 4.0 * (double)count;
       }
     }
-    if (!repeated) w = point_work<D>(pt, sg, ns);
-    if (D != 5 && cluster_mode && (sym || D == 3) && !shots && !repeated) {
+    if (!repeated) w = closed_all ? 16.0 * (double)ns : point_work<D>(pt, sg, ns);
+    if (D != 5 && cluster_mode && (sym || D == 3) && !shots && !repeated && !closed_all) {
       double cost = 0.0;
       // the slot headers are written on the way (harmless if the point stays on the plain path); unequal atoms
       // (3-level model only) take the two-atom bounds and the general kernel

@@ -811,10 +811,14 @@ template <int D> struct ClusterRing { static constexpr int value = D == 3 ? 8 : 
     }                                                                                               \
     {                                                                                               \
       double (&x)[Sys_coh11s_d##D::N] = xcoh;                                                       \
+      double cf = 0.0;                                                                              \
       st = 0.0;                                                                                     \
-      run_system_cluster<Sys_coh11s_d##D, ClusterRing<D>::value>(x, xcol, rcol, pt, seg, n_seg, NOISY, rec, table, st); \
+      if (ClosedCoh11s<D>::template run<NOISY>(x, pt, seg, n_seg, cf)) flops += cf;                 \
+      else {                                                                                        \
+        run_system_cluster<Sys_coh11s_d##D, ClusterRing<D>::value>(x, xcol, rcol, pt, seg, n_seg, NOISY, rec, table, st); \
+        steps += st; flops += st * 2.0 * (3 * Sys_coh11s_d##D::NNZ + 4 * Sys_coh11s_d##D::N);       \
+      }                                                                                             \
       RYDCZ_RECONVERGE(pt.live);                                                                    \
-      steps += st; flops += st * 2.0 * (3 * Sys_coh11s_d##D::NNZ + 4 * Sys_coh11s_d##D::N);         \
       c11r = x[COH11S_RE_D##D]; c11i = x[COH11S_IM_D##D];                                           \
       if (!NOISY) ryd = 1.0 - (c11r * c11r + c11i * c11i);                                          \
       if (!NOISY || states) {                                                                       \
@@ -825,7 +829,21 @@ template <int D> struct ClusterRing { static constexpr int value = D == 3 ? 8 : 
       }                                                                                             \
     }                                                                                               \
     if (!ok) return false;                                                                          \
-    if (NOISY) {                                                                                    \
+    if (NOISY && ClosedCoh11s<D>::available) {                                                      \
+      double x[Sys_rho01_d##D::N]; st = 0.0;                                                        \
+      run_system<Sys_rho01_d##D>(x, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);           \
+      steps += st; flops += st * 2.0 * (Sys_rho01_d##D::NNZ + Sys_rho01_d##D::N);                   \
+      p01 = x[RHO01_POP_D##D];                                                                      \
+      double xc[Sys_coh01_d##D::N];                                                                 \
+      single_atom_coherence<Sys_coh01_d##D, true>(xc, pt, seg, n_seg, true, steps, flops);          \
+      c01r = xc[COH01_RE_D##D]; c01i = xc[COH01_IM_D##D];                                           \
+      if (states) {                                                                                 \
+        RYDCZ_UNROLL for (int i = 0; i < Sys_rho01_d##D::N; ++i) {                                  \
+          states[SL::RHO01 + i] = x[i]; states[SL::RHO10 + i] = x[i]; }                             \
+        RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d##D::N; ++i) {                                  \
+          states[SL::COH01 + i] = xc[i]; states[SL::COH10 + i] = xc[i]; }                           \
+      }                                                                                             \
+    } else if (NOISY) {                                                                             \
       double x[Sys_in01_d##D::N]; st = 0.0;                                                         \
       run_system<Sys_in01_d##D>(x, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);            \
       steps += st; flops += st * 2.0 * (Sys_in01_d##D::NNZ + Sys_in01_d##D::N);                     \
@@ -838,9 +856,8 @@ template <int D> struct ClusterRing { static constexpr int value = D == 3 ? 8 : 
           states[SL::COH01 + i] = x[IN01_COH_OFFSET_D##D + i]; states[SL::COH10 + i] = x[IN01_COH_OFFSET_D##D + i]; } \
       }                                                                                             \
     } else {                                                                                        \
-      double x[Sys_coh01_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_coh01_d##D>(x, pt, seg, n_seg, false, st); RYDCZ_RECONVERGE(pt.live);          \
-      steps += st; flops += st * 2.0 * (Sys_coh01_d##D::NNZ + Sys_coh01_d##D::N);                   \
+      double x[Sys_coh01_d##D::N];                                                                  \
+      single_atom_coherence<Sys_coh01_d##D, false>(x, pt, seg, n_seg, true, steps, flops);          \
       c01r = x[COH01_RE_D##D]; c01i = x[COH01_IM_D##D];                                             \
       if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d##D::N; ++i) {                      \
         states[SL::COH01 + i] = x[i]; states[SL::COH10 + i] = x[i]; } }                             \
@@ -889,33 +906,34 @@ RYDCZ_HD bool evaluate_point_cluster_general_d3(const PointView pt, const Col xc
   }
   if (!ok) return false;
   if (NOISY) {
-    double x[Sys_in01_d3::N]; st = 0.0;
-    run_system<Sys_in01_d3>(x, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);
-    steps += st; flops += st * 2.0 * (Sys_in01_d3::NNZ + Sys_in01_d3::N);
+    // single-atom inputs: rho_ab on its Chebyshev loop, the |ab><00| coherence in closed form (rydcz_closed.cuh)
+    double x[Sys_rho01_d3::N]; st = 0.0;
+    run_system<Sys_rho01_d3>(x, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);
+    steps += st; flops += st * 2.0 * (Sys_rho01_d3::NNZ + Sys_rho01_d3::N);
     p01 = x[RHO01_POP_D3];
-    c01r = x[IN01_COH_OFFSET_D3 + COH01_RE_D3]; c01i = x[IN01_COH_OFFSET_D3 + COH01_IM_D3];
+    double xc[Sys_coh01_d3::N];
+    single_atom_coherence<Sys_coh01_d3, true>(xc, pt, seg, n_seg, true, steps, flops);
+    c01r = xc[COH01_RE_D3]; c01i = xc[COH01_IM_D3];
+    double y[Sys_rho10_d3::N]; st = 0.0;
+    run_system<Sys_rho10_d3>(y, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);
+    steps += st; flops += st * 2.0 * (Sys_rho10_d3::NNZ + Sys_rho10_d3::N);
+    p10 = y[RHO10_POP_D3];
+    double yc[Sys_coh10_d3::N];
+    single_atom_coherence<Sys_coh10_d3, true>(yc, pt, seg, n_seg, false, steps, flops);
+    c10r = yc[COH10_RE_D3]; c10i = yc[COH10_IM_D3];
     if (states) {
       RYDCZ_UNROLL for (int i = 0; i < Sys_rho01_d3::N; ++i) states[SL::RHO01 + i] = x[i];
-      RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d3::N; ++i) states[SL::COH01 + i] = x[IN01_COH_OFFSET_D3 + i];
-    }
-    double y[Sys_in10_d3::N]; st = 0.0;
-    run_system<Sys_in10_d3>(y, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);
-    steps += st; flops += st * 2.0 * (Sys_in10_d3::NNZ + Sys_in10_d3::N);
-    p10 = y[RHO10_POP_D3];
-    c10r = y[IN10_COH_OFFSET_D3 + COH10_RE_D3]; c10i = y[IN10_COH_OFFSET_D3 + COH10_IM_D3];
-    if (states) {
+      RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d3::N; ++i) states[SL::COH01 + i] = xc[i];
       RYDCZ_UNROLL for (int i = 0; i < Sys_rho10_d3::N; ++i) states[SL::RHO10 + i] = y[i];
-      RYDCZ_UNROLL for (int i = 0; i < Sys_coh10_d3::N; ++i) states[SL::COH10 + i] = y[IN10_COH_OFFSET_D3 + i];
+      RYDCZ_UNROLL for (int i = 0; i < Sys_coh10_d3::N; ++i) states[SL::COH10 + i] = yc[i];
     }
   } else {
-    double x[Sys_coh01_d3::N]; st = 0.0;
-    run_system<Sys_coh01_d3>(x, pt, seg, n_seg, false, st); RYDCZ_RECONVERGE(pt.live);
-    steps += st; flops += st * 2.0 * (Sys_coh01_d3::NNZ + Sys_coh01_d3::N);
+    double x[Sys_coh01_d3::N];
+    single_atom_coherence<Sys_coh01_d3, false>(x, pt, seg, n_seg, true, steps, flops);
     c01r = x[COH01_RE_D3]; c01i = x[COH01_IM_D3];
     if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d3::N; ++i) states[SL::COH01 + i] = x[i]; }
-    double y[Sys_coh10_d3::N]; st = 0.0;
-    run_system<Sys_coh10_d3>(y, pt, seg, n_seg, false, st); RYDCZ_RECONVERGE(pt.live);
-    steps += st; flops += st * 2.0 * (Sys_coh10_d3::NNZ + Sys_coh10_d3::N);
+    double y[Sys_coh10_d3::N];
+    single_atom_coherence<Sys_coh10_d3, false>(y, pt, seg, n_seg, false, steps, flops);
     c10r = y[COH10_RE_D3]; c10i = y[COH10_IM_D3];
     if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh10_d3::N; ++i) states[SL::COH10 + i] = y[i]; }
   }

@@ -585,6 +585,48 @@ RYDCZ_HD void run_system_huge(const XV x, const XV b1, const XV b2, const PointV
   }
 }
 
+// ---- closed forms for the |ab><00| coherences of the 3-level model (rydcz_closed.cuh) --------------------------
+#ifndef RYDCZ_CLOSED_COHERENCE
+#define RYDCZ_CLOSED_COHERENCE 1     // 0: every system on the Chebyshev loops (A/B builds, round-1 behaviour)
+#endif
+#include "rydcz_closed.cuh"
+
+// The exchange-folded |11><00| coherence in closed form, where there is one: false = not available for this model
+// or a non-finite value appeared -- the caller runs the system's Chebyshev loop instead.
+template <int D> struct ClosedCoh11s {
+  static constexpr bool available = false;
+  template <bool NOISY, int N>
+  RYDCZ_HD static bool run(double (&)[N], const PointView, const double* __restrict__, int, double&) { return false; }
+};
+template <> struct ClosedCoh11s<3> {
+  static constexpr bool available = RYDCZ_CLOSED_COHERENCE != 0;
+  template <bool NOISY>
+  RYDCZ_HD static bool run(double (&x)[Sys_coh11s_d3::N], const PointView pt, const double* __restrict__ seg, int n_seg,
+                           double& flops) {
+    return available && coh11s_closed_d3<NOISY>(x, pt, seg, n_seg, flops);
+  }
+};
+
+// A single-atom coherence |01><00| (atom_b) or |10><00|: closed form for the 3-level model, else (or when that
+// fails) the Chebyshev loop of the system.  Every live lane of the warp reaches the reconvergence point.
+template <class SysCoh, bool NOISY>
+RYDCZ_HD void single_atom_coherence(double (&y)[SysCoh::N], const PointView pt, const double* __restrict__ seg,
+                                    int n_seg, bool atom_b, double& steps, double& flops) {
+  bool done = false;
+  if constexpr (SysCoh::DIM == 3 && RYDCZ_CLOSED_COHERENCE != 0) {
+    double cf = 0.0;
+    done = coh01_closed_d3<NOISY>(y, pt, seg, n_seg, atom_b, cf);
+    if (done) flops += cf;
+  }
+  if (!done) {
+    double st = 0.0;
+    run_system<SysCoh>(y, pt, seg, n_seg, NOISY, st);
+    steps += st; flops += st * 2.0 * (SysCoh::NNZ + SysCoh::N);
+  }
+  RYDCZ_RECONVERGE(pt.live);
+}
+
+
 RYDCZ_HD double wrap_pi(double x) {
   // Python: (x + pi) % (2 pi) - pi, with % taking the sign of the divisor  (RG/simulation.py:608)
   const double twopi = 6.283185307179586476925286766559;
@@ -651,7 +693,29 @@ RYDCZ_HD void cz_epilogue(bool noisy, double p01, double p10, double p11,
       if (!NOISY) ryd = 1.0 - (c11r * c11r + c11i * c11i);                                          \
       if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh11_d##D::N; ++i) states[SL::COH11 + i] = x[i]; } \
     }                                                                                               \
-    if (NOISY) {                                                                                    \
+    if (NOISY && ClosedCoh11s<D>::available) {                                                      \
+      /* single-atom inputs: rho_ab on its Chebyshev loop, its |ab><00| coherence in closed form */   \
+      double x[Sys_rho01_d##D::N]; st = 0.0;                                                        \
+      run_system<Sys_rho01_d##D>(x, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);           \
+      steps += st; flops += st * 2.0 * (Sys_rho01_d##D::NNZ + Sys_rho01_d##D::N);                   \
+      p01 = x[RHO01_POP_D##D];                                                                      \
+      double xc[Sys_coh01_d##D::N];                                                                 \
+      single_atom_coherence<Sys_coh01_d##D, true>(xc, pt, seg, n_seg, true, steps, flops);          \
+      c01r = xc[COH01_RE_D##D]; c01i = xc[COH01_IM_D##D];                                           \
+      double y[Sys_rho10_d##D::N]; st = 0.0;                                                        \
+      run_system<Sys_rho10_d##D>(y, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);           \
+      steps += st; flops += st * 2.0 * (Sys_rho10_d##D::NNZ + Sys_rho10_d##D::N);                   \
+      p10 = y[RHO10_POP_D##D];                                                                      \
+      double yc[Sys_coh10_d##D::N];                                                                 \
+      single_atom_coherence<Sys_coh10_d##D, true>(yc, pt, seg, n_seg, false, steps, flops);         \
+      c10r = yc[COH10_RE_D##D]; c10i = yc[COH10_IM_D##D];                                           \
+      if (states) {                                                                                 \
+        RYDCZ_UNROLL for (int i = 0; i < Sys_rho01_d##D::N; ++i) states[SL::RHO01 + i] = x[i];      \
+        RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d##D::N; ++i) states[SL::COH01 + i] = xc[i];     \
+        RYDCZ_UNROLL for (int i = 0; i < Sys_rho10_d##D::N; ++i) states[SL::RHO10 + i] = y[i];      \
+        RYDCZ_UNROLL for (int i = 0; i < Sys_coh10_d##D::N; ++i) states[SL::COH10 + i] = yc[i];     \
+      }                                                                                             \
+    } else if (NOISY) {                                                                             \
       /* single-atom inputs: rho_ab and its |ab><00| coherence share one Chebyshev loop */           \
       double x[Sys_in01_d##D::N]; st = 0.0;                                                         \
       run_system<Sys_in01_d##D>(x, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);            \
@@ -672,14 +736,12 @@ RYDCZ_HD void cz_epilogue(bool noisy, double p01, double p10, double p11,
         RYDCZ_UNROLL for (int i = 0; i < Sys_coh10_d##D::N; ++i) states[SL::COH10 + i] = y[IN10_COH_OFFSET_D##D + i]; \
       }                                                                                             \
     } else {                                                                                        \
-      double x[Sys_coh01_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_coh01_d##D>(x, pt, seg, n_seg, false, st); RYDCZ_RECONVERGE(pt.live);          \
-      steps += st; flops += st * 2.0 * (Sys_coh01_d##D::NNZ + Sys_coh01_d##D::N);                   \
+      double x[Sys_coh01_d##D::N];                                                                  \
+      single_atom_coherence<Sys_coh01_d##D, false>(x, pt, seg, n_seg, true, steps, flops);          \
       c01r = x[COH01_RE_D##D]; c01i = x[COH01_IM_D##D];                                             \
       if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d##D::N; ++i) states[SL::COH01 + i] = x[i]; } \
-      double y[Sys_coh10_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_coh10_d##D>(y, pt, seg, n_seg, false, st); RYDCZ_RECONVERGE(pt.live);          \
-      steps += st; flops += st * 2.0 * (Sys_coh10_d##D::NNZ + Sys_coh10_d##D::N);                   \
+      double y[Sys_coh10_d##D::N];                                                                  \
+      single_atom_coherence<Sys_coh10_d##D, false>(y, pt, seg, n_seg, false, steps, flops);         \
       c10r = y[COH10_RE_D##D]; c10i = y[COH10_IM_D##D];                                             \
       if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh10_d##D::N; ++i) states[SL::COH10 + i] = y[i]; } \
     }                                                                                               \
@@ -714,9 +776,13 @@ RYDCZ_DEFINE_EVALUATE(4)
       if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_rho11s_d##D::FULL_N; ++i) states[SL::RHO11 + i] = xf[i]; } \
     }                                                                                               \
     {                                                                                               \
-      double x[Sys_coh11s_d##D::N]; st = 0.0;                                                       \
-      run_system<Sys_coh11s_d##D>(x, pt, seg, n_seg, NOISY, st); RYDCZ_RECONVERGE(pt.live);         \
-      steps += st; flops += st * 2.0 * (Sys_coh11s_d##D::NNZ + Sys_coh11s_d##D::N);                 \
+      double x[Sys_coh11s_d##D::N], cf = 0.0; st = 0.0;                                             \
+      if (ClosedCoh11s<D>::template run<NOISY>(x, pt, seg, n_seg, cf)) flops += cf;                 \
+      else {                                                                                        \
+        run_system<Sys_coh11s_d##D>(x, pt, seg, n_seg, NOISY, st);                                  \
+        steps += st; flops += st * 2.0 * (Sys_coh11s_d##D::NNZ + Sys_coh11s_d##D::N);               \
+      }                                                                                             \
+      RYDCZ_RECONVERGE(pt.live);                                                                    \
       c11r = x[COH11S_RE_D##D]; c11i = x[COH11S_IM_D##D];                                           \
       if (!NOISY) ryd = 1.0 - (c11r * c11r + c11i * c11i);                                          \
       if (states) {                                                                                 \
@@ -725,7 +791,21 @@ RYDCZ_DEFINE_EVALUATE(4)
         RYDCZ_UNROLL for (int i = 0; i < Sys_coh11s_d##D::FULL_N; ++i) states[SL::COH11 + i] = xf[i]; \
       }                                                                                             \
     }                                                                                               \
-    if (NOISY) {                                                                                    \
+    if (NOISY && ClosedCoh11s<D>::available) {                                                      \
+      double x[Sys_rho01_d##D::N]; st = 0.0;                                                        \
+      run_system<Sys_rho01_d##D>(x, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);           \
+      steps += st; flops += st * 2.0 * (Sys_rho01_d##D::NNZ + Sys_rho01_d##D::N);                   \
+      p01 = x[RHO01_POP_D##D];                                                                      \
+      double xc[Sys_coh01_d##D::N];                                                                 \
+      single_atom_coherence<Sys_coh01_d##D, true>(xc, pt, seg, n_seg, true, steps, flops);          \
+      c01r = xc[COH01_RE_D##D]; c01i = xc[COH01_IM_D##D];                                           \
+      if (states) {                                                                                 \
+        RYDCZ_UNROLL for (int i = 0; i < Sys_rho01_d##D::N; ++i) {                                  \
+          states[SL::RHO01 + i] = x[i]; states[SL::RHO10 + i] = x[i]; }                             \
+        RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d##D::N; ++i) {                                  \
+          states[SL::COH01 + i] = xc[i]; states[SL::COH10 + i] = xc[i]; }                           \
+      }                                                                                             \
+    } else if (NOISY) {                                                                             \
       double x[Sys_in01_d##D::N]; st = 0.0;                                                         \
       run_system<Sys_in01_d##D>(x, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);            \
       steps += st; flops += st * 2.0 * (Sys_in01_d##D::NNZ + Sys_in01_d##D::N);                     \
@@ -738,9 +818,8 @@ RYDCZ_DEFINE_EVALUATE(4)
           states[SL::COH01 + i] = x[IN01_COH_OFFSET_D##D + i]; states[SL::COH10 + i] = x[IN01_COH_OFFSET_D##D + i]; } \
       }                                                                                             \
     } else {                                                                                        \
-      double x[Sys_coh01_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_coh01_d##D>(x, pt, seg, n_seg, false, st); RYDCZ_RECONVERGE(pt.live);          \
-      steps += st; flops += st * 2.0 * (Sys_coh01_d##D::NNZ + Sys_coh01_d##D::N);                   \
+      double x[Sys_coh01_d##D::N];                                                                  \
+      single_atom_coherence<Sys_coh01_d##D, false>(x, pt, seg, n_seg, true, steps, flops);          \
       c01r = x[COH01_RE_D##D]; c01i = x[COH01_IM_D##D];                                             \
       if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh01_d##D::N; ++i) {                      \
         states[SL::COH01 + i] = x[i]; states[SL::COH10 + i] = x[i]; } }                             \

@@ -127,7 +127,9 @@ extern "C" int hostsim_evaluate(int dim, int noisy, long long n_points, const do
     double* o = out + i * OUT_STRIDE;
     // same dispatch rule as the CUDA kernels: identical atoms take the exchange-folded path
     const bool sym = g_allow_sym && pt[PT_OFF_A] == pt[PT_OFF_B];
-    if (g_cluster && sym && dim == 3) {
+    // (noiseless, identical atoms, 3-level: closed forms only -- the planner keeps such points on the plain folded path)
+    const bool closed_all = dim == 3 && RYDCZ_CLOSED_COHERENCE != 0 && sym && !noisy;
+    if (g_cluster && sym && dim == 3 && !closed_all) {
       // repeated-segment path (csrc/rydcz_repeat.cuh): same rule as the CUDA planner
       int first = 0, count = 0;
       if (repeat_eligible(sg, n_seg[i], first, count)) {
@@ -148,7 +150,7 @@ extern "C" int hostsim_evaluate(int dim, int noisy, long long n_points, const do
       double* st = states ? states + i * StateLayout<3>::STRIDE : nullptr;
       if (try_cluster_general(pt, row, sg, n_seg[i], noisy != 0, o, st)) continue;
     }
-    if (g_cluster && sym && (dim == 3 || dim == 4)) {
+    if (g_cluster && sym && (dim == 3 || dim == 4) && !closed_all) {
       double* st = states ? states + i * (dim == 3 ? StateLayout<3>::STRIDE : StateLayout<4>::STRIDE) : nullptr;
       if (dim == 3 ? try_cluster<3>(pt, row, sg, n_seg[i], noisy != 0, o, st)
                    : try_cluster<4>(pt, row, sg, n_seg[i], noisy != 0, o, st)) continue;
@@ -197,4 +199,26 @@ extern "C" int hostsim_prologue(const double* model, long long n_points, const d
     for (int k = 0; k < stride; ++k) points[i * stride + k] = pt[k];
   }
   return 0;
+}
+
+// closed-form coherences (csrc/rydcz_closed.cuh) of one point, for tests/test_closed_coherence.py:
+// which = 0: exchange-folded |11><00| (6 doubles), 1: |01><00| (atom B driven), 2: |10><00| (4 doubles).  Returns 1 when finite.
+extern "C" int hostsim_closed_coherence(int which, int noisy, const double* point, const double* segs, int n_seg,
+                                        double* x) {
+  using namespace rydcz;
+  double row[PT_MAX_STRIDE + PT_SCRATCH];
+  for (int k = 0; k < (int)PT_STRIDE; ++k) row[k] = point[k];
+  const PointView pt{row, 1};
+  double flops = 0.0;
+  if (which == 0) {
+    double v[6];
+    const bool ok = noisy ? coh11s_closed_d3<true>(v, pt, segs, n_seg, flops) : coh11s_closed_d3<false>(v, pt, segs, n_seg, flops);
+    for (int k = 0; k < 6; ++k) x[k] = v[k];
+    return ok ? 1 : 0;
+  }
+  double v[4];
+  const bool ok = noisy ? coh01_closed_d3<true>(v, pt, segs, n_seg, which == 1, flops)
+                        : coh01_closed_d3<false>(v, pt, segs, n_seg, which == 1, flops);
+  for (int k = 0; k < 4; ++k) x[k] = v[k];
+  return ok ? 1 : 0;
 }

@@ -1,0 +1,112 @@
+"""Closed-form |ab><00| coherences of the 3-level model (csrc/rydcz_closed.cuh) against 40-digit matrix
+exponentials of the code generator's own generators (codegen/model.py), through the host build of the header."""
+import ctypes as Ct
+
+import mpmath as mp
+import numpy as np
+import pytest
+
+import _cases as C
+from noisyquantumsimulator_b200.codegen import model as M
+
+DP = Ct.POINTER(Ct.c_double)
+
+
+@pytest.fixture(scope="module")
+def hostsim():
+    return C.load_hostsim()
+
+
+def _closed(hostsim, which, noisy, pt, segs):
+    lib = hostsim.lib
+    lib.hostsim_closed_coherence.argtypes = [Ct.c_int, Ct.c_int, DP, DP, Ct.c_int, DP]
+    x = np.zeros(6 if which == 0 else 4)
+    segs = np.ascontiguousarray(segs, dtype=np.float64)
+    ok = lib.hostsim_closed_coherence(which, int(noisy), np.ascontiguousarray(pt).ctypes.data_as(DP),
+                                      segs.ctypes.data_as(DP), len(segs), x.ctypes.data_as(DP))
+    return ok, x
+
+
+def _exact(system, pt, segs, noisy, det_key):
+    """exp(h_S G_S) ... exp(h_1 G_1) x0 with 40 digits."""
+    mp.mp.dps = 40
+    x = mp.matrix(system.x0.tolist())
+    for dt, re, im, det in segs:
+        if dt == 0.0:
+            continue
+        vals = dict(om_re=re, om_im=im, det=det + pt[2], det_a=det + pt[2], det_b=det + pt[3], V=pt[0], delta1=pt[1],
+                    g_r1=pt[4] * noisy, g_r0=pt[5] * noisy, g_phi=pt[6] * noisy, g_sc=pt[7] * noisy)
+        G = system.generator([vals[k] for k in system.params])
+        x = mp.expm(mp.matrix((dt * G).tolist())) * x
+    return np.array([float(t) for t in x])
+
+
+def _random_point(rng, trial):
+    Om = 2 * np.pi * rng.uniform(1e6, 6e6)
+    V = Om * 10 ** rng.uniform(-1.5, 3)
+    det = Om * rng.uniform(-1, 1)
+    d1 = 2 * np.pi * rng.uniform(-3e5, 3e5)
+    if trial % 11 == 0:
+        Om = 0.0
+    if trial % 13 == 0:
+        det = -d1                       # d0 = d1 on the diagonal
+    if trial % 17 == 0:
+        V = det + d1                    # d2 ~ d1
+    if trial % 19 == 0:
+        d1 = 0.0
+    pt = np.zeros(12)
+    pt[[0, 1, 4, 5, 6, 7]] = [V, d1, rng.uniform(0, 5e3), rng.uniform(0, 5e3), rng.uniform(0, 1e5), rng.uniform(0, 1e3)]
+    n_seg = int(rng.integers(1, 6))
+    segs = np.zeros((n_seg, 4))
+    scale = max(Om, 2 * np.pi * 1e6)
+    for s in range(n_seg):
+        ph = rng.uniform(-np.pi, np.pi)
+        segs[s] = [rng.uniform(0.05, 8) / scale * (1 if (trial + s) % 5 else -1), Om * np.cos(ph), Om * np.sin(ph), det]
+    if trial % 4 == 0 and n_seg > 1:
+        segs[1:, 0] = segs[0, 0]        # repeated durations: the cached exponentials
+    if trial % 6 == 0 and n_seg > 2:
+        segs[1, 0] = 0.0                # an inactive row
+    return pt, segs
+
+
+@pytest.mark.parametrize("noisy", [True, False])
+def test_folded_11_coherence_against_40_digit_expm(hostsim, noisy):
+    rng = np.random.default_rng(7 + noisy)
+    system = M.symmetric_systems(3)["coh11s"]
+    worst = 0.0
+    for trial in range(120):
+        pt, segs = _random_point(rng, trial)
+        ok, x = _closed(hostsim, 0, noisy, pt, segs)
+        y = _exact(system, pt, segs, noisy, "det")
+        tol = 2e-13 + 4e-16 * np.abs(segs[:, 0] * pt[0]).sum()       # the phase h V itself carries eps |h V|
+        err = np.abs(x - y).max() / max(np.abs(y).max(), 1e-300)
+        worst = max(worst, err / tol)
+        assert ok == 1 and err < tol, (trial, err, tol)
+    assert worst < 1.0
+
+
+@pytest.mark.parametrize("which", [1, 2])
+def test_single_atom_coherence_against_40_digit_expm(hostsim, which):
+    rng = np.random.default_rng(70 + which)
+    system = M.standard_systems(3)["coh01" if which == 1 else "coh10"]
+    for trial in range(80):
+        pt, segs = _random_point(rng, trial)
+        pt[2], pt[3] = 2 * np.pi * rng.normal(0, 5e4, 2)             # per-atom detuning offsets
+        ok, x = _closed(hostsim, which, True, pt, segs)
+        y = _exact(system, pt, segs, 1.0, "det_b" if which == 1 else "det_a")
+        err = np.abs(x - y).max() / max(np.abs(y).max(), 1e-300)
+        assert ok == 1 and err < 2e-13, (trial, err)
+
+
+def test_noiseless_identical_atoms_need_no_chebyshev_step(hostsim):
+    """Every system of a noiseless identical-atom evaluation is a coherence: the fixture is reproduced with zero
+    Chebyshev steps, states included."""
+    case = next(c for c in C.load("reference_cases.json") if c["name"] == "vb_bb7_paper")
+    pts, seg, ns = C.pack_batch([case])
+    out, st = hostsim(3, False, pts, seg, ns)
+    assert out[0, C.OUT["steps"]] == 0
+    gold = C.golden_finals(case)
+    ops = C.states_to_operators(3, st[0])
+    for lab in ("01", "10", "11"):
+        assert np.abs(ops["coh" + lab][:, 0] - gold[lab]).max() < 1e-11
+    assert abs(out[0, C.OUT["avg"]] - case["result"]["avg_fidelity"]) < 1e-10

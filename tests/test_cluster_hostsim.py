@@ -217,6 +217,8 @@ def test_random_points_agree_on_both_paths(hostsim, dim, noisy):
     hostsim.cluster_stats()
     b_, sb = hostsim(dim, noisy, P, G, ns, cluster=1)
     used, back = hostsim.cluster_stats()
-    assert n // 3 < used < n and back == 0            # weak-blockade points stay on the plain path
+    # weak-blockade points stay on the plain path -- and so do noiseless identical atoms of the 3-level model, whose
+    # systems all have closed forms (rydcz_closed.cuh): there only the unequal-atom points are planned
+    assert (0 if (dim == 3 and not noisy) else n // 3) < used < n and back == 0
     assert np.abs(sa - sb).max() < 1e-11
     assert np.abs(a[:, :14] - b_[:, :14]).max() < 5e-11

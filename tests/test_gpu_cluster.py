@@ -26,11 +26,12 @@ def test_forced_cluster_path_matches_plain_path_and_golden(ev, dim, noisy):
     ev.set_cluster(2)
     b, sb = ev.evaluate_host(dim, noisy, pts, seg, ns, want_states=True)
     planned, back = ev.cluster_stats()
-    assert planned >= len(cases) // 2 and back == 0
+    closed = dim == 3 and not noisy      # every system has a closed form (rydcz_closed.cuh): nothing to plan, no Chebyshev step
+    assert (planned == 0 if closed else planned >= len(cases) // 2) and back == 0
     assert np.abs(a[:, :14] - b[:, :14]).max() < 5e-11
     assert np.abs(sa - sb).max() < 5e-11
     # fewer operator applications where the path was taken
-    assert b[:, 14].sum() < 0.7 * a[:, 14].sum()
+    assert (a[:, 14].sum() == 0 and b[:, 14].sum() == 0) if closed else b[:, 14].sum() < 0.7 * a[:, 14].sum()
     for i, c in enumerate(cases):
         gold = C.golden_finals(c)
         ops = C.states_to_operators(dim, sb[i])
