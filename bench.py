@@ -412,6 +412,7 @@ def measure_sharded(b, name, proto, n_points, kwargs, n_shots=0, reps=5):
 def run_ours(args, rank, world, local_rank):
     b = Bench(rank, world, local_rank)
     torch, dist, ev, dev = b.torch, b.dist, b.ev, b.dev
+    ev.set_table(args.table)
 
     from noisyquantumsimulator_b200 import rydberg_gates as rg
     from noisyquantumsimulator_b200.rydberg_gates import device_prologue as dpro
@@ -607,8 +608,12 @@ def run_ours(args, rank, world, local_rank):
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "jp_bangbang_5seg_lindblad_3level", "candidates_per_gpu": B_PER_GPU,
-                       "propagation": ("clustered-spectrum Chebyshev (csrc/rydcz_cluster.cuh)" if clustered
-                                       else "single-interval Chebyshev"),
+                       "propagation": ("rho_11: clustered-spectrum Chebyshev (csrc/rydcz_cluster.cuh); single-atom rho: "
+                                       "single-interval Chebyshev; |ab><00| coherences: closed form (csrc/rydcz_closed.cuh)"
+                                       if clustered else "single-interval Chebyshev; coherences in closed form"),
+                       "coefficient_table": {0: "off", 1: "entries generated again in every step",
+                                             2: "entries kept across steps (library default): generated during warm-up, "
+                                                "as an optimiser's generations find them"}[args.table],
                        "segments": N_SEG, "apparatus": "medium (RG/optimize_cz_gate.py:196-213), full noise",
                        "l2": f"{N_ROT} distinct input batches of {40 * 8 * B_PER_GPU / 1e6:.0f} MB used in turn "
                              "(inputs larger than the 126 MB L2; no flush kernel inside the step)",
@@ -632,8 +637,9 @@ def run_ours(args, rank, world, local_rank):
                          # capture of this command (profiles/ncu_traffic.json), scaled to this batch size
                          "traffic": traffic, "traffic_kernel": traffic_kernel, "traffic_source": traffic_src,
                          "algorithmic_bytes": alg_bytes, "coefficient_record_bytes": record_bytes,
-                         # shared coefficient table (rydcz_set_table mode 1: entries generated again in EVERY step):
-                         # slots of the step's candidates that read the table / entries generated for them
+                         # shared coefficient table (rydcz_set_table; default 2 = entries kept across calls, as an
+                         # optimiser's generations find them; --table 1 regenerates them in EVERY step): slots of the
+                         # step's candidates that read the table / entries generated for them inside the timed steps
                          "table_slots_per_step": tb_slots / max(args.steps, 1),
                          "table_entries_generated_per_step": tb_entries / max(args.steps, 1),
                          "kernel": ("rydcz::evaluate_cluster_kernel<3,true,true>" if clustered
@@ -672,6 +678,9 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed batch")
     ap.add_argument("--parity-samples", type=int, default=64)
     ap.add_argument("--candidates", type=int, default=B_PER_GPU, help="bang-bang candidates per GPU per step")
+    ap.add_argument("--table", type=int, default=2, choices=[0, 1, 2],
+                    help="shared coefficient table (rydcz_set_table): 2 = entries kept across steps (library default), "
+                         "1 = generated again in every step, 0 = off")
     args = ap.parse_args()
     B_PER_GPU = args.candidates
     rank = int(os.environ.get("RANK", "0"))

@@ -120,8 +120,8 @@ int rydcz_set_cluster(rydcz_ctx* ctx, int mode);
  * share the blockade and the drive (every candidate of an optimiser population, every chunk of a sweep at fixed
  * apparatus) share a few thousand table entries instead of generating 1-8 sets of records per point.
  * 0 = off (every slot generates its own records, round-1 behaviour), 1 = table entries generated once per
- * evaluation call (default; nothing is carried from one call to the next), 2 = entries kept across calls
- * (an optimiser's generations re-use them).  Device memory: 1.2 GB, allocated at the first clustered call; if
+ * evaluation call (nothing is carried from one call to the next), 2 = entries kept across calls (default: an
+ * entry is a pure function of its index; an optimiser's generations and a sweep's calls re-use them).  Device memory: 1.2 GB, allocated at the first clustered call; if
  * that fails the context silently behaves like mode 0 (results identical to rounding in every mode). */
 int rydcz_set_table(rydcz_ctx* ctx, int mode);
 /* table entries generated / slots of clustered points that took their records from the table, since the last

@@ -119,7 +119,13 @@ __device__ __forceinline__ unsigned work_bin(double w) {
 // Block-level counting: every CTA counts its keys in shared memory and touches the global counters once per
 // non-empty bin (262,144 points x 6 keys straight onto ~100 global addresses serialise in the L2 atomic units:
 // measured 0.2 ms per pass; per-CTA shared-memory histograms bring that to ~1/30 of the global atomics).
-constexpr int kPlanBlock = 256;
+#ifndef RYDCZ_PLAN_BLOCK
+#define RYDCZ_PLAN_BLOCK 256
+#endif
+#ifndef RYDCZ_PLAN_MIN_CTAS
+#define RYDCZ_PLAN_MIN_CTAS 1
+#endif
+constexpr int kPlanBlock = RYDCZ_PLAN_BLOCK;
 constexpr int kPlanStageSegs = 8;      // schedules up to this many rows are staged in shared memory by plan_kernel
 struct PlanShared {
   unsigned pts[kBins];        // points per bin in this CTA; later: running rank inside the CTA's range
@@ -127,10 +133,19 @@ struct PlanShared {
   unsigned tsk[kTaskBins];
   unsigned tbase[kTaskBins];
 };
+struct PlanSharedCounts {     // plan_kernel only counts: half the shared memory, one more resident CTA
+  unsigned pts[kBins];
+  unsigned tsk[kTaskBins];
+};
 static_assert(sizeof(ClusterTableDir) % sizeof(int) == 0, "directory is copied word by word");
 __device__ __forceinline__ void plan_shared_clear(PlanShared& sh, bool with_base) {
   for (int b = threadIdx.x; b < kBins; b += kPlanBlock) { sh.pts[b] = 0u; if (with_base) sh.pbase[b] = 0u; }
   if (threadIdx.x < kTaskBins) { sh.tsk[threadIdx.x] = 0u; sh.tbase[threadIdx.x] = 0u; }
+  __syncthreads();
+}
+__device__ __forceinline__ void plan_shared_clear(PlanSharedCounts& sh, bool) {
+  for (int b = threadIdx.x; b < kBins; b += kPlanBlock) sh.pts[b] = 0u;
+  if (threadIdx.x < kTaskBins) sh.tsk[threadIdx.x] = 0u;
   __syncthreads();
 }
 
@@ -138,7 +153,8 @@ __device__ __forceinline__ void plan_shared_clear(PlanShared& sh, bool with_base
 // points of one kind and similar cost.  cluster_mode: 0 = plain path only, 1 = clustered path where the
 // planner finds it cheaper, 2 = wherever it is eligible.
 template <int D>
-__global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
+__global__ void __launch_bounds__(kPlanBlock, RYDCZ_PLAN_MIN_CTAS)
+plan_kernel(int64_t n_points, const double* __restrict__ points,
                             const double* __restrict__ segs, const int32_t* __restrict__ n_seg,
                             int max_seg, int seg_div, int seg_staged, int shots, int noisy, int cluster_mode,
                             uint32_t* __restrict__ keys,
@@ -148,7 +164,7 @@ __global__ void plan_kernel(int64_t n_points, const double* __restrict__ points,
                             double* __restrict__ scratch, const ClusterTable table,
                             unsigned long long* __restrict__ counters,
                             unsigned* __restrict__ repeat_count, PlanCounts* __restrict__ plan) {
-  __shared__ PlanShared sh;
+  __shared__ PlanSharedCounts sh;
   // the table's directory (2.3 KB) in shared memory: the lookup reads five of its arrays per slot
   __shared__ ClusterTableDir s_dir;
   struct SharedTable {                     // ClusterTable's interface over the shared-memory copy
@@ -1013,7 +1029,8 @@ struct rydcz_ctx {
   unsigned long long* cl_counters = nullptr;            // [0] clustered points, [1] handed back, [2] records, [3] repeated-segment points,
                                                         // [4] unsupported points (NaN rows), [5] spare
   // shared coefficient table (rydcz_cluster.cuh): 0 = off, 1 = entries generated once per call, 2 = kept across calls
-  int table_mode = 1;
+  // (default: an entry is a pure function of its index, so there is nothing to invalidate)
+  int table_mode = 2;
   ClusterTableDir* tb_dir = nullptr;                    // device copy of the directory
   unsigned* tb_stamp = nullptr;                         // per entry: epoch of the last call that requested it
   unsigned* tb_mark = nullptr;                          // per entry: generation its records belong to

@@ -73,7 +73,24 @@ RYDCZ_HD double repeat_build_column(int c, const PointView pt, const double* __r
   RYDCZ_UNROLL
   for (int i = 0; i < N; ++i) x[i] = i == c ? 1.0 : 0.0;
   double st = 0.0;
-  run_system<Sys>(x, pt, row, 1, noisy, st, false);
+  // the coherence systems have a closed form (rydcz_closed.cuh): their columns cost one segment formula, not a
+  // Chebyshev propagation -- 10 of the 30 columns of the noisy 3-level evaluation
+  bool done = false;
+  if constexpr (RYDCZ_CLOSED_COHERENCE != 0 && Sys::DIM == 3 && !Sys::HERMITIAN && (N == 6 || N == 4)) {
+    const double G = noisy ? pt[PT_G_R1] + pt[PT_G_R0] + pt[PT_G_PHI] : 0.0, g_sc = noisy ? pt[PT_G_SC] : 0.0;
+    const double det = row[SG_DET] + pt[PT_OFF_A];        // (identical atoms on this path: OFF_A = OFF_B)
+    if constexpr (N == 6) {
+      Closed3Cache cache;
+      cache.om2 = -1.0; cache.det = 0.0; cache.h = 0.0;
+      done = coh11s_closed_segment_d3(x, cache, row[SG_DT], row[SG_RE], 0.0, det, pt[PT_V], pt[PT_DELTA1], G, g_sc);
+    } else {
+      Closed2Cache cache;
+      cache.om2 = -1.0; cache.det = 0.0; cache.h = 0.0;
+      done = coh01_closed_segment_d3(x, cache, row[SG_DT], row[SG_RE], 0.0, det, pt[PT_DELTA1], G, g_sc);
+    }
+    if (!done) { RYDCZ_UNROLL for (int i = 0; i < N; ++i) x[i] = i == c ? 1.0 : 0.0; }
+  }
+  if (!done) run_system<Sys>(x, pt, row, 1, noisy, st, false);
   RYDCZ_UNROLL
   for (int r = 0; r < N; ++r) E[(long long)(r * N + c) * stride] = x[r];
   return st;
