@@ -82,7 +82,7 @@ enum rydcz_status {
   RYDCZ_STATUS_CLUSTER_GENERAL = 2,  /* clustered-spectrum expansion, unequal atoms / Monte-Carlo shot   */
   RYDCZ_STATUS_CLUSTER = 3,          /* clustered-spectrum expansion, identical atoms                    */
   RYDCZ_STATUS_REPEAT = 5,           /* one propagator for a phase-modulated pulse (smooth JP)           */
-  RYDCZ_STATUS_UNSUPPORTED = 6,      /* not evaluated: the row is NaN (dim 5 with OFF_A != OFF_B)        */
+  RYDCZ_STATUS_UNSUPPORTED = 6,      /* not evaluated: the row is NaN (no case left since round 2)       */
   RYDCZ_STATUS_HANDED_BACK = 0x10    /* flag: the clustered path's invariant check failed and the plain
                                         kernel re-evaluated the point inside the same call             */
 };

@@ -91,9 +91,10 @@ def test_repeated_segment_path_for_smooth_jp(ev):
         ev.repeat_stats()
         ev.set_cluster(1)
         b, sb = ev.evaluate_host(3, noisy, P, S, N, want_states=True)
-        assert ev.repeat_stats() == len(P)
+        # (noiseless identical atoms: closed forms only, rydcz_closed.cuh -- no planned path, no Chebyshev step)
+        assert ev.repeat_stats() == (len(P) if noisy else 0)
         assert np.abs(a[:, :14] - b[:, :14]).max() < 5e-11 and np.abs(sa - sb).max() < 5e-11
-        assert b[:, 14].sum() < 0.2 * a[:, 14].sum()
+        assert b[:, 14].sum() < 0.2 * a[:, 14].sum() if noisy else (a[:, 14].sum() == 0 and b[:, 14].sum() == 0)
         b1, sb1 = ev.evaluate_host(3, noisy, pts, seg, ns, want_states=True)     # unsorted small batch
         assert np.array_equal(b1[:, :14], b[:len(cases), :14])
         for i, c in enumerate(cases):

@@ -121,8 +121,12 @@ def test_mixed_kinds_in_one_sorted_batch(evaluator):
         evaluator.repeat_stats()
         out, st = evaluator.evaluate_host(3, noisy, P, G, ns, want_states=True)
         status = evaluator.point_status(len(items)) & 0x0f
-        assert evaluator.repeat_stats() == 24
-        assert (status[1::4] == 5).all() and (status[0::4] == 2).all() and (status[2::4] == 3).all()
+        if noisy:
+            assert evaluator.repeat_stats() == 24
+            assert (status[1::4] == 5).all() and (status[0::4] == 2).all() and (status[2::4] == 3).all()
+        else:      # identical atoms without noise are closed forms on the plain folded path (status 1)
+            assert evaluator.repeat_stats() == 0
+            assert (status[1::4] == 1).all() and (status[0::4] == 2).all() and (status[2::4] == 1).all()
         assert np.isfinite(out).all()
         evaluator.set_cluster(0)
         out0, st0 = evaluator.evaluate_host(3, noisy, P, G, ns, want_states=True)
@@ -133,25 +137,26 @@ def test_mixed_kinds_in_one_sorted_batch(evaluator):
                                                     evaluator.evaluate_host(3, True, P, G, ns, want_states=True)])
 
 
-def test_status_flags_and_five_level_refusal(evaluator):
-    from noisyquantumsimulator_b200.engine import RydczError
+def test_status_flags_and_five_level_general_rows(evaluator):
+    """dim 5, a row with unequal atoms among identical ones: round 1 returned a NaN row and flagged the call; now the
+    general systems evaluate it (status: plain), on the host and on the device entry alike, and no flag is raised."""
     import torch
     cases = [c for c in C.load("five_level_cases.json")][:3]
     P, G, ns = C.pack_batch5(cases)
     out, _ = evaluator.evaluate_host(5, True, P, G, ns)
     assert np.isfinite(out).all() and evaluator.call_flags() == (0, 0)
-    bad = P.copy()
-    bad[1, 3] = bad[1, 2] + 1.0e3                      # OFF_B != OFF_A: the general 5-level system is not built
-    with pytest.raises(RydczError, match="different detunings"):
-        evaluator.evaluate_host(5, True, bad, G, ns)
+    odd = P.copy()
+    odd[1, 3] = odd[1, 2] + 1.0e3                      # OFF_B != OFF_A
+    oh, _ = evaluator.evaluate_host(5, True, odd, G, ns)
     dev = torch.device("cuda:0")
-    o, _ = evaluator.evaluate_device(5, True, torch.from_numpy(bad).to(dev), torch.from_numpy(G).to(dev),
+    o, _ = evaluator.evaluate_device(5, True, torch.from_numpy(odd).to(dev), torch.from_numpy(G).to(dev),
                                      torch.from_numpy(ns).to(dev))
     o = o.cpu().numpy()
-    assert np.isnan(o[1]).all() and np.isfinite(o[[0, 2]]).all()
-    flags, n_bad = evaluator.call_flags()
-    assert flags & 2 and n_bad == 1
-    assert list(evaluator.point_status(3)) == [1, 6, 1]
+    assert np.isfinite(o).all() and np.array_equal(o[:, :14], oh[:, :14])
+    assert np.array_equal(o[[0, 2], :14], out[[0, 2], :14])
+    assert 1e-12 < np.abs(o[1, :14] - out[1, :14]).max() < 1e-3       # 1 kHz of differential detuning: a small change
+    assert evaluator.call_flags() == (0, 0)
+    assert list(evaluator.point_status(3)) == [1, 0, 1]
 
 
 def test_selected_columns_equal_full_rows_on_device(evaluator):
@@ -291,7 +296,8 @@ def test_paths_agree_on_random_batches(evaluator):
         evaluator.set_cluster(0)
         out0, st0 = evaluator.evaluate_host(dim, noisy, P, G, ns, want_states=True)
         evaluator.set_cluster(1)
-        assert planned > n // 4 and back == 0
+        # (3-level, noiseless: identical atoms are closed forms on the plain folded path; only unequal atoms are planned)
+        assert planned > (n // 8 if (dim == 3 and not noisy) else n // 4) and back == 0
         worst = max(worst, np.abs(out[:, :14] - out0[:, :14]).max(), np.abs(st - st0).max())
     assert worst < 5e-11
 
@@ -312,7 +318,8 @@ def test_shaped_lp_pulses_on_the_device_prologue(evaluator):
             status = get_evaluator(0).point_status(B) & 0x0f     # (the context simulate_CZ_gate_batch runs on)
             b = rg.simulate_CZ_gate_batch("lp", B=B, pulse_shape=shape, prologue="host", include_noise=noise, **base)
             assert np.abs(a.raw[:, :14] - b.raw[:, :14]).max() < 1e-9, (shape, noise)
-            assert (status == want).all(), (shape, noise, np.unique(status))
+            # (without noise every system of identical atoms has a closed form: plain folded path, no planning)
+            assert (status == (want if noise else 1)).all(), (shape, noise, np.unique(status))
     # the fixtures generated by the reference's own evolve_shaped_pulse
     for name in ("lp_shaped_gaussian", "lp_shaped_cosine", "lp_shaped_blackman", "lp_shaped_cosine_noisy"):
         case = REF[name]

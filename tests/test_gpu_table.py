@@ -19,7 +19,8 @@ def ev(evaluator):
     evaluator.set_table(1)
 
 
-@pytest.mark.parametrize("dim,noisy", [(3, True), (3, False), (4, True)])
+# (3-level noiseless identical atoms are closed forms, rydcz_closed.cuh: no clustered slots; the 4-level model covers that branch)
+@pytest.mark.parametrize("dim,noisy", [(3, True), (4, False), (4, True)])
 def test_population_shares_table_entries(ev, dim, noisy):
     n = 20000
     P, G, ns = _population(n, 7)
@@ -67,7 +68,10 @@ def test_fixtures_on_the_table(ev):
             ev.table_stats()
             out, st = ev.evaluate_host(dim, noisy, pts, seg, ns, want_states=True)
             gen, shared = ev.table_stats()
-            assert gen > 0 and shared >= gen
+            if dim == 3 and not noisy:          # closed forms only: nothing is planned
+                assert gen == 0 and shared == 0
+            else:
+                assert gen > 0 and shared >= gen
             for i, c in enumerate(cases):
                 gold = C.golden_finals(c)
                 ops = C.states_to_operators(dim, st[i])
