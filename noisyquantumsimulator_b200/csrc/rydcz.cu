@@ -156,7 +156,7 @@ template <int D>
 __global__ void __launch_bounds__(kPlanBlock, RYDCZ_PLAN_MIN_CTAS)
 plan_kernel(int64_t n_points, const double* __restrict__ points,
                             const double* __restrict__ segs, const int32_t* __restrict__ n_seg,
-                            int max_seg, int seg_div, int seg_staged, int shots, int noisy, int cluster_mode,
+                            int max_seg, int seg_div, int seg_staged, int shots, int noisy, int cluster_mode, int uniform,
                             uint32_t* __restrict__ keys,
                             uint32_t* __restrict__ idx, uint8_t* __restrict__ kind,
                             uint32_t* __restrict__ task_key, uint32_t* __restrict__ task_val,
@@ -218,7 +218,12 @@ plan_kernel(int64_t n_points, const double* __restrict__ points,
     const bool closed_all = D == 3 && RYDCZ_CLOSED_COHERENCE != 0 && sym && !noisy;
     if (D == 3 && repeat_count && sym && !shots && !closed_all) {
       int first, count;
-      if (repeat_eligible(sg, ns, first, count)) {
+      // uniform: the device prologue wrote the schedule and every row shares (duration, |Omega|, Delta) by construction
+      // (smooth JP; shaped LP of constant amplitude) -- row 0 decides, the 300 / 998 rows are not walked
+      const bool eligible = uniform ? (ns >= RP_MIN_COUNT && segment_active(sg[SG_DT]) && (sg[SG_RE] != 0.0 || sg[SG_IM] != 0.0))
+                                    : repeat_eligible(sg, ns, first, count);
+      if (uniform) { first = 0; count = ns; }
+      if (eligible) {
         // one propagator for all segments (rydcz_repeat.cuh): 30 column builds + count dense steps
         repeated = true; group = GROUP_REPEAT; w = 40.0 * 30.0 + 4.0 * (double)count;
       }
@@ -808,13 +813,15 @@ evaluate5_general_kernel(int64_t n_items, const uint32_t* __restrict__ order, co
 struct ModelArg { double v[MD_STRIDE]; };
 __global__ void prologue_kernel(ModelArg md, int64_t n_points, const double* __restrict__ app,
                                 int64_t app_stride, double* __restrict__ points, double* __restrict__ segs,
-                                int32_t* __restrict__ n_seg, double* __restrict__ scalars) {
+                                int32_t* __restrict__ n_seg, double* __restrict__ scalars, double* __restrict__ wave) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_points) return;
   const int S = (int)md.v[MD_NSEG];
   const int stride = (int)md.v[MD_DIM] == 5 ? (int)PT5_STRIDE : (int)PT_STRIDE;
   double pt[PT5_STRIDE], sc[SC_STRIDE];
-  const int ns = prologue_point(md.v, AppView{app + i, app_stride}, pt, segs + i * (int64_t)S * SG_STRIDE, sc);
+  // wave: [WAVE_STRIDE][n_points]; given, long schedules are left to schedule_fill_kernel
+  const int ns = prologue_point(md.v, AppView{app + i, app_stride}, pt, segs + i * (int64_t)S * SG_STRIDE, sc,
+                                wave ? wave + i : nullptr, n_points);
 #pragma unroll
   for (int k = 0; k < PT5_STRIDE; ++k)
     if (k < stride) points[i * stride + k] = pt[k];
@@ -823,6 +830,19 @@ __global__ void prologue_kernel(ModelArg md, int64_t n_points, const double* __r
 #pragma unroll
     for (int k = 0; k < SC_STRIDE; ++k) scalars[i * SC_STRIDE + k] = sc[k];
   }
+}
+
+// the rows of the long schedules prologue_kernel left out: one thread per (point, row)
+__global__ void schedule_fill_kernel(int64_t n_points, int S, const double* __restrict__ wave, double* __restrict__ segs) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_points * S) return;
+  const int64_t i = t / S;
+  const int s = (int)(t - i * S);
+  const double* w = wave + i;
+  if (w[WV_KIND * n_points] == 0.0 || (double)s >= w[WV_ROWS * n_points]) return;
+  double row[SG_STRIDE];
+  schedule_row(w, n_points, s, row);
+  *reinterpret_cast<double4*>(segs + t * SG_STRIDE) = make_double4(row[0], row[1], row[2], row[3]);
 }
 
 // apparatus slots that are the same for every point of a batch are not sent over PCIe: the host
@@ -1042,6 +1062,9 @@ struct rydcz_ctx {
   bool cl_smem_gen_set = false;
   bool rp_smem_set = false;
   double* shot_rows = nullptr; size_t shot_rows_cap = 0;   // one perturbed point row per (point, shot)
+  void* wave = nullptr; size_t wave_cap = 0;               // long schedules: WAVE_STRIDE doubles per point (rydcz_prologue.cuh)
+  bool schedule_uniform = false;                           // set by the simulate entry points: every row of every schedule of the
+                                                           // call shares (duration, |Omega|, Delta) -- the planner need not walk them
   void* sel_out = nullptr; size_t sel_out_cap = 0;         // column-major staging of the selected result columns
   void* sel_sc = nullptr; size_t sel_sc_cap = 0;           // ... and of the selected scalar columns
   double* rp_E = nullptr; size_t rp_cap = 0;            // repeated-segment path: propagators, [entry][position]
@@ -1278,7 +1301,7 @@ static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const do
     ctx->plan_smem_set[D == 3 ? 0 : (D == 4 ? 1 : 2)] = true;
   }
   plan_kernel<D><<<(unsigned)((n + kPlanBlock - 1) / kPlanBlock), kPlanBlock, plan_smem, st>>>(n, d_points, d_segs, d_n_seg, max_seg, seg_div, seg_staged, shots, noisy,
-                                                              mode, sc.keys, sc.idx, sc.kind, tk, tv, th, sc.cl, table,
+                                                              mode, ctx->schedule_uniform ? 1 : 0, sc.keys, sc.idx, sc.kind, tk, tv, th, sc.cl, table,
                                                               ctx->cl_counters, rpc, sc.plan);
   CK(cudaGetLastError());
   ctx->launches++;
@@ -1451,7 +1474,7 @@ void rydcz_destroy(rydcz_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->keys); cudaFree(ctx->keys_sorted); cudaFree(ctx->idx); cudaFree(ctx->idx_sorted);
   cudaFree(ctx->kind); cudaFree(ctx->cl_scratch); cudaFree(ctx->cl_counters); cudaFree(ctx->task); cudaFree(ctx->task_hdr);
-  cudaFree(ctx->rp_E); cudaFree(ctx->rp_count); cudaFree(ctx->shot_rows); cudaFree(ctx->sel_out); cudaFree(ctx->sel_sc);
+  cudaFree(ctx->rp_E); cudaFree(ctx->rp_count); cudaFree(ctx->shot_rows); cudaFree(ctx->sel_out); cudaFree(ctx->sel_sc); cudaFree(ctx->wave);
   if (ctx->busy) cudaEventDestroy(ctx->busy);
   if (ctx->evc0) cudaEventDestroy(ctx->evc0);
   if (ctx->evc1) cudaEventDestroy(ctx->evc1);
@@ -1889,15 +1912,33 @@ static int check_model(rydcz_ctx* ctx, const double* m) {
   return 0;
 }
 
+// Does the device prologue write schedules whose rows all share (duration, |Omega|, Delta)?  Smooth JP: yes (300 equal
+// steps, phase-modulated); shaped LP: the shapes that degenerate to a constant amplitude (everything but the cosine
+// envelope, rydcz_prologue.cuh) -- both pulses have the same step and |xi| = 1.
+static bool model_schedule_uniform(const double* h_model) {
+  const int proto = (int)h_model[MD_PROTOCOL], S = (int)h_model[MD_NSEG];
+  if (proto == 2) return true;
+  return proto == 0 && S > 2 && (int)h_model[MD_LEAK_SHAPE] != 2;
+}
+
 static int prologue_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_points, const double* d_app,
                          int64_t app_stride, double* d_points, double* d_segs, int32_t* d_n_seg,
-                         double* d_scalars, cudaStream_t st) {
+                         double* d_scalars, cudaStream_t st, double* d_wave) {
   ModelArg md;
   memcpy(md.v, h_model, sizeof(md.v));
+  // long schedules (smooth JP, shaped LP): rows written by one thread each, from the per-point numbers in `d_wave`
+  const int proto = (int)h_model[MD_PROTOCOL], S = (int)h_model[MD_NSEG];
+  if (!((proto == 2 || (proto == 0 && S > 2)) && S >= 32)) d_wave = nullptr;
   prologue_kernel<<<(unsigned)((n_points + 127) / 128), 128, 0, st>>>(md, n_points, d_app, app_stride, d_points,
-                                                                       d_segs, d_n_seg, d_scalars);
+                                                                       d_segs, d_n_seg, d_scalars, d_wave);
   CK(cudaGetLastError());
   ctx->launches++;
+  if (d_wave) {
+    const int64_t rows = n_points * S;
+    schedule_fill_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(n_points, S, d_wave, d_segs);
+    CK(cudaGetLastError());
+    ctx->launches++;
+  }
   return 0;
 }
 
@@ -1910,7 +1951,9 @@ int rydcz_prologue_device(rydcz_ctx* ctx, const double* h_model, int64_t n_point
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
   if (enter_call(ctx, st)) return 1;      // d_points / d_segs may be the context's own plan buffers
-  if (int rc = prologue_impl(ctx, h_model, n_points, d_app, n_points, d_points, d_segs, d_n_seg, d_scalars, st)) return rc;
+  if (grow(ctx, &ctx->wave, &ctx->wave_cap, (size_t)n_points * WAVE_STRIDE * sizeof(double))) return 1;
+  if (int rc = prologue_impl(ctx, h_model, n_points, d_app, n_points, d_points, d_segs, d_n_seg, d_scalars, st,
+                             (double*)ctx->wave)) return rc;
   return leave_call(ctx, st);
 }
 
@@ -1935,9 +1978,11 @@ int rydcz_simulate_device(rydcz_ctx* ctx, const double* h_model, int64_t n_point
                                        (const double*)ctx->plan[1], (const int32_t*)ctx->plan[2], S, d_out,
                                        nullptr, stream);
   ctx->atoms_identical = true;      // rows written by prologue_kernel: OFF_A = OFF_B = 0
+  ctx->schedule_uniform = model_schedule_uniform(h_model);
   rc = rydcz_evaluate_device(ctx, dim, noisy, n_points, (const double*)ctx->plan[0], (const double*)ctx->plan[1],
                              (const int32_t*)ctx->plan[2], S, d_out, d_states, stream);
   ctx->atoms_identical = false;
+  ctx->schedule_uniform = false;
   return rc;
 }
 
@@ -2071,6 +2116,7 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
   if (grow(ctx, &ctx->plan[0], &ctx->plan_cap[0], n * pstride * sizeof(double))) return 1;
   if (grow(ctx, &ctx->plan[1], &ctx->plan_cap[1], n * S * SG_STRIDE * sizeof(double))) return 1;
   if (grow(ctx, &ctx->plan[2], &ctx->plan_cap[2], n * sizeof(int32_t))) return 1;
+  if (grow(ctx, &ctx->wave, &ctx->wave_cap, n * WAVE_STRIDE * sizeof(double))) return 1;
   ctx->call_flags = 0;
   if (order_reserve(ctx, n_points * per_item, dim != 5 && (n_shots == 0 || dim == 3))) return 1;
   if (table_new_call(ctx)) return 1;      // one generation for the whole pipelined call: its chunks share the entries
@@ -2205,8 +2251,9 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
     CK(cudaGetLastError());
     ctx->launches++;
     double* c_sc = d_sc ? d_sc + i0 * SC_STRIDE : nullptr;
+    // (the chunk's span of the wave block: [WAVE_STRIDE][nc] at i0 * WAVE_STRIDE)
     if (prologue_impl(ctx, h_model, nc, d_app + i0, n_points, d_pts + i0 * pstride,
-                      d_segs + i0 * (int64_t)S * SG_STRIDE, d_ns + i0, c_sc, st)) return 1;
+                      d_segs + i0 * (int64_t)S * SG_STRIDE, d_ns + i0, c_sc, st, (double*)ctx->wave + i0 * WAVE_STRIDE)) return 1;
     SortScratch sc = context_scratch(ctx, nc * per_item, i0 * per_item, 1 + (int)(c % rydcz_ctx::kLanes));
     const int mark = (c == 0 ? 1 : 0) | (c == n_chunks - 1 ? 2 : 0);
     int rc;
@@ -2218,10 +2265,12 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
                       st, mark);
     else {
       ctx->atoms_identical = true;      // rows written by prologue_kernel: OFF_A = OFF_B = 0
+      ctx->schedule_uniform = model_schedule_uniform(h_model);
       rc = evaluate_impl(ctx, sc, dim, noisy, nc, d_pts + i0 * pstride, d_segs + i0 * (int64_t)S * SG_STRIDE,
                          d_ns + i0, S, d_out + i0 * OUT_STRIDE, d_st ? d_st + i0 * (sb / sizeof(double)) : nullptr,
                          st, mark);
       ctx->atoms_identical = false;
+      ctx->schedule_uniform = false;
     }
     if (rc) return rc;
     if (sel_out) {

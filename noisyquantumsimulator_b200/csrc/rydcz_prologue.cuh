@@ -144,9 +144,45 @@ struct AppView {
   RYDCZ_HD double operator[](int k) const { return base[(long long)k * stride]; }
 };
 
+// Long schedules (smooth JP: 300 rows, shaped LP: 998) are written by one thread per ROW on the device: the point's
+// thread leaves the handful of numbers a row needs in `wave` and schedule_row below turns them into row s.  (One
+// thread per point writing 300 rows one after the other -- 300 dependent sincos, 9.6 KB of scattered stores -- was
+// 0.22 ms of a 0.96 ms generation of 8192 smooth-JP candidates.)  The serial path calls the same function.
+constexpr int WAVE_STRIDE = 10;
+enum WaveSlot { WV_KIND = 0 /* 0 none, 1 shaped LP, 2 smooth JP */, WV_N = 1, WV_T = 2, WV_AMP = 3, WV_DET = 4,
+                WV_A = 5, WV_B = 6, WV_C = 7, WV_ROWS = 8 };
+RYDCZ_HD void schedule_row(const double* __restrict__ wave, long long wstride, int s, double* __restrict__ row) {
+  const double PI_ = 3.14159265358979323846;
+  const int kind = (int)wave[WV_KIND * wstride];
+  const double T = wave[WV_T * wstride], amp = wave[WV_AMP * wstride], det = wave[WV_DET * wstride];
+  const double a_ = wave[WV_A * wstride], b_ = wave[WV_B * wstride], c_ = wave[WV_C * wstride];
+  if (kind == 2) {
+    // smooth JP: T = dts, amp = Omega, a_ = A, b_ = omega_mod, c_ = phi
+    const double t_mid = s * T + T / 2;
+    const double ph = a_ * cos(b_ * t_mid - c_);
+    row[0] = T; row[1] = amp * cos(ph); row[2] = amp * sin(ph); row[3] = det;
+  } else {
+    // shaped LP: T = tau_single, amp = peak, a_ + i b_ = xi, c_ = shape; rows 0 .. n-2 first pulse, then the second
+    const int n = (int)wave[WV_N * wstride];
+    const bool second = s >= n - 1;
+    const int k = second ? s - (n - 1) : s;
+    const double step = T / (double)(n - 1), dt = T / (double)n;
+    const double t0 = (double)k * step, t1 = (k + 1 == n - 1) ? T : (double)(k + 1) * step;   // np.linspace
+    const double t_mid = (t0 + t1) / 2;
+    double env = 1.0;
+    if ((int)c_ == 2) { const double sn = sin(PI_ * t_mid / T); env = sn * sn; }
+    const double a = amp * env;
+    row[0] = dt; row[1] = second ? a * a_ : a; row[2] = second ? a * b_ : 0.0; row[3] = det;
+  }
+}
+
+// `wave` (may be null): WAVE_STRIDE doubles of this point, element k at wave[k * wstride].  Given, a long schedule is
+// NOT written here: the caller runs schedule_row for rows 0 .. wave[WV_ROWS] - 1 (wave[WV_KIND] = 0: written here).
 RYDCZ_HD int prologue_point(const double* __restrict__ md, const AppView app,
-                            double* __restrict__ pt, double* __restrict__ seg, double* __restrict__ sc) {
+                            double* __restrict__ pt, double* __restrict__ seg, double* __restrict__ sc,
+                            double* __restrict__ wave = nullptr, long long wstride = 1) {
   using namespace phys;
+  if (wave) { wave[WV_KIND * wstride] = 0.0; wave[WV_ROWS * wstride] = 0.0; }
   const int protocol = (int)md[MD_PROTOCOL], dim = (int)md[MD_DIM], S = (int)md[MD_NSEG];
   const double P1 = app[APP_P1], w1 = app[APP_W1], P2 = app[APP_P2], w2 = app[APP_W2], De = app[APP_DELTA_E];
   const double lw1 = app[APP_LW1], lw2 = app[APP_LW2];
@@ -288,18 +324,15 @@ RYDCZ_HD int prologue_point(const double* __restrict__ md, const AppView app,
     // normalise by their own maximum (gaussian, blackman; RG/pulse_shaping.py:184-186, 291-293) return 1: they run
     // as square pulses of the corrected amplitude.  Only the cosine envelope sin^2(pi t / tau) really shapes.
     const int n = S / 2 + 1, shape = (int)md[MD_LEAK_SHAPE];
-    const double step = tau_single / (double)(n - 1), dt = tau_single / (double)n, peak = Om * md[MD_AREA_CORRECTION];
-    for (int k = 0; k < n - 1; ++k) {
-      const double t0 = (double)k * step, t1 = (k + 1 == n - 1) ? tau_single : (double)(k + 1) * step;   // np.linspace
-      const double t_mid = (t0 + t1) / 2;
-      double env = 1.0;
-      if (shape == 2) { const double sn = sin(PI * t_mid / tau_single); env = sn * sn; }
-      const double a = peak * env;
-      double* s1 = seg + 4 * k;
-      double* s2 = seg + 4 * (n - 1 + k);
-      s1[0] = dt; s1[1] = a; s1[2] = 0.0; s1[3] = Delta_gate;
-      s2[0] = dt; s2[1] = a * xi_re; s2[2] = a * xi_im; s2[3] = Delta_gate;
-    }
+    const double peak = Om * md[MD_AREA_CORRECTION];
+    double wv[WAVE_STRIDE];
+    double* w = wave ? wave : wv;
+    const long long ws = wave ? wstride : 1;
+    w[WV_KIND * ws] = 1.0; w[WV_N * ws] = (double)n; w[WV_T * ws] = tau_single; w[WV_AMP * ws] = peak;
+    w[WV_DET * ws] = Delta_gate; w[WV_A * ws] = xi_re; w[WV_B * ws] = xi_im; w[WV_C * ws] = (double)shape;
+    w[WV_ROWS * ws] = (double)(2 * (n - 1));
+    if (!wave)
+      for (int k = 0; k < 2 * (n - 1); ++k) schedule_row(w, ws, k, seg + 4 * k);
     return 2 * (n - 1);
   }
   if (protocol == 1) {
@@ -321,11 +354,13 @@ RYDCZ_HD int prologue_point(const double* __restrict__ md, const AppView app,
   const double phi = (pp[3] == pp[3] && pp[3] != 0.0) ? pp[3] : 4.696;
   const double doo = De > 0 ? -fabs(d_o) : fabs(d_o);
   const double dts = tau_total / S, om_mod = ratio * Om, Dsm = doo * Om;
-  for (int s = 0; s < S; ++s) {
-    const double t_mid = s * dts + dts / 2;
-    const double ph = A * cos(om_mod * t_mid - phi);
-    seg[4 * s + 0] = dts; seg[4 * s + 1] = Om * cos(ph); seg[4 * s + 2] = Om * sin(ph); seg[4 * s + 3] = Dsm;
-  }
+  double wv[WAVE_STRIDE];
+  double* w = wave ? wave : wv;
+  const long long ws = wave ? wstride : 1;
+  w[WV_KIND * ws] = 2.0; w[WV_N * ws] = (double)S; w[WV_T * ws] = dts; w[WV_AMP * ws] = Om; w[WV_DET * ws] = Dsm;
+  w[WV_A * ws] = A; w[WV_B * ws] = om_mod; w[WV_C * ws] = phi; w[WV_ROWS * ws] = (double)S;
+  if (!wave)
+    for (int k = 0; k < S; ++k) schedule_row(w, ws, k, seg + 4 * k);
   return S;
 }
 
