@@ -723,6 +723,121 @@ repeat_apply_kernel(int64_t n_points, const unsigned* __restrict__ repeat_count,
   }
 }
 
+// apply, FOUR LANES PER POINT (noisy runs; round 2).  The one-thread-per-point kernel above is a serial chain of
+// 300 steps x 302 FMAs, each with a shared-memory operand, one warp per CTA: a generation of 8192 candidates is 256
+// warps on 148 SMs and took 0.41 ms.  Here the rows of the four dense matvecs are dealt to the four lanes of a point
+// (rows q, q + 4, ... of every system: 4 + 2 + 2 + 1 rows, the same instruction stream in every lane, surplus rows
+// masked), every lane keeps ITS rows of E0 in registers (86 doubles) and a full copy of the four state vectors (30),
+// and the new rows are exchanged by shuffles inside the group of four (30 values per step).  No shared memory, no
+// memory operand in the loop: 86 FMAs per lane and step, four times the warps.  (A first version read E0 from the
+// [entry][point] shared-memory block: the four lanes of a point hit one bank, 0.98 ms against 0.49 ms.)
+constexpr int kRepeat4Block = 128;
+__global__ void __launch_bounds__(kRepeat4Block, 2)
+repeat_apply4_kernel(int64_t n_points, const unsigned* __restrict__ repeat_count, const uint32_t* __restrict__ order,
+                     const uint8_t* __restrict__ kind, const double* __restrict__ segs,
+                     const int32_t* __restrict__ n_seg, int max_seg, const double* __restrict__ E,
+                     double* __restrict__ out, double* __restrict__ states) {
+  typedef RepeatLayout<3> RL;
+  constexpr int NA = RL::NA, NB = RL::NB, NC_ = RL::NC_, ND = RL::ND, P = kRepeat4Block / 4;     // P: points per CTA
+  static_assert(NA <= 16 && NB <= 8 && NC_ <= 8 && ND == 4, "row deal of repeat_apply4_kernel");
+  const int64_t n_eff = order ? (int64_t)*repeat_count : n_points;
+  const int slot = threadIdx.x >> 2, q = threadIdx.x & 3;
+  const int lane0 = (threadIdx.x & 31) & ~3;            // first lane of this point's group inside the warp
+  // the four lanes of a point run in lockstep (same schedule); points of one warp do not (different row counts,
+  // inactive rows): the exchange is synchronised per group of four
+  const unsigned group = 0xFu << lane0;
+  for (int64_t g0 = (int64_t)blockIdx.x * P; g0 < n_eff; g0 += (int64_t)gridDim.x * P) {
+    const int64_t g = g0 + slot;
+    const bool inside = g < n_eff;
+    const int64_t point = inside ? (order ? order[g] : g) : 0;
+    if (!(inside && kind[point] == KIND_REPEAT)) continue;
+    const double* Eg = E + g;                   // entry e of this position: Eg[e * n_points]
+    // this lane's rows of the four propagators (row index clamped; surplus rows are computed and never read back)
+    double ea[4][NA], eb[2][NB], ec[2][NC_], ed[ND];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = q + 4 * j < NA ? q + 4 * j : NA - 1;
+#pragma unroll
+      for (int c = 0; c < NA; ++c) ea[j][c] = Eg[(int64_t)(RL::RHO11 + r * NA + c) * n_points];
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int rb = q + 4 * j < NB ? q + 4 * j : NB - 1, rc = q + 4 * j < NC_ ? q + 4 * j : NC_ - 1;
+#pragma unroll
+      for (int c = 0; c < NB; ++c) eb[j][c] = Eg[(int64_t)(RL::COH11 + rb * NB + c) * n_points];
+#pragma unroll
+      for (int c = 0; c < NC_; ++c) ec[j][c] = Eg[(int64_t)(RL::RHO01 + rc * NC_ + c) * n_points];
+    }
+#pragma unroll
+    for (int c = 0; c < ND; ++c) ed[c] = Eg[(int64_t)(RL::COH01 + q * ND + c) * n_points];
+    const double* sg = segs + point * (int64_t)max_seg * SG_STRIDE;
+    const int ns = n_seg ? n_seg[point] : max_seg;
+    double xa[NA], xb[NB], xc[NC_], xd[ND];
+    Sys_rho11s_d3::init(xa); Sys_coh11s_d3::init(xb); Sys_rho01_d3::init(xc); Sys_coh01_d3::init(xd);
+    double pr = 1.0, pi = 0.0;
+    int count = 0;
+    double nd = 0.0, nre = 0.0, nim = 0.0;
+    if (ns > 0) { nd = sg[SG_DT]; nre = sg[SG_RE]; nim = sg[SG_IM]; }
+    for (int s = 0; s < ns; ++s) {
+      const double d = nd, re = nre, im = nim;
+      if (s + 1 < ns) {
+        const double* nx = sg + (int64_t)(s + 1) * SG_STRIDE;
+        nd = nx[SG_DT]; nre = nx[SG_RE]; nim = nx[SG_IM];
+      }
+      if (!(d != 0.0 && d == d)) continue;      // (the four lanes of a point take the same branch)
+      ++count;
+      const double inv = 1.0 / sqrt(re * re + im * im);
+      const double ur = re * inv, ui = im * inv;
+      const double c1 = pr * ur + pi * ui, s1 = pi * ur - pr * ui;
+      Sys_rho11s_d3::rotate(xa, c1, s1); Sys_coh11s_d3::rotate(xb, c1, s1);
+      Sys_rho01_d3::rotate(xc, c1, s1); Sys_coh01_d3::rotate(xd, c1, s1);
+      double ya[4], yb[2], yc[2], yd;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double acc = ea[j][0] * xa[0];
+#pragma unroll
+        for (int c = 1; c < NA; ++c) acc = fma(ea[j][c], xa[c], acc);
+        ya[j] = acc;
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        double acc = eb[j][0] * xb[0];
+#pragma unroll
+        for (int c = 1; c < NB; ++c) acc = fma(eb[j][c], xb[c], acc);
+        yb[j] = acc;
+        double acc2 = ec[j][0] * xc[0];
+#pragma unroll
+        for (int c = 1; c < NC_; ++c) acc2 = fma(ec[j][c], xc[c], acc2);
+        yc[j] = acc2;
+      }
+      yd = ed[0] * xd[0];
+#pragma unroll
+      for (int c = 1; c < ND; ++c) yd = fma(ed[c], xd[c], yd);
+      // row i of a system was computed by lane i & 3 as its local row i >> 2
+#pragma unroll
+      for (int i = 0; i < NA; ++i) xa[i] = __shfl_sync(group, ya[i >> 2], lane0 + (i & 3));
+#pragma unroll
+      for (int i = 0; i < NB; ++i) xb[i] = __shfl_sync(group, yb[i >> 2], lane0 + (i & 3));
+#pragma unroll
+      for (int i = 0; i < NC_; ++i) xc[i] = __shfl_sync(group, yc[i >> 2], lane0 + (i & 3));
+#pragma unroll
+      for (int i = 0; i < ND; ++i) xd[i] = __shfl_sync(group, yd, lane0 + i);
+      pr = ur; pi = ui;
+    }
+    if (q != 0) continue;
+    // back to the laboratory frame, readouts (lane 0 of the point)
+    Sys_rho11s_d3::rotate(xa, pr, pi); Sys_rho01_d3::rotate(xc, pr, pi);
+    Sys_coh11s_d3::rotate(xb, pr, pi); Sys_coh01_d3::rotate(xd, pr, pi);
+    double o[OUT_STRIDE];
+    double* st = states ? states + point * StateLayout<3>::STRIDE : nullptr;
+    repeat_finish_d3<true>(xa, xb, xc, xd, count, Eg, n_points, o, st);
+    double* op = out + point * OUT_STRIDE;
+#pragma unroll
+    for (int k = 0; k < OUT_STRIDE; k += 2)
+      *reinterpret_cast<double2*>(op + k) = make_double2(o[k], o[k + 1]);
+  }
+}
+
 // dim = 5 (intermediate state kept; identical atoms).  Per thread, in dynamic shared memory
 // ([slot][thread], conflict-free): the point row + scratch (26 slots), the start vector of rho_11
 // (45) and its generator coefficients (41) -- 896 B per thread, 112 KB per CTA, two CTAs per SM.
@@ -1063,6 +1178,8 @@ struct rydcz_ctx {
   bool rp_smem_set = false;
   double* shot_rows = nullptr; size_t shot_rows_cap = 0;   // one perturbed point row per (point, shot)
   void* wave = nullptr; size_t wave_cap = 0;               // long schedules: WAVE_STRIDE doubles per point (rydcz_prologue.cuh)
+  int repeat_lanes = 4;                                    // lanes per point of the repeated-segment apply kernel (env RYDCZ_REPEAT_LANES=1: the
+                                                           // one-thread-per-point kernel, for A/B timing)
   bool schedule_uniform = false;                           // set by the simulate entry points: every row of every schedule of the
                                                            // call shares (duration, |Omega|, Delta) -- the planner need not walk them
   void* sel_out = nullptr; size_t sel_out_cap = 0;         // column-major staging of the selected result columns
@@ -1398,8 +1515,12 @@ static int launch_eval(rydcz_ctx* ctx, const SortScratch& sc, int64_t n_items, i
     repeat_build_kernel<NOISY><<<need_b < pg ? need_b : pg, kBlock, 0, st>>>(n_items, sc.rp_count, order, sc.kind, d_points,
                                                                                d_segs, d_n_seg, max_seg, sc.rp);
     CK(cudaGetLastError());
-    repeat_apply_kernel<NOISY><<<need_a < pg ? need_a : pg, kRepeatBlock, kRepeatSmem, st>>>(n_items, sc.rp_count, order, sc.kind, d_segs,
-                                                                               d_n_seg, max_seg, sc.rp, d_out, d_states);
+    if (NOISY && ctx->repeat_lanes == 4)
+      repeat_apply4_kernel<<<need_a < pg ? need_a : pg, kRepeat4Block, 0, st>>>(n_items, sc.rp_count, order, sc.kind, d_segs,
+                                                                                 d_n_seg, max_seg, sc.rp, d_out, d_states);
+    else
+      repeat_apply_kernel<NOISY><<<need_a < pg ? need_a : pg, kRepeatBlock, kRepeatSmem, st>>>(n_items, sc.rp_count, order, sc.kind, d_segs,
+                                                                                 d_n_seg, max_seg, sc.rp, d_out, d_states);
     CK(cudaGetLastError());
     ctx->launches += 2;
   }
@@ -1452,6 +1573,7 @@ int rydcz_create(int device, rydcz_ctx** out) {
     (void)cores; (void)ranks;
     if (const char* e = getenv("RYDCZ_PACK_THREADS")) { t = atoi(e); t = t < 1 ? 1 : (t > 16 ? 16 : t); }
     ctx->pack_threads = t;
+    if (const char* e = getenv("RYDCZ_REPEAT_LANES")) ctx->repeat_lanes = atoi(e) == 1 ? 1 : 4;
     if (const char* e = getenv("RYDCZ_HOST_WAIT")) ctx->host_wait = (strcmp(e, "sleep") == 0 || strcmp(e, "1") == 0) ? 1 : 0;
   }
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
