@@ -213,9 +213,10 @@ plan_kernel(int64_t n_points, const double* __restrict__ points,
     // first *repeat_count positions), clustered general, general, plain folded, clustered
     uint32_t group = sym ? GROUP_SYM : GROUP_GENERAL;
     double w = 0.0;
-    // noiseless, identical atoms, 3-level model: every system is a coherence with a closed form (rydcz_closed.cuh);
-    // the plain folded kernel evaluates the point in a few hundred instructions per segment, no planned path pays
-    const bool closed_all = D == 3 && RYDCZ_CLOSED_COHERENCE != 0 && sym && !noisy;
+    // noiseless, 3-level model: every system is a coherence with a closed form (rydcz_closed.cuh); the plain kernels
+    // evaluate the point in a few hundred instructions per segment, no planned path pays.  (Unequal atoms: the 4 x 4
+    // form declines for weak blockade or offsets ~ |Omega| and the plain kernel then runs its Chebyshev loop.)
+    const bool closed_all = D == 3 && RYDCZ_CLOSED_COHERENCE != 0 && !noisy;
     if (D == 3 && repeat_count && sym && !shots && !closed_all) {
       int first, count;
       // uniform: the device prologue wrote the schedule and every row shares (duration, |Omega|, Delta) by construction

@@ -199,6 +199,123 @@ RYDCZ_HD bool coh01_closed_segment_d3(double (&x)[4], Closed2Cache& cache, doubl
   return cx_finite(w0) && cx_finite(w1);
 }
 
+// ---- the |11><00| coherence of UNEQUAL atoms (variables of Sys_coh11_d3: re/im of |11>, |1r>, |r1>, |rr>) -----------
+//   M = [ d0   mc   mc   0  ]   d0 = -2 i delta1 - g_sc,  dA = -i (delta1 - Delta_B) - (G + g_sc) / 2  (|1r>: atom B driven),
+//       [ m    dA   0    mc ]   dB = -i (delta1 - Delta_A) - (G + g_sc) / 2,  d3 = -i (V - Delta_A - Delta_B) - G,
+//       [ m    0    dB   mc ]   m = -i Om / 2,  mc = -i Om* / 2.
+//       [ 0    m    m    d3 ]
+// In the basis (|11>, S, |rr>, A) of the symmetric / antisymmetric combinations of |1r>, |r1> this is the tridiagonal block
+// of identical atoms (diagonal d0, dS = (dA + dB) / 2, d3) with A hanging on S by kappa = (dA - dB) / 2:
+//     p4(mu) = (mu - dS) p3(mu) - kappa^2 (mu - d0)(mu - d3),      p3 = the cubic of tridiagonal3_eigenvalues.
+// Roots: Newton on p4 (product form) from the three roots of p3 and from dS -- a Doppler shot has |kappa| << |Omega|.
+// A degree-3 Newton form through all four roots would carry terms of size (h V)^2 that cancel (the products (M - n) v
+// grow by V per factor); instead the FAST eigenvector (root n3 ~ -i V) is split off with its right / left eigenvectors,
+//     exp(h M) v = e^{h n3} P3 v + p(M) (v - P3 v),        p: degree 2 through the three slow roots,
+// and the rounding-level fast component that every matvec re-creates is projected out again.  Accepted only when the
+// iteration converged to four different roots and the fast root is isolated (V >~ 16 |Omega|: what the clustered path
+// needs anyway); else false, and the caller runs the Chebyshev loop.  Against 40-digit expm: <= 2e-13 + 4e-16 |h V|.
+struct Closed4Cache {
+  double om2, det_a, det_b, h;
+  Cx n[4];                     // n[0..2]: slow roots, closest pair first; n[3]: the fast one
+  Cx E3, f0, f01, f012;
+  bool ok;
+};
+
+RYDCZ_HD bool coh11_closed_segment_d3(double (&x)[8], Closed4Cache& cache, double h, double om_re, double om_im,
+                                      double det_a, double det_b, double V, double delta1, double G, double g_sc) {
+  const Cx d0 = cx(-g_sc, -2.0 * delta1), dA = cx(-0.5 * (G + g_sc), det_b - delta1), dB = cx(-0.5 * (G + g_sc), det_a - delta1);
+  const Cx d3 = cx(-G, det_a + det_b - V);
+  const double om2 = fma(om_re, om_re, om_im * om_im);
+  const bool same_roots = cache.om2 >= 0.0 && fabs(om2 - cache.om2) <= 1e-12 * cache.om2 && det_a == cache.det_a &&
+                          det_b == cache.det_b;
+  if (!same_roots) {
+    const Cx dS = 0.5 * (dA + dB), kap = 0.5 * (dA - dB), k2 = kap * kap;
+    const double q = -0.5 * om2;
+    Cx c[3];
+    tridiagonal3_eigenvalues(d0, dS, d3, q, q, c);        // c[2]: the one far from the closest pair
+    Cx start[4];
+    start[0] = c[0]; start[1] = c[1]; start[2] = dS; start[3] = c[2];
+    const double sc = sqrt(cx_abs2(d0)) + sqrt(cx_abs2(dS)) + sqrt(cx_abs2(d3)) + sqrt(om2) + 1e-300;
+    const double tiny2 = (1e-15 * sc) * (1e-15 * sc), lim = 1e-13 * sqrt(om2) + 1e-15 * sc;
+    bool ok = true;
+    RYDCZ_UNROLL
+    for (int k = 0; k < 4; ++k) {
+      Cx mu = start[k];
+      double step2 = 0.0;
+      for (int it = 0; it < 8; ++it) {
+        const Cx a = mu - d0, s_ = mu - dS, cc = mu - d3;
+        const Cx p3 = a * (s_ * cc) - q * cc - q * a;
+        const Cx p3p = s_ * cc + a * cc + a * s_ - cx(2.0 * q, 0.0);
+        const Cx f = s_ * p3 - k2 * (a * cc);
+        const Cx fp = p3 + s_ * p3p - k2 * (a + cc);
+        if (!(cx_abs2(fp) > 0.0)) { step2 = 0.0; break; }
+        const Cx st = f / fp;
+        mu = mu - st;
+        step2 = cx_abs2(st);
+        if (step2 <= tiny2) break;
+      }
+      ok = ok && step2 <= lim * lim;
+      cache.n[k] = mu;
+    }
+    // four different roots (their sum is the trace), the fast one isolated
+    const Cx tr = d0 + dA + dB + d3;
+    const Cx sum = cache.n[0] + cache.n[1] + cache.n[2] + cache.n[3];
+    const double mag = sqrt(cx_abs2(cache.n[0])) + sqrt(cx_abs2(cache.n[1])) + sqrt(cx_abs2(cache.n[2])) + sqrt(cx_abs2(cache.n[3])) + 1e-300;
+    ok = ok && cx_abs2(sum - tr) <= (1e-9 * mag) * (1e-9 * mag);
+    const double g01 = cx_abs2(cache.n[1] - cache.n[0]), g02 = cx_abs2(cache.n[2] - cache.n[0]), g12 = cx_abs2(cache.n[2] - cache.n[1]);
+    const double gmax = fmax(g01, fmax(g02, g12));
+    const double iso = fmin(cx_abs2(cache.n[3] - cache.n[0]), fmin(cx_abs2(cache.n[3] - cache.n[1]), cx_abs2(cache.n[3] - cache.n[2])));
+    ok = ok && iso >= 64.0 * gmax && iso > 0.0;
+    // closest slow pair first
+    if (g02 <= g01 && g02 <= g12) { const Cx t = cache.n[1]; cache.n[1] = cache.n[2]; cache.n[2] = t; }
+    else if (g12 <= g01 && g12 <= g02) { const Cx t = cache.n[0]; cache.n[0] = cache.n[2]; cache.n[2] = t; }
+    cache.ok = ok;
+    cache.om2 = om2; cache.det_a = det_a; cache.det_b = det_b;
+  }
+  if (!cache.ok) return false;
+  if (!same_roots || h != cache.h) {
+    const Cx E0 = cx_exp(h * cache.n[0]), E1 = cx_exp(h * cache.n[1]), E2 = cx_exp(h * cache.n[2]);
+    cache.E3 = cx_exp(h * cache.n[3]);
+    cache.f0 = E0;
+    cache.f01 = cx_exp_dd(cache.n[0], cache.n[1], h, E0, E1);
+    const Cx f12 = cx_exp_dd(cache.n[1], cache.n[2], h, E1, E2);
+    const Cx g = cache.n[2] - cache.n[0];
+    cache.f012 = cx_abs2(g) > 0.0 ? (f12 - cache.f01) / g : (0.5 * h * h) * E0;
+    cache.h = h;
+  }
+  const Cx m = cx(0.5 * om_im, -0.5 * om_re), mc = cx(-0.5 * om_im, -0.5 * om_re);      // -i Om / 2, -i Om* / 2
+  const Cx n3 = cache.n[3];
+  // right / left eigenvectors of the fast root, last component 1 (they turn with the laser phase: not cached)
+  const Cx one = cx(1.0, 0.0);
+  const Cx gA = one / (dA - n3), gB = one / (dB - n3), g = gA + gB;
+  const Cx den = (d0 - n3) - (mc * m) * g;
+  const Cx r0 = ((mc * mc) * g) / den, l0 = ((m * m) * g) / den;
+  const Cx tr_ = m * r0 + mc, tl_ = mc * l0 + m;
+  const Cx r1 = -(tr_ * gA), r2 = -(tr_ * gB), l1 = -(tl_ * gA), l2 = -(tl_ * gB);
+  const Cx lr = one / (l0 * r0 + l1 * r1 + l2 * r2 + one);
+  Cx v0 = cx(x[0], x[1]), v1 = cx(x[2], x[3]), v2 = cx(x[4], x[5]), v3 = cx(x[6], x[7]);
+  // fast part / slow part of v
+  const Cx cf = (l0 * v0 + l1 * v1 + l2 * v2 + v3) * lr;
+  const Cx w0f = cf * r0, w1f = cf * r1, w2f = cf * r2, w3f = cf;
+  v0 = v0 - w0f; v1 = v1 - w1f; v2 = v2 - w2f; v3 = v3 - w3f;
+  // u = (M - n0) v, re-projected; t = (M - n1) u, re-projected
+  const Cx a0 = cache.n[0], a1 = cache.n[1];
+  Cx u0 = (d0 - a0) * v0 + mc * (v1 + v2), u1 = m * v0 + (dA - a0) * v1 + mc * v3;
+  Cx u2 = m * v0 + (dB - a0) * v2 + mc * v3, u3 = m * (v1 + v2) + (d3 - a0) * v3;
+  Cx cu = (l0 * u0 + l1 * u1 + l2 * u2 + u3) * lr;
+  u0 = u0 - cu * r0; u1 = u1 - cu * r1; u2 = u2 - cu * r2; u3 = u3 - cu;
+  Cx t0 = (d0 - a1) * u0 + mc * (u1 + u2), t1 = m * u0 + (dA - a1) * u1 + mc * u3;
+  Cx t2 = m * u0 + (dB - a1) * u2 + mc * u3, t3 = m * (u1 + u2) + (d3 - a1) * u3;
+  cu = (l0 * t0 + l1 * t1 + l2 * t2 + t3) * lr;
+  t0 = t0 - cu * r0; t1 = t1 - cu * r1; t2 = t2 - cu * r2; t3 = t3 - cu;
+  const Cx y0 = cache.E3 * w0f + cache.f0 * v0 + cache.f01 * u0 + cache.f012 * t0;
+  const Cx y1 = cache.E3 * w1f + cache.f0 * v1 + cache.f01 * u1 + cache.f012 * t1;
+  const Cx y2 = cache.E3 * w2f + cache.f0 * v2 + cache.f01 * u2 + cache.f012 * t2;
+  const Cx y3 = cache.E3 * w3f + cache.f0 * v3 + cache.f01 * u3 + cache.f012 * t3;
+  x[0] = y0.re; x[1] = y0.im; x[2] = y1.re; x[3] = y1.im; x[4] = y2.re; x[5] = y2.im; x[6] = y3.re; x[7] = y3.im;
+  return cx_finite(y0) && cx_finite(y1) && cx_finite(y2) && cx_finite(y3);
+}
+
 // FP64 operations of one segment, for the kernels' own flop count (products 6, sums 2, quotients 11; the
 // transcendental functions are not counted): roots, exponentials + divided differences, the two matvecs + combination
 constexpr double kClosed3FlopsRoots = 400.0, kClosed3FlopsExp = 90.0, kClosed3FlopsApply = 200.0;
@@ -225,6 +342,28 @@ RYDCZ_HD bool coh11s_closed_d3(double (&x)[6], const PointView pt, const double*
                                    : (cache.h != h_before ? kClosed3FlopsExp : 0.0));
   }
   return ok;
+}
+constexpr double kClosed4FlopsRoots = 1200.0, kClosed4FlopsExp = 110.0, kClosed4FlopsApply = 600.0;
+// unequal atoms: the general |11><00| coherence (Sys_coh11_d3).  false: not accepted (see above) or non-finite.
+template <bool NOISY>
+RYDCZ_HD bool coh11_closed_d3(double (&x)[8], const PointView pt, const double* __restrict__ seg, int n_seg,
+                              double& flops) {
+  Sys_coh11_d3::init(x);
+  Closed4Cache cache;
+  cache.om2 = -1.0; cache.det_a = 0.0; cache.det_b = 0.0; cache.h = 0.0; cache.ok = false;
+  const double V = pt[PT_V], delta1 = pt[PT_DELTA1], off_a = pt[PT_OFF_A], off_b = pt[PT_OFF_B];
+  const double G = NOISY ? pt[PT_G_R1] + pt[PT_G_R0] + pt[PT_G_PHI] : 0.0, g_sc = NOISY ? pt[PT_G_SC] : 0.0;
+  for (int s = 0; s < n_seg; ++s) {
+    const double* sg = seg + (long long)s * SG_STRIDE;
+    const double dt = sg[SG_DT], re = sg[SG_RE], im = sg[SG_IM], det = sg[SG_DET];
+    if (!segment_active(dt)) continue;
+    const double om2_before = cache.om2, da_before = cache.det_a, db_before = cache.det_b, h_before = cache.h;
+    if (!coh11_closed_segment_d3(x, cache, dt, re, im, det + off_a, det + off_b, V, delta1, G, g_sc)) return false;
+    flops += kClosed4FlopsApply + ((cache.om2 != om2_before || cache.det_a != da_before || cache.det_b != db_before)
+                                       ? kClosed4FlopsRoots + kClosed4FlopsExp
+                                       : (cache.h != h_before ? kClosed4FlopsExp : 0.0));
+  }
+  return true;
 }
 // atom_b: the |01> input (atom B driven, offset PT_OFF_B), else the |10> input (atom A, PT_OFF_A)
 template <bool NOISY>

@@ -896,10 +896,14 @@ RYDCZ_HD bool evaluate_point_cluster_general_d3(const PointView pt, const Col xc
     if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_rho11_d3::N; ++i) states[SL::RHO11 + i] = x[i]; }
   }
   {
-    double x[Sys_coh11_d3::N]; st = 0.0;
-    run_system_cluster<Sys_coh11_d3, CL_RING_GENERAL>(x, xcol, rcol, pt, seg, n_seg, NOISY, rec, table, st);
+    double x[Sys_coh11_d3::N], cf = 0.0; st = 0.0;
+    // closed form (rydcz_closed.cuh) where it is accepted: strong blockade and Doppler-sized offsets, i.e. every shot
+    if (ClosedCoh11<3>::run<NOISY>(x, pt, seg, n_seg, cf)) flops += cf;
+    else {
+      run_system_cluster<Sys_coh11_d3, CL_RING_GENERAL>(x, xcol, rcol, pt, seg, n_seg, NOISY, rec, table, st);
+      steps += st; flops += st * 2.0 * (3 * Sys_coh11_d3::NNZ + 4 * Sys_coh11_d3::N);
+    }
     RYDCZ_RECONVERGE(pt.live);
-    steps += st; flops += st * 2.0 * (3 * Sys_coh11_d3::NNZ + 4 * Sys_coh11_d3::N);
     c11r = x[COH11_RE_D3]; c11i = x[COH11_IM_D3];
     if (!NOISY) { ryd = 1.0 - (c11r * c11r + c11i * c11i); ok = fabs(coh11_norm2_d3(x) - 1.0) <= 1e-9; }
     if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh11_d3::N; ++i) states[SL::COH11 + i] = x[i]; }

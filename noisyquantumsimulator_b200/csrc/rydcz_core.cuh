@@ -607,6 +607,19 @@ template <> struct ClosedCoh11s<3> {
   }
 };
 
+// ... and the |11><00| coherence of unequal atoms (4 x 4; declines outside the strong-blockade, small-offset regime)
+template <int D> struct ClosedCoh11 {
+  template <bool NOISY, int N>
+  RYDCZ_HD static bool run(double (&)[N], const PointView, const double* __restrict__, int, double&) { return false; }
+};
+template <> struct ClosedCoh11<3> {
+  template <bool NOISY>
+  RYDCZ_HD static bool run(double (&x)[Sys_coh11_d3::N], const PointView pt, const double* __restrict__ seg, int n_seg,
+                           double& flops) {
+    return RYDCZ_CLOSED_COHERENCE != 0 && coh11_closed_d3<NOISY>(x, pt, seg, n_seg, flops);
+  }
+};
+
 // A single-atom coherence |01><00| (atom_b) or |10><00|: closed form for the 3-level model, else (or when that
 // fails) the Chebyshev loop of the system.  Every live lane of the warp reaches the reconvergence point.
 template <class SysCoh, bool NOISY>
@@ -686,9 +699,13 @@ RYDCZ_HD void cz_epilogue(bool noisy, double p01, double p10, double p11,
       if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_rho11_d##D::N; ++i) states[SL::RHO11 + i] = x[i]; } \
     }                                                                                               \
     {                                                                                               \
-      double x[Sys_coh11_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_coh11_d##D>(x, pt, seg, n_seg, NOISY, st); RYDCZ_RECONVERGE(pt.live);          \
-      steps += st; flops += st * 2.0 * (Sys_coh11_d##D::NNZ + Sys_coh11_d##D::N);                   \
+      double x[Sys_coh11_d##D::N], cf = 0.0; st = 0.0;                                              \
+      if (ClosedCoh11<D>::template run<NOISY>(x, pt, seg, n_seg, cf)) flops += cf;                  \
+      else {                                                                                        \
+        run_system<Sys_coh11_d##D>(x, pt, seg, n_seg, NOISY, st);                                   \
+        steps += st; flops += st * 2.0 * (Sys_coh11_d##D::NNZ + Sys_coh11_d##D::N);                 \
+      }                                                                                             \
+      RYDCZ_RECONVERGE(pt.live);                                                                    \
       c11r = x[COH11_RE_D##D]; c11i = x[COH11_IM_D##D];                                             \
       if (!NOISY) ryd = 1.0 - (c11r * c11r + c11i * c11i);                                          \
       if (states) { RYDCZ_UNROLL for (int i = 0; i < Sys_coh11_d##D::N; ++i) states[SL::COH11 + i] = x[i]; } \

@@ -128,7 +128,7 @@ extern "C" int hostsim_evaluate(int dim, int noisy, long long n_points, const do
     // same dispatch rule as the CUDA kernels: identical atoms take the exchange-folded path
     const bool sym = g_allow_sym && pt[PT_OFF_A] == pt[PT_OFF_B];
     // (noiseless, identical atoms, 3-level: closed forms only -- the planner keeps such points on the plain folded path)
-    const bool closed_all = dim == 3 && RYDCZ_CLOSED_COHERENCE != 0 && sym && !noisy;
+    const bool closed_all = dim == 3 && RYDCZ_CLOSED_COHERENCE != 0 && !noisy;
     if (g_cluster && sym && dim == 3 && !closed_all) {
       // repeated-segment path (csrc/rydcz_repeat.cuh): same rule as the CUDA planner
       int first = 0, count = 0;
@@ -146,7 +146,7 @@ extern "C" int hostsim_evaluate(int dim, int noisy, long long n_points, const do
         continue;
       }
     }
-    if (g_cluster && !sym && dim == 3 && g_allow_sym) {
+    if (g_cluster && !sym && dim == 3 && g_allow_sym && !closed_all) {
       double* st = states ? states + i * StateLayout<3>::STRIDE : nullptr;
       if (try_cluster_general(pt, row, sg, n_seg[i], noisy != 0, o, st)) continue;
     }
@@ -202,7 +202,8 @@ extern "C" int hostsim_prologue(const double* model, long long n_points, const d
 }
 
 // closed-form coherences (csrc/rydcz_closed.cuh) of one point, for tests/test_closed_coherence.py:
-// which = 0: exchange-folded |11><00| (6 doubles), 1: |01><00| (atom B driven), 2: |10><00| (4 doubles).  Returns 1 when finite.
+// which = 0: exchange-folded |11><00| (6 doubles), 1: |01><00| (atom B driven), 2: |10><00| (4 doubles), 3: |11><00| of
+// unequal atoms (8 doubles).  Returns 1 when the closed form was accepted and finite.
 extern "C" int hostsim_closed_coherence(int which, int noisy, const double* point, const double* segs, int n_seg,
                                         double* x) {
   using namespace rydcz;
@@ -214,6 +215,12 @@ extern "C" int hostsim_closed_coherence(int which, int noisy, const double* poin
     double v[6];
     const bool ok = noisy ? coh11s_closed_d3<true>(v, pt, segs, n_seg, flops) : coh11s_closed_d3<false>(v, pt, segs, n_seg, flops);
     for (int k = 0; k < 6; ++k) x[k] = v[k];
+    return ok ? 1 : 0;
+  }
+  if (which == 3) {      // unequal atoms: the general |11><00| coherence (8 doubles)
+    double v[8];
+    const bool ok = noisy ? coh11_closed_d3<true>(v, pt, segs, n_seg, flops) : coh11_closed_d3<false>(v, pt, segs, n_seg, flops);
+    for (int k = 0; k < 8; ++k) x[k] = v[k];
     return ok ? 1 : 0;
   }
   double v[4];

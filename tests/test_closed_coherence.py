@@ -20,7 +20,7 @@ def hostsim():
 def _closed(hostsim, which, noisy, pt, segs):
     lib = hostsim.lib
     lib.hostsim_closed_coherence.argtypes = [Ct.c_int, Ct.c_int, DP, DP, Ct.c_int, DP]
-    x = np.zeros(6 if which == 0 else 4)
+    x = np.zeros({0: 6, 3: 8}.get(which, 4))
     segs = np.ascontiguousarray(segs, dtype=np.float64)
     ok = lib.hostsim_closed_coherence(which, int(noisy), np.ascontiguousarray(pt).ctypes.data_as(DP),
                                       segs.ctypes.data_as(DP), len(segs), x.ctypes.data_as(DP))
@@ -96,6 +96,38 @@ def test_single_atom_coherence_against_40_digit_expm(hostsim, which):
         y = _exact(system, pt, segs, 1.0, "det_b" if which == 1 else "det_a")
         err = np.abs(x - y).max() / max(np.abs(y).max(), 1e-300)
         assert ok == 1 and err < 2e-13, (trial, err)
+
+
+@pytest.mark.parametrize("noisy", [True, False])
+def test_unequal_atoms_11_coherence_against_40_digit_expm(hostsim, noisy):
+    """The general |11><00| coherence (4 x 4: the fast eigenvector split off, three slow roots by Newton on the
+    quartic).  In the regime of a Doppler shot (V / Omega >= 16, offsets of tens of kHz) it is always accepted; with
+    weak blockade or strongly unequal atoms it may decline (the kernels then run the Chebyshev loop) -- but whatever
+    it accepts is accurate."""
+    rng = np.random.default_rng(17 + noisy)
+    system = M.standard_systems(3)["coh11"]
+    declined = 0
+    for trial in range(160):
+        pt, segs = _random_point(rng, trial)
+        realistic = trial % 2 == 0
+        Om = max(np.hypot(segs[0, 1], segs[0, 2]), 2 * np.pi * 1e6)
+        if realistic:
+            pt[0] = Om * 10 ** rng.uniform(1.2, 2.9)
+            pt[2], pt[3] = 2 * np.pi * rng.normal(0, 8e4, 2)
+            if np.hypot(segs[0, 1], segs[0, 2]) == 0.0:
+                continue                                    # (an idle segment between unequal atoms: declined by design)
+        else:
+            pt[2], pt[3] = 2 * np.pi * rng.normal(0, 1e6, 2)
+        ok, x = _closed(hostsim, 3, noisy, pt, segs)
+        if not ok:
+            declined += 1
+            assert not realistic, trial
+            continue
+        y = _exact(system, pt, segs, noisy, None)
+        tol = 2e-13 + 4e-16 * np.abs(segs[:, 0] * pt[0]).sum()
+        err = np.abs(x - y).max() / max(np.abs(y).max(), 1e-300)
+        assert err < tol, (trial, err, tol)
+    assert 0 < declined < 80
 
 
 def test_noiseless_identical_atoms_need_no_chebyshev_step(hostsim):

@@ -94,7 +94,8 @@ def test_random_unequal_atoms_against_oracle(evaluator, dim, noisy):
     _compare(dim, noisy, items, out, st)
     if dim == 3:
         status = evaluator.point_status(len(items)) & 0x0f
-        assert set(status) <= {0, 2} and (status == 2).any()          # general plain / general clustered
+        # general plain / general clustered; without noise every system is a closed form and nothing is planned
+        assert set(status) <= {0, 2} and ((status == 2).any() if noisy else (status == 0).all())
 
 
 def test_mixed_kinds_in_one_sorted_batch(evaluator):
@@ -124,9 +125,9 @@ def test_mixed_kinds_in_one_sorted_batch(evaluator):
         if noisy:
             assert evaluator.repeat_stats() == 24
             assert (status[1::4] == 5).all() and (status[0::4] == 2).all() and (status[2::4] == 3).all()
-        else:      # identical atoms without noise are closed forms on the plain folded path (status 1)
+        else:      # without noise every system is a closed form: plain kernels (status 1 folded, 0 general), nothing planned
             assert evaluator.repeat_stats() == 0
-            assert (status[1::4] == 1).all() and (status[0::4] == 2).all() and (status[2::4] == 1).all()
+            assert (status[1::4] == 1).all() and (status[0::4] == 0).all() and (status[2::4] == 1).all()
         assert np.isfinite(out).all()
         evaluator.set_cluster(0)
         out0, st0 = evaluator.evaluate_host(3, noisy, P, G, ns, want_states=True)
@@ -296,8 +297,8 @@ def test_paths_agree_on_random_batches(evaluator):
         evaluator.set_cluster(0)
         out0, st0 = evaluator.evaluate_host(dim, noisy, P, G, ns, want_states=True)
         evaluator.set_cluster(1)
-        # (3-level, noiseless: identical atoms are closed forms on the plain folded path; only unequal atoms are planned)
-        assert planned > (n // 8 if (dim == 3 and not noisy) else n // 4) and back == 0
+        # (3-level, noiseless: every system is a closed form on the plain kernels; nothing is planned)
+        assert (planned == 0 if (dim == 3 and not noisy) else planned > n // 4) and back == 0
         worst = max(worst, np.abs(out[:, :14] - out0[:, :14]).max(), np.abs(st - st0).max())
     assert worst < 5e-11
 
