@@ -25,8 +25,8 @@
 //     smooth-JP pulses change only the laser phase, which enters the off-diagonal elements of M alone.
 //
 // Plain C++ when RYDCZ_HD is empty (tests/hostsim), like rydcz_core.cuh.  3-level model only: with r+ / r- the |11>
-// input has five folded components (quintic), and the general (unequal-atom) |11> input four (quartic); those keep
-// the Chebyshev loop, as does everything that is not a coherence.
+// input has five folded components (quintic) and keeps the Chebyshev loop, as does everything that is not a
+// coherence.  The |11> input of UNEQUAL atoms has four components (a quartic): its form is further down.
 #pragma once
 // (included by rydcz_core.cuh inside namespace rydcz, after run_system)
 
