@@ -74,6 +74,10 @@ if os.environ.get("E2E_QUICK") == "1":       # the N = 8 run: GPU-minutes are ch
     ev.set_host_wait(True)
     n = ev.bind_host_to_gpu()
     measure(f"host wait = sleep, bound to {n} cpus")
+    ev.set_host_wait(False)
+    for chunk in (65536, 131072, 32768):
+        ev.set_chunk(chunk)
+        measure(f"spin, chunk={chunk}")
     if world > 1:
         dist.destroy_process_group()
     sys.exit(0)
