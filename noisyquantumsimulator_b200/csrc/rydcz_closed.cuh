@@ -177,7 +177,7 @@ RYDCZ_HD bool coh01_closed_segment_d3(double (&x)[4], Closed2Cache& cache, doubl
   const Cx dl = 0.5 * (d0 - d1);
   if (!(cache.om2 >= 0.0 && fabs(om2 - cache.om2) <= 1e-12 * cache.om2 && det == cache.det && h == cache.h)) {
     const Cx z = h * cx_sqrt(dl * dl - cx(0.25 * om2, 0.0));
-    const Cx ez = cx_exp(z), emz = cx_exp(-z);
+    const Cx ez = cx_exp(z), emz = cx(1.0, 0.0) / ez;
     cache.ch = 0.5 * (ez + emz);
     if (cx_abs2(z) >= 0.01) cache.sh = h * ((0.5 * (ez - emz)) / z);
     else {
@@ -365,6 +365,161 @@ RYDCZ_HD bool coh11_closed_d3(double (&x)[8], const PointView pt, const double* 
   }
   return true;
 }
+// ---- the single-atom density operator rho_01 / rho_10 (variables of Sys_rho01_d3 / Sys_rho10_d3) -------------------
+// x = (p0, p1, re c, im c, pr) of the driven atom: the optical Bloch equations with decay r -> 1 (g_r1) and r -> 0
+// (g_r0).  The trace is conserved (p0' = g_r0 pr = -(p1 + pr)'), so p0 follows from the other four, which obey a REAL
+// 4 x 4 system whose characteristic polynomial has coefficients that are sums of positive terms
+//     a3 = 2 G2 + G,   a2 = G2^2 + 2 G2 G + d^2 + |Om|^2,   a1 = G (G2^2 + d^2) + |Om|^2 (G2 + g_r0 / 2),
+//     a0 = G2 g_r0 |Om|^2 / 2          (G = g_r1 + g_r0, G2 = (G + g_phi + g_sc) / 2, d = Delta + delta1):
+// a FAST pair lam, lam* ~ -G' +- i sqrt(|Om|^2 + d^2) (Newton on the quartic) and a SLOW pair of size ~ G, the roots of
+// mu^2 + b' mu + c' with c' = a0 / |lam|^2, b' = (a1 - b c') / |lam|^2 (no cancellation: the slow roots come out with
+// their full relative accuracy although they are 1e-4 of the fast ones).  With q(mu) = (mu - lam)(mu - lam*),
+//     exp(h M) = al0 + al1 M + q(M) (be0 + be1 M),
+// al: the line through exp(h mu) at the fast pair; be: the line through (exp(h mu) - al0 - al1 mu) / q(mu) at the slow
+// pair (divided differences by Leibniz' rule: nothing is divided by the small gap of the slow pair).  Every term is
+// O(|v|): q(M) removes the fast components, so nothing of size (h Omega)^k has to cancel.  Declines (false: the caller
+// runs the Chebyshev loop) when Newton did not converge or the pairs are not separated (|q(slow)| < a2 / 256: drive
+// and detuning both ~ 0, or damping ~ drive).  Against 40-digit expm, |Om| 1e2..1e8, rates up to 3e6: <= 1e-14 + 2e-16 |h Om_eff|.
+struct ClosedRhoCache {
+  double om2, det, h;          // |Omega|^2, Delta (+ offset) and duration the entries below belong to (om2 < 0: none)
+  double b, c;                 // q(mu) = mu^2 + b mu + c
+  Cx lam, r1, r2;              // fast root (upper half plane), slow roots (both real, or a conjugate pair)
+  double al0, al1, be0, be1;
+  bool ok;
+};
+
+RYDCZ_HD bool rho01_closed_segment_d3(double (&x)[5], ClosedRhoCache& cache, double h, double om_re, double om_im,
+                                      double det, double delta1, double g_r1, double g_r0, double g_phi, double g_sc) {
+  const double om2 = fma(om_re, om_re, om_im * om_im);
+  const double G = g_r1 + g_r0, G2 = 0.5 * (G + g_phi + g_sc), d = det + delta1;
+  const bool same_roots = cache.om2 >= 0.0 && fabs(om2 - cache.om2) <= 1e-12 * cache.om2 && det == cache.det;
+  if (!same_roots) {
+    const double a3 = 2.0 * G2 + G, a2 = G2 * G2 + 2.0 * G2 * G + d * d + om2;
+    const double a1 = G * (G2 * G2 + d * d) + om2 * (G2 + 0.5 * g_r0), a0 = 0.5 * G2 * g_r0 * om2;
+    cache.om2 = om2; cache.det = det; cache.h = 0.0;
+    cache.ok = false;
+    if (!(a2 > 0.0) || !(a2 <= 1.7e308)) return false;
+    Cx lam = cx(-0.5 * (a3 - a1 / a2), sqrt(a2));
+    double step2 = 0.0;
+    bool ok = true;
+    RYDCZ_UNROLL
+    for (int it = 0; it < 5; ++it) {
+      const Cx p = (((lam + cx(a3, 0.0)) * lam + cx(a2, 0.0)) * lam + cx(a1, 0.0)) * lam + cx(a0, 0.0);
+      const Cx dp = ((4.0 * lam + cx(3.0 * a3, 0.0)) * lam + cx(2.0 * a2, 0.0)) * lam + cx(a1, 0.0);
+      if (!(cx_abs2(dp) > 0.0)) { ok = false; break; }
+      const Cx st = p / dp;
+      lam = lam - st;
+      step2 = cx_abs2(st);
+    }
+    const double c = cx_abs2(lam), b = -2.0 * lam.re;
+    ok = ok && c > 0.0 && step2 <= 1e-24 * c;
+    if (!ok) return false;
+    const double cp = a0 / c, bp = (a1 - b * cp) / c;
+    const double disc = bp * bp - 4.0 * cp;
+    Cx r1, r2;
+    if (disc >= 0.0) {
+      const double sq = sqrt(disc);
+      const double q = -0.5 * (bp + (bp >= 0.0 ? sq : -sq));
+      r1 = cx(q, 0.0);
+      r2 = cx(q != 0.0 ? cp / q : 0.0, 0.0);
+    } else {
+      r1 = cx(-0.5 * bp, 0.5 * sqrt(-disc));
+      r2 = cx_conj(r1);
+    }
+    // two Newton steps on the quartic itself (Horner is stable next to 0: every term is of the size of a0)
+    RYDCZ_UNROLL
+    for (int k = 0; k < 2; ++k) {
+      Cx r = k == 0 ? r1 : r2;
+      RYDCZ_UNROLL
+      for (int it = 0; it < 2; ++it) {
+        const Cx p = (((r + cx(a3, 0.0)) * r + cx(a2, 0.0)) * r + cx(a1, 0.0)) * r + cx(a0, 0.0);
+        const Cx dp = ((4.0 * r + cx(3.0 * a3, 0.0)) * r + cx(2.0 * a2, 0.0)) * r + cx(a1, 0.0);
+        if (cx_abs2(dp) > 0.0) r = r - p / dp;
+      }
+      if (k == 0) r1 = r; else r2 = r;
+    }
+    if (disc < 0.0) r2 = cx_conj(r1);
+    const Cx q1 = (r1 + cx(b, 0.0)) * r1 + cx(c, 0.0), q2 = (r2 + cx(b, 0.0)) * r2 + cx(c, 0.0);
+    const double sep = a2 * (1.0 / 256.0);
+    if (!(cx_abs2(q1) >= sep * sep) || !(cx_abs2(q2) >= sep * sep)) return false;
+    cache.lam = lam; cache.r1 = r1; cache.r2 = r2; cache.b = b; cache.c = c;
+    cache.ok = true;
+  }
+  if (!cache.ok) return false;
+  if (!same_roots || h != cache.h) {
+    const Cx lam = cache.lam, r1 = cache.r1, r2 = cache.r2;
+    const Cx E = cx_exp(h * lam);
+    cache.al1 = cx_exp_dd(lam, cx_conj(lam), h, E, cx_conj(E)).re;
+    cache.al0 = (E - cache.al1 * lam).re;
+    const Cx q1 = (r1 + cx(cache.b, 0.0)) * r1 + cx(cache.c, 0.0), q2 = (r2 + cx(cache.b, 0.0)) * r2 + cx(cache.c, 0.0);
+    Cx E1, E2, F12;
+    if (r1.im == 0.0 && r2.im == 0.0) {
+      // the usual case, two real slow roots: real exponentials, and exp(h (r1 + r2) / 2) = sqrt(E1 E2)
+      E1 = cx(exp(h * r1.re), 0.0); E2 = cx(exp(h * r2.re), 0.0);
+      const double z = 0.5 * h * (r2.re - r1.re), z2 = z * z;
+      double dd;
+      if (z2 >= 0.01) dd = (E2.re - E1.re) / (r2.re - r1.re);
+      else {
+        double sr = fma(z2, 1.0 / 72.0, 1.0);
+        sr = fma(z2 * sr, 1.0 / 42.0, 1.0);
+        sr = fma(z2 * sr, 1.0 / 20.0, 1.0);
+        sr = fma(z2 * sr, 1.0 / 6.0, 1.0);
+        dd = h * sqrt(E1.re * E2.re) * sr;
+      }
+      F12 = cx(dd - cache.al1, 0.0);
+    } else {
+      E1 = cx_exp(h * r1); E2 = cx_exp(h * r2);
+      F12 = cx_exp_dd(r1, r2, h, E1, E2) - cx(cache.al1, 0.0);
+    }
+    const Cx g1 = (E1 - cx(cache.al0, 0.0) - cache.al1 * r1) / q1;
+    cache.be1 = ((F12 - g1 * (r1 + r2 + cx(cache.b, 0.0))) / q2).re;
+    cache.be0 = (g1 - cache.be1 * r1).re;
+    cache.h = h;
+  }
+  // M on (p1, re c, im c, pr): the rows of Sys_rho01_d3::apply
+  const double hr = 0.5 * om_re, hi = 0.5 * om_im, Gr = g_r1 + g_r0;
+#define RYDCZ_RHO01_M(o, v)                                                  \
+  const double o##0 = -om_im * v##1 - om_re * v##2 + g_r1 * v##3;           \
+  const double o##1 = hi * (v##0 - v##3) - G2 * v##1 + d * v##2;            \
+  const double o##2 = hr * (v##0 - v##3) - d * v##1 - G2 * v##2;            \
+  const double o##3 = om_im * v##1 + om_re * v##2 - Gr * v##3;
+  const double v0 = x[1], v1 = x[2], v2 = x[3], v3 = x[4];
+  RYDCZ_RHO01_M(u, v)
+  RYDCZ_RHO01_M(t, u)
+  const double w0 = t0 + cache.b * u0 + cache.c * v0, w1 = t1 + cache.b * u1 + cache.c * v1;
+  const double w2 = t2 + cache.b * u2 + cache.c * v2, w3 = t3 + cache.b * u3 + cache.c * v3;
+  RYDCZ_RHO01_M(z, w)
+#undef RYDCZ_RHO01_M
+  const double y0 = cache.al0 * v0 + cache.al1 * u0 + cache.be0 * w0 + cache.be1 * z0;
+  const double y1 = cache.al0 * v1 + cache.al1 * u1 + cache.be0 * w1 + cache.be1 * z1;
+  const double y2 = cache.al0 * v2 + cache.al1 * u2 + cache.be0 * w2 + cache.be1 * z2;
+  const double y3 = cache.al0 * v3 + cache.al1 * u3 + cache.be0 * w3 + cache.be1 * z3;
+  x[0] += (v0 + v3) - (y0 + y3);      // the trace is conserved
+  x[1] = y0; x[2] = y1; x[3] = y2; x[4] = y3;
+  return fabs(y0) <= 1.7e308 && fabs(y1) <= 1.7e308 && fabs(y2) <= 1.7e308 && fabs(y3) <= 1.7e308;
+}
+constexpr double kClosedRhoFlopsRoots = 900.0, kClosedRhoFlopsExp = 160.0, kClosedRhoFlopsApply = 130.0;
+// The whole pulse.  atom_b: rho_01 (atom B driven, offset PT_OFF_B), else rho_10 (atom A, PT_OFF_A).  false: declined
+// (x is then unspecified and the caller runs the Chebyshev loop from the start operator).
+RYDCZ_HD bool rho01_closed_d3(double (&x)[5], const PointView pt, const double* __restrict__ seg, int n_seg,
+                              bool atom_b, double& flops) {
+  Sys_rho01_d3::init(x);
+  ClosedRhoCache cache;
+  cache.om2 = -1.0; cache.det = 0.0; cache.h = 0.0; cache.ok = false;
+  const double delta1 = pt[PT_DELTA1], off = atom_b ? pt[PT_OFF_B] : pt[PT_OFF_A];
+  const double g_r1 = pt[PT_G_R1], g_r0 = pt[PT_G_R0], g_phi = pt[PT_G_PHI], g_sc = pt[PT_G_SC];
+  for (int s = 0; s < n_seg; ++s) {
+    const double* sg = seg + (long long)s * SG_STRIDE;
+    const double dt = sg[SG_DT], re = sg[SG_RE], im = sg[SG_IM], det = sg[SG_DET] + off;
+    if (!segment_active(dt)) continue;
+    const double h_before = cache.h, om2_before = cache.om2, det_before = cache.det;
+    if (!rho01_closed_segment_d3(x, cache, dt, re, im, det, delta1, g_r1, g_r0, g_phi, g_sc)) return false;
+    flops += kClosedRhoFlopsApply + ((cache.om2 != om2_before || cache.det != det_before) ? kClosedRhoFlopsRoots + kClosedRhoFlopsExp
+                                     : (cache.h != h_before ? kClosedRhoFlopsExp : 0.0));
+  }
+  return true;
+}
+
 // atom_b: the |01> input (atom B driven, offset PT_OFF_B), else the |10> input (atom A, PT_OFF_A)
 template <bool NOISY>
 RYDCZ_HD bool coh01_closed_d3(double (&x)[4], const PointView pt, const double* __restrict__ seg, int n_seg,

@@ -830,9 +830,8 @@ template <int D> struct ClusterRing { static constexpr int value = D == 3 ? 8 : 
     }                                                                                               \
     if (!ok) return false;                                                                          \
     if (NOISY && ClosedCoh11s<D>::available) {                                                      \
-      double x[Sys_rho01_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_rho01_d##D>(x, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);           \
-      steps += st; flops += st * 2.0 * (Sys_rho01_d##D::NNZ + Sys_rho01_d##D::N);                   \
+      double x[Sys_rho01_d##D::N];                                                                  \
+      single_atom_rho<Sys_rho01_d##D>(x, pt, seg, n_seg, true, steps, flops);                       \
       p01 = x[RHO01_POP_D##D];                                                                      \
       double xc[Sys_coh01_d##D::N];                                                                 \
       single_atom_coherence<Sys_coh01_d##D, true>(xc, pt, seg, n_seg, true, steps, flops);          \
@@ -911,16 +910,14 @@ RYDCZ_HD bool evaluate_point_cluster_general_d3(const PointView pt, const Col xc
   if (!ok) return false;
   if (NOISY) {
     // single-atom inputs: rho_ab on its Chebyshev loop, the |ab><00| coherence in closed form (rydcz_closed.cuh)
-    double x[Sys_rho01_d3::N]; st = 0.0;
-    run_system<Sys_rho01_d3>(x, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);
-    steps += st; flops += st * 2.0 * (Sys_rho01_d3::NNZ + Sys_rho01_d3::N);
+    double x[Sys_rho01_d3::N];
+    single_atom_rho<Sys_rho01_d3>(x, pt, seg, n_seg, true, steps, flops);
     p01 = x[RHO01_POP_D3];
     double xc[Sys_coh01_d3::N];
     single_atom_coherence<Sys_coh01_d3, true>(xc, pt, seg, n_seg, true, steps, flops);
     c01r = xc[COH01_RE_D3]; c01i = xc[COH01_IM_D3];
-    double y[Sys_rho10_d3::N]; st = 0.0;
-    run_system<Sys_rho10_d3>(y, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);
-    steps += st; flops += st * 2.0 * (Sys_rho10_d3::NNZ + Sys_rho10_d3::N);
+    double y[Sys_rho10_d3::N];
+    single_atom_rho<Sys_rho10_d3>(y, pt, seg, n_seg, false, steps, flops);
     p10 = y[RHO10_POP_D3];
     double yc[Sys_coh10_d3::N];
     single_atom_coherence<Sys_coh10_d3, true>(yc, pt, seg, n_seg, false, steps, flops);

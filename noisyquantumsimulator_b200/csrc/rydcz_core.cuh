@@ -589,6 +589,9 @@ RYDCZ_HD void run_system_huge(const XV x, const XV b1, const XV b2, const PointV
 #ifndef RYDCZ_CLOSED_COHERENCE
 #define RYDCZ_CLOSED_COHERENCE 1     // 0: every system on the Chebyshev loops (A/B builds, round-1 behaviour)
 #endif
+#ifndef RYDCZ_CLOSED_RHO01
+#define RYDCZ_CLOSED_RHO01 1         // 0: single-atom rho on its Chebyshev loop (A/B builds)
+#endif
 #include "rydcz_closed.cuh"
 
 // The exchange-folded |11><00| coherence in closed form, where there is one: false = not available for this model
@@ -639,6 +642,25 @@ RYDCZ_HD void single_atom_coherence(double (&y)[SysCoh::N], const PointView pt, 
   RYDCZ_RECONVERGE(pt.live);
 }
 
+
+// A single-atom density operator rho_01 (atom_b) or rho_10: closed form for the 3-level model (optical Bloch
+// equations, rydcz_closed.cuh), else (or when that declines) the Chebyshev loop of the system.
+template <class SysRho>
+RYDCZ_HD void single_atom_rho(double (&x)[SysRho::N], const PointView pt, const double* __restrict__ seg,
+                              int n_seg, bool atom_b, double& steps, double& flops) {
+  bool done = false;
+  if constexpr (SysRho::DIM == 3 && RYDCZ_CLOSED_COHERENCE != 0 && RYDCZ_CLOSED_RHO01 != 0) {
+    double cf = 0.0;
+    done = rho01_closed_d3(x, pt, seg, n_seg, atom_b, cf);
+    if (done) flops += cf;
+  }
+  if (!done) {
+    double st = 0.0;
+    run_system<SysRho>(x, pt, seg, n_seg, true, st);
+    steps += st; flops += st * 2.0 * (SysRho::NNZ + SysRho::N);
+  }
+  RYDCZ_RECONVERGE(pt.live);
+}
 
 RYDCZ_HD double wrap_pi(double x) {
   // Python: (x + pi) % (2 pi) - pi, with % taking the sign of the divisor  (RG/simulation.py:608)
@@ -712,16 +734,14 @@ RYDCZ_HD void cz_epilogue(bool noisy, double p01, double p10, double p11,
     }                                                                                               \
     if (NOISY && ClosedCoh11s<D>::available) {                                                      \
       /* single-atom inputs: rho_ab on its Chebyshev loop, its |ab><00| coherence in closed form */   \
-      double x[Sys_rho01_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_rho01_d##D>(x, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);           \
-      steps += st; flops += st * 2.0 * (Sys_rho01_d##D::NNZ + Sys_rho01_d##D::N);                   \
+      double x[Sys_rho01_d##D::N];                                                                  \
+      single_atom_rho<Sys_rho01_d##D>(x, pt, seg, n_seg, true, steps, flops);                       \
       p01 = x[RHO01_POP_D##D];                                                                      \
       double xc[Sys_coh01_d##D::N];                                                                 \
       single_atom_coherence<Sys_coh01_d##D, true>(xc, pt, seg, n_seg, true, steps, flops);          \
       c01r = xc[COH01_RE_D##D]; c01i = xc[COH01_IM_D##D];                                           \
-      double y[Sys_rho10_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_rho10_d##D>(y, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);           \
-      steps += st; flops += st * 2.0 * (Sys_rho10_d##D::NNZ + Sys_rho10_d##D::N);                   \
+      double y[Sys_rho10_d##D::N];                                                                  \
+      single_atom_rho<Sys_rho10_d##D>(y, pt, seg, n_seg, false, steps, flops);                      \
       p10 = y[RHO10_POP_D##D];                                                                      \
       double yc[Sys_coh10_d##D::N];                                                                 \
       single_atom_coherence<Sys_coh10_d##D, true>(yc, pt, seg, n_seg, false, steps, flops);         \
@@ -809,9 +829,8 @@ RYDCZ_DEFINE_EVALUATE(4)
       }                                                                                             \
     }                                                                                               \
     if (NOISY && ClosedCoh11s<D>::available) {                                                      \
-      double x[Sys_rho01_d##D::N]; st = 0.0;                                                        \
-      run_system<Sys_rho01_d##D>(x, pt, seg, n_seg, true, st); RYDCZ_RECONVERGE(pt.live);           \
-      steps += st; flops += st * 2.0 * (Sys_rho01_d##D::NNZ + Sys_rho01_d##D::N);                   \
+      double x[Sys_rho01_d##D::N];                                                                  \
+      single_atom_rho<Sys_rho01_d##D>(x, pt, seg, n_seg, true, steps, flops);                       \
       p01 = x[RHO01_POP_D##D];                                                                      \
       double xc[Sys_coh01_d##D::N];                                                                 \
       single_atom_coherence<Sys_coh01_d##D, true>(xc, pt, seg, n_seg, true, steps, flops);          \

@@ -90,6 +90,16 @@ RYDCZ_HD double repeat_build_column(int c, const PointView pt, const double* __r
     }
     if (!done) { RYDCZ_UNROLL for (int i = 0; i < N; ++i) x[i] = i == c ? 1.0 : 0.0; }
   }
+  // ... and so has the single-atom density operator (optical Bloch equations): 5 more columns
+  if constexpr (RYDCZ_CLOSED_COHERENCE != 0 && RYDCZ_CLOSED_RHO01 != 0 && Sys::DIM == 3 && Sys::HERMITIAN && N == 5) {
+    if (noisy) {
+      ClosedRhoCache cache;
+      cache.om2 = -1.0; cache.det = 0.0; cache.h = 0.0; cache.ok = false;
+      done = rho01_closed_segment_d3(x, cache, row[SG_DT], row[SG_RE], 0.0, row[SG_DET] + pt[PT_OFF_A], pt[PT_DELTA1],
+                                     pt[PT_G_R1], pt[PT_G_R0], pt[PT_G_PHI], pt[PT_G_SC]);
+      if (!done) { RYDCZ_UNROLL for (int i = 0; i < N; ++i) x[i] = i == c ? 1.0 : 0.0; }
+    }
+  }
   if (!done) run_system<Sys>(x, pt, row, 1, noisy, st, false);
   RYDCZ_UNROLL
   for (int r = 0; r < N; ++r) E[(long long)(r * N + c) * stride] = x[r];

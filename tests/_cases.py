@@ -95,7 +95,7 @@ def load_hostsim():
     so = os.path.join(d, "libhostsim.so")
     srcs = [os.path.join(d, "hostsim.cpp")] + [
         os.path.join(HERE, "..", "noisyquantumsimulator_b200", "csrc", f)
-        for f in ("rydcz_core.cuh", "rydcz_cluster.cuh", "rydcz_repeat.cuh", "rydcz_prologue.cuh", "rydcz_systems_d3.inc", "rydcz_systems_d4.inc",
+        for f in ("rydcz_core.cuh", "rydcz_closed.cuh", "rydcz_cluster.cuh", "rydcz_repeat.cuh", "rydcz_prologue.cuh", "rydcz_systems_d3.inc", "rydcz_systems_d4.inc",
                   "rydcz_systems_d5.inc")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, srcs[0]])

@@ -203,7 +203,7 @@ extern "C" int hostsim_prologue(const double* model, long long n_points, const d
 
 // closed-form coherences (csrc/rydcz_closed.cuh) of one point, for tests/test_closed_coherence.py:
 // which = 0: exchange-folded |11><00| (6 doubles), 1: |01><00| (atom B driven), 2: |10><00| (4 doubles), 3: |11><00| of
-// unequal atoms (8 doubles).  Returns 1 when the closed form was accepted and finite.
+// unequal atoms (8 doubles), 4 / 5: the single-atom density operators rho_01 / rho_10 (5 doubles).  Returns 1 when the closed form was accepted and finite.
 extern "C" int hostsim_closed_coherence(int which, int noisy, const double* point, const double* segs, int n_seg,
                                         double* x) {
   using namespace rydcz;
@@ -221,6 +221,12 @@ extern "C" int hostsim_closed_coherence(int which, int noisy, const double* poin
     double v[8];
     const bool ok = noisy ? coh11_closed_d3<true>(v, pt, segs, n_seg, flops) : coh11_closed_d3<false>(v, pt, segs, n_seg, flops);
     for (int k = 0; k < 8; ++k) x[k] = v[k];
+    return ok ? 1 : 0;
+  }
+  if (which == 4 || which == 5) {      // single-atom rho_01 (atom B driven) / rho_10 (5 doubles); noisy rates always on
+    double v[5];
+    const bool ok = rho01_closed_d3(v, pt, segs, n_seg, which == 4, flops);
+    for (int k = 0; k < 5; ++k) x[k] = v[k];
     return ok ? 1 : 0;
   }
   double v[4];

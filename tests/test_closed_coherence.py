@@ -20,7 +20,7 @@ def hostsim():
 def _closed(hostsim, which, noisy, pt, segs):
     lib = hostsim.lib
     lib.hostsim_closed_coherence.argtypes = [Ct.c_int, Ct.c_int, DP, DP, Ct.c_int, DP]
-    x = np.zeros({0: 6, 3: 8}.get(which, 4))
+    x = np.zeros({0: 6, 3: 8, 4: 5, 5: 5}.get(which, 4))
     segs = np.ascontiguousarray(segs, dtype=np.float64)
     ok = lib.hostsim_closed_coherence(which, int(noisy), np.ascontiguousarray(pt).ctypes.data_as(DP),
                                       segs.ctypes.data_as(DP), len(segs), x.ctypes.data_as(DP))
@@ -96,6 +96,57 @@ def test_single_atom_coherence_against_40_digit_expm(hostsim, which):
         y = _exact(system, pt, segs, 1.0, "det_b" if which == 1 else "det_a")
         err = np.abs(x - y).max() / max(np.abs(y).max(), 1e-300)
         assert ok == 1 and err < 2e-13, (trial, err)
+
+
+@pytest.mark.parametrize("which", [4, 5])
+def test_single_atom_rho_against_40_digit_expm(hostsim, which):
+    """rho_01 / rho_10: the optical Bloch equations with decay as a real 4 x 4 closed form (fast pair by Newton, slow
+    pair from the deflated quadratic).  Accepted whenever drive or detuning dominate the rates -- every pulse segment
+    of the path -- and accurate wherever it is accepted; an idle segment at zero detuning is declined."""
+    rng = np.random.default_rng(40 + which)
+    system = M.standard_systems(3)["rho01" if which == 4 else "rho10"]
+    declined = 0
+    for trial in range(120):
+        pt, segs = _random_point(rng, trial)
+        pt[2], pt[3] = 2 * np.pi * rng.normal(0, 5e4, 2)
+        if trial % 7 == 0:
+            pt[5] = 0.0                                     # no decay to |0>: a root at exactly 0
+        if trial % 9 == 0:
+            segs[:, 0] *= 25.0                              # long segments: |h Omega| up to 200
+        ok, x = _closed(hostsim, which, True, pt, segs)
+        om_eff = np.sqrt(segs[0, 1] ** 2 + segs[0, 2] ** 2 + (segs[0, 3] + pt[2 if which == 5 else 3] + pt[1]) ** 2)
+        if not ok:
+            declined += 1
+            assert om_eff < 64 * (pt[4] + pt[5] + pt[6] + pt[7]), (trial, om_eff)
+            continue
+        y = _exact(system, pt, segs, 1.0, None)
+        tol = 2e-14 + 4e-16 * np.abs(segs[:, 0]).sum() * om_eff
+        err = np.abs(x - y).max()
+        assert err < tol, (trial, err, tol)
+        assert abs(x[0] + x[1] + x[4] - 1.0) < 1e-14
+    assert declined < 12
+
+
+def test_single_atom_rho_declines_what_it_cannot_separate(hostsim):
+    """Strong damping against a weak drive: the closed form either declines or is accurate -- never wrong."""
+    rng = np.random.default_rng(5)
+    system = M.standard_systems(3)["rho01"]
+    accepted = declined = 0
+    for trial in range(150):
+        Om = 10 ** rng.uniform(2, 8)
+        pt = np.zeros(12)
+        pt[4:8] = 10 ** rng.uniform(0, 6.5, 4)
+        det = Om * rng.uniform(-3, 3) * (trial % 3 != 0)
+        ph = rng.uniform(-np.pi, np.pi)
+        segs = np.array([[rng.uniform(0.05, 8) / max(Om, 1e5), Om * np.cos(ph), Om * np.sin(ph), det]])
+        ok, x = _closed(hostsim, 4, True, pt, segs)
+        if not ok:
+            declined += 1
+            continue
+        accepted += 1
+        y = _exact(system, pt, segs, 1.0, None)
+        assert np.abs(x - y).max() < 5e-14, (trial, np.abs(x - y).max())
+    assert accepted > 30 and declined > 30
 
 
 @pytest.mark.parametrize("noisy", [True, False])
