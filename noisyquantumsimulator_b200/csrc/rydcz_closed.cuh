@@ -1,4 +1,6 @@
-// rydcz_closed.cuh -- the |ab><00| coherences of the 3-level model in closed form.
+// rydcz_closed.cuh -- the |ab><00| coherences and the single-atom density operators of the 3-level model in closed form.
+// (The single-atom rho_01 / rho_10 -- optical Bloch equations, a real 4 x 4 -- have their own header comment further
+//  down; what follows is about the coherences.)
 //
 // The phase-carrying inputs X = |ab><00| (compute_CZ_fidelity's phases, RG/simulation.py:225-633; the whole state
 // when the run is noiseless) obey a CLOSED linear equation of their own: <00| is inert under H and under every

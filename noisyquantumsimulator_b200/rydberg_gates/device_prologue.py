@@ -24,7 +24,29 @@ LEAK_SHAPE_CODE = {"square": 0, "gaussian": 1, "cosine": 2, "blackman": 3, "drag
 SCALARS = ("Omega", "V", "tau_total", "tau_single", "Delta", "xi_re", "xi_im", "omega_tau")
 
 
-def model_constants(protocol: str, *, config: AtomicConfiguration = None, species="Rb87", n_rydberg=70,
+_MODEL_CACHE: Dict = {}
+
+
+def model_constants(protocol: str, **kwargs) -> np.ndarray:
+    """The 32 model constants of a batch (``_model_constants``), kept per distinct keyword set: an optimiser calls
+    with the same model thousands of times, and the atom-database lookups behind the constants took a third of the
+    Python time of a small generation.  (An ``AtomicConfiguration`` object, or any unhashable value, is not cached.)"""
+    try:
+        key = (protocol, tuple(sorted(kwargs.items())))
+        hit = _MODEL_CACHE.get(key)
+    except TypeError:
+        return _model_constants(protocol, **kwargs)
+    if hit is None:
+        if kwargs.get("config") is not None:
+            return _model_constants(protocol, **kwargs)
+        if len(_MODEL_CACHE) > 256:
+            _MODEL_CACHE.clear()
+        hit = _MODEL_CACHE[key] = _model_constants(protocol, **kwargs)
+        hit.setflags(write=False)
+    return hit
+
+
+def _model_constants(protocol: str, *, config: AtomicConfiguration = None, species="Rb87", n_rydberg=70,
                     qubit_0=(1, 0), qubit_1=(2, 0), hilbert_space_dim=3, include_noise=True,
                     include_motional_dephasing=True, include_doppler_dephasing=True,
                     include_intensity_noise=True, counter_propagating=True, trap_laser_on=True,
@@ -98,6 +120,8 @@ def apparatus_columns(protocol: str, B: int, *, laser_1_power, laser_1_waist, la
     def put(slot, v):
         if v is None:
             cols[slot] = np.nan
+        elif type(v) is float or type(v) is int:
+            cols[slot] = float(v)
         elif np.ndim(v) == 0:
             cols[slot] = float(v)
         else:
@@ -108,7 +132,9 @@ def apparatus_columns(protocol: str, B: int, *, laser_1_power, laser_1_waist, la
     for slot, v in enumerate((laser_1_power, laser_1_waist, laser_2_power, laser_2_waist, Delta_e,
                               laser_1_linewidth_hz, laser_2_linewidth_hz)):
         put(slot, v)
-    put(7, np.minimum(polarization_purity_1, polarization_purity_2))
+    put(7, min(polarization_purity_1, polarization_purity_2)
+        if type(polarization_purity_1) is float and type(polarization_purity_2) is float
+        else np.minimum(polarization_purity_1, polarization_purity_2))
     for slot, v in ((8, tweezer_power), (9, tweezer_waist), (10, tweezer_wavelength_nm), (11, temperature),
                     (12, B_field), (13, NA), (14, spacing_factor), (15, background_loss_rate_hz),
                     (16, intensity_noise_frac)):
