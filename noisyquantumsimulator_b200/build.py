@@ -36,16 +36,27 @@ def build(force: bool = False, verbose: bool = True) -> str:
     """Compile csrc/rydcz.cu -> csrc/librydcz.so.  Returns the library path."""
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + SOURCES
-    if verbose:
-        print("[rydcz build]", " ".join(cmd), flush=True)
-    res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    log = res.stdout + res.stderr
-    with open(os.path.join(CSRC, "build.log"), "w") as f:
-        f.write(log)
-    if res.returncode != 0:
-        sys.stderr.write(log)
-        raise RuntimeError("nvcc failed building librydcz.so")
+    # one builder at a time (pytest-xdist workers, ranks of one node), and the library appears atomically: a process
+    # that loads it while another one builds never sees a half-written file
+    import fcntl
+    with open(os.path.join(CSRC, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not is_stale():
+            return LIB
+        tmp = LIB + f".tmp{os.getpid()}"
+        cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", tmp] + SOURCES
+        if verbose:
+            print("[rydcz build]", " ".join(cmd), flush=True)
+        res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
+        log = res.stdout + res.stderr
+        with open(os.path.join(CSRC, "build.log"), "w") as f:
+            f.write(log)
+        if res.returncode != 0:
+            if os.path.exists(tmp):
+                os.remove(tmp)
+            sys.stderr.write(log)
+            raise RuntimeError("nvcc failed building librydcz.so")
+        os.replace(tmp, LIB)
     return LIB
 
 

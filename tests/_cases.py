@@ -97,8 +97,17 @@ def load_hostsim():
         os.path.join(HERE, "..", "noisyquantumsimulator_b200", "csrc", f)
         for f in ("rydcz_core.cuh", "rydcz_closed.cuh", "rydcz_cluster.cuh", "rydcz_repeat.cuh", "rydcz_prologue.cuh", "rydcz_systems_d3.inc", "rydcz_systems_d4.inc",
                   "rydcz_systems_d5.inc")]
-    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, srcs[0]])
+    def stale():
+        return not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+
+    if stale():
+        import fcntl
+        with open(os.path.join(d, ".build.lock"), "w") as lock:      # xdist workers: one builds, the others wait
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            if stale():
+                tmp = so + f".tmp{os.getpid()}"
+                subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", tmp, srcs[0]])
+                os.replace(tmp, so)
     lib = ctypes.CDLL(so)
     dp = ctypes.POINTER(ctypes.c_double)
     lib.hostsim_evaluate.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_longlong, dp, dp,
