@@ -500,7 +500,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- end to end through the public API: NumPy candidate arrays in host memory -> simulate_CZ_gate_batch
     # (apparatus slots as columns -> rydcz_simulate_host_select: per chunk, pack the varying slots into pinned
     # staging, H2D, prologue + planner + evaluate kernels, gather of the requested columns, D2H; chunks pipelined on
-    # three streams) -> the metric columns the reference's optimiser reads (extract_metrics), in host memory
+    # eight streams) -> the metric columns the reference's optimiser reads (extract_metrics), in host memory
     # The step's inputs sit in page-locked host memory (contract: "host->device copy of that step's inputs from pinned
     # host memory"): the candidate arrays as the optimiser would hold them, row-major [B], [B, 4], [B, 5].
     cand_host = {k: ev.pinned_copy("bench_" + k, v) for k, v in cand.items()}
@@ -625,7 +625,7 @@ def run_ours(args, rank, world, local_rank):
                     "api": "rydberg_gates.simulate_CZ_gate_batch(outputs=METRIC_OUTPUTS) -> rydcz_simulate_host_select "
                            "(C ABI): the candidates' row-major arrays in page-locked host memory -> H2D per 32768-point chunk "
                            "(transposed into apparatus slots on the device), the optimiser's 11 metric columns out into "
-                           "page-locked memory, chunks pipelined on 3 streams"},
+                           "page-locked memory, chunks pipelined on 8 streams"},
             "gpu_launches": launches,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": dfma_peak, "unit": "TFLOP/s",
                          "frac": achieved / dfma_peak,

@@ -210,7 +210,7 @@ int rydcz_simulate_host(rydcz_ctx* ctx, const double* h_model, int64_t n_points,
  * constant h_const[k] (h_cols, col_stride, h_const: RYDCZ_APP_STRIDE entries; col_stride NULL = all
  * 1; strides in doubles, so a column of a row-major [n][m] array is {ptr + k, m}).  Only varying
  * slots cross PCIe.  The batch is cut into chunks (rydcz_set_chunk, default 32768 evaluations) and
- * each chunk's packing, H2D copy, kernels and D2H copy run on one of three streams, so copies and
+ * each chunk's packing, H2D copy, kernels and D2H copy run on one of eight streams, so copies and
  * host work overlap the kernels of the neighbouring chunks.  Results are identical to the
  * unchunked call (Monte-Carlo shots are keyed by the point's index in the whole batch).  h_out /
  * h_scalars / h_states should be page-locked for the D2H copies to overlap. */

@@ -1133,6 +1133,12 @@ class PackPool {
   bool stop_ = false;
 };
 
+#ifndef RYDCZ_LANES
+#define RYDCZ_LANES 8      // streams the chunks of a pipelined host call rotate over.  A chunk's H2D copy waits for the D2H copy
+                           // of the chunk that used its stream before: with 3 streams (rounds 1-2) that wait was visible -- 262,144
+                           // bang-bang candidates end to end: 3 -> 115.5, 4 -> 118.3, 6 -> 120.4, 8 -> 122.2, 12 -> 122.1 M evaluations/s
+                           // (profiles/r02_e2e_lanes_sweep.txt; A/B builds: -DRYDCZ_LANES=n)
+#endif
 struct rydcz_ctx {
   int device = 0;
   int sm_count = 148;
@@ -1205,7 +1211,7 @@ struct rydcz_ctx {
     double* ring = nullptr; size_t ring_cap = 0;  // page-locked staging for the packed columns
     double* d_ring = nullptr;                     // its device twin (scattered to the slot rows by fill_slots_kernel)
   };
-  static constexpr int kLanes = 3;
+  static constexpr int kLanes = RYDCZ_LANES;
   Lane lane[kLanes];
   int pack_threads = 1;                           // host threads that gather the columns (rydcz_set_pack_threads)
   PackPool* pool = nullptr;
@@ -1398,7 +1404,7 @@ static int make_order(rydcz_ctx* ctx, const SortScratch& sc, int64_t n, const do
                       cudaStream_t st, const uint32_t** order, int seg_div = 1) {
   *order = nullptr;
   const int mode = (sc.cl && D != 5 && !shots && n * (int64_t)CL_RECORDS < 0x7fffffffLL) ? ctx->cluster_mode : 0;
-  // The table is shared by every work order of the context (the chunks of a pipelined call run on three streams):
+  // The table is shared by every work order of the context (the chunks of a pipelined call run on several streams):
   // every order generates the entries IT requested unless they already carry the generation mark (cluster_table_kernel).
   const bool use_table = mode && ctx->table_mode && ctx->tb_dir;
   const ClusterTable table{use_table ? ctx->tb_dir : nullptr, use_table ? ctx->tb_stamp : nullptr, ctx->tb_epoch};

@@ -227,7 +227,7 @@ class Evaluator:
         """Column form of ``simulate_host`` (rydcz_simulate_host_cols): ``cols`` is the list of 40
         apparatus slots from ``device_prologue.apparatus_columns`` -- floats for batch-wide constants,
         1-D float64 arrays (any stride) for slots that vary.  Only the varying slots are copied to
-        the GPU, and the batch is pipelined in chunks over three streams.  Results land in
+        the GPU, and the batch is pipelined in chunks over eight streams.  Results land in
         page-locked buffers owned by the evaluator (valid until the next call)."""
         model, m_ptr = _host(model, np.float64)
         assert model.shape == (_lib.MODEL_STRIDE,) and len(cols) == _lib.APP_STRIDE

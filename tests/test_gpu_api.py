@@ -154,7 +154,7 @@ def test_population_objective_and_sharded_evaluation_on_gpu():
 
 
 def test_pipelined_column_entry_equals_block_entry():
-    """rydcz_simulate_host_cols (varying slots only over PCIe, chunks pipelined on three streams)
+    """rydcz_simulate_host_cols (varying slots only over PCIe, chunks pipelined on eight streams)
     against rydcz_simulate_host (whole [40, B] block, one stream): bit-identical rows, whatever the
     chunk size, with strided columns, with and without Monte-Carlo shots."""
     from noisyquantumsimulator_b200.engine import Evaluator

@@ -101,7 +101,7 @@ def test_unequal_atoms_and_mixed_kinds_on_the_table(ev):
 
 
 def test_pipelined_chunks_share_the_table_across_streams(ev):
-    """rydcz_simulate_host_cols cuts a batch into chunks on three streams; a chunk may rely on an entry that another
+    """rydcz_simulate_host_cols cuts a batch into chunks on eight streams; a chunk may rely on an entry that another
     chunk's planner claimed.  Same results as one chunk, and as the table switched off."""
     from noisyquantumsimulator_b200 import rydberg_gates as rg
     from noisyquantumsimulator_b200.engine import get_evaluator

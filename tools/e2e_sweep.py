@@ -16,7 +16,7 @@ from noisyquantumsimulator_b200.rydberg_gates.simulation import METRIC_OUTPUTS  
 ev = get_evaluator(0)
 # like bench.py's e2e leg: candidates in page-locked memory, the optimiser's metric columns back
 cand = {k: ev.pinned_copy("c_" + k, v) for k, v in bench.make_candidates(B, 1234).items()}
-for chunk in (131072, 65536, 49152, 32768, 24576, 16384):
+for chunk in (65536, 32768, 24576, 20480, 16384, 12288):
     ev.set_chunk(chunk)
     for _ in range(2):
         rg.simulate_CZ_gate_batch("jp", B=B, prologue="device", copy=False, outputs=METRIC_OUTPUTS, **bench.MEDIUM, **cand)
