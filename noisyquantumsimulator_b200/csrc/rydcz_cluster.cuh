@@ -779,7 +779,14 @@ RYDCZ_HD void run_system_cluster(double (&x)[Sys::N], const XC xc, const XC rc, 
 // the noiseless ket): the caller then leaves the point to the plain kernel.
 // slots of the record ring: 8 for the 3-level model; 4 for the 4-level one, whose 63 start-vector columns
 // leave less shared memory at two CTAs per SM
-template <int D> struct ClusterRing { static constexpr int value = D == 3 ? 8 : 4; };
+#ifndef RYDCZ_CL_RING3
+#define RYDCZ_CL_RING3 8
+#endif
+template <int D> struct ClusterRing { static constexpr int value = D == 3 ? RYDCZ_CL_RING3 : 4; };
+// (the ring runs across (sub)step boundaries: a (sub)step's length must be a multiple of the ring size, or record k of
+//  the next (sub)step would not land in slot k % RING -- measured the hard way with CL_ALIGN = 4 and a ring of 8: every
+//  point failed its invariant check and was handed back to the plain kernel)
+static_assert(CL_ALIGN % RYDCZ_CL_RING3 == 0 && CL_ALIGN % 4 == 0, "CL_ALIGN must be a multiple of the record ring sizes");
 // (rho_11 and the coherence advanced in ONE loop -- records read once, transitions shared, two independent
 // chains -- was measured on B200 in round 1: slower, 2.44 ms against 2.22 ms per 262,144 bang-bang candidates,
 // 255 registers with 45 doubles spilled; gpurun_out/cluster_ab_r01p.log.  The code was removed in round 2.)
