@@ -40,7 +40,13 @@ static_assert(PT_STRIDE == RYDCZ_POINT_STRIDE, "layout");
 static_assert(SG_STRIDE == RYDCZ_SEG_STRIDE, "layout");
 static_assert(OUT_STRIDE == RYDCZ_OUT_STRIDE, "layout");
 
-constexpr int kBlock = 128;
+#ifndef RYDCZ_BLOCK
+#define RYDCZ_BLOCK 128
+#endif
+// threads per CTA of the evaluate kernels (one point per thread).  64-thread CTAs were measured (A/B builds, -DRYDCZ_BLOCK=64,
+// and a build that picks 64 for the clustered kernels below one CTA per SM): 262,144 candidates 1.6 % slower, an 8192-candidate
+// generation 0-4 % faster (LP 0.0835 -> 0.0833 ms, bang-bang 0.2145 -> 0.2062 ms) -- not worth six more instantiations.
+constexpr int kBlock = RYDCZ_BLOCK;
 
 // ---------------------------------------------------------------- Philox4x32-10
 struct Philox {
