@@ -112,6 +112,33 @@ def test_random_batch_against_oracle(evaluator, protocol, noisy):
         assert abs(out[i, C.OUT["czf"]] - info["cz_phase_fidelity"]) < 1e-9
 
 
+def test_single_atom_rho_closed_form_and_its_fallback_in_one_warp(evaluator):
+    """rho_01 / rho_10 come from the closed form (csrc/rydcz_closed.cuh) where it is accepted and from the Chebyshev
+    loop where it declines (damping comparable to the drive; an idle segment on resonance).  Both kinds sit in the
+    same warp here, identical and unequal atoms, and every state is compared with the expm oracle."""
+    rng = np.random.default_rng(99)
+    pts, segs = _random_points(rng, 16, "bb")
+    for i, (V, d1, r) in enumerate(pts):
+        if i % 2:                                    # dephasing of the order of the Rabi frequency: declined
+            r.gamma_phi_laser = 0.4 * abs(segs[i][0].Omega)
+    P, G, ns = _pack(pts, segs)
+    P[8:, 2] = 2 * np.pi * rng.normal(0, 5e4, 8)      # unequal atoms: the general kernels, rho_01 != rho_10
+    P[8:, 3] = 2 * np.pi * rng.normal(0, 5e4, 8)
+    G[3, 1, 1:] = 0.0                                # an idle segment (Omega = 0) ...
+    P[3, 1] = 0.0                                    # ... on resonance: declined as well
+    out, st = evaluator.evaluate_host(3, True, P, G, ns, want_states=True)
+    steps = out[:, C.OUT["steps"]]
+    assert steps[1::2].min() > 1.5 * steps[0:8:2].max()      # the declined points ran the single-atom loop
+    for i, ((V, d1, r), sg) in enumerate(zip(pts, segs)):
+        sg = [orc.Segment(s.dt, complex(G[i, k, 1], G[i, k, 2]), s.Delta) for k, s in enumerate(sg)]
+        fid, avg, info, fin = orc.evaluate(3, sg, V, P[i, 1], r, "exact", "coherence",
+                                           detuning_offsets=(P[i, 2], P[i, 3]))
+        ops = C.states_to_operators(3, st[i])
+        for lab in ("01", "10", "11"):
+            assert np.abs(ops["rho" + lab] - fin[lab]).max() < 1e-10, (i, lab)
+        assert abs(out[i, C.OUT["avg"]] - avg) < 1e-9
+
+
 def test_empty_and_single_point_batches(evaluator):
     out, st = evaluator.evaluate_host(3, True, np.zeros((0, 12)), np.zeros((0, 2, 4)),
                                       np.zeros(0, dtype=np.int32), want_states=True)
