@@ -86,13 +86,14 @@ def states_to_operators(dim, row):
     return out
 
 
-def load_hostsim():
-    """Build (if needed) and load the host harness of csrc/rydcz_core.cuh."""
+def load_hostsim(variant: str = "", defines=()):
+    """Build (if needed) and load the host harness of csrc/rydcz_core.cuh.  ``variant`` / ``defines``: an A/B build
+    of the same sources under another name, e.g. ("chebrho", ["-DRYDCZ_CLOSED_RHO01=0"])."""
     import ctypes
     import subprocess
 
     d = os.path.join(HERE, "hostsim")
-    so = os.path.join(d, "libhostsim.so")
+    so = os.path.join(d, f"libhostsim{'_' + variant if variant else ''}.so")
     srcs = [os.path.join(d, "hostsim.cpp")] + [
         os.path.join(HERE, "..", "noisyquantumsimulator_b200", "csrc", f)
         for f in ("rydcz_core.cuh", "rydcz_closed.cuh", "rydcz_cluster.cuh", "rydcz_repeat.cuh", "rydcz_prologue.cuh", "rydcz_systems_d3.inc", "rydcz_systems_d4.inc",
@@ -106,7 +107,7 @@ def load_hostsim():
             fcntl.flock(lock, fcntl.LOCK_EX)
             if stale():
                 tmp = so + f".tmp{os.getpid()}"
-                subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", tmp, srcs[0]])
+                subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", *defines, "-o", tmp, srcs[0]])
                 os.replace(tmp, so)
     lib = ctypes.CDLL(so)
     dp = ctypes.POINTER(ctypes.c_double)

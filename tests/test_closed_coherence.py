@@ -181,6 +181,41 @@ def test_unequal_atoms_11_coherence_against_40_digit_expm(hostsim, noisy):
     assert 0 < declined < 80
 
 
+def test_closed_single_atom_rho_against_the_chebyshev_build_of_the_same_evaluator(hostsim):
+    """Path against path: the whole evaluation (all paths, identical and unequal atoms, LP / bang-bang) with the
+    closed-form rho_01 / rho_10 equals the build that keeps them on the Chebyshev loop (-DRYDCZ_CLOSED_RHO01=0),
+    states and result columns, and it counts fewer Chebyshev steps."""
+    cheb = C.load_hostsim("chebrho", ["-DRYDCZ_CLOSED_RHO01=0"])
+    rng = np.random.default_rng(321)
+    B, S = 96, 5
+    P = np.zeros((B, 12))
+    G = np.zeros((B, S, 4))
+    ns = np.full(B, S, dtype=np.int32)
+    for i in range(B):
+        Om = 2 * np.pi * rng.uniform(1.5e6, 9e6)
+        P[i, 0] = Om * 10 ** rng.uniform(0.8, 2.6)
+        P[i, 1] = 2 * np.pi * rng.uniform(0, 3e5)
+        if i % 3 == 0:
+            P[i, 2:4] = 2 * np.pi * rng.normal(0, 6e4, 2)         # unequal atoms
+        P[i, 4:8] = [rng.uniform(2e3, 5e3), rng.uniform(2e3, 6e3), rng.uniform(1e2, 1e5), rng.uniform(1e3, 2e4)]
+        if i % 2:                                                  # bang-bang: five phases, Delta = 0
+            ot = rng.uniform(5, 40)
+            t = np.concatenate([[0.0], np.sort(rng.uniform(0.01, 0.99, 4)) * ot, [ot]]) / Om
+            ph = rng.uniform(-np.pi, np.pi, 5)
+            G[i] = np.stack([np.diff(t), Om * np.cos(ph), Om * np.sin(ph), np.zeros(5)], 1)
+        else:                                                      # LP: two pulses with a phase jump, Delta != 0
+            tau, det, xi = rng.uniform(3.5, 5.5) / Om, rng.uniform(0.2, 0.5) * Om, rng.uniform(-np.pi, np.pi)
+            G[i, 0] = [tau, Om, 0.0, det]
+            G[i, 1] = [tau, Om * np.cos(xi), Om * np.sin(xi), det]
+            ns[i] = 2
+    for cluster in (0, 1):
+        a, sa = hostsim(3, True, P, G, ns, cluster=cluster)
+        b, sb = cheb(3, True, P, G, ns, cluster=cluster)
+        assert np.abs(sa - sb).max() < 2e-12
+        assert np.abs(a[:, :14] - b[:, :14]).max() < 2e-12
+        assert np.all(a[:, C.OUT["steps"]] < b[:, C.OUT["steps"]])
+
+
 def test_noiseless_identical_atoms_need_no_chebyshev_step(hostsim):
     """Every system of a noiseless identical-atom evaluation is a coherence: the fixture is reproduced with zero
     Chebyshev steps, states included."""
