@@ -608,9 +608,10 @@ def run_ours(args, rank, world, local_rank):
             "warmup": max(args.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "jp_bangbang_5seg_lindblad_3level", "candidates_per_gpu": B_PER_GPU,
-                       "propagation": ("rho_11: clustered-spectrum Chebyshev (csrc/rydcz_cluster.cuh); single-atom rho: "
-                                       "single-interval Chebyshev; |ab><00| coherences: closed form (csrc/rydcz_closed.cuh)"
-                                       if clustered else "single-interval Chebyshev; coherences in closed form"),
+                       "propagation": ("rho_11: clustered-spectrum Chebyshev (csrc/rydcz_cluster.cuh); single-atom rho "
+                                       "and the |ab><00| coherences: closed forms (csrc/rydcz_closed.cuh)"
+                                       if clustered else "rho_11: single-interval Chebyshev; single-atom rho and "
+                                                         "coherences in closed form"),
                        "coefficient_table": {0: "off", 1: "entries generated again in every step",
                                              2: "entries kept across steps (library default): generated during warm-up, "
                                                 "as an optimiser's generations find them"}[args.table],
