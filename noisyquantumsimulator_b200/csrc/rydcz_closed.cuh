@@ -381,7 +381,7 @@ RYDCZ_HD bool coh11_closed_d3(double (&x)[8], const PointView pt, const double* 
 // pair (divided differences by Leibniz' rule: nothing is divided by the small gap of the slow pair).  Every term is
 // O(|v|): q(M) removes the fast components, so nothing of size (h Omega)^k has to cancel.  Declines (false: the caller
 // runs the Chebyshev loop) when Newton did not converge or the pairs are not separated (|q(slow)| < a2 / 256: drive
-// and detuning both ~ 0, or damping ~ drive).  Against 40-digit expm, |Om| 1e2..1e8, rates up to 3e6: <= 1e-14 + 2e-16 |h Om_eff|.
+// and detuning both ~ 0, or damping ~ drive).  Against 40-digit expm, |Om| 1e2..1e8, rates up to 3e6: <= 2e-14 + 4e-16 |h Om_eff| (tests/test_closed_coherence.py).
 struct ClosedRhoCache {
   double om2, det, h;          // |Omega|^2, Delta (+ offset) and duration the entries below belong to (om2 < 0: none)
   double b, c;                 // q(mu) = mu^2 + b mu + c
