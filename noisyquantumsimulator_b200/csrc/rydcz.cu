@@ -2237,7 +2237,8 @@ static int simulate_cols_impl(rydcz_ctx* ctx, const double* h_model, int64_t n_p
   // 4.83 ms against 4.56 ms per call -- the small pieces add more launches than they save in fill time.  Tried once
   // more with the closed-form kernels (first chunk cut in 1/4 + 3/4, last one in 3/4 + 1/4): 2.41-2.48 ms against
   // 2.28-2.30 ms per call at 32,768, worse at every chunk size (profiles/r02_e2e_chunk_sweep_taper.txt): a quarter
-  // chunk is 64 CTAs whose kernels take a third of a full chunk's time.  Uniform chunks stay.
+  // chunk is 64 CTAs whose kernels take a third of a full chunk's time.  The first chunk alone cut at 1/2, 1/4 or 1/8,
+  // with eight streams: 2.16-2.21 against 2.12-2.14 ms.  Uniform chunks stay.
   const int64_t per_item = n_shots > 0 ? n_shots : 1;
   // (the 5-level kernel runs ~25 ms per 65,536 points: there a chunk must be several waves of resident threads,
   //  32,768-point chunks cost it 19 %)
