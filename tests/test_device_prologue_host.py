@@ -99,3 +99,21 @@ def test_shaped_pulses_through_the_batch_api(monkeypatch):
         assert np.array_equal(c.avg_fidelity, a.avg_fidelity)
     with pytest.raises(TypeError):           # 'drag' lacks its Delta_leak argument in the reference as well
         rg.simulate_CZ_gate_batch("lp", B=B, pulse_shape="drag", **base)
+
+
+def test_model_constants_are_memoised_per_keyword_set():
+    """An optimiser calls with the same model thousands of times: the constants come from a cache, read-only, and a
+    different keyword set (or an explicit AtomicConfiguration) is never answered from another set's entry."""
+    from noisyquantumsimulator_b200.rydberg_gates.configurations import AtomicConfiguration
+    a = dp.model_constants("jp", n_segments=5, species="Rb87", n_rydberg=70, include_noise=True)
+    b = dp.model_constants("jp", n_segments=5, species="Rb87", n_rydberg=70, include_noise=True)
+    assert a is b and not a.flags.writeable
+    assert np.array_equal(a, dp._model_constants("jp", n_segments=5, species="Rb87", n_rydberg=70, include_noise=True))
+    c = dp.model_constants("jp", n_segments=5, species="Cs133", n_rydberg=70, include_noise=True)
+    d = dp.model_constants("jp", n_segments=7, species="Rb87", n_rydberg=70, include_noise=True)
+    e = dp.model_constants("lp", species="Rb87", n_rydberg=70, include_noise=True)
+    assert not np.array_equal(a, c) and d[2] == 7 and a[2] == 5 and e[1] == 0 and a[1] == 1
+    cfg = AtomicConfiguration(species="Rb87", qubit_0=(1, 0), qubit_1=(2, 0), n_rydberg=60, L_rydberg="S")
+    f = dp.model_constants("jp", n_segments=5, config=cfg)
+    g = dp.model_constants("jp", n_segments=5, config=cfg)
+    assert f is not g and np.array_equal(f, g) and f.flags.writeable and not np.array_equal(f, a)
